@@ -1,0 +1,132 @@
+"""CPU suite: pins the oracle (oracle/vmenv_oracle.c) against the reference.
+
+ * per-step fixtures recorded from the unmodified reference classes (tests/golden/make_golden.py);
+ * the reference's own published result rows (data/exp_performance_small/summary.csv:3-4,
+   data/exp_performance/summary.csv:3-4; per-seed values from SURVEY §8c KAT-1..4);
+ * numpy's reduction / sort orders the reference silently depends on.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+import vmoracle as vo
+
+
+def _make_oracle(cfg, trace_steps, trace_adm):
+    return vo.OracleVmEnv(vo.OracleConfig(**cfg), trace_steps=trace_steps, trace_adm=trace_adm)
+
+
+@pytest.mark.parametrize("name", gu.fixture_names())
+def test_oracle_replays_reference_fixture(name):
+    gu.replay(gu.load(name), _make_oracle)
+
+
+@pytest.mark.parametrize("name", [n for n in gu.fixture_names() if "firstfit" in n or "bestfit" in n])
+def test_oracle_agents_reproduce_reference_actions(name):
+    """firstfit.py:21-38 / bestfit.py:21-40: same float32 observation -> same action vector, every step."""
+    fx = gu.load(name)
+    cfg = fx["cfg"]
+    P, V = cfg["pms"], cfg["vms"]
+    tie = vo.TIE_NUMPY_INTROSORT if str(fx["tiebreak"]) == "numpy_introsort" else vo.TIE_STABLE
+    T = fx["action"].shape[0]
+    for t in range(T):
+        obs = np.concatenate([fx["placement"][t].astype(np.float64), fx["vm_cpu_code"][t] / 100.0,
+                              fx["vm_mem_code"][t] / 100.0, fx["cpu"][t], fx["memory"][t]]).astype(np.float32)
+        a = vo.firstfit_act(P, V, obs) if str(fx["agent"]) == "firstfit" else vo.bestfit_act(P, V, obs, tie)
+        assert np.array_equal(a, fx["action"][t].astype(np.int64)), f"{name} step {t}"
+
+
+def test_np_sum_order():
+    """np.sum of float64 == 0 + pairwise(a) with 8 accumulators / 128-blocks (drives `ut`, `kl`, target means)."""
+    rng = np.random.default_rng(0)
+    for n in list(range(0, 40)) + [100, 127, 128, 129, 130, 136, 137, 200, 299, 300, 301, 1000, 3000]:
+        for _ in range(10):
+            a = rng.uniform(0, 1, n)
+            assert vo.np_sum(a) == float(np.sum(a)), n
+
+
+def test_introsort_matches_numpy_scalar():
+    """the oracle's aquicksort restatement == np.argsort with the SIMD sort kernels disabled."""
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+import vmoracle as vo
+rng = np.random.default_rng(5)
+bad = 0
+for n in (2, 10, 16, 17, 18, 33, 100, 128, 300, 1000):
+    for rep in range(60):
+        k = rng.integers(1, max(2, n // 3))
+        v = (rng.integers(0, k + 1, n) / 64.0).astype(np.float32)
+        if not np.array_equal(np.argsort(v), vo.argsort_introsort_f32(v)): bad += 1
+print(bad)
+""" % os.path.dirname(os.path.abspath(vo.__file__))
+    env = dict(os.environ, NPY_DISABLE_CPU_FEATURES="AVX512F AVX512CD AVX512_SKX AVX512_CLX AVX512_CNL AVX512_ICL "
+                                                    "AVX512_SPR AVX2 FMA3")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True)
+    assert out.stdout.strip().splitlines()[-1] == "0", out.stdout + out.stderr
+
+
+def test_trace_exhaustion_flag():
+    cfg = vo.OracleConfig(pms=3, vms=5, arrival_rate=2.0, service_length=3, training_steps=50, eval_steps=50)
+    env = vo.OracleVmEnv(cfg, trace_steps=10, trace_adm=4)
+    for _ in range(12):
+        env.step(env.state()["vm_placement"])
+    assert env.state()["trace_exhausted"] == 1
+
+
+# ---- known-answer rows published by the reference (100 000-step eval episodes, 5 seeds) ---------------------
+KATS = {
+    # arrival_rate = round(pms/0.55/service_length, 4) (exp_performance.py:26, exp_performance_small.py:23)
+    # name: (config base, arrival_rate, reward, agent, tiebreak, seeds, per-seed (return, served, place), csv row)
+    "KAT1_firstfit_s10": ("10", 0.0182, "ut", vo.AGENT_FIRSTFIT, vo.TIE_STABLE, [1, 2, 3, 4, 5],
+                          [(702661.695, 1260, 1275), (690616.030, 1248, 1261), (695187.965, 1250, 1262),
+                           (695977.240, 1260, 1272), (700256.885, 1272, 1283)],
+                          dict(ret=696939.963, drop=0.241, served=1258, cpu=0.697, var=0.051, mem=0.697, wait=0.539)),
+    "KAT2_firstfit_s100": ("100", 0.1818, "wr", vo.AGENT_FIRSTFIT, vo.TIE_STABLE, [0, 1, 2, 3, 4],
+                           [(-53615.794, 13360, 13494), (-53208.140, 13409, 13541), (-53318.037, 13411, 13542),
+                            (-52963.827, 13466, 13601), (-53735.479, 13324, 13459)],
+                           dict(ret=-53368.255, drop=0.203, served=13394, cpu=0.737, var=0.052, mem=0.736, wait=0.534)),
+    "KAT3_bestfit_s10": ("10", 0.0182, "ut", vo.AGENT_BESTFIT, vo.TIE_STABLE, [1, 2, 3, 4, 5],
+                         [(699859.415, None, None), (694840.720, None, None), (698802.250, None, None),
+                          (697559.640, None, None), (703166.045, None, None)],
+                         dict(ret=698845.614, drop=0.242, served=1260, cpu=0.699, var=0.053, mem=0.699, wait=0.537)),
+    "KAT4_bestfit_s100": ("100", 0.1818, "wr", vo.AGENT_BESTFIT, vo.TIE_NUMPY_INTROSORT, [0, 1, 2, 3, 4],
+                          [(-52064.658, 13794, 13935), (-51690.685, 13811, 13957), (-51570.904, 13892, 14029),
+                           (-51202.317, 13950, 14090), (-51729.035, 13863, 14001)],
+                          dict(ret=-51651.520, drop=0.182, served=13862, cpu=0.763, var=0.057, mem=0.762, wait=0.517)),
+}
+_BASE = {
+    "10": dict(pms=10, vms=30, service_length=1000, training_steps=10000, eval_steps=100000, cap_target_util=True,
+               sequence="uniform", beta=0.5, allow_null_action=True),          # config/10.yml:1-13
+    "100": dict(pms=100, vms=300, service_length=1000, training_steps=10000, eval_steps=100000, cap_target_util=True,
+                sequence="uniform", beta=0.5, allow_null_action=True),         # config/100.yml:1-13
+}
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("kat", sorted(KATS))
+def test_published_rows(kat):
+    base, lam, reward, agent, tie, seeds, per_seed, row = KATS[kat]
+    stats = []
+    for seed, want in zip(seeds, per_seed):
+        cfg = vo.OracleConfig(arrival_rate=lam, reward_function=reward, seed=seed, **_BASE[base])
+        env = vo.OracleVmEnv(cfg)           # full-length traces exactly like env.reset (2*max_steps sizes)
+        env.eval()
+        n, st = env.rollout(agent, 10**9, tie)
+        assert n == 100000
+        assert round(st["return"], 3) == pytest.approx(want[0], abs=2e-3), (kat, seed, st["return"])
+        if want[1] is not None:
+            assert (int(st["served"]), int(st["place"])) == want[1:], (kat, seed)
+        stats.append(st)
+    m = {k: float(np.mean([s[k] for s in stats])) for k in stats[0]}
+    assert "%.3f" % m["return"] == "%.3f" % row["ret"]
+    assert "%.3f" % m["drop_rate_mean"] == "%.3f" % row["drop"]
+    assert "%d" % m["served"] == "%d" % row["served"]
+    assert "%.3f" % m["cpu_mean"] == "%.3f" % row["cpu"]
+    assert "%.3f" % m["cpu_var"] == "%.3f" % row["var"]
+    assert "%.3f" % m["mem_mean"] == "%.3f" % row["mem"]
+    assert "%.3f" % m["waiting_ratio_mean"] == "%.3f" % row["wait"]
