@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/sec of the batched VM-placement hot path (BASELINE.json metric).
+
+Workload (N=1): BASELINE.json configs[1] — config/100.yml, best-fit evaluation, 100 PMs / 300 VM slots, uniform VM
+sizes, 4096 envs per GPU.  One "step" = agent.act + env.step for every env of the batch (one launch of the fused
+kernel, observation written to HBM every step as the gym API does).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--envs E]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line on rank 0 (see DESIGN.md §7 for every field).  `--impl reference` times the CPU oracle port of
+the reference path (the reference is pure Python and is not on the GPU box) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [os.path.join(ROOT, "vm-placement-migration-gym_b200"), os.path.join(ROOT, "oracle")]
+
+import numpy as np  # noqa: E402
+import yaml  # noqa: E402
+
+METRIC = "env-steps/sec (100 PMs, best-fit act+step, whole job)"
+UNIT = "env-steps/s"
+WARM_STEPS = 3000          # reach saturation (~300/300 slots occupied) before timing, SURVEY §8d
+
+
+def load_env_cfg():
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "configs", "100.yml")))["environment"]
+    cfg["reward_function"] = "wr"        # main.py:94 CLI default overrides the YAML (main.py:34)
+    return cfg
+
+
+def algorithmic_bytes(P, V):
+    """state record S = 16P + 5V + 48 read and written once, observation 4(3V+2P) written, plus
+    16 B of per-step scalars (reward, done, trace words)."""
+    S = 16 * P + 5 * V + 48
+    return 2 * S + 4 * (3 * V + 2 * P) + 16
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path, one env per process like the reference's drivers (exp.py:1)
+# --------------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, warm, steps = args
+    import vmoracle as vo
+    cfg = load_env_cfg()
+    cfg["seed"] = int(seed)
+    env = vo.OracleVmEnv(vo.OracleConfig(**cfg), trace_steps=warm + steps + 8, trace_adm=4 * (warm + steps) + 4096)
+    env.rollout(vo.AGENT_BESTFIT, warm)
+    t0 = time.perf_counter()
+    n, _ = env.rollout(vo.AGENT_BESTFIT, steps)
+    return n, time.perf_counter() - t0
+
+
+def cpu_arm(steps_per_env=2000, warm=WARM_STEPS, cores=None):
+    import vmoracle as vo
+    vo.build()
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(s, warm, steps_per_env) for s in range(cores)])
+    wall = time.perf_counter() - t0
+    total = sum(n for n, _ in res)
+    slowest = max(dt for _, dt in res)
+    return dict(value=total / slowest, unit=UNIT, cores=cores, kind="port",
+                sample=f"{cores} envs x {steps_per_env} best-fit act+step after {warm} warm-up steps, one env per "
+                       f"process (C oracle port of env.py/bestfit.py; the Python reference measured 62-68 steps/s/process, "
+                       f"BASELINE.md §3)", per_process=total / cores / slowest, wall_s=wall)
+
+
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.samples.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for n, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from vmgym import Config, VecVmEnv
+    from vmgym.agents import BestFitAgent
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = load_env_cfg()
+    E = args.envs
+    # envs shard contiguously: rank g owns global env ids [g*E, (g+1)*E); seeds derive from the global id
+    seeds = cfg["seed"] + rank * E + np.arange(E, dtype=np.int64)
+    vec = VecVmEnv(Config(**cfg), E, device=dev, rng="philox", seeds=seeds)
+    P, V, D = vec.P, vec.V, vec.obs_dim
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up: saturate the envs, then W untimed steps of exactly the timed call ----
+    vec.agent_step("bestfit", n_steps=WARM_STEPS, want_obs=False, want_action=False, want_valid=False)
+    for _ in range(max(3, args.warmup)):
+        vec.agent_step("bestfit", 1, want_obs=True, want_action=False, want_valid=False)
+    barrier()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+
+    # ---- timed region A (value): K fused steps, state + outputs resident in HBM, L2 flushed between steps ----
+    K = args.steps
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    barrier()
+    for k in range(K):
+        flush.fill_(k & 0xff)                      # evict state/obs from L2 (outside the event pair)
+        starts[k].record()
+        vec.agent_step("bestfit", 1, want_obs=True, want_action=False, want_valid=False)
+        ends[k].record()
+    barrier()
+    dev_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = float(sum(dev_ms))
+
+    # ---- timed region B (rollout): same work, 100 steps per launch with the state resident in shared memory ----
+    chunk, n_chunks = 100, 5
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(n_chunks):
+        vec.agent_step("bestfit", chunk, want_obs=True, want_action=False, want_valid=False)
+    r1.record()
+    barrier()
+    rollout_ms = r0.elapsed_time(r1)
+
+    # ---- timed region C (e2e): the reference-facing calls with HOST buffers, copies inside the timed region ----
+    agent = BestFitAgent(vec)
+    Ke = max(3, min(K, 20))
+    h_obs = torch.empty((E, D), dtype=torch.float32).pin_memory()
+    h_act = torch.empty((E, V), dtype=vec.place_dtype).pin_memory()
+    h_rew = torch.empty(E, dtype=torch.float64).pin_memory()
+    h_term = torch.empty(E, dtype=torch.uint8).pin_memory()
+    h_obs.copy_(vec.observe())
+    d_obs_in = torch.empty((E, D), dtype=torch.float32, device=dev)
+    d_act_in = torch.empty((E, V), dtype=vec.place_dtype, device=dev)
+
+    def e2e_step():
+        # action = agent.act(obs): host obs -> device, scan kernel, action -> host
+        d_obs_in.copy_(h_obs, non_blocking=True)
+        act = agent.act(d_obs_in)
+        h_act.copy_(act, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        # obs, reward, done = env.step(action): host action -> device, step kernel, results -> host
+        d_act_in.copy_(h_act, non_blocking=True)
+        obs, rew, term, _, _ = vec.step(d_act_in, want_valid=False)
+        h_obs.copy_(obs, non_blocking=True)
+        h_rew.copy_(rew, non_blocking=True)
+        h_term.copy_(vec.terminated, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.finish() if sampler else None
+
+    if world > 1:
+        t = torch.tensor([total_ms, rollout_ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, rollout_ms, e2e_s = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    B = algorithmic_bytes(P, V)
+    avg_launch_s = (sum(dev_ms) / K) * 1e-3
+    achieved = B * E / avg_launch_s / 1e9
+    value = world * E * K / (total_ms * 1e-3)
+    h2d = E * D * 4 + E * V * h_act.element_size()
+    d2h = E * V * h_act.element_size() + E * D * 4 + E * 8 + E
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 PM accumulators / u8 slot arrays / f32 observation", "data": "synthetic (Philox arrivals, uniform sizes)",
+        "config": {"workload": "config/100.yml best-fit evaluation: 100 PMs, 300 VM slots, uniform sizes, "
+                               f"{E} envs per GPU, reward wr, saturated after {WARM_STEPS} warm-up steps",
+                   "envs_per_gpu": E, "l2": "flushed between timed steps (256 MiB fill outside the event pairs)",
+                   "rng": "philox", "tiebreak": "stable", "obs_written": True},
+        "gpu_launches": K,
+        "e2e": {"value": world * E * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": Ke, "path": "BestFitAgent.act(host obs) + VecVmEnv.step(host action) with pinned host buffers"},
+        "rollout": {"value": world * E * chunk * n_chunks / (rollout_ms * 1e-3), "unit": UNIT,
+                    "steps_per_launch": chunk, "note": "same fused kernel, env state resident in shared memory across steps"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "vmgym::step_kernel<u8> (fused best-fit + step)",
+                     "bytes_per_env_step": B, "peak_source": peak_src},
+        "clocks": clocks,
+    }
+    if not args.no_cpu:
+        out["cpu_baseline"] = cpu_arm(steps_per_env=args.cpu_steps)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, W = max(1, args.steps), max(0, args.warmup)
+    per_step = max(100, args.cpu_steps // max(1, K))
+    vals = []
+    base = None
+    for k in range(W + K):
+        r = cpu_arm(steps_per_env=per_step)
+        if k >= W:
+            vals.append(r["value"])
+            base = r
+    value = float(np.mean(vals))
+    base["value"] = value
+    cfg = load_env_cfg()
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+           "steps": K, "warmup": W, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic (numpy PCG64 traces, uniform sizes)",
+           "config": {"workload": "config/100.yml best-fit evaluation: 100 PMs, 300 VM slots, uniform sizes, one env per "
+                                  f"host process x {base['cores']} processes, reward wr, saturated after {WARM_STEPS} warm-up steps",
+                      "arrival_rate": cfg["arrival_rate"]},
+           "cpu_baseline": base,
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--cpu-steps", type=int, default=2000, help="timed CPU steps per env in the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

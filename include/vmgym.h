@@ -1,0 +1,162 @@
+/*
+ * vmgym.h — C ABI of the B200-native batched VM placement/migration env (libvmgym.so).
+ *
+ * This is the drop-in boundary of the hot path: plain pointers and sizes, no torch types.  All pointers
+ * named `d_*` are DEVICE pointers; every call enqueues its kernels on the caller's `stream` (a
+ * cudaStream_t passed as void*), never synchronises, and is CUDA-graph capturable.  Return value: 0 on
+ * success, a negative VMGYM_E* code otherwise (nothing is thrown across the boundary;
+ * vmgym_last_error() gives the message of the calling thread's last failure).
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference root,
+ * yzh503/vm-placement-migration-gym).  The reference has no FFI of its own (it is pure Python), so the
+ * "binding a maintainer would add" is the ctypes stub shown in INTEGRATION.md.
+ */
+#ifndef VMGYM_H_
+#define VMGYM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VMGYM_ABI_VERSION 1
+
+enum vmgym_status {
+    VMGYM_OK = 0,
+    VMGYM_EINVAL = -1,      /* bad shape / null pointer / unsupported value */
+    VMGYM_ECUDA = -2,       /* a CUDA runtime call failed */
+    VMGYM_EARCH = -3,       /* device is not sm_100 */
+    VMGYM_EUNSUPPORTED = -4
+};
+
+/* vmenv/envs/env.py:125,151,153 and main.py:94 — "reward 1/2/3" of the paper */
+enum vmgym_reward { VMGYM_REWARD_WR = 1, VMGYM_REWARD_UT = 2, VMGYM_REWARD_KL = 3 };
+/* src/agents/{firstfit,bestfit}.py; src/agents/drlvmp.py:549-617 (worst-fit / min-dot / min-L2 choices) */
+enum vmgym_agent {
+    VMGYM_AGENT_NONE = 0, VMGYM_AGENT_FIRSTFIT = 1, VMGYM_AGENT_BESTFIT = 2, VMGYM_AGENT_WORSTFIT = 3,
+    VMGYM_AGENT_MINDOT = 4, VMGYM_AGENT_MINL2 = 5
+};
+/* best-fit tie rule (src/agents/bestfit.py:33 uses an unstable np.argsort; see DESIGN.md "tie-break") */
+enum vmgym_tiebreak { VMGYM_TIE_STABLE = 0, VMGYM_TIE_NUMPY_INTROSORT = 1 };
+/* element type of an action tensor */
+enum vmgym_dtype { VMGYM_U8 = 1, VMGYM_I16 = 2, VMGYM_I64 = 3 };
+enum vmgym_trace_mode { VMGYM_TRACE_PRESAMPLED = 0, VMGYM_TRACE_PHILOX = 1 };
+
+/* vmenv/envs/config.py:3-16 (the fields the device path needs) + the active step limit. */
+typedef struct vmgym_config {
+    int32_t pms;                /* P: physical machines */
+    int32_t vms;                /* V: VM slots */
+    int32_t allow_null_action;  /* action_dim A = P+2 if set else P+1 (env.py:26) */
+    int32_t reward_function;    /* enum vmgym_reward */
+    int32_t cap_target_util;    /* env.py:117-121 */
+    int32_t step_limit;         /* eval_steps in eval mode else training_steps (env.py:160-163) */
+    double beta;                /* `ut` mixing weight (env.py:152) */
+} vmgym_config;
+
+/* Byte layout of one env record in HBM (struct-of-arrays inside a record, records contiguous).
+ * Filled by vmgym_get_layout; the host mirror builds strided tensor views from it. */
+typedef struct vmgym_layout {
+    int32_t record_bytes;       /* multiple of 128 */
+    int32_t pms_padded, vms_padded;
+    int32_t place_bytes;        /* 1 (P <= 253) or 2 */
+    int32_t off_cpu;            /* f64[P]  PM cpu utilisation accumulators (env.py:190) */
+    int32_t off_memory;         /* f64[P]  PM memory utilisation accumulators (env.py:191) */
+    int32_t off_remaining;      /* u16[V]  vm_remaining_runtime (env.py:192) */
+    int32_t off_placement;      /* u8|u16[V] vm_placement: 0..P-1 running, P waiting, P+1 empty (env.py:187) */
+    int32_t off_cpu_code;       /* u8[V]   vm_cpu in hundredths, bit 7 = vm_suspended (env.py:188,204) */
+    int32_t off_mem_code;       /* u8[V]   vm_memory in hundredths (env.py:189) */
+    int32_t off_scalars;        /* struct vmgym_env_scalars */
+    int32_t obs_dim;            /* 3V + 2P (env.py:27,295-296) */
+    int32_t action_dim;         /* A */
+    int32_t smem_bytes_per_env; /* shared memory one resident env needs in the step kernels */
+} vmgym_layout;
+
+/* Per-env scalar block inside the record (env.py:193-208). */
+typedef struct vmgym_env_scalars {
+    int32_t timestep;           /* starts at 1 */
+    int32_t total_requests, served_requests, dropped_requests, suspend_actions, place_actions;
+    uint32_t arrival_pos;       /* arrivals consumed from the arrival stream (rng3, env.py:272) */
+    uint32_t admission_pos;     /* entries consumed from the size/service streams (rng1,2,4; env.py:279-289) */
+    uint32_t status;            /* bit 0: pre-sampled trace exhausted (the reference would raise at env.py:282) */
+    uint32_t episode;
+    uint64_t seed;              /* Philox key of this env */
+    int64_t cpu_code_sum;       /* 100 * total_cpu_requested (exact integer) */
+    int64_t mem_code_sum;       /* 100 * total_memory_requested */
+    double episode_return;      /* sum of rewards since reset */
+    double last_reward;
+} vmgym_env_scalars;
+
+/* Source of the env's randomness.  PRESAMPLED: arrays drawn by the host exactly like the reference draws
+ * them (numpy PCG64, env.py:172-178,211-219,272,289) so trajectories are bit-identical to the reference.
+ * PHILOX: counter-based generation inside the kernel (key = env seed). */
+typedef struct vmgym_trace {
+    int32_t mode;                    /* enum vmgym_trace_mode */
+    int32_t reserved;
+    const uint16_t* d_arrivals;      /* [n_envs, arrivals_len]  Poisson(arrival_rate) per step */
+    int64_t arrivals_len;
+    const uint32_t* d_admissions;    /* [n_envs, admissions_len] cpu_code | mem_code<<8 | (Poisson(service)+1)<<16 */
+    int64_t admissions_len;
+    /* Philox mode: inverse-CDF tables as 64-bit thresholds, P(X <= kmin+i) * 2^64 */
+    const uint64_t* d_arrival_cdf;  int32_t arrival_cdf_len;  int32_t arrival_kmin;
+    const uint64_t* d_service_cdf;  int32_t service_cdf_len;  int32_t service_kmin;
+    int32_t size_lo_code, size_hi_code;  /* 10..100 uniform, 10..65 lowuniform, 25..100 highuniform (env.py:211-219) */
+} vmgym_trace;
+
+/* Optional per-step outputs; any pointer may be NULL. */
+typedef struct vmgym_outputs {
+    float* d_obs;            /* [n_envs, 3V+2P] float32 observation after the step (env.py:295-296) */
+    double* d_reward;        /* [n_envs] (env.py:123-156) */
+    uint8_t* d_terminated;   /* [n_envs] (env.py:160-163) */
+    uint8_t* d_valid;        /* [n_envs, V] info["valid"] (env.py:69-74,91-94) */
+    void* d_action;          /* [n_envs, V] actions chosen by a fused agent, element type = placement type */
+    double* d_stats;         /* [n_envs, 8] running sums for the eval summary (src/record.py:98-134), see DESIGN.md */
+} vmgym_outputs;
+
+const char* vmgym_last_error(void);
+int vmgym_abi_version(void);
+
+/* Record layout for a config.  Replaces the attribute set created by VmEnv.reset (env.py:186-208). */
+int vmgym_get_layout(const vmgym_config* cfg, vmgym_layout* out);
+
+/* VmEnv.reset (env.py:180-226): zero the state of the selected envs (all when d_env_mask is NULL, else
+ * those with d_env_mask[i] != 0).  d_seeds (u64[n_envs], may be NULL) re-keys the env's streams and rewinds
+ * the stream cursors; with d_seeds == NULL the cursors continue (reset() without seed, drlvmp.py:450-452).
+ * d_obs (may be NULL) receives the reset observation. */
+int vmgym_reset(const vmgym_config* cfg, void* d_state, int64_t n_envs, const uint8_t* d_env_mask,
+                const uint64_t* d_seeds, int rewind_streams, float* d_obs, void* stream);
+
+/* VmEnv.step (env.py:66-103) for n_envs envs: apply action[n_envs, V] sequentially per env with fp64
+ * validity checks, service countdown and departures (_run_vms, :244-268), arrivals (_accept_vm_requests,
+ * :271-293), metrics + reward (_process_action, :108-170), observation, termination flag, timestep += 1.
+ * Out-of-range action values are invalid no-ops, as in validate() (:35-42). */
+int vmgym_step(const vmgym_config* cfg, void* d_state, int64_t n_envs, const vmgym_trace* trace,
+               const void* d_action, int action_dtype, const vmgym_outputs* out, void* stream);
+
+/* Fused agent.act(obs) + env.step(action) (the body of Base.test's loop, src/agents/base.py:71-86) for the
+ * heuristic agents, n_steps times per launch with the env state resident in shared memory.
+ * FirstFitAgent.act: firstfit.py:21-38; BestFitAgent.act: bestfit.py:21-40.  Stops early at termination. */
+int vmgym_agent_step(const vmgym_config* cfg, void* d_state, int64_t n_envs, const vmgym_trace* trace, int agent,
+                     int tiebreak, int n_steps, const vmgym_outputs* out, void* stream);
+
+/* agent.act(observation) on a batch of float32 observations (firstfit.py:21-38, bestfit.py:21-40,
+ * drlvmp.py:549-617 heuristics).  d_action element type given by action_dtype. */
+int vmgym_agent_act(const vmgym_config* cfg, int agent, int tiebreak, const float* d_obs, int64_t n_envs,
+                    void* d_action, int action_dtype, void* stream);
+
+/* VmEnv._get_obs (env.py:295-296). */
+int vmgym_observe(const vmgym_config* cfg, const void* d_state, int64_t n_envs, float* d_obs, void* stream);
+
+/* VmEnv.get_invalid_action_mask (env.py:45-53): d_mask[n_envs, V, A], 1 = invalid. */
+int vmgym_invalid_action_mask(const vmgym_config* cfg, const void* d_state, int64_t n_envs, uint8_t* d_mask,
+                              void* stream);
+
+/* Tuning knobs (process-wide): warps per CTA of the step kernels (0 = auto) and bulk-async record copies
+ * (cp.async.bulk) on/off.  For experiments; defaults are chosen per config. */
+int vmgym_set_tuning(int warps_per_cta, int use_bulk_copy);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMGYM_H_ */

@@ -1,0 +1,243 @@
+"""-m gpu: parity of the CUDA env path (through the C ABI, via the Python mirror) against the oracle and the
+golden fixtures recorded from the reference.
+
+Bar (BASELINE.json north_star): placements, validity flags, queue contents (slot arrays), remaining runtimes and
+episode counters bit-exact; fp64 PM accumulators bit-exact; float32 observations bit-exact; rewards within 1e-6
+relative (they are in fact bit-exact for wr/ut and ~1e-14 for kl, whose log() differs from glibc's by <= 1 ulp).
+"""
+import numpy as np
+import pytest
+
+import golden_util as gu
+import vmoracle as vo
+
+pytestmark = pytest.mark.gpu
+
+REWARD_RTOL = 1e-6   # the tolerance north_star states (fp64 on both sides; see module docstring)
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _cfg(**kw):
+    from vmgym import Config
+    return Config(**kw)
+
+
+def _make_cuda_env(cfg, trace_steps, trace_adm):
+    from vmgym import VmEnv
+    return VmEnv(_cfg(**cfg), trace_steps=trace_steps, max_admissions=trace_adm)
+
+
+@pytest.mark.parametrize("name", gu.fixture_names())
+def test_cuda_env_replays_reference_fixture(name):
+    fx = gu.load(name)
+    tie = "numpy_introsort" if str(fx["tiebreak"]) == "numpy_introsort" else "stable"
+    steps = 600 if fx["cfg"]["pms"] >= 100 else 1000
+    if fx["reset_at"].size:
+        steps = None          # episode fixtures: run through the resets
+    gu.replay(fx, _make_cuda_env, reward_rtol=REWARD_RTOL, max_steps=steps)
+    del tie
+
+
+def _oracle_batch(cfg_kw, seeds, steps, adm):
+    envs = []
+    for s in seeds:
+        kw = dict(cfg_kw, seed=int(s))
+        envs.append(vo.OracleVmEnv(vo.OracleConfig(**kw), trace_steps=steps, trace_adm=adm))
+    return envs
+
+
+def _compare_state(vec, oracles, t, check_reward=None):
+    cnt = vec.counters()
+    for i, o in enumerate(oracles):
+        s = vec.state_dict_host(i)
+        so = o.state()
+        for k in ("vm_placement", "vm_remaining_runtime", "vm_suspended"):
+            assert np.array_equal(s[k], so[k]), f"{k} env {i} step {t}"
+        assert np.array_equal(s["vm_cpu"], so["vm_cpu"]) and np.array_equal(s["vm_memory"], so["vm_memory"]), (i, t)
+        assert s["cpu"].tobytes() == so["cpu"].tobytes(), f"fp64 cpu env {i} step {t}"
+        assert s["memory"].tobytes() == so["memory"].tobytes(), f"fp64 memory env {i} step {t}"
+        for k in ("timestep", "total_requests", "served_requests", "dropped_requests", "suspend_action", "place_action",
+                  "arr_cursor", "adm_cursor", "trace_exhausted"):
+            assert s[k] == so[k], f"{k} env {i} step {t}: {s[k]} vs {so[k]}"
+    return cnt
+
+
+SHAPES = {
+    "s10": dict(pms=10, vms=30, arrival_rate=0.3, service_length=30, training_steps=400, eval_steps=100000,
+                reward_function="kl", allow_null_action=True),
+    "s100": dict(pms=100, vms=300, arrival_rate=1.8182, service_length=1000, training_steps=10000, eval_steps=100000,
+                 reward_function="wr", allow_null_action=True),
+    "odd": dict(pms=33, vms=65, arrival_rate=1.0, service_length=50, training_steps=10000, eval_steps=100000,
+                reward_function="ut", beta=0.3, allow_null_action=False, sequence="highuniform", cap_target_util=False),
+    "wide": dict(pms=300, vms=700, arrival_rate=4.0, service_length=120, training_steps=10000, eval_steps=100000,
+                 reward_function="kl", allow_null_action=True, sequence="lowuniform"),
+}
+
+
+@pytest.mark.parametrize("shape,n_envs,steps", [("s10", 37, 450), ("s100", 8, 300), ("odd", 16, 400), ("wide", 4, 250)])
+@pytest.mark.parametrize("bulk", [1, 0])
+def test_batched_step_matches_oracle_random_actions(shape, n_envs, steps, bulk):
+    """N envs with different seeds, adversarial random action streams (out-of-range values, suspend storms,
+    simultaneous placements on one PM, NULL-slot actions): every env equals its own oracle after every step."""
+    torch = _torch()
+    from vmgym import VecVmEnv
+    from vmgym import _native as nv
+    kw = SHAPES[shape]
+    nv.lib().vmgym_set_tuning(0, bulk)
+    try:
+        seeds = 100 + 7 * np.arange(n_envs)
+        vec = VecVmEnv(_cfg(**kw), n_envs, seeds=seeds, trace_steps=steps + 4, max_admissions=20000)
+        oracles = _oracle_batch(kw, seeds, steps + 4, 20000)
+        P, V, A = kw["pms"], kw["vms"], vec.action_dim
+        rng = np.random.default_rng(99)
+        obs = vec.obs.cpu().numpy()
+        for i, o in enumerate(oracles):
+            assert np.array_equal(obs[i], o._obs())
+        for t in range(steps):
+            place = np.stack([o.state()["vm_placement"] for o in oracles])
+            ff = np.stack([vo.firstfit_act(P, V, o._obs()) for o in oracles])
+            u = rng.random((n_envs, V))
+            act = np.where(u < 0.5, ff, place)
+            act = np.where(u > 0.93, rng.integers(0, A + 2, size=(n_envs, V)), act)
+            act = np.where((u > 0.88) & (u <= 0.93), P, act)
+            dtype = [torch.int64, torch.int16, torch.uint8][t % 3] if P <= 253 else [torch.int64, torch.int16][t % 2]
+            obs_d, rew_d, term_d, _, info = vec.step(torch.from_numpy(act).to(vec.device).to(dtype))
+            obs_h, rew_h, term_h, valid_h = obs_d.cpu().numpy(), rew_d.cpu().numpy(), term_d.cpu().numpy(), info["valid"].cpu().numpy()
+            for i, o in enumerate(oracles):
+                a = act[i].astype(np.int64)
+                if dtype == torch.uint8:
+                    a = a.astype(np.uint8).astype(np.int64)
+                o_obs, o_r, o_term, _, o_info = o.step(a)
+                assert np.array_equal(valid_h[i], o_info["valid"].astype(np.uint8)), (i, t)
+                assert obs_h[i].tobytes() == o_obs.tobytes(), (i, t)
+                assert rew_h[i] == pytest.approx(o_r, rel=REWARD_RTOL, abs=1e-300), (i, t)
+                assert bool(term_h[i]) == o_term
+            if t % 25 == 0 or t == steps - 1:
+                _compare_state(vec, oracles, t)
+    finally:
+        nv.lib().vmgym_set_tuning(0, 1)
+
+
+@pytest.mark.parametrize("agent,tie", [("firstfit", "stable"), ("bestfit", "stable"), ("bestfit", "numpy_introsort")])
+@pytest.mark.parametrize("shape,n_envs,steps,chunk", [("s100", 6, 1300, 1), ("s100", 6, 1300, 64), ("s10", 20, 380, 7),
+                                                       ("odd", 9, 500, 25)])
+def test_fused_agent_step_matches_oracle_rollout(agent, tie, shape, n_envs, steps, chunk):
+    """agent.act + env.step fused in one kernel (chunk steps per launch) == oracle act()/step() loop."""
+    from vmgym import VecVmEnv
+    kw = SHAPES[shape]
+    seeds = 5 + 3 * np.arange(n_envs)
+    vec = VecVmEnv(_cfg(**kw), n_envs, seeds=seeds, trace_steps=steps + 4, max_admissions=30000, tiebreak=tie)
+    oracles = _oracle_batch(kw, seeds, steps + 4, 30000)
+    P, V = kw["pms"], kw["vms"]
+    otie = vo.TIE_NUMPY_INTROSORT if tie == "numpy_introsort" else vo.TIE_STABLE
+    returns = np.zeros(n_envs)
+    done = 0
+    while done < steps:
+        n = min(chunk, steps - done)
+        vec.agent_step(agent, n_steps=n, want_stats=True)
+        act_d = vec.agent_action.cpu().numpy().astype(np.int64)
+        obs_h, rew_h = vec.obs.cpu().numpy(), vec.reward.cpu().numpy()
+        for i, o in enumerate(oracles):
+            for k in range(n):
+                ob = o._obs()
+                a = vo.firstfit_act(P, V, ob) if agent == "firstfit" else vo.bestfit_act(P, V, ob, otie)
+                o_obs, o_r, o_term, _, _ = o.step(a)
+                returns[i] += o_r
+                if o_term:
+                    break
+            assert np.array_equal(act_d[i], a), (i, done)
+            assert obs_h[i].tobytes() == o_obs.tobytes(), (i, done)
+            assert rew_h[i] == pytest.approx(o_r, rel=REWARD_RTOL, abs=1e-300)
+        done += n
+        if done % 256 < chunk or done == steps:
+            cnt = _compare_state(vec, oracles, done)
+            assert np.allclose(cnt["episode_return"], returns, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["s100_firstfit_wr", "s100_bestfit_stable_wr", "s100_bestfit_introsort_wr",
+                                  "s10_bestfit_stable_ut", "odd_p37_v70_eval"])
+def test_agent_act_kernel_on_reference_observations(name):
+    """FirstFitAgent.act / BestFitAgent.act on the reference's own observations -> the reference's actions
+    (unperturbed fixtures only: the recorded action IS the agent's output)."""
+    torch = _torch()
+    from vmgym import VecVmEnv
+    from vmgym.agents import BestFitAgent, FirstFitAgent
+    fx = gu.load(name)
+    cfg = fx["cfg"]
+    T = fx["action"].shape[0]
+    obs = np.concatenate([fx["placement"][:T].astype(np.float64), fx["vm_cpu_code"][:T] / 100.0,
+                          fx["vm_mem_code"][:T] / 100.0, fx["cpu"][:T], fx["memory"][:T]], axis=1).astype(np.float32)
+    tie = "numpy_introsort" if str(fx["tiebreak"]) == "numpy_introsort" else "stable"
+    vec = VecVmEnv(_cfg(**cfg), 1, trace_steps=4, max_admissions=16, tiebreak=tie)
+    agent = (FirstFitAgent if str(fx["agent"]) == "firstfit" else BestFitAgent)(vec)
+    got = agent.act(torch.from_numpy(obs).to(vec.device)).cpu().numpy().astype(np.int64)
+    P, V = cfg["pms"], cfg["vms"]
+    otie = vo.TIE_NUMPY_INTROSORT if tie == "numpy_introsort" else vo.TIE_STABLE
+    for t in range(T):
+        want = vo.firstfit_act(P, V, obs[t]) if str(fx["agent"]) == "firstfit" else vo.bestfit_act(P, V, obs[t], otie)
+        assert np.array_equal(got[t], want), t
+    if name != "odd_p37_v70_eval":   # that fixture's recorded actions are perturbed
+        assert np.array_equal(got, fx["action"].astype(np.int64))
+    # numpy in / numpy out form of the reference API
+    one = agent.act(obs[T // 2])
+    assert one.dtype == np.int64 and np.array_equal(one, got[T // 2])
+
+
+def test_invalid_action_mask_matches_oracle():
+    from vmgym import VecVmEnv
+    kw = SHAPES["s100"]
+    n_envs, steps = 5, 700
+    seeds = 40 + np.arange(n_envs)
+    vec = VecVmEnv(_cfg(**kw), n_envs, seeds=seeds, trace_steps=steps + 4, max_admissions=20000)
+    oracles = _oracle_batch(kw, seeds, steps + 4, 20000)
+    for t in range(0, steps, 100):
+        vec.agent_step("firstfit", n_steps=100, want_obs=False)
+        for o in oracles:
+            o.rollout(vo.AGENT_FIRSTFIT, 100)
+        m = vec.get_invalid_action_mask(True).cpu().numpy()
+        for i, o in enumerate(oracles):
+            assert np.array_equal(m[i], o.get_invalid_action_mask(True)), (i, t)
+    assert not vec.get_invalid_action_mask(False).any()
+
+
+def test_full_size_invariants_4096_envs():
+    """BASELINE config 2 size (4096 envs x 100 PMs): size-independent properties after a long fused rollout."""
+    from vmgym import VecVmEnv
+    kw = dict(SHAPES["s100"])
+    vec = VecVmEnv(_cfg(**kw), 4096, rng="philox")
+    vec.agent_step("bestfit", n_steps=1500, want_obs=True)
+    P, V = 100, 300
+    place = vec.vm_placement.cpu().numpy().astype(np.int64)
+    cc = (vec.vm_cpu_code.cpu().numpy() & 0x7f).astype(np.int64)
+    mc = vec.vm_mem_code.cpu().numpy().astype(np.int64)
+    cpu, mem = vec.cpu.cpu().numpy(), vec.memory.cpu().numpy()
+    cnt = vec.counters()
+    # conservation: every request is dropped, served, or still in a slot
+    existing = (place <= P).sum(1)
+    assert np.array_equal(cnt["total_requests"], cnt["dropped_requests"] + cnt["served_requests"] + existing)
+    assert np.all(cnt["timestep"] == 1501) and np.all(cnt["arrival_pos"] == 1500)
+    assert np.array_equal(cnt["admission_pos"], cnt["served_requests"] + existing)
+    # PM accumulators equal the sum of the sizes placed on them (up to fp64 drift), and never exceed capacity
+    onehot_cpu = np.zeros((4096, P + 2)); onehot_mem = np.zeros((4096, P + 2))
+    rows = np.repeat(np.arange(4096), V)
+    np.add.at(onehot_cpu, (rows, place.reshape(-1)), cc.reshape(-1) / 100.0)
+    np.add.at(onehot_mem, (rows, place.reshape(-1)), mc.reshape(-1) / 100.0)
+    assert np.allclose(cpu, onehot_cpu[:, :P], atol=1e-9) and np.allclose(mem, onehot_mem[:, :P], atol=1e-9)
+    assert cpu.max() <= 1.0 and mem.max() <= 1.0 and cpu.min() >= 0.0
+    # empty slots carry no size / runtime; running and waiting VMs have a positive remaining runtime
+    rem = vec.vm_remaining_runtime.cpu().numpy().astype(np.int64) & 0xFFFF
+    assert np.all(cc[place == P + 1] == 0) and np.all(rem[place == P + 1] == 0)
+    assert np.all(rem[place <= P] > 0) and np.all(cc[place <= P] >= 10)
+    # the observation is the float32 image of the state
+    obs = vec.obs.cpu().numpy()
+    want = np.concatenate([place, cc / 100.0, mc / 100.0, cpu, mem], axis=1).astype(np.float32)
+    assert obs.tobytes() == want.tobytes()
+    # envs are independent: a different batch composition reproduces env 7's trajectory exactly
+    vec2 = VecVmEnv(_cfg(**kw), 3, rng="philox", seeds=[kw.get("seed", 0) + 7, 12345, 999])
+    vec2.agent_step("bestfit", n_steps=1500, want_obs=True)
+    assert vec2.state[0].cpu().numpy()[: vec2._layout.off_scalars].tobytes() == \
+        vec.state[7].cpu().numpy()[: vec._layout.off_scalars].tobytes()

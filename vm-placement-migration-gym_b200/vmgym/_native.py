@@ -1,0 +1,118 @@
+"""ctypes binding of libvmgym.so — the C ABI declared in include/vmgym.h.
+
+The library is plain CUDA C++ (no torch types in any signature); PyTorch is only used by the callers for
+device memory and streams.  `build()` compiles it in-tree with nvcc for sm_100a; there is NO fallback: if the
+library is missing or fails to load, importing the env raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PKG_ROOT = os.path.dirname(_HERE)
+REPO_ROOT = os.path.dirname(PKG_ROOT)
+CSRC = os.path.join(PKG_ROOT, "csrc")
+LIB_PATH = os.path.join(_HERE, "libvmgym.so")
+SOURCES = ["vmgym_env.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+OK, EINVAL, ECUDA, EARCH, EUNSUPPORTED = 0, -1, -2, -3, -4
+REWARD_IDS = {"wr": 1, "ut": 2, "kl": 3}
+AGENT_NONE, AGENT_FIRSTFIT, AGENT_BESTFIT = 0, 1, 2
+TIE_IDS = {"stable": 0, "numpy_introsort": 1}
+U8, I16, I64 = 1, 2, 3
+TRACE_PRESAMPLED, TRACE_PHILOX = 0, 1
+
+
+class Config(C.Structure):
+    _fields_ = [("pms", C.c_int32), ("vms", C.c_int32), ("allow_null_action", C.c_int32),
+                ("reward_function", C.c_int32), ("cap_target_util", C.c_int32), ("step_limit", C.c_int32),
+                ("beta", C.c_double)]
+
+
+class Layout(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "record_bytes", "pms_padded", "vms_padded", "place_bytes", "off_cpu", "off_memory", "off_remaining",
+        "off_placement", "off_cpu_code", "off_mem_code", "off_scalars", "obs_dim", "action_dim",
+        "smem_bytes_per_env")]
+
+
+class Trace(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("reserved", C.c_int32),
+                ("d_arrivals", C.c_void_p), ("arrivals_len", C.c_int64),
+                ("d_admissions", C.c_void_p), ("admissions_len", C.c_int64),
+                ("d_arrival_cdf", C.c_void_p), ("arrival_cdf_len", C.c_int32), ("arrival_kmin", C.c_int32),
+                ("d_service_cdf", C.c_void_p), ("service_cdf_len", C.c_int32), ("service_kmin", C.c_int32),
+                ("size_lo_code", C.c_int32), ("size_hi_code", C.c_int32)]
+
+
+class Outputs(C.Structure):
+    _fields_ = [("d_obs", C.c_void_p), ("d_reward", C.c_void_p), ("d_terminated", C.c_void_p),
+                ("d_valid", C.c_void_p), ("d_action", C.c_void_p), ("d_stats", C.c_void_p)]
+
+
+# offsets inside struct vmgym_env_scalars (include/vmgym.h)
+SCALARS_I32 = ["timestep", "total_requests", "served_requests", "dropped_requests", "suspend_actions", "place_actions",
+               "arrival_pos", "admission_pos", "status", "episode"]
+SCALARS_BYTES = 80
+
+EXPORTS = ["vmgym_last_error", "vmgym_abi_version", "vmgym_get_layout", "vmgym_reset", "vmgym_step",
+           "vmgym_agent_step", "vmgym_agent_act", "vmgym_observe", "vmgym_invalid_action_mask", "vmgym_set_tuning"]
+
+
+class VmgymError(RuntimeError):
+    pass
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu into vmgym/libvmgym.so (sm_100a, -lineinfo).  nvcc cross-compiles without a GPU."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = srcs + [os.path.join(CSRC, "vmgym_device.cuh"), os.path.join(REPO_ROOT, "include", "vmgym.h")]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(REPO_ROOT, "include"), "-o", LIB_PATH] + srcs
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load libvmgym.so (building it first if the sources are newer and nvcc is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    try:
+        build()
+    except (OSError, subprocess.CalledProcessError) as e:
+        if not os.path.exists(LIB_PATH):
+            raise VmgymError(f"libvmgym.so is not built and nvcc failed ({e}); there is no CPU fallback") from e
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    L.vmgym_last_error.restype = C.c_char_p
+    L.vmgym_abi_version.restype = i32
+    L.vmgym_get_layout.argtypes = [C.POINTER(Config), C.POINTER(Layout)]
+    L.vmgym_reset.argtypes = [C.POINTER(Config), vp, i64, vp, vp, i32, vp, vp]
+    L.vmgym_step.argtypes = [C.POINTER(Config), vp, i64, C.POINTER(Trace), vp, i32, C.POINTER(Outputs), vp]
+    L.vmgym_agent_step.argtypes = [C.POINTER(Config), vp, i64, C.POINTER(Trace), i32, i32, i32, C.POINTER(Outputs), vp]
+    L.vmgym_agent_act.argtypes = [C.POINTER(Config), i32, i32, vp, i64, vp, i32, vp]
+    L.vmgym_observe.argtypes = [C.POINTER(Config), vp, i64, vp, vp]
+    L.vmgym_invalid_action_mask.argtypes = [C.POINTER(Config), vp, i64, vp, vp]
+    L.vmgym_set_tuning.argtypes = [i32, i32]
+    for name in EXPORTS:
+        getattr(L, name)
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise VmgymError(f"{what} failed ({rc}): {lib().vmgym_last_error().decode()}")

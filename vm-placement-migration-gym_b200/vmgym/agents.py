@@ -1,0 +1,85 @@
+"""Heuristic agents with the reference's interface (src/agents/base.py:15-149, firstfit.py, bestfit.py):
+`act(observation) -> action`, plus no-op learn/load_model/save_model/eval.  `act` accepts what the reference
+accepts (one float32 observation, numpy) and also a device batch [N, 3V+2P]; the scan itself is the CUDA kernel
+`vmgym_agent_act` — agents decide on the float32 view and accumulate locally in float32 exactly like the
+reference (SURVEY App. B-2,3)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as nv
+
+
+class HeuristicAgent:
+    kind = nv.AGENT_NONE
+    name = "HeuristicAgent"
+
+    def __init__(self, env, tiebreak: str | None = None):
+        self.env = env
+        self.vec = getattr(env, "vec", env)            # VmEnv facade or VecVmEnv
+        self.config = None
+        self.tiebreak = tiebreak or getattr(self.vec, "tiebreak", "stable")
+        self.total_steps = 0
+
+    # reference no-ops (firstfit.py:9-19)
+    def learn(self):
+        pass
+
+    def load_model(self, modelpath):
+        pass
+
+    def save_model(self, modelpath):
+        pass
+
+    def eval(self, model=True):
+        pass
+
+    def act(self, observation):
+        vec = self.vec
+        single = False
+        if isinstance(observation, np.ndarray):
+            single = observation.ndim == 1
+            obs = torch.from_numpy(np.ascontiguousarray(observation, dtype=np.float32).reshape(-1, vec.obs_dim)).to(vec.device)
+        else:
+            obs = observation.to(vec.device, torch.float32)
+            single = obs.dim() == 1
+            obs = obs.reshape(-1, vec.obs_dim).contiguous()
+        n = obs.shape[0]
+        host_out = isinstance(observation, np.ndarray)
+        dtype = torch.int64 if host_out else vec.place_dtype
+        action = torch.empty((n, vec.V), dtype=dtype, device=vec.device)
+        code = {torch.uint8: nv.U8, torch.int16: nv.I16, torch.int64: nv.I64}[dtype]
+        with torch.cuda.device(vec.device):
+            nv.check(nv.lib().vmgym_agent_act(C.byref(vec._ccfg()), self.kind, nv.TIE_IDS[self.tiebreak], obs.data_ptr(), n,
+                                              action.data_ptr(), code, vec._stream()), "vmgym_agent_act")
+        if host_out:
+            a = action.cpu().numpy()
+            return a[0] if single else a
+        return action[0] if single else action
+
+    def test(self, steps: int | None = None):
+        """Base.test (base.py:63-86) through the gym surface: eval mode, reset(seed), act/step until done."""
+        env = self.env
+        env.eval()
+        obs, _ = env.reset(seed=env.config.seed)
+        done, ret, n = False, 0.0, 0
+        while not done and (steps is None or n < steps):
+            obs, reward, done, _, info = env.step(self.act(obs))
+            ret += reward
+            n += 1
+        return ret, n
+
+
+class FirstFitAgent(HeuristicAgent):
+    """src/agents/firstfit.py:21-38."""
+    kind = nv.AGENT_FIRSTFIT
+    name = "FirstFitAgent"
+
+
+class BestFitAgent(HeuristicAgent):
+    """src/agents/bestfit.py:21-40 (tie rule: DESIGN.md "best-fit tie-break")."""
+    kind = nv.AGENT_BESTFIT
+    name = "BestFitAgent"

@@ -1,0 +1,261 @@
+"""VecVmEnv — N independent reference-semantics VmEnv instances resident on one B200.
+
+Mirrors the reference env surface (vmenv/envs/env.py:19-325) with a leading env axis:
+    reset(seed) -> obs[N, 3V+2P] f32                       (env.py:180-226)
+    step(action[N, V]) -> obs, reward[N] f64, terminated[N] bool, truncated[N] bool, info  (env.py:66-103)
+    get_invalid_action_mask(masked) -> bool[N, V, A]       (env.py:45-53)
+    eval(mode), seed(seed), close()                        (env.py:105-106,172-178,241-242)
+plus the fused heuristic rollouts `agent_step(kind, n_steps)` (Base.test loop, src/agents/base.py:71-86).
+
+All state lives in one device buffer of env records (include/vmgym.h: vmgym_layout); every method enqueues
+hand-written sm_100a kernels from libvmgym.so on the current CUDA stream.  Returned tensors are views of
+buffers owned by the env and are overwritten by the next call (unlike the reference, which returns fresh
+arrays) — clone them if they must survive a step.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as nv
+from .config import Config
+from .trace import EnvStreams, poisson_cdf_table, sample_numpy_traces, size_code_range
+
+_TORCH_ACTION_DTYPES = {torch.uint8: nv.U8, torch.int16: nv.I16, torch.int64: nv.I64}
+
+
+class VecVmEnv:
+    def __init__(self, config: Config, num_envs: int, device="cuda", rng: str = "numpy", seeds=None,
+                 trace_steps: int | None = None, max_admissions: int | None = None, tiebreak: str = "stable"):
+        if not torch.cuda.is_available():
+            raise nv.VmgymError("VecVmEnv needs a CUDA device (sm_100a); there is no CPU path")
+        self.config = config.validate()
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise nv.VmgymError("VecVmEnv needs a CUDA device")
+        self.rng_mode = rng
+        if rng not in ("numpy", "philox"):
+            raise ValueError("rng must be 'numpy' (reference-exact pre-sampled traces) or 'philox'")
+        self.tiebreak = tiebreak
+        self.eval_mode = False
+        self.P, self.V = int(config.pms), int(config.vms)
+        self.action_dim = config.action_dim
+        self.obs_dim = config.obs_dim
+        self.WAIT_STATUS, self.NULL_STATUS = self.P, self.P + 1
+        self._lib = nv.lib()
+        self._layout = nv.Layout()
+        nv.check(self._lib.vmgym_get_layout(C.byref(self._ccfg()), C.byref(self._layout)), "vmgym_get_layout")
+        L = self._layout
+        self.place_dtype = torch.uint8 if L.place_bytes == 1 else torch.int16
+        N = self.num_envs
+        with torch.cuda.device(self.device):
+            self.state = torch.zeros((N, L.record_bytes), dtype=torch.uint8, device=self.device)
+            self.obs = torch.zeros((N, self.obs_dim), dtype=torch.float32, device=self.device)
+            self.reward = torch.zeros(N, dtype=torch.float64, device=self.device)
+            self.terminated = torch.zeros(N, dtype=torch.uint8, device=self.device)
+            self.valid = torch.zeros((N, self.V), dtype=torch.uint8, device=self.device)
+            self.agent_action = torch.zeros((N, self.V), dtype=self.place_dtype, device=self.device)
+            self.stats = torch.zeros((N, 8), dtype=torch.float64, device=self.device)
+        self._trace_steps = trace_steps
+        self._max_admissions = max_admissions
+        self._streams = None
+        self._trace = None          # nv.Trace
+        self._trace_tensors = ()
+        self._seeds = None
+        self._build_views()
+        base = int(config.seed)
+        self.reset(seed=(base + np.arange(N, dtype=np.int64)) if seeds is None else np.asarray(seeds, np.int64))
+
+    # ------------------------------------------------------------------------------------------------
+    def _ccfg(self) -> nv.Config:
+        c = self.config
+        limit = int(c.eval_steps) if self.eval_mode else int(c.training_steps)
+        return nv.Config(int(c.pms), int(c.vms), int(bool(c.allow_null_action)), nv.REWARD_IDS[c.reward_function],
+                         int(bool(c.cap_target_util)), limit, float(c.beta))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _build_views(self):
+        L, P, V = self._layout, self.P, self.V
+        s = self.state
+        self.cpu = s[:, L.off_cpu:L.off_cpu + 8 * P].view(torch.float64)
+        self.memory = s[:, L.off_memory:L.off_memory + 8 * P].view(torch.float64)
+        self.vm_remaining_runtime = s[:, L.off_remaining:L.off_remaining + 2 * V].view(torch.int16)
+        pb = L.place_bytes
+        self.vm_placement = s[:, L.off_placement:L.off_placement + pb * V].view(self.place_dtype)
+        self.vm_cpu_code = s[:, L.off_cpu_code:L.off_cpu_code + V]
+        self.vm_mem_code = s[:, L.off_mem_code:L.off_mem_code + V]
+        sc = s[:, L.off_scalars:L.off_scalars + nv.SCALARS_BYTES]
+        self._scalars_i32 = sc[:, :40].view(torch.int32)
+        self._scalars_i64 = sc[:, 40:80].view(torch.int64)     # seed, cpu_code_sum, mem_code_sum, (f64 x2 as bits)
+        self._scalars_f64 = sc[:, 64:80].view(torch.float64)   # episode_return, last_reward
+
+    # ------------------------------------------------------------------------------------------------
+    # reference API
+    # ------------------------------------------------------------------------------------------------
+    def eval(self, eval_mode: bool = True):
+        self.eval_mode = bool(eval_mode)
+
+    def seed(self, seed=None):
+        """env.py:172-178 — (re)create the four generators of every env at seed_i .. seed_i+3."""
+        if seed is None:
+            seed = int(self.config.seed) + np.arange(self.num_envs, dtype=np.int64)
+        seeds = np.broadcast_to(np.asarray(seed, np.int64), (self.num_envs,)).copy() if np.ndim(seed) else \
+            int(seed) + np.arange(self.num_envs, dtype=np.int64)
+        self._seeds = seeds
+        if self.rng_mode == "numpy":
+            self._streams = [EnvStreams(int(s)) for s in seeds]
+        self._reseeded = True
+
+    def reset(self, seed=None, options=None):
+        """env.py:180-226.  `seed` None continues the arrival/service streams; an int seeds env i with seed+i;
+        an array gives one seed per env."""
+        if seed is not None:
+            self.seed(seed)
+        rewind = 1
+        d_seeds = None
+        with torch.cuda.device(self.device):
+            if self.rng_mode == "numpy":
+                if not getattr(self, "_reseeded", False) and self._trace is not None:
+                    pos = self._scalars_i32[:, 6:8].cpu().numpy().astype(np.int64)
+                    for s, (a, j) in zip(self._streams, pos):
+                        s.rewind_to(self.config, a, j)
+                T = self._trace_steps or max(int(self.config.training_steps), int(self.config.eval_steps))
+                arr, adm = sample_numpy_traces(self.config, self._streams, T, self._max_admissions)
+                d_arr = torch.from_numpy(arr.view(np.int16)).to(self.device)
+                d_adm = torch.from_numpy(adm.view(np.int32)).to(self.device)
+                self._trace_tensors = (d_arr, d_adm)
+                self._trace = nv.Trace(mode=nv.TRACE_PRESAMPLED, d_arrivals=d_arr.data_ptr(), arrivals_len=arr.shape[1],
+                                       d_admissions=d_adm.data_ptr(), admissions_len=adm.shape[1])
+            else:
+                if self._trace is None:
+                    ka, ta = poisson_cdf_table(self.config.arrival_rate)
+                    ks, ts = poisson_cdf_table(self.config.service_length)
+                    d_ta = torch.from_numpy(ta.view(np.int64)).to(self.device)
+                    d_ts = torch.from_numpy(ts.view(np.int64)).to(self.device)
+                    lo, hi = size_code_range(self.config.sequence)
+                    self._trace_tensors = (d_ta, d_ts)
+                    self._trace = nv.Trace(mode=nv.TRACE_PHILOX, d_arrival_cdf=d_ta.data_ptr(), arrival_cdf_len=len(ta),
+                                           arrival_kmin=ka, d_service_cdf=d_ts.data_ptr(), service_cdf_len=len(ts),
+                                           service_kmin=ks, size_lo_code=lo, size_hi_code=hi)
+                    self.philox_tables = (ka, ta, ks, ts, lo, hi)
+                if getattr(self, "_reseeded", False):
+                    d_seeds = torch.from_numpy(self._seeds.copy()).to(self.device)
+                else:
+                    rewind = 0
+            self._reseeded = False
+            self.stats.zero_()
+            nv.check(self._lib.vmgym_reset(C.byref(self._ccfg()), self.state.data_ptr(), self.num_envs, None,
+                                           d_seeds.data_ptr() if d_seeds is not None else None, rewind,
+                                           self.obs.data_ptr(), self._stream()), "vmgym_reset")
+        return self.obs, {}
+
+    def _outputs(self, want_action=False, want_stats=False, want_obs=True, want_valid=True) -> nv.Outputs:
+        return nv.Outputs(d_obs=self.obs.data_ptr() if want_obs else None, d_reward=self.reward.data_ptr(),
+                          d_terminated=self.terminated.data_ptr(), d_valid=self.valid.data_ptr() if want_valid else None,
+                          d_action=self.agent_action.data_ptr() if want_action else None,
+                          d_stats=self.stats.data_ptr() if want_stats else None)
+
+    def step(self, action, want_obs: bool = True, want_valid: bool = True):
+        """env.py:66-103 for all envs.  `action`: [N, V] device tensor (uint8 / int16 / int64) or numpy int array."""
+        if not isinstance(action, torch.Tensor):
+            action = torch.from_numpy(np.ascontiguousarray(action, dtype=np.int64)).to(self.device, non_blocking=True)
+        if action.shape != (self.num_envs, self.V):
+            raise ValueError(f"action must have shape {(self.num_envs, self.V)}, got {tuple(action.shape)}")
+        if action.dtype not in _TORCH_ACTION_DTYPES:
+            action = action.to(torch.int64)
+        action = action.contiguous()
+        out = self._outputs(want_obs=want_obs, want_valid=want_valid)
+        with torch.cuda.device(self.device):
+            nv.check(self._lib.vmgym_step(C.byref(self._ccfg()), self.state.data_ptr(), self.num_envs,
+                                          C.byref(self._trace), action.data_ptr(), _TORCH_ACTION_DTYPES[action.dtype],
+                                          C.byref(out), self._stream()), "vmgym_step")
+        info = {"action": action, "valid": self.valid}
+        return self.obs, self.reward, self.terminated.bool(), torch.zeros_like(self.terminated, dtype=torch.bool), info
+
+    def agent_step(self, agent: str, n_steps: int = 1, want_obs: bool = True, want_action: bool = True,
+                   want_stats: bool = False, want_valid: bool = True, tiebreak: str | None = None):
+        """Fused heuristic agent.act + env.step, `n_steps` per launch (firstfit.py:21-38 / bestfit.py:21-40 +
+        env.py:66-103).  Returns (obs, reward, terminated) of the last executed step."""
+        kind = {"firstfit": nv.AGENT_FIRSTFIT, "bestfit": nv.AGENT_BESTFIT}[agent]
+        out = self._outputs(want_action=want_action, want_stats=want_stats, want_obs=want_obs, want_valid=want_valid)
+        with torch.cuda.device(self.device):
+            nv.check(self._lib.vmgym_agent_step(C.byref(self._ccfg()), self.state.data_ptr(), self.num_envs,
+                                                C.byref(self._trace), kind, nv.TIE_IDS[tiebreak or self.tiebreak],
+                                                int(n_steps), C.byref(out), self._stream()), "vmgym_agent_step")
+        return self.obs, self.reward, self.terminated.bool()
+
+    def observe(self):
+        with torch.cuda.device(self.device):
+            nv.check(self._lib.vmgym_observe(C.byref(self._ccfg()), self.state.data_ptr(), self.num_envs,
+                                             self.obs.data_ptr(), self._stream()), "vmgym_observe")
+        return self.obs
+
+    def get_invalid_action_mask(self, masked: bool = True):
+        """env.py:45-53: bool[N, V, A], True = invalid (all False when `masked` is False)."""
+        mask = torch.zeros((self.num_envs, self.V, self.action_dim), dtype=torch.uint8, device=self.device)
+        if masked:
+            with torch.cuda.device(self.device):
+                nv.check(self._lib.vmgym_invalid_action_mask(C.byref(self._ccfg()), self.state.data_ptr(), self.num_envs,
+                                                             mask.data_ptr(), self._stream()), "vmgym_invalid_action_mask")
+        return mask.bool()
+
+    def close(self):
+        pass
+
+    # ------------------------------------------------------------------------------------------------
+    # state access (device views / host snapshots)
+    # ------------------------------------------------------------------------------------------------
+    def counters(self):
+        """dict of int64 numpy arrays [N]: the scalar attributes of env.py:197-208."""
+        i32 = self._scalars_i32.cpu().numpy().astype(np.int64)
+        i64 = self._scalars_i64.cpu().numpy()
+        f64 = self._scalars_f64.cpu().numpy()
+        d = {k: i32[:, i] for i, k in enumerate(nv.SCALARS_I32)}
+        d["seed"] = i64[:, 0]
+        d["total_cpu_requested"] = i64[:, 1] / 100.0
+        d["total_memory_requested"] = i64[:, 2] / 100.0
+        d["episode_return"] = f64[:, 0]
+        d["last_reward"] = f64[:, 1]
+        return d
+
+    def state_dict_host(self, env: int = 0):
+        """Host snapshot of one env in the reference's attribute names/dtypes (for parity tests / the N=1 facade)."""
+        P, V = self.P, self.V
+        rec = self.state[env].cpu().numpy()
+        L = self._layout
+        place = rec[L.off_placement:L.off_placement + L.place_bytes * V].view(np.uint8 if L.place_bytes == 1 else np.uint16)
+        cc = rec[L.off_cpu_code:L.off_cpu_code + V]
+        mc = rec[L.off_mem_code:L.off_mem_code + V]
+        i32 = rec[L.off_scalars:L.off_scalars + 40].view(np.int32)
+        i64 = rec[L.off_scalars + 40:L.off_scalars + 64].view(np.int64)
+        f64 = rec[L.off_scalars + 64:L.off_scalars + 80].view(np.float64)
+        placement = place.astype(np.int64)
+        vm_cpu = (cc & 0x7f) / 100.0
+        vm_memory = mc / 100.0
+        existing = placement <= P
+        n_ex = int(existing.sum())
+        s = dict(vm_placement=placement, vm_cpu=vm_cpu, vm_memory=vm_memory,
+                 cpu=rec[L.off_cpu:L.off_cpu + 8 * P].view(np.float64).copy(),
+                 memory=rec[L.off_memory:L.off_memory + 8 * P].view(np.float64).copy(),
+                 vm_remaining_runtime=rec[L.off_remaining:L.off_remaining + 2 * V].view(np.uint16).astype(np.int64),
+                 vm_suspended=(cc >> 7).astype(np.int64))
+        for i, k in enumerate(nv.SCALARS_I32):
+            s[k] = int(i32[i])
+        s["suspend_action"], s["place_action"] = s["suspend_actions"], s["place_actions"]
+        s["arr_cursor"], s["adm_cursor"], s["trace_exhausted"] = s["arrival_pos"], s["admission_pos"], s["status"] & 1
+        s["total_cpu_requested"] = int(i64[1]) / 100.0
+        s["total_memory_requested"] = int(i64[2]) / 100.0
+        s["episode_return"], s["last_reward"] = float(f64[0]), float(f64[1])
+        # derived metrics of env.py:112-121 (not stored on the device)
+        s["waiting_ratio"] = float((placement == P).sum()) / n_ex if n_ex else 0
+        tc = float(np.sum((cc & 0x7f)[existing].astype(np.int64))) / 100.0 / P
+        tm = float(np.sum(mc[existing].astype(np.int64))) / 100.0 / P
+        if self.config.cap_target_util:
+            tc, tm = min(tc, 1.0), min(tm, 1.0)
+        s["target_cpu_mean"], s["target_memory_mean"] = tc, tm
+        return s
