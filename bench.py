@@ -159,11 +159,12 @@ def gpu_arm(args):
     K = args.steps
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    one_step = vec.capture(lambda: vec.agent_step("bestfit", 1, want_obs=True, want_action=False, want_valid=False))
     barrier()
     for k in range(K):
         flush.fill_(k & 0xff)                      # evict state/obs from L2 (outside the event pair)
         starts[k].record()
-        vec.agent_step("bestfit", 1, want_obs=True, want_action=False, want_valid=False)
+        one_step.replay()                          # the fused step kernel, launched as a 1-node CUDA graph
         ends[k].record()
     barrier()
     dev_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
@@ -202,7 +203,7 @@ def gpu_arm(args):
         obs, rew, term, _, _ = vec.step(d_act_in, want_valid=False)
         h_obs.copy_(obs, non_blocking=True)
         h_rew.copy_(rew, non_blocking=True)
-        h_term.copy_(vec.terminated, non_blocking=True)
+        h_term.copy_(vec.terminated_u8, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     for _ in range(3):

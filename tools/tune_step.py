@@ -21,6 +21,8 @@ B = 2 * (16 * 100 + 5 * 300 + 48) + 4 * 1100 + 16
 
 
 def timeit(fn, iters=30, do_flush=True):
+    g = vec.capture(fn)
+    fn = g.replay
     for _ in range(3):
         fn()
     ts = []

@@ -53,7 +53,8 @@ static int make_layout(const vmgym_config* c, DevLayout* L, vmgym_layout* pub)
     l.sm_act = l.sm_mem32 + align_up(4 * l.P, 16);
     l.sm_tmp = l.sm_act + 2 * l.Vp;
     const int tmp_bytes = align_up((2 * l.Vp > 6 * l.Pp) ? 2 * l.Vp : 6 * l.Pp, 16);
-    l.sm_bar = l.sm_tmp + tmp_bytes;
+    l.sm_fit = l.sm_tmp + tmp_bytes;                       // u32 fitm[128] | u16 cap[Pp]
+    l.sm_bar = l.sm_fit + 512 + align_up(2 * l.Pp, 16);
     l.sm_stride = align_up(l.sm_bar + 16, 128);
     l.sm_tables = SIZE_TABLE * 8 + SIZE_TABLE * 4;
     if (L) *L = l;
@@ -91,8 +92,10 @@ struct Env {
     uint8_t* cpuc; uint8_t* memc;      // size codes (bit 7 of cpuc = suspended)
     vmgym_env_scalars* sc;
     float* cpu32; float* mem32;        // the agents' float32 view (env.py:296) with local accumulation
-    PT* act;                           // action chosen by a fused agent
+    uint16_t* act;                     // this step's action vector (external or chosen by a fused agent)
     uint8_t* tmp;                      // compaction / sort scratch
+    uint16_t* cap;                     // per-PM capacity codes of the float32 view: cpu | mem << 8
+    unsigned* fitm;                    // fit table over cpu codes (see rebuild_fit_table)
     const double* sz64; const float* sz32;   // code -> k/100.0 and (float)(k/100.0)
     int P, V, lane;
 };
@@ -185,23 +188,74 @@ __device__ __noinline__ void introsort_argsort(const float* v, uint16_t* t, int 
 // A VM that fits nowhere makes every later VM with component-wise >= sizes fit nowhere too (PM loads only
 // grow inside act() and fp32 rounding is monotone), so such VMs are skipped without a scan.
 // ---------------------------------------------------------------------------------------------------
-template <typename PT, class FW, class FC, class FM>
-__device__ __forceinline__ void agent_act(Env<PT>& e, int agent, int tiebreak, FW waiting, FC c32of, FM m32of)
+// largest size code k in [0,100] with x + sz32[k] <= 1.0f (monotone in k because fp32 rounding is monotone)
+__device__ __forceinline__ int max_code(const float* sz32, float x)
+{
+    int lo = 0, hi = 101;
+#pragma unroll
+    for (int it = 0; it < 7; it++) {
+        const int mid = (lo + hi) >> 1;
+        if (x + sz32[mid] <= 1.0f) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// fitm[c] = 1 + max{ mem-capacity code of PM p : cpu-capacity code of p >= c }, 0 if no PM takes cpu code c.
+// A VM with size codes (c, m) fits on SOME PM iff m + 1 <= fitm[c] — an exact O(1) test that removes the hopeless
+// waiting VMs (the large majority at saturation) from the sequential scan.
+template <typename PT>
+__device__ __forceinline__ void rebuild_fit_table(Env<PT>& e)
+{
+    const int lane = e.lane;
+    for (int c = lane; c < 128; c += 32) e.fitm[c] = 0u;
+    __syncwarp();
+    for (int p = lane; p < e.P; p += 32) {
+        const unsigned w = e.cap[p];
+        atomicMax(&e.fitm[w & 0xffu], (w >> 8) + 1u);
+    }
+    __syncwarp();
+    uint4 q = reinterpret_cast<uint4*>(e.fitm)[lane];          // lane owns codes 4*lane .. 4*lane+3
+    q.z = max(q.z, q.w); q.y = max(q.y, q.z); q.x = max(q.x, q.y);
+    unsigned s = q.x;                                          // suffix max over lanes >= lane
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_down_sync(FULL, s, o);
+        if (lane + o < 32) s = max(s, t);
+    }
+    unsigned ex = __shfl_down_sync(FULL, s, 1);
+    if (lane == 31) ex = 0u;
+    q.x = max(q.x, ex); q.y = max(q.y, ex); q.z = max(q.z, ex); q.w = max(q.w, ex);
+    reinterpret_cast<uint4*>(e.fitm)[lane] = q;
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Heuristic agents on the float32 view (firstfit.py:21-38, bestfit.py:21-40).  lanes own PMs p = lane+32i.
+// `waiting(v)`: slot v is a waiting VM in the observation; `ccode/mcode(v)`: its size codes (hundredths) or -1
+// when the observed size is not an exact hundredth (then the VM is always scanned); `c32of/m32of(v)`: the sizes
+// as the agent sees them.  Writes e.act[v] for the waiting VMs it places (others keep their placement).
+// ---------------------------------------------------------------------------------------------------
+template <typename PT, class FW, class FK, class FL, class FC, class FM>
+__device__ __forceinline__ void agent_act(Env<PT>& e, int agent, int tiebreak, FW waiting, FK ccode, FL mcode, FC c32of,
+                                          FM m32of)
 {
     const int P = e.P, V = e.V, lane = e.lane;
-    float fc0 = 2.f, fm0 = 2.f, fc1 = 2.f, fm1 = 2.f, fc2 = 2.f, fm2 = 2.f, fc3 = 2.f, fm3 = 2.f;  // failed sizes
-    int nf = 0;
+    for (int p = lane; p < P; p += 32)
+        e.cap[p] = (uint16_t)(max_code(e.sz32, e.cpu32[p]) | (max_code(e.sz32, e.mem32[p]) << 8));
+    rebuild_fit_table(e);
     for (int c0 = 0; c0 < V; c0 += 32) {
         const int v = c0 + lane;
-        unsigned m = __ballot_sync(FULL, v < V && waiting(v));
+        bool cand = v < V && waiting(v);
+        if (cand) {
+            const int cc = ccode(v), mc = mcode(v);
+            if (cc >= 0 && mc >= 0) cand = (unsigned)(mc + 1) <= e.fitm[cc];
+        }
+        unsigned m = __ballot_sync(FULL, cand);
         while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
             const int vv = c0 + b;
             const float c32 = c32of(vv), m32 = m32of(vv);
-            if ((c32 >= fc0 && m32 >= fm0) || (c32 >= fc1 && m32 >= fm1) || (c32 >= fc2 && m32 >= fm2) ||
-                (c32 >= fc3 && m32 >= fm3))
-                continue;
             int found = -1;
             if (agent == VMGYM_AGENT_FIRSTFIT) {
                 for (int i0 = 0; i0 < P; i0 += 32) {
@@ -210,7 +264,11 @@ __device__ __forceinline__ void agent_act(Env<PT>& e, int agent, int tiebreak, F
                     const unsigned bb = __ballot_sync(FULL, fit);
                     if (bb) { found = i0 + __ffs(bb) - 1; break; }
                 }
-                if (found >= 0 && lane == (found & 31)) e.cpu32[found] = e.cpu32[found] + c32;   // firstfit.py:36
+                if (found >= 0 && lane == (found & 31)) {
+                    const float nc = e.cpu32[found] + c32;       // firstfit.py:36 — only the local cpu is updated
+                    e.cpu32[found] = nc;
+                    e.cap[found] = (uint16_t)((e.cap[found] & 0xff00u) | (unsigned)max_code(e.sz32, nc));
+                }
             } else {
                 // best-fit: first fitting PM in descending (cpu+memory) order (bestfit.py:33-39)
                 unsigned bestk = 0;
@@ -249,18 +307,20 @@ __device__ __forceinline__ void agent_act(Env<PT>& e, int agent, int tiebreak, F
                         }
                     }
                     if (lane == (found & 31)) {
-                        e.cpu32[found] = e.cpu32[found] + c32;      // bestfit.py:37-38
-                        e.mem32[found] = e.mem32[found] + m32;
+                        const float nc = e.cpu32[found] + c32, nm = e.mem32[found] + m32;   // bestfit.py:37-38
+                        e.cpu32[found] = nc;
+                        e.mem32[found] = nm;
+                        e.cap[found] = (uint16_t)(max_code(e.sz32, nc) | (max_code(e.sz32, nm) << 8));
                     }
-                    if (tiebreak == VMGYM_TIE_NUMPY_INTROSORT) __syncwarp();
                 }
             }
             if (found >= 0) {
-                if (lane == 0) e.act[vv] = (PT)found;
-            } else if (nf < 4) {
-                if (nf == 0) { fc0 = c32; fm0 = m32; } else if (nf == 1) { fc1 = c32; fm1 = m32; }
-                else if (nf == 2) { fc2 = c32; fm2 = m32; } else { fc3 = c32; fm3 = m32; }
-                nf++;
+                if (lane == 0) e.act[vv] = (uint16_t)found;
+                __syncwarp();
+                rebuild_fit_table(e);              // capacities shrank: later candidates of this chunk are re-tested
+                const int cc = v < V ? ccode(v) : -1, mc = v < V ? mcode(v) : -1;
+                const bool still = !(cc >= 0 && mc >= 0) || (unsigned)(mc + 1) <= e.fitm[cc];
+                m &= __ballot_sync(FULL, still);
             }
         }
     }
@@ -313,9 +373,8 @@ __device__ __noinline__ double reward_kl(const double* cpu, const double* mem, i
 // ---------------------------------------------------------------------------------------------------
 struct StepResult { double reward; int terminated; int rejected; int waiting, arrived; };
 
-template <typename PT, class FA>
-__device__ __forceinline__ StepResult env_step(Env<PT>& e, const StepParams& p, long long env_id, FA get_action,
-                                               uint8_t* valid_g)
+template <typename PT>
+__device__ __forceinline__ StepResult env_step(Env<PT>& e, const StepParams& p, long long env_id, uint8_t* valid_g)
 {
     const int P = e.P, V = e.V, lane = e.lane;
     vmgym_env_scalars* sc = e.sc;
@@ -324,7 +383,7 @@ __device__ __forceinline__ StepResult env_step(Env<PT>& e, const StepParams& p, 
     // ---- 1. apply actions in VM-index order, each seeing earlier updates (env.py:69-87, validate :35-42) ----
     for (int c0 = 0; c0 < V; c0 += 32) {
         const int v = c0 + lane;
-        const int a = v < V ? get_action(v) : 0;
+        const int a = v < V ? (int)e.act[v] : 0;
         const int cur = v < V ? (int)e.place[v] : 0;
         const bool diff = v < V && a != cur;
         unsigned m = __ballot_sync(FULL, diff);
@@ -527,8 +586,10 @@ __device__ __forceinline__ void bind_env(Env<PT>& e, unsigned char* base, const 
     e.sc = reinterpret_cast<vmgym_env_scalars*>(base + L.off_scal);
     e.cpu32 = reinterpret_cast<float*>(base + L.sm_cpu32);
     e.mem32 = reinterpret_cast<float*>(base + L.sm_mem32);
-    e.act = reinterpret_cast<PT*>(base + L.sm_act);
+    e.act = reinterpret_cast<uint16_t*>(base + L.sm_act);
     e.tmp = base + L.sm_tmp;
+    e.fitm = reinterpret_cast<unsigned*>(base + L.sm_fit);
+    e.cap = reinterpret_cast<uint16_t*>(base + L.sm_fit + 512);
     e.sz64 = sz64; e.sz32 = sz32; e.P = L.P; e.V = L.V; e.lane = lane;
 }
 
@@ -603,20 +664,21 @@ __global__ void __launch_bounds__(256, 4) step_kernel(const StepParams p)
             if (p.agent != VMGYM_AGENT_NONE) {
                 // the agent sees the float32 observation of the current state (env.py:296)
                 for (int q = lane; q < L.P; q += 32) { e.cpu32[q] = (float)e.cpu[q]; e.mem32[q] = (float)e.mem[q]; }
-                for (int v = lane; v < L.V; v += 32) e.act[v] = e.place[v];
+                for (int v = lane; v < L.V; v += 32) e.act[v] = (uint16_t)e.place[v];
                 __syncwarp();
                 const PT* place = e.place; const uint8_t* cpuc = e.cpuc; const uint8_t* memc = e.memc;
                 const float* t32 = sz32;
                 const int P = L.P;
                 agent_act(e, p.agent, p.tiebreak, [=](int v) { return (int)place[v] == P; },
+                          [=](int v) { return (int)(cpuc[v] & 0x7f); }, [=](int v) { return (int)memc[v]; },
                           [=](int v) { return t32[cpuc[v] & 0x7f]; }, [=](int v) { return t32[memc[v]]; });
-                const PT* act = e.act;
-                res = env_step(e, p, env, [=](int v) { return (int)act[v]; }, valid_g);
             } else {
                 const int adt = p.action_dtype;
                 const unsigned char* arow = reinterpret_cast<const unsigned char*>(p.action) + env * (long long)L.V * dtype_bytes(adt);
-                res = env_step(e, p, env, [=](int v) { return load_action(arow, adt, v); }, valid_g);
+                for (int v = lane; v < L.V; v += 32) e.act[v] = (uint16_t)load_action(arow, adt, v);
+                __syncwarp();
             }
+            res = env_step(e, p, env, valid_g);
             if (p.out.d_stats) {
                 // running sums for the eval summary (record.py:98-134, exp_performance.py:104-113)
                 double sc_ = 0, sm_ = 0;
@@ -640,7 +702,7 @@ __global__ void __launch_bounds__(256, 4) step_kernel(const StepParams p)
         if (p.out.d_obs) write_obs(e, p.out.d_obs + env * (long long)L.D);
         if (p.out.d_action && p.agent != VMGYM_AGENT_NONE) {
             PT* ao = reinterpret_cast<PT*>(p.out.d_action) + env * (long long)L.V;
-            for (int v = lane; v < L.V; v += 32) ao[v] = e.act[v];
+            for (int v = lane; v < L.V; v += 32) ao[v] = (PT)e.act[v];
         }
         if (lane == 0) {
             if (p.out.d_reward) p.out.d_reward[env] = res.reward;
@@ -762,15 +824,23 @@ __global__ void mask_kernel(DevLayout L, const unsigned char* state, long long n
 }
 
 // agent.act(observation) on float32 observations [n_envs, D] (firstfit.py:21-38, bestfit.py:21-40).
+// per-warp shared memory: obs row f32[D] | act PT[Vp] | tmp (sort scratch) | fitm u32[128] | cap u16[Pp]
+__host__ __device__ inline int act_row_bytes(const DevLayout& L) { return align_up(4 * L.D, 16); }
+__host__ __device__ inline int act_smem_per_warp(const DevLayout& L)
+{
+    return act_row_bytes(L) + 2 * L.Vp + align_up(6 * L.Pp, 16) + 512 + align_up(2 * L.Pp, 16);
+}
+
 template <typename PT>
 __global__ void act_kernel(DevLayout L, int agent, int tiebreak, const float* obs, long long n_envs, void* action, int adt)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-    // per-warp: obs row f32[D] | act PT[Vp] (as u16 slots) | tmp
-    const int row_bytes = align_up(4 * L.D, 16);
-    const int per_warp = row_bytes + 2 * L.Vp + ((6 * L.Pp + 15) & ~15);
-    unsigned char* base = smem + (size_t)warp * per_warp;
+    float* sz32 = reinterpret_cast<float*>(smem);
+    for (int k = threadIdx.x; k < SIZE_TABLE; k += blockDim.x) sz32[k] = (float)((double)k / 100.0);
+    __syncthreads();
+    const int row_bytes = act_row_bytes(L);
+    unsigned char* base = smem + SIZE_TABLE * 4 + (size_t)warp * act_smem_per_warp(L);
     float* row = reinterpret_cast<float*>(base);
     const long long env = (long long)blockIdx.x * wpc + warp;
     if (env >= n_envs) return;
@@ -779,14 +849,22 @@ __global__ void act_kernel(DevLayout L, int agent, int tiebreak, const float* ob
     __syncwarp();
     Env<PT> e;
     e.P = L.P; e.V = L.V; e.lane = lane;
+    e.sz32 = sz32; e.sz64 = nullptr;
     e.cpu32 = row + 3 * L.V; e.mem32 = row + 3 * L.V + L.P;
-    e.act = reinterpret_cast<PT*>(base + row_bytes);
+    e.act = reinterpret_cast<uint16_t*>(base + row_bytes);
     e.tmp = base + row_bytes + 2 * L.Vp;
-    const int V = L.V;
-    const float fP = (float)L.P;
-    for (int v = lane; v < V; v += 32) e.act[v] = (PT)(int)row[v];           // utils.py:41 astype(int)
+    e.fitm = reinterpret_cast<unsigned*>(e.tmp + align_up(6 * L.Pp, 16));
+    e.cap = reinterpret_cast<uint16_t*>(e.tmp + align_up(6 * L.Pp, 16) + 512);
+    const int V = L.V, P = L.P;
+    for (int v = lane; v < V; v += 32) e.act[v] = (uint16_t)(int)row[v];      // utils.py:41 astype(int)
     __syncwarp();
-    agent_act(e, agent, tiebreak, [=](int v) { return (int)row[v] == (int)fP; }, [=](int v) { return row[V + v]; },
+    // size code of an observed size: the hundredth whose float32 image equals it, else -1 (never filtered)
+    auto code_of = [=](float x) {
+        const int k = __float2int_rn(x * 100.0f);
+        return (k >= 0 && k <= 100 && sz32[k] == x) ? k : -1;
+    };
+    agent_act(e, agent, tiebreak, [=](int v) { return (int)row[v] == P; }, [=](int v) { return code_of(row[V + v]); },
+              [=](int v) { return code_of(row[2 * V + v]); }, [=](int v) { return row[V + v]; },
               [=](int v) { return row[2 * V + v]; });
     unsigned char* ao = reinterpret_cast<unsigned char*>(action) + env * (long long)V * dtype_bytes(adt);
     for (int v = lane; v < V; v += 32) {
@@ -842,11 +920,18 @@ static int launch_step(StepParams& sp, cudaStream_t st)
     const size_t smem = (size_t)L.sm_tables + (size_t)w * L.sm_stride;
     if (smem > 227 * 1024) return fail(VMGYM_EUNSUPPORTED, "env record does not fit in shared memory (pms/vms too large)");
     auto kern = step_kernel<PT>;
-    int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute");
-    if (rc) return rc;
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, w * 32, smem);
-    if (occ < 1) occ = 1;
+    // per (kernel, smem, warps) launch plan, computed once (also keeps these calls out of CUDA-graph capture)
+    static thread_local size_t plan_smem = 0;
+    static thread_local int plan_w = 0, plan_occ = 1;
+    if (plan_smem != smem || plan_w != w) {
+        int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute");
+        if (rc) return rc;
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, w * 32, smem);
+        plan_occ = occ < 1 ? 1 : occ;
+        plan_smem = smem; plan_w = w;
+    }
+    const int occ = plan_occ;
     long long blocks = (sp.n_envs + w - 1) / w;
     const long long cap = (long long)sm_count() * occ;
     if (blocks > cap) blocks = cap;
@@ -956,11 +1041,10 @@ int vmgym_agent_act(const vmgym_config* cfg, int agent, int tiebreak, const floa
     if (!d_obs || !d_action || n_envs < 0) return fail(VMGYM_EINVAL, "null obs/action");
     if (agent != VMGYM_AGENT_FIRSTFIT && agent != VMGYM_AGENT_BESTFIT) return fail(VMGYM_EUNSUPPORTED, "agent must be firstfit or bestfit");
     if (n_envs == 0) return VMGYM_OK;
-    const int row_bytes = align_up(4 * L.D, 16);
-    const int per_warp = row_bytes + 2 * L.Vp + ((6 * L.Pp + 15) & ~15);
+    const int per_warp = act_smem_per_warp(L);
     int w = 4;
     while (w > 1 && (size_t)w * per_warp > 200 * 1024) w >>= 1;
-    const size_t smem = (size_t)w * per_warp;
+    const size_t smem = (size_t)SIZE_TABLE * 4 + (size_t)w * per_warp;
     if (smem > 227 * 1024) return fail(VMGYM_EUNSUPPORTED, "observation row does not fit in shared memory");
     const long long blocks = (n_envs + w - 1) / w;
     cudaStream_t st = (cudaStream_t)stream;

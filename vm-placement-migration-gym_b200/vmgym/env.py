@@ -52,7 +52,7 @@ class VmEnv:
     def step(self, action):
         action = np.ascontiguousarray(action, dtype=np.int64).reshape(1, -1)
         obs, reward, term, trunc, info = self.vec.step(torch.from_numpy(action).to(self.vec.device))
-        out = torch.cat([obs[0].double(), reward[:1], term[:1].double()]).cpu().numpy()   # one D2H
+        out = torch.cat([obs[0].double(), reward[:1], term[:1].double()]).cpu().numpy()   # one D2H (f32 -> f64 is exact)
         valid = self.vec.valid[0].cpu().numpy().astype(np.int64)
         info = {"action": action[0].copy(), "valid": valid}
         if self.eval_mode:

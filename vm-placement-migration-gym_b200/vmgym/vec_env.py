@@ -23,7 +23,10 @@ from . import _native as nv
 from .config import Config
 from .trace import EnvStreams, poisson_cdf_table, sample_numpy_traces, size_code_range
 
+import contextlib
+
 _TORCH_ACTION_DTYPES = {torch.uint8: nv.U8, torch.int16: nv.I16, torch.int64: nv.I64}
+_NULL_CTX = contextlib.nullcontext()
 
 
 class VecVmEnv:
@@ -46,16 +49,22 @@ class VecVmEnv:
         self.obs_dim = config.obs_dim
         self.WAIT_STATUS, self.NULL_STATUS = self.P, self.P + 1
         self._lib = nv.lib()
+        self._ccfg_cache = {}
+        self._out_cache = {}
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", self._dev_index)
         self._layout = nv.Layout()
         nv.check(self._lib.vmgym_get_layout(C.byref(self._ccfg()), C.byref(self._layout)), "vmgym_get_layout")
         L = self._layout
         self.place_dtype = torch.uint8 if L.place_bytes == 1 else torch.int16
         N = self.num_envs
-        with torch.cuda.device(self.device):
+        with self._on_device():
             self.state = torch.zeros((N, L.record_bytes), dtype=torch.uint8, device=self.device)
             self.obs = torch.zeros((N, self.obs_dim), dtype=torch.float32, device=self.device)
             self.reward = torch.zeros(N, dtype=torch.float64, device=self.device)
-            self.terminated = torch.zeros(N, dtype=torch.uint8, device=self.device)
+            self.terminated_u8 = torch.zeros(N, dtype=torch.uint8, device=self.device)
+            self.terminated = self.terminated_u8.view(torch.bool)      # same storage, reference dtype
+            self.truncated = torch.zeros(N, dtype=torch.bool, device=self.device)   # always False (env.py:102)
             self.valid = torch.zeros((N, self.V), dtype=torch.uint8, device=self.device)
             self.agent_action = torch.zeros((N, self.V), dtype=self.place_dtype, device=self.device)
             self.stats = torch.zeros((N, 8), dtype=torch.float64, device=self.device)
@@ -71,13 +80,23 @@ class VecVmEnv:
 
     # ------------------------------------------------------------------------------------------------
     def _ccfg(self) -> nv.Config:
-        c = self.config
-        limit = int(c.eval_steps) if self.eval_mode else int(c.training_steps)
-        return nv.Config(int(c.pms), int(c.vms), int(bool(c.allow_null_action)), nv.REWARD_IDS[c.reward_function],
-                         int(bool(c.cap_target_util)), limit, float(c.beta))
+        cached = self._ccfg_cache.get(self.eval_mode)
+        if cached is None:
+            c = self.config
+            limit = int(c.eval_steps) if self.eval_mode else int(c.training_steps)
+            cached = nv.Config(int(c.pms), int(c.vms), int(bool(c.allow_null_action)), nv.REWARD_IDS[c.reward_function],
+                               int(bool(c.cap_target_util)), limit, float(c.beta))
+            self._ccfg_cache[self.eval_mode] = cached
+        return cached
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _on_device(self):
+        """Context that makes self.device current (no-op when it already is: the common one-process-per-GPU case)."""
+        if torch.cuda.current_device() == self._dev_index:
+            return _NULL_CTX
+        return torch.cuda.device(self.device)
 
     def _build_views(self):
         L, P, V = self._layout, self.P, self.V
@@ -118,7 +137,7 @@ class VecVmEnv:
             self.seed(seed)
         rewind = 1
         d_seeds = None
-        with torch.cuda.device(self.device):
+        with self._on_device():
             if self.rng_mode == "numpy":
                 if not getattr(self, "_reseeded", False) and self._trace is not None:
                     pos = self._scalars_i32[:, 6:8].cpu().numpy().astype(np.int64)
@@ -155,10 +174,16 @@ class VecVmEnv:
         return self.obs, {}
 
     def _outputs(self, want_action=False, want_stats=False, want_obs=True, want_valid=True) -> nv.Outputs:
-        return nv.Outputs(d_obs=self.obs.data_ptr() if want_obs else None, d_reward=self.reward.data_ptr(),
-                          d_terminated=self.terminated.data_ptr(), d_valid=self.valid.data_ptr() if want_valid else None,
-                          d_action=self.agent_action.data_ptr() if want_action else None,
-                          d_stats=self.stats.data_ptr() if want_stats else None)
+        key = (want_action, want_stats, want_obs, want_valid)
+        out = self._out_cache.get(key)
+        if out is None:
+            out = nv.Outputs(d_obs=self.obs.data_ptr() if want_obs else None, d_reward=self.reward.data_ptr(),
+                             d_terminated=self.terminated_u8.data_ptr(),
+                             d_valid=self.valid.data_ptr() if want_valid else None,
+                             d_action=self.agent_action.data_ptr() if want_action else None,
+                             d_stats=self.stats.data_ptr() if want_stats else None)
+            self._out_cache[key] = out
+        return out
 
     def step(self, action, want_obs: bool = True, want_valid: bool = True):
         """env.py:66-103 for all envs.  `action`: [N, V] device tensor (uint8 / int16 / int64) or numpy int array."""
@@ -170,12 +195,11 @@ class VecVmEnv:
             action = action.to(torch.int64)
         action = action.contiguous()
         out = self._outputs(want_obs=want_obs, want_valid=want_valid)
-        with torch.cuda.device(self.device):
+        with self._on_device():
             nv.check(self._lib.vmgym_step(C.byref(self._ccfg()), self.state.data_ptr(), self.num_envs,
                                           C.byref(self._trace), action.data_ptr(), _TORCH_ACTION_DTYPES[action.dtype],
                                           C.byref(out), self._stream()), "vmgym_step")
-        info = {"action": action, "valid": self.valid}
-        return self.obs, self.reward, self.terminated.bool(), torch.zeros_like(self.terminated, dtype=torch.bool), info
+        return self.obs, self.reward, self.terminated, self.truncated, {"action": action, "valid": self.valid}
 
     def agent_step(self, agent: str, n_steps: int = 1, want_obs: bool = True, want_action: bool = True,
                    want_stats: bool = False, want_valid: bool = True, tiebreak: str | None = None):
@@ -183,14 +207,29 @@ class VecVmEnv:
         env.py:66-103).  Returns (obs, reward, terminated) of the last executed step."""
         kind = {"firstfit": nv.AGENT_FIRSTFIT, "bestfit": nv.AGENT_BESTFIT}[agent]
         out = self._outputs(want_action=want_action, want_stats=want_stats, want_obs=want_obs, want_valid=want_valid)
-        with torch.cuda.device(self.device):
+        with self._on_device():
             nv.check(self._lib.vmgym_agent_step(C.byref(self._ccfg()), self.state.data_ptr(), self.num_envs,
                                                 C.byref(self._trace), kind, nv.TIE_IDS[tiebreak or self.tiebreak],
                                                 int(n_steps), C.byref(out), self._stream()), "vmgym_agent_step")
-        return self.obs, self.reward, self.terminated.bool()
+        return self.obs, self.reward, self.terminated
+
+    def capture(self, fn, warmup: int = 2):
+        """Capture `fn` (a callable issuing env calls with fixed arguments, e.g. one fused agent step) into a CUDA
+        graph; returns the torch.cuda.CUDAGraph — `.replay()` re-issues the launches without host-side overhead."""
+        with self._on_device():
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    fn()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                fn()
+        return graph
 
     def observe(self):
-        with torch.cuda.device(self.device):
+        with self._on_device():
             nv.check(self._lib.vmgym_observe(C.byref(self._ccfg()), self.state.data_ptr(), self.num_envs,
                                              self.obs.data_ptr(), self._stream()), "vmgym_observe")
         return self.obs
@@ -199,7 +238,7 @@ class VecVmEnv:
         """env.py:45-53: bool[N, V, A], True = invalid (all False when `masked` is False)."""
         mask = torch.zeros((self.num_envs, self.V, self.action_dim), dtype=torch.uint8, device=self.device)
         if masked:
-            with torch.cuda.device(self.device):
+            with self._on_device():
                 nv.check(self._lib.vmgym_invalid_action_mask(C.byref(self._ccfg()), self.state.data_ptr(), self.num_envs,
                                                              mask.data_ptr(), self._stream()), "vmgym_invalid_action_mask")
         return mask.bool()
