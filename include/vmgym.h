@@ -79,8 +79,10 @@ typedef struct vmgym_env_scalars {
     int32_t total_requests, served_requests, dropped_requests, suspend_actions, place_actions;
     uint32_t arrival_pos;       /* arrivals consumed from the arrival stream (rng3, env.py:272) */
     uint32_t admission_pos;     /* entries consumed from the size/service streams (rng1,2,4; env.py:279-289) */
-    uint32_t status;            /* bit 0: pre-sampled trace exhausted (the reference would raise at env.py:282) */
-    uint32_t episode;
+    uint32_t status;            /* bit 0: pre-sampled trace exhausted (the reference would raise at env.py:282);
+                                   bit 1: no waiting VM fits any PM in the float32 view (lets fused agents skip act()) */
+    uint16_t n_waiting;         /* slots with vm_placement == P   (env.py:114) */
+    uint16_t n_empty;           /* slots with vm_placement == P+1 (env.py:273) */
     uint64_t seed;              /* Philox key of this env */
     int64_t cpu_code_sum;       /* 100 * total_cpu_requested (exact integer) */
     int64_t mem_code_sum;       /* 100 * total_memory_requested */

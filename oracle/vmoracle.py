@@ -57,6 +57,9 @@ def lib():
         L.vmo_rollout.restype = C.c_int64
         L.vmo_rollout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, f64p]
         L.vmo_get_state.argtypes = [C.c_void_p, i64p, f64p, f64p, f64p, f64p, i64p, i64p, i64p, f64p]
+        u64p = C.POINTER(C.c_uint64)
+        L.vmo_philox_trace.argtypes = [C.c_uint64, C.c_int64, C.c_int64, u64p, C.c_int, C.c_int, u64p, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, i32p, f64p, f64p, i64p]
         L.vmo_np_sum.restype = C.c_double
         L.vmo_np_sum.argtypes = [f64p, C.c_int64]
         _lib = L
@@ -265,3 +268,15 @@ def argsort_introsort_f32(keys):
 def np_sum(a):
     a = np.ascontiguousarray(a, dtype=np.float64)
     return lib().vmo_np_sum(_p(a, C.c_double), a.size)
+
+
+def philox_trace(seed, n_steps, n_adm, arr_kmin, arr_cdf, svc_kmin, svc_cdf, lo_code, hi_code) -> Trace:
+    """The draws the CUDA kernel makes in VMGYM_TRACE_PHILOX mode, as a pre-sampled Trace for the oracle env."""
+    arr_cdf = np.ascontiguousarray(arr_cdf, np.uint64)
+    svc_cdf = np.ascontiguousarray(svc_cdf, np.uint64)
+    arrivals = np.empty(n_steps, np.int32)
+    cpu, mem, svc = np.empty(n_adm), np.empty(n_adm), np.empty(n_adm, np.int64)
+    lib().vmo_philox_trace(int(seed), n_steps, n_adm, _p(arr_cdf, C.c_uint64), arr_cdf.size, int(arr_kmin),
+                           _p(svc_cdf, C.c_uint64), svc_cdf.size, int(svc_kmin), int(lo_code), int(hi_code),
+                           _p(arrivals, C.c_int32), _p(cpu, C.c_double), _p(mem, C.c_double), _p(svc, C.c_int64))
+    return Trace(arrivals, cpu, mem, svc)

@@ -204,6 +204,33 @@ def test_invalid_action_mask_matches_oracle():
     assert not vec.get_invalid_action_mask(False).any()
 
 
+@pytest.mark.parametrize("shape,n_envs,steps", [("s100", 6, 900), ("s10", 12, 390), ("wide", 3, 300)])
+def test_philox_mode_matches_oracle_on_same_draws(shape, n_envs, steps):
+    """rng='philox': the kernel's in-flight Philox/inverse-CDF draws == the host restatement of the same
+    counters fed to the oracle env as a pre-sampled trace (arrivals, sizes, service lengths, cursors)."""
+    from vmgym import VecVmEnv
+    kw = SHAPES[shape]
+    seeds = np.array([3, 2**31 + 5, 2**40 + 1, 17, 99, 12345678901, 8, 21, 34, 55, 89, 144][:n_envs], dtype=np.int64)
+    vec = VecVmEnv(_cfg(**kw), n_envs, rng="philox", seeds=seeds)
+    ka, ta, ks, ts, lo, hi = vec.philox_tables
+    oracles = []
+    for s in seeds:
+        o = vo.OracleVmEnv(vo.OracleConfig(**dict(kw, seed=0)), trace_steps=4, trace_adm=4)
+        o.reset(trace=vo.philox_trace(int(s), steps + 4, 40000, ka, ta, ks, ts, lo, hi))
+        oracles.append(o)
+    P, V = kw["pms"], kw["vms"]
+    for t0 in range(0, steps, 130):
+        n = min(130, steps - t0)
+        vec.agent_step("firstfit", n_steps=n)
+        for o in oracles:
+            o.rollout(vo.AGENT_FIRSTFIT, n)
+        _compare_state(vec, oracles, t0 + n)
+    obs = vec.obs.cpu().numpy()
+    for i, o in enumerate(oracles):
+        assert obs[i].tobytes() == o._obs().tobytes()
+    del P, V
+
+
 def test_full_size_invariants_4096_envs():
     """BASELINE config 2 size (4096 envs x 100 PMs): size-independent properties after a long fused rollout."""
     from vmgym import VecVmEnv

@@ -13,6 +13,7 @@ namespace vmgym {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int SIZE_TABLE = 128;   // size codes are hundredths 0..100 (7 bits)
+constexpr int ARR_CDF_SMEM = 64;  // arrival inverse-CDF thresholds kept in shared memory when the table is this small
 
 struct DevLayout {
     int P, V, A, Pp, Vp, D;

@@ -56,7 +56,7 @@ static int make_layout(const vmgym_config* c, DevLayout* L, vmgym_layout* pub)
     l.sm_fit = l.sm_tmp + tmp_bytes;                       // u32 fitm[128] | u16 cap[Pp]
     l.sm_bar = l.sm_fit + 512 + align_up(2 * l.Pp, 16);
     l.sm_stride = align_up(l.sm_bar + 16, 128);
-    l.sm_tables = SIZE_TABLE * 8 + SIZE_TABLE * 4;
+    l.sm_tables = SIZE_TABLE * 8 + SIZE_TABLE * 4 + ARR_CDF_SMEM * 8;
     if (L) *L = l;
     if (pub) {
         pub->record_bytes = l.rec_bytes; pub->pms_padded = l.Pp; pub->vms_padded = l.Vp; pub->place_bytes = pb;
@@ -97,6 +97,7 @@ struct Env {
     uint16_t* cap;                     // per-PM capacity codes of the float32 view: cpu | mem << 8
     unsigned* fitm;                    // fit table over cpu codes (see rebuild_fit_table)
     const double* sz64; const float* sz32;   // code -> k/100.0 and (float)(k/100.0)
+    const uint64_t* arr_cdf;           // arrival inverse-CDF thresholds (shared-memory copy when small)
     int P, V, lane;
 };
 
@@ -191,13 +192,10 @@ __device__ __noinline__ void introsort_argsort(const float* v, uint16_t* t, int 
 // largest size code k in [0,100] with x + sz32[k] <= 1.0f (monotone in k because fp32 rounding is monotone)
 __device__ __forceinline__ int max_code(const float* sz32, float x)
 {
-    int lo = 0, hi = 101;
-#pragma unroll
-    for (int it = 0; it < 7; it++) {
-        const int mid = (lo + hi) >> 1;
-        if (x + sz32[mid] <= 1.0f) lo = mid; else hi = mid;
-    }
-    return lo;
+    int k = min(100, max(0, (int)((1.0f - x) * 100.0f)));      // estimate, then exact correction (usually 1-2 probes)
+    while (k < 100 && x + sz32[k + 1] <= 1.0f) k++;
+    while (k > 0 && x + sz32[k] > 1.0f) k--;
+    return k;
 }
 
 // fitm[c] = 1 + max{ mem-capacity code of PM p : cpu-capacity code of p >= c }, 0 if no PM takes cpu code c.
@@ -236,10 +234,11 @@ __device__ __forceinline__ void rebuild_fit_table(Env<PT>& e)
 // as the agent sees them.  Writes e.act[v] for the waiting VMs it places (others keep their placement).
 // ---------------------------------------------------------------------------------------------------
 template <typename PT, class FW, class FK, class FL, class FC, class FM>
-__device__ __forceinline__ void agent_act(Env<PT>& e, int agent, int tiebreak, FW waiting, FK ccode, FL mcode, FC c32of,
-                                          FM m32of)
+__device__ __forceinline__ int agent_act(Env<PT>& e, int agent, int tiebreak, FW waiting, FK ccode, FL mcode, FC c32of,
+                                         FM m32of)
 {
     const int P = e.P, V = e.V, lane = e.lane;
+    int n_found = 0;
     for (int p = lane; p < P; p += 32)
         e.cap[p] = (uint16_t)(max_code(e.sz32, e.cpu32[p]) | (max_code(e.sz32, e.mem32[p]) << 8));
     rebuild_fit_table(e);
@@ -315,6 +314,7 @@ __device__ __forceinline__ void agent_act(Env<PT>& e, int agent, int tiebreak, F
                 }
             }
             if (found >= 0) {
+                n_found++;
                 if (lane == 0) e.act[vv] = (uint16_t)found;
                 __syncwarp();
                 rebuild_fit_table(e);              // capacities shrank: later candidates of this chunk are re-tested
@@ -325,6 +325,7 @@ __device__ __forceinline__ void agent_act(Env<PT>& e, int agent, int tiebreak, F
         }
     }
     __syncwarp();
+    return n_found;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -371,88 +372,150 @@ __device__ __noinline__ double reward_kl(const double* cpu, const double* mem, i
 // ---------------------------------------------------------------------------------------------------
 // One env.step on the shared-memory record.  Returns the reward (uniform across lanes).
 // ---------------------------------------------------------------------------------------------------
-struct StepResult { double reward; int terminated; int rejected; int waiting, arrived; };
+struct StepResult { double reward; int terminated; int rejected; int waiting, arrived; int changed; };
 
+constexpr uint32_t STATUS_EXHAUSTED = 1u;   // pre-sampled trace ran out (the reference would raise, env.py:282)
+constexpr uint32_t STATUS_ACT_CLEAN = 2u;   // no waiting VM fits on any PM in the float32 view (see step_kernel)
+
+// ---------------------------------------------------------------------------------------------------
+// One env.step on the shared-memory record.  `have_actions` == false means "every action equals the current
+// placement" (a fused agent that proposed nothing): phase 1 is skipped and every action is valid.
+// The per-env counters n_waiting / n_empty are maintained incrementally so the common quiet step (nothing
+// placed, nothing departs, nothing admitted) costs only the service countdown, one arrival draw and the outputs.
+// ---------------------------------------------------------------------------------------------------
 template <typename PT>
-__device__ __forceinline__ StepResult env_step(Env<PT>& e, const StepParams& p, long long env_id, uint8_t* valid_g)
+__device__ __forceinline__ StepResult env_step(Env<PT>& e, const StepParams& p, long long env_id, uint8_t* valid_g,
+                                               bool have_actions)
 {
     const int P = e.P, V = e.V, lane = e.lane;
     vmgym_env_scalars* sc = e.sc;
     int n_place = 0, n_susp = 0, rejected = 0;
 
     // ---- 1. apply actions in VM-index order, each seeing earlier updates (env.py:69-87, validate :35-42) ----
-    for (int c0 = 0; c0 < V; c0 += 32) {
-        const int v = c0 + lane;
-        const int a = v < V ? (int)e.act[v] : 0;
-        const int cur = v < V ? (int)e.place[v] : 0;
-        const bool diff = v < V && a != cur;
-        unsigned m = __ballot_sync(FULL, diff);
-        unsigned okbits = 0;
-        while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            const int av = __shfl_sync(FULL, a, b), cv = __shfl_sync(FULL, cur, b), vv = c0 + b;
-            bool ok = false;
-            if (cv == P) {                                   // waiting VM: place iff it fits in fp64 (:38-39,55-56)
-                if ((unsigned)av < (unsigned)P) {
-                    const double nc = e.cpu[av] + e.sz64[e.cpuc[vv] & 0x7f];
-                    const double nm = e.mem[av] + e.sz64[e.memc[vv]];
-                    if (nc <= 1.0 && nm <= 1.0) {
+    if (have_actions) {
+        for (int c0 = 0; c0 < V; c0 += 32) {
+            const int v = c0 + lane;
+            const int a = v < V ? (int)e.act[v] : 0;
+            const int cur = v < V ? (int)e.place[v] : 0;
+            const bool diff = v < V && a != cur;
+            unsigned m = __ballot_sync(FULL, diff);
+            unsigned okbits = 0;
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const int av = __shfl_sync(FULL, a, b), cv = __shfl_sync(FULL, cur, b), vv = c0 + b;
+                bool ok = false;
+                if (cv == P) {                                   // waiting VM: place iff it fits in fp64 (:38-39,55-56)
+                    if ((unsigned)av < (unsigned)P) {
+                        const double nc = e.cpu[av] + e.sz64[e.cpuc[vv] & 0x7f];
+                        const double nm = e.mem[av] + e.sz64[e.memc[vv]];
+                        if (nc <= 1.0 && nm <= 1.0) {
+                            ok = true;
+                            n_place++;
+                            __syncwarp();
+                            if (lane == 0) { e.cpu[av] = nc; e.mem[av] = nm; e.place[vv] = (PT)av; e.cpuc[vv] &= 0x7f; }  // :82-85
+                        }
+                    }
+                } else if (cv < P) {                             // running VM: only suspend is legal (:40-41,78-81)
+                    if (av == P) {
                         ok = true;
-                        n_place++;
+                        n_susp++;
+                        const double nc = e.cpu[cv] - e.sz64[e.cpuc[vv] & 0x7f];
+                        const double nm = e.mem[cv] - e.sz64[e.memc[vv]];
                         __syncwarp();
-                        if (lane == 0) { e.cpu[av] = nc; e.mem[av] = nm; e.place[vv] = (PT)av; e.cpuc[vv] &= 0x7f; }  // :82-85
+                        if (lane == 0) { e.cpu[cv] = nc; e.mem[cv] = nm; e.place[vv] = (PT)P; e.cpuc[vv] |= 0x80; }
                     }
                 }
-            } else if (cv < P) {                             // running VM: only suspend is legal (:40-41,78-81)
-                if (av == P) {
-                    ok = true;
-                    n_susp++;
-                    const double nc = e.cpu[cv] - e.sz64[e.cpuc[vv] & 0x7f];
-                    const double nm = e.mem[cv] - e.sz64[e.memc[vv]];
-                    __syncwarp();
-                    if (lane == 0) { e.cpu[cv] = nc; e.mem[cv] = nm; e.place[vv] = (PT)P; e.cpuc[vv] |= 0x80; }
-                }
+                __syncwarp();
+                okbits |= ok ? (1u << b) : 0u;
             }
-            __syncwarp();
-            okbits |= ok ? (1u << b) : 0u;
+            const bool okv = !diff || ((okbits >> lane) & 1u);
+            rejected += __popc(__ballot_sync(FULL, v < V && !okv));
+            if (valid_g && v < V) valid_g[v] = okv ? 1 : 0;
         }
-        const bool okv = !diff || ((okbits >> lane) & 1u);
-        rejected += __popc(__ballot_sync(FULL, v < V && !okv));
-        if (valid_g && v < V) valid_g[v] = okv ? 1 : 0;
+    } else if (valid_g) {
+        for (int v = lane; v < V; v += 32) valid_g[v] = 1;
     }
 
     // ---- 2+3. service countdown and departures in VM-index order (_run_vms, env.py:244-265) ----
     int served = 0;
-    for (int c0 = 0; c0 < V; c0 += 32) {
-        const int v = c0 + lane;
-        const int pl = v < V ? (int)e.place[v] : P + 1;
-        int r = v < V ? (int)e.rem[v] : 0;
-        const bool running = pl < P;
-        if (running && r > 0) { r -= 1; e.rem[v] = (uint16_t)r; }
-        const bool term = running && r == 0;
-        unsigned m = __ballot_sync(FULL, term);
-        served += __popc(m);
-        if (m) {
-            if (lane == 0) {
-                unsigned mm = m;
-                while (mm) {
-                    const int b = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    const int vv = c0 + b, pm = (int)e.place[vv];
-                    e.cpu[pm] -= e.sz64[e.cpuc[vv] & 0x7f];
-                    e.mem[pm] -= e.sz64[e.memc[vv]];
+    if (sizeof(PT) == 1) {
+        // 4 slots per lane: placement bytes as one u32, remaining runtimes as 4 x u16 (padding slots are empty)
+        const uint32_t P4 = (uint32_t)P * 0x01010101u;
+        const uint32_t* pl4 = reinterpret_cast<const uint32_t*>(e.place);
+        uint2* rem4 = reinterpret_cast<uint2*>(e.rem);
+        const int groups = (V + 3) >> 2;
+        for (int g0 = 0; g0 < groups; g0 += 32) {
+            const int g = g0 + lane;
+            unsigned term4 = 0;
+            if (g < groups) {
+                const uint32_t run = __vcmpltu4(pl4[g], P4);            // 0xff per running slot
+                if (run) {
+                    uint2 r = rem4[g];
+                    const uint32_t dlo = (run & 1u) | ((run & 0x100u) << 8), dhi = ((run >> 16) & 1u) | ((run >> 8) & 0x10000u);
+                    r.x = __vsubus2(r.x, dlo);                           // if remaining > 0: remaining -= 1 (:245-247)
+                    r.y = __vsubus2(r.y, dhi);
+                    rem4[g] = r;
+                    const uint32_t zlo = __vcmpeq2(r.x, 0u), zhi = __vcmpeq2(r.y, 0u);
+                    term4 = ((zlo & 1u) | ((zlo >> 15) & 2u) | ((zhi & 1u) << 2) | ((zhi >> 13) & 8u)) &
+                            ((run & 1u) | ((run >> 7) & 2u) | ((run >> 14) & 4u) | ((run >> 21) & 8u));
                 }
             }
-            __syncwarp();
-            if (term) { e.place[v] = (PT)(P + 1); e.cpuc[v] = 0; e.memc[v] = 0; e.rem[v] = 0; }
+            unsigned m = __ballot_sync(FULL, term4 != 0);
+            if (m) {                                                      // rare: some VM finished (:248-265)
+                __syncwarp();
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    unsigned t4 = __shfl_sync(FULL, term4, b);
+                    served += __popc(t4);
+                    if (lane == 0) {
+                        while (t4) {
+                            const int j = __ffs(t4) - 1;
+                            t4 &= t4 - 1;
+                            const int vv = 4 * (g0 + b) + j, pm = (int)e.place[vv];
+                            e.cpu[pm] -= e.sz64[e.cpuc[vv] & 0x7f];
+                            e.mem[pm] -= e.sz64[e.memc[vv]];
+                            e.place[vv] = (PT)(P + 1); e.cpuc[vv] = 0; e.memc[vv] = 0; e.rem[vv] = 0;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        for (int c0 = 0; c0 < V; c0 += 32) {
+            const int v = c0 + lane;
+            const int pl = v < V ? (int)e.place[v] : P + 1;
+            int r = v < V ? (int)e.rem[v] : 0;
+            const bool running = pl < P;
+            if (running && r > 0) { r -= 1; e.rem[v] = (uint16_t)r; }
+            const bool term = running && r == 0;
+            unsigned m = __ballot_sync(FULL, term);
+            served += __popc(m);
+            if (m) {
+                if (lane == 0) {
+                    unsigned mm = m;
+                    while (mm) {
+                        const int b = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        const int vv = c0 + b, pm = (int)e.place[vv];
+                        e.cpu[pm] -= e.sz64[e.cpuc[vv] & 0x7f];
+                        e.mem[pm] -= e.sz64[e.memc[vv]];
+                    }
+                }
+                __syncwarp();
+                if (term) { e.place[v] = (PT)(P + 1); e.cpuc[v] = 0; e.memc[v] = 0; e.rem[v] = 0; }
+            }
         }
     }
     __syncwarp();
-    // ---- 4. clamp (env.py:267-268) ----
-    for (int q = lane; q < P; q += 32) {
-        if (e.cpu[q] < 1e-7) e.cpu[q] = 0.0;
-        if (e.mem[q] < 1e-7) e.mem[q] = 0.0;
+    // ---- 4. clamp (env.py:267-268): values only shrink when something was subtracted this step ----
+    if (served > 0 || n_susp > 0) {
+        for (int q = lane; q < P; q += 32) {
+            if (e.cpu[q] < 1e-7) e.cpu[q] = 0.0;
+            if (e.mem[q] < 1e-7) e.mem[q] = 0.0;
+        }
     }
 
     // ---- 5. arrivals (_accept_vm_requests, env.py:271-293) ----
@@ -463,8 +526,9 @@ __device__ __forceinline__ StepResult env_step(Env<PT>& e, const StepParams& p, 
     } else {
         const Philox4 r = philox4x32_10(sc->arrival_pos, 0u, 1u, 0u, (uint32_t)sc->seed, (uint32_t)(sc->seed >> 32));
         const uint64_t u = ((uint64_t)r.x << 32) | r.y;
+        const uint64_t* cdf = e.arr_cdf;            // shared-memory copy when it fits, else the global table
         int lo = 0, hi = tr.arrival_cdf_len;       // first i with cdf[i] > u
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (tr.d_arrival_cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
         n_arr = tr.arrival_kmin + min(lo, tr.arrival_cdf_len - 1);
     }
     int exhausted = (tr.mode == VMGYM_TRACE_PRESAMPLED && (long long)sc->arrival_pos >= tr.arrivals_len) ? 1 : 0;
@@ -473,9 +537,10 @@ __device__ __forceinline__ StepResult env_step(Env<PT>& e, const StepParams& p, 
         const long long left = tr.admissions_len - (long long)sc->admission_pos;
         if ((long long)quota > left) { quota = (int)(left > 0 ? left : 0); exhausted = 1; }
     }
+    const int n_empty0 = (int)sc->n_empty + served;            // empty slots before admission
     int admitted = 0;
     long long csum = 0, msum = 0;
-    if (quota > 0) {
+    if (quota > 0 && n_empty0 > 0) {
         for (int c0 = 0; c0 < V && admitted < quota; c0 += 32) {
             const int v = c0 + lane;
             const bool empty = v < V && (int)e.place[v] == P + 1;
@@ -506,35 +571,40 @@ __device__ __forceinline__ StepResult env_step(Env<PT>& e, const StepParams& p, 
         admitted = min(admitted, quota);
         csum = (long long)__reduce_add_sync(FULL, (unsigned)csum);
         msum = (long long)__reduce_add_sync(FULL, (unsigned)msum);
+        __syncwarp();
     }
-    __syncwarp();
 
-    // ---- 6. metrics (env.py:112-121) ----
-    int waiting = 0, arrived = 0;
-    const bool need_kl = p.reward_fn == VMGYM_REWARD_KL;
-    uint8_t* ex_cc = e.tmp;
-    uint8_t* ex_mc = e.tmp + ((V + 15) & ~15);
-    for (int c0 = 0; c0 < V; c0 += 32) {
-        const int v = c0 + lane;
-        const int pl = v < V ? (int)e.place[v] : P + 1;
-        const unsigned mw = __ballot_sync(FULL, pl == P);
-        const unsigned mx = __ballot_sync(FULL, pl <= P);
-        if (need_kl && pl <= P) {                              // compacted vm_cpu[existing], vm_memory[existing]
-            const int pos = arrived + __popc(mx & ((1u << lane) - 1u));
-            ex_cc[pos] = e.cpuc[v] & 0x7f;
-            ex_mc[pos] = e.memc[v];
-        }
-        waiting += __popc(mw);
-        arrived += __popc(mx);
-    }
-    __syncwarp();
+    // ---- 6. metrics (env.py:112-121) from the incrementally maintained slot counters ----
+    const int n_empty = n_empty0 - admitted;
+    const int waiting = (int)sc->n_waiting - n_place + n_susp + admitted;
+    const int arrived = V - n_empty;
 
     // ---- 7. reward (env.py:123-156) ----
     double reward = 0.0;
     if (arrived > 0) {
-        if (p.reward_fn == VMGYM_REWARD_WR) reward = -((double)waiting / (double)arrived);
-        else if (p.reward_fn == VMGYM_REWARD_UT) reward = reward_ut(e.cpu, e.mem, P, p.beta);
-        else reward = reward_kl(e.cpu, e.mem, P, ex_cc, ex_mc, arrived, e.sz64, p.cap_target);
+        if (p.reward_fn == VMGYM_REWARD_WR) {
+            reward = -((double)waiting / (double)arrived);
+        } else if (p.reward_fn == VMGYM_REWARD_UT) {
+            reward = reward_ut(e.cpu, e.mem, P, p.beta);
+        } else {
+            // compacted vm_cpu[existing], vm_memory[existing] in slot order (the reference's boolean indexing)
+            uint8_t* ex_cc = e.tmp;
+            uint8_t* ex_mc = e.tmp + ((V + 15) & ~15);
+            int pos0 = 0;
+            for (int c0 = 0; c0 < V; c0 += 32) {
+                const int v = c0 + lane;
+                const bool ex = v < V && (int)e.place[v] <= P;
+                const unsigned mx = __ballot_sync(FULL, ex);
+                if (ex) {
+                    const int pos = pos0 + __popc(mx & ((1u << lane) - 1u));
+                    ex_cc[pos] = e.cpuc[v] & 0x7f;
+                    ex_mc[pos] = e.memc[v];
+                }
+                pos0 += __popc(mx);
+            }
+            __syncwarp();
+            reward = reward_kl(e.cpu, e.mem, P, ex_cc, ex_mc, arrived, e.sz64, p.cap_target);
+        }
     }
 
     // ---- 9. termination flag, counters, clock (env.py:160-163,101) ----
@@ -549,6 +619,8 @@ __device__ __forceinline__ StepResult env_step(Env<PT>& e, const StepParams& p, 
         sc->arrival_pos += 1;
         sc->admission_pos += (uint32_t)admitted;
         sc->status |= (uint32_t)exhausted;
+        sc->n_waiting = (uint16_t)waiting;
+        sc->n_empty = (uint16_t)n_empty;
         sc->cpu_code_sum += csum;
         sc->mem_code_sum += msum;
         sc->episode_return += reward;
@@ -558,6 +630,7 @@ __device__ __forceinline__ StepResult env_step(Env<PT>& e, const StepParams& p, 
     __syncwarp();
     StepResult res;
     res.reward = reward; res.terminated = terminated; res.rejected = rejected; res.waiting = waiting; res.arrived = arrived;
+    res.changed = n_place + n_susp + served + admitted;      // anything that can change which waiting VMs fit
     return res;
 }
 
@@ -566,6 +639,28 @@ template <typename PT>
 __device__ __forceinline__ void write_obs(const Env<PT>& e, float* __restrict__ o)
 {
     const int P = e.P, V = e.V;
+    if (sizeof(PT) == 1 && (V & 3) == 0 && (P & 3) == 0) {
+        // 128-bit stores: the row and its five segments are 16-byte aligned when V and P are multiples of 4
+        float4* o4 = reinterpret_cast<float4*>(o);
+        const uint32_t* pl4 = reinterpret_cast<const uint32_t*>(e.place);
+        const uint32_t* cc4 = reinterpret_cast<const uint32_t*>(e.cpuc);
+        const uint32_t* mc4 = reinterpret_cast<const uint32_t*>(e.memc);
+        const int vg = V >> 2, pg = P >> 2;
+        for (int g = e.lane; g < vg; g += 32) {
+            const uint32_t a = pl4[g], c = cc4[g] & 0x7f7f7f7fu, m = mc4[g];
+            o4[g] = make_float4((float)(a & 0xff), (float)((a >> 8) & 0xff), (float)((a >> 16) & 0xff), (float)(a >> 24));
+            o4[vg + g] = make_float4(e.sz32[c & 0xff], e.sz32[(c >> 8) & 0xff], e.sz32[(c >> 16) & 0xff], e.sz32[c >> 24]);
+            o4[2 * vg + g] = make_float4(e.sz32[m & 0xff], e.sz32[(m >> 8) & 0xff], e.sz32[(m >> 16) & 0xff], e.sz32[m >> 24]);
+        }
+        const double2* c2 = reinterpret_cast<const double2*>(e.cpu);
+        const double2* m2 = reinterpret_cast<const double2*>(e.mem);
+        for (int g = e.lane; g < pg; g += 32) {
+            const double2 a = c2[2 * g], b = c2[2 * g + 1], c = m2[2 * g], d = m2[2 * g + 1];
+            o4[3 * vg + g] = make_float4((float)a.x, (float)a.y, (float)b.x, (float)b.y);
+            o4[3 * vg + pg + g] = make_float4((float)c.x, (float)c.y, (float)d.x, (float)d.y);
+        }
+        return;
+    }
     for (int v = e.lane; v < V; v += 32) o[v] = (float)e.place[v];
     for (int v = e.lane; v < V; v += 32) o[V + v] = e.sz32[e.cpuc[v] & 0x7f];
     for (int v = e.lane; v < V; v += 32) o[2 * V + v] = e.sz32[e.memc[v]];
@@ -631,12 +726,17 @@ __global__ void __launch_bounds__(256, 4) step_kernel(const StepParams p)
     unsigned char* base = smem + L.sm_tables + (size_t)warp * L.sm_stride;
     uint64_t* bar = reinterpret_cast<uint64_t*>(base + L.sm_bar);
     fill_tables(sz64, sz32);
+    uint64_t* arr_cdf_s = reinterpret_cast<uint64_t*>(smem + SIZE_TABLE * 12);
+    const bool cdf_in_smem = p.tr.mode == VMGYM_TRACE_PHILOX && p.tr.arrival_cdf_len <= ARR_CDF_SMEM;
+    if (cdf_in_smem)
+        for (int k = threadIdx.x; k < p.tr.arrival_cdf_len; k += blockDim.x) arr_cdf_s[k] = p.tr.d_arrival_cdf[k];
     const bool BULK = p.use_bulk != 0;
     if (BULK && lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
     __syncthreads();
 
     Env<PT> e;
     bind_env(e, base, L, sz64, sz32, lane);
+    e.arr_cdf = cdf_in_smem ? arr_cdf_s : p.tr.d_arrival_cdf;
     uint32_t phase = 0;
     const long long stride = (long long)gridDim.x * wpc;
     for (long long env = (long long)blockIdx.x * wpc + warp; env < p.n_envs; env += stride) {
@@ -658,27 +758,43 @@ __global__ void __launch_bounds__(256, 4) step_kernel(const StepParams p)
 
         uint8_t* valid_g = p.out.d_valid ? p.out.d_valid + env * (long long)L.V : nullptr;
         StepResult res;
-        res.reward = 0.0; res.terminated = 0; res.rejected = 0; res.waiting = 0; res.arrived = 0;
+        res.reward = 0.0; res.terminated = 0; res.rejected = 0; res.waiting = 0; res.arrived = 0; res.changed = 0;
         double st_drop = 0, st_wr = 0, st_mc = 0, st_vc = 0, st_mm = 0, st_vm = 0, st_rej = 0, st_n = 0;
+        bool act_valid = false;            // e.act[] holds this step's action vector
+        // STATUS_ACT_CLEAN: "no waiting VM fits on any PM in the float32 view".  It is established by a fused
+        // agent evaluation that places nothing and stays true until a placement, suspension, departure or
+        // admission changes the PM loads or the set of waiting VMs; while it holds, act() is skipped (the agent
+        // would return the current placement unchanged, firstfit.py:31-37 / bestfit.py:31-39).
+        bool clean = (e.sc->status & STATUS_ACT_CLEAN) != 0;
         for (int s = 0; s < p.n_steps; s++) {
+            bool have_actions;
             if (p.agent != VMGYM_AGENT_NONE) {
-                // the agent sees the float32 observation of the current state (env.py:296)
-                for (int q = lane; q < L.P; q += 32) { e.cpu32[q] = (float)e.cpu[q]; e.mem32[q] = (float)e.mem[q]; }
-                for (int v = lane; v < L.V; v += 32) e.act[v] = (uint16_t)e.place[v];
-                __syncwarp();
-                const PT* place = e.place; const uint8_t* cpuc = e.cpuc; const uint8_t* memc = e.memc;
-                const float* t32 = sz32;
-                const int P = L.P;
-                agent_act(e, p.agent, p.tiebreak, [=](int v) { return (int)place[v] == P; },
-                          [=](int v) { return (int)(cpuc[v] & 0x7f); }, [=](int v) { return (int)memc[v]; },
-                          [=](int v) { return t32[cpuc[v] & 0x7f]; }, [=](int v) { return t32[memc[v]]; });
+                int n_found = 0;
+                act_valid = false;
+                if (!clean) {
+                    // the agent sees the float32 observation of the current state (env.py:296)
+                    for (int q = lane; q < L.P; q += 32) { e.cpu32[q] = (float)e.cpu[q]; e.mem32[q] = (float)e.mem[q]; }
+                    for (int v = lane; v < L.V; v += 32) e.act[v] = (uint16_t)e.place[v];
+                    __syncwarp();
+                    const PT* place = e.place; const uint8_t* cpuc = e.cpuc; const uint8_t* memc = e.memc;
+                    const float* t32 = sz32;
+                    const int P = L.P;
+                    n_found = agent_act(e, p.agent, p.tiebreak, [=](int v) { return (int)place[v] == P; },
+                                        [=](int v) { return (int)(cpuc[v] & 0x7f); }, [=](int v) { return (int)memc[v]; },
+                                        [=](int v) { return t32[cpuc[v] & 0x7f]; }, [=](int v) { return t32[memc[v]]; });
+                    act_valid = true;
+                    clean = (n_found == 0);
+                }
+                have_actions = n_found > 0;
             } else {
                 const int adt = p.action_dtype;
                 const unsigned char* arow = reinterpret_cast<const unsigned char*>(p.action) + env * (long long)L.V * dtype_bytes(adt);
                 for (int v = lane; v < L.V; v += 32) e.act[v] = (uint16_t)load_action(arow, adt, v);
                 __syncwarp();
+                have_actions = true;
             }
-            res = env_step(e, p, env, valid_g);
+            res = env_step(e, p, env, valid_g, have_actions);
+            if (res.changed) clean = false;
             if (p.out.d_stats) {
                 // running sums for the eval summary (record.py:98-134, exp_performance.py:104-113)
                 double sc_ = 0, sm_ = 0;
@@ -702,9 +818,10 @@ __global__ void __launch_bounds__(256, 4) step_kernel(const StepParams p)
         if (p.out.d_obs) write_obs(e, p.out.d_obs + env * (long long)L.D);
         if (p.out.d_action && p.agent != VMGYM_AGENT_NONE) {
             PT* ao = reinterpret_cast<PT*>(p.out.d_action) + env * (long long)L.V;
-            for (int v = lane; v < L.V; v += 32) ao[v] = (PT)e.act[v];
+            for (int v = lane; v < L.V; v += 32) ao[v] = act_valid ? (PT)e.act[v] : e.place[v];
         }
         if (lane == 0) {
+            e.sc->status = (e.sc->status & ~STATUS_ACT_CLEAN) | (clean ? STATUS_ACT_CLEAN : 0u);
             if (p.out.d_reward) p.out.d_reward[env] = res.reward;
             if (p.out.d_terminated) p.out.d_terminated[env] = (uint8_t)res.terminated;
             if (p.out.d_stats) {
@@ -753,14 +870,15 @@ __global__ void reset_kernel(DevLayout L, unsigned char* state, long long n_envs
     for (int i = lane; i < L.rec_bytes / 16; i += 32) r4[i] = make_uint4(0, 0, 0, 0);
     __syncwarp();
     PT* place = reinterpret_cast<PT*>(rec + L.off_place);
-    for (int v = lane; v < L.V; v += 32) place[v] = (PT)(L.P + 1);       // env.py:187
+    for (int v = lane; v < L.Vp; v += 32) place[v] = (PT)(L.P + 1);      // env.py:187 (padding slots stay empty forever)
     if (lane == 0) {
         sc->timestep = 1;                                                 // env.py:197
-        sc->episode = keep.episode + 1;
+        sc->n_waiting = 0;
+        sc->n_empty = (uint16_t)L.V;
         sc->seed = seeds ? seeds[env] : keep.seed;
         sc->arrival_pos = rewind ? 0u : keep.arrival_pos;
         sc->admission_pos = rewind ? 0u : keep.admission_pos;
-        sc->status = rewind ? 0u : keep.status;
+        sc->status = rewind ? 0u : (keep.status & STATUS_EXHAUSTED);
     }
     if (obs) {
         float* o = obs + env * (long long)L.D;
@@ -901,12 +1019,13 @@ static int sm_count()
     return g_sm_count;
 }
 
-// warps per CTA: keep >= ~4 CTAs of work per SM when the batch is small, up to 8 warps when it is large.
+// warps per CTA: keep >= ~6 CTAs of work per SM when the batch is small (balance across the 148 SMs), up to 8
+// warps when it is large.
 static int pick_warps(long long n_envs, int smem_per_warp, int smem_fixed)
 {
     if (g_warps_per_cta > 0) return g_warps_per_cta;
     int w = 8;
-    while (w > 1 && n_envs < (long long)sm_count() * w * 2) w >>= 1;
+    while (w > 1 && n_envs < (long long)sm_count() * w * 6) w >>= 1;
     while (w > 1 && smem_fixed + w * smem_per_warp > 200 * 1024) w >>= 1;
     return w;
 }

@@ -56,7 +56,7 @@ class Outputs(C.Structure):
 
 # offsets inside struct vmgym_env_scalars (include/vmgym.h)
 SCALARS_I32 = ["timestep", "total_requests", "served_requests", "dropped_requests", "suspend_actions", "place_actions",
-               "arrival_pos", "admission_pos", "status", "episode"]
+               "arrival_pos", "admission_pos", "status", "slot_counts"]   # slot_counts = n_waiting | n_empty << 16
 SCALARS_BYTES = 80
 
 EXPORTS = ["vmgym_last_error", "vmgym_abi_version", "vmgym_get_layout", "vmgym_reset", "vmgym_step",
