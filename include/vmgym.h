@@ -80,7 +80,9 @@ typedef struct vmgym_env_scalars {
     uint32_t arrival_pos;       /* arrivals consumed from the arrival stream (rng3, env.py:272) */
     uint32_t admission_pos;     /* entries consumed from the size/service streams (rng1,2,4; env.py:279-289) */
     uint32_t status;            /* bit 0: pre-sampled trace exhausted (the reference would raise at env.py:282);
-                                   bit 1: no waiting VM fits any PM in the float32 view (lets fused agents skip act()) */
+                                   bit 1: QUIET — a fused agent's act()+apply would change nothing (skipped while set);
+                                   bits 8-15: agent/tiebreak that established QUIET (0 = any); bits 16-31: rejected
+                                   proposals per quiet step */
     uint16_t n_waiting;         /* slots with vm_placement == P   (env.py:114) */
     uint16_t n_empty;           /* slots with vm_placement == P+1 (env.py:273) */
     uint64_t seed;              /* Philox key of this env */

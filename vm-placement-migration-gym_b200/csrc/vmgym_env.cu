@@ -375,7 +375,9 @@ __device__ __noinline__ double reward_kl(const double* cpu, const double* mem, i
 struct StepResult { double reward; int terminated; int rejected; int waiting, arrived; int changed; };
 
 constexpr uint32_t STATUS_EXHAUSTED = 1u;   // pre-sampled trace ran out (the reference would raise, env.py:282)
-constexpr uint32_t STATUS_ACT_CLEAN = 2u;   // no waiting VM fits on any PM in the float32 view (see step_kernel)
+constexpr uint32_t STATUS_QUIET = 2u;       // a fused agent's act()+apply would change nothing (see step_kernel)
+constexpr uint32_t STATUS_KEY_SHIFT = 8;    // bits 8..15: which (agent, tiebreak) established QUIET; 0 = any agent
+constexpr uint32_t STATUS_KEY_MASK = 0xff00u;
 
 // ---------------------------------------------------------------------------------------------------
 // One env.step on the shared-memory record.  `have_actions` == false means "every action equals the current
@@ -760,18 +762,24 @@ __global__ void __launch_bounds__(256, 4) step_kernel(const StepParams p)
         StepResult res;
         res.reward = 0.0; res.terminated = 0; res.rejected = 0; res.waiting = 0; res.arrived = 0; res.changed = 0;
         double st_drop = 0, st_wr = 0, st_mc = 0, st_vc = 0, st_mm = 0, st_vm = 0, st_rej = 0, st_n = 0;
-        bool act_valid = false;            // e.act[] holds this step's action vector
-        // STATUS_ACT_CLEAN: "no waiting VM fits on any PM in the float32 view".  It is established by a fused
-        // agent evaluation that places nothing and stays true until a placement, suspension, departure or
-        // admission changes the PM loads or the set of waiting VMs; while it holds, act() is skipped (the agent
-        // would return the current placement unchanged, firstfit.py:31-37 / bestfit.py:31-39).
-        bool clean = (e.sc->status & STATUS_ACT_CLEAN) != 0;
+        // STATUS_QUIET: "a fused agent's act() followed by the env's apply loop would change nothing".  It is
+        // established by a full evaluation after which the step changed no placement (the agent proposed nothing, or
+        // every proposal was rejected by the fp64 capacity check — SURVEY App. B-2) and nothing departed or was
+        // admitted: the next act() then sees the same float32 PM loads and the same waiting VMs, proposes the same
+        // actions and the env rejects them again.  While it holds, act() and the apply loop are skipped.  The key
+        // records which agent established it (0 = "no waiting VM fits anywhere", which holds for every agent).
+        const bool need_vectors = p.out.d_action != nullptr || p.out.d_valid != nullptr;
+        const uint32_t my_key = (uint32_t)(p.agent | (p.tiebreak << 4));
+        uint32_t status = e.sc->status;
+        bool quiet = (status & STATUS_QUIET) != 0;
+        uint32_t quiet_key = (status & STATUS_KEY_MASK) >> STATUS_KEY_SHIFT;
+        int quiet_rejected = (int)(status >> 16);
         for (int s = 0; s < p.n_steps; s++) {
             bool have_actions;
+            bool evaluated = false;
+            int n_found = 0;
             if (p.agent != VMGYM_AGENT_NONE) {
-                int n_found = 0;
-                act_valid = false;
-                if (!clean) {
+                if (!(quiet && (quiet_key == 0 || quiet_key == my_key)) || need_vectors) {
                     // the agent sees the float32 observation of the current state (env.py:296)
                     for (int q = lane; q < L.P; q += 32) { e.cpu32[q] = (float)e.cpu[q]; e.mem32[q] = (float)e.mem[q]; }
                     for (int v = lane; v < L.V; v += 32) e.act[v] = (uint16_t)e.place[v];
@@ -782,8 +790,7 @@ __global__ void __launch_bounds__(256, 4) step_kernel(const StepParams p)
                     n_found = agent_act(e, p.agent, p.tiebreak, [=](int v) { return (int)place[v] == P; },
                                         [=](int v) { return (int)(cpuc[v] & 0x7f); }, [=](int v) { return (int)memc[v]; },
                                         [=](int v) { return t32[cpuc[v] & 0x7f]; }, [=](int v) { return t32[memc[v]]; });
-                    act_valid = true;
-                    clean = (n_found == 0);
+                    evaluated = true;
                 }
                 have_actions = n_found > 0;
             } else {
@@ -794,7 +801,15 @@ __global__ void __launch_bounds__(256, 4) step_kernel(const StepParams p)
                 have_actions = true;
             }
             res = env_step(e, p, env, valid_g, have_actions);
-            if (res.changed) clean = false;
+            if (res.changed) {
+                quiet = false;
+            } else if (evaluated) {
+                quiet = true;
+                quiet_key = n_found == 0 ? 0u : my_key;
+                quiet_rejected = res.rejected;
+            } else if (quiet && p.agent != VMGYM_AGENT_NONE) {
+                res.rejected = quiet_rejected;        // the skipped proposals would have been rejected again
+            }
             if (p.out.d_stats) {
                 // running sums for the eval summary (record.py:98-134, exp_performance.py:104-113)
                 double sc_ = 0, sm_ = 0;
@@ -818,10 +833,11 @@ __global__ void __launch_bounds__(256, 4) step_kernel(const StepParams p)
         if (p.out.d_obs) write_obs(e, p.out.d_obs + env * (long long)L.D);
         if (p.out.d_action && p.agent != VMGYM_AGENT_NONE) {
             PT* ao = reinterpret_cast<PT*>(p.out.d_action) + env * (long long)L.V;
-            for (int v = lane; v < L.V; v += 32) ao[v] = act_valid ? (PT)e.act[v] : e.place[v];
+            for (int v = lane; v < L.V; v += 32) ao[v] = (PT)e.act[v];    // need_vectors forced the evaluation
         }
         if (lane == 0) {
-            e.sc->status = (e.sc->status & ~STATUS_ACT_CLEAN) | (clean ? STATUS_ACT_CLEAN : 0u);
+            e.sc->status = (e.sc->status & STATUS_EXHAUSTED) |
+                           (quiet ? (STATUS_QUIET | (quiet_key << STATUS_KEY_SHIFT) | ((uint32_t)quiet_rejected << 16)) : 0u);
             if (p.out.d_reward) p.out.d_reward[env] = res.reward;
             if (p.out.d_terminated) p.out.d_terminated[env] = (uint8_t)res.terminated;
             if (p.out.d_stats) {
