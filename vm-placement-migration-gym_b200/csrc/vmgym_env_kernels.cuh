@@ -1,0 +1,990 @@
+// vmgym_env_kernels.cuh — device code of the batched env hot path (sm_100a).
+//
+// Semantics follow the reference's vmenv/envs/env.py and src/agents/{firstfit,bestfit}.py line by line (cited at
+// each phase); the mapping onto the GPU is new: one warp owns one env, the env record (vmgym_layout) is staged
+// HBM -> shared memory by one bulk-async copy (cp.async.bulk + mbarrier), mutated there for n_steps steps, and
+// written back by one bulk-async store.  fp64 PM accumulators are updated in the reference's VM-index order so
+// capacity decisions are bit-identical.  Compiled with -fmad=false: no FMA contraction.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vmgym_device.cuh"
+#include "vmgym_sort.cuh"
+
+namespace vmgym {
+
+struct StepParams {
+    DevLayout L;
+    int reward_fn, cap_target, step_limit;
+    double beta;
+    unsigned char* state;
+    long long n_envs;
+    vmgym_trace tr;
+    const void* action;       // [n_envs, V] of action_dtype (external-action mode)
+    int action_dtype;
+    vmgym_outputs out;
+    int agent, tiebreak, n_steps;
+    int use_bulk;             // stage records with cp.async.bulk (1) or 128-bit loads/stores (0)
+};
+
+constexpr uint32_t STATUS_EXHAUSTED = 1u;   // pre-sampled trace ran out (the reference would raise, env.py:282)
+constexpr uint32_t STATUS_QUIET = 2u;       // a fused agent's act()+apply would change nothing (see step_kernel)
+constexpr uint32_t STATUS_KEY_SHIFT = 8;    // bits 8..15: which (agent, tiebreak) established QUIET; 0 = any agent
+constexpr uint32_t STATUS_KEY_MASK = 0xff00u;
+
+__host__ __device__ static inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------------
+// Per-warp env context: one base pointer into shared memory + the layout (kernel-parameter constant bank), so the
+// dozen array pointers are recomputed from constants instead of living in (spilled) registers.
+// ---------------------------------------------------------------------------------------------------
+template <typename PT>
+struct Env {
+    unsigned char* base;
+    const DevLayout* L;
+    const double* sz64;                // code -> k/100.0   (== np.around(u, 2), env.py:212-219)
+    const float* sz32;                 // code -> (float)(k/100.0)   (env.py:296)
+    const uint64_t* arr_cdf;           // arrival / service inverse-CDF thresholds (shared-memory copies when small)
+    const uint64_t* svc_cdf;
+    int P, V, lane;
+
+    __device__ __forceinline__ double* cpu() const { return reinterpret_cast<double*>(base); }           // env.py:190
+    __device__ __forceinline__ double* mem() const { return reinterpret_cast<double*>(base + L->off_mem); }
+    __device__ __forceinline__ uint16_t* rem() const { return reinterpret_cast<uint16_t*>(base + L->off_rem); }
+    __device__ __forceinline__ PT* place() const { return reinterpret_cast<PT*>(base + L->off_place); }
+    __device__ __forceinline__ uint8_t* cpuc() const { return base + L->off_cpuc; }                      // bit 7 = suspended
+    __device__ __forceinline__ uint8_t* memc() const { return base + L->off_memc; }
+    __device__ __forceinline__ vmgym_env_scalars* sc() const { return reinterpret_cast<vmgym_env_scalars*>(base + L->off_scal); }
+    // scratch (not part of the record)
+    __device__ __forceinline__ float* cpu32() const { return reinterpret_cast<float*>(base + L->sm_cpu32); }  // agents' fp32 view
+    __device__ __forceinline__ float* mem32() const { return reinterpret_cast<float*>(base + L->sm_mem32); }
+    __device__ __forceinline__ uint16_t* act() const { return reinterpret_cast<uint16_t*>(base + L->sm_act); }
+    __device__ __forceinline__ uint8_t* tmp() const { return base + L->sm_tmp; }
+    __device__ __forceinline__ unsigned* fitm() const { return reinterpret_cast<unsigned*>(base + L->sm_fit); }
+    __device__ __forceinline__ uint16_t* cap() const { return reinterpret_cast<uint16_t*>(base + L->sm_fit + 512); }
+    __device__ __forceinline__ unsigned* prop() const { return reinterpret_cast<unsigned*>(base + L->sm_prop); }
+};
+
+// Where the agent reads the slots it decides on: arrays of placements and size codes (+ float sizes as the agent
+// sees them).  In the fused kernel these are the record's own arrays; in act_kernel they are built from the
+// observation row.
+template <typename PT>
+struct AgentView {
+    const PT* place;
+    const uint8_t* cc;       // cpu size code (bit 7 may carry the suspended flag; masked on use)
+    const uint8_t* mc;
+    const float* c32;        // nullptr -> sz32[code]
+    const float* m32;
+    const float* sz32;
+    __device__ __forceinline__ float cpu_size(int v) const { return c32 ? c32[v] : sz32[cc[v] & 0x7f]; }
+    __device__ __forceinline__ float mem_size(int v) const { return m32 ? m32[v] : sz32[mc[v]]; }
+};
+
+__device__ __forceinline__ double warp_sum(double x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+
+// largest size code k in [0,100] with x + sz32[k] <= 1.0f (monotone in k because fp32 rounding is monotone)
+__device__ __forceinline__ int max_code(const float* sz32, float x)
+{
+    int k = min(100, max(0, (int)((1.0f - x) * 100.0f)));      // estimate, then exact correction (usually 1-2 probes)
+    while (k < 100 && x + sz32[k + 1] <= 1.0f) k++;
+    while (k > 0 && x + sz32[k] > 1.0f) k--;
+    return k;
+}
+
+// fitm[c] = 1 + max{ mem-capacity code of PM p : cpu-capacity code of p >= c }, 0 if no PM takes cpu code c.
+// A VM with size codes (c, m) fits on SOME PM iff m + 1 <= fitm[c] — an exact O(1) test that removes the hopeless
+// waiting VMs (the large majority at saturation) from the sequential scan.
+template <typename PT>
+__device__ __forceinline__ void rebuild_fit_table(const Env<PT>& e)
+{
+    const int lane = e.lane;
+    unsigned* fitm = e.fitm();
+    const uint16_t* cap = e.cap();
+    reinterpret_cast<uint4*>(fitm)[lane] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    for (int p = lane; p < e.P; p += 32) {
+        const unsigned w = cap[p];
+        atomicMax(&fitm[w & 0xffu], (w >> 8) + 1u);
+    }
+    __syncwarp();
+    uint4 q = reinterpret_cast<uint4*>(fitm)[lane];            // lane owns codes 4*lane .. 4*lane+3
+    q.z = max(q.z, q.w); q.y = max(q.y, q.z); q.x = max(q.x, q.y);
+    unsigned s = q.x;                                          // suffix max over lanes >= lane
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_down_sync(FULL, s, o);
+        if (lane + o < 32) s = max(s, t);
+    }
+    unsigned ex = __shfl_down_sync(FULL, s, 1);
+    if (lane == 31) ex = 0u;
+    q.x = max(q.x, ex); q.y = max(q.y, ex); q.z = max(q.z, ex); q.w = max(q.w, ex);
+    reinterpret_cast<uint4*>(fitm)[lane] = q;
+    __syncwarp();
+}
+
+// candidate bits of the 4 slots 4g..4g+3 (u8 placements): waiting VMs that fit on some PM
+__device__ __forceinline__ unsigned cand_bits4(uint32_t pl4, uint32_t cc4, uint32_t mc4, uint32_t P4, const unsigned* fitm)
+{
+    const uint32_t w4 = __vcmpeq4(pl4, P4);
+    unsigned c = 0;
+    if (w4) {
+        cc4 &= 0x7f7f7f7fu;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if ((w4 >> (8 * j)) & 1u) c |= (((mc4 >> (8 * j)) & 0xffu) + 1u <= fitm[(cc4 >> (8 * j)) & 0xffu]) ? (1u << j) : 0u;
+    }
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Heuristic agents on the float32 view (firstfit.py:21-38, bestfit.py:21-40).  Lanes own PMs p = lane + 32 i.
+// For every waiting VM, in slot order: first-fit takes the lowest-index PM that fits, best-fit the fitting PM with
+// the largest cpu+memory (ties: see `tiebreak`); the local float32 loads are updated like the reference does
+// (first-fit: cpu only, firstfit.py:36).  Proposals are recorded as act[v] = pm plus a bit in prop[v / 32].
+// Returns the number of proposals.
+// ---------------------------------------------------------------------------------------------------
+template <typename PT>
+__device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& av, int agent, int tiebreak)
+{
+    const int P = e.P, V = e.V, lane = e.lane;
+    float* cpu32 = e.cpu32();
+    float* mem32 = e.mem32();
+    uint16_t* cap = e.cap();
+    const unsigned* fitm = e.fitm();
+    int n_found = 0;
+    for (int p = lane; p < P; p += 32) cap[p] = (uint16_t)(max_code(e.sz32, cpu32[p]) | (max_code(e.sz32, mem32[p]) << 8));
+    for (int c = lane; c < (V + 31) / 32; c += 32) e.prop()[c] = 0u;
+    rebuild_fit_table(e);
+
+    // slots are visited in groups: 4 per lane (128 per pass) for byte placements, 1 per lane otherwise
+    constexpr int SPL = sizeof(PT) == 1 ? 4 : 1;
+    const uint32_t P4 = (uint32_t)P * 0x01010101u;
+    const int n_units = (V + SPL - 1) / SPL;
+    for (int u0 = 0; u0 < n_units; u0 += 32) {
+        const int u = u0 + lane;
+        unsigned cb = 0;                      // candidate bits of this lane's SPL slots
+        if (u < n_units) {
+            if (SPL == 4) {
+                cb = cand_bits4(reinterpret_cast<const uint32_t*>(av.place)[u], reinterpret_cast<const uint32_t*>(av.cc)[u],
+                                reinterpret_cast<const uint32_t*>(av.mc)[u], P4, fitm);
+            } else {
+                cb = ((int)av.place[u] == P && (unsigned)av.mc[u] + 1u <= fitm[av.cc[u] & 0x7f]) ? 1u : 0u;
+            }
+        }
+        unsigned m = __ballot_sync(FULL, cb != 0);
+        while (m) {
+            const int b = __ffs(m) - 1;
+            unsigned bits = __shfl_sync(FULL, cb, b);
+            bool placed_any = false;
+            while (bits) {
+                const int j = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int vv = SPL * (u0 + b) + j;
+                const float c32 = av.cpu_size(vv), m32 = av.mem_size(vv);
+                int found = -1;
+                if (agent == VMGYM_AGENT_FIRSTFIT) {
+                    for (int i0 = 0; i0 < P; i0 += 32) {
+                        const int p = i0 + lane;
+                        const bool fit = p < P && (cpu32[p] + c32 <= 1.0f) && (mem32[p] + m32 <= 1.0f);
+                        const unsigned bb = __ballot_sync(FULL, fit);
+                        if (bb) { found = i0 + __ffs(bb) - 1; break; }
+                    }
+                    if (found >= 0 && lane == (found & 31)) {
+                        const float nc = cpu32[found] + c32;        // firstfit.py:36 — only the local cpu is updated
+                        cpu32[found] = nc;
+                        cap[found] = (uint16_t)((cap[found] & 0xff00u) | (unsigned)max_code(e.sz32, nc));
+                    }
+                } else {
+                    // best-fit: first fitting PM in descending (cpu+memory) order (bestfit.py:33-39)
+                    unsigned bestk = 0;
+                    int bestp = -1;
+                    for (int p = lane; p < P; p += 32) {
+                        const bool fit = (cpu32[p] + c32 <= 1.0f) && (mem32[p] + m32 <= 1.0f);
+                        const unsigned kb = __float_as_uint(cpu32[p] + mem32[p]) + 1u;   // keys >= 0: bits order like values
+                        if (fit && kb >= bestk) { bestk = kb; bestp = p; }
+                    }
+                    const unsigned gk = __reduce_max_sync(FULL, bestk);
+                    if (gk != 0) {
+                        found = (int)__reduce_max_sync(FULL, (unsigned)((bestk == gk ? bestp : -1) + 1)) - 1;  // ties -> highest index
+                        if (tiebreak == VMGYM_TIE_NUMPY_INTROSORT) {
+                            int cnt = 0;
+                            for (int p = lane; p < P; p += 32) {
+                                const bool fit = (cpu32[p] + c32 <= 1.0f) && (mem32[p] + m32 <= 1.0f);
+                                cnt += (fit && __float_as_uint(cpu32[p] + mem32[p]) + 1u == gk);
+                            }
+                            cnt = __reduce_add_sync(FULL, cnt);
+                            if (cnt >= 2) {
+                                // several fitting PMs share the maximal key: numpy's unstable default argsort decides
+                                float* keys = reinterpret_cast<float*>(e.tmp());
+                                uint16_t* perm = reinterpret_cast<uint16_t*>(e.tmp() + 4 * ((P + 1) & ~1));
+                                for (int p = lane; p < P; p += 32) keys[p] = cpu32[p] + mem32[p];
+                                __syncwarp();
+                                int pick = -1;
+                                if (lane == 0) {
+                                    introsort_argsort(keys, perm, P);
+                                    for (int i = P - 1; i >= 0; i--) {
+                                        const int p = perm[i];
+                                        if ((cpu32[p] + c32 <= 1.0f) && (mem32[p] + m32 <= 1.0f)) { pick = p; break; }
+                                    }
+                                }
+                                found = __shfl_sync(FULL, pick, 0);
+                                __syncwarp();
+                            }
+                        }
+                        if (lane == (found & 31)) {
+                            const float nc = cpu32[found] + c32, nm = mem32[found] + m32;   // bestfit.py:37-38
+                            cpu32[found] = nc;
+                            mem32[found] = nm;
+                            cap[found] = (uint16_t)(max_code(e.sz32, nc) | (max_code(e.sz32, nm) << 8));
+                        }
+                    }
+                }
+                if (found >= 0) {
+                    n_found++;
+                    placed_any = true;
+                    if (lane == 0) { e.act()[vv] = (uint16_t)found; e.prop()[vv >> 5] |= 1u << (vv & 31); }
+                    __syncwarp();
+                    rebuild_fit_table(e);          // capacities shrank: the remaining candidates are re-tested
+                    if (bits) {
+                        unsigned nb;
+                        if (SPL == 4) {
+                            const int ub = u0 + b;
+                            nb = cand_bits4(reinterpret_cast<const uint32_t*>(av.place)[ub], reinterpret_cast<const uint32_t*>(av.cc)[ub],
+                                            reinterpret_cast<const uint32_t*>(av.mc)[ub], P4, fitm);
+                        } else nb = 0;
+                        bits &= nb;
+                    }
+                }
+            }
+            m &= m - 1;
+            if (placed_any && m) {
+                // re-test the not-yet-visited lanes' candidates against the shrunken capacities
+                if (u < n_units && lane > b) {
+                    if (SPL == 4)
+                        cb = cand_bits4(reinterpret_cast<const uint32_t*>(av.place)[u], reinterpret_cast<const uint32_t*>(av.cc)[u],
+                                        reinterpret_cast<const uint32_t*>(av.mc)[u], P4, fitm);
+                    else
+                        cb = ((int)av.place[u] == P && (unsigned)av.mc[u] + 1u <= fitm[av.cc[u] & 0x7f]) ? 1u : 0u;
+                }
+                m &= __ballot_sync(FULL, cb != 0);
+            }
+        }
+    }
+    __syncwarp();
+    return n_found;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Rewards `ut` (env.py:151-152) and `kl` (env.py:125-150, kl_divergence :8-17).  All reductions use numpy's
+// summation order so the fp64 values (and the exact-zero variance tests) are those of the reference.
+// ---------------------------------------------------------------------------------------------------
+__device__ __noinline__ double reward_ut(const double* cpu, const double* mem, int P, double beta)
+{
+    const SumSrc sc{cpu, nullptr, nullptr, 0.0, 0}, sm{mem, nullptr, nullptr, 0.0, 0};
+    return beta * np_sum(sc, P) + (1 - beta) * np_sum(sm, P);
+}
+
+__device__ __noinline__ double reward_kl(const double* cpu, const double* mem, int P, const uint8_t* ex_cc,
+                                         const uint8_t* ex_mc, int arrived, const double* sz, int cap_target)
+{
+    const double dP = (double)P, dn = (double)arrived;
+    const double ex_sum_c = np_sum(SumSrc{nullptr, ex_cc, sz, 0.0, 0}, arrived);
+    const double ex_sum_m = np_sum(SumSrc{nullptr, ex_mc, sz, 0.0, 0}, arrived);
+    double t_cpu = ex_sum_c / dP, t_mem = ex_sum_m / dP;                         // env.py:116,119
+    if (cap_target && t_cpu > 1) t_cpu = 1.0;
+    if (cap_target && t_mem > 1) t_mem = 1.0;
+    const double cur_cpu = np_sum(SumSrc{cpu, nullptr, nullptr, 0.0, 0}, P) / dP;  // np.mean(self.cpu)
+    const double cur_mem = np_sum(SumSrc{mem, nullptr, nullptr, 0.0, 0}, P) / dP;
+    double cpu_var = np_sum(SumSrc{cpu, nullptr, nullptr, cur_cpu, 1}, P) / dP;    // np.var(self.cpu)
+    double mem_var = np_sum(SumSrc{mem, nullptr, nullptr, cur_mem, 1}, P) / dP;
+    if (cpu_var == 0) cpu_var = 1e-6;
+    if (mem_var == 0) mem_var = 1e-6;
+    // np.var(vm_cpu[existing]): deviations from the compacted array's own mean (sum / n)
+    const double xm_c = ex_sum_c / dn, xm_m = ex_sum_m / dn;
+    double t_cpu_var = np_sum(SumSrc{nullptr, ex_cc, sz, xm_c, 1}, arrived) / dn;
+    double t_mem_var = np_sum(SumSrc{nullptr, ex_mc, sz, xm_m, 1}, arrived) / dn;
+    if (t_cpu_var == 0) t_cpu_var = 1e-6;
+    if (t_mem_var == 0) t_mem_var = 1e-6;
+    if (t_cpu == 0 || t_mem == 0) return 0.0;
+    // diagonal 2x2 covariances: det = product, inverse = reciprocals; evaluation order of env.py:17 kept
+    const double det_p = t_cpu_var * t_mem_var, det_q = cpu_var * mem_var;
+    const double qi0 = 1.0 / cpu_var, qi1 = 1.0 / mem_var;
+    const double trace_term = qi0 * t_cpu_var + qi1 * t_mem_var;
+    const double d0 = t_cpu - cur_cpu, d1 = t_mem - cur_mem;
+    const double m1 = (d0 * qi0) * d0 + (d1 * qi1) * d1;
+    return -(0.5 * (log(det_q / det_p) - 2 + trace_term + m1 - trace_term));
+}
+
+__device__ __forceinline__ int cdf_search(const uint64_t* cdf, int len, uint64_t u)
+{
+    int lo = 0, hi = len;            // first i with cdf[i] > u
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+    return min(lo, len - 1);
+}
+
+struct StepResult { double reward; int terminated; int rejected; int waiting, arrived; int changed; };
+
+// ---------------------------------------------------------------------------------------------------
+// One env.step on the shared-memory record.  The action vector is given as act[v] for the slots whose bit is
+// set in prop[] (slots whose action differs from their placement); every other action is a valid no-op
+// (validate(), env.py:36-37).  The per-env counters n_waiting / n_empty are maintained incrementally so the
+// common quiet step (nothing placed, nothing departs, nothing admitted) costs only the service countdown, one
+// arrival draw and the outputs.
+// ---------------------------------------------------------------------------------------------------
+template <typename PT>
+__device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParams& p, long long env_id, uint8_t* valid_g,
+                                               bool have_actions)
+{
+    const int P = e.P, V = e.V, lane = e.lane;
+    vmgym_env_scalars* sc = e.sc();
+    double* cpu = e.cpu();
+    double* mem = e.mem();
+    PT* place = e.place();
+    uint8_t* cpuc = e.cpuc();
+    uint8_t* memc = e.memc();
+    uint16_t* rem = e.rem();
+    int n_place = 0, n_susp = 0, rejected = 0;
+
+    // ---- 1. apply actions in VM-index order, each seeing earlier updates (env.py:69-87, validate :35-42) ----
+    if (have_actions) {
+        const uint16_t* act = e.act();
+        const unsigned* prop = e.prop();
+        for (int c0 = 0; c0 < V; c0 += 32) {
+            const unsigned pm = prop[c0 >> 5];
+            unsigned m = pm, okbits = 0;
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const int vv = c0 + b, a = (int)act[vv], cv = (int)place[vv];
+                bool ok = false;
+                if (cv == P) {                                   // waiting VM: place iff it fits in fp64 (:38-39,55-56)
+                    if ((unsigned)a < (unsigned)P) {
+                        const double nc = cpu[a] + e.sz64[cpuc[vv] & 0x7f];
+                        const double nm = mem[a] + e.sz64[memc[vv]];
+                        if (nc <= 1.0 && nm <= 1.0) {
+                            ok = true;
+                            n_place++;
+                            __syncwarp();
+                            if (lane == 0) { cpu[a] = nc; mem[a] = nm; place[vv] = (PT)a; cpuc[vv] &= 0x7f; }   // :82-85
+                        }
+                    }
+                } else if (cv < P) {                             // running VM: only suspend is legal (:40-41,78-81)
+                    if (a == P) {
+                        ok = true;
+                        n_susp++;
+                        const double nc = cpu[cv] - e.sz64[cpuc[vv] & 0x7f];
+                        const double nm = mem[cv] - e.sz64[memc[vv]];
+                        __syncwarp();
+                        if (lane == 0) { cpu[cv] = nc; mem[cv] = nm; place[vv] = (PT)P; cpuc[vv] |= 0x80; }
+                    }
+                }
+                __syncwarp();
+                okbits |= ok ? (1u << b) : 0u;
+            }
+            rejected += __popc(pm & ~okbits);
+            if (valid_g && c0 + lane < V) valid_g[c0 + lane] = ((pm & ~okbits) >> lane) & 1u ? 0 : 1;
+        }
+    } else if (valid_g) {
+        for (int v = lane; v < V; v += 32) valid_g[v] = 1;
+    }
+
+    // ---- 2+3. service countdown and departures in VM-index order (_run_vms, env.py:244-265) ----
+    int served = 0;
+    if (sizeof(PT) == 1) {
+        // 4 slots per lane: placement bytes as one u32, remaining runtimes as 4 x u16 (padding slots are empty)
+        const uint32_t P4 = (uint32_t)P * 0x01010101u;
+        const uint32_t* pl4 = reinterpret_cast<const uint32_t*>(place);
+        uint2* rem4 = reinterpret_cast<uint2*>(rem);
+        const int groups = (V + 3) >> 2;
+        for (int g0 = 0; g0 < groups; g0 += 32) {
+            const int g = g0 + lane;
+            unsigned term4 = 0;
+            if (g < groups) {
+                const uint32_t run = __vcmpltu4(pl4[g], P4);            // 0xff per running slot
+                if (run) {
+                    uint2 r = rem4[g];
+                    const uint32_t dlo = (run & 1u) | ((run & 0x100u) << 8), dhi = ((run >> 16) & 1u) | ((run >> 8) & 0x10000u);
+                    r.x = __vsubus2(r.x, dlo);                           // if remaining > 0: remaining -= 1 (:245-247)
+                    r.y = __vsubus2(r.y, dhi);
+                    rem4[g] = r;
+                    const uint32_t zlo = __vcmpeq2(r.x, 0u), zhi = __vcmpeq2(r.y, 0u);
+                    term4 = ((zlo & 1u) | ((zlo >> 15) & 2u) | ((zhi & 1u) << 2) | ((zhi >> 13) & 8u)) &
+                            ((run & 1u) | ((run >> 7) & 2u) | ((run >> 14) & 4u) | ((run >> 21) & 8u));
+                }
+            }
+            unsigned m = __ballot_sync(FULL, term4 != 0);
+            if (m) {                                                      // some VM finished (:248-265)
+                __syncwarp();
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    unsigned t4 = __shfl_sync(FULL, term4, b);
+                    served += __popc(t4);
+                    if (lane == 0) {
+                        while (t4) {
+                            const int j = __ffs(t4) - 1;
+                            t4 &= t4 - 1;
+                            const int vv = 4 * (g0 + b) + j, pm = (int)place[vv];
+                            cpu[pm] -= e.sz64[cpuc[vv] & 0x7f];
+                            mem[pm] -= e.sz64[memc[vv]];
+                            place[vv] = (PT)(P + 1); cpuc[vv] = 0; memc[vv] = 0; rem[vv] = 0;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        for (int c0 = 0; c0 < V; c0 += 32) {
+            const int v = c0 + lane;
+            const int pl = v < V ? (int)place[v] : P + 1;
+            int r = v < V ? (int)rem[v] : 0;
+            const bool running = pl < P;
+            if (running && r > 0) { r -= 1; rem[v] = (uint16_t)r; }
+            const bool term = running && r == 0;
+            unsigned m = __ballot_sync(FULL, term);
+            served += __popc(m);
+            if (m) {
+                if (lane == 0) {
+                    unsigned mm = m;
+                    while (mm) {
+                        const int b = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        const int vv = c0 + b, pm = (int)place[vv];
+                        cpu[pm] -= e.sz64[cpuc[vv] & 0x7f];
+                        mem[pm] -= e.sz64[memc[vv]];
+                    }
+                }
+                __syncwarp();
+                if (term) { place[v] = (PT)(P + 1); cpuc[v] = 0; memc[v] = 0; rem[v] = 0; }
+            }
+        }
+    }
+    __syncwarp();
+    // ---- 4. clamp (env.py:267-268): values only shrink when something was subtracted this step ----
+    if (served > 0 || n_susp > 0) {
+        for (int q = lane; q < P; q += 32) {
+            if (cpu[q] < 1e-7) cpu[q] = 0.0;
+            if (mem[q] < 1e-7) mem[q] = 0.0;
+        }
+    }
+
+    // ---- 5. arrivals (_accept_vm_requests, env.py:271-293) ----
+    int n_arr = 0;
+    const vmgym_trace& tr = p.tr;
+    const uint32_t arrival_pos = sc->arrival_pos, admission_pos = sc->admission_pos;
+    const uint32_t k0 = (uint32_t)sc->seed, k1 = (uint32_t)(sc->seed >> 32);
+    int exhausted = 0;
+    if (tr.mode == VMGYM_TRACE_PRESAMPLED) {
+        if ((long long)arrival_pos < tr.arrivals_len) n_arr = tr.d_arrivals[env_id * tr.arrivals_len + arrival_pos];
+        else exhausted = 1;
+    } else {
+        const Philox4 r = philox4x32_10(arrival_pos, 0u, 1u, 0u, k0, k1);
+        n_arr = tr.arrival_kmin + cdf_search(e.arr_cdf, tr.arrival_cdf_len, ((uint64_t)r.x << 32) | r.y);
+    }
+    int quota = n_arr;                                         // admissions still allowed this step
+    if (tr.mode == VMGYM_TRACE_PRESAMPLED) {
+        const long long left = tr.admissions_len - (long long)admission_pos;
+        if ((long long)quota > left) { quota = (int)(left > 0 ? left : 0); exhausted = 1; }
+    }
+    const int n_empty0 = (int)sc->n_empty + served;            // empty slots before admission
+    int admitted = 0;
+    long long csum = 0, msum = 0;
+    if (quota > 0 && n_empty0 > 0) {
+        for (int c0 = 0; c0 < V && admitted < quota; c0 += 32) {
+            const int v = c0 + lane;
+            const bool empty = v < V && (int)place[v] == P + 1;
+            const unsigned m = __ballot_sync(FULL, empty);
+            const int rank = admitted + __popc(m & ((1u << lane) - 1u));
+            if (empty && rank < quota) {                       // lowest-index empty slots (:275-277)
+                const uint32_t j = admission_pos + (uint32_t)rank;
+                uint32_t cc, mc, svc;
+                if (tr.mode == VMGYM_TRACE_PRESAMPLED) {
+                    const uint32_t w = tr.d_admissions[env_id * tr.admissions_len + j];
+                    cc = w & 0xff; mc = (w >> 8) & 0xff; svc = w >> 16;
+                } else {
+                    const Philox4 r = philox4x32_10(j, 0u, 2u, 0u, k0, k1);
+                    const uint32_t span = 2u * (uint32_t)(tr.size_hi_code - tr.size_lo_code);
+                    cc = (uint32_t)tr.size_lo_code + ((mulhi32(r.x, span) + 1u) >> 1);
+                    mc = (uint32_t)tr.size_lo_code + ((mulhi32(r.y, span) + 1u) >> 1);
+                    svc = (uint32_t)(tr.service_kmin + cdf_search(e.svc_cdf, tr.service_cdf_len, ((uint64_t)r.z << 32) | r.w)) + 1u;  // :289
+                }
+                place[v] = (PT)P;
+                cpuc[v] = (uint8_t)cc; memc[v] = (uint8_t)mc; rem[v] = (uint16_t)svc;
+                csum += cc; msum += mc;
+            }
+            admitted += __popc(m);
+        }
+        admitted = min(admitted, quota);
+        csum = (long long)__reduce_add_sync(FULL, (unsigned)csum);
+        msum = (long long)__reduce_add_sync(FULL, (unsigned)msum);
+        __syncwarp();
+    }
+
+    // ---- 6. metrics (env.py:112-121) from the incrementally maintained slot counters ----
+    const int n_empty = n_empty0 - admitted;
+    const int waiting = (int)sc->n_waiting - n_place + n_susp + admitted;
+    const int arrived = V - n_empty;
+
+    // ---- 7. reward (env.py:123-156) ----
+    double reward = 0.0;
+    if (arrived > 0) {
+        if (p.reward_fn == VMGYM_REWARD_WR) {
+            reward = -((double)waiting / (double)arrived);
+        } else if (p.reward_fn == VMGYM_REWARD_UT) {
+            reward = reward_ut(cpu, mem, P, p.beta);
+        } else {
+            // compacted vm_cpu[existing], vm_memory[existing] in slot order (the reference's boolean indexing)
+            uint8_t* ex_cc = e.tmp();
+            uint8_t* ex_mc = e.tmp() + ((V + 15) & ~15);
+            int pos0 = 0;
+            for (int c0 = 0; c0 < V; c0 += 32) {
+                const int v = c0 + lane;
+                const bool ex = v < V && (int)place[v] <= P;
+                const unsigned mx = __ballot_sync(FULL, ex);
+                if (ex) {
+                    const int pos = pos0 + __popc(mx & ((1u << lane) - 1u));
+                    ex_cc[pos] = cpuc[v] & 0x7f;
+                    ex_mc[pos] = memc[v];
+                }
+                pos0 += __popc(mx);
+            }
+            __syncwarp();
+            reward = reward_kl(cpu, mem, P, ex_cc, ex_mc, arrived, e.sz64, p.cap_target);
+        }
+    }
+
+    // ---- 9. termination flag, counters, clock (env.py:160-163,101) ----
+    const int terminated = sc->timestep >= p.step_limit;
+    __syncwarp();
+    if (lane == 0) {
+        sc->total_requests += n_arr;
+        sc->served_requests += served;
+        sc->dropped_requests += n_arr - admitted;
+        sc->suspend_actions += n_susp;
+        sc->place_actions += n_place;
+        sc->arrival_pos = arrival_pos + 1;
+        sc->admission_pos = admission_pos + (uint32_t)admitted;
+        sc->status |= (uint32_t)exhausted;
+        sc->n_waiting = (uint16_t)waiting;
+        sc->n_empty = (uint16_t)n_empty;
+        sc->cpu_code_sum += csum;
+        sc->mem_code_sum += msum;
+        sc->episode_return += reward;
+        sc->last_reward = reward;
+        sc->timestep += 1;
+    }
+    __syncwarp();
+    StepResult res;
+    res.reward = reward; res.terminated = terminated; res.rejected = rejected; res.waiting = waiting; res.arrived = arrived;
+    res.changed = n_place + n_susp + served + admitted;      // anything that can change which waiting VMs fit
+    return res;
+}
+
+// observation row (env.py:295-296): f32[ placement | vm_cpu | vm_memory | cpu | memory ]
+template <typename PT>
+__device__ __forceinline__ void write_obs(const Env<PT>& e, float* __restrict__ o)
+{
+    const int P = e.P, V = e.V;
+    const PT* place = e.place();
+    const uint8_t* cpuc = e.cpuc();
+    const uint8_t* memc = e.memc();
+    const double* cpu = e.cpu();
+    const double* mem = e.mem();
+    if (sizeof(PT) == 1 && (V & 3) == 0 && (P & 3) == 0) {
+        // 128-bit stores: the row and its five segments are 16-byte aligned when V and P are multiples of 4
+        float4* o4 = reinterpret_cast<float4*>(o);
+        const uint32_t* pl4 = reinterpret_cast<const uint32_t*>(place);
+        const uint32_t* cc4 = reinterpret_cast<const uint32_t*>(cpuc);
+        const uint32_t* mc4 = reinterpret_cast<const uint32_t*>(memc);
+        const int vg = V >> 2, pg = P >> 2;
+        for (int g = e.lane; g < vg; g += 32) {
+            const uint32_t a = pl4[g], c = cc4[g] & 0x7f7f7f7fu, m = mc4[g];
+            o4[g] = make_float4((float)(a & 0xff), (float)((a >> 8) & 0xff), (float)((a >> 16) & 0xff), (float)(a >> 24));
+            o4[vg + g] = make_float4(e.sz32[c & 0xff], e.sz32[(c >> 8) & 0xff], e.sz32[(c >> 16) & 0xff], e.sz32[c >> 24]);
+            o4[2 * vg + g] = make_float4(e.sz32[m & 0xff], e.sz32[(m >> 8) & 0xff], e.sz32[(m >> 16) & 0xff], e.sz32[m >> 24]);
+        }
+        const double2* c2 = reinterpret_cast<const double2*>(cpu);
+        const double2* m2 = reinterpret_cast<const double2*>(mem);
+        for (int g = e.lane; g < pg; g += 32) {
+            const double2 a = c2[2 * g], b = c2[2 * g + 1], c = m2[2 * g], d = m2[2 * g + 1];
+            o4[3 * vg + g] = make_float4((float)a.x, (float)a.y, (float)b.x, (float)b.y);
+            o4[3 * vg + pg + g] = make_float4((float)c.x, (float)c.y, (float)d.x, (float)d.y);
+        }
+        return;
+    }
+    for (int v = e.lane; v < V; v += 32) o[v] = (float)place[v];
+    for (int v = e.lane; v < V; v += 32) o[V + v] = e.sz32[cpuc[v] & 0x7f];
+    for (int v = e.lane; v < V; v += 32) o[2 * V + v] = e.sz32[memc[v]];
+    for (int q = e.lane; q < P; q += 32) o[3 * V + q] = (float)cpu[q];
+    for (int q = e.lane; q < P; q += 32) o[3 * V + P + q] = (float)mem[q];
+}
+
+__device__ __forceinline__ void fill_tables(double* sz64, float* sz32)
+{
+    for (int k = threadIdx.x; k < SIZE_TABLE; k += blockDim.x) {
+        const double x = (double)k / 100.0;      // == np.around(u, 2) for the code k (env.py:212-219)
+        sz64[k] = x;
+        sz32[k] = (float)x;                        // env.py:296 float32 cast
+    }
+}
+
+// action element -> int; anything outside [0, 65534] becomes 0xFFFF, which matches no placement value and
+// therefore fails every branch of validate() (env.py:35-42) exactly like an out-of-range action does.
+__device__ __forceinline__ int load_action(const void* row, int dtype, int v)
+{
+    if (dtype == VMGYM_U8) return (int)reinterpret_cast<const uint8_t*>(row)[v];
+    if (dtype == VMGYM_I16) {
+        const int x = reinterpret_cast<const int16_t*>(row)[v];
+        return x < 0 ? 0xFFFF : x;
+    }
+    const long long x = reinterpret_cast<const long long*>(row)[v];
+    return (x < 0 || x > 65534) ? 0xFFFF : (int)x;
+}
+__host__ __device__ __forceinline__ int dtype_bytes(int dtype) { return dtype == VMGYM_U8 ? 1 : (dtype == VMGYM_I16 ? 2 : 8); }
+
+// ---------------------------------------------------------------------------------------------------
+// The step kernel: external actions (agent == NONE) or fused heuristic agent, n_steps per launch.
+// Grid-stride over envs, one warp per env, <= 4 warps per CTA.
+// ---------------------------------------------------------------------------------------------------
+template <typename PT>
+__global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ StepParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const DevLayout& L = p.L;
+    double* sz64 = reinterpret_cast<double*>(smem);
+    float* sz32 = reinterpret_cast<float*>(smem + SIZE_TABLE * 8);
+    uint64_t* arr_cdf_s = reinterpret_cast<uint64_t*>(smem + SIZE_TABLE * 12);
+    uint64_t* svc_cdf_s = arr_cdf_s + ARR_CDF_SMEM;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    unsigned char* base = smem + L.sm_tables + (size_t)warp * L.sm_stride;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(base + L.sm_bar);
+    fill_tables(sz64, sz32);
+    const bool philox = p.tr.mode == VMGYM_TRACE_PHILOX;
+    const bool arr_in_smem = philox && p.tr.arrival_cdf_len <= ARR_CDF_SMEM;
+    const bool svc_in_smem = philox && p.tr.service_cdf_len <= L.svc_cdf_smem;
+    if (arr_in_smem)
+        for (int k = threadIdx.x; k < p.tr.arrival_cdf_len; k += blockDim.x) arr_cdf_s[k] = p.tr.d_arrival_cdf[k];
+    if (svc_in_smem)
+        for (int k = threadIdx.x; k < p.tr.service_cdf_len; k += blockDim.x) svc_cdf_s[k] = p.tr.d_service_cdf[k];
+    const bool BULK = p.use_bulk != 0;
+    if (BULK && lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    __syncthreads();
+
+    Env<PT> e;
+    e.base = base; e.L = &p.L; e.sz64 = sz64; e.sz32 = sz32; e.P = L.P; e.V = L.V; e.lane = lane;
+    e.arr_cdf = arr_in_smem ? arr_cdf_s : p.tr.d_arrival_cdf;
+    e.svc_cdf = svc_in_smem ? svc_cdf_s : p.tr.d_service_cdf;
+    uint32_t phase = 0;
+    const long long stride = (long long)gridDim.x * wpc;
+    for (long long env = (long long)blockIdx.x * wpc + warp; env < p.n_envs; env += stride) {
+        unsigned char* grec = p.state + env * (long long)L.rec_bytes;
+        // ---- stage the record into shared memory ----
+        if (BULK) {
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar, (uint32_t)L.rec_bytes);
+                bulk_g2s(base, grec, (uint32_t)L.rec_bytes, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        } else {
+            const uint4* src = reinterpret_cast<const uint4*>(grec);
+            uint4* dst = reinterpret_cast<uint4*>(base);
+            for (int i = lane; i < L.rec_bytes / 16; i += 32) dst[i] = __ldg(src + i);
+            __syncwarp();
+        }
+
+        uint8_t* valid_g = p.out.d_valid ? p.out.d_valid + env * (long long)L.V : nullptr;
+        StepResult res;
+        res.reward = 0.0; res.terminated = 0; res.rejected = 0; res.waiting = 0; res.arrived = 0; res.changed = 0;
+        double* st_acc = reinterpret_cast<double*>(base + L.sm_stats);     // per-launch stats sums (lane 0)
+        if (p.out.d_stats && lane < 8) st_acc[lane] = 0.0;
+        // STATUS_QUIET: "a fused agent's act() followed by the env's apply loop would change nothing".  It is
+        // established by a full evaluation after which the step changed no placement (the agent proposed nothing, or
+        // every proposal was rejected by the fp64 capacity check — SURVEY App. B-2) and nothing departed or was
+        // admitted: the next act() then sees the same float32 PM loads and the same waiting VMs, proposes the same
+        // actions and the env rejects them again.  While it holds, act() and the apply loop are skipped.  The key
+        // records which agent established it (0 = "no waiting VM fits anywhere", which holds for every agent).
+        const bool need_vectors = p.out.d_action != nullptr || p.out.d_valid != nullptr;
+        const uint32_t my_key = (uint32_t)(p.agent | (p.tiebreak << 4));
+        const uint32_t status0 = e.sc()->status;
+        bool quiet = (status0 & STATUS_QUIET) != 0;
+        uint32_t quiet_key = (status0 & STATUS_KEY_MASK) >> STATUS_KEY_SHIFT;
+        int quiet_rejected = (int)(status0 >> 16);
+        for (int s = 0; s < p.n_steps; s++) {
+            bool have_actions, evaluated = false;
+            int n_found = 0;
+            if (p.agent != VMGYM_AGENT_NONE) {
+                if (!(quiet && (quiet_key == 0 || quiet_key == my_key)) || need_vectors) {
+                    // the agent sees the float32 observation of the current state (env.py:296)
+                    const double* cpu = e.cpu();
+                    const double* mem = e.mem();
+                    for (int q = lane; q < L.P; q += 32) { e.cpu32()[q] = (float)cpu[q]; e.mem32()[q] = (float)mem[q]; }
+                    __syncwarp();
+                    AgentView<PT> av;
+                    av.place = e.place(); av.cc = e.cpuc(); av.mc = e.memc(); av.c32 = nullptr; av.m32 = nullptr; av.sz32 = sz32;
+                    n_found = agent_act(e, av, p.agent, p.tiebreak);
+                    evaluated = true;
+                    if (p.out.d_action) {        // the action vector: proposals, else the current placement (firstfit.py:29)
+                        PT* ao = reinterpret_cast<PT*>(p.out.d_action) + env * (long long)L.V;
+                        for (int v = lane; v < L.V; v += 32)
+                            ao[v] = ((e.prop()[v >> 5] >> (v & 31)) & 1u) ? (PT)e.act()[v] : e.place()[v];
+                    }
+                }
+                have_actions = n_found > 0;
+            } else {
+                // external actions: stage the row and mark the slots whose action differs from their placement
+                const int adt = p.action_dtype;
+                const unsigned char* arow = reinterpret_cast<const unsigned char*>(p.action) + env * (long long)L.V * dtype_bytes(adt);
+                unsigned any = 0;
+                for (int c0 = 0; c0 < L.V; c0 += 32) {
+                    const int v = c0 + lane;
+                    const int a = v < L.V ? load_action(arow, adt, v) : 0;
+                    const bool diff = v < L.V && a != (int)e.place()[v];
+                    if (diff) e.act()[v] = (uint16_t)a;
+                    const unsigned m = __ballot_sync(FULL, diff);
+                    if (lane == 0) e.prop()[c0 >> 5] = m;
+                    any |= m;
+                }
+                __syncwarp();
+                have_actions = any != 0;
+            }
+            res = env_step(e, p, env, valid_g, have_actions);
+            if (res.changed) {
+                quiet = false;
+            } else if (evaluated) {
+                quiet = true;
+                quiet_key = n_found == 0 ? 0u : my_key;
+                quiet_rejected = res.rejected;
+            } else if (quiet && p.agent != VMGYM_AGENT_NONE) {
+                res.rejected = quiet_rejected;        // the skipped proposals would have been rejected again
+            }
+            if (p.out.d_stats) {
+                // running sums for the eval summary (record.py:98-134, exp_performance.py:104-113)
+                const double* cpu = e.cpu();
+                const double* mem = e.mem();
+                double sc_ = 0, sm_ = 0;
+                for (int q = lane; q < L.P; q += 32) { sc_ += cpu[q]; sm_ += mem[q]; }
+                const double mc = warp_sum(sc_) / L.P, mm = warp_sum(sm_) / L.P;
+                double vc = 0, vm = 0;
+                for (int q = lane; q < L.P; q += 32) {
+                    const double dc = cpu[q] - mc, dm = mem[q] - mm;
+                    vc += dc * dc; vm += dm * dm;
+                }
+                vc = warp_sum(vc) / L.P; vm = warp_sum(vm) / L.P;
+                const int tot = e.sc()->total_requests;
+                if (lane == 0) {
+                    st_acc[0] += tot ? (double)e.sc()->dropped_requests / (double)tot : 0.0;
+                    st_acc[1] += res.arrived ? (double)res.waiting / (double)res.arrived : 0.0;
+                    st_acc[2] += mc; st_acc[3] += vc; st_acc[4] += mm; st_acc[5] += vm;
+                    st_acc[6] += res.rejected; st_acc[7] += 1;
+                }
+            }
+            if (res.terminated) break;
+        }
+
+        // ---- outputs ----
+        if (p.out.d_obs) write_obs(e, p.out.d_obs + env * (long long)L.D);
+        if (lane == 0) {
+            e.sc()->status = (e.sc()->status & STATUS_EXHAUSTED) |
+                             (quiet ? (STATUS_QUIET | (quiet_key << STATUS_KEY_SHIFT) | ((uint32_t)quiet_rejected << 16)) : 0u);
+            if (p.out.d_reward) p.out.d_reward[env] = res.reward;
+            if (p.out.d_terminated) p.out.d_terminated[env] = (uint8_t)res.terminated;
+            if (p.out.d_stats) {
+                double* st = p.out.d_stats + env * 8;
+                for (int k = 0; k < 8; k++) st[k] += st_acc[k];
+            }
+        }
+
+        // ---- write the record back ----
+        if (BULK) {
+            fence_proxy_async();          // generic-proxy writes to smem -> visible to the async proxy
+            __syncwarp();
+            if (lane == 0) {
+                bulk_s2g(grec, base, (uint32_t)L.rec_bytes);
+                bulk_commit();
+                bulk_wait_read0();        // smem may be overwritten by the next bulk load after this
+            }
+            __syncwarp();
+        } else {
+            __syncwarp();
+            const uint4* src = reinterpret_cast<const uint4*>(base);
+            uint4* dst = reinterpret_cast<uint4*>(grec);
+            for (int i = lane; i < L.rec_bytes / 16; i += 32) dst[i] = src[i];
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// reset / observe / invalid-action mask / agent.act(obs)
+// ---------------------------------------------------------------------------------------------------
+template <typename PT>
+__global__ void reset_kernel(DevLayout L, unsigned char* state, long long n_envs, const uint8_t* env_mask,
+                             const uint64_t* seeds, int rewind, float* obs)
+{
+    const int lane = threadIdx.x & 31;
+    const long long env = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (env >= n_envs) return;
+    if (env_mask && !env_mask[env]) return;
+    unsigned char* rec = state + env * (long long)L.rec_bytes;
+    vmgym_env_scalars* sc = reinterpret_cast<vmgym_env_scalars*>(rec + L.off_scal);
+    vmgym_env_scalars keep = *sc;
+    __syncwarp();
+    uint4* r4 = reinterpret_cast<uint4*>(rec);
+    for (int i = lane; i < L.rec_bytes / 16; i += 32) r4[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    PT* place = reinterpret_cast<PT*>(rec + L.off_place);
+    for (int v = lane; v < L.Vp; v += 32) place[v] = (PT)(L.P + 1);      // env.py:187 (padding slots stay empty forever)
+    if (lane == 0) {
+        sc->timestep = 1;                                                 // env.py:197
+        sc->n_waiting = 0;
+        sc->n_empty = (uint16_t)L.V;
+        sc->seed = seeds ? seeds[env] : keep.seed;
+        sc->arrival_pos = rewind ? 0u : keep.arrival_pos;
+        sc->admission_pos = rewind ? 0u : keep.admission_pos;
+        sc->status = rewind ? 0u : (keep.status & STATUS_EXHAUSTED);
+    }
+    if (obs) {
+        float* o = obs + env * (long long)L.D;
+        for (int i = lane; i < L.D; i += 32) o[i] = i < L.V ? (float)(L.P + 1) : 0.0f;
+    }
+}
+
+template <typename PT>
+__global__ void observe_kernel(DevLayout L, const unsigned char* state, long long n_envs, float* obs)
+{
+    const int lane = threadIdx.x & 31;
+    const long long env = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (env >= n_envs) return;
+    const unsigned char* rec = state + env * (long long)L.rec_bytes;
+    const double* cpu = reinterpret_cast<const double*>(rec);
+    const double* mem = reinterpret_cast<const double*>(rec + L.off_mem);
+    const PT* place = reinterpret_cast<const PT*>(rec + L.off_place);
+    const uint8_t* cpuc = rec + L.off_cpuc;
+    const uint8_t* memc = rec + L.off_memc;
+    float* o = obs + env * (long long)L.D;
+    const int V = L.V, P = L.P;
+    for (int v = lane; v < V; v += 32) {
+        o[v] = (float)place[v];
+        o[V + v] = (float)((double)(cpuc[v] & 0x7f) / 100.0);
+        o[2 * V + v] = (float)((double)memc[v] / 100.0);
+    }
+    for (int q = lane; q < P; q += 32) { o[3 * V + q] = (float)cpu[q]; o[3 * V + P + q] = (float)mem[q]; }
+}
+
+// get_invalid_action_mask (env.py:45-53), evaluated against the current state (not sequentially).
+template <typename PT>
+__global__ void mask_kernel(DevLayout L, const unsigned char* state, long long n_envs, uint8_t* mask)
+{
+    const int lane = threadIdx.x & 31;
+    const long long env = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (env >= n_envs) return;
+    const unsigned char* rec = state + env * (long long)L.rec_bytes;
+    const double* cpu = reinterpret_cast<const double*>(rec);
+    const double* mem = reinterpret_cast<const double*>(rec + L.off_mem);
+    const PT* place = reinterpret_cast<const PT*>(rec + L.off_place);
+    const uint8_t* cpuc = rec + L.off_cpuc;
+    const uint8_t* memc = rec + L.off_memc;
+    const int V = L.V, P = L.P, A = L.A;
+    uint8_t* out = mask + env * (long long)V * A;
+    const long long total = (long long)V * A;
+    for (long long i = lane; i < total; i += 32) {
+        const int v = (int)(i / A), a = (int)(i - (long long)v * A);
+        const int cur = (int)place[v];
+        bool valid;
+        if (a == cur) valid = true;
+        else if (cur == P) {
+            valid = false;
+            if (a < P) {
+                const double vc = (double)(cpuc[v] & 0x7f) / 100.0, vm = (double)memc[v] / 100.0;
+                valid = (cpu[a] + vc <= 1.0) && (mem[a] + vm <= 1.0);
+            }
+        } else if (cur < P) valid = (a == P);
+        else valid = false;
+        out[i] = valid ? 0 : 1;
+    }
+}
+
+// agent.act(observation) on float32 observations [n_envs, D] (firstfit.py:21-38, bestfit.py:21-40).
+// per-warp shared memory: obs row f32[D] | place PT[Vp] | cc u8[Vp] | mc u8[Vp] | act u16[Vp] | tmp | fitm | cap | prop
+struct ActLayout { int row, place, cc, mc, act, tmp, fit, prop, stride; };
+__host__ __device__ inline ActLayout act_layout(const DevLayout& L)
+{
+    ActLayout a;
+    a.row = 0;
+    a.place = align_up(4 * L.D, 16);
+    a.cc = a.place + 2 * L.Vp;
+    a.mc = a.cc + L.Vp;
+    a.act = a.mc + L.Vp;
+    a.tmp = a.act + 2 * L.Vp;
+    a.fit = a.tmp + align_up(6 * L.Pp, 16);
+    a.prop = a.fit + 512 + align_up(2 * L.Pp, 16);
+    a.stride = align_up(a.prop + 4 * ((L.Vp + 31) / 32), 128);
+    return a;
+}
+
+template <typename PT>
+__global__ void act_kernel(DevLayout Lg, int agent, int tiebreak, const float* obs, long long n_envs, void* action, int adt)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ DevLayout L;                       // per-CTA layout whose scratch offsets point into the act layout
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    float* sz32 = reinterpret_cast<float*>(smem);
+    for (int k = threadIdx.x; k < SIZE_TABLE; k += blockDim.x) sz32[k] = (float)((double)k / 100.0);
+    const ActLayout al = act_layout(Lg);
+    if (threadIdx.x == 0) {
+        L = Lg;
+        L.sm_cpu32 = al.row + 4 * 3 * Lg.V;       // the row's cpu / memory segments are the agent's local loads
+        L.sm_mem32 = al.row + 4 * (3 * Lg.V + Lg.P);
+        L.sm_act = al.act; L.sm_tmp = al.tmp; L.sm_fit = al.fit; L.sm_prop = al.prop;
+    }
+    __syncthreads();
+    const long long env = (long long)blockIdx.x * wpc + warp;
+    if (env >= n_envs) return;
+    unsigned char* base = smem + SIZE_TABLE * 4 + (size_t)warp * al.stride;
+    float* row = reinterpret_cast<float*>(base + al.row);
+    PT* place = reinterpret_cast<PT*>(base + al.place);
+    uint8_t* cc = base + al.cc;
+    uint8_t* mc = base + al.mc;
+    const int V = Lg.V, P = Lg.P;
+    const float* o = obs + env * (long long)Lg.D;
+    for (int i = lane; i < Lg.D; i += 32) row[i] = o[i];
+    __syncwarp();
+    // slot arrays as the agent reads them (utils.py:41 astype(int)); a size that is not the float32 image of a
+    // hundredth gets code 0 so the fit filter never rejects it
+    for (int v = lane; v < Lg.Vp; v += 32) {
+        int pl = P + 1, kc = 0, km = 0;
+        if (v < V) {
+            pl = (int)row[v];
+            const float xc = row[V + v], xm = row[2 * V + v];
+            const int a = __float2int_rn(xc * 100.0f), b = __float2int_rn(xm * 100.0f);
+            const bool exact = a >= 0 && a <= 100 && b >= 0 && b <= 100 && sz32[a] == xc && sz32[b] == xm;
+            kc = exact ? a : 0; km = exact ? b : 0;
+            pl = pl < 0 ? P + 1 : min(pl, (sizeof(PT) == 1) ? 255 : 65535);
+        }
+        place[v] = (PT)pl; cc[v] = (uint8_t)kc; mc[v] = (uint8_t)km;
+    }
+    __syncwarp();
+    Env<PT> e;
+    e.base = base; e.L = &L; e.sz64 = nullptr; e.sz32 = sz32; e.arr_cdf = nullptr; e.svc_cdf = nullptr;
+    e.P = P; e.V = V; e.lane = lane;
+    AgentView<PT> av;
+    av.place = place; av.cc = cc; av.mc = mc; av.c32 = row + V; av.m32 = row + 2 * V; av.sz32 = sz32;
+    agent_act(e, av, agent, tiebreak);
+    unsigned char* ao = reinterpret_cast<unsigned char*>(action) + env * (long long)V * dtype_bytes(adt);
+    for (int v = lane; v < V; v += 32) {
+        const int a = ((e.prop()[v >> 5] >> (v & 31)) & 1u) ? (int)e.act()[v] : (int)row[v];
+        if (adt == VMGYM_U8) ao[v] = (uint8_t)a;
+        else if (adt == VMGYM_I16) reinterpret_cast<int16_t*>(ao)[v] = (int16_t)a;
+        else reinterpret_cast<long long*>(ao)[v] = a;
+    }
+}
+
+}  // namespace vmgym

@@ -70,7 +70,8 @@ class VmgymError(RuntimeError):
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu into vmgym/libvmgym.so (sm_100a, -lineinfo).  nvcc cross-compiles without a GPU."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "vmgym_device.cuh"), os.path.join(REPO_ROOT, "include", "vmgym.h")]
+    deps = srcs + [os.path.join(CSRC, h) for h in ("vmgym_device.cuh", "vmgym_sort.cuh", "vmgym_env_kernels.cuh")] + \
+        [os.path.join(REPO_ROOT, "include", "vmgym.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
