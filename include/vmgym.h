@@ -71,6 +71,8 @@ typedef struct vmgym_layout {
     int32_t obs_dim;            /* 3V + 2P (env.py:27,295-296) */
     int32_t action_dim;         /* A */
     int32_t smem_bytes_per_env; /* shared memory one resident env needs in the step kernels */
+    int32_t off_capacity;       /* u16[P]  derived cache: per-PM max admissible size codes in the float32 view
+                                   (cpu | mem << 8); maintained by every kernel that changes PM utilisation */
 } vmgym_layout;
 
 /* Per-env scalar block inside the record (env.py:193-208). */
@@ -106,6 +108,7 @@ typedef struct vmgym_trace {
     const uint64_t* d_arrival_cdf;  int32_t arrival_cdf_len;  int32_t arrival_kmin;
     const uint64_t* d_service_cdf;  int32_t service_cdf_len;  int32_t service_kmin;
     int32_t size_lo_code, size_hi_code;  /* 10..100 uniform, 10..65 lowuniform, 25..100 highuniform (env.py:211-219) */
+    const uint16_t* d_service_bracket;   /* optional u16[65]: #{i : service_cdf[i] <= b << 58} for b = 0..64 (search start) */
 } vmgym_trace;
 
 /* Optional per-step outputs; any pointer may be NULL. */

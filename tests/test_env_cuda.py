@@ -50,8 +50,21 @@ def _oracle_batch(cfg_kw, seeds, steps, adm):
     return envs
 
 
+_SZ32 = (np.arange(101) / 100.0).astype(np.float32)
+
+
+def _expected_caps(load64):
+    """max size code k with float32(load) + float32(k/100) <= 1 in float32 arithmetic (the agents' fit test)."""
+    x = load64.astype(np.float32)[:, None]
+    fits = (x + _SZ32[None, :]).astype(np.float32) <= np.float32(1.0)
+    return fits.sum(1).astype(np.int64) - 1
+
+
 def _compare_state(vec, oracles, t, check_reward=None):
     cnt = vec.counters()
+    L = vec._layout
+    caps = vec.state[:, L.off_capacity:L.off_capacity + 2 * vec.P].cpu().numpy().view(np.uint16)
+    slot = cnt["slot_counts"]
     for i, o in enumerate(oracles):
         s = vec.state_dict_host(i)
         so = o.state()
@@ -63,6 +76,11 @@ def _compare_state(vec, oracles, t, check_reward=None):
         for k in ("timestep", "total_requests", "served_requests", "dropped_requests", "suspend_action", "place_action",
                   "arr_cursor", "adm_cursor", "trace_exhausted"):
             assert s[k] == so[k], f"{k} env {i} step {t}: {s[k]} vs {so[k]}"
+        # derived caches kept in the record: per-PM capacity codes and the slot counters
+        assert np.array_equal(caps[i] & 0xff, _expected_caps(so["cpu"])), f"cpu capacity codes env {i} step {t}"
+        assert np.array_equal(caps[i] >> 8, _expected_caps(so["memory"])), f"memory capacity codes env {i} step {t}"
+        assert (slot[i] & 0xffff) == int((so["vm_placement"] == vec.P).sum()), f"n_waiting env {i} step {t}"
+        assert (slot[i] >> 16) == int((so["vm_placement"] == vec.P + 1).sum()), f"n_empty env {i} step {t}"
     return cnt
 
 

@@ -13,11 +13,12 @@ namespace vmgym {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int SIZE_TABLE = 128;   // size codes are hundredths 0..100 (7 bits)
+constexpr int SVC_BRACKETS = 64;  // the service inverse-CDF search starts from the bracket of the top 6 bits of u
 constexpr int ARR_CDF_SMEM = 64;  // arrival inverse-CDF thresholds kept in shared memory when the table is this small
 
 struct DevLayout {
     int P, V, A, Pp, Vp, D;
-    int off_mem, off_rem, off_place, off_cpuc, off_memc, off_scal, rec_bytes;
+    int off_mem, off_rem, off_place, off_cpuc, off_memc, off_cap, off_scal, rec_bytes;
     // per-warp shared memory (byte offsets from the warp's base)
     int sm_cpu32, sm_mem32, sm_act, sm_tmp, sm_fit, sm_prop, sm_stats, sm_bar, sm_stride;
     // CTA-wide shared memory

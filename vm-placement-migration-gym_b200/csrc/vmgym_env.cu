@@ -44,7 +44,8 @@ static int make_layout(const vmgym_config* c, DevLayout* L, vmgym_layout* pub)
     l.off_place = l.off_rem + 2 * l.Vp;
     l.off_cpuc = l.off_place + pb * l.Vp;
     l.off_memc = l.off_cpuc + l.Vp;
-    l.off_scal = l.off_memc + l.Vp;
+    l.off_cap = l.off_memc + l.Vp;
+    l.off_scal = l.off_cap + align_up(2 * l.Pp, 16);
     l.rec_bytes = align_up(l.off_scal + (int)sizeof(vmgym_env_scalars), 128);
     l.sm_cpu32 = l.rec_bytes;
     l.sm_mem32 = l.sm_cpu32 + align_up(4 * l.P, 16);
@@ -57,12 +58,12 @@ static int make_layout(const vmgym_config* c, DevLayout* L, vmgym_layout* pub)
     l.sm_bar = l.sm_stats + 64;
     l.sm_stride = align_up(l.sm_bar + 16, 128);
     l.svc_cdf_smem = 0;                                    // service table stays in global memory (used on admissions only)
-    l.sm_tables = SIZE_TABLE * 8 + SIZE_TABLE * 4 + ARR_CDF_SMEM * 8 + l.svc_cdf_smem * 8;
+    l.sm_tables = align_up(SIZE_TABLE * 8 + SIZE_TABLE * 4 + ARR_CDF_SMEM * 8 + l.svc_cdf_smem * 8 + (SVC_BRACKETS + 1) * 2, 128);
     if (L) *L = l;
     if (pub) {
         pub->record_bytes = l.rec_bytes; pub->pms_padded = l.Pp; pub->vms_padded = l.Vp; pub->place_bytes = pb;
         pub->off_cpu = 0; pub->off_memory = l.off_mem; pub->off_remaining = l.off_rem; pub->off_placement = l.off_place;
-        pub->off_cpu_code = l.off_cpuc; pub->off_mem_code = l.off_memc; pub->off_scalars = l.off_scal;
+        pub->off_cpu_code = l.off_cpuc; pub->off_mem_code = l.off_memc; pub->off_scalars = l.off_scal; pub->off_capacity = l.off_cap;
         pub->obs_dim = l.D; pub->action_dim = l.A; pub->smem_bytes_per_env = l.sm_stride;
     }
     return VMGYM_OK;

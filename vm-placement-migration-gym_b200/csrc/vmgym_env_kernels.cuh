@@ -47,6 +47,7 @@ struct Env {
     const float* sz32;                 // code -> (float)(k/100.0)   (env.py:296)
     const uint64_t* arr_cdf;           // arrival / service inverse-CDF thresholds (shared-memory copies when small)
     const uint64_t* svc_cdf;
+    const uint16_t* svc_bracket;       // 65-entry search brackets of the service table (shared memory) or nullptr
     int P, V, lane;
 
     __device__ __forceinline__ double* cpu() const { return reinterpret_cast<double*>(base); }           // env.py:190
@@ -55,6 +56,9 @@ struct Env {
     __device__ __forceinline__ PT* place() const { return reinterpret_cast<PT*>(base + L->off_place); }
     __device__ __forceinline__ uint8_t* cpuc() const { return base + L->off_cpuc; }                      // bit 7 = suspended
     __device__ __forceinline__ uint8_t* memc() const { return base + L->off_memc; }
+    // capacity codes of every PM in the agents' float32 view, kept consistent with cpu()/mem() by every update:
+    // rcap[p] = kc | km << 8 with kc = max{k : (float)cpu[p] + sz32[k] <= 1.0f} (likewise km for memory)
+    __device__ __forceinline__ uint16_t* rcap() const { return reinterpret_cast<uint16_t*>(base + L->off_cap); }
     __device__ __forceinline__ vmgym_env_scalars* sc() const { return reinterpret_cast<vmgym_env_scalars*>(base + L->off_scal); }
     // scratch (not part of the record)
     __device__ __forceinline__ float* cpu32() const { return reinterpret_cast<float*>(base + L->sm_cpu32); }  // agents' fp32 view
@@ -97,21 +101,31 @@ __device__ __forceinline__ int max_code(const float* sz32, float x)
     return k;
 }
 
+template <typename PT>
+__device__ __forceinline__ void refresh_cap(const Env<PT>& e, int p)
+{
+    e.rcap()[p] = (uint16_t)(max_code(e.sz32, (float)e.cpu()[p]) | (max_code(e.sz32, (float)e.mem()[p]) << 8));
+}
+
 // fitm[c] = 1 + max{ mem-capacity code of PM p : cpu-capacity code of p >= c }, 0 if no PM takes cpu code c.
 // A VM with size codes (c, m) fits on SOME PM iff m + 1 <= fitm[c] — an exact O(1) test that removes the hopeless
 // waiting VMs (the large majority at saturation) from the sequential scan.
+// Returns (max cpu capacity code) | (max mem capacity code) << 8 over all PMs, for the cheap byte pre-filter.
 template <typename PT>
-__device__ __forceinline__ void rebuild_fit_table(const Env<PT>& e)
+__device__ __forceinline__ unsigned rebuild_fit_table(const Env<PT>& e)
 {
     const int lane = e.lane;
     unsigned* fitm = e.fitm();
     const uint16_t* cap = e.cap();
     reinterpret_cast<uint4*>(fitm)[lane] = make_uint4(0u, 0u, 0u, 0u);
     __syncwarp();
+    unsigned kcmax = 0, kmmax = 0;
     for (int p = lane; p < e.P; p += 32) {
         const unsigned w = cap[p];
         atomicMax(&fitm[w & 0xffu], (w >> 8) + 1u);
+        kcmax = max(kcmax, w & 0xffu); kmmax = max(kmmax, w >> 8);
     }
+    kcmax = __reduce_max_sync(FULL, kcmax); kmmax = __reduce_max_sync(FULL, kmmax);
     __syncwarp();
     uint4 q = reinterpret_cast<uint4*>(fitm)[lane];            // lane owns codes 4*lane .. 4*lane+3
     q.z = max(q.z, q.w); q.y = max(q.y, q.z); q.x = max(q.x, q.y);
@@ -126,15 +140,18 @@ __device__ __forceinline__ void rebuild_fit_table(const Env<PT>& e)
     q.x = max(q.x, ex); q.y = max(q.y, ex); q.z = max(q.z, ex); q.w = max(q.w, ex);
     reinterpret_cast<uint4*>(fitm)[lane] = q;
     __syncwarp();
+    return kcmax | (kmmax << 8);
 }
 
 // candidate bits of the 4 slots 4g..4g+3 (u8 placements): waiting VMs that fit on some PM
-__device__ __forceinline__ unsigned cand_bits4(uint32_t pl4, uint32_t cc4, uint32_t mc4, uint32_t P4, const unsigned* fitm)
+__device__ __forceinline__ unsigned cand_bits4(uint32_t pl4, uint32_t cc4, uint32_t mc4, uint32_t P4, const unsigned* fitm,
+                                               unsigned kmax)
 {
-    const uint32_t w4 = __vcmpeq4(pl4, P4);
+    cc4 &= 0x7f7f7f7fu;
+    // waiting, and not larger than the largest free cpu / memory capacity of any PM (cheap necessary condition)
+    const uint32_t w4 = __vcmpeq4(pl4, P4) & __vcmpleu4(cc4, (kmax & 0xffu) * 0x01010101u) & __vcmpleu4(mc4, (kmax >> 8) * 0x01010101u);
     unsigned c = 0;
     if (w4) {
-        cc4 &= 0x7f7f7f7fu;
 #pragma unroll
         for (int j = 0; j < 4; j++)
             if ((w4 >> (8 * j)) & 1u) c |= (((mc4 >> (8 * j)) & 0xffu) + 1u <= fitm[(cc4 >> (8 * j)) & 0xffu]) ? (1u << j) : 0u;
@@ -150,7 +167,7 @@ __device__ __forceinline__ unsigned cand_bits4(uint32_t pl4, uint32_t cc4, uint3
 // Returns the number of proposals.
 // ---------------------------------------------------------------------------------------------------
 template <typename PT>
-__device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& av, int agent, int tiebreak)
+__device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& av, int agent, int tiebreak, bool have_rcap)
 {
     const int P = e.P, V = e.V, lane = e.lane;
     float* cpu32 = e.cpu32();
@@ -158,9 +175,12 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
     uint16_t* cap = e.cap();
     const unsigned* fitm = e.fitm();
     int n_found = 0;
-    for (int p = lane; p < P; p += 32) cap[p] = (uint16_t)(max_code(e.sz32, cpu32[p]) | (max_code(e.sz32, mem32[p]) << 8));
+    // local capacity codes: the record's (fused kernel) or computed from the observed loads (act_kernel); the agent's
+    // own proposals then shrink this local copy only, like the reference's local cpu/memory arrays
+    if (have_rcap) { for (int p = lane; p < P; p += 32) cap[p] = e.rcap()[p]; }
+    else { for (int p = lane; p < P; p += 32) cap[p] = (uint16_t)(max_code(e.sz32, cpu32[p]) | (max_code(e.sz32, mem32[p]) << 8)); }
     for (int c = lane; c < (V + 31) / 32; c += 32) e.prop()[c] = 0u;
-    rebuild_fit_table(e);
+    unsigned kmax = rebuild_fit_table(e);
 
     // slots are visited in groups: 4 per lane (128 per pass) for byte placements, 1 per lane otherwise
     constexpr int SPL = sizeof(PT) == 1 ? 4 : 1;
@@ -172,7 +192,7 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
         if (u < n_units) {
             if (SPL == 4) {
                 cb = cand_bits4(reinterpret_cast<const uint32_t*>(av.place)[u], reinterpret_cast<const uint32_t*>(av.cc)[u],
-                                reinterpret_cast<const uint32_t*>(av.mc)[u], P4, fitm);
+                                reinterpret_cast<const uint32_t*>(av.mc)[u], P4, fitm, kmax);
             } else {
                 cb = ((int)av.place[u] == P && (unsigned)av.mc[u] + 1u <= fitm[av.cc[u] & 0x7f]) ? 1u : 0u;
             }
@@ -250,13 +270,13 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
                     placed_any = true;
                     if (lane == 0) { e.act()[vv] = (uint16_t)found; e.prop()[vv >> 5] |= 1u << (vv & 31); }
                     __syncwarp();
-                    rebuild_fit_table(e);          // capacities shrank: the remaining candidates are re-tested
+                    kmax = rebuild_fit_table(e);   // capacities shrank: the remaining candidates are re-tested
                     if (bits) {
                         unsigned nb;
                         if (SPL == 4) {
                             const int ub = u0 + b;
                             nb = cand_bits4(reinterpret_cast<const uint32_t*>(av.place)[ub], reinterpret_cast<const uint32_t*>(av.cc)[ub],
-                                            reinterpret_cast<const uint32_t*>(av.mc)[ub], P4, fitm);
+                                            reinterpret_cast<const uint32_t*>(av.mc)[ub], P4, fitm, kmax);
                         } else nb = 0;
                         bits &= nb;
                     }
@@ -268,7 +288,7 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
                 if (u < n_units && lane > b) {
                     if (SPL == 4)
                         cb = cand_bits4(reinterpret_cast<const uint32_t*>(av.place)[u], reinterpret_cast<const uint32_t*>(av.cc)[u],
-                                        reinterpret_cast<const uint32_t*>(av.mc)[u], P4, fitm);
+                                        reinterpret_cast<const uint32_t*>(av.mc)[u], P4, fitm, kmax);
                     else
                         cb = ((int)av.place[u] == P && (unsigned)av.mc[u] + 1u <= fitm[av.cc[u] & 0x7f]) ? 1u : 0u;
                 }
@@ -328,6 +348,15 @@ __device__ __forceinline__ int cdf_search(const uint64_t* cdf, int len, uint64_t
     return min(lo, len - 1);
 }
 
+// same result as cdf_search, started from the bracket of the top 6 bits of u: bracket[b] = #{i : cdf[i] <= b << 58}
+__device__ __forceinline__ int cdf_search_bracketed(const uint64_t* cdf, int len, const uint16_t* bracket, uint64_t u)
+{
+    const int b = (int)(u >> 58);
+    int lo = bracket[b], hi = bracket[b + 1];
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+    return min(lo, len - 1);
+}
+
 struct StepResult { double reward; int terminated; int rejected; int waiting, arrived; int changed; };
 
 // ---------------------------------------------------------------------------------------------------
@@ -371,7 +400,10 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                             ok = true;
                             n_place++;
                             __syncwarp();
-                            if (lane == 0) { cpu[a] = nc; mem[a] = nm; place[vv] = (PT)a; cpuc[vv] &= 0x7f; }   // :82-85
+                            if (lane == 0) {                                                                   // :82-85
+                                cpu[a] = nc; mem[a] = nm; place[vv] = (PT)a; cpuc[vv] &= 0x7f;
+                                e.rcap()[a] = (uint16_t)(max_code(e.sz32, (float)nc) | (max_code(e.sz32, (float)nm) << 8));
+                            }
                         }
                     }
                 } else if (cv < P) {                             // running VM: only suspend is legal (:40-41,78-81)
@@ -381,7 +413,10 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                         const double nc = cpu[cv] - e.sz64[cpuc[vv] & 0x7f];
                         const double nm = mem[cv] - e.sz64[memc[vv]];
                         __syncwarp();
-                        if (lane == 0) { cpu[cv] = nc; mem[cv] = nm; place[vv] = (PT)P; cpuc[vv] |= 0x80; }
+                        if (lane == 0) {
+                            cpu[cv] = nc; mem[cv] = nm; place[vv] = (PT)P; cpuc[vv] |= 0x80;
+                            e.rcap()[cv] = (uint16_t)(max_code(e.sz32, (float)nc) | (max_code(e.sz32, (float)nm) << 8));
+                        }
                     }
                 }
                 __syncwarp();
@@ -396,6 +431,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
 
     // ---- 2+3. service countdown and departures in VM-index order (_run_vms, env.py:244-265) ----
     int served = 0;
+    bool need_full_refresh = false;
     if (sizeof(PT) == 1) {
         // 4 slots per lane: placement bytes as one u32, remaining runtimes as 4 x u16 (padding slots are empty)
         const uint32_t P4 = (uint32_t)P * 0x01010101u;
@@ -433,6 +469,9 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                             const int vv = 4 * (g0 + b) + j, pm = (int)place[vv];
                             cpu[pm] -= e.sz64[cpuc[vv] & 0x7f];
                             mem[pm] -= e.sz64[memc[vv]];
+                            if (cpu[pm] < 1e-7) cpu[pm] = 0.0;           // :267-268 clamp, applied here for this PM
+                            if (mem[pm] < 1e-7) mem[pm] = 0.0;
+                            refresh_cap(e, pm);
                             place[vv] = (PT)(P + 1); cpuc[vv] = 0; memc[vv] = 0; rem[vv] = 0;
                         }
                     }
@@ -463,6 +502,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                 }
                 __syncwarp();
                 if (term) { place[v] = (PT)(P + 1); cpuc[v] = 0; memc[v] = 0; rem[v] = 0; }
+                need_full_refresh = true;
             }
         }
     }
@@ -470,9 +510,12 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
     // ---- 4. clamp (env.py:267-268): values only shrink when something was subtracted this step ----
     if (served > 0 || n_susp > 0) {
         for (int q = lane; q < P; q += 32) {
-            if (cpu[q] < 1e-7) cpu[q] = 0.0;
-            if (mem[q] < 1e-7) mem[q] = 0.0;
+            bool ch = need_full_refresh;
+            if (cpu[q] < 1e-7 && cpu[q] != 0.0) { cpu[q] = 0.0; ch = true; }
+            if (mem[q] < 1e-7 && mem[q] != 0.0) { mem[q] = 0.0; ch = true; }
+            if (ch) refresh_cap(e, q);
         }
+        __syncwarp();
     }
 
     // ---- 5. arrivals (_accept_vm_requests, env.py:271-293) ----
@@ -513,7 +556,10 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                     const uint32_t span = 2u * (uint32_t)(tr.size_hi_code - tr.size_lo_code);
                     cc = (uint32_t)tr.size_lo_code + ((mulhi32(r.x, span) + 1u) >> 1);
                     mc = (uint32_t)tr.size_lo_code + ((mulhi32(r.y, span) + 1u) >> 1);
-                    svc = (uint32_t)(tr.service_kmin + cdf_search(e.svc_cdf, tr.service_cdf_len, ((uint64_t)r.z << 32) | r.w)) + 1u;  // :289
+                    const uint64_t us = ((uint64_t)r.z << 32) | r.w;
+                    const int ks = e.svc_bracket ? cdf_search_bracketed(e.svc_cdf, tr.service_cdf_len, e.svc_bracket, us)
+                                                 : cdf_search(e.svc_cdf, tr.service_cdf_len, us);
+                    svc = (uint32_t)(tr.service_kmin + ks) + 1u;                                  // Poisson + 1 (:289)
                 }
                 place[v] = (PT)P;
                 cpuc[v] = (uint8_t)cc; memc[v] = (uint8_t)mc; rem[v] = (uint16_t)svc;
@@ -662,6 +708,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
     float* sz32 = reinterpret_cast<float*>(smem + SIZE_TABLE * 8);
     uint64_t* arr_cdf_s = reinterpret_cast<uint64_t*>(smem + SIZE_TABLE * 12);
     uint64_t* svc_cdf_s = arr_cdf_s + ARR_CDF_SMEM;
+    uint16_t* svc_bracket_s = reinterpret_cast<uint16_t*>(svc_cdf_s + L.svc_cdf_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     unsigned char* base = smem + L.sm_tables + (size_t)warp * L.sm_stride;
     uint64_t* bar = reinterpret_cast<uint64_t*>(base + L.sm_bar);
@@ -673,6 +720,9 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
         for (int k = threadIdx.x; k < p.tr.arrival_cdf_len; k += blockDim.x) arr_cdf_s[k] = p.tr.d_arrival_cdf[k];
     if (svc_in_smem)
         for (int k = threadIdx.x; k < p.tr.service_cdf_len; k += blockDim.x) svc_cdf_s[k] = p.tr.d_service_cdf[k];
+    const bool have_bracket = philox && p.tr.d_service_bracket != nullptr;
+    if (have_bracket)
+        for (int k = threadIdx.x; k < SVC_BRACKETS + 1; k += blockDim.x) svc_bracket_s[k] = p.tr.d_service_bracket[k];
     const bool BULK = p.use_bulk != 0;
     if (BULK && lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
     __syncthreads();
@@ -681,6 +731,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
     e.base = base; e.L = &p.L; e.sz64 = sz64; e.sz32 = sz32; e.P = L.P; e.V = L.V; e.lane = lane;
     e.arr_cdf = arr_in_smem ? arr_cdf_s : p.tr.d_arrival_cdf;
     e.svc_cdf = svc_in_smem ? svc_cdf_s : p.tr.d_service_cdf;
+    e.svc_bracket = have_bracket ? svc_bracket_s : nullptr;
     uint32_t phase = 0;
     const long long stride = (long long)gridDim.x * wpc;
     for (long long env = (long long)blockIdx.x * wpc + warp; env < p.n_envs; env += stride) {
@@ -729,7 +780,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
                     __syncwarp();
                     AgentView<PT> av;
                     av.place = e.place(); av.cc = e.cpuc(); av.mc = e.memc(); av.c32 = nullptr; av.m32 = nullptr; av.sz32 = sz32;
-                    n_found = agent_act(e, av, p.agent, p.tiebreak);
+                    n_found = agent_act(e, av, p.agent, p.tiebreak, true);
                     evaluated = true;
                     if (p.out.d_action) {        // the action vector: proposals, else the current placement (firstfit.py:29)
                         PT* ao = reinterpret_cast<PT*>(p.out.d_action) + env * (long long)L.V;
@@ -842,6 +893,8 @@ __global__ void reset_kernel(DevLayout L, unsigned char* state, long long n_envs
     __syncwarp();
     PT* place = reinterpret_cast<PT*>(rec + L.off_place);
     for (int v = lane; v < L.Vp; v += 32) place[v] = (PT)(L.P + 1);      // env.py:187 (padding slots stay empty forever)
+    uint16_t* rcap = reinterpret_cast<uint16_t*>(rec + L.off_cap);
+    for (int q = lane; q < L.P; q += 32) rcap[q] = (uint16_t)(100u | (100u << 8));   // empty PM: every size code fits
     if (lane == 0) {
         sc->timestep = 1;                                                 // env.py:197
         sc->n_waiting = 0;
@@ -973,11 +1026,11 @@ __global__ void act_kernel(DevLayout Lg, int agent, int tiebreak, const float* o
     }
     __syncwarp();
     Env<PT> e;
-    e.base = base; e.L = &L; e.sz64 = nullptr; e.sz32 = sz32; e.arr_cdf = nullptr; e.svc_cdf = nullptr;
+    e.base = base; e.L = &L; e.sz64 = nullptr; e.sz32 = sz32; e.arr_cdf = nullptr; e.svc_cdf = nullptr; e.svc_bracket = nullptr;
     e.P = P; e.V = V; e.lane = lane;
     AgentView<PT> av;
     av.place = place; av.cc = cc; av.mc = mc; av.c32 = row + V; av.m32 = row + 2 * V; av.sz32 = sz32;
-    agent_act(e, av, agent, tiebreak);
+    agent_act(e, av, agent, tiebreak, false);
     unsigned char* ao = reinterpret_cast<unsigned char*>(action) + env * (long long)V * dtype_bytes(adt);
     for (int v = lane; v < V; v += 32) {
         const int a = ((e.prop()[v >> 5] >> (v & 31)) & 1u) ? (int)e.act()[v] : (int)row[v];

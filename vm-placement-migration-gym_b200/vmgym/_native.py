@@ -37,7 +37,7 @@ class Layout(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "record_bytes", "pms_padded", "vms_padded", "place_bytes", "off_cpu", "off_memory", "off_remaining",
         "off_placement", "off_cpu_code", "off_mem_code", "off_scalars", "obs_dim", "action_dim",
-        "smem_bytes_per_env")]
+        "smem_bytes_per_env", "off_capacity")]
 
 
 class Trace(C.Structure):
@@ -46,7 +46,7 @@ class Trace(C.Structure):
                 ("d_admissions", C.c_void_p), ("admissions_len", C.c_int64),
                 ("d_arrival_cdf", C.c_void_p), ("arrival_cdf_len", C.c_int32), ("arrival_kmin", C.c_int32),
                 ("d_service_cdf", C.c_void_p), ("service_cdf_len", C.c_int32), ("service_kmin", C.c_int32),
-                ("size_lo_code", C.c_int32), ("size_hi_code", C.c_int32)]
+                ("size_lo_code", C.c_int32), ("size_hi_code", C.c_int32), ("d_service_bracket", C.c_void_p)]
 
 
 class Outputs(C.Structure):

@@ -106,5 +106,13 @@ def poisson_cdf_table(lam: float):
     return kmin, np.array(th, dtype=np.uint64)
 
 
+def cdf_brackets(thresholds: np.ndarray, bits: int = 6) -> np.ndarray:
+    """u16[2^bits + 1]: bracket[b] = #{i : thresholds[i] <= b << (64 - bits)}, bracket[2^bits] = len (search start)."""
+    n = 1 << bits
+    edges = (np.arange(n, dtype=np.uint64) << np.uint64(64 - bits))
+    lo = np.searchsorted(thresholds, edges, side="right")
+    return np.concatenate([lo, [len(thresholds)]]).astype(np.uint16)
+
+
 def size_code_range(sequence: str):
     return SEQUENCE_CODES[sequence]

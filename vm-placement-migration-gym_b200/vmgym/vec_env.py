@@ -21,7 +21,7 @@ import torch
 
 from . import _native as nv
 from .config import Config
-from .trace import EnvStreams, poisson_cdf_table, sample_numpy_traces, size_code_range
+from .trace import EnvStreams, cdf_brackets, poisson_cdf_table, sample_numpy_traces, size_code_range
 
 import contextlib
 
@@ -157,10 +157,12 @@ class VecVmEnv:
                     d_ta = torch.from_numpy(ta.view(np.int64)).to(self.device)
                     d_ts = torch.from_numpy(ts.view(np.int64)).to(self.device)
                     lo, hi = size_code_range(self.config.sequence)
-                    self._trace_tensors = (d_ta, d_ts)
+                    d_br = torch.from_numpy(cdf_brackets(ts).view(np.int16)).to(self.device) if len(ts) < 65536 else None
+                    self._trace_tensors = (d_ta, d_ts, d_br)
                     self._trace = nv.Trace(mode=nv.TRACE_PHILOX, d_arrival_cdf=d_ta.data_ptr(), arrival_cdf_len=len(ta),
                                            arrival_kmin=ka, d_service_cdf=d_ts.data_ptr(), service_cdf_len=len(ts),
-                                           service_kmin=ks, size_lo_code=lo, size_hi_code=hi)
+                                           service_kmin=ks, size_lo_code=lo, size_hi_code=hi,
+                                           d_service_bracket=d_br.data_ptr() if d_br is not None else None)
                     self.philox_tables = (ka, ta, ks, ts, lo, hi)
                 if getattr(self, "_reseeded", False):
                     d_seeds = torch.from_numpy(self._seeds.copy()).to(self.device)
