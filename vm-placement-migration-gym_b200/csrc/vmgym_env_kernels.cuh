@@ -93,7 +93,7 @@ __device__ __forceinline__ double warp_sum(double x)
 }
 
 // largest size code k in [0,100] with x + sz32[k] <= 1.0f (monotone in k because fp32 rounding is monotone)
-__device__ __forceinline__ int max_code(const float* sz32, float x)
+__device__ __noinline__ int max_code(const float* sz32, float x)
 {
     int k = min(100, max(0, (int)((1.0f - x) * 100.0f)));      // estimate, then exact correction (usually 1-2 probes)
     while (k < 100 && x + sz32[k + 1] <= 1.0f) k++;
@@ -112,7 +112,7 @@ __device__ __forceinline__ void refresh_cap(const Env<PT>& e, int p)
 // waiting VMs (the large majority at saturation) from the sequential scan.
 // Returns (max cpu capacity code) | (max mem capacity code) << 8 over all PMs, for the cheap byte pre-filter.
 template <typename PT>
-__device__ __forceinline__ unsigned rebuild_fit_table(const Env<PT>& e)
+__device__ __noinline__ unsigned rebuild_fit_table(const Env<PT> e)
 {
     const int lane = e.lane;
     unsigned* fitm = e.fitm();
@@ -341,11 +341,41 @@ __device__ __noinline__ double reward_kl(const double* cpu, const double* mem, i
     return -(0.5 * (log(det_q / det_p) - 2 + trace_term + m1 - trace_term));
 }
 
+__device__ __noinline__ Philox4 philox_dev(uint32_t c0, uint32_t c2, uint32_t k0, uint32_t k1)
+{
+    return philox4x32_10(c0, 0u, c2, 0u, k0, k1);
+}
+
 __device__ __forceinline__ int cdf_search(const uint64_t* cdf, int len, uint64_t u)
 {
     int lo = 0, hi = len;            // first i with cdf[i] > u
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
     return min(lo, len - 1);
+}
+
+// `kl` reward of one env: compact vm_cpu[existing], vm_memory[existing] in slot order (the reference's boolean
+// indexing, env.py:113,129-130) and evaluate reward_kl.
+template <typename PT>
+__device__ __noinline__ double reward_kl_env(const Env<PT> e, int arrived, int cap_target)
+{
+    const int P = e.P, V = e.V, lane = e.lane;
+    const PT* place = e.place();
+    uint8_t* ex_cc = e.tmp();
+    uint8_t* ex_mc = e.tmp() + ((V + 15) & ~15);
+    int pos0 = 0;
+    for (int c0 = 0; c0 < V; c0 += 32) {
+        const int v = c0 + lane;
+        const bool ex = v < V && (int)place[v] <= P;
+        const unsigned mx = __ballot_sync(FULL, ex);
+        if (ex) {
+            const int pos = pos0 + __popc(mx & ((1u << lane) - 1u));
+            ex_cc[pos] = e.cpuc()[v] & 0x7f;
+            ex_mc[pos] = e.memc()[v];
+        }
+        pos0 += __popc(mx);
+    }
+    __syncwarp();
+    return reward_kl(e.cpu(), e.mem(), P, ex_cc, ex_mc, arrived, e.sz64, cap_target);
 }
 
 // same result as cdf_search, started from the bracket of the top 6 bits of u: bracket[b] = #{i : cdf[i] <= b << 58}
@@ -358,6 +388,32 @@ __device__ __forceinline__ int cdf_search_bracketed(const uint64_t* cdf, int len
 }
 
 struct StepResult { double reward; int terminated; int rejected; int waiting, arrived; int changed; };
+
+// running sums for the eval summary (record.py:98-134, exp_performance.py:104-113): drop rate, waiting ratio,
+// per-step mean / population variance of PM cpu and memory, rejected actions, step count
+template <typename PT>
+__device__ __noinline__ void stats_update(const Env<PT> e, const StepResult res, double* st_acc)
+{
+    const int P = e.P, lane = e.lane;
+    const double* cpu = e.cpu();
+    const double* mem = e.mem();
+    double sc_ = 0, sm_ = 0;
+    for (int q = lane; q < P; q += 32) { sc_ += cpu[q]; sm_ += mem[q]; }
+    const double mc = warp_sum(sc_) / P, mm = warp_sum(sm_) / P;
+    double vc = 0, vm = 0;
+    for (int q = lane; q < P; q += 32) {
+        const double dc = cpu[q] - mc, dm = mem[q] - mm;
+        vc += dc * dc; vm += dm * dm;
+    }
+    vc = warp_sum(vc) / P; vm = warp_sum(vm) / P;
+    if (lane == 0) {
+        const int tot = e.sc()->total_requests;
+        st_acc[0] += tot ? (double)e.sc()->dropped_requests / (double)tot : 0.0;
+        st_acc[1] += res.arrived ? (double)res.waiting / (double)res.arrived : 0.0;
+        st_acc[2] += mc; st_acc[3] += vc; st_acc[4] += mm; st_acc[5] += vm;
+        st_acc[6] += res.rejected; st_acc[7] += 1;
+    }
+}
 
 // ---------------------------------------------------------------------------------------------------
 // One env.step on the shared-memory record.  The action vector is given as act[v] for the slots whose bit is
@@ -528,7 +584,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
         if ((long long)arrival_pos < tr.arrivals_len) n_arr = tr.d_arrivals[env_id * tr.arrivals_len + arrival_pos];
         else exhausted = 1;
     } else {
-        const Philox4 r = philox4x32_10(arrival_pos, 0u, 1u, 0u, k0, k1);
+        const Philox4 r = philox_dev(arrival_pos, 1u, k0, k1);
         n_arr = tr.arrival_kmin + cdf_search(e.arr_cdf, tr.arrival_cdf_len, ((uint64_t)r.x << 32) | r.y);
     }
     int quota = n_arr;                                         // admissions still allowed this step
@@ -552,7 +608,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                     const uint32_t w = tr.d_admissions[env_id * tr.admissions_len + j];
                     cc = w & 0xff; mc = (w >> 8) & 0xff; svc = w >> 16;
                 } else {
-                    const Philox4 r = philox4x32_10(j, 0u, 2u, 0u, k0, k1);
+                    const Philox4 r = philox_dev(j, 2u, k0, k1);
                     const uint32_t span = 2u * (uint32_t)(tr.size_hi_code - tr.size_lo_code);
                     cc = (uint32_t)tr.size_lo_code + ((mulhi32(r.x, span) + 1u) >> 1);
                     mc = (uint32_t)tr.size_lo_code + ((mulhi32(r.y, span) + 1u) >> 1);
@@ -586,23 +642,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
         } else if (p.reward_fn == VMGYM_REWARD_UT) {
             reward = reward_ut(cpu, mem, P, p.beta);
         } else {
-            // compacted vm_cpu[existing], vm_memory[existing] in slot order (the reference's boolean indexing)
-            uint8_t* ex_cc = e.tmp();
-            uint8_t* ex_mc = e.tmp() + ((V + 15) & ~15);
-            int pos0 = 0;
-            for (int c0 = 0; c0 < V; c0 += 32) {
-                const int v = c0 + lane;
-                const bool ex = v < V && (int)place[v] <= P;
-                const unsigned mx = __ballot_sync(FULL, ex);
-                if (ex) {
-                    const int pos = pos0 + __popc(mx & ((1u << lane) - 1u));
-                    ex_cc[pos] = cpuc[v] & 0x7f;
-                    ex_mc[pos] = memc[v];
-                }
-                pos0 += __popc(mx);
-            }
-            __syncwarp();
-            reward = reward_kl(cpu, mem, P, ex_cc, ex_mc, arrived, e.sz64, p.cap_target);
+            reward = reward_kl_env(e, arrived, p.cap_target);
         }
     }
 
@@ -631,6 +671,21 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
     res.reward = reward; res.terminated = terminated; res.rejected = rejected; res.waiting = waiting; res.arrived = arrived;
     res.changed = n_place + n_susp + served + admitted;      // anything that can change which waiting VMs fit
     return res;
+}
+
+template <typename PT>
+__device__ __noinline__ void write_obs_generic(const Env<PT> e, float* __restrict__ o)
+{
+    const int P = e.P, V = e.V;
+    const PT* place = e.place();
+    const uint8_t* cpuc = e.cpuc();
+    const uint8_t* memc = e.memc();
+    const double* cpu = e.cpu();
+    const double* mem = e.mem();
+#pragma unroll 1
+    for (int v = e.lane; v < V; v += 32) { o[v] = (float)place[v]; o[V + v] = e.sz32[cpuc[v] & 0x7f]; o[2 * V + v] = e.sz32[memc[v]]; }
+#pragma unroll 1
+    for (int q = e.lane; q < P; q += 32) { o[3 * V + q] = (float)cpu[q]; o[3 * V + P + q] = (float)mem[q]; }
 }
 
 // observation row (env.py:295-296): f32[ placement | vm_cpu | vm_memory | cpu | memory ]
@@ -665,20 +720,27 @@ __device__ __forceinline__ void write_obs(const Env<PT>& e, float* __restrict__ 
         }
         return;
     }
-    for (int v = e.lane; v < V; v += 32) o[v] = (float)place[v];
-    for (int v = e.lane; v < V; v += 32) o[V + v] = e.sz32[cpuc[v] & 0x7f];
-    for (int v = e.lane; v < V; v += 32) o[2 * V + v] = e.sz32[memc[v]];
-    for (int q = e.lane; q < P; q += 32) o[3 * V + q] = (float)cpu[q];
-    for (int q = e.lane; q < P; q += 32) o[3 * V + P + q] = (float)mem[q];
+    write_obs_generic(e, o);
 }
 
-__device__ __forceinline__ void fill_tables(double* sz64, float* sz32)
+__device__ __noinline__ void fill_tables(double* sz64, float* sz32)
 {
     for (int k = threadIdx.x; k < SIZE_TABLE; k += blockDim.x) {
         const double x = (double)k / 100.0;      // == np.around(u, 2) for the code k (env.py:212-219)
         sz64[k] = x;
         sz32[k] = (float)x;                        // env.py:296 float32 cast
     }
+}
+
+// plain 128-bit copy of a record (the non-bulk fallback of the staging path)
+__device__ __noinline__ void copy16(void* dst, const void* src, int bytes, int lane)
+{
+    __syncwarp();
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll 1
+    for (int i = lane; i < bytes / 16; i += 32) d4[i] = s4[i];
+    __syncwarp();
 }
 
 // action element -> int; anything outside [0, 65534] becomes 0xFFFF, which matches no placement value and
@@ -745,10 +807,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
             mbar_wait(bar, phase);
             phase ^= 1;
         } else {
-            const uint4* src = reinterpret_cast<const uint4*>(grec);
-            uint4* dst = reinterpret_cast<uint4*>(base);
-            for (int i = lane; i < L.rec_bytes / 16; i += 32) dst[i] = __ldg(src + i);
-            __syncwarp();
+            copy16(base, grec, L.rec_bytes, lane);
         }
 
         uint8_t* valid_g = p.out.d_valid ? p.out.d_valid + env * (long long)L.V : nullptr;
@@ -816,27 +875,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
             } else if (quiet && p.agent != VMGYM_AGENT_NONE) {
                 res.rejected = quiet_rejected;        // the skipped proposals would have been rejected again
             }
-            if (p.out.d_stats) {
-                // running sums for the eval summary (record.py:98-134, exp_performance.py:104-113)
-                const double* cpu = e.cpu();
-                const double* mem = e.mem();
-                double sc_ = 0, sm_ = 0;
-                for (int q = lane; q < L.P; q += 32) { sc_ += cpu[q]; sm_ += mem[q]; }
-                const double mc = warp_sum(sc_) / L.P, mm = warp_sum(sm_) / L.P;
-                double vc = 0, vm = 0;
-                for (int q = lane; q < L.P; q += 32) {
-                    const double dc = cpu[q] - mc, dm = mem[q] - mm;
-                    vc += dc * dc; vm += dm * dm;
-                }
-                vc = warp_sum(vc) / L.P; vm = warp_sum(vm) / L.P;
-                const int tot = e.sc()->total_requests;
-                if (lane == 0) {
-                    st_acc[0] += tot ? (double)e.sc()->dropped_requests / (double)tot : 0.0;
-                    st_acc[1] += res.arrived ? (double)res.waiting / (double)res.arrived : 0.0;
-                    st_acc[2] += mc; st_acc[3] += vc; st_acc[4] += mm; st_acc[5] += vm;
-                    st_acc[6] += res.rejected; st_acc[7] += 1;
-                }
-            }
+            if (p.out.d_stats) stats_update(e, res, st_acc);
             if (res.terminated) break;
         }
 
@@ -864,11 +903,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
             }
             __syncwarp();
         } else {
-            __syncwarp();
-            const uint4* src = reinterpret_cast<const uint4*>(base);
-            uint4* dst = reinterpret_cast<uint4*>(grec);
-            for (int i = lane; i < L.rec_bytes / 16; i += 32) dst[i] = src[i];
-            __syncwarp();
+            copy16(grec, base, L.rec_bytes, lane);
         }
     }
 }
