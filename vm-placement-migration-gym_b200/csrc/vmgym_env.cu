@@ -114,17 +114,20 @@ static int launch_step(StepParams& sp, cudaStream_t st)
     const int w = pick_warps(sp.n_envs, L.sm_stride, L.sm_tables);
     const size_t smem = (size_t)L.sm_tables + (size_t)w * L.sm_stride;
     if (smem > 227 * 1024) return fail(VMGYM_EUNSUPPORTED, "env record does not fit in shared memory (pms/vms too large)");
-    auto kern = step_kernel<PT>;
+    void (*kern)(const StepParams) = step_kernel<PT, 0, 0>;
+    if (sizeof(PT) == 1 && L.P == 100 && L.V == 300) kern = step_kernel<PT, 100, 300>;      // config/100.yml
+    else if (sizeof(PT) == 1 && L.P == 10 && L.V == 30) kern = step_kernel<PT, 10, 30>;     // config/10.yml
     // per (kernel, smem, warps) launch plan, computed once (also keeps these calls out of CUDA-graph capture)
     static thread_local size_t plan_smem = 0;
     static thread_local int plan_w = 0, plan_occ = 1;
-    if (plan_smem != smem || plan_w != w) {
+    static thread_local void (*plan_kern)(const StepParams) = nullptr;
+    if (plan_smem != smem || plan_w != w || plan_kern != kern) {
         int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute");
         if (rc) return rc;
         int occ = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, w * 32, smem);
         plan_occ = occ < 1 ? 1 : occ;
-        plan_smem = smem; plan_w = w;
+        plan_smem = smem; plan_w = w; plan_kern = kern;
     }
     const int occ = plan_occ;
     long long blocks = (sp.n_envs + w - 1) / w;

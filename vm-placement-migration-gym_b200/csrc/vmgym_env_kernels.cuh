@@ -93,7 +93,7 @@ __device__ __forceinline__ double warp_sum(double x)
 }
 
 // largest size code k in [0,100] with x + sz32[k] <= 1.0f (monotone in k because fp32 rounding is monotone)
-__device__ __noinline__ int max_code(const float* sz32, float x)
+__device__ __forceinline__ int max_code(const float* sz32, float x)
 {
     int k = min(100, max(0, (int)((1.0f - x) * 100.0f)));      // estimate, then exact correction (usually 1-2 probes)
     while (k < 100 && x + sz32[k + 1] <= 1.0f) k++;
@@ -112,7 +112,7 @@ __device__ __forceinline__ void refresh_cap(const Env<PT>& e, int p)
 // waiting VMs (the large majority at saturation) from the sequential scan.
 // Returns (max cpu capacity code) | (max mem capacity code) << 8 over all PMs, for the cheap byte pre-filter.
 template <typename PT>
-__device__ __noinline__ unsigned rebuild_fit_table(const Env<PT> e)
+__device__ __forceinline__ unsigned rebuild_fit_table(const Env<PT>& e)
 {
     const int lane = e.lane;
     unsigned* fitm = e.fitm();
@@ -341,7 +341,7 @@ __device__ __noinline__ double reward_kl(const double* cpu, const double* mem, i
     return -(0.5 * (log(det_q / det_p) - 2 + trace_term + m1 - trace_term));
 }
 
-__device__ __noinline__ Philox4 philox_dev(uint32_t c0, uint32_t c2, uint32_t k0, uint32_t k1)
+__device__ __forceinline__ Philox4 philox_dev(uint32_t c0, uint32_t c2, uint32_t k0, uint32_t k1)
 {
     return philox4x32_10(c0, 0u, c2, 0u, k0, k1);
 }
@@ -761,11 +761,14 @@ __host__ __device__ __forceinline__ int dtype_bytes(int dtype) { return dtype ==
 // The step kernel: external actions (agent == NONE) or fused heuristic agent, n_steps per launch.
 // Grid-stride over envs, one warp per env, <= 4 warps per CTA.
 // ---------------------------------------------------------------------------------------------------
-template <typename PT>
+// PC / VC: compile-time pms / vms of the instantiation (0 = take them from the layout at run time); the named
+// configs of the reference (config/10.yml, config/100.yml) get fully unrolled loops.
+template <typename PT, int PC, int VC>
 __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ StepParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const DevLayout& L = p.L;
+    const int cP = PC ? PC : L.P, cV = VC ? VC : L.V, cD = 3 * cV + 2 * cP;
     double* sz64 = reinterpret_cast<double*>(smem);
     float* sz32 = reinterpret_cast<float*>(smem + SIZE_TABLE * 8);
     uint64_t* arr_cdf_s = reinterpret_cast<uint64_t*>(smem + SIZE_TABLE * 12);
@@ -790,7 +793,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
     __syncthreads();
 
     Env<PT> e;
-    e.base = base; e.L = &p.L; e.sz64 = sz64; e.sz32 = sz32; e.P = L.P; e.V = L.V; e.lane = lane;
+    e.base = base; e.L = &p.L; e.sz64 = sz64; e.sz32 = sz32; e.P = cP; e.V = cV; e.lane = lane;
     e.arr_cdf = arr_in_smem ? arr_cdf_s : p.tr.d_arrival_cdf;
     e.svc_cdf = svc_in_smem ? svc_cdf_s : p.tr.d_service_cdf;
     e.svc_bracket = have_bracket ? svc_bracket_s : nullptr;
@@ -810,7 +813,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
             copy16(base, grec, L.rec_bytes, lane);
         }
 
-        uint8_t* valid_g = p.out.d_valid ? p.out.d_valid + env * (long long)L.V : nullptr;
+        uint8_t* valid_g = p.out.d_valid ? p.out.d_valid + env * (long long)cV : nullptr;
         StepResult res;
         res.reward = 0.0; res.terminated = 0; res.rejected = 0; res.waiting = 0; res.arrived = 0; res.changed = 0;
         double* st_acc = reinterpret_cast<double*>(base + L.sm_stats);     // per-launch stats sums (lane 0)
@@ -835,15 +838,15 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
                     // the agent sees the float32 observation of the current state (env.py:296)
                     const double* cpu = e.cpu();
                     const double* mem = e.mem();
-                    for (int q = lane; q < L.P; q += 32) { e.cpu32()[q] = (float)cpu[q]; e.mem32()[q] = (float)mem[q]; }
+                    for (int q = lane; q < cP; q += 32) { e.cpu32()[q] = (float)cpu[q]; e.mem32()[q] = (float)mem[q]; }
                     __syncwarp();
                     AgentView<PT> av;
                     av.place = e.place(); av.cc = e.cpuc(); av.mc = e.memc(); av.c32 = nullptr; av.m32 = nullptr; av.sz32 = sz32;
                     n_found = agent_act(e, av, p.agent, p.tiebreak, true);
                     evaluated = true;
                     if (p.out.d_action) {        // the action vector: proposals, else the current placement (firstfit.py:29)
-                        PT* ao = reinterpret_cast<PT*>(p.out.d_action) + env * (long long)L.V;
-                        for (int v = lane; v < L.V; v += 32)
+                        PT* ao = reinterpret_cast<PT*>(p.out.d_action) + env * (long long)cV;
+                        for (int v = lane; v < cV; v += 32)
                             ao[v] = ((e.prop()[v >> 5] >> (v & 31)) & 1u) ? (PT)e.act()[v] : e.place()[v];
                     }
                 }
@@ -851,12 +854,12 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
             } else {
                 // external actions: stage the row and mark the slots whose action differs from their placement
                 const int adt = p.action_dtype;
-                const unsigned char* arow = reinterpret_cast<const unsigned char*>(p.action) + env * (long long)L.V * dtype_bytes(adt);
+                const unsigned char* arow = reinterpret_cast<const unsigned char*>(p.action) + env * (long long)cV * dtype_bytes(adt);
                 unsigned any = 0;
-                for (int c0 = 0; c0 < L.V; c0 += 32) {
+                for (int c0 = 0; c0 < cV; c0 += 32) {
                     const int v = c0 + lane;
-                    const int a = v < L.V ? load_action(arow, adt, v) : 0;
-                    const bool diff = v < L.V && a != (int)e.place()[v];
+                    const int a = v < cV ? load_action(arow, adt, v) : 0;
+                    const bool diff = v < cV && a != (int)e.place()[v];
                     if (diff) e.act()[v] = (uint16_t)a;
                     const unsigned m = __ballot_sync(FULL, diff);
                     if (lane == 0) e.prop()[c0 >> 5] = m;
@@ -880,7 +883,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
         }
 
         // ---- outputs ----
-        if (p.out.d_obs) write_obs(e, p.out.d_obs + env * (long long)L.D);
+        if (p.out.d_obs) write_obs(e, p.out.d_obs + env * (long long)cD);
         if (lane == 0) {
             e.sc()->status = (e.sc()->status & STATUS_EXHAUSTED) |
                              (quiet ? (STATUS_QUIET | (quiet_key << STATUS_KEY_SHIFT) | ((uint32_t)quiet_rejected << 16)) : 0u);
