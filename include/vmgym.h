@@ -159,6 +159,29 @@ int vmgym_observe(const vmgym_config* cfg, const void* d_state, int64_t n_envs, 
 int vmgym_invalid_action_mask(const vmgym_config* cfg, const void* d_state, int64_t n_envs, uint8_t* d_mask,
                               void* stream);
 
+/* Network.get_action (src/agents/ppo.py:115-126) on the actor's logits d_logits[n_envs, V*A]: masked logits
+ * (-1e7, :119), V categoricals of A, sample (Gumbel-max on a Philox stream keyed by seed/counter) or evaluate
+ * d_action_in, sum of log-probs and of entropies per env.  The invalid-action mask (env.py:45-53) is built on the fly
+ * from the env records d_state, or read as packed bits d_mask_in[n_envs, V, ceil(A/32)] (1 = invalid); masked == 0
+ * disables it (get_invalid_action_mask(False)).  migration_ratio >= 0 applies PPOAgent.act's gating (ppo.py:153-155);
+ * pass a negative value for training rollouts (ppo.py:196-197).  d_mask_out (may be NULL) receives the effective
+ * packed mask for the update pass. */
+int vmgym_policy_heads(const vmgym_config* cfg, const void* d_state, const uint32_t* d_mask_in, int masked,
+                       const float* d_logits, int64_t n_envs, const void* d_action_in, int action_dtype,
+                       float migration_ratio, uint64_t seed, uint64_t counter, void* d_action_out, float* d_logprob,
+                       float* d_entropy, uint32_t* d_mask_out, void* stream);
+
+/* Gradient of (sum_i g_logprob[i]*logprob[i] + g_entropy[i]*entropy[i]) w.r.t. the logits, for PPOAgent.update
+ * (ppo.py:257-258,284-285); masked columns get zero gradient like the in-place fill of ppo.py:119. */
+int vmgym_policy_heads_backward(const vmgym_config* cfg, const uint32_t* d_mask_in, int masked, const float* d_logits,
+                                int64_t n_envs, const void* d_action_in, int action_dtype, const float* d_g_logprob,
+                                const float* d_g_entropy, float* d_g_logits, void* stream);
+
+/* GAE advantages and returns (ppo.py:237-243) for time-major tensors [T, n_envs]; `dones` masks both the bootstrap
+ * and the recursion. */
+int vmgym_gae(const float* d_rewards, const float* d_values, const float* d_next_values, const uint8_t* d_dones, int32_t T,
+              int64_t n_envs, float gamma, float lambda, float* d_advantages, float* d_returns, void* stream);
+
 /* Tuning knobs (process-wide): warps per CTA of the step kernels (0 = auto) and bulk-async record copies
  * (cp.async.bulk) on/off.  For experiments; defaults are chosen per config. */
 int vmgym_set_tuning(int warps_per_cta, int use_bulk_copy);

@@ -1,0 +1,165 @@
+"""-m gpu: PPO-side kernels against plain torch restatements of the reference formulas (floating point: tolerances
+stated per check).  Reference: src/agents/ppo.py:115-126 (masked heads), :153-155 (gating), :237-243 (GAE)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape="s10", n_envs=6, steps=150):
+    import torch
+    from vmgym import Config, VecVmEnv
+    kw = dict(pms=10, vms=30, arrival_rate=0.4, service_length=30, training_steps=400, eval_steps=1000,
+              reward_function="wr", allow_null_action=True) if shape == "s10" else \
+        dict(pms=100, vms=300, arrival_rate=1.8182, service_length=1000, training_steps=10000, eval_steps=100000,
+             reward_function="wr", allow_null_action=True)
+    vec = VecVmEnv(Config(**kw), n_envs, rng="philox")
+    vec.agent_step("firstfit", n_steps=steps)
+    # suspend a few VMs so that running / waiting / empty rows all occur
+    act = vec.vm_placement.clone()
+    run = act < kw["pms"]
+    act[run & (torch.rand_like(act, dtype=torch.float32) < 0.2)] = kw["pms"]
+    vec.step(act)
+    return vec, kw
+
+
+def _ref_heads(logits, mask, action, A):
+    import torch
+    n, VA = logits.shape
+    V = VA // A
+    z = logits.double().reshape(n, V, A).masked_fill(mask, -1e7)
+    logp = torch.log_softmax(z, dim=-1)
+    lp = logp.gather(-1, action.long().unsqueeze(-1)).squeeze(-1).sum(1)
+    ent = -(logp.exp() * logp).sum(-1).sum(1)
+    return lp, ent
+
+
+@pytest.mark.parametrize("shape,n_envs", [("s10", 6), ("s100", 4)])
+def test_heads_forward_backward_match_torch(shape, n_envs):
+    import torch
+    from vmgym.ppo import PPOAgent, PPOConfig, _MaskedHeads
+    vec, kw = _mk(shape, n_envs)
+    agent = PPOAgent(vec, PPOConfig(hidden_size=64))
+    V, A = vec.V, vec.action_dim
+    torch.manual_seed(1)
+    logits = (torch.randn(n_envs, V * A, device=vec.device) * 3).requires_grad_(True)
+    mask = vec.get_invalid_action_mask(True)
+    # sample with the on-the-fly mask; packed mask must equal the env's mask; sampled actions must be valid
+    action, lp, ent, bits = agent._heads(logits.detach().contiguous(), -1.0, want_mask=True)
+    W = (A + 31) // 32
+    unpacked = ((bits.view(n_envs, V, W, 1) >> torch.arange(32, device=vec.device, dtype=torch.int32)) & 1).bool()
+    unpacked = unpacked.reshape(n_envs, V, W * 32)[:, :, :A]
+    assert torch.equal(unpacked, mask)
+    assert not mask.gather(-1, action.long().unsqueeze(-1)).any(), "sampled an invalid action"
+    rlp, rent = _ref_heads(logits.detach(), mask, action, A)
+    assert torch.allclose(lp.double(), rlp, rtol=1e-5, atol=1e-4) and torch.allclose(ent.double(), rent, rtol=1e-5, atol=1e-4)
+    # evaluate + backward through the autograd function vs torch autograd of the reference formula (fp64)
+    nlp, nent = _MaskedHeads.apply(logits, bits, action, vec._ccfg(), True)
+    g1, g2 = torch.randn(n_envs, device=vec.device), torch.randn(n_envs, device=vec.device)
+    (nlp * g1 + nent * g2).sum().backward()
+    ref_logits = logits.detach().double().requires_grad_(True)
+    rlp2, rent2 = _ref_heads(ref_logits, mask, action, A)
+    (rlp2 * g1.double() + rent2 * g2.double()).sum().backward()
+    assert torch.allclose(nlp.double(), rlp2, rtol=1e-5, atol=1e-4)
+    assert torch.allclose(logits.grad.double(), ref_logits.grad, rtol=1e-4, atol=1e-5)
+    # unmasked mode (get_invalid_action_mask(False), ppo.py:152 with masked=False)
+    agent.config.masked = False
+    a2, lp2, ent2, _ = agent._heads(logits.detach().contiguous(), -1.0, want_mask=False)
+    rlp3, rent3 = _ref_heads(logits.detach(), torch.zeros_like(mask), a2, A)
+    assert torch.allclose(lp2.double(), rlp3, rtol=1e-5, atol=1e-4) and torch.allclose(ent2.double(), rent3, rtol=1e-5, atol=1e-4)
+
+
+def test_gating_semantics():
+    """ppo.py:153-155: rows with > 1 invalid column whose WAIT column is valid lose it with prob 1 - migration_ratio."""
+    import torch
+    from vmgym.ppo import PPOAgent, PPOConfig
+    vec, kw = _mk("s10", 8)
+    agent = PPOAgent(vec, PPOConfig(hidden_size=32))
+    P, V, A = vec.P, vec.V, vec.action_dim
+    logits = torch.zeros(8, V * A, device=vec.device)
+    mask = vec.get_invalid_action_mask(True)
+    eligible = (mask.sum(-1) > 1) & ~mask[:, :, P]
+
+    def unpack(bits):
+        W = (A + 31) // 32
+        u = ((bits.view(8, V, W, 1) >> torch.arange(32, device=vec.device, dtype=torch.int32)) & 1).bool()
+        return u.reshape(8, V, W * 32)[:, :, :A]
+    _, _, _, b1 = agent._heads(logits, 1.0, want_mask=True)      # rand() > 1 never: mask unchanged
+    assert torch.equal(unpack(b1), mask)
+    _, _, _, b0 = agent._heads(logits, 0.0, want_mask=True)      # rand() > 0 (almost surely): WAIT masked for eligible rows
+    m0 = unpack(b0)
+    want = mask.clone()
+    want[:, :, P] |= eligible
+    assert torch.equal(m0, want)
+    frac = []
+    for _ in range(40):
+        _, _, _, b = agent._heads(logits, 0.3, want_mask=True)
+        frac.append((unpack(b)[:, :, P] & eligible).sum().item() / max(1, eligible.sum().item()))
+    assert abs(np.mean(frac) - 0.7) < 0.05
+
+
+def test_sampling_distribution():
+    import torch
+    from vmgym import Config, VecVmEnv
+    from vmgym.ppo import PPOAgent, PPOConfig
+    kw = dict(pms=3, vms=5, arrival_rate=0.01, service_length=5, training_steps=100, eval_steps=100, allow_null_action=True)
+    vec = VecVmEnv(Config(**kw), 512, rng="philox")
+    agent = PPOAgent(vec, PPOConfig(hidden_size=8, masked=False))
+    V, A = 5, 5
+    row = torch.tensor([0.0, 1.0, -1.0, 2.0, 0.5], device=vec.device)
+    logits = row.repeat(512, V).contiguous()
+    counts = torch.zeros(A, device=vec.device)
+    for _ in range(40):
+        a, _, _, _ = agent._heads(logits, -1.0, want_mask=False)
+        counts += torch.bincount(a.flatten().long(), minlength=A).float()
+    p = torch.softmax(row, 0)
+    n = counts.sum()
+    chi2 = (((counts - n * p) ** 2) / (n * p)).sum().item()
+    assert chi2 < 30.0, (counts / n, p)          # 4 dof: P(chi2 > 30) ~ 5e-6
+
+
+@pytest.mark.parametrize("T,N", [(100, 37), (7, 5), (33, 64), (1, 3)])
+def test_gae_matches_reference_loop(T, N):
+    import torch
+    from vmgym.ppo import gae
+    g = torch.Generator().manual_seed(T * 131 + N)
+    r, v, nv_ = torch.randn(T, N, generator=g), torch.randn(T, N, generator=g), torch.randn(T, N, generator=g)
+    d = (torch.rand(T, N, generator=g) < 0.1)
+    adv, ret = gae(r.cuda(), v.cuda(), nv_.cuda(), d.cuda(), 0.99, 0.98)
+    # ppo.py:237-243, per env in float64
+    ref = torch.zeros(T, N, dtype=torch.float64)
+    nd = 1.0 - d.double()
+    deltas = r.double() + nd * 0.99 * nv_.double() - v.double()
+    run = torch.zeros(N, dtype=torch.float64)
+    for i in reversed(range(T)):
+        run = deltas[i] + nd[i] * 0.99 * 0.98 * run
+        ref[i] = run
+    assert torch.allclose(adv.cpu().double(), ref, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(ret.cpu().double(), ref + v.double(), rtol=1e-4, atol=1e-4)
+
+
+def test_ppo_learn_smoke_and_checkpoint(tmp_path):
+    import torch
+    from vmgym import Config, VecVmEnv
+    from vmgym.ppo import PPOAgent, PPOConfig
+    kw = dict(pms=10, vms=30, arrival_rate=0.3, service_length=20, training_steps=60, eval_steps=200, reward_function="wr",
+              allow_null_action=True)
+    vec = VecVmEnv(Config(**kw), 16, rng="philox")
+    agent = PPOAgent(vec, PPOConfig(hidden_size=64, batch_size=20, minibatch_size=5, episodes=1, env_chunk=8, lr=1e-3, kl_max=1e9))
+    before = [p.detach().clone() for p in agent.model.parameters()]
+    agent.learn(episodes=1)
+    after = list(agent.model.parameters())
+    assert all(torch.isfinite(p).all() for p in after)
+    assert any(not torch.equal(a, b) for a, b in zip(after, before))
+    path = str(tmp_path / "ppo.pt")
+    agent.save_model(path)
+    assert all(k.startswith("_orig_mod.") for k in torch.load(path))
+    other = PPOAgent(vec, PPOConfig(hidden_size=64))
+    other.load_model(path)
+    assert all(torch.equal(a, b) for a, b in zip(other.model.parameters(), agent.model.parameters()))
+    vec.eval(True)
+    obs, _ = vec.reset(seed=3)
+    a = other.act(obs)
+    assert a.shape == (16, 30)
+    obs, r, term, _, info = vec.step(a)
+    assert info["valid"].float().mean().item() > 0.9           # masked sampling proposes (almost) only valid actions

@@ -117,7 +117,7 @@ __device__ __forceinline__ double np_leaf_sum(const SumSrc& f, int s, int n)
     return res;
 }
 
-__device__ __noinline__ double np_sum(const SumSrc f, int n)
+static __device__ __noinline__ double np_sum(const SumSrc f, int n)
 {
     if (n <= 128) return np_leaf_sum(f, 0, n);
     // explicit post-order walk of the halving recursion (depth <= 10 for n <= 65536)

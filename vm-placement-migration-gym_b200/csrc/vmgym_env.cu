@@ -163,6 +163,7 @@ static int fill_params(StepParams* sp, const vmgym_config* cfg, void* d_state, i
 extern "C" {
 
 const char* vmgym_last_error(void) { return g_err; }
+void vmgym_internal_set_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
 int vmgym_abi_version(void) { return VMGYM_ABI_VERSION; }
 
 int vmgym_set_tuning(int warps_per_cta, int use_bulk_copy)

@@ -304,13 +304,13 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
 // Rewards `ut` (env.py:151-152) and `kl` (env.py:125-150, kl_divergence :8-17).  All reductions use numpy's
 // summation order so the fp64 values (and the exact-zero variance tests) are those of the reference.
 // ---------------------------------------------------------------------------------------------------
-__device__ __noinline__ double reward_ut(const double* cpu, const double* mem, int P, double beta)
+static __device__ __noinline__ double reward_ut(const double* cpu, const double* mem, int P, double beta)
 {
     const SumSrc sc{cpu, nullptr, nullptr, 0.0, 0}, sm{mem, nullptr, nullptr, 0.0, 0};
     return beta * np_sum(sc, P) + (1 - beta) * np_sum(sm, P);
 }
 
-__device__ __noinline__ double reward_kl(const double* cpu, const double* mem, int P, const uint8_t* ex_cc,
+static __device__ __noinline__ double reward_kl(const double* cpu, const double* mem, int P, const uint8_t* ex_cc,
                                          const uint8_t* ex_mc, int arrived, const double* sz, int cap_target)
 {
     const double dP = (double)P, dn = (double)arrived;
@@ -723,7 +723,7 @@ __device__ __forceinline__ void write_obs(const Env<PT>& e, float* __restrict__ 
     write_obs_generic(e, o);
 }
 
-__device__ __noinline__ void fill_tables(double* sz64, float* sz32)
+static __device__ __noinline__ void fill_tables(double* sz64, float* sz32)
 {
     for (int k = threadIdx.x; k < SIZE_TABLE; k += blockDim.x) {
         const double x = (double)k / 100.0;      // == np.around(u, 2) for the code k (env.py:212-219)
@@ -733,7 +733,7 @@ __device__ __noinline__ void fill_tables(double* sz64, float* sz32)
 }
 
 // plain 128-bit copy of a record (the non-bulk fallback of the staging path)
-__device__ __noinline__ void copy16(void* dst, const void* src, int bytes, int lane)
+static __device__ __noinline__ void copy16(void* dst, const void* src, int bytes, int lane)
 {
     __syncwarp();
     const uint4* s4 = reinterpret_cast<const uint4*>(src);

@@ -1,0 +1,324 @@
+// vmgym_policy.cu — PPO-side kernels of the hot path (sm_100a): masked multi-categorical heads on the actor's
+// logits (mask built on the fly from the env records, migration-ratio gating, Gumbel-max sampling with Philox,
+// log-prob and entropy), their backward, and the GAE reverse scan.
+//
+// Reference: src/agents/ppo.py — Network.get_action (:115-126), PPOAgent.act gating (:151-155), update GAE (:237-242);
+// vmenv/envs/env.py:45-53 (get_invalid_action_mask), :35-42 (validate).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "vmgym_env_kernels.cuh"
+
+namespace vmgym {
+
+}  // namespace vmgym
+extern "C" void vmgym_internal_set_error(const char* msg);   // vmgym_env.cu: the message vmgym_last_error() returns
+namespace vmgym {
+static int pfail(int code, const char* msg)
+{
+    vmgym_internal_set_error(msg);
+    return code;
+}
+
+struct HeadParams {
+    DevLayout L;
+    const unsigned char* state;       // env records (mask built on the fly) or nullptr
+    const uint32_t* mask_in;          // packed invalid bits [n, V, W] or nullptr
+    const float* logits;              // [n, V*A]
+    long long n_envs;
+    const void* action_in;            // evaluate these actions (update pass) or nullptr (sample)
+    int action_dtype;
+    float migration_ratio;            // >= 0: PPOAgent.act gating (ppo.py:153-155); < 0: none (training rollouts, ppo.py:196)
+    unsigned long long seed, counter; // Philox key / per-call counter
+    void* action_out;                 // [n, V] placement dtype
+    float* logprob;                   // [n]   sum over VMs (ppo.py:126)
+    float* entropy;                   // [n]
+    uint32_t* mask_out;               // packed effective mask [n, V, W] or nullptr
+    // backward
+    const float* g_logprob;           // [n]
+    const float* g_entropy;           // [n]
+    float* g_logits;                  // [n, V*A]
+    int masked;                       // 0: get_invalid_action_mask(masked=False) -> nothing is masked
+};
+
+constexpr float MASK_LOGIT = -1e7f;   // ppo.py:119
+
+// Row v of the invalid-action mask for columns a = lane + 32 i, as a bit per i (1 = invalid), built from the env
+// record exactly like env.py:45-53 / validate :35-42 (fp64 capacity checks against the current state).
+template <typename PT>
+__device__ __forceinline__ unsigned row_invalid_bits(const unsigned char* rec, const DevLayout& L, const double* s_cpu,
+                                                     const double* s_mem, int v, int lane, int A)
+{
+    const PT* place = reinterpret_cast<const PT*>(rec + L.off_place);
+    const int P = L.P;
+    const int cur = (int)place[v];
+    double vc = 0.0, vm = 0.0;
+    if (cur == P) {
+        vc = (double)(rec[L.off_cpuc + v] & 0x7f) / 100.0;
+        vm = (double)rec[L.off_memc + v] / 100.0;
+    }
+    unsigned bits = 0;
+    for (int i = 0; i * 32 < A; i++) {
+        const int a = i * 32 + lane;
+        if (a >= A) break;
+        bool valid;
+        if (a == cur) valid = true;
+        else if (cur == P) valid = a < P && (s_cpu[a] + vc <= 1.0) && (s_mem[a] + vm <= 1.0);
+        else if (cur < P) valid = (a == P);
+        else valid = false;
+        bits |= valid ? 0u : (1u << i);
+    }
+    return bits;
+}
+
+// One CTA per env; each warp walks rows v = warp, warp + W, ...  Per row: mask (+ gating), log-softmax, entropy,
+// Gumbel-max sample or evaluation of a given action.  Per-env sums are reduced in a fixed order (deterministic).
+template <typename PT, bool BACKWARD>
+__global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
+{
+    extern __shared__ __align__(16) unsigned char hs[];
+    const DevLayout& L = p.L;
+    const int P = L.P, V = L.V, A = L.A;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const long long env = blockIdx.x;
+    double* s_cpu = reinterpret_cast<double*>(hs);
+    double* s_mem = s_cpu + L.Pp;
+    float* s_part = reinterpret_cast<float*>(s_mem + L.Pp);      // [2][nwarps] partial sums
+    const unsigned char* rec = p.state ? p.state + env * (long long)L.rec_bytes : nullptr;
+    if (rec) {
+        const double* g_cpu = reinterpret_cast<const double*>(rec);
+        const double* g_mem = reinterpret_cast<const double*>(rec + L.off_mem);
+        for (int q = threadIdx.x; q < P; q += blockDim.x) { s_cpu[q] = g_cpu[q]; s_mem[q] = g_mem[q]; }
+    }
+    __syncthreads();
+    const int W = (A + 31) / 32;                  // mask words per row
+    const int NI = W;                             // columns per lane
+    float lp_sum = 0.f, ent_sum = 0.f;
+    const float glp = BACKWARD ? p.g_logprob[env] : 0.f, gent = BACKWARD ? p.g_entropy[env] : 0.f;
+    for (int v = warp; v < V; v += nwarps) {
+        // ---- mask bits for this lane's columns ----
+        unsigned inv = 0;
+        if (p.masked) {
+            if (rec) inv = row_invalid_bits<PT>(rec, L, s_cpu, s_mem, v, lane, A);
+            else if (p.mask_in) {
+                const uint32_t* mw = p.mask_in + (env * V + v) * (long long)W;
+                for (int i = 0; i < NI; i++) inv |= ((mw[i] >> lane) & 1u) << i;
+            }
+        }
+        if (p.migration_ratio >= 0.f && rec) {
+            // ppo.py:153-155: if count_nonzero(invalid_row) > 1 and not invalid_row[P] and rand() > migration_ratio:
+            //                     invalid_row[P] = True
+            int cnt = __popc(inv);
+            cnt = __reduce_add_sync(FULL, cnt);
+            const int wl = P & 31, wi = P >> 5;
+            const unsigned wait_inv = __shfl_sync(FULL, (inv >> wi) & 1u, wl);
+            if (cnt > 1 && !wait_inv) {
+                const Philox4 r = philox4x32_10((uint32_t)v, (uint32_t)env, 3u, (uint32_t)p.counter, (uint32_t)p.seed,
+                                                (uint32_t)(p.seed >> 32));
+                const float u = (float)(r.x >> 8) * (1.0f / 16777216.0f);
+                if (u > p.migration_ratio && lane == wl) inv |= 1u << wi;
+            }
+        }
+        if (p.mask_out) {
+            uint32_t* mo = p.mask_out + (env * V + v) * (long long)W;
+            for (int i = 0; i < NI; i++) {
+                const unsigned word = __ballot_sync(FULL, (inv >> i) & 1u);
+                if (lane == 0) mo[i] = word;
+            }
+        }
+        // ---- masked logits, log-softmax ----
+        const float* z = p.logits + (env * V + v) * (long long)A;
+        float zl[8];
+        float mx = -INFINITY;
+        for (int i = 0; i < NI; i++) {
+            const int a = i * 32 + lane;
+            float x = -INFINITY;
+            if (a < A) x = ((inv >> i) & 1u) ? MASK_LOGIT : z[a];
+            zl[i] = x;
+            mx = fmaxf(mx, x);
+        }
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+        float se = 0.f;
+        for (int i = 0; i < NI; i++) se += (i * 32 + lane < A) ? expf(zl[i] - mx) : 0.f;
+        for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(FULL, se, o);
+        const float lse = mx + logf(se);
+        float ent = 0.f;
+        for (int i = 0; i < NI; i++) {
+            if (i * 32 + lane < A) {
+                const float l = zl[i] - lse, pr = expf(l);
+                ent -= pr * l;                                   // Categorical.entropy: -sum p * logp (0 for masked)
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) ent += __shfl_xor_sync(FULL, ent, o);
+        // ---- action: given or Gumbel-max sample ----
+        int act;
+        if (p.action_in) {
+            const unsigned char* arow = reinterpret_cast<const unsigned char*>(p.action_in) + env * (long long)V * dtype_bytes(p.action_dtype);
+            act = load_action(arow, p.action_dtype, v);
+        } else {
+            float best = -INFINITY;
+            int besta = 0;
+            for (int i = 0; i < NI; i++) {
+                const int a = i * 32 + lane;
+                if (a < A) {
+                    const Philox4 r = philox4x32_10((uint32_t)(v * A + a), (uint32_t)env, 4u, (uint32_t)p.counter, (uint32_t)p.seed,
+                                                    (uint32_t)(p.seed >> 32));
+                    const float u = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);     // (0,1)
+                    const float g = -logf(-logf(u));
+                    const float s = zl[i] + g;
+                    if (s > best) { best = s; besta = a; }
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(FULL, best, o);
+                const int oa = __shfl_xor_sync(FULL, besta, o);
+                if (ob > best || (ob == best && oa < besta)) { best = ob; besta = oa; }
+            }
+            act = besta;
+            if (p.action_out && lane == 0) reinterpret_cast<PT*>(p.action_out)[env * V + v] = (PT)act;
+        }
+        float lpa = 0.f;
+        if ((unsigned)act < (unsigned)A) lpa = __shfl_sync(FULL, zl[act >> 5], act & 31) - lse;
+        lp_sum += lpa;
+        ent_sum += ent;
+        if (BACKWARD) {
+            // d(sum logprob)/dz_j = [j == a] - p_j ; d(sum entropy)/dz_j = -p_j (logp_j + H); masked columns get 0
+            float* gz = p.g_logits + (env * V + v) * (long long)A;
+            for (int i = 0; i < NI; i++) {
+                const int a = i * 32 + lane;
+                if (a < A) {
+                    const float l = zl[i] - lse, pr = expf(l);
+                    float g = glp * ((a == act ? 1.f : 0.f) - pr) - gent * pr * (l + ent);
+                    if ((inv >> i) & 1u) g = 0.f;
+                    gz[a] = g;
+                }
+            }
+        }
+    }
+    if (!BACKWARD) {
+        if (lane == 0) { s_part[warp] = lp_sum; s_part[nwarps + warp] = ent_sum; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float a = 0.f, b = 0.f;
+            for (int w = 0; w < nwarps; w++) { a += s_part[w]; b += s_part[nwarps + w]; }
+            if (p.logprob) p.logprob[env] = a;
+            if (p.entropy) p.entropy[env] = b;
+        }
+    }
+}
+
+// GAE (ppo.py:237-242) per env along T:  A_t = delta_t + gamma*lambda*(1-done_t) * A_{t+1},
+// delta_t = r_t + gamma*(1-done_t)*V(s_{t+1}) - V(s_t);  returns = A + V.   Tensors are [T, N] (time-major).
+// One warp per env: the recurrence is a composition of affine maps x -> c*x + d, scanned in reverse with shuffles,
+// 32 time steps per pass with a carry.
+__global__ void gae_kernel(const float* rewards, const float* values, const float* next_values, const uint8_t* dones, int T,
+                           long long N, float gamma, float lambda, float* adv, float* ret)
+{
+    const int lane = threadIdx.x & 31;
+    const long long env = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (env >= N) return;
+    float carry = 0.f;                                  // A_{t+1} beyond the current chunk
+    for (int t1 = T; t1 > 0; t1 -= 32) {
+        const int t = t1 - 1 - lane;                    // lane 0 holds the latest step of the chunk
+        float c = 0.f, d = 0.f, v = 0.f;
+        if (t >= 0) {
+            const long long i = (long long)t * N + env;
+            const float nd = 1.f - (float)dones[i];
+            v = values[i];
+            d = rewards[i] + nd * gamma * next_values[i] - v;
+            c = nd * gamma * lambda;
+        }
+        // inclusive scan over lanes 0..lane of f_lane o ... o f_0 where f(x) = c*x + d, applied to `carry`
+        for (int o = 1; o < 32; o <<= 1) {
+            const float pc = __shfl_up_sync(FULL, c, o), pd = __shfl_up_sync(FULL, d, o);
+            if (lane >= o) { d = c * pd + d; c = c * pc; }
+        }
+        const float a = c * carry + d;
+        if (t >= 0) {
+            const long long i = (long long)t * N + env;
+            adv[i] = a;
+            ret[i] = a + v;
+        }
+        carry = __shfl_sync(FULL, a, min(31, t1 - 1));  // A at the earliest step of this chunk
+    }
+}
+
+}  // namespace vmgym
+
+using namespace vmgym;
+
+extern "C" {
+
+static int heads_launch(HeadParams& hp, const vmgym_config* cfg, bool backward, void* stream)
+{
+    vmgym_layout pub;
+    int rc = vmgym_get_layout(cfg, &pub);
+    if (rc) return pfail(rc, vmgym_last_error());
+    // rebuild the device layout from the public one (only the fields the heads kernel reads)
+    DevLayout& L = hp.L;
+    L.P = cfg->pms; L.V = cfg->vms; L.A = pub.action_dim; L.Pp = pub.pms_padded; L.Vp = pub.vms_padded; L.D = pub.obs_dim;
+    L.off_mem = pub.off_memory; L.off_rem = pub.off_remaining; L.off_place = pub.off_placement; L.off_cpuc = pub.off_cpu_code;
+    L.off_memc = pub.off_mem_code; L.off_cap = pub.off_capacity; L.off_scal = pub.off_scalars; L.rec_bytes = pub.record_bytes;
+    if (L.A > 256) return pfail(VMGYM_EUNSUPPORTED, "action_dim > 256 not supported by the heads kernel yet");
+    if (!hp.logits || hp.n_envs < 0) return pfail(VMGYM_EINVAL, "null logits");
+    if (hp.n_envs == 0) return VMGYM_OK;
+    const int threads = 256;
+    const size_t smem = (size_t)16 * L.Pp + 2 * (threads / 32) * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool small = L.P <= 253;
+    if (backward) {
+        if (small) heads_kernel<uint8_t, true><<<(unsigned)hp.n_envs, threads, smem, st>>>(hp);
+        else heads_kernel<uint16_t, true><<<(unsigned)hp.n_envs, threads, smem, st>>>(hp);
+    } else {
+        if (small) heads_kernel<uint8_t, false><<<(unsigned)hp.n_envs, threads, smem, st>>>(hp);
+        else heads_kernel<uint16_t, false><<<(unsigned)hp.n_envs, threads, smem, st>>>(hp);
+    }
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return pfail(VMGYM_ECUDA, cudaGetErrorString(err));
+    return VMGYM_OK;
+}
+
+int vmgym_policy_heads(const vmgym_config* cfg, const void* d_state, const uint32_t* d_mask_in, int masked,
+                       const float* d_logits, int64_t n_envs, const void* d_action_in, int action_dtype,
+                       float migration_ratio, uint64_t seed, uint64_t counter, void* d_action_out, float* d_logprob,
+                       float* d_entropy, uint32_t* d_mask_out, void* stream)
+{
+    HeadParams hp = {};
+    hp.state = (const unsigned char*)d_state; hp.mask_in = d_mask_in; hp.masked = masked; hp.logits = d_logits;
+    hp.n_envs = n_envs; hp.action_in = d_action_in; hp.action_dtype = action_dtype; hp.migration_ratio = migration_ratio;
+    hp.seed = seed; hp.counter = counter; hp.action_out = d_action_out; hp.logprob = d_logprob; hp.entropy = d_entropy;
+    hp.mask_out = d_mask_out;
+    if (!d_action_in && !d_action_out) return pfail(VMGYM_EINVAL, "need action_in (evaluate) or action_out (sample)");
+    return heads_launch(hp, cfg, false, stream);
+}
+
+int vmgym_policy_heads_backward(const vmgym_config* cfg, const uint32_t* d_mask_in, int masked, const float* d_logits,
+                                int64_t n_envs, const void* d_action_in, int action_dtype, const float* d_g_logprob,
+                                const float* d_g_entropy, float* d_g_logits, void* stream)
+{
+    HeadParams hp = {};
+    hp.mask_in = d_mask_in; hp.masked = masked; hp.logits = d_logits; hp.n_envs = n_envs; hp.action_in = d_action_in;
+    hp.action_dtype = action_dtype; hp.migration_ratio = -1.f; hp.g_logprob = d_g_logprob; hp.g_entropy = d_g_entropy;
+    hp.g_logits = d_g_logits;
+    if (!d_action_in || !d_g_logprob || !d_g_entropy || !d_g_logits) return pfail(VMGYM_EINVAL, "null backward operand");
+    return heads_launch(hp, cfg, true, stream);
+}
+
+int vmgym_gae(const float* d_rewards, const float* d_values, const float* d_next_values, const uint8_t* d_dones, int32_t T,
+              int64_t n_envs, float gamma, float lambda, float* d_advantages, float* d_returns, void* stream)
+{
+    if (!d_rewards || !d_values || !d_next_values || !d_dones || !d_advantages || !d_returns || T < 0 || n_envs < 0)
+        return pfail(VMGYM_EINVAL, "null GAE operand");
+    if (T == 0 || n_envs == 0) return VMGYM_OK;
+    const int threads = 256;
+    const long long blocks = (n_envs * 32 + threads - 1) / threads;
+    gae_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(d_rewards, d_values, d_next_values, d_dones, T, n_envs,
+                                                                     gamma, lambda, d_advantages, d_returns);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return pfail(VMGYM_ECUDA, cudaGetErrorString(err));
+    return VMGYM_OK;
+}
+
+}  // extern "C"

@@ -3,7 +3,7 @@
 #include <stdint.h>
 namespace vmgym {
 // ---- numpy's scalar argsort replayed by one lane (best-fit compat tie mode) ------------
-__device__ __noinline__ void introsort_argsort(const float* v, uint16_t* t, int num)
+static __device__ __noinline__ void introsort_argsort(const float* v, uint16_t* t, int num)
 {
     // third-party algorithm: numpy npysort aquicksort_<float> (median-of-3 quicksort, insertion sort for
     // partitions of <= 16, larger side pushed); the heapsort fallback (depth limit) is kept for completeness.

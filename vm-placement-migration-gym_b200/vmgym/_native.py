@@ -15,7 +15,7 @@ PKG_ROOT = os.path.dirname(_HERE)
 REPO_ROOT = os.path.dirname(PKG_ROOT)
 CSRC = os.path.join(PKG_ROOT, "csrc")
 LIB_PATH = os.path.join(_HERE, "libvmgym.so")
-SOURCES = ["vmgym_env.cu"]
+SOURCES = ["vmgym_env.cu", "vmgym_policy.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -60,7 +60,8 @@ SCALARS_I32 = ["timestep", "total_requests", "served_requests", "dropped_request
 SCALARS_BYTES = 80
 
 EXPORTS = ["vmgym_last_error", "vmgym_abi_version", "vmgym_get_layout", "vmgym_reset", "vmgym_step",
-           "vmgym_agent_step", "vmgym_agent_act", "vmgym_observe", "vmgym_invalid_action_mask", "vmgym_set_tuning"]
+           "vmgym_agent_step", "vmgym_agent_act", "vmgym_observe", "vmgym_invalid_action_mask", "vmgym_set_tuning",
+           "vmgym_policy_heads", "vmgym_policy_heads_backward", "vmgym_gae"]
 
 
 class VmgymError(RuntimeError):
@@ -108,6 +109,10 @@ def lib():
     L.vmgym_observe.argtypes = [C.POINTER(Config), vp, i64, vp, vp]
     L.vmgym_invalid_action_mask.argtypes = [C.POINTER(Config), vp, i64, vp, vp]
     L.vmgym_set_tuning.argtypes = [i32, i32]
+    f32, u64 = C.c_float, C.c_uint64
+    L.vmgym_policy_heads.argtypes = [C.POINTER(Config), vp, vp, i32, vp, i64, vp, i32, f32, u64, u64, vp, vp, vp, vp, vp]
+    L.vmgym_policy_heads_backward.argtypes = [C.POINTER(Config), vp, i32, vp, i64, vp, i32, vp, vp, vp, vp]
+    L.vmgym_gae.argtypes = [vp, vp, vp, vp, C.c_int32, i64, f32, f32, vp, vp, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

@@ -1,0 +1,298 @@
+"""PPO agent of the reference (src/agents/ppo.py) on the batched device env.
+
+Same interface — `PPOConfig` fields (ppo.py:14-36), `Network` (actor / critic 3-layer tanh MLPs with the reference's
+orthogonal init, ppo.py:85-109), `PPOAgent.act / learn / update / save_model / load_model / eval` — with the hot numeric
+pieces on hand-written kernels:
+
+  * masked multi-categorical heads (mask built on the fly from the env records, migration-ratio gating, sampling,
+    log-prob, entropy) and their backward: `vmgym_policy_heads{,_backward}` (csrc/vmgym_policy.cu);
+  * GAE: `vmgym_gae` (warp-level reverse scan);
+  * env stepping / masks: the env kernels.
+The dense layers run through torch (cuBLAS) in this round; autograd, AdamW and the NCCL gradient all-reduce are
+torch plumbing.  Sampling uses a Philox stream, so sampled trajectories differ from torch's CPU generator by
+construction; logits / log-prob / entropy / GAE are parity-tested against the reference formulas.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _native as nv
+
+
+@dataclass
+class PPOConfig:
+    episodes: int = 2000
+    hidden_size: int = 256
+    migration_ratio: float = 0.5
+    masked: bool = True
+    lr: float = 5e-5
+    gamma: float = 0.99
+    lamda: float = 0.98
+    ent_coef: float = 0.01
+    vf_coef: float = 0.5
+    vf_loss_clip: bool = True
+    k_epochs: int = 4
+    kl_max: float = 0.02
+    eps_clip: float = 0.1
+    max_grad_norm: float = 0.5
+    batch_size: int = 100          # rollout length T (steps) between updates
+    minibatch_size: int = 25       # time steps per minibatch (sequential, ppo.py:251-252)
+    det: bool = False
+    network_arch: str = "separate"
+    reward_scaling: bool = False
+    training_progress_bar: bool = True
+    device: str = "cuda"
+    env_chunk: int = 256           # envs per forward/backward chunk inside a minibatch (gradient accumulation)
+
+
+def _ortho(layer: nn.Linear, gain: float) -> nn.Linear:
+    nn.init.orthogonal_(layer.weight, gain=gain)       # ppo.py:85-88
+    nn.init.constant_(layer.bias, 0.0)
+    return layer
+
+
+class Network(nn.Module):
+    """ppo.py:91-131: separate critic (-> 1) and actor (-> sum(nvec) logits), tanh, orthogonal init (gains sqrt2,
+    sqrt2, then 1 / 0.01)."""
+
+    def __init__(self, input_size: int, n_vms: int, action_dim: int, hidden_size: int, dtype=torch.float32):
+        super().__init__()
+        self.n_vms, self.action_dim = int(n_vms), int(action_dim)
+        g = math.sqrt(2.0)
+        self.critic = nn.Sequential(_ortho(nn.Linear(input_size, hidden_size, dtype=dtype), g), nn.Tanh(),
+                                    _ortho(nn.Linear(hidden_size, hidden_size, dtype=dtype), g), nn.Tanh(),
+                                    _ortho(nn.Linear(hidden_size, 1, dtype=dtype), 1.0))
+        self.actor = nn.Sequential(_ortho(nn.Linear(input_size, hidden_size, dtype=dtype), g), nn.Tanh(),
+                                   _ortho(nn.Linear(hidden_size, hidden_size, dtype=dtype), g), nn.Tanh(),
+                                   _ortho(nn.Linear(hidden_size, self.n_vms * self.action_dim, dtype=dtype), 0.01))
+
+    def get_value(self, obs):
+        return self.critic(obs)
+
+    def get_det_action(self, obs):
+        """ppo.py:128-131: per-VM argmax of the UNMASKED logits."""
+        return self.actor(obs).reshape(-1, self.n_vms, self.action_dim).argmax(dim=-1)
+
+
+class _MaskedHeads(torch.autograd.Function):
+    """(logits, stored packed mask, stored actions) -> (sum log-prob, sum entropy) per env, with the backward kernel."""
+
+    @staticmethod
+    def forward(ctx, logits, mask_bits, actions, ccfg, masked):
+        logits = logits.contiguous()
+        n = logits.shape[0]
+        logprob = torch.empty(n, dtype=torch.float32, device=logits.device)
+        entropy = torch.empty(n, dtype=torch.float32, device=logits.device)
+        code = {torch.uint8: nv.U8, torch.int16: nv.I16, torch.int64: nv.I64}[actions.dtype]
+        stream = C.c_void_p(torch.cuda.current_stream(logits.device).cuda_stream)
+        nv.check(nv.lib().vmgym_policy_heads(C.byref(ccfg), None, mask_bits.data_ptr() if mask_bits is not None else None,
+                                             int(masked), logits.data_ptr(), n, actions.data_ptr(), code, -1.0, 0, 0, None,
+                                             logprob.data_ptr(), entropy.data_ptr(), None, stream), "vmgym_policy_heads")
+        ctx.save_for_backward(logits, mask_bits if mask_bits is not None else torch.empty(0, device=logits.device), actions)
+        ctx.ccfg, ctx.masked, ctx.code, ctx.has_mask = ccfg, masked, code, mask_bits is not None
+        return logprob, entropy
+
+    @staticmethod
+    def backward(ctx, g_logprob, g_entropy):
+        logits, mask_bits, actions = ctx.saved_tensors
+        g_logits = torch.empty_like(logits)
+        n = logits.shape[0]
+        stream = C.c_void_p(torch.cuda.current_stream(logits.device).cuda_stream)
+        g_logprob = g_logprob.contiguous().float()
+        g_entropy = g_entropy.contiguous().float()
+        nv.check(nv.lib().vmgym_policy_heads_backward(C.byref(ctx.ccfg), mask_bits.data_ptr() if ctx.has_mask else None,
+                                                      int(ctx.masked), logits.data_ptr(), n, actions.data_ptr(), ctx.code,
+                                                      g_logprob.data_ptr(), g_entropy.data_ptr(), g_logits.data_ptr(), stream),
+                 "vmgym_policy_heads_backward")
+        return g_logits, None, None, None, None
+
+
+def gae(rewards, values, next_values, dones, gamma: float, lamda: float):
+    """ppo.py:237-243 on time-major [T, N] float32 tensors (dones uint8/bool).  Returns (advantages, returns)."""
+    T, N = rewards.shape
+    rewards, values, next_values = rewards.contiguous().float(), values.contiguous().float(), next_values.contiguous().float()
+    dones = dones.contiguous().to(torch.uint8)
+    adv, ret = torch.empty_like(rewards), torch.empty_like(rewards)
+    stream = C.c_void_p(torch.cuda.current_stream(rewards.device).cuda_stream)
+    nv.check(nv.lib().vmgym_gae(rewards.data_ptr(), values.data_ptr(), next_values.data_ptr(), dones.data_ptr(), T, N,
+                                float(gamma), float(lamda), adv.data_ptr(), ret.data_ptr(), stream), "vmgym_gae")
+    return adv, ret
+
+
+class PPOAgent:
+    """Reference-shaped agent (Base API: learn / act / save_model / load_model / eval) over a VecVmEnv or VmEnv."""
+
+    name = "PPOAgent"
+
+    def __init__(self, env, config: PPOConfig | None = None, seed: int | None = None):
+        self.env = env
+        self.vec = getattr(env, "vec", env)
+        self.config = config or PPOConfig()
+        vec = self.vec
+        self.device = vec.device
+        self.obs_dim, self.V, self.A = vec.obs_dim, vec.V, vec.action_dim
+        self.model = Network(self.obs_dim, self.V, self.A, self.config.hidden_size).to(self.device)
+        self.optimizer = torch.optim.AdamW(self.model.parameters(), lr=self.config.lr)
+        self.mask_words = (self.A + 31) // 32
+        self.seed = int(vec.config.seed if seed is None else seed)
+        self._calls = 0
+        self.total_steps = 0
+        self.training = True
+
+    # ---- reference API -------------------------------------------------------------------------------------
+    def eval(self, mode=True):
+        self.training = not mode
+        self.model.train(not mode)
+
+    def save_model(self, modelpath):
+        if modelpath:
+            # the reference saves the torch.compile-wrapped module: keys carry the `_orig_mod.` prefix (ppo.py:142,166)
+            torch.save({"_orig_mod." + k: v for k, v in self.model.state_dict().items()}, modelpath)
+
+    def load_model(self, modelpath):
+        sd = torch.load(modelpath, map_location=self.device)
+        sd = {k[len("_orig_mod."):] if k.startswith("_orig_mod.") else k: v for k, v in sd.items()}
+        self.model.load_state_dict(sd)
+        self.model.eval()
+
+    def _heads(self, logits, migration_ratio: float, want_mask: bool):
+        vec = self.vec
+        n = logits.shape[0]
+        action = torch.empty((n, self.V), dtype=vec.place_dtype, device=self.device)
+        logprob = torch.empty(n, dtype=torch.float32, device=self.device)
+        entropy = torch.empty(n, dtype=torch.float32, device=self.device)
+        mask = torch.empty((n, self.V, self.mask_words), dtype=torch.int32, device=self.device) if want_mask else None
+        self._calls += 1
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        nv.check(nv.lib().vmgym_policy_heads(C.byref(vec._ccfg()), vec.state.data_ptr(), None, int(bool(self.config.masked)),
+                                             logits.data_ptr(), n, None, nv.U8, float(migration_ratio), self.seed, self._calls,
+                                             action.data_ptr(), logprob.data_ptr(), entropy.data_ptr(),
+                                             mask.data_ptr() if mask is not None else None, stream), "vmgym_policy_heads")
+        return action, logprob, entropy, mask
+
+    @torch.no_grad()
+    def act(self, obs):
+        """ppo.py:151-161: mask + migration-ratio gating + sampled (or deterministic) action for the env's CURRENT state."""
+        single = False
+        if isinstance(obs, np.ndarray):
+            single = obs.ndim == 1
+            obs_t = torch.from_numpy(np.ascontiguousarray(obs, np.float32).reshape(-1, self.obs_dim)).to(self.device)
+        else:
+            single = obs.dim() == 1
+            obs_t = obs.reshape(-1, self.obs_dim).to(self.device, torch.float32)
+        if self.config.det:
+            action = self.model.get_det_action(obs_t).to(self.vec.place_dtype)
+        else:
+            logits = self.model.actor(obs_t).contiguous()
+            action, _, _, _ = self._heads(logits, self.config.migration_ratio, want_mask=False)
+        if isinstance(obs, np.ndarray):
+            a = action.cpu().numpy().astype(np.int64)
+            return a[0] if single else a
+        return action[0] if single else action
+
+    # ---- training ------------------------------------------------------------------------------------------
+    def learn(self, episodes: int | None = None, max_updates: int | None = None):
+        """ppo.py:172-226 with N envs stepping in lock-step: every `batch_size` steps one `update` on the [T, N] rollout.
+        Runs `episodes` episodes of `training_steps` steps (the reference's loop bound is a known slip)."""
+        cfg, vec = self.config, self.vec
+        T, N = cfg.batch_size, vec.num_envs
+        dev = self.device
+        buf = dict(
+            obs=torch.empty((T, N, self.obs_dim), dtype=torch.float32, device=dev),
+            next_obs=torch.empty((T, N, self.obs_dim), dtype=torch.float32, device=dev),
+            action=torch.empty((T, N, self.V), dtype=vec.place_dtype, device=dev),
+            mask=torch.empty((T, N, self.V, self.mask_words), dtype=torch.int32, device=dev),
+            logprob=torch.empty((T, N), dtype=torch.float32, device=dev),
+            reward=torch.empty((T, N), dtype=torch.float32, device=dev),
+            done=torch.empty((T, N), dtype=torch.uint8, device=dev))
+        returns, updates = [], 0
+        vec.eval(False)
+        for ep in range(int(cfg.episodes if episodes is None else episodes)):
+            obs, _ = vec.reset(seed=int(vec.config.seed) + ep)        # ppo.py:192
+            obs = obs.clone()
+            ep_ret = torch.zeros(N, dtype=torch.float64, device=dev)
+            done, i = False, 0
+            while not done:
+                with torch.no_grad():
+                    logits = self.model.actor(obs).contiguous()
+                    action, logprob, _, mask = self._heads(logits, -1.0, want_mask=True)   # no gating in training (ppo.py:196-197)
+                nobs, reward, term, _, _ = vec.step(action, want_valid=False)
+                buf["obs"][i], buf["next_obs"][i], buf["action"][i], buf["mask"][i] = obs, nobs, action, mask
+                buf["logprob"][i], buf["reward"][i], buf["done"][i] = logprob, reward.float(), vec.terminated_u8
+                ep_ret += reward
+                obs = nobs.clone()
+                i += 1
+                self.total_steps += 1
+                done = bool(term[0].item())                           # all envs share the step limit
+                if i >= T:
+                    self.update(**buf)
+                    i = 0
+                    updates += 1
+                    if max_updates is not None and updates >= max_updates:
+                        return returns
+            returns.append(ep_ret.mean().item())
+        return returns
+
+    def update(self, obs, next_obs, action, mask, logprob, reward, done):
+        """ppo.py:229-295 on a time-major rollout [T, N, ...]."""
+        cfg, vec = self.config, self.vec
+        T, N = reward.shape
+        with torch.no_grad():
+            values = self.model.get_value(obs.reshape(T * N, -1)).reshape(T, N)
+            next_values = self.model.get_value(next_obs.reshape(T * N, -1)).reshape(T, N)
+            advantages, returns = gae(reward, values, next_values, done, cfg.gamma, cfg.lamda)
+        ccfg = vec._ccfg()
+        world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
+        stats = {}
+        for epoch in range(cfg.k_epochs):
+            for t0 in range(0, T, cfg.minibatch_size):                 # sequential minibatches (ppo.py:251-252)
+                t1 = min(T, t0 + cfg.minibatch_size)
+                adv_mb = advantages[t0:t1]
+                adv_mb = (adv_mb - adv_mb.mean()) / (adv_mb.std() + 1e-10)      # unbiased std (ppo.py:256)
+                # pass 1 (no grad): KL early stop is decided on the whole minibatch (ppo.py:263-264)
+                n_mb = (t1 - t0) * N
+                self.optimizer.zero_grad(set_to_none=True)
+                logratio_sum = torch.zeros((), dtype=torch.float64, device=self.device)
+                chunks = []
+                for t in range(t0, t1):
+                    for e0 in range(0, N, cfg.env_chunk):
+                        chunks.append((t, e0, min(N, e0 + cfg.env_chunk)))
+                with torch.no_grad():
+                    for t, e0, e1 in chunks:
+                        lg = self.model.actor(obs[t, e0:e1])
+                        nlp, _ = _MaskedHeads.apply(lg, mask[t, e0:e1].contiguous(), action[t, e0:e1].contiguous(), ccfg, cfg.masked)
+                        logratio_sum += (nlp - logprob[t, e0:e1]).double().sum()
+                if -(logratio_sum / n_mb).item() > cfg.kl_max:
+                    break
+                for t, e0, e1 in chunks:
+                    o = obs[t, e0:e1]
+                    lg = self.model.actor(o)
+                    nlp, ent = _MaskedHeads.apply(lg, mask[t, e0:e1].contiguous(), action[t, e0:e1].contiguous(), ccfg, cfg.masked)
+                    ratios = torch.exp(nlp - logprob[t, e0:e1])
+                    a = adv_mb[t - t0, e0:e1]
+                    loss_clipped = torch.max(-ratios * a, -torch.clamp(ratios, 1 - cfg.eps_clip, 1 + cfg.eps_clip) * a).sum()
+                    newv = self.model.get_value(o).flatten()
+                    v_old, ret = values[t, e0:e1], returns[t, e0:e1]
+                    l_un = torch.square(newv - ret)
+                    l_cl = torch.square(v_old + torch.clamp(newv - v_old, -cfg.eps_clip, cfg.eps_clip) - ret)
+                    loss_vf = 0.5 * (torch.max(l_un, l_cl) if cfg.vf_loss_clip else l_un).sum()
+                    loss = (loss_clipped - cfg.ent_coef * ent.sum() + cfg.vf_coef * loss_vf) / n_mb   # means over the minibatch
+                    loss.backward()
+                if world > 1:                                          # data parallel: average gradients over ranks (NCCL)
+                    flat = torch.cat([p.grad.flatten() for p in self.model.parameters()])
+                    torch.distributed.all_reduce(flat)
+                    flat /= world
+                    off = 0
+                    for p in self.model.parameters():
+                        p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                        off += p.numel()
+                nn.utils.clip_grad_norm_(self.model.parameters(), cfg.max_grad_norm)
+                self.optimizer.step()
+                stats = {"kl": -(logratio_sum / n_mb).item()}
+        return stats
