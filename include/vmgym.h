@@ -182,6 +182,12 @@ int vmgym_policy_heads_backward(const vmgym_config* cfg, const uint32_t* d_mask_
 int vmgym_gae(const float* d_rewards, const float* d_values, const float* d_next_values, const uint8_t* d_dones, int32_t T,
               int64_t n_envs, float gamma, float lambda, float* d_advantages, float* d_returns, void* stream);
 
+/* DRLVMPAgent._convert_action heuristics (src/agents/drlvmp.py:517-617) for one waiting VM per env:
+ * d_choice[i] in {0 worst-fit, 1 min dot-product, 2 min L2 distance, 3 best-fit}, d_vm_index[i] = slot (or -1 to skip);
+ * d_pm_out[i] = chosen PM, or -1 when worst-/best-fit find no PM that fits (the placement then stays WAIT). */
+int vmgym_drlvmp_choice(const vmgym_config* cfg, const float* d_obs, const int32_t* d_vm_index, const int32_t* d_choice,
+                        int64_t n_envs, int32_t* d_pm_out, void* stream);
+
 /* Tuning knobs (process-wide): warps per CTA of the step kernels (0 = auto) and bulk-async record copies
  * (cp.async.bulk) on/off.  For experiments; defaults are chosen per config. */
 int vmgym_set_tuning(int warps_per_cta, int use_bulk_copy);

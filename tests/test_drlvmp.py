@@ -1,0 +1,72 @@
+"""DRL-VMP rollout side against golden vectors recorded from the unmodified reference (tests/golden/drlvmp.npz,
+made by tests/golden/make_golden_drlvmp.py): network forward on CPU (not gpu), heuristics kernel and act loop on GPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "drlvmp.npz")
+
+
+def _load():
+    z = np.load(GOLD)
+    return {k: z[k] for k in z.files}
+
+
+def test_network_matches_reference_q_values():
+    """drlvmp.py:355-372 — same state_dict keys, same q-values (fp32, CPU): |dq| <= 1e-4 on q ~ 100."""
+    from vmgym.drlvmp import Network
+    g = _load()
+    net = Network(110, 24, 4, 51, torch.linspace(0.0, 200.0, 51))
+    sd = {k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("net.")}
+    missing = net.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    with torch.no_grad():
+        q = net(torch.from_numpy(g["net_x"]))
+    assert torch.allclose(q, torch.from_numpy(g["net_q"]), atol=1e-4, rtol=1e-6)
+    assert torch.equal(q.argmax(1), torch.from_numpy(g["net_q"]).argmax(1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("base,P,V", [("10", 10, 30), ("100", 100, 300)])
+def test_heuristics_kernel_matches_reference(base, P, V):
+    """_get_worstfit/_dot/_norm2/_bestfit_action (drlvmp.py:549-617) on the reference's own observations."""
+    from vmgym import Config, VecVmEnv
+    from vmgym.drlvmp import DRLVMPAgent, DRLVMPConfig
+    g = _load()
+    vec = VecVmEnv(Config(pms=P, vms=V, allow_null_action=True, training_steps=10, eval_steps=10), 1, rng="philox")
+    agent = DRLVMPAgent(vec, DRLVMPConfig(hidden_size=8))
+    obs = torch.from_numpy(g[f"h{base}_obs"]).cuda()
+    pm = agent.heuristic(obs.contiguous(), torch.from_numpy(g[f"h{base}_v"]).cuda(), torch.from_numpy(g[f"h{base}_choice"]).cuda())
+    got, want, ch = pm.cpu().numpy(), g[f"h{base}_pm"], g[f"h{base}_choice"]
+    bad = np.flatnonzero(got != want)
+    assert bad.size == 0, [(int(i), int(ch[i]), int(got[i]), int(want[i])) for i in bad[:10]]
+
+
+@pytest.mark.gpu
+def test_act_loop_equals_sequential_restatement():
+    """act (drlvmp.py:504-512): per waiting VM in slot order, network choice on the working observation, heuristic on
+    it, placement written back — batched over envs == one env at a time."""
+    from vmgym import Config, VecVmEnv
+    from vmgym.drlvmp import DRLVMPAgent, DRLVMPConfig
+    torch.manual_seed(0)
+    vec = VecVmEnv(Config(pms=10, vms=30, arrival_rate=0.5, service_length=40, allow_null_action=True, training_steps=500,
+                          eval_steps=500), 7, rng="philox")
+    vec.agent_step("firstfit", n_steps=60)
+    act = vec.vm_placement.clone()
+    act[(act < 10) & (torch.rand_like(act, dtype=torch.float32) < 0.5)] = 10        # suspend some -> waiting VMs that fit
+    obs, *_ = vec.step(act)
+    obs = obs.clone()
+    agent = DRLVMPAgent(vec, DRLVMPConfig(hidden_size=16))
+    batched = agent.act(obs).cpu().numpy()
+    for i in range(7):
+        o = obs[i:i + 1].clone()
+        for v in torch.flatnonzero(obs[i, :30] == 10.0).tolist():
+            choice = agent.dqn(o).argmax(1).to(torch.int32)
+            pm = agent.heuristic(o.contiguous(), torch.tensor([v], dtype=torch.int32, device="cuda"), choice)
+            if pm.item() >= 0:
+                o[0, v] = float(pm.item())
+        assert np.array_equal(batched[i], o[0, :30].long().cpu().numpy()), i
+    one = agent.act(obs[3].cpu().numpy())
+    assert one.dtype == np.int64 and np.array_equal(one, batched[3])

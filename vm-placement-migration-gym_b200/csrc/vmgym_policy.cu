@@ -322,3 +322,63 @@ int vmgym_gae(const float* d_rewards, const float* d_values, const float* d_next
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// DRL-VMP placement heuristics (src/agents/drlvmp.py:549-617): for one waiting VM of each env and a choice in
+// {0 worst-fit, 1 min dot-product, 2 min L2 distance, 3 best-fit}, pick a PM from the float32 observation.  The
+// reference never updates cpu/memory in the observation copy between VMs (drlvmp.py:557-565), so every call sees
+// the original PM loads.  Tie rules: worst-fit / dot / L2 -> lowest PM index (first minimum, torch.argmin; ascending
+// stable order), best-fit -> highest PM index among equal keys (torch.flip of a stable ascending argsort).
+// ---------------------------------------------------------------------------------------------------
+namespace vmgym {
+
+__global__ void drlvmp_choice_kernel(int P, int V, int D, const float* obs, const int* vm_index, const int* choice,
+                                     long long n_envs, int* pm_out)
+{
+    const int lane = threadIdx.x & 31;
+    const long long env = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (env >= n_envs) return;
+    const int v = vm_index[env];
+    if (v < 0 || v >= V) { if (lane == 0) pm_out[env] = -1; return; }
+    const float* o = obs + env * (long long)D;
+    const float vc = o[V + v], vm = o[2 * V + v];
+    const float* cpu = o + 3 * V;
+    const float* mem = o + 3 * V + P;
+    const int ch = choice[env];
+    // lexicographic arg-min of (key, tie) over PMs; `tie` encodes the index order wanted among equal keys
+    float bestk = INFINITY;
+    int bestt = 0x7fffffff, bestp = -1;
+    for (int p = lane; p < P; p += 32) {
+        const float c = cpu[p], m = mem[p];
+        float key;
+        int tie = p;
+        bool ok = true;
+        if (ch == 0) { key = c + m; ok = (c + vc <= 1.0f) && (m + vm <= 1.0f); }                    // worst-fit: smallest load that fits
+        else if (ch == 3) { key = -(c + m); tie = -p; ok = (c + vc <= 1.0f) && (m + vm <= 1.0f); }  // best-fit: largest load that fits
+        else if (ch == 1) key = c * vc + m * vm;                                                     // torch.dot([c,m],[vc,vm])
+        else { const float dc = c - vc, dm = m - vm; key = sqrtf(dc * dc + dm * dm); }              // torch.norm
+        if (ok && (key < bestk || (key == bestk && tie < bestt))) { bestk = key; bestt = tie; bestp = p; }
+    }
+    for (int o2 = 16; o2 > 0; o2 >>= 1) {
+        const float ok_ = __shfl_xor_sync(FULL, bestk, o2);
+        const int ot = __shfl_xor_sync(FULL, bestt, o2), op = __shfl_xor_sync(FULL, bestp, o2);
+        if (op >= 0 && (bestp < 0 || ok_ < bestk || (ok_ == bestk && ot < bestt))) { bestk = ok_; bestt = ot; bestp = op; }
+    }
+    if (lane == 0) pm_out[env] = bestp;
+}
+
+}  // namespace vmgym
+
+extern "C" int vmgym_drlvmp_choice(const vmgym_config* cfg, const float* d_obs, const int32_t* d_vm_index,
+                                   const int32_t* d_choice, int64_t n_envs, int32_t* d_pm_out, void* stream)
+{
+    if (!cfg || !d_obs || !d_vm_index || !d_choice || !d_pm_out || n_envs < 0) return pfail(VMGYM_EINVAL, "null operand");
+    if (n_envs == 0) return VMGYM_OK;
+    const int P = cfg->pms, V = cfg->vms, D = 3 * V + 2 * P;
+    const int threads = 256;
+    const long long blocks = (n_envs * 32 + threads - 1) / threads;
+    drlvmp_choice_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(P, V, D, d_obs, d_vm_index, d_choice, n_envs, d_pm_out);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return pfail(VMGYM_ECUDA, cudaGetErrorString(err));
+    return VMGYM_OK;
+}

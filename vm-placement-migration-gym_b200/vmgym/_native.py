@@ -61,7 +61,7 @@ SCALARS_BYTES = 80
 
 EXPORTS = ["vmgym_last_error", "vmgym_abi_version", "vmgym_get_layout", "vmgym_reset", "vmgym_step",
            "vmgym_agent_step", "vmgym_agent_act", "vmgym_observe", "vmgym_invalid_action_mask", "vmgym_set_tuning",
-           "vmgym_policy_heads", "vmgym_policy_heads_backward", "vmgym_gae"]
+           "vmgym_policy_heads", "vmgym_policy_heads_backward", "vmgym_gae", "vmgym_drlvmp_choice"]
 
 
 class VmgymError(RuntimeError):
@@ -113,6 +113,7 @@ def lib():
     L.vmgym_policy_heads.argtypes = [C.POINTER(Config), vp, vp, i32, vp, i64, vp, i32, f32, u64, u64, vp, vp, vp, vp, vp]
     L.vmgym_policy_heads_backward.argtypes = [C.POINTER(Config), vp, i32, vp, i64, vp, i32, vp, vp, vp, vp]
     L.vmgym_gae.argtypes = [vp, vp, vp, vp, C.c_int32, i64, f32, f32, vp, vp, vp]
+    L.vmgym_drlvmp_choice.argtypes = [C.POINTER(Config), vp, vp, vp, i64, vp, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L
