@@ -40,8 +40,20 @@ def test_heuristics_kernel_matches_reference(base, P, V):
     obs = torch.from_numpy(g[f"h{base}_obs"]).cuda()
     pm = agent.heuristic(obs.contiguous(), torch.from_numpy(g[f"h{base}_v"]).cuda(), torch.from_numpy(g[f"h{base}_choice"]).cuda())
     got, want, ch = pm.cpu().numpy(), g[f"h{base}_pm"], g[f"h{base}_choice"]
-    bad = np.flatnonzero(got != want)
-    assert bad.size == 0, [(int(i), int(ch[i]), int(got[i]), int(want[i])) for i in bad[:10]]
+    o = g[f"h{base}_obs"]
+    key = o[:, 3 * V:3 * V + P] + o[:, 3 * V + P:]                     # cpu + memory, float32 (drlvmp.py:556,575)
+    n_tie = 0
+    for i in np.flatnonzero(got != want):
+        # torch.argsort's order among EQUAL keys is unspecified (SURVEY §8c "DRL-VMP"): a different PM is accepted only
+        # for the two sort-based heuristics, only when both PMs carry the same key, and ours must follow the pinned rule
+        assert ch[i] in (0, 3) and got[i] >= 0 and want[i] >= 0, (int(i), int(ch[i]), int(got[i]), int(want[i]))
+        assert key[i, got[i]] == key[i, want[i]], (int(i), int(ch[i]), int(got[i]), int(want[i]))
+        same = np.flatnonzero(key[i] == key[i, got[i]])
+        v = g[f"h{base}_v"][i]
+        fits = [p for p in same if np.float32(o[i, 3 * V + p] + o[i, V + v]) <= 1 and np.float32(o[i, 3 * V + P + p] + o[i, 2 * V + v]) <= 1]
+        assert got[i] == (min(fits) if ch[i] == 0 else max(fits))      # worst-fit: lowest index, best-fit: highest
+        n_tie += 1
+    assert n_tie < 0.5 * len(got)
 
 
 @pytest.mark.gpu
