@@ -74,7 +74,7 @@ def test_act_loop_equals_sequential_restatement():
     batched = agent.act(obs).cpu().numpy()
     for i in range(7):
         o = obs[i:i + 1].clone()
-        for v in torch.flatnonzero(obs[i, :30] == 10.0).tolist():
+        for v in torch.nonzero(obs[i, :30] == 10.0).flatten().tolist():
             choice = agent.dqn(o).argmax(1).to(torch.int32)
             pm = agent.heuristic(o.contiguous(), torch.tensor([v], dtype=torch.int32, device="cuda"), choice)
             if pm.item() >= 0:
