@@ -223,10 +223,51 @@ def gpu_arm(args):
     e2e_s = time.perf_counter() - t0
     clocks = sampler.finish() if sampler else None
 
+    # ---- extra A: the same kernel with 8x the envs (several resident waves per SM -> load/compute/store overlap) ----
+    big = None
+    if not args.no_extras:
+        Eb = 8 * E
+        vb = VecVmEnv(Config(**cfg), Eb, device=dev, rng="philox", seeds=cfg["seed"] + 10**6 + rank * Eb + np.arange(Eb, dtype=np.int64))
+        vb.agent_step("bestfit", n_steps=WARM_STEPS, want_obs=False, want_action=False, want_valid=False)
+        gb = vb.capture(lambda: vb.agent_step("bestfit", 1, want_obs=True, want_action=False, want_valid=False))
+        tb = []
+        for k in range(10):
+            vb.agent_step("bestfit", 99, want_obs=False, want_action=False, want_valid=False)
+            flush.fill_(k)
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(); gb.replay(); s1.record(); torch.cuda.synchronize()
+            tb.append(s0.elapsed_time(s1))
+        big = {"envs_per_gpu": Eb, "ms_per_step": float(np.mean(tb))}
+        del vb, gb
+
+    # ---- extra B: PPO training throughput (rollout with the masked-heads kernel + GAE + k_epochs update) ----
+    ppo = None
+    if not args.no_extras:
+        from vmgym.ppo import PPOAgent, PPOConfig
+        Np, Tp = 512, 16
+        vp = VecVmEnv(Config(**cfg), Np, device=dev, rng="philox", seeds=cfg["seed"] + 2 * 10**6 + rank * Np + np.arange(Np, dtype=np.int64))
+        agent_p = PPOAgent(vp, PPOConfig(hidden_size=512, batch_size=Tp, minibatch_size=Tp // 4, episodes=1, env_chunk=512,
+                                         masked=True, kl_max=1e9))
+        if world > 1:
+            for p_ in agent_p.model.parameters():
+                dist.broadcast(p_.data, 0)
+        agent_p.learn(episodes=1, max_updates=1)            # warm-up (allocations, cuBLAS heuristics)
+        barrier()
+        t0 = time.perf_counter()
+        agent_p.learn(episodes=1, max_updates=2)
+        barrier()
+        ppo = {"seconds": time.perf_counter() - t0, "env_steps": 2 * Np * Tp}
+        del vp, agent_p
+
     if world > 1:
-        t = torch.tensor([total_ms, rollout_ms, e2e_s], dtype=torch.float64, device=dev)
+        t = torch.tensor([total_ms, rollout_ms, e2e_s, big["ms_per_step"] if big else 0.0, ppo["seconds"] if ppo else 0.0],
+                         dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, rollout_ms, e2e_s = t.tolist()
+        total_ms, rollout_ms, e2e_s = t.tolist()[:3]
+        if big:
+            big["ms_per_step"] = t[3].item()
+        if ppo:
+            ppo["seconds"] = t[4].item()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -264,6 +305,16 @@ def gpu_arm(args):
                      "bytes_per_env_step": B, "peak_source": peak_src},
         "clocks": clocks,
     }
+    if big:
+        Eb, msb = big["envs_per_gpu"], big["ms_per_step"]
+        out["large_batch"] = {"envs_per_gpu": Eb, "value": world * Eb / (msb * 1e-3), "unit": UNIT, "ms_per_step": msb,
+                              "roofline_frac": B * Eb / (msb * 1e-3) / 1e9 / peak,
+                              "note": "same kernel and timing protocol, 8x the envs (10 timed steps, 100 apart)"}
+    if ppo:
+        out["ppo_train"] = {"value": world * ppo["env_steps"] / ppo["seconds"], "unit": "PPO train env-steps/s",
+                            "config": "config/100.yml, 512 envs/GPU, rollout T=16, k_epochs=4, 4 minibatches, H=512, "
+                                      "actor/critic layers via cuBLAS (torch), masked heads + GAE custom kernels",
+                            "seconds": ppo["seconds"]}
     if not args.no_cpu:
         out["cpu_baseline"] = cpu_arm(steps_per_env=args.cpu_steps)
     print(json.dumps(out), flush=True)
@@ -307,6 +358,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--cpu-steps", type=int, default=2000, help="timed CPU steps per env in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the large-batch and PPO extras")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
