@@ -188,6 +188,13 @@ int vmgym_gae(const float* d_rewards, const float* d_values, const float* d_next
 int vmgym_drlvmp_choice(const vmgym_config* cfg, const float* d_obs, const int32_t* d_vm_index, const int32_t* d_choice,
                         int64_t n_envs, int32_t* d_pm_out, void* stream);
 
+/* The actor's output layer (src/agents/ppo.py:103-109, nn.Linear(hidden, V*A)) on tcgen05 tensor cores:
+ * d_c[M, N] (fp32, row stride ldc) = d_a[M, K] (bf16) . d_w[N, K]^T (bf16, the nn.Linear weight layout) + d_bias[N].
+ * K must be a multiple of 8, operands 16-byte aligned.  bf16 inputs are a throughput mode (rollouts); parity of
+ * logits with the fp32 reference is stated per math mode in DESIGN.md. */
+int vmgym_linear_bf16(const void* d_a_bf16, const void* d_w_bf16, const float* d_bias, float* d_c, int64_t M, int64_t N,
+                      int64_t K, int64_t ldc, void* stream);
+
 /* Tuning knobs (process-wide): warps per CTA of the step kernels (0 = auto) and bulk-async record copies
  * (cp.async.bulk) on/off.  For experiments; defaults are chosen per config. */
 int vmgym_set_tuning(int warps_per_cta, int use_bulk_copy);

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "vmgym.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(vmgym_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(vmgym_[a-z_0-9]+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol():

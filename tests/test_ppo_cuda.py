@@ -163,3 +163,23 @@ def test_ppo_learn_smoke_and_checkpoint(tmp_path):
     assert a.shape == (16, 30)
     obs, r, term, _, info = vec.step(a)
     assert info["valid"].float().mean().item() > 0.9           # masked sampling proposes (almost) only valid actions
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 30600, 512), (200, 300, 128), (4096, 1000, 512), (1, 7, 8)])
+def test_tcgen05_linear_matches_torch(M, N, K):
+    """vmgym_linear_bf16 (TMA + tcgen05.mma + TMEM epilogue) vs torch on the same bf16 operands with fp32 accumulation.
+    Floating point: only the summation order differs -> |diff| <= 2e-3 * (|ref| + 1) is generous for K <= 512."""
+    import torch
+    from vmgym.ppo import linear_bf16
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.1).to(torch.bfloat16)
+    b = torch.randn(N, device="cuda", generator=g)
+    out = linear_bf16(a, w, b)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().T + b
+    err = (out - ref).abs()
+    assert torch.isfinite(out).all()
+    assert (err <= 2e-3 * (ref.abs() + 1)).all(), float(err.max())
+    out2 = linear_bf16(a, w, None)
+    assert torch.allclose(out2, ref - b, rtol=2e-3, atol=2e-3)

@@ -1,0 +1,253 @@
+// vmgym_gemm.cu — the one dense contraction of the hot path on Blackwell tensor cores (sm_100a):
+//   C[M, N] (fp32) = A[M, K] (bf16, K-major) · W[N, K]^T (bf16, K-major = nn.Linear.weight) + bias[N]
+// used for the actor's output layer (src/agents/ppo.py:103-109, Linear(hidden, V·A): 512 -> 30 600 at 100 PMs),
+// which is 95 % of the policy's FLOPs.
+//
+// Hand-written tcgen05 pipeline, one 128x128 output tile per CTA:
+//   warp 0   : TMA producer  (cp.async.bulk.tensor.2d, 128B-swizzled 128x64 bf16 boxes of A and W, mbarrier tx-count)
+//   warp 1   : MMA issuer    (one elected lane: tcgen05.mma.cta_group::1.kind::f16, M=128 N=128 K=16, accumulator in TMEM;
+//                             tcgen05.commit releases smem stages / signals the epilogue)
+//   warps 2-5: epilogue      (tcgen05.ld 32x32b.x32 TMEM -> registers, + bias, fp32 stores)
+// SASS: UTMALDG (TMA), UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/vmgym.h"
+
+extern "C" void vmgym_internal_set_error(const char* msg);
+
+namespace vmgym_gemm {
+
+constexpr int BM = 128, BN = 128, BK = 64;      // BK * sizeof(bf16) = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 3;
+constexpr int STAGE_BYTES = (BM + BN) * BK * 2; // 32 KiB
+constexpr int TMEM_COLS = 128;                  // fp32 accumulator: 128 lanes x 128 columns
+constexpr int THREADS = 192;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// K-major, 128B-swizzled operand tile (rows of 128 B, 8-row groups 1024 B apart):
+// start>>4 | LBO=1 (unused for swizzled K-major) | SBO = 1024>>4 | version 1 (sm_100) | layout SWIZZLE_128B (2)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
+{
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9 / 10-12 = 1), K-major both, N>>3 at 17, M>>4 at 24
+__device__ __forceinline__ uint32_t umma_idesc_bf16_f32(int m, int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1) linear_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                  const __grid_constant__ CUtensorMap map_w,
+                                                                  const float* __restrict__ bias, float* __restrict__ C, int M,
+                                                                  int N, int K, long long ldc)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int k_blocks = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {   // one warp allocates the accumulator columns and publishes the TMEM base address
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < k_blocks; kb++) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);                    // slot free (passes immediately on the first round)
+                unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
+                unsigned char* sb = sa + BM * BK * 2;
+                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                tma_load_2d(sa, &map_a, kb * BK, m0, &full_bar[s]);
+                tma_load_2d(sb, &map_w, kb * BK, n0, &full_bar[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (single thread) =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+            for (int kb = 0; kb < k_blocks; kb++) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(&full_bar[s], ph);                          // TMA bytes have landed
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                const uint32_t sb = sa + BM * BK * 2;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; k++) {
+                    // advance 16 bf16 = 32 B inside the 128-B swizzle row
+                    umma_bf16(tmem_base, umma_desc_sw128(sa + k * UMMA_K * 2), umma_desc_sw128(sb + k * UMMA_K * 2), idesc,
+                              (kb | k) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);                           // frees the smem stage when these MMAs retire
+            }
+            umma_commit(tmem_full_bar);                               // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 (= rows of the tile) =====
+        const int q = warp & 3;
+        mbar_wait(tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < M) {
+                float* crow = C + (long long)row * ldc + n0 + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int col = n0 + c0 + j;
+                    if (col < N) crow[j] = __uint_as_float(r[j]) + (bias ? bias[col] : 0.0f);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// row-major [rows, K] bf16 matrix -> 2-D tensor map with a (BK x box_rows) box, 128B swizzle, zero fill out of bounds
+static int make_map(CUtensorMap* map, const void* ptr, int rows, int K, int box_rows)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return -1;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+}  // namespace vmgym_gemm
+
+extern "C" int vmgym_linear_bf16(const void* d_a_bf16, const void* d_w_bf16, const float* d_bias, float* d_c, int64_t M, int64_t N,
+                                 int64_t K, int64_t ldc, void* stream)
+{
+    using namespace vmgym_gemm;
+    if (!d_a_bf16 || !d_w_bf16 || !d_c || M < 0 || N < 0 || K <= 0) { vmgym_internal_set_error("vmgym_linear_bf16: null operand"); return VMGYM_EINVAL; }
+    if (M == 0 || N == 0) return VMGYM_OK;
+    if (K % 8 != 0 || ((uintptr_t)d_a_bf16 & 15) || ((uintptr_t)d_w_bf16 & 15)) {
+        vmgym_internal_set_error("vmgym_linear_bf16: K must be a multiple of 8 and operands 16-byte aligned (TMA)");
+        return VMGYM_EINVAL;
+    }
+    CUtensorMap map_a, map_w;
+    if (make_map(&map_a, d_a_bf16, (int)M, (int)K, BM) || make_map(&map_w, d_w_bf16, (int)N, (int)K, BN)) {
+        vmgym_internal_set_error("vmgym_linear_bf16: cuTensorMapEncodeTiled failed");
+        return VMGYM_ECUDA;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(linear_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e != cudaSuccess) { vmgym_internal_set_error(cudaGetErrorString(e)); return VMGYM_ECUDA; }
+        attr_set = true;
+    }
+    dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
+    linear_bf16_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, d_bias, d_c, (int)M, (int)N, (int)K, ldc);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { vmgym_internal_set_error(cudaGetErrorString(e)); return VMGYM_ECUDA; }
+    return VMGYM_OK;
+}

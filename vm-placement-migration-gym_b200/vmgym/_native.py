@@ -15,7 +15,8 @@ PKG_ROOT = os.path.dirname(_HERE)
 REPO_ROOT = os.path.dirname(PKG_ROOT)
 CSRC = os.path.join(PKG_ROOT, "csrc")
 LIB_PATH = os.path.join(_HERE, "libvmgym.so")
-SOURCES = ["vmgym_env.cu", "vmgym_policy.cu"]
+SOURCES = ["vmgym_env.cu", "vmgym_policy.cu", "vmgym_gemm.cu"]
+# -fmad=false: the env kernels reproduce numpy's fp64/fp32 arithmetic exactly, so no FMA contraction anywhere
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -61,7 +62,7 @@ SCALARS_BYTES = 80
 
 EXPORTS = ["vmgym_last_error", "vmgym_abi_version", "vmgym_get_layout", "vmgym_reset", "vmgym_step",
            "vmgym_agent_step", "vmgym_agent_act", "vmgym_observe", "vmgym_invalid_action_mask", "vmgym_set_tuning",
-           "vmgym_policy_heads", "vmgym_policy_heads_backward", "vmgym_gae", "vmgym_drlvmp_choice"]
+           "vmgym_policy_heads", "vmgym_policy_heads_backward", "vmgym_gae", "vmgym_drlvmp_choice", "vmgym_linear_bf16"]
 
 
 class VmgymError(RuntimeError):
@@ -114,6 +115,7 @@ def lib():
     L.vmgym_policy_heads_backward.argtypes = [C.POINTER(Config), vp, i32, vp, i64, vp, i32, vp, vp, vp, vp]
     L.vmgym_gae.argtypes = [vp, vp, vp, vp, C.c_int32, i64, f32, f32, vp, vp, vp]
     L.vmgym_drlvmp_choice.argtypes = [C.POINTER(Config), vp, vp, vp, i64, vp, vp]
+    L.vmgym_linear_bf16.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

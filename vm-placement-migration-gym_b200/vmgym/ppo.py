@@ -113,6 +113,20 @@ class _MaskedHeads(torch.autograd.Function):
         return g_logits, None, None, None, None
 
 
+def linear_bf16(a: torch.Tensor, weight_bf16: torch.Tensor, bias: torch.Tensor | None = None) -> torch.Tensor:
+    """a[M, K] @ weight[N, K]^T + bias on the hand-written tcgen05 kernel (bf16 operands, fp32 accumulate / output)."""
+    a = a.to(torch.bfloat16).contiguous()
+    M, K = a.shape
+    N = weight_bf16.shape[0]
+    assert weight_bf16.dtype == torch.bfloat16 and weight_bf16.is_contiguous() and weight_bf16.shape[1] == K
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    b = bias.float().contiguous() if bias is not None else None
+    stream = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
+    nv.check(nv.lib().vmgym_linear_bf16(a.data_ptr(), weight_bf16.data_ptr(), b.data_ptr() if b is not None else None,
+                                        out.data_ptr(), M, N, K, N, stream), "vmgym_linear_bf16")
+    return out
+
+
 def gae(rewards, values, next_values, dones, gamma: float, lamda: float):
     """ppo.py:237-243 on time-major [T, N] float32 tensors (dones uint8/bool).  Returns (advantages, returns)."""
     T, N = rewards.shape
