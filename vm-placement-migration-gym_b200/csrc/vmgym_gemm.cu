@@ -158,7 +158,11 @@ __global__ void __launch_bounds__(THREADS, 1) linear_bf16_kernel(const __grid_co
         const int q = warp & 3;
         mbar_wait(tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = m0 + q * 32 + lane;
+        // All smem stages are free once the accumulator is complete (one tile per CTA): each epilogue warp uses
+        // 32 rows x 36 floats of it to turn "thread = row" (TMEM layout) into "lanes = consecutive columns" so the
+        // fp32 tile leaves as full 128-byte segments.
+        float* tr = reinterpret_cast<float*>(smem) + q * (32 * 36);
+        const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
@@ -173,12 +177,34 @@ __global__ void __launch_bounds__(THREADS, 1) linear_bf16_kernel(const __grid_co
                   "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < M) {
-                float* crow = C + (long long)row * ldc + n0 + c0;
+            __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const int col = n0 + c0 + j;
-                    if (col < N) crow[j] = __uint_as_float(r[j]) + (bias ? bias[col] : 0.0f);
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(tr + lane * 36 + j) =
+                    make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            __syncwarp();
+            // lanes 0-7 cover the 32 columns of one row with float4; 4 rows per instruction
+            const int cl = (lane & 7) * 4, rsub = lane >> 3;
+            const int col = n0 + c0 + cl;
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias) {
+                bv.x = col < N ? bias[col] : 0.f; bv.y = col + 1 < N ? bias[col + 1] : 0.f;
+                bv.z = col + 2 < N ? bias[col + 2] : 0.f; bv.w = col + 3 < N ? bias[col + 3] : 0.f;
+            }
+#pragma unroll
+            for (int rr = 0; rr < 32; rr += 4) {
+                const int rloc = rr + rsub, row = m0 + q * 32 + rloc;
+                float4 v = *reinterpret_cast<const float4*>(tr + rloc * 36 + cl);
+                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                if (row < M) {
+                    float* dst = C + (long long)row * ldc + col;
+                    if (vec_ok && col + 3 < N) *reinterpret_cast<float4*>(dst) = v;
+                    else {
+                        if (col < N) dst[0] = v.x;
+                        if (col + 1 < N) dst[1] = v.y;
+                        if (col + 2 < N) dst[2] = v.z;
+                        if (col + 3 < N) dst[3] = v.w;
+                    }
                 }
             }
         }
