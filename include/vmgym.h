@@ -195,6 +195,16 @@ int vmgym_drlvmp_choice(const vmgym_config* cfg, const float* d_obs, const int32
 int vmgym_linear_bf16(const void* d_a_bf16, const void* d_w_bf16, const float* d_bias, float* d_c, int64_t M, int64_t N,
                       int64_t K, int64_t ldc, void* stream);
 
+/* Fused actor head (ppo.py:103-109 output layer + :115-126 get_action): logits = h . Wpad^T + bias_pad are produced
+ * per (128 envs x 1 VM) tile in tensor memory and consumed there — masked (-1e7), sampled (or d_action_in evaluated),
+ * log-prob and entropy per (env, VM) — so the [M, V*A] logits never touch HBM.  d_wpad_bf16[V*128, K] / d_bias_pad[V*128]
+ * hold VM v's A rows at [128 v, 128 v + A) (zero above); d_mask_bits[M, V, 4] are the packed invalid bits written by
+ * vmgym_policy_heads(d_logits = NULL, d_mask_out = ...), or NULL for no mask.  Requires action_dim <= 128 (u8 actions).
+ * Sum d_logprob / d_entropy [M, V] over V for the per-env values of ppo.py:126. */
+int vmgym_policy_fused(const void* d_h_bf16, const void* d_wpad_bf16, const float* d_bias_pad, const uint32_t* d_mask_bits,
+                       const void* d_action_in, int64_t M, int64_t V, int64_t A, int64_t K, uint64_t seed, uint64_t counter,
+                       uint8_t* d_action_out, float* d_logprob, float* d_entropy, void* stream);
+
 /* Tuning knobs (process-wide): warps per CTA of the step kernels (0 = auto) and bulk-async record copies
  * (cp.async.bulk) on/off.  For experiments; defaults are chosen per config. */
 int vmgym_set_tuning(int warps_per_cta, int use_bulk_copy);

@@ -183,3 +183,45 @@ def test_tcgen05_linear_matches_torch(M, N, K):
     assert (err <= 2e-3 * (ref.abs() + 1)).all(), float(err.max())
     out2 = linear_bf16(a, w, None)
     assert torch.allclose(out2, ref - b, rtol=2e-3, atol=2e-3)
+
+
+def test_fused_actor_head_equals_gemm_plus_heads():
+    """vmgym_policy_fused (logits only ever in TMEM) == vmgym_linear_bf16 -> vmgym_policy_heads on the same bf16 operands,
+    mask bits and Philox stream: identical sampled actions; log-prob / entropy to fp32 summation-order tolerance."""
+    import ctypes as C
+    import torch
+    from vmgym import _native as nv
+    from vmgym.ppo import FusedActorHead, PPOAgent, PPOConfig, linear_bf16
+    vec, kw = _mk("s100", 130)                       # 130 envs: a full 128-row tile and a ragged one
+    agent = PPOAgent(vec, PPOConfig(hidden_size=512))
+    torch.manual_seed(5)
+    with torch.no_grad():
+        agent.model.actor[4].weight.mul_(40.0)        # spread the logits so the softmax is not flat
+        agent.model.actor[4].bias.normal_(0, 0.5)
+    V, A = vec.V, vec.action_dim
+    obs = vec.observe().clone()
+    hidden = agent.model.actor[:4](obs).detach()
+    bits = agent._mask_bits(-1.0)
+    head = FusedActorHead(agent.model.actor[4], V, A)
+    seed, counter = 77, 5
+    act_f, lp_f, ent_f = head(hidden, bits, seed, counter)
+    # unfused path on the same operands
+    w3 = agent.model.actor[4].weight.detach().to(torch.bfloat16).contiguous()
+    logits = linear_bf16(hidden, w3, agent.model.actor[4].bias.detach())
+    n = logits.shape[0]
+    act_u = torch.empty((n, V), dtype=torch.uint8, device=vec.device)
+    lp_u = torch.empty(n, device=vec.device); ent_u = torch.empty(n, device=vec.device)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    nv.check(nv.lib().vmgym_policy_heads(C.byref(vec._ccfg()), None, bits.data_ptr(), 1, logits.data_ptr(), n, None, nv.U8, -1.0,
+                                         seed, counter, act_u.data_ptr(), lp_u.data_ptr(), ent_u.data_ptr(), None, stream), "heads")
+    torch.cuda.synchronize()
+    assert torch.equal(act_f, act_u)
+    assert torch.allclose(lp_f, lp_u, rtol=1e-4, atol=5e-3) and torch.allclose(ent_f, ent_u, rtol=1e-4, atol=5e-3)
+    mask = vec.get_invalid_action_mask(True)
+    assert not mask.gather(-1, act_f.long().unsqueeze(-1)).any()
+    # evaluate mode: log-prob of given actions
+    _, lp_e, ent_e = head(hidden, bits, seed, counter, action_in=act_f)
+    assert torch.allclose(lp_e, lp_f, rtol=1e-5, atol=1e-4) and torch.allclose(ent_e, ent_f, rtol=1e-5, atol=1e-4)
+    # agent-level entry point
+    a2, lp2, ent2, _ = agent.fused_sample(obs)
+    assert a2.shape == (130, V) and torch.isfinite(lp2).all() and not mask.gather(-1, a2.long().unsqueeze(-1)).any()

@@ -16,6 +16,7 @@
 #include <stdio.h>
 
 #include "../../include/vmgym.h"
+#include "vmgym_sample.cuh"
 
 extern "C" void vmgym_internal_set_error(const char* msg);
 
@@ -27,7 +28,7 @@ constexpr int STAGES = 3;
 constexpr int STAGE_BYTES = (BM + BN) * BK * 2; // 32 KiB
 constexpr int TMEM_COLS = 128;                  // fp32 accumulator: 128 lanes x 128 columns
 constexpr int THREADS = 192;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 1024 /* barriers, TMEM ptr, bias tile */;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -216,6 +217,158 @@ __global__ void __launch_bounds__(THREADS, 1) linear_bf16_kernel(const __grid_co
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fused actor head: the same TMA / tcgen05 main loop, but the epilogue consumes the 128x128 fp32 accumulator
+// straight from TMEM — one tile = the A_pad = 128 logits of ONE VM for 128 envs — and emits the sampled action,
+// its log-prob and the row entropy (Network.get_action, ppo.py:115-126).  The logits never reach HBM.
+// Weights are re-laid out once on the host so VM v occupies rows [128 v, 128 v + A) (zero rows above A).
+// The invalid-action bits (env.py:45-53 + the gating of ppo.py:153-155) come packed, 4 words per (env, VM).
+// ---------------------------------------------------------------------------------------------------
+struct FusedOut {
+    const uint32_t* mask_bits;   // [M, V, 4] or nullptr (unmasked)
+    const float* bias_pad;       // [V * 128]
+    const void* action_in;       // evaluate these actions (u8) or nullptr
+    uint8_t* action_out;         // [M, V]
+    float* logprob;              // [M, V]
+    float* entropy;              // [M, V]
+    int A, V;
+    unsigned long long seed;
+    uint32_t counter;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) policy_fused_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                   const __grid_constant__ CUtensorMap map_w, FusedOut fo, int M, int K)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);          // 128 floats (inside the 1 KiB tail region)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int v = blockIdx.x, m0 = blockIdx.y * BM, n0 = v * BN;
+    const int k_blocks = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) { const int t = threadIdx.x - 64; s_bias[t] = fo.bias_pad[n0 + t]; }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < k_blocks; kb++) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
+                unsigned char* sb = sa + BM * BK * 2;
+                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                tma_load_2d(sa, &map_a, kb * BK, m0, &full_bar[s]);
+                tma_load_2d(sb, &map_w, kb * BK, n0, &full_bar[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+            for (int kb = 0; kb < k_blocks; kb++) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                const uint32_t sb = sa + BM * BK * 2;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; k++)
+                    umma_bf16(tmem_base, umma_desc_sw128(sa + k * UMMA_K * 2), umma_desc_sw128(sb + k * UMMA_K * 2), idesc,
+                              (kb | k) ? 1u : 0u);
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        // ===== fused epilogue: thread = env row, registers = this VM's logits =====
+        const int q = warp & 3;
+        const int e = m0 + q * 32 + lane;
+        const int A = fo.A;
+        uint4 inv = make_uint4(0u, 0u, 0u, 0u);
+        if (fo.mask_bits && e < M) inv = reinterpret_cast<const uint4*>(fo.mask_bits)[(long long)e * fo.V + v];
+        int act_given = -1;
+        if (fo.action_in && e < M) act_given = reinterpret_cast<const uint8_t*>(fo.action_in)[(long long)e * fo.V + v];
+        mbar_wait(tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // online log-softmax statistics relative to the running max m:  s = sum e^(z-m),  t = sum e^(z-m) (z-m)
+        float m = 0.f, ssum = 0.f, tsum = 0.f, best = -INFINITY, best_z = 0.f, z_given = 0.f;
+        int best_a = 0;
+        vmgym::Philox4 rnd = {0u, 0u, 0u, 0u};
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN && c0 < A; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const uint32_t iw = c0 == 0 ? inv.x : (c0 == 32 ? inv.y : (c0 == 64 ? inv.z : inv.w));
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int a = c0 + j;
+                if (a < A) {
+                    float z = __uint_as_float(r[j]) + s_bias[a];
+                    if ((iw >> j) & 1u) z = -1e7f;                       // ppo.py:119
+                    if (a == 0) { m = z; ssum = 1.f; tsum = 0.f; }
+                    else {
+                        if (z > m) { const float d = z - m, sc = expf(-d); tsum = (tsum - d * ssum) * sc; ssum *= sc; m = z; }
+                        const float x = z - m, ex = expf(x);
+                        ssum += ex; tsum += ex * x;
+                    }
+                    if (a == act_given) z_given = z;
+                    if (!fo.action_in) {
+                        if ((a & 3) == 0) rnd = vmgym::sample_block(v, a >> 2, (uint32_t)e, fo.seed, fo.counter);
+                        const float sc2 = z + vmgym::gumbel_from(rnd, a & 3);
+                        if (sc2 > best) { best = sc2; best_a = a; best_z = z; }
+                    }
+                }
+            }
+        }
+        if (e < M) {
+            const float ls = logf(ssum);
+            const int act = fo.action_in ? act_given : best_a;
+            const float za = fo.action_in ? z_given : best_z;
+            const long long o = (long long)e * fo.V + v;
+            if (fo.action_out) fo.action_out[o] = (uint8_t)act;
+            fo.logprob[o] = ((unsigned)act < (unsigned)A) ? (za - m) - ls : 0.f;
+            fo.entropy[o] = ls - tsum / ssum;                            // -sum p log p
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -273,6 +426,41 @@ extern "C" int vmgym_linear_bf16(const void* d_a_bf16, const void* d_w_bf16, con
     }
     dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
     linear_bf16_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, d_bias, d_c, (int)M, (int)N, (int)K, ldc);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { vmgym_internal_set_error(cudaGetErrorString(e)); return VMGYM_ECUDA; }
+    return VMGYM_OK;
+}
+
+extern "C" int vmgym_policy_fused(const void* d_h_bf16, const void* d_wpad_bf16, const float* d_bias_pad, const uint32_t* d_mask_bits,
+                                  const void* d_action_in, int64_t M, int64_t V, int64_t A, int64_t K, uint64_t seed,
+                                  uint64_t counter, uint8_t* d_action_out, float* d_logprob, float* d_entropy, void* stream)
+{
+    using namespace vmgym_gemm;
+    if (!d_h_bf16 || !d_wpad_bf16 || !d_bias_pad || !d_logprob || !d_entropy || (!d_action_in && !d_action_out) || M < 0) {
+        vmgym_internal_set_error("vmgym_policy_fused: null operand");
+        return VMGYM_EINVAL;
+    }
+    if (A < 1 || A > 128 || K % 8 != 0 || ((uintptr_t)d_h_bf16 & 15) || ((uintptr_t)d_wpad_bf16 & 15) || ((uintptr_t)d_mask_bits & 15)) {
+        vmgym_internal_set_error("vmgym_policy_fused: needs action_dim <= 128, K % 8 == 0 and 16-byte aligned operands");
+        return VMGYM_EUNSUPPORTED;
+    }
+    if (M == 0 || V == 0) return VMGYM_OK;
+    CUtensorMap map_a, map_w;
+    if (make_map(&map_a, d_h_bf16, (int)M, (int)K, BM) || make_map(&map_w, d_wpad_bf16, (int)(V * BN), (int)K, BN)) {
+        vmgym_internal_set_error("vmgym_policy_fused: cuTensorMapEncodeTiled failed");
+        return VMGYM_ECUDA;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(policy_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e != cudaSuccess) { vmgym_internal_set_error(cudaGetErrorString(e)); return VMGYM_ECUDA; }
+        attr_set = true;
+    }
+    FusedOut fo;
+    fo.mask_bits = d_mask_bits; fo.bias_pad = d_bias_pad; fo.action_in = d_action_in; fo.action_out = d_action_out;
+    fo.logprob = d_logprob; fo.entropy = d_entropy; fo.A = (int)A; fo.V = (int)V; fo.seed = seed; fo.counter = (uint32_t)counter;
+    dim3 grid((unsigned)V, (unsigned)((M + BM - 1) / BM));
+    policy_fused_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, fo, (int)M, (int)K);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { vmgym_internal_set_error(cudaGetErrorString(e)); return VMGYM_ECUDA; }
     return VMGYM_OK;

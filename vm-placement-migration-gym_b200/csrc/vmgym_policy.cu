@@ -10,6 +10,7 @@
 #include <stdio.h>
 
 #include "vmgym_env_kernels.cuh"
+#include "vmgym_sample.cuh"
 
 namespace vmgym {
 
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
                 if (lane == 0) mo[i] = word;
             }
         }
+        if (!p.logits) continue;                     // mask-only call (the fused policy kernel consumes the packed bits)
         // ---- masked logits, log-softmax ----
         const float* z = p.logits + (env * V + v) * (long long)A;
         float zl[8];
@@ -163,10 +165,8 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
             for (int i = 0; i < NI; i++) {
                 const int a = i * 32 + lane;
                 if (a < A) {
-                    const Philox4 r = philox4x32_10((uint32_t)(v * A + a), (uint32_t)env, 4u, (uint32_t)p.counter, (uint32_t)p.seed,
-                                                    (uint32_t)(p.seed >> 32));
-                    const float u = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);     // (0,1)
-                    const float g = -logf(-logf(u));
+                    const Philox4 r = sample_block(v, a >> 2, (uint32_t)env, p.seed, (uint32_t)p.counter);
+                    const float g = gumbel_from(r, a & 3);
                     const float s = zl[i] + g;
                     if (s > best) { best = s; besta = a; }
                 }
@@ -262,7 +262,7 @@ static int heads_launch(HeadParams& hp, const vmgym_config* cfg, bool backward, 
     L.off_mem = pub.off_memory; L.off_rem = pub.off_remaining; L.off_place = pub.off_placement; L.off_cpuc = pub.off_cpu_code;
     L.off_memc = pub.off_mem_code; L.off_cap = pub.off_capacity; L.off_scal = pub.off_scalars; L.rec_bytes = pub.record_bytes;
     if (L.A > 256) return pfail(VMGYM_EUNSUPPORTED, "action_dim > 256 not supported by the heads kernel yet");
-    if (!hp.logits || hp.n_envs < 0) return pfail(VMGYM_EINVAL, "null logits");
+    if ((!hp.logits && !hp.mask_out) || hp.n_envs < 0) return pfail(VMGYM_EINVAL, "null logits");
     if (hp.n_envs == 0) return VMGYM_OK;
     const int threads = 256;
     const size_t smem = (size_t)16 * L.Pp + 2 * (threads / 32) * sizeof(float);
@@ -290,7 +290,7 @@ int vmgym_policy_heads(const vmgym_config* cfg, const void* d_state, const uint3
     hp.n_envs = n_envs; hp.action_in = d_action_in; hp.action_dtype = action_dtype; hp.migration_ratio = migration_ratio;
     hp.seed = seed; hp.counter = counter; hp.action_out = d_action_out; hp.logprob = d_logprob; hp.entropy = d_entropy;
     hp.mask_out = d_mask_out;
-    if (!d_action_in && !d_action_out) return pfail(VMGYM_EINVAL, "need action_in (evaluate) or action_out (sample)");
+    if (d_logits && !d_action_in && !d_action_out) return pfail(VMGYM_EINVAL, "need action_in (evaluate) or action_out (sample)");
     return heads_launch(hp, cfg, false, stream);
 }
 

@@ -62,7 +62,7 @@ SCALARS_BYTES = 80
 
 EXPORTS = ["vmgym_last_error", "vmgym_abi_version", "vmgym_get_layout", "vmgym_reset", "vmgym_step",
            "vmgym_agent_step", "vmgym_agent_act", "vmgym_observe", "vmgym_invalid_action_mask", "vmgym_set_tuning",
-           "vmgym_policy_heads", "vmgym_policy_heads_backward", "vmgym_gae", "vmgym_drlvmp_choice", "vmgym_linear_bf16"]
+           "vmgym_policy_heads", "vmgym_policy_heads_backward", "vmgym_gae", "vmgym_drlvmp_choice", "vmgym_linear_bf16", "vmgym_policy_fused"]
 
 
 class VmgymError(RuntimeError):
@@ -72,7 +72,7 @@ class VmgymError(RuntimeError):
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu into vmgym/libvmgym.so (sm_100a, -lineinfo).  nvcc cross-compiles without a GPU."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in ("vmgym_device.cuh", "vmgym_sort.cuh", "vmgym_env_kernels.cuh")] + \
+    deps = srcs + [os.path.join(CSRC, h) for h in ("vmgym_device.cuh", "vmgym_sort.cuh", "vmgym_env_kernels.cuh", "vmgym_sample.cuh")] + \
         [os.path.join(REPO_ROOT, "include", "vmgym.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
@@ -116,6 +116,7 @@ def lib():
     L.vmgym_gae.argtypes = [vp, vp, vp, vp, C.c_int32, i64, f32, f32, vp, vp, vp]
     L.vmgym_drlvmp_choice.argtypes = [C.POINTER(Config), vp, vp, vp, i64, vp, vp]
     L.vmgym_linear_bf16.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp]
+    L.vmgym_policy_fused.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, u64, u64, vp, vp, vp, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

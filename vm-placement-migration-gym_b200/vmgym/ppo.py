@@ -127,6 +127,46 @@ def linear_bf16(a: torch.Tensor, weight_bf16: torch.Tensor, bias: torch.Tensor |
     return out
 
 
+class FusedActorHead:
+    """The actor's output layer + masked multi-categorical heads as ONE tcgen05 kernel (vmgym_policy_fused): logits live
+    only in tensor memory.  Holds the bf16 re-layout of nn.Linear(hidden, V*A): VM v's A rows at [128 v, 128 v + A)."""
+
+    TILE = 128
+
+    def __init__(self, linear: nn.Linear, n_vms: int, action_dim: int):
+        if action_dim > self.TILE:
+            raise nv.VmgymError("the fused actor head needs action_dim <= 128")
+        self.V, self.A, self.K = int(n_vms), int(action_dim), linear.in_features
+        self.linear = linear
+        self.refresh()
+
+    @torch.no_grad()
+    def refresh(self):
+        """Re-derive the padded bf16 weights after an optimiser step."""
+        V, A, K, T = self.V, self.A, self.K, self.TILE
+        w = torch.zeros((V, T, K), dtype=torch.bfloat16, device=self.linear.weight.device)
+        w[:, :A] = self.linear.weight.detach().view(V, A, K).to(torch.bfloat16)
+        b = torch.zeros((V, T), dtype=torch.float32, device=w.device)
+        b[:, :A] = self.linear.bias.detach().view(V, A).float()
+        self.w_pad, self.b_pad = w.view(V * T, K).contiguous(), b.view(-1).contiguous()
+
+    def __call__(self, hidden, mask_bits, seed: int, counter: int, action_in=None):
+        """hidden [M, K] -> (action u8 [M, V], logprob [M], entropy [M]); `mask_bits` int32 [M, V, 4] or None."""
+        h = hidden.to(torch.bfloat16).contiguous()
+        M = h.shape[0]
+        dev = h.device
+        action = torch.empty((M, self.V), dtype=torch.uint8, device=dev) if action_in is None else None
+        lp = torch.empty((M, self.V), dtype=torch.float32, device=dev)
+        ent = torch.empty((M, self.V), dtype=torch.float32, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        nv.check(nv.lib().vmgym_policy_fused(h.data_ptr(), self.w_pad.data_ptr(), self.b_pad.data_ptr(),
+                                             mask_bits.data_ptr() if mask_bits is not None else None,
+                                             action_in.data_ptr() if action_in is not None else None, M, self.V, self.A, self.K,
+                                             int(seed), int(counter), action.data_ptr() if action is not None else None,
+                                             lp.data_ptr(), ent.data_ptr(), stream), "vmgym_policy_fused")
+        return (action if action_in is None else action_in), lp.sum(1), ent.sum(1)
+
+
 def gae(rewards, values, next_values, dones, gamma: float, lamda: float):
     """ppo.py:237-243 on time-major [T, N] float32 tensors (dones uint8/bool).  Returns (advantages, returns)."""
     T, N = rewards.shape
@@ -156,6 +196,7 @@ class PPOAgent:
         self.mask_words = (self.A + 31) // 32
         self.seed = int(vec.config.seed if seed is None else seed)
         self._calls = 0
+        self._fused = None
         self.total_steps = 0
         self.training = True
 
@@ -189,6 +230,32 @@ class PPOAgent:
                                              action.data_ptr(), logprob.data_ptr(), entropy.data_ptr(),
                                              mask.data_ptr() if mask is not None else None, stream), "vmgym_policy_heads")
         return action, logprob, entropy, mask
+
+    def _mask_bits(self, migration_ratio: float):
+        """Packed invalid-action bits [N, V, ceil(A/32)] of the env's current state (+ gating), no logits involved."""
+        vec = self.vec
+        n = vec.num_envs
+        mask = torch.empty((n, self.V, self.mask_words), dtype=torch.int32, device=self.device)
+        self._calls += 1
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        nv.check(nv.lib().vmgym_policy_heads(C.byref(vec._ccfg()), vec.state.data_ptr(), None, int(bool(self.config.masked)),
+                                             None, n, None, nv.U8, float(migration_ratio), self.seed, self._calls, None, None,
+                                             None, mask.data_ptr(), stream), "vmgym_policy_heads(mask)")
+        return mask
+
+    @torch.no_grad()
+    def fused_sample(self, obs, migration_ratio: float = -1.0):
+        """Rollout forward on tensor cores: obs -> hidden (torch) -> fused output layer + heads (tcgen05, bf16 operands).
+        Returns (action u8 [N, V], logprob [N], entropy [N], packed mask).  Needs action_dim <= 128."""
+        if self._fused is None:
+            self._fused = FusedActorHead(self.model.actor[4], self.V, self.A)
+        hidden = self.model.actor[:4](obs)
+        mask = self._mask_bits(migration_ratio) if self.mask_words == 4 else None
+        if mask is None and self.config.masked:
+            raise nv.VmgymError("fused head expects 4 mask words per row (96 < action_dim <= 128)")
+        self._calls += 1
+        action, lp, ent = self._fused(hidden, mask if self.config.masked else None, self.seed, self._calls)
+        return action, lp, ent, mask
 
     @torch.no_grad()
     def act(self, obs):
