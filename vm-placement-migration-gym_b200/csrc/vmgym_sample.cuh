@@ -7,16 +7,26 @@
 
 namespace vmgym {
 
-// One Philox4x32-10 call serves 4 consecutive columns of row (env, v): counter (v*64 + a/4, env, 4, call counter).
+// One Philox4x32-7 call (7 rounds: the fastest Crush-resistant variant of Salmon et al.) serves 4 consecutive columns
+// of row (env, v): counter (v*64 + a/4, env, 4, call counter).
 __device__ __forceinline__ Philox4 sample_block(int v, int a4, uint32_t env, unsigned long long seed, uint32_t counter)
 {
-    return philox4x32_10((uint32_t)(v * 64 + a4), env, 4u, counter, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint32_t c0 = (uint32_t)(v * 64 + a4), c1 = env, c2 = 4u, c3 = counter, k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 7; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0, hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return Philox4{c0, c1, c2, c3};
 }
+// Gumbel(0,1) noise from 24 random bits; the fast log intrinsic is ample for sampling noise and is used by both kernels
 __device__ __forceinline__ float gumbel_from(const Philox4& r, int sub)
 {
     const uint32_t bits = sub == 0 ? r.x : (sub == 1 ? r.y : (sub == 2 ? r.z : r.w));
     const float u = ((float)(bits >> 8) + 0.5f) * (1.0f / 16777216.0f);     // (0,1)
-    return -logf(-logf(u));
+    return -__logf(-__logf(u));
 }
 
 }  // namespace vmgym
