@@ -312,10 +312,10 @@ __global__ void __launch_bounds__(THREADS, 1) policy_fused_kernel(const __grid_c
         if (fo.action_in && e < M) act_given = reinterpret_cast<const uint8_t*>(fo.action_in)[(long long)e * fo.V + v];
         mbar_wait(tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // online log-softmax statistics relative to the running max m:  s = sum e^(z-m),  t = sum e^(z-m) (z-m)
-        float m = 0.f, ssum = 0.f, tsum = 0.f, best = -INFINITY, best_z = 0.f, z_given = 0.f;
+        // log-softmax statistics relative to the running max m:  s = sum e^(z-m),  t = sum e^(z-m) (z-m), merged chunk by
+        // chunk (32 columns): one max + one rescale per chunk, then 32 independent exponentials (instruction-level parallelism)
+        float m = -1e30f, ssum = 0.f, tsum = 0.f, best = -INFINITY, best_z = 0.f, z_given = 0.f;
         int best_a = 0;
-        vmgym::Philox4 rnd = {0u, 0u, 0u, 0u};
 #pragma unroll 1
         for (int c0 = 0; c0 < BN && c0 < A; c0 += 32) {
             uint32_t r[32];
@@ -331,29 +331,51 @@ __global__ void __launch_bounds__(THREADS, 1) policy_fused_kernel(const __grid_c
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             const uint32_t iw = c0 == 0 ? inv.x : (c0 == 32 ? inv.y : (c0 == 64 ? inv.z : inv.w));
+            float z[32];
+            float cm = -1e30f;
 #pragma unroll
             for (int j = 0; j < 32; j++) {
                 const int a = c0 + j;
-                if (a < A) {
-                    float z = __uint_as_float(r[j]) + s_bias[a];
-                    if ((iw >> j) & 1u) z = -1e7f;                       // ppo.py:119
-                    if (a == 0) { m = z; ssum = 1.f; tsum = 0.f; }
-                    else {
-                        if (z > m) { const float d = z - m, sc = expf(-d); tsum = (tsum - d * ssum) * sc; ssum *= sc; m = z; }
-                        const float x = z - m, ex = expf(x);
-                        ssum += ex; tsum += ex * x;
-                    }
-                    if (a == act_given) z_given = z;
-                    if (!fo.action_in) {
-                        if ((a & 3) == 0) rnd = vmgym::sample_block(v, a >> 2, (uint32_t)e, fo.seed, fo.counter);
-                        const float sc2 = z + vmgym::gumbel_from(rnd, a & 3);
-                        if (sc2 > best) { best = sc2; best_a = a; best_z = z; }
+                float x = __uint_as_float(r[j]) + s_bias[a];
+                if ((iw >> j) & 1u) x = -1e7f;                           // ppo.py:119
+                if (a >= A) x = -1e30f;                                  // padding columns of the 128-wide tile
+                z[j] = x;
+                cm = fmaxf(cm, x);
+            }
+            if (cm > m) {
+                if (c0 > 0) { const float d = cm - m, sc = __expf(-d); tsum = (tsum - d * ssum) * sc; ssum *= sc; }
+                m = cm;
+            }
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float x0 = z[j] - m, x1 = z[j + 1] - m, x2 = z[j + 2] - m, x3 = z[j + 3] - m;
+                const float e0 = __expf(x0), e1 = __expf(x1), e2 = __expf(x2), e3 = __expf(x3);
+                s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+                t0 += e0 * x0; t1 += e1 * x1; t2 += e2 * x2; t3 += e3 * x3;
+            }
+            ssum += (s0 + s1) + (s2 + s3);
+            tsum += (t0 + t1) + (t2 + t3);
+            if (fo.action_in) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) if (c0 + j == act_given) z_given = z[j];
+            } else {
+#pragma unroll
+                for (int j4 = 0; j4 < 32; j4 += 4) {
+                    if (c0 + j4 < A) {
+                        const vmgym::Philox4 rnd = vmgym::sample_block(v, (c0 + j4) >> 2, (uint32_t)e, fo.seed, fo.counter);
+#pragma unroll
+                        for (int jj = 0; jj < 4; jj++) {
+                            const int a = c0 + j4 + jj;
+                            const float sc2 = z[j4 + jj] + vmgym::gumbel_from(rnd, jj);
+                            if (a < A && sc2 > best) { best = sc2; best_a = a; best_z = z[j4 + jj]; }
+                        }
                     }
                 }
             }
         }
         if (e < M) {
-            const float ls = logf(ssum);
+            const float ls = __logf(ssum);
             const int act = fo.action_in ? act_given : best_a;
             const float za = fo.action_in ? z_given : best_z;
             const long long o = (long long)e * fo.V + v;
