@@ -246,8 +246,9 @@ def gpu_arm(args):
         from vmgym.ppo import PPOAgent, PPOConfig
         Np, Tp = 512, 16
         vp = VecVmEnv(Config(**cfg), Np, device=dev, rng="philox", seeds=cfg["seed"] + 2 * 10**6 + rank * Np + np.arange(Np, dtype=np.int64))
+        torch.set_float32_matmul_precision("high")      # as the reference does (main.py:45): TF32 for the fp32 layers
         agent_p = PPOAgent(vp, PPOConfig(hidden_size=512, batch_size=Tp, minibatch_size=Tp // 4, episodes=1, env_chunk=512,
-                                         masked=True, kl_max=1e9))
+                                         masked=True, kl_max=1e9, fused_rollout=True))
         if world > 1:
             for p_ in agent_p.model.parameters():
                 dist.broadcast(p_.data, 0)
@@ -313,7 +314,7 @@ def gpu_arm(args):
     if ppo:
         out["ppo_train"] = {"value": world * ppo["env_steps"] / ppo["seconds"], "unit": "PPO train env-steps/s",
                             "config": "config/100.yml, 512 envs/GPU, rollout T=16, k_epochs=4, 4 minibatches, H=512, "
-                                      "actor/critic layers via cuBLAS (torch), masked heads + GAE custom kernels",
+                                      "rollout: fused tcgen05 actor head (bf16), update: cuBLAS TF32 layers + masked-heads/GAE kernels",
                             "seconds": ppo["seconds"]}
     if not args.no_cpu:
         out["cpu_baseline"] = cpu_arm(steps_per_env=args.cpu_steps)

@@ -146,6 +146,7 @@ def test_ppo_learn_smoke_and_checkpoint(tmp_path):
               allow_null_action=True)
     vec = VecVmEnv(Config(**kw), 16, rng="philox")
     agent = PPOAgent(vec, PPOConfig(hidden_size=64, batch_size=20, minibatch_size=5, episodes=1, env_chunk=8, lr=1e-3, kl_max=1e9))
+    assert agent.mask_words == 1          # action_dim 12: the fused tcgen05 head needs 96 < action_dim <= 128, not used here
     before = [p.detach().clone() for p in agent.model.parameters()]
     agent.learn(episodes=1)
     after = list(agent.model.parameters())
@@ -225,3 +226,20 @@ def test_fused_actor_head_equals_gemm_plus_heads():
     # agent-level entry point
     a2, lp2, ent2, _ = agent.fused_sample(obs)
     assert a2.shape == (130, V) and torch.isfinite(lp2).all() and not mask.gather(-1, a2.long().unsqueeze(-1)).any()
+
+
+def test_ppo_learn_with_fused_rollout_s100():
+    """One short training iteration at the config/100.yml shape with rollouts through the fused tcgen05 actor head."""
+    import torch
+    from vmgym import Config, VecVmEnv
+    from vmgym.ppo import PPOAgent, PPOConfig
+    kw = dict(pms=100, vms=300, arrival_rate=1.8182, service_length=1000, training_steps=12, eval_steps=100, reward_function="wr",
+              allow_null_action=True)
+    vec = VecVmEnv(Config(**kw), 64, rng="philox")
+    agent = PPOAgent(vec, PPOConfig(hidden_size=128, batch_size=6, minibatch_size=3, episodes=1, env_chunk=32, lr=1e-4, kl_max=1e9,
+                                    fused_rollout=True))
+    before = [p.detach().clone() for p in agent.model.parameters()]
+    agent.learn(episodes=1)
+    assert all(torch.isfinite(p).all() for p in agent.model.parameters())
+    assert any(not torch.equal(a, b) for a, b in zip(agent.model.parameters(), before))
+    assert vec.counters()["place_actions"].sum() > 0

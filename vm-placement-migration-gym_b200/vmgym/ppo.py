@@ -49,6 +49,7 @@ class PPOConfig:
     training_progress_bar: bool = True
     device: str = "cuda"
     env_chunk: int = 256           # envs per forward/backward chunk inside a minibatch (gradient accumulation)
+    fused_rollout: bool = False    # rollouts through the fused tcgen05 actor head (bf16 operands; action_dim <= 128)
 
 
 def _ortho(layer: nn.Linear, gain: float) -> nn.Linear:
@@ -301,8 +302,11 @@ class PPOAgent:
             done, i = False, 0
             while not done:
                 with torch.no_grad():
-                    logits = self.model.actor(obs).contiguous()
-                    action, logprob, _, mask = self._heads(logits, -1.0, want_mask=True)   # no gating in training (ppo.py:196-197)
+                    if cfg.fused_rollout:
+                        action, logprob, _, mask = self.fused_sample(obs, -1.0)
+                    else:
+                        logits = self.model.actor(obs).contiguous()
+                        action, logprob, _, mask = self._heads(logits, -1.0, want_mask=True)   # no gating in training (ppo.py:196-197)
                 nobs, reward, term, _, _ = vec.step(action, want_valid=False)
                 buf["obs"][i], buf["next_obs"][i], buf["action"][i], buf["mask"][i] = obs, nobs, action, mask
                 buf["logprob"][i], buf["reward"][i], buf["done"][i] = logprob, reward.float(), vec.terminated_u8
@@ -313,6 +317,8 @@ class PPOAgent:
                 done = bool(term[0].item())                           # all envs share the step limit
                 if i >= T:
                     self.update(**buf)
+                    if self._fused is not None:
+                        self._fused.refresh()
                     i = 0
                     updates += 1
                     if max_updates is not None and updates >= max_updates:
