@@ -92,13 +92,17 @@ __device__ __forceinline__ double warp_sum(double x)
     return x;
 }
 
-// largest size code k in [0,100] with x + sz32[k] <= 1.0f (monotone in k because fp32 rounding is monotone)
+// largest size code k in [0,100] with x + sz32[k] <= 1.0f (monotone in k because fp32 rounding is monotone).
+// k0 = trunc((1 - x) * 100) is within one of the answer: 1 - x and the product carry < 1.3e-5 of absolute error in
+// units of k, and the rounding of x + sz32[k] moves the threshold by < 1e-5, so the two can only disagree next to an
+// integer — one probe up and one probe down settle it without a loop (checked against the definition over 2 M loads
+// incl. every boundary neighbour, and by the capacity-cache parity checks in tests/test_env_cuda.py).
 __device__ __forceinline__ int max_code(const float* sz32, float x)
 {
-    int k = min(100, max(0, (int)((1.0f - x) * 100.0f)));      // estimate, then exact correction (usually 1-2 probes)
-    while (k < 100 && x + sz32[k + 1] <= 1.0f) k++;
-    while (k > 0 && x + sz32[k] > 1.0f) k--;
-    return k;
+    const int k0 = min(100, max(0, (int)((1.0f - x) * 100.0f)));
+    const int up = (k0 < 100 && x + sz32[min(k0 + 1, 100)] <= 1.0f) ? 1 : 0;
+    const int dn = (k0 > 0 && x + sz32[k0] > 1.0f) ? 1 : 0;
+    return k0 + up - dn;
 }
 
 template <typename PT>
@@ -488,6 +492,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
     // ---- 2+3. service countdown and departures in VM-index order (_run_vms, env.py:244-265) ----
     int served = 0;
     bool need_full_refresh = false;
+    int freed0 = -1, freed1 = -1, freed2 = -1, freed3 = -1;    // first slots freed by this step's departures (slot order)
     if (sizeof(PT) == 1) {
         // 4 slots per lane: placement bytes as one u32, remaining runtimes as 4 x u16 (padding slots are empty)
         const uint32_t P4 = (uint32_t)P * 0x01010101u;
@@ -517,7 +522,12 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                     const int b = __ffs(m) - 1;
                     m &= m - 1;
                     unsigned t4 = __shfl_sync(FULL, term4, b);
-                    served += __popc(t4);
+                    for (unsigned tt = t4; tt; tt &= tt - 1) {
+                        const int vf = 4 * (g0 + b) + __ffs(tt) - 1;
+                        if (served == 0) freed0 = vf; else if (served == 1) freed1 = vf; else if (served == 2) freed2 = vf;
+                        else if (served == 3) freed3 = vf;
+                        served++;
+                    }
                     if (lane == 0) {
                         while (t4) {
                             const int j = __ffs(t4) - 1;
@@ -596,9 +606,16 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
     int admitted = 0;
     long long csum = 0, msum = 0;
     if (quota > 0 && n_empty0 > 0) {
-        for (int c0 = 0; c0 < V && admitted < quota; c0 += 32) {
-            const int v = c0 + lane;
-            const bool empty = v < V && (int)place[v] == P + 1;
+        // When no slot was empty before this step, the empty slots are exactly the ones this step's departures freed,
+        // already known in slot order: lane k admits into the k-th of them.  Otherwise scan for the lowest-index empties.
+        const bool known = sizeof(PT) == 1 && sc->n_empty == 0 && served <= 4;
+        for (int c0 = 0; c0 < (known ? 32 : V) && admitted < quota; c0 += 32) {
+            int v = c0 + lane;
+            bool empty = v < V && !known && (int)place[v] == P + 1;
+            if (known) {
+                v = lane == 0 ? freed0 : (lane == 1 ? freed1 : (lane == 2 ? freed2 : freed3));
+                empty = lane < served;
+            }
             const unsigned m = __ballot_sync(FULL, empty);
             const int rank = admitted + __popc(m & ((1u << lane) - 1u));
             if (empty && rank < quota) {                       // lowest-index empty slots (:275-277)
