@@ -794,6 +794,19 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     unsigned char* base = smem + L.sm_tables + (size_t)warp * L.sm_stride;
     uint64_t* bar = reinterpret_cast<uint64_t*>(base + L.sm_bar);
+    const bool BULK = p.use_bulk != 0;
+    const long long stride = (long long)gridDim.x * wpc;
+    const long long env0 = (long long)blockIdx.x * wpc + warp;
+    // Start staging this warp's first record before anything else: the bulk copy only needs the warp's own mbarrier, so
+    // its DRAM round trip overlaps the table set-up below instead of following it.
+    if (BULK && lane == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+        if (env0 < p.n_envs) {
+            mbar_arrive_expect_tx(bar, (uint32_t)L.rec_bytes);
+            bulk_g2s(base, p.state + env0 * (long long)L.rec_bytes, (uint32_t)L.rec_bytes, bar);
+        }
+    }
     fill_tables(sz64, sz32);
     const bool philox = p.tr.mode == VMGYM_TRACE_PHILOX;
     const bool arr_in_smem = philox && p.tr.arrival_cdf_len <= ARR_CDF_SMEM;
@@ -805,8 +818,6 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
     const bool have_bracket = philox && p.tr.d_service_bracket != nullptr;
     if (have_bracket)
         for (int k = threadIdx.x; k < SVC_BRACKETS + 1; k += blockDim.x) svc_bracket_s[k] = p.tr.d_service_bracket[k];
-    const bool BULK = p.use_bulk != 0;
-    if (BULK && lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
     __syncthreads();
 
     Env<PT> e;
@@ -815,12 +826,11 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
     e.svc_cdf = svc_in_smem ? svc_cdf_s : p.tr.d_service_cdf;
     e.svc_bracket = have_bracket ? svc_bracket_s : nullptr;
     uint32_t phase = 0;
-    const long long stride = (long long)gridDim.x * wpc;
-    for (long long env = (long long)blockIdx.x * wpc + warp; env < p.n_envs; env += stride) {
+    for (long long env = env0; env < p.n_envs; env += stride) {
         unsigned char* grec = p.state + env * (long long)L.rec_bytes;
         // ---- stage the record into shared memory ----
         if (BULK) {
-            if (lane == 0) {
+            if (lane == 0 && env != env0) {
                 mbar_arrive_expect_tx(bar, (uint32_t)L.rec_bytes);
                 bulk_g2s(base, grec, (uint32_t)L.rec_bytes, bar);
             }
