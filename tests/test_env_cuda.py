@@ -91,6 +91,8 @@ SHAPES = {
                  reward_function="wr", allow_null_action=True),
     "odd": dict(pms=33, vms=65, arrival_rate=1.0, service_length=50, training_steps=10000, eval_steps=100000,
                 reward_function="ut", beta=0.3, allow_null_action=False, sequence="highuniform", cap_target_util=False),
+    "s1000": dict(pms=1000, vms=3000, arrival_rate=1.6, service_length=1000, training_steps=10000, eval_steps=100000,
+                  reward_function="wr", allow_null_action=True, sequence="highuniform"),      # BASELINE config 5 shape
     "wide": dict(pms=300, vms=700, arrival_rate=4.0, service_length=120, training_steps=10000, eval_steps=100000,
                  reward_function="kl", allow_null_action=True, sequence="lowuniform"),
 }
@@ -142,7 +144,7 @@ def test_batched_step_matches_oracle_random_actions(shape, n_envs, steps, bulk):
 
 @pytest.mark.parametrize("agent,tie", [("firstfit", "stable"), ("bestfit", "stable"), ("bestfit", "numpy_introsort")])
 @pytest.mark.parametrize("shape,n_envs,steps,chunk", [("s100", 6, 1300, 1), ("s100", 6, 1300, 64), ("s10", 20, 380, 7),
-                                                       ("odd", 9, 500, 25)])
+                                                       ("odd", 9, 500, 25), ("s1000", 2, 150, 50)])
 @pytest.mark.parametrize("vectors", [True, False])
 def test_fused_agent_step_matches_oracle_rollout(agent, tie, shape, n_envs, steps, chunk, vectors):
     """agent.act + env.step fused in one kernel (chunk steps per launch) == oracle act()/step() loop.
@@ -290,3 +292,45 @@ def test_full_size_invariants_4096_envs():
     vec2.agent_step("bestfit", n_steps=1500, want_obs=True)
     assert vec2.state[0].cpu().numpy()[: vec2._layout.off_scalars].tobytes() == \
         vec.state[7].cpu().numpy()[: vec._layout.off_scalars].tobytes()
+
+
+# ---- the reference's published rows, reproduced by the CUDA path (5 seeds x 100 000 eval steps, fused agents) ----------
+GPU_KATS = {
+    # name: (config base, arrival_rate, reward, agent, tiebreak, seeds, per-seed returns, csv row) — SURVEY §8c KAT-1..4;
+    # arrival_rate = round(pms / 0.55 / service_length, 4) (exp_performance.py:26, exp_performance_small.py:23)
+    "KAT1_firstfit_s10": ("10", 0.0182, "ut", "firstfit", "stable", [1, 2, 3, 4, 5],
+                          [702661.695, 690616.030, 695187.965, 695977.240, 700256.885],
+                          dict(ret=696939.963, drop=0.241, served=1258, cpu=0.697, var=0.051, mem=0.697, wait=0.539)),
+    "KAT2_firstfit_s100": ("100", 0.1818, "wr", "firstfit", "stable", [0, 1, 2, 3, 4],
+                           [-53615.794, -53208.140, -53318.037, -52963.827, -53735.479],
+                           dict(ret=-53368.255, drop=0.203, served=13394, cpu=0.737, var=0.052, mem=0.736, wait=0.534)),
+    "KAT3_bestfit_s10": ("10", 0.0182, "ut", "bestfit", "stable", [1, 2, 3, 4, 5],
+                         [699859.415, 694840.720, 698802.250, 697559.640, 703166.045],
+                         dict(ret=698845.614, drop=0.242, served=1260, cpu=0.699, var=0.053, mem=0.699, wait=0.537)),
+    "KAT4_bestfit_s100": ("100", 0.1818, "wr", "bestfit", "numpy_introsort", [0, 1, 2, 3, 4],
+                          [-52064.658, -51690.685, -51570.904, -51202.317, -51729.035],
+                          dict(ret=-51651.520, drop=0.182, served=13862, cpu=0.763, var=0.057, mem=0.762, wait=0.517)),
+}
+
+
+@pytest.mark.parametrize("kat", sorted(GPU_KATS))
+def test_published_rows_on_the_cuda_path(kat):
+    """data/exp_performance_small/summary.csv:3-4 and data/exp_performance/summary.csv:3-4 of the reference, every printed
+    digit, from VecVmEnv.evaluate (numpy-exact traces, fused agent kernel, on-device episode statistics)."""
+    from vmgym import VecVmEnv
+    base, lam, reward, agent, tie, seeds, per_seed, row = GPU_KATS[kat]
+    P, V = (10, 30) if base == "10" else (100, 300)
+    cfg = _cfg(pms=P, vms=V, service_length=1000, arrival_rate=lam, training_steps=10000, eval_steps=100000,
+               reward_function=reward, cap_target_util=True, sequence="uniform", beta=0.5, allow_null_action=True)
+    vec = VecVmEnv(cfg, len(seeds), seeds=seeds, tiebreak=tie)
+    s = vec.evaluate(agent, seeds=seeds)
+    assert np.all(s["steps"] == 100000)
+    for got, want in zip(s["total rewards"], per_seed):
+        assert round(float(got), 3) == pytest.approx(want, abs=2e-3)
+    assert "%.3f" % s["total rewards"].mean() == "%.3f" % row["ret"]
+    assert "%.3f" % s["drop rate"].mean() == "%.3f" % row["drop"]
+    assert "%d" % s["total served VMs"].mean() == "%d" % row["served"]
+    assert "%.3f" % s["cpu mean"].mean() == "%.3f" % row["cpu"]
+    assert "%.3f" % s["cpu var"].mean() == "%.3f" % row["var"]
+    assert "%.3f" % s["memory mean"].mean() == "%.3f" % row["mem"]
+    assert "%.3f" % s["waiting ratio"].mean() == "%.3f" % row["wait"]

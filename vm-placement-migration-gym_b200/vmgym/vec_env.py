@@ -215,6 +215,30 @@ class VecVmEnv:
                                                 int(n_steps), C.byref(out), self._stream()), "vmgym_agent_step")
         return self.obs, self.reward, self.terminated
 
+    def evaluate(self, agent: str, seeds=None, chunk: int = 1000, tiebreak: str | None = None):
+        """Base.test (src/agents/base.py:63-124) for a fused heuristic agent, entirely on the device: eval mode,
+        reset(seed), act/step until the episode terminates, with the running sums behind Record.get_summary
+        (src/record.py:110-134) and the columns of the published tables (exp_performance.py:104-147) accumulated in the
+        kernel.  Returns a dict of numpy arrays [N]."""
+        self.eval(True)
+        self.reset(seed=self.config.seed + np.arange(self.num_envs) if seeds is None else np.asarray(seeds, np.int64))
+        limit = int(self.config.eval_steps)
+        done = 0
+        while done < limit:
+            n = min(chunk, limit - done)
+            self.agent_step(agent, n_steps=n, want_obs=False, want_action=False, want_valid=False, want_stats=True,
+                            tiebreak=tiebreak)
+            done += n
+        c = self.counters()
+        st = self.stats.cpu().numpy()
+        steps = np.maximum(st[:, 7], 1.0)
+        return {"total rewards": c["episode_return"], "total served VMs": c["served_requests"], "total requests": c["total_requests"],
+                "total cpu requested": c["total_cpu_requested"], "total memory requested": c["total_memory_requested"],
+                "total suspend actions": c["suspend_actions"], "total place actions": c["place_actions"],
+                "dropped requests": c["dropped_requests"], "drop rate": st[:, 0] / steps, "waiting ratio": st[:, 1] / steps,
+                "cpu mean": st[:, 2] / steps, "cpu var": st[:, 3] / steps, "memory mean": st[:, 4] / steps,
+                "memory var": st[:, 5] / steps, "rejected actions": st[:, 6], "steps": st[:, 7]}
+
     def capture(self, fn, warmup: int = 2):
         """Capture `fn` (a callable issuing env calls with fixed arguments, e.g. one fused agent step) into a CUDA
         graph; returns the torch.cuda.CUDAGraph — `.replay()` re-issues the launches without host-side overhead."""
