@@ -205,6 +205,15 @@ int vmgym_policy_fused(const void* d_h_bf16, const void* d_wpad_bf16, const floa
                        const void* d_action_in, int64_t M, int64_t V, int64_t A, int64_t K, uint64_t seed, uint64_t counter,
                        uint8_t* d_action_out, float* d_logprob, float* d_entropy, void* stream);
 
+/* SumSegmentTree / MinSegmentTree of the prioritized replay buffer (src/segment_tree.py:8-142): d_*_tree are fp64
+ * arrays of 2*capacity nodes (root at 1, leaves at capacity..2*capacity-1; capacity a power of two, :30-32), either may
+ * be NULL.  Update = `tree[idx] = val` for a batch (:63-71, last write wins on duplicates); the root holds sum() / min(). */
+int vmgym_segtree_update(double* d_sum_tree, double* d_min_tree, int64_t capacity, const int64_t* d_idx, const double* d_val,
+                         int32_t n, void* stream);
+/* SumSegmentTree.retrieve (src/segment_tree.py:103-118) for a batch of upper bounds -> leaf indices. */
+int vmgym_segtree_retrieve(const double* d_sum_tree, int64_t capacity, const double* d_upper, int32_t n, int64_t* d_out,
+                           void* stream);
+
 /* Tuning knobs (process-wide): warps per CTA of the step kernels (0 = auto) and bulk-async record copies
  * (cp.async.bulk) on/off.  For experiments; defaults are chosen per config. */
 int vmgym_set_tuning(int warps_per_cta, int use_bulk_copy);

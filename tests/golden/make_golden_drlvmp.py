@@ -67,5 +67,26 @@ for k, v in net.state_dict().items():
     out["net." + k] = v.numpy()
 out["net_x"] = x.numpy()
 out["net_q"] = q.numpy()
+# ---- prioritized-replay segment trees (src/segment_tree.py) -------------------------------------------------------
+from src.segment_tree import MinSegmentTree, SumSegmentTree  # noqa: E402
+
+cap = 1024
+st, mt = SumSegmentTree(cap), MinSegmentTree(cap)
+rng = np.random.default_rng(11)
+b_idx, b_val, sums, mins, ubs, rets = [], [], [], [], [], []
+for b in range(12):
+    idx = rng.integers(0, 700, size=40)                 # duplicates inside a batch on purpose (last write wins)
+    val = rng.random(40) ** 0.6 + 1e-6
+    for i, v in zip(idx, val):
+        st[int(i)] = float(v)
+        mt[int(i)] = float(v)
+    total = st.sum()
+    ub = rng.random(30) * total
+    b_idx.append(idx); b_val.append(val); sums.append(total); mins.append(mt.min()); ubs.append(ub)
+    rets.append([st.retrieve(float(u)) for u in ub])
+out.update(st_cap=cap, st_idx=np.array(b_idx, np.int64), st_val=np.array(b_val), st_sum=np.array(sums), st_min=np.array(mins),
+           st_ub=np.array(ubs), st_ret=np.array(rets, np.int64))
+print("segment tree: 12 batches, final sum", sums[-1])
+
 np.savez_compressed(os.path.join(HERE, "drlvmp.npz"), **out)
 print("wrote drlvmp.npz", os.path.getsize(os.path.join(HERE, "drlvmp.npz")) // 1024, "KiB")

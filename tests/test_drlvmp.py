@@ -82,3 +82,19 @@ def test_act_loop_equals_sequential_restatement():
         assert np.array_equal(batched[i], o[0, :30].long().cpu().numpy()), i
     one = agent.act(obs[3].cpu().numpy())
     assert one.dtype == np.int64 and np.array_equal(one, batched[3])
+
+
+@pytest.mark.gpu
+def test_device_segment_trees_match_reference():
+    """SumSegmentTree / MinSegmentTree (src/segment_tree.py): batched stores, sum(), min(), retrieve() — bit-identical fp64."""
+    from vmgym.drlvmp import DeviceSegmentTrees
+    g = _load()
+    trees = DeviceSegmentTrees(int(g["st_cap"]))
+    for b in range(g["st_idx"].shape[0]):
+        trees.set(g["st_idx"][b], g["st_val"][b])
+        assert trees.sum().item() == g["st_sum"][b]
+        assert trees.min().item() == g["st_min"][b]
+        got = trees.retrieve(g["st_ub"][b]).cpu().numpy()
+        assert np.array_equal(got, g["st_ret"][b]), b
+    with pytest.raises(AssertionError):
+        DeviceSegmentTrees(1000)

@@ -382,3 +382,80 @@ extern "C" int vmgym_drlvmp_choice(const vmgym_config* cfg, const float* d_obs, 
     if (err != cudaSuccess) return pfail(VMGYM_ECUDA, cudaGetErrorString(err));
     return VMGYM_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Prioritized-replay segment trees (src/segment_tree.py:8-142, used by src/agents/drlvmp.py:157-241): array-backed
+// binary trees over `capacity` (power of two) leaves holding fp64 values, node i = op(node 2i, node 2i+1) with the
+// reference's association, so sums / minima / prefix-sum descents are bit-identical to the Python floats.
+// ---------------------------------------------------------------------------------------------------
+namespace vmgym {
+
+// __setitem__ for a batch (segment_tree.py:63-71): leaves first, then one tree level per barrier; threads that share
+// a parent write the same value.  Duplicated indices resolve to the LAST value of the batch, like sequential stores.
+__global__ void segtree_update_kernel(double* sum_tree, double* min_tree, long long capacity, const long long* idx,
+                                      const double* val, int n)
+{
+    const int t = threadIdx.x;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + t;
+        long long node = 0;
+        bool owner = false;
+        if (i < n) {
+            node = idx[i] + capacity;
+            owner = true;
+            for (int j = i + 1; j < n; j++) if (idx[j] == idx[i]) { owner = false; break; }   // a later write wins
+            if (owner) { if (sum_tree) sum_tree[node] = val[i]; if (min_tree) min_tree[node] = val[i]; }
+        }
+        __syncthreads();
+        for (node >>= 1; ; node >>= 1) {
+            if (i < n && node >= 1) {
+                if (sum_tree) sum_tree[node] = sum_tree[2 * node] + sum_tree[2 * node + 1];
+                if (min_tree) min_tree[node] = fmin(min_tree[2 * node], min_tree[2 * node + 1]);
+            }
+            __syncthreads();
+            if (__syncthreads_and(node <= 1)) break;
+        }
+    }
+}
+
+// SumSegmentTree.retrieve (segment_tree.py:103-118) for a batch of upper bounds
+__global__ void segtree_retrieve_kernel(const double* sum_tree, long long capacity, const double* upper, int n, long long* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double ub = upper[i];
+    long long node = 1;
+    while (node < capacity) {
+        const long long left = 2 * node;
+        const double l = sum_tree[left];
+        if (l > ub) node = left;
+        else { ub -= l; node = left + 1; }
+    }
+    out[i] = node - capacity;
+}
+
+}  // namespace vmgym
+
+extern "C" int vmgym_segtree_update(double* d_sum_tree, double* d_min_tree, int64_t capacity, const int64_t* d_idx,
+                                    const double* d_val, int32_t n, void* stream)
+{
+    if ((!d_sum_tree && !d_min_tree) || !d_idx || !d_val || n < 0 || capacity < 1 || (capacity & (capacity - 1)))
+        return pfail(VMGYM_EINVAL, "segment tree: capacity must be a positive power of two (segment_tree.py:30-32)");
+    if (n == 0) return VMGYM_OK;
+    segtree_update_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_sum_tree, d_min_tree, capacity, (const long long*)d_idx, d_val, n);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return pfail(VMGYM_ECUDA, cudaGetErrorString(err));
+    return VMGYM_OK;
+}
+
+extern "C" int vmgym_segtree_retrieve(const double* d_sum_tree, int64_t capacity, const double* d_upper, int32_t n,
+                                      int64_t* d_out, void* stream)
+{
+    if (!d_sum_tree || !d_upper || !d_out || n < 0 || capacity < 1 || (capacity & (capacity - 1)))
+        return pfail(VMGYM_EINVAL, "segment tree: bad operand");
+    if (n == 0) return VMGYM_OK;
+    segtree_retrieve_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_sum_tree, capacity, d_upper, n, (long long*)d_out);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return pfail(VMGYM_ECUDA, cudaGetErrorString(err));
+    return VMGYM_OK;
+}

@@ -163,3 +163,38 @@ class DRLVMPAgent:
             a = action.cpu().numpy()
             return a[0] if single else a
         return action[0] if single else action
+
+
+class DeviceSegmentTrees:
+    """Sum + Min segment trees of the prioritized replay buffer (src/segment_tree.py, drlvmp.py:157-241) on the device:
+    batched `tree[idx] = priority ** alpha` stores, `sum()`, `min()` and batched `retrieve(upperbound)` with the
+    reference's fp64 association (bit-identical to its Python floats)."""
+
+    def __init__(self, capacity: int, device="cuda"):
+        assert capacity > 0 and capacity & (capacity - 1) == 0, "capacity must be positive and a power of 2."   # :30-32
+        self.capacity = int(capacity)
+        self.device = torch.device(device)
+        self.sum_tree = torch.zeros(2 * capacity, dtype=torch.float64, device=self.device)                     # init 0.0
+        self.min_tree = torch.full((2 * capacity,), float("inf"), dtype=torch.float64, device=self.device)     # init inf
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set(self, idx, val):
+        idx = torch.as_tensor(idx, dtype=torch.int64, device=self.device).contiguous()
+        val = torch.as_tensor(val, dtype=torch.float64, device=self.device).contiguous()
+        nv.check(nv.lib().vmgym_segtree_update(self.sum_tree.data_ptr(), self.min_tree.data_ptr(), self.capacity, idx.data_ptr(),
+                                               val.data_ptr(), idx.numel(), self._stream()), "vmgym_segtree_update")
+
+    def sum(self):
+        return self.sum_tree[1]
+
+    def min(self):
+        return self.min_tree[1]
+
+    def retrieve(self, upperbound):
+        ub = torch.as_tensor(upperbound, dtype=torch.float64, device=self.device).contiguous()
+        out = torch.empty(ub.numel(), dtype=torch.int64, device=self.device)
+        nv.check(nv.lib().vmgym_segtree_retrieve(self.sum_tree.data_ptr(), self.capacity, ub.data_ptr(), ub.numel(),
+                                                 out.data_ptr(), self._stream()), "vmgym_segtree_retrieve")
+        return out
