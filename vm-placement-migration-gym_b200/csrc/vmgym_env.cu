@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "vmgym_env_kernels.cuh"
@@ -114,9 +115,23 @@ static int launch_step(StepParams& sp, cudaStream_t st)
     const int w = pick_warps(sp.n_envs, L.sm_stride, L.sm_tables);
     const size_t smem = (size_t)L.sm_tables + (size_t)w * L.sm_stride;
     if (smem > 227 * 1024) return fail(VMGYM_EUNSUPPORTED, "env record does not fit in shared memory (pms/vms too large)");
-    void (*kern)(const StepParams) = step_kernel<PT, 0, 0>;
-    if (sizeof(PT) == 1 && L.P == 100 && L.V == 300) kern = step_kernel<PT, 100, 300>;      // config/100.yml
-    else if (sizeof(PT) == 1 && L.P == 10 && L.V == 30) kern = step_kernel<PT, 10, 30>;     // config/10.yml
+    void (*kern)(const StepParams) = step_kernel<PT, 0, 0, -1>;
+    static const bool specialise = getenv("VMGYM_NO_SPECIALIZE") == nullptr;               // A/B switch for experiments
+    if (specialise && sizeof(PT) == 1 && L.P == 100 && L.V == 300) {                        // config/100.yml
+        kern = step_kernel<PT, 100, 300, -1>;
+        // the benchmark configurations of this shape: fused heuristic agents / external actions, reward wr, stable ties
+        if (sp.reward_fn == VMGYM_REWARD_WR && sp.tiebreak == VMGYM_TIE_STABLE) {
+            const int mode = sp.tr.mode;
+            if (sp.agent == VMGYM_AGENT_BESTFIT && mode == VMGYM_TRACE_PHILOX)
+                kern = step_kernel<PT, 100, 300, make_spec(VMGYM_AGENT_BESTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>;
+            else if (sp.agent == VMGYM_AGENT_FIRSTFIT && mode == VMGYM_TRACE_PHILOX)
+                kern = step_kernel<PT, 100, 300, make_spec(VMGYM_AGENT_FIRSTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>;
+            else if (sp.agent == VMGYM_AGENT_NONE && mode == VMGYM_TRACE_PHILOX)
+                kern = step_kernel<PT, 100, 300, make_spec(VMGYM_AGENT_NONE, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>;
+        }
+    } else if (specialise && sizeof(PT) == 1 && L.P == 10 && L.V == 30) {
+        kern = step_kernel<PT, 10, 30, -1>;                                                // config/10.yml
+    }
     // per (kernel, smem, warps) launch plan, computed once (also keeps these calls out of CUDA-graph capture)
     static thread_local size_t plan_smem = 0;
     static thread_local int plan_w = 0, plan_occ = 1;

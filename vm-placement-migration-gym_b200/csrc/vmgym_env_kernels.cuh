@@ -426,10 +426,12 @@ __device__ __noinline__ void stats_update(const Env<PT> e, const StepResult res,
 // common quiet step (nothing placed, nothing departs, nothing admitted) costs only the service countdown, one
 // arrival draw and the outputs.
 // ---------------------------------------------------------------------------------------------------
-template <typename PT>
+template <typename PT, int REWARD_CT, int MODE_CT>
 __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParams& p, long long env_id, uint8_t* valid_g,
                                                bool have_actions)
 {
+    const int reward_fn = REWARD_CT ? REWARD_CT : p.reward_fn;            // compile-time in the specialised kernels
+    const int trace_mode = MODE_CT >= 0 ? MODE_CT : p.tr.mode;
     const int P = e.P, V = e.V, lane = e.lane;
     vmgym_env_scalars* sc = e.sc();
     double* cpu = e.cpu();
@@ -590,7 +592,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
     const uint32_t arrival_pos = sc->arrival_pos, admission_pos = sc->admission_pos;
     const uint32_t k0 = (uint32_t)sc->seed, k1 = (uint32_t)(sc->seed >> 32);
     int exhausted = 0;
-    if (tr.mode == VMGYM_TRACE_PRESAMPLED) {
+    if (trace_mode == VMGYM_TRACE_PRESAMPLED) {
         if ((long long)arrival_pos < tr.arrivals_len) n_arr = tr.d_arrivals[env_id * tr.arrivals_len + arrival_pos];
         else exhausted = 1;
     } else {
@@ -598,7 +600,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
         n_arr = tr.arrival_kmin + cdf_search(e.arr_cdf, tr.arrival_cdf_len, ((uint64_t)r.x << 32) | r.y);
     }
     int quota = n_arr;                                         // admissions still allowed this step
-    if (tr.mode == VMGYM_TRACE_PRESAMPLED) {
+    if (trace_mode == VMGYM_TRACE_PRESAMPLED) {
         const long long left = tr.admissions_len - (long long)admission_pos;
         if ((long long)quota > left) { quota = (int)(left > 0 ? left : 0); exhausted = 1; }
     }
@@ -621,7 +623,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
             if (empty && rank < quota) {                       // lowest-index empty slots (:275-277)
                 const uint32_t j = admission_pos + (uint32_t)rank;
                 uint32_t cc, mc, svc;
-                if (tr.mode == VMGYM_TRACE_PRESAMPLED) {
+                if (trace_mode == VMGYM_TRACE_PRESAMPLED) {
                     const uint32_t w = tr.d_admissions[env_id * tr.admissions_len + j];
                     cc = w & 0xff; mc = (w >> 8) & 0xff; svc = w >> 16;
                 } else {
@@ -654,9 +656,9 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
     // ---- 7. reward (env.py:123-156) ----
     double reward = 0.0;
     if (arrived > 0) {
-        if (p.reward_fn == VMGYM_REWARD_WR) {
+        if (reward_fn == VMGYM_REWARD_WR) {
             reward = -((double)waiting / (double)arrived);
-        } else if (p.reward_fn == VMGYM_REWARD_UT) {
+        } else if (reward_fn == VMGYM_REWARD_UT) {
             reward = reward_ut(cpu, mem, P, p.beta);
         } else {
             reward = reward_kl_env(e, arrived, p.cap_target);
@@ -780,9 +782,16 @@ __host__ __device__ __forceinline__ int dtype_bytes(int dtype) { return dtype ==
 // ---------------------------------------------------------------------------------------------------
 // PC / VC: compile-time pms / vms of the instantiation (0 = take them from the layout at run time); the named
 // configs of the reference (config/10.yml, config/100.yml) get fully unrolled loops.
-template <typename PT, int PC, int VC>
+// SPEC >= 0 additionally fixes (agent, tiebreak, reward, trace mode) = spec_* fields at compile time (SPEC < 0: run time).
+constexpr int make_spec(int agent, int tiebreak, int reward, int mode) { return agent | (tiebreak << 4) | (reward << 8) | (mode << 12); }
+
+template <typename PT, int PC, int VC, int SPEC>
 __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ StepParams p)
 {
+    constexpr int REWARD_CT = SPEC >= 0 ? ((SPEC >> 8) & 0xf) : 0;
+    constexpr int MODE_CT = SPEC >= 0 ? ((SPEC >> 12) & 0xf) : -1;
+    const int agent_k = SPEC >= 0 ? (SPEC & 0xf) : p.agent;
+    const int tiebreak_k = SPEC >= 0 ? ((SPEC >> 4) & 0xf) : p.tiebreak;
     extern __shared__ __align__(128) unsigned char smem[];
     const DevLayout& L = p.L;
     const int cP = PC ? PC : L.P, cV = VC ? VC : L.V, cD = 3 * cV + 2 * cP;
@@ -808,7 +817,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
         }
     }
     fill_tables(sz64, sz32);
-    const bool philox = p.tr.mode == VMGYM_TRACE_PHILOX;
+    const bool philox = (MODE_CT >= 0 ? MODE_CT : p.tr.mode) == VMGYM_TRACE_PHILOX;
     const bool arr_in_smem = philox && p.tr.arrival_cdf_len <= ARR_CDF_SMEM;
     const bool svc_in_smem = philox && p.tr.service_cdf_len <= L.svc_cdf_smem;
     if (arr_in_smem)
@@ -852,7 +861,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
         // actions and the env rejects them again.  While it holds, act() and the apply loop are skipped.  The key
         // records which agent established it (0 = "no waiting VM fits anywhere", which holds for every agent).
         const bool need_vectors = p.out.d_action != nullptr || p.out.d_valid != nullptr;
-        const uint32_t my_key = (uint32_t)(p.agent | (p.tiebreak << 4));
+        const uint32_t my_key = (uint32_t)(agent_k | (tiebreak_k << 4));
         const uint32_t status0 = e.sc()->status;
         bool quiet = (status0 & STATUS_QUIET) != 0;
         uint32_t quiet_key = (status0 & STATUS_KEY_MASK) >> STATUS_KEY_SHIFT;
@@ -860,7 +869,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
         for (int s = 0; s < p.n_steps; s++) {
             bool have_actions, evaluated = false;
             int n_found = 0;
-            if (p.agent != VMGYM_AGENT_NONE) {
+            if (agent_k != VMGYM_AGENT_NONE) {
                 if (!(quiet && (quiet_key == 0 || quiet_key == my_key)) || need_vectors) {
                     // the agent sees the float32 observation of the current state (env.py:296)
                     const double* cpu = e.cpu();
@@ -869,7 +878,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
                     __syncwarp();
                     AgentView<PT> av;
                     av.place = e.place(); av.cc = e.cpuc(); av.mc = e.memc(); av.c32 = nullptr; av.m32 = nullptr; av.sz32 = sz32;
-                    n_found = agent_act(e, av, p.agent, p.tiebreak, true);
+                    n_found = agent_act(e, av, agent_k, tiebreak_k, true);
                     evaluated = true;
                     if (p.out.d_action) {        // the action vector: proposals, else the current placement (firstfit.py:29)
                         PT* ao = reinterpret_cast<PT*>(p.out.d_action) + env * (long long)cV;
@@ -895,14 +904,14 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
                 __syncwarp();
                 have_actions = any != 0;
             }
-            res = env_step(e, p, env, valid_g, have_actions);
+            res = env_step<PT, REWARD_CT, MODE_CT>(e, p, env, valid_g, have_actions);
             if (res.changed) {
                 quiet = false;
             } else if (evaluated) {
                 quiet = true;
                 quiet_key = n_found == 0 ? 0u : my_key;
                 quiet_rejected = res.rejected;
-            } else if (quiet && p.agent != VMGYM_AGENT_NONE) {
+            } else if (quiet && agent_k != VMGYM_AGENT_NONE) {
                 res.rejected = quiet_rejected;        // the skipped proposals would have been rejected again
             }
             if (p.out.d_stats) stats_update(e, res, st_acc);
