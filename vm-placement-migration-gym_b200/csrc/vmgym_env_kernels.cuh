@@ -45,7 +45,8 @@ struct Env {
     const DevLayout* L;
     const double* sz64;                // code -> k/100.0   (== np.around(u, 2), env.py:212-219)
     const float* sz32;                 // code -> (float)(k/100.0)   (env.py:296)
-    const uint64_t* arr_cdf;           // arrival / service inverse-CDF thresholds (shared-memory copies when small)
+    const uint64_t* arr_cdf;           // arrival / service inverse-CDF thresholds (global tables)
+    const uint32_t* arr_cdf32;         // top 32 bits of the arrival thresholds in shared memory (nullptr if the table is too long)
     const uint64_t* svc_cdf;
     const uint16_t* svc_bracket;       // 65-entry search brackets of the service table (shared memory) or nullptr
     int P, V, lane;
@@ -596,8 +597,18 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
         if ((long long)arrival_pos < tr.arrivals_len) n_arr = tr.d_arrivals[env_id * tr.arrivals_len + arrival_pos];
         else exhausted = 1;
     } else {
-        const Philox4 r = philox_dev(arrival_pos, 1u, k0, k1);
-        n_arr = tr.arrival_kmin + cdf_search(e.arr_cdf, tr.arrival_cdf_len, ((uint64_t)r.x << 32) | r.y);
+        // one Philox call serves four consecutive steps: step t takes 32-bit word (t & 3) of block (t >> 2) and inverts
+        // the Poisson CDF on the top 32 bits of the thresholds (resolution 2^-32)
+        const Philox4 r = philox_dev(arrival_pos >> 2, 1u, k0, k1);
+        const uint32_t sub = arrival_pos & 3u;
+        const uint32_t u32 = sub == 0 ? r.x : (sub == 1 ? r.y : (sub == 2 ? r.z : r.w));
+        int lo = 0, hi = tr.arrival_cdf_len;
+        if (e.arr_cdf32) {
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (e.arr_cdf32[mid] <= u32) lo = mid + 1; else hi = mid; }
+        } else {
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if ((uint32_t)(e.arr_cdf[mid] >> 32) <= u32) lo = mid + 1; else hi = mid; }
+        }
+        n_arr = tr.arrival_kmin + min(lo, tr.arrival_cdf_len - 1);
     }
     int quota = n_arr;                                         // admissions still allowed this step
     if (trace_mode == VMGYM_TRACE_PRESAMPLED) {
@@ -797,8 +808,8 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
     const int cP = PC ? PC : L.P, cV = VC ? VC : L.V, cD = 3 * cV + 2 * cP;
     double* sz64 = reinterpret_cast<double*>(smem);
     float* sz32 = reinterpret_cast<float*>(smem + SIZE_TABLE * 8);
-    uint64_t* arr_cdf_s = reinterpret_cast<uint64_t*>(smem + SIZE_TABLE * 12);
-    uint64_t* svc_cdf_s = arr_cdf_s + ARR_CDF_SMEM;
+    uint32_t* arr_cdf_s = reinterpret_cast<uint32_t*>(smem + SIZE_TABLE * 12);
+    uint64_t* svc_cdf_s = reinterpret_cast<uint64_t*>(smem + SIZE_TABLE * 12) + ARR_CDF_SMEM;
     uint16_t* svc_bracket_s = reinterpret_cast<uint16_t*>(svc_cdf_s + L.svc_cdf_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     unsigned char* base = smem + L.sm_tables + (size_t)warp * L.sm_stride;
@@ -821,7 +832,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
     const bool arr_in_smem = philox && p.tr.arrival_cdf_len <= ARR_CDF_SMEM;
     const bool svc_in_smem = philox && p.tr.service_cdf_len <= L.svc_cdf_smem;
     if (arr_in_smem)
-        for (int k = threadIdx.x; k < p.tr.arrival_cdf_len; k += blockDim.x) arr_cdf_s[k] = p.tr.d_arrival_cdf[k];
+        for (int k = threadIdx.x; k < p.tr.arrival_cdf_len; k += blockDim.x) arr_cdf_s[k] = (uint32_t)(p.tr.d_arrival_cdf[k] >> 32);
     if (svc_in_smem)
         for (int k = threadIdx.x; k < p.tr.service_cdf_len; k += blockDim.x) svc_cdf_s[k] = p.tr.d_service_cdf[k];
     const bool have_bracket = philox && p.tr.d_service_bracket != nullptr;
@@ -831,7 +842,8 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
 
     Env<PT> e;
     e.base = base; e.L = &p.L; e.sz64 = sz64; e.sz32 = sz32; e.P = cP; e.V = cV; e.lane = lane;
-    e.arr_cdf = arr_in_smem ? arr_cdf_s : p.tr.d_arrival_cdf;
+    e.arr_cdf = p.tr.d_arrival_cdf;
+    e.arr_cdf32 = arr_in_smem ? arr_cdf_s : nullptr;
     e.svc_cdf = svc_in_smem ? svc_cdf_s : p.tr.d_service_cdf;
     e.svc_bracket = have_bracket ? svc_bracket_s : nullptr;
     uint32_t phase = 0;
@@ -1100,7 +1112,7 @@ __global__ void act_kernel(DevLayout Lg, int agent, int tiebreak, const float* o
     }
     __syncwarp();
     Env<PT> e;
-    e.base = base; e.L = &L; e.sz64 = nullptr; e.sz32 = sz32; e.arr_cdf = nullptr; e.svc_cdf = nullptr; e.svc_bracket = nullptr;
+    e.base = base; e.L = &L; e.sz64 = nullptr; e.sz32 = sz32; e.arr_cdf = nullptr; e.arr_cdf32 = nullptr; e.svc_cdf = nullptr; e.svc_bracket = nullptr;
     e.P = P; e.V = V; e.lane = lane;
     AgentView<PT> av;
     av.place = place; av.cc = cc; av.mc = mc; av.c32 = row + V; av.m32 = row + 2 * V; av.sz32 = sz32;
