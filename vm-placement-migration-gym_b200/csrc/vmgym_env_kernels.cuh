@@ -366,32 +366,36 @@ __device__ __forceinline__ int agent_act_partial(const Env<PT>& e, const AgentVi
     const int n_units = (V + 3) >> 2;
     int n_found = 0;
     __syncwarp();
-    for (int u0 = 0; u0 < n_units; u0 += 32) {
-        const int u = u0 + lane;
+    // candidate bits of unit u (4 slots): waiting and (fits a pending PM, by its current local capacity codes, or pending slot)
+    auto unit_bits = [&](int u) -> unsigned {
+        const uint32_t pl4 = reinterpret_cast<const uint32_t*>(av.place)[u];
+        const uint32_t w4 = __vcmpeq4(pl4, P4);
         unsigned cb = 0;
-        if (u < n_units) {
-            const uint32_t pl4 = reinterpret_cast<const uint32_t*>(av.place)[u];
-            uint32_t w4 = __vcmpeq4(pl4, P4);
-            if (w4) {
-                const uint32_t cc4 = reinterpret_cast<const uint32_t*>(av.cc)[u] & 0x7f7f7f7fu, mc4 = reinterpret_cast<const uint32_t*>(av.mc)[u];
-                uint32_t fit = 0;
+        if (w4) {
+            const uint32_t cc4 = reinterpret_cast<const uint32_t*>(av.cc)[u] & 0x7f7f7f7fu, mc4 = reinterpret_cast<const uint32_t*>(av.mc)[u];
+            uint32_t fit = 0;
 #pragma unroll
-                for (int i = 0; i < 4; i++)
-                    if (i < pend.n_pm) fit |= __vcmpleu4(cc4, kc4[i]) & __vcmpleu4(mc4, km4[i]);
-                const uint32_t c4 = w4 & fit;
-                cb = (c4 & 1u) | ((c4 >> 7) & 2u) | ((c4 >> 14) & 4u) | ((c4 >> 21) & 8u);
+            for (int i = 0; i < 4; i++)
+                if (i < pend.n_pm) fit |= __vcmpleu4(cc4, kc4[i]) & __vcmpleu4(mc4, km4[i]);
+            const uint32_t c4 = w4 & fit;
+            cb = (c4 & 1u) | ((c4 >> 7) & 2u) | ((c4 >> 14) & 4u) | ((c4 >> 21) & 8u);
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int f = pend.vm[i];
-                    if (i < pend.n_vm && (f >> 2) == u && ((w4 >> (8 * (f & 3))) & 1u)) cb |= 1u << (f & 3);
-                }
+            for (int i = 0; i < 4; i++) {
+                const int f = pend.vm[i];
+                if (i < pend.n_vm && (f >> 2) == u && ((w4 >> (8 * (f & 3))) & 1u)) cb |= 1u << (f & 3);
             }
         }
+        return cb;
+    };
+    for (int u0 = 0; u0 < n_units; u0 += 32) {
+        const int u = u0 + lane;
+        unsigned cb = u < n_units ? unit_bits(u) : 0u;
         unsigned m = __ballot_sync(FULL, cb != 0);
         while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
             unsigned bits = __shfl_sync(FULL, cb, b);
+            bool shrunk = false;
             while (bits) {
                 const int j = __ffs(bits) - 1;
                 bits &= bits - 1;
@@ -401,7 +405,22 @@ __device__ __forceinline__ int agent_act_partial(const Env<PT>& e, const AgentVi
                     n_found++;
                     if (lane == 0) { e.act()[vv] = (uint16_t)found; e.prop()[vv >> 5] |= 1u << (vv & 31); }
                     __syncwarp();
+                    // a pending PM that just took a VM has less room: refresh its local capacity codes and re-test the
+                    // candidates not visited yet (slots of this unit after j, and the later units)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        if (i < pend.n_pm && pend.pm[i] == found) {
+                            kc4[i] = (uint32_t)max_code(e.sz32, e.cpu32()[found]) * 0x01010101u;
+                            km4[i] = (uint32_t)max_code(e.sz32, e.mem32()[found]) * 0x01010101u;
+                            shrunk = true;
+                        }
+                    }
+                    if (shrunk && bits) bits &= unit_bits(u0 + b);
                 }
+            }
+            if (shrunk && m) {
+                if (u < n_units && lane > b) cb = unit_bits(u);
+                m &= __ballot_sync(FULL, cb != 0);
             }
         }
     }
