@@ -342,6 +342,32 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
     return n_found;
 }
 
+// candidate bits of unit u (4 byte-placement slots): waiting and (fits a pending PM by its current local capacity codes,
+// or is a pending slot)
+template <typename PT>
+__device__ __forceinline__ unsigned pending_unit_bits(const AgentView<PT>& av, int u, uint32_t P4, const uint32_t (&kc4)[4],
+                                                      const uint32_t (&km4)[4], const Events& pend)
+{
+    const uint32_t pl4 = reinterpret_cast<const uint32_t*>(av.place)[u];
+    const uint32_t w4 = __vcmpeq4(pl4, P4);
+    unsigned cb = 0;
+    if (w4) {
+        const uint32_t cc4 = reinterpret_cast<const uint32_t*>(av.cc)[u] & 0x7f7f7f7fu, mc4 = reinterpret_cast<const uint32_t*>(av.mc)[u];
+        uint32_t fit = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (i < pend.n_pm) fit |= __vcmpleu4(cc4, kc4[i]) & __vcmpleu4(mc4, km4[i]);
+        const uint32_t c4 = w4 & fit;
+        cb = (c4 & 1u) | ((c4 >> 7) & 2u) | ((c4 >> 14) & 4u) | ((c4 >> 21) & 8u);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int f = pend.vm[i];
+            if (i < pend.n_vm && (f >> 2) == u && ((w4 >> (8 * (f & 3))) & 1u)) cb |= 1u << (f & 3);
+        }
+    }
+    return cb;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Incremental act(): valid when an earlier evaluation established "no waiting VM fits on any PM" and every change
 // since then is listed in `pend` — PMs whose capacity may have grown (departures, suspensions) or whose true float32
@@ -366,30 +392,9 @@ __device__ __forceinline__ int agent_act_partial(const Env<PT>& e, const AgentVi
     const int n_units = (V + 3) >> 2;
     int n_found = 0;
     __syncwarp();
-    // candidate bits of unit u (4 slots): waiting and (fits a pending PM, by its current local capacity codes, or pending slot)
-    auto unit_bits = [&](int u) -> unsigned {
-        const uint32_t pl4 = reinterpret_cast<const uint32_t*>(av.place)[u];
-        const uint32_t w4 = __vcmpeq4(pl4, P4);
-        unsigned cb = 0;
-        if (w4) {
-            const uint32_t cc4 = reinterpret_cast<const uint32_t*>(av.cc)[u] & 0x7f7f7f7fu, mc4 = reinterpret_cast<const uint32_t*>(av.mc)[u];
-            uint32_t fit = 0;
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (i < pend.n_pm) fit |= __vcmpleu4(cc4, kc4[i]) & __vcmpleu4(mc4, km4[i]);
-            const uint32_t c4 = w4 & fit;
-            cb = (c4 & 1u) | ((c4 >> 7) & 2u) | ((c4 >> 14) & 4u) | ((c4 >> 21) & 8u);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int f = pend.vm[i];
-                if (i < pend.n_vm && (f >> 2) == u && ((w4 >> (8 * (f & 3))) & 1u)) cb |= 1u << (f & 3);
-            }
-        }
-        return cb;
-    };
     for (int u0 = 0; u0 < n_units; u0 += 32) {
         const int u = u0 + lane;
-        unsigned cb = u < n_units ? unit_bits(u) : 0u;
+        unsigned cb = u < n_units ? pending_unit_bits(av, u, P4, kc4, km4, pend) : 0u;
         unsigned m = __ballot_sync(FULL, cb != 0);
         while (m) {
             const int b = __ffs(m) - 1;
@@ -415,11 +420,11 @@ __device__ __forceinline__ int agent_act_partial(const Env<PT>& e, const AgentVi
                             shrunk = true;
                         }
                     }
-                    if (shrunk && bits) bits &= unit_bits(u0 + b);
+                    if (shrunk && bits) bits &= pending_unit_bits(av, u0 + b, P4, kc4, km4, pend);
                 }
             }
             if (shrunk && m) {
-                if (u < n_units && lane > b) cb = unit_bits(u);
+                if (u < n_units && lane > b) cb = pending_unit_bits(av, u, P4, kc4, km4, pend);
                 m &= __ballot_sync(FULL, cb != 0);
             }
         }
@@ -609,7 +614,12 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                 }
                 __syncwarp();
                 okbits |= ok ? (1u << b) : 0u;
-                if (!ok) ev.add_vm(vv);                          // still waiting and possibly placeable: re-test it next step
+                if (!ok) {
+                    // still waiting and possibly placeable: re-test it next step; the agent reserved room for it on PM `a`
+                    // in its local view, which other VMs may have been refused because of -> that PM is pending too
+                    ev.add_vm(vv);
+                    if ((unsigned)a < (unsigned)P) ev.add_pm(a);
+                }
             }
             rejected += __popc(pm & ~okbits);
             if (valid_g && c0 + lane < V) valid_g[c0 + lane] = ((pm & ~okbits) >> lane) & 1u ? 0 : 1;
