@@ -83,7 +83,6 @@ typedef struct vmgym_env_scalars {
     uint32_t admission_pos;     /* entries consumed from the size/service streams (rng1,2,4; env.py:279-289) */
     uint32_t status;            /* bit 0: pre-sampled trace exhausted (the reference would raise at env.py:282);
                                    bit 1: QUIET — a fused agent's act()+apply would change nothing (skipped while set);
-                                   bit 2: PARTIAL — only pend_pm / pend_vm need re-evaluation;
                                    bits 8-15: agent/tiebreak that established QUIET (0 = any); bits 16-31: rejected
                                    proposals per quiet step */
     uint16_t n_waiting;         /* slots with vm_placement == P   (env.py:114) */
@@ -93,8 +92,6 @@ typedef struct vmgym_env_scalars {
     int64_t mem_code_sum;       /* 100 * total_memory_requested */
     double episode_return;      /* sum of rewards since reset */
     double last_reward;
-    uint16_t pend_pm[4];        /* status bit 2 (PARTIAL): PMs / slots the next fused act() has to re-examine, 0xFFFF = none */
-    uint16_t pend_vm[4];
 } vmgym_env_scalars;
 
 /* Source of the env's randomness.  PRESAMPLED: arrays drawn by the host exactly like the reference draws

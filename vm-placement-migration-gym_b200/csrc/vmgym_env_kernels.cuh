@@ -30,32 +30,10 @@ struct StepParams {
 
 constexpr uint32_t STATUS_EXHAUSTED = 1u;   // pre-sampled trace ran out (the reference would raise, env.py:282)
 constexpr uint32_t STATUS_QUIET = 2u;       // a fused agent's act()+apply would change nothing (see step_kernel)
-constexpr uint32_t STATUS_PARTIAL = 4u;     // only the pending PMs / slots of the scalar block need re-evaluation
 constexpr uint32_t STATUS_KEY_SHIFT = 8;    // bits 8..15: which (agent, tiebreak) established QUIET; 0 = any agent
 constexpr uint32_t STATUS_KEY_MASK = 0xff00u;
 
 __host__ __device__ static inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
-
-// What changed in a step, for the incremental re-evaluation of the fused agents (see step_kernel): PMs whose free
-// capacity may have grown or whose true float32 load may differ from the agent's local estimate, and slots holding VMs
-// the last evaluation has not tested (newly admitted, suspended, or proposed-but-rejected).
-struct Events {
-    int n_pm, n_vm, overflow;
-    int pm[4], vm[4];
-    __device__ __forceinline__ void clear() { n_pm = n_vm = overflow = 0; pm[0] = pm[1] = pm[2] = pm[3] = -1; vm[0] = vm[1] = vm[2] = vm[3] = -1; }
-    __device__ __forceinline__ void add_pm(int p)
-    {
-        if (p == pm[0] || p == pm[1] || p == pm[2] || p == pm[3]) return;
-        if (n_pm == 0) pm[0] = p; else if (n_pm == 1) pm[1] = p; else if (n_pm == 2) pm[2] = p; else if (n_pm == 3) pm[3] = p; else { overflow = 1; return; }
-        n_pm++;
-    }
-    __device__ __forceinline__ void add_vm(int v)
-    {
-        if (v == vm[0] || v == vm[1] || v == vm[2] || v == vm[3]) return;
-        if (n_vm == 0) vm[0] = v; else if (n_vm == 1) vm[1] = v; else if (n_vm == 2) vm[2] = v; else if (n_vm == 3) vm[3] = v; else { overflow = 1; return; }
-        n_vm++;
-    }
-};
 
 // ---------------------------------------------------------------------------------------------------
 // Per-warp env context: one base pointer into shared memory + the layout (kernel-parameter constant bank), so the
@@ -186,79 +164,6 @@ __device__ __forceinline__ unsigned cand_bits4(uint32_t pl4, uint32_t cc4, uint3
     return c;
 }
 
-// One waiting VM `vv` against all PMs of the agent's local float32 view: first-fit takes the lowest-index PM that fits
-// (firstfit.py:31-37), best-fit the fitting PM with the largest cpu+memory (bestfit.py:31-39; ties per `tiebreak`); the
-// local loads (and, when `use_cap`, the local capacity codes) are updated like the reference's local arrays.
-// Returns the PM or -1.  Warp-uniform.
-template <typename PT>
-__device__ __forceinline__ int scan_one(const Env<PT>& e, const AgentView<PT>& av, int agent, int tiebreak, int vv, bool use_cap)
-{
-    const int P = e.P, lane = e.lane;
-    float* cpu32 = e.cpu32();
-    float* mem32 = e.mem32();
-    uint16_t* cap = e.cap();
-    const float c32 = av.cpu_size(vv), m32 = av.mem_size(vv);
-    int found = -1;
-    if (agent == VMGYM_AGENT_FIRSTFIT) {
-        for (int i0 = 0; i0 < P; i0 += 32) {
-            const int p = i0 + lane;
-            const bool fit = p < P && (cpu32[p] + c32 <= 1.0f) && (mem32[p] + m32 <= 1.0f);
-            const unsigned bb = __ballot_sync(FULL, fit);
-            if (bb) { found = i0 + __ffs(bb) - 1; break; }
-        }
-        if (found >= 0 && lane == (found & 31)) {
-            const float nc = cpu32[found] + c32;        // firstfit.py:36 — only the local cpu is updated
-            cpu32[found] = nc;
-            if (use_cap) cap[found] = (uint16_t)((cap[found] & 0xff00u) | (unsigned)max_code(e.sz32, nc));
-        }
-    } else {
-        // best-fit: first fitting PM in descending (cpu+memory) order (bestfit.py:33-39)
-        unsigned bestk = 0;
-        int bestp = -1;
-        for (int p = lane; p < P; p += 32) {
-            const bool fit = (cpu32[p] + c32 <= 1.0f) && (mem32[p] + m32 <= 1.0f);
-            const unsigned kb = __float_as_uint(cpu32[p] + mem32[p]) + 1u;   // keys >= 0: bits order like values
-            if (fit && kb >= bestk) { bestk = kb; bestp = p; }
-        }
-        const unsigned gk = __reduce_max_sync(FULL, bestk);
-        if (gk != 0) {
-            found = (int)__reduce_max_sync(FULL, (unsigned)((bestk == gk ? bestp : -1) + 1)) - 1;  // ties -> highest index
-            if (tiebreak == VMGYM_TIE_NUMPY_INTROSORT) {
-                int cnt = 0;
-                for (int p = lane; p < P; p += 32) {
-                    const bool fit = (cpu32[p] + c32 <= 1.0f) && (mem32[p] + m32 <= 1.0f);
-                    cnt += (fit && __float_as_uint(cpu32[p] + mem32[p]) + 1u == gk);
-                }
-                cnt = __reduce_add_sync(FULL, cnt);
-                if (cnt >= 2) {
-                    // several fitting PMs share the maximal key: numpy's unstable default argsort decides
-                    float* keys = reinterpret_cast<float*>(e.tmp());
-                    uint16_t* perm = reinterpret_cast<uint16_t*>(e.tmp() + 4 * ((P + 1) & ~1));
-                    for (int p = lane; p < P; p += 32) keys[p] = cpu32[p] + mem32[p];
-                    __syncwarp();
-                    int pick = -1;
-                    if (lane == 0) {
-                        introsort_argsort(keys, perm, P);
-                        for (int i = P - 1; i >= 0; i--) {
-                            const int p = perm[i];
-                            if ((cpu32[p] + c32 <= 1.0f) && (mem32[p] + m32 <= 1.0f)) { pick = p; break; }
-                        }
-                    }
-                    found = __shfl_sync(FULL, pick, 0);
-                    __syncwarp();
-                }
-            }
-            if (lane == (found & 31)) {
-                const float nc = cpu32[found] + c32, nm = mem32[found] + m32;   // bestfit.py:37-38
-                cpu32[found] = nc;
-                mem32[found] = nm;
-                if (use_cap) cap[found] = (uint16_t)(max_code(e.sz32, nc) | (max_code(e.sz32, nm) << 8));
-            }
-        }
-    }
-    return found;
-}
-
 // ---------------------------------------------------------------------------------------------------
 // Heuristic agents on the float32 view (firstfit.py:21-38, bestfit.py:21-40).  Lanes own PMs p = lane + 32 i.
 // For every waiting VM, in slot order: first-fit takes the lowest-index PM that fits, best-fit the fitting PM with
@@ -306,7 +211,65 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
                 const int j = __ffs(bits) - 1;
                 bits &= bits - 1;
                 const int vv = SPL * (u0 + b) + j;
-                const int found = scan_one(e, av, agent, tiebreak, vv, true);
+                const float c32 = av.cpu_size(vv), m32 = av.mem_size(vv);
+                int found = -1;
+                if (agent == VMGYM_AGENT_FIRSTFIT) {
+                    for (int i0 = 0; i0 < P; i0 += 32) {
+                        const int p = i0 + lane;
+                        const bool fit = p < P && (cpu32[p] + c32 <= 1.0f) && (mem32[p] + m32 <= 1.0f);
+                        const unsigned bb = __ballot_sync(FULL, fit);
+                        if (bb) { found = i0 + __ffs(bb) - 1; break; }
+                    }
+                    if (found >= 0 && lane == (found & 31)) {
+                        const float nc = cpu32[found] + c32;        // firstfit.py:36 — only the local cpu is updated
+                        cpu32[found] = nc;
+                        cap[found] = (uint16_t)((cap[found] & 0xff00u) | (unsigned)max_code(e.sz32, nc));
+                    }
+                } else {
+                    // best-fit: first fitting PM in descending (cpu+memory) order (bestfit.py:33-39)
+                    unsigned bestk = 0;
+                    int bestp = -1;
+                    for (int p = lane; p < P; p += 32) {
+                        const bool fit = (cpu32[p] + c32 <= 1.0f) && (mem32[p] + m32 <= 1.0f);
+                        const unsigned kb = __float_as_uint(cpu32[p] + mem32[p]) + 1u;   // keys >= 0: bits order like values
+                        if (fit && kb >= bestk) { bestk = kb; bestp = p; }
+                    }
+                    const unsigned gk = __reduce_max_sync(FULL, bestk);
+                    if (gk != 0) {
+                        found = (int)__reduce_max_sync(FULL, (unsigned)((bestk == gk ? bestp : -1) + 1)) - 1;  // ties -> highest index
+                        if (tiebreak == VMGYM_TIE_NUMPY_INTROSORT) {
+                            int cnt = 0;
+                            for (int p = lane; p < P; p += 32) {
+                                const bool fit = (cpu32[p] + c32 <= 1.0f) && (mem32[p] + m32 <= 1.0f);
+                                cnt += (fit && __float_as_uint(cpu32[p] + mem32[p]) + 1u == gk);
+                            }
+                            cnt = __reduce_add_sync(FULL, cnt);
+                            if (cnt >= 2) {
+                                // several fitting PMs share the maximal key: numpy's unstable default argsort decides
+                                float* keys = reinterpret_cast<float*>(e.tmp());
+                                uint16_t* perm = reinterpret_cast<uint16_t*>(e.tmp() + 4 * ((P + 1) & ~1));
+                                for (int p = lane; p < P; p += 32) keys[p] = cpu32[p] + mem32[p];
+                                __syncwarp();
+                                int pick = -1;
+                                if (lane == 0) {
+                                    introsort_argsort(keys, perm, P);
+                                    for (int i = P - 1; i >= 0; i--) {
+                                        const int p = perm[i];
+                                        if ((cpu32[p] + c32 <= 1.0f) && (mem32[p] + m32 <= 1.0f)) { pick = p; break; }
+                                    }
+                                }
+                                found = __shfl_sync(FULL, pick, 0);
+                                __syncwarp();
+                            }
+                        }
+                        if (lane == (found & 31)) {
+                            const float nc = cpu32[found] + c32, nm = mem32[found] + m32;   // bestfit.py:37-38
+                            cpu32[found] = nc;
+                            mem32[found] = nm;
+                            cap[found] = (uint16_t)(max_code(e.sz32, nc) | (max_code(e.sz32, nm) << 8));
+                        }
+                    }
+                }
                 if (found >= 0) {
                     n_found++;
                     placed_any = true;
@@ -334,97 +297,6 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
                     else
                         cb = ((int)av.place[u] == P && (unsigned)av.mc[u] + 1u <= fitm[av.cc[u] & 0x7f]) ? 1u : 0u;
                 }
-                m &= __ballot_sync(FULL, cb != 0);
-            }
-        }
-    }
-    __syncwarp();
-    return n_found;
-}
-
-// candidate bits of unit u (4 byte-placement slots): waiting and (fits a pending PM by its current local capacity codes,
-// or is a pending slot)
-template <typename PT>
-__device__ __forceinline__ unsigned pending_unit_bits(const AgentView<PT>& av, int u, uint32_t P4, const uint32_t (&kc4)[4],
-                                                      const uint32_t (&km4)[4], const Events& pend)
-{
-    const uint32_t pl4 = reinterpret_cast<const uint32_t*>(av.place)[u];
-    const uint32_t w4 = __vcmpeq4(pl4, P4);
-    unsigned cb = 0;
-    if (w4) {
-        const uint32_t cc4 = reinterpret_cast<const uint32_t*>(av.cc)[u] & 0x7f7f7f7fu, mc4 = reinterpret_cast<const uint32_t*>(av.mc)[u];
-        uint32_t fit = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            if (i < pend.n_pm) fit |= __vcmpleu4(cc4, kc4[i]) & __vcmpleu4(mc4, km4[i]);
-        const uint32_t c4 = w4 & fit;
-        cb = (c4 & 1u) | ((c4 >> 7) & 2u) | ((c4 >> 14) & 4u) | ((c4 >> 21) & 8u);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int f = pend.vm[i];
-            if (i < pend.n_vm && (f >> 2) == u && ((w4 >> (8 * (f & 3))) & 1u)) cb |= 1u << (f & 3);
-        }
-    }
-    return cb;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Incremental act(): valid when an earlier evaluation established "no waiting VM fits on any PM" and every change
-// since then is listed in `pend` — PMs whose capacity may have grown (departures, suspensions) or whose true float32
-// load may differ from the agent's local sum (accepted placements), and slots with untested VMs (admitted, suspended,
-// rejected proposals).  PM loads elsewhere are unchanged and capacities only shrink inside act(), so the only waiting
-// VMs that can be placed are those that fit one of the pending PMs, plus the pending slots; each of them gets the
-// ordinary scan over all PMs, in slot order.  Byte-placement layouts only.
-// ---------------------------------------------------------------------------------------------------
-template <typename PT>
-__device__ __forceinline__ int agent_act_partial(const Env<PT>& e, const AgentView<PT>& av, int agent, int tiebreak, const Events& pend)
-{
-    const int P = e.P, V = e.V, lane = e.lane;
-    for (int c = lane; c < (V + 31) / 32; c += 32) e.prop()[c] = 0u;
-    uint32_t kc4[4], km4[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const unsigned w = (i < pend.n_pm) ? (unsigned)e.rcap()[pend.pm[i]] : 0u;
-        kc4[i] = (w & 0xffu) * 0x01010101u;
-        km4[i] = (w >> 8) * 0x01010101u;
-    }
-    const uint32_t P4 = (uint32_t)P * 0x01010101u;
-    const int n_units = (V + 3) >> 2;
-    int n_found = 0;
-    __syncwarp();
-    for (int u0 = 0; u0 < n_units; u0 += 32) {
-        const int u = u0 + lane;
-        unsigned cb = u < n_units ? pending_unit_bits(av, u, P4, kc4, km4, pend) : 0u;
-        unsigned m = __ballot_sync(FULL, cb != 0);
-        while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            unsigned bits = __shfl_sync(FULL, cb, b);
-            bool shrunk = false;
-            while (bits) {
-                const int j = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int vv = 4 * (u0 + b) + j;
-                const int found = scan_one(e, av, agent, tiebreak, vv, false);
-                if (found >= 0) {
-                    n_found++;
-                    if (lane == 0) { e.act()[vv] = (uint16_t)found; e.prop()[vv >> 5] |= 1u << (vv & 31); }
-                    __syncwarp();
-                    // a pending PM that just took a VM has less room: refresh its local capacity codes and re-test the
-                    // candidates not visited yet (slots of this unit after j, and the later units)
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        if (i < pend.n_pm && pend.pm[i] == found) {
-                            kc4[i] = (uint32_t)max_code(e.sz32, e.cpu32()[found]) * 0x01010101u;
-                            km4[i] = (uint32_t)max_code(e.sz32, e.mem32()[found]) * 0x01010101u;
-                            shrunk = true;
-                        }
-                    }
-                    if (shrunk && bits) bits &= pending_unit_bits(av, u0 + b, P4, kc4, km4, pend);
-                }
-            }
-            if (shrunk && m) {
-                if (u < n_units && lane > b) cb = pending_unit_bits(av, u, P4, kc4, km4, pend);
                 m &= __ballot_sync(FULL, cb != 0);
             }
         }
@@ -557,7 +429,7 @@ __device__ __noinline__ void stats_update(const Env<PT> e, const StepResult res,
 // ---------------------------------------------------------------------------------------------------
 template <typename PT, int REWARD_CT, int MODE_CT>
 __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParams& p, long long env_id, uint8_t* valid_g,
-                                               bool have_actions, Events& ev)
+                                               bool have_actions)
 {
     const int reward_fn = REWARD_CT ? REWARD_CT : p.reward_fn;            // compile-time in the specialised kernels
     const int trace_mode = MODE_CT >= 0 ? MODE_CT : p.tr.mode;
@@ -590,7 +462,6 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                         if (nc <= 1.0 && nm <= 1.0) {
                             ok = true;
                             n_place++;
-                            ev.add_pm(a);                        // its true float32 load may differ from the agent's local sum
                             __syncwarp();
                             if (lane == 0) {                                                                   // :82-85
                                 cpu[a] = nc; mem[a] = nm; place[vv] = (PT)a; cpuc[vv] &= 0x7f;
@@ -602,7 +473,6 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                     if (a == P) {
                         ok = true;
                         n_susp++;
-                        ev.add_pm(cv); ev.add_vm(vv);
                         const double nc = cpu[cv] - e.sz64[cpuc[vv] & 0x7f];
                         const double nm = mem[cv] - e.sz64[memc[vv]];
                         __syncwarp();
@@ -614,12 +484,6 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                 }
                 __syncwarp();
                 okbits |= ok ? (1u << b) : 0u;
-                if (!ok) {
-                    // still waiting and possibly placeable: re-test it next step; the agent reserved room for it on PM `a`
-                    // in its local view, which other VMs may have been refused because of -> that PM is pending too
-                    ev.add_vm(vv);
-                    if ((unsigned)a < (unsigned)P) ev.add_pm(a);
-                }
             }
             rejected += __popc(pm & ~okbits);
             if (valid_g && c0 + lane < V) valid_g[c0 + lane] = ((pm & ~okbits) >> lane) & 1u ? 0 : 1;
@@ -666,9 +530,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                         if (served == 0) freed0 = vf; else if (served == 1) freed1 = vf; else if (served == 2) freed2 = vf;
                         else if (served == 3) freed3 = vf;
                         served++;
-                        ev.add_pm((int)place[vf]);               // capacity of that PM grows
                     }
-                    __syncwarp();
                     if (lane == 0) {
                         while (t4) {
                             const int j = __ffs(t4) - 1;
@@ -710,7 +572,6 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                 __syncwarp();
                 if (term) { place[v] = (PT)(P + 1); cpuc[v] = 0; memc[v] = 0; rem[v] = 0; }
                 need_full_refresh = true;
-                ev.overflow = 1;
             }
         }
     }
@@ -793,14 +654,6 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
             admitted += __popc(m);
         }
         admitted = min(admitted, quota);
-        if (admitted > 0) {
-            if (known) {
-                ev.add_vm(freed0);
-                if (admitted > 1) ev.add_vm(freed1);
-                if (admitted > 2) ev.add_vm(freed2);
-                if (admitted > 3) ev.add_vm(freed3);
-            } else ev.overflow = 1;
-        }
         csum = (long long)__reduce_add_sync(FULL, (unsigned)csum);
         msum = (long long)__reduce_add_sync(FULL, (unsigned)msum);
         __syncwarp();
@@ -1025,24 +878,11 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
         bool quiet = (status0 & STATUS_QUIET) != 0;
         uint32_t quiet_key = (status0 & STATUS_KEY_MASK) >> STATUS_KEY_SHIFT;
         int quiet_rejected = (int)(status0 >> 16);
-        // STATUS_PARTIAL: the last evaluation left "no waiting VM fits anywhere" true except for the pending PMs / slots
-        // stored in the scalar block; only those need re-evaluation (agent_act_partial).
-        bool partial = (status0 & STATUS_PARTIAL) != 0 && sizeof(PT) == 1;
-        Events pend;
-        pend.clear();
-        if (partial) {
-            for (int i = 0; i < 4; i++) {
-                const int pq = e.sc()->pend_pm[i], vq = e.sc()->pend_vm[i];
-                if (pq != 0xFFFF) pend.add_pm(pq);
-                if (vq != 0xFFFF) pend.add_vm(vq);
-            }
-        }
         for (int s = 0; s < p.n_steps; s++) {
             bool have_actions, evaluated = false;
             int n_found = 0;
             if (agent_k != VMGYM_AGENT_NONE) {
-                const bool skip = quiet && (quiet_key == 0 || quiet_key == my_key) && !need_vectors;
-                if (!skip) {
+                if (!(quiet && (quiet_key == 0 || quiet_key == my_key)) || need_vectors) {
                     // the agent sees the float32 observation of the current state (env.py:296)
                     const double* cpu = e.cpu();
                     const double* mem = e.mem();
@@ -1050,8 +890,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
                     __syncwarp();
                     AgentView<PT> av;
                     av.place = e.place(); av.cc = e.cpuc(); av.mc = e.memc(); av.c32 = nullptr; av.m32 = nullptr; av.sz32 = sz32;
-                    if (partial && !quiet && !need_vectors) n_found = agent_act_partial(e, av, agent_k, tiebreak_k, pend);
-                    else n_found = agent_act(e, av, agent_k, tiebreak_k, true);
+                    n_found = agent_act(e, av, agent_k, tiebreak_k, true);
                     evaluated = true;
                     if (p.out.d_action) {        // the action vector: proposals, else the current placement (firstfit.py:29)
                         PT* ao = reinterpret_cast<PT*>(p.out.d_action) + env * (long long)cV;
@@ -1077,28 +916,15 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
                 __syncwarp();
                 have_actions = any != 0;
             }
-            Events ev;
-            ev.clear();
-            res = env_step<PT, REWARD_CT, MODE_CT>(e, p, env, valid_g, have_actions, ev);
-            // ---- what the next act() has to look at ----
-            if (agent_k == VMGYM_AGENT_NONE) {
-                if (res.changed) { quiet = false; partial = false; }       // external actions: re-evaluate everything
-            } else if (!res.changed) {
-                if (evaluated) {
-                    quiet = true;                                         // nothing proposed, or every proposal rejected again
-                    quiet_key = n_found == 0 ? 0u : my_key;
-                    quiet_rejected = res.rejected;
-                    partial = false;
-                } else {
-                    res.rejected = quiet_rejected;                        // the skipped proposals would have been rejected again
-                }
-            } else {
-                // something changed: the invariant survives iff this step started from a complete picture (an evaluation,
-                // or a skipped step of the agent-independent quiet state) and every change fits the pending lists
-                const bool complete = evaluated || (quiet && quiet_key == 0);
+            res = env_step<PT, REWARD_CT, MODE_CT>(e, p, env, valid_g, have_actions);
+            if (res.changed) {
                 quiet = false;
-                partial = complete && !ev.overflow && sizeof(PT) == 1;
-                pend = ev;
+            } else if (evaluated) {
+                quiet = true;
+                quiet_key = n_found == 0 ? 0u : my_key;
+                quiet_rejected = res.rejected;
+            } else if (quiet && agent_k != VMGYM_AGENT_NONE) {
+                res.rejected = quiet_rejected;        // the skipped proposals would have been rejected again
             }
             if (p.out.d_stats) stats_update(e, res, st_acc);
             if (res.terminated) break;
@@ -1107,12 +933,8 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
         // ---- outputs ----
         if (p.out.d_obs) write_obs(e, p.out.d_obs + env * (long long)cD);
         if (lane == 0) {
-            e.sc()->status = (e.sc()->status & STATUS_EXHAUSTED) | (partial && !quiet ? STATUS_PARTIAL : 0u) |
+            e.sc()->status = (e.sc()->status & STATUS_EXHAUSTED) |
                              (quiet ? (STATUS_QUIET | (quiet_key << STATUS_KEY_SHIFT) | ((uint32_t)quiet_rejected << 16)) : 0u);
-            for (int i = 0; i < 4; i++) {
-                e.sc()->pend_pm[i] = (uint16_t)((partial && i < pend.n_pm) ? pend.pm[i] : 0xFFFF);
-                e.sc()->pend_vm[i] = (uint16_t)((partial && i < pend.n_vm) ? pend.vm[i] : 0xFFFF);
-            }
             if (p.out.d_reward) p.out.d_reward[env] = res.reward;
             if (p.out.d_terminated) p.out.d_terminated[env] = (uint8_t)res.terminated;
             if (p.out.d_stats) {
