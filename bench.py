@@ -32,6 +32,7 @@ METRIC = "env-steps/sec (100 PMs, best-fit act+step, whole job)"
 UNIT = "env-steps/s"
 WARM_STEPS = 3000          # reach saturation (~300/300 slots occupied) before timing, SURVEY §8d
 PERIOD = 1000              # service_length of config/100.yml: one departure wave per period
+NCU_TRAFFIC_PER_LAUNCH = 14.25e6   # bytes, ncu --set full capture of the 4096-env launch (profiles/r1_step_kernel_full.md)
 
 
 def load_env_cfg():
@@ -290,19 +291,23 @@ def gpu_arm(args):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64 PM accumulators / u8 slot arrays / f32 observation", "data": "synthetic (Philox arrivals, uniform sizes)",
+        "dtype": "f64", "data": "synthetic (Philox arrivals, uniform sizes)",
         "config": {"workload": "config/100.yml best-fit evaluation: 100 PMs, 300 VM slots, uniform sizes, "
                                f"{E} envs per GPU, reward wr, saturated after {WARM_STEPS} warm-up steps",
                    "envs_per_gpu": E, "l2": "flushed between timed steps (256 MiB fill outside the event pairs)",
                    "phase_sampling": f"timed steps spread over one service period ({spread} untimed fused steps between them)",
-                   "rng": "philox", "tiebreak": "stable", "obs_written": True},
+                   "rng": "philox", "tiebreak": "stable", "obs_written": True,
+                   "state_types": "f64 PM accumulators, u8 placements / size codes, u16 runtimes, f32 observation"},
         "gpu_launches": K,
         "e2e": {"value": world * E * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "path": "BestFitAgent.act(host obs) + VecVmEnv.step(host action) with pinned host buffers"},
         "rollout": {"value": world * E * chunk * n_chunks / (rollout_ms * 1e-3), "unit": UNIT,
                     "steps_per_launch": chunk, "note": "same fused kernel, env state resident in shared memory across steps"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "vmgym::step_kernel<u8> (fused best-fit + step)",
+                     "traffic": NCU_TRAFFIC_PER_LAUNCH if E == 4096 else None,
+                     "traffic_note": "profiles/r1_step_kernel_full.md: dram__bytes_read 14.23 MB + dram__bytes_write 0.02 MB per "
+                                     "launch; the 32 MB the kernel stores stay in the 126 MB L2 until the benchmark's flush",
+                     "kernel": "vmgym::step_kernel<u8,100,300> (fused best-fit + step)",
                      "bytes_per_env_step": B, "peak_source": peak_src},
         "clocks": clocks,
     }
@@ -357,7 +362,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
-    ap.add_argument("--cpu-steps", type=int, default=2000, help="timed CPU steps per env in the cpu_baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=6000, help="timed CPU steps per env in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the large-batch and PPO extras")
     args = ap.parse_args()
