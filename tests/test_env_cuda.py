@@ -93,12 +93,17 @@ SHAPES = {
                 reward_function="ut", beta=0.3, allow_null_action=False, sequence="highuniform", cap_target_util=False),
     "s1000": dict(pms=1000, vms=3000, arrival_rate=1.6, service_length=1000, training_steps=10000, eval_steps=100000,
                   reward_function="wr", allow_null_action=True, sequence="highuniform"),      # BASELINE config 5 shape
+    "p253": dict(pms=253, vms=61, arrival_rate=2.0, service_length=25, training_steps=10000, eval_steps=100000,
+                 reward_function="kl", allow_null_action=True),                                # largest byte-placement layout
+    "p254": dict(pms=254, vms=61, arrival_rate=2.0, service_length=25, training_steps=10000, eval_steps=100000,
+                 reward_function="ut", allow_null_action=True),                                # smallest u16-placement layout
     "wide": dict(pms=300, vms=700, arrival_rate=4.0, service_length=120, training_steps=10000, eval_steps=100000,
                  reward_function="kl", allow_null_action=True, sequence="lowuniform"),
 }
 
 
-@pytest.mark.parametrize("shape,n_envs,steps", [("s10", 37, 450), ("s100", 8, 300), ("odd", 16, 400), ("wide", 4, 250)])
+@pytest.mark.parametrize("shape,n_envs,steps", [("s10", 37, 450), ("s100", 8, 300), ("odd", 16, 400), ("wide", 4, 250),
+                                                ("p253", 3, 200), ("p254", 3, 200), ("s10", 1, 120)])
 @pytest.mark.parametrize("bulk", [1, 0])
 def test_batched_step_matches_oracle_random_actions(shape, n_envs, steps, bulk):
     """N envs with different seeds, adversarial random action streams (out-of-range values, suspend storms,
@@ -334,3 +339,26 @@ def test_published_rows_on_the_cuda_path(kat):
     assert "%.3f" % s["cpu var"].mean() == "%.3f" % row["var"]
     assert "%.3f" % s["memory mean"].mean() == "%.3f" % row["mem"]
     assert "%.3f" % s["waiting ratio"].mean() == "%.3f" % row["wait"]
+
+
+def test_empty_batch_and_bad_arguments():
+    """Zero envs is a no-op, not an error; API misuse returns a status instead of launching (no exception crosses the C ABI)."""
+    import ctypes as C
+    torch = _torch()
+    from vmgym import VecVmEnv
+    from vmgym import _native as nv
+    vec = VecVmEnv(_cfg(**SHAPES["s10"]), 0, rng="philox")
+    assert vec.obs.shape == (0, 110)
+    vec.agent_step("firstfit", n_steps=3)
+    obs, r, term, trunc, info = vec.step(torch.zeros((0, 30), dtype=torch.int64, device=vec.device))
+    assert obs.shape == (0, 110) and r.numel() == 0 and vec.get_invalid_action_mask().shape == (0, 30, 12)
+    vec1 = VecVmEnv(_cfg(**SHAPES["s10"]), 2, rng="philox")
+    with pytest.raises(ValueError):
+        vec1.step(torch.zeros((2, 29), dtype=torch.int64, device=vec1.device))
+    lib = nv.lib()
+    out = nv.Outputs()
+    rc = lib.vmgym_step(C.byref(vec1._ccfg()), vec1.state.data_ptr(), 2, C.byref(vec1._trace), None, nv.I64, C.byref(out), None)
+    assert rc == nv.EINVAL and b"action" in lib.vmgym_last_error()
+    rc = lib.vmgym_agent_step(C.byref(vec1._ccfg()), vec1.state.data_ptr(), 2, C.byref(vec1._trace), 9, 0, 1, C.byref(out), None)
+    assert rc == nv.EUNSUPPORTED
+    torch.cuda.synchronize()
