@@ -157,6 +157,7 @@ static int fill_params(StepParams* sp, const vmgym_config* cfg, void* d_state, i
 {
     int rc = make_layout(cfg, &sp->L, nullptr);
     if (rc) return rc;
+    if (n_envs == 0) return VMGYM_OK;     // callers test n_envs == 0 again before launching
     if (!d_state || n_envs < 0) return fail(VMGYM_EINVAL, "null state / negative n_envs");
     if (!trace) return fail(VMGYM_EINVAL, "null trace");
     if (trace->mode == VMGYM_TRACE_PRESAMPLED) {
@@ -201,8 +202,8 @@ int vmgym_reset(const vmgym_config* cfg, void* d_state, int64_t n_envs, const ui
     DevLayout L;
     int rc = make_layout(cfg, &L, nullptr);
     if (rc) return rc;
-    if (!d_state || n_envs < 0) return fail(VMGYM_EINVAL, "null state / negative n_envs");
     if (n_envs == 0) return VMGYM_OK;
+    if (!d_state || n_envs < 0) return fail(VMGYM_EINVAL, "null state / negative n_envs");
     const int threads = 256;
     const long long blocks = (n_envs * 32 + threads - 1) / threads;
     if (L.P <= 253)
@@ -218,8 +219,8 @@ int vmgym_step(const vmgym_config* cfg, void* d_state, int64_t n_envs, const vmg
     StepParams sp;
     int rc = fill_params(&sp, cfg, d_state, n_envs, trace, out);
     if (rc) return rc;
-    if (!d_action) return fail(VMGYM_EINVAL, "null action");
     if (n_envs == 0) return VMGYM_OK;
+    if (!d_action) return fail(VMGYM_EINVAL, "null action");
     sp.action = d_action;
     sp.action_dtype = action_dtype;
     cudaStream_t st = (cudaStream_t)stream;
@@ -252,6 +253,7 @@ int vmgym_agent_act(const vmgym_config* cfg, int agent, int tiebreak, const floa
     DevLayout L;
     int rc = make_layout(cfg, &L, nullptr);
     if (rc) return rc;
+    if (n_envs == 0) return VMGYM_OK;
     if (!d_obs || !d_action || n_envs < 0) return fail(VMGYM_EINVAL, "null obs/action");
     if (agent != VMGYM_AGENT_FIRSTFIT && agent != VMGYM_AGENT_BESTFIT) return fail(VMGYM_EUNSUPPORTED, "agent must be firstfit or bestfit");
     if (n_envs == 0) return VMGYM_OK;
@@ -283,6 +285,7 @@ int vmgym_observe(const vmgym_config* cfg, const void* d_state, int64_t n_envs, 
     DevLayout L;
     int rc = make_layout(cfg, &L, nullptr);
     if (rc) return rc;
+    if (n_envs == 0) return VMGYM_OK;
     if (!d_state || !d_obs || n_envs < 0) return fail(VMGYM_EINVAL, "null state/obs");
     if (n_envs == 0) return VMGYM_OK;
     const int threads = 256;
@@ -297,6 +300,7 @@ int vmgym_invalid_action_mask(const vmgym_config* cfg, const void* d_state, int6
     DevLayout L;
     int rc = make_layout(cfg, &L, nullptr);
     if (rc) return rc;
+    if (n_envs == 0) return VMGYM_OK;
     if (!d_state || !d_mask || n_envs < 0) return fail(VMGYM_EINVAL, "null state/mask");
     if (n_envs == 0) return VMGYM_OK;
     const int threads = 256;
