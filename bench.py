@@ -260,16 +260,28 @@ def gpu_arm(args):
         barrier()
         ppo = {"seconds": time.perf_counter() - t0, "env_steps": 2 * Np * Tp}
         del vp, agent_p
+        # PPO evaluation rollouts (BASELINE config 3 shape): mask + gating + fused tcgen05 actor head + env.step, E envs
+        agent_e = PPOAgent(vec, PPOConfig(hidden_size=512, masked=True, migration_ratio=0.002))
+        agent_e.rollout(3)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        agent_e.rollout(20)
+        e1.record()
+        barrier()
+        ppo["eval_ms_per_step"] = e0.elapsed_time(e1) / 20
+        del agent_e
 
     if world > 1:
-        t = torch.tensor([total_ms, rollout_ms, e2e_s, big["ms_per_step"] if big else 0.0, ppo["seconds"] if ppo else 0.0],
-                         dtype=torch.float64, device=dev)
+        t = torch.tensor([total_ms, rollout_ms, e2e_s, big["ms_per_step"] if big else 0.0, ppo["seconds"] if ppo else 0.0,
+                          ppo["eval_ms_per_step"] if ppo else 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, rollout_ms, e2e_s = t.tolist()[:3]
         if big:
             big["ms_per_step"] = t[3].item()
         if ppo:
             ppo["seconds"] = t[4].item()
+            ppo["eval_ms_per_step"] = t[5].item()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -321,6 +333,9 @@ def gpu_arm(args):
                             "config": "config/100.yml, 512 envs/GPU, rollout T=16, k_epochs=4, 4 minibatches, H=512, "
                                       "rollout: fused tcgen05 actor head (bf16), update: cuBLAS TF32 layers + masked-heads/GAE kernels",
                             "seconds": ppo["seconds"]}
+        out["ppo_eval"] = {"value": world * E / (ppo["eval_ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": ppo["eval_ms_per_step"],
+                           "config": f"config/100.yml PPO evaluation rollouts, {E} envs/GPU, reference-shaped MLP (H=512, random init: the "
+                                     "100-PM weights are not shipped), masked, migration_ratio 0.002, fused tcgen05 actor head (bf16)"}
     if not args.no_cpu:
         out["cpu_baseline"] = cpu_arm(steps_per_env=args.cpu_steps)
     print(json.dumps(out), flush=True)

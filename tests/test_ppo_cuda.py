@@ -243,3 +243,21 @@ def test_ppo_learn_with_fused_rollout_s100():
     assert all(torch.isfinite(p).all() for p in agent.model.parameters())
     assert any(not torch.equal(a, b) for a, b in zip(agent.model.parameters(), before))
     assert vec.counters()["place_actions"].sum() > 0
+
+
+def test_ppo_eval_rollout_fused_and_unfused():
+    """PPOAgent.rollout (eval loop with act): both forward paths run, only valid actions reach the env, rewards accumulate."""
+    import torch
+    from vmgym import Config, VecVmEnv
+    from vmgym.ppo import PPOAgent, PPOConfig
+    kw = dict(pms=100, vms=300, arrival_rate=1.8182, service_length=1000, training_steps=10000, eval_steps=100000,
+              reward_function="wr", allow_null_action=True)
+    for fused in (True, False):
+        vec = VecVmEnv(Config(**kw), 32, rng="philox")
+        vec.eval(True)
+        agent = PPOAgent(vec, PPOConfig(hidden_size=128, migration_ratio=0.002))
+        ret = agent.rollout(12, fused=fused)
+        c = vec.counters()
+        assert ret.shape == (32,) and torch.isfinite(ret).all() and (ret <= 0).all()
+        assert c["timestep"].min() == 13 and c["place_actions"].sum() > 0
+        assert torch.allclose(ret, torch.from_numpy(c["episode_return"]).to(ret.device))

@@ -278,6 +278,25 @@ class PPOAgent:
             return a[0] if single else a
         return action[0] if single else action
 
+    @torch.no_grad()
+    def rollout(self, n_steps: int, fused: bool | None = None):
+        """Evaluation rollout (Base.test with PPOAgent.act, base.py:71-86 + ppo.py:151-161) on all envs in lock-step:
+        mask + migration-ratio gating + sampled action + env.step, `n_steps` times from the envs' current state.
+        `fused` (default: whenever the action space allows it) uses the tcgen05 fused actor head.  Returns the per-env
+        sum of rewards (float64, device)."""
+        vec = self.vec
+        use_fused = (self.mask_words == 4 and self.A <= 128) if fused is None else fused
+        obs = vec.observe()
+        ret = torch.zeros(vec.num_envs, dtype=torch.float64, device=self.device)
+        for _ in range(int(n_steps)):
+            if use_fused and not self.config.det:
+                action = self.fused_sample(obs, self.config.migration_ratio)[0]
+            else:
+                action = self.act(obs)
+            obs, reward, term, _, _ = vec.step(action, want_valid=False)
+            ret += reward
+        return ret
+
     # ---- training ------------------------------------------------------------------------------------------
     def learn(self, episodes: int | None = None, max_updates: int | None = None):
         """ppo.py:172-226 with N envs stepping in lock-step: every `batch_size` steps one `update` on the [T, N] rollout.
