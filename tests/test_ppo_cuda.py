@@ -98,6 +98,47 @@ def test_gating_semantics():
     assert abs(np.mean(frac) - 0.7) < 0.05
 
 
+@pytest.mark.parametrize("shape,n_envs", [("s10", 9), ("s100", 7), ("p37", 5), ("p200", 3)])
+def test_mask_bits_kernel_equals_env_mask_and_heads_gating(shape, n_envs):
+    """The thread-per-row mask kernel (capacity codes + byte compares) == env.py:45-53 mask, and with gating == the
+    warp-per-row heads kernel on the same Philox call counter."""
+    import torch
+    from vmgym import Config, VecVmEnv
+    from vmgym.ppo import PPOAgent, PPOConfig
+    if shape in ("s10", "s100"):
+        vec, kw = _mk(shape, n_envs)
+    else:
+        pms, vms = (37, 70) if shape == "p37" else (200, 90)
+        kw = dict(pms=pms, vms=vms, arrival_rate=0.9, service_length=60, training_steps=500, eval_steps=1000,
+                  reward_function="wr", allow_null_action=True)
+        vec = VecVmEnv(Config(**kw), n_envs, rng="philox")
+        vec.agent_step("bestfit", n_steps=130)
+        act = vec.vm_placement.clone()
+        run = act < pms
+        act[run & (torch.rand_like(act, dtype=torch.float32) < 0.3)] = pms
+        vec.step(act)
+    agent = PPOAgent(vec, PPOConfig(hidden_size=32))
+    P, V, A = vec.P, vec.V, vec.action_dim
+    W = (A + 31) // 32
+
+    def unpack(bits):
+        u = ((bits.view(n_envs, V, W, 1) >> torch.arange(32, device=vec.device, dtype=torch.int32)) & 1).bool()
+        return u.reshape(n_envs, V, W * 32)
+    mask = vec.get_invalid_action_mask(True)
+    b = unpack(agent._mask_bits(-1.0))
+    assert torch.equal(b[:, :, :A], mask) and not b[:, :, A:].any()
+    assert mask[:, :, :P].logical_not().any() and mask[:, :, :P].any()
+    logits = torch.zeros(n_envs, V * A, device=vec.device)
+    for ratio in (0.0, 0.3, 1.0):
+        calls = agent._calls
+        bm = agent._mask_bits(ratio)
+        agent._calls = calls                                   # same Philox call counter for the other kernel
+        _, _, _, bh = agent._heads(logits, ratio, want_mask=True)
+        assert torch.equal(bm, bh), ratio
+    agent.config.masked = False
+    assert not agent._mask_bits(-1.0).any()
+
+
 def test_sampling_distribution():
     import torch
     from vmgym import Config, VecVmEnv

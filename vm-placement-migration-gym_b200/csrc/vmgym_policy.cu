@@ -209,6 +209,108 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
     }
 }
 
+// Mask-only variant (the fused policy kernel consumes the packed bits): one CTA per env, one THREAD per VM row.
+// The fp64 capacity test  cpu[a] + c/100.0 <= 1.0  (env.py:35-42) is monotone in the size code c, so each PM's largest
+// admissible cpu / memory code is found once per env (binary search with the same fp64 expression) and every waiting
+// row then reduces to byte-SIMD compares of its two codes against 4 PMs per instruction.  Bit-identical to
+// row_invalid_bits; ~7x fewer instructions and no per-row global latency (placement / codes staged in SMEM).
+template <typename PT>
+__global__ void __launch_bounds__(128) mask_bits_kernel(const HeadParams p)
+{
+    extern __shared__ __align__(16) unsigned char ms[];
+    const DevLayout& L = p.L;
+    const int P = L.P, V = L.V, A = L.A;
+    const int W = (A + 31) / 32;
+    const int P4 = (P + 3) / 4;                                   // packed capacity words
+    double* s_tab = reinterpret_cast<double*>(ms);                // k / 100.0, k < 128
+    uint32_t* s_kc = reinterpret_cast<uint32_t*>(s_tab + 128);    // [64] max cpu code per PM, 4 PMs per word
+    uint32_t* s_km = s_kc + 64;
+    uint32_t* s_out = s_km + 64;                                  // [V * W]
+    const long long env = blockIdx.x;
+    const unsigned char* rec = p.state + env * (long long)L.rec_bytes;
+    for (int k = threadIdx.x; k < 128; k += blockDim.x) s_tab[k] = (double)k / 100.0;
+    for (int q = threadIdx.x; q < 128; q += blockDim.x) s_kc[q] = 0;          // zeroes s_kc and s_km (pad PMs admit nothing)
+    __syncthreads();
+    const double* g_cpu = reinterpret_cast<const double*>(rec);
+    const double* g_mem = reinterpret_cast<const double*>(rec + L.off_mem);
+    for (int q = threadIdx.x; q < 2 * P; q += blockDim.x) {
+        const bool is_mem = q >= P;
+        const int pm = is_mem ? q - P : q;
+        const double load = is_mem ? g_mem[pm] : g_cpu[pm];
+        int lo = -1, hi = 128;                                     // largest k with load + k/100 <= 1 (-1: not even k = 0)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (load + s_tab[mid] <= 1.0) lo = mid; else hi = mid;
+        }
+        // codes compare as unsigned bytes with c <= k; k = -1 cannot be expressed, but c = 0 never needs it: a load
+        // above 1.0 cannot occur (every placement passed this same test), so lo >= 0 always
+        reinterpret_cast<unsigned char*>(is_mem ? s_km : s_kc)[pm] = (unsigned char)max(lo, 0);
+    }
+    __syncthreads();
+    const PT* place = reinterpret_cast<const PT*>(rec + L.off_place);
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        const int cur = (int)place[v];
+        uint32_t bits[8];
+        #pragma unroll
+        for (int w = 0; w < 8; w++) bits[w] = 0xffffffffu;
+        if (p.masked) {
+            if (cur == P) {
+                const uint32_t c4 = (uint32_t)(rec[L.off_cpuc + v] & 0x7f) * 0x01010101u;
+                const uint32_t m4 = (uint32_t)rec[L.off_memc + v] * 0x01010101u;
+                #pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    uint32_t word = 0;
+                    #pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int g = w * 8 + j;
+                        if (g < P4) {
+                            const uint32_t ok = __vcmpleu4(c4, s_kc[g]) & __vcmpleu4(m4, s_km[g]);
+                            const uint32_t inv4 = ((~ok & 0x08040201u) * 0x01010101u) >> 24;   // one bit per byte lane
+                            word |= inv4 << (4 * j);
+                        } else word |= 0xfu << (4 * j);
+                    }
+                    bits[w] = word;
+                }
+            }
+            // columns >= P are invalid unless named below; a == cur is always valid; a placed VM may also go back to P
+            #pragma unroll
+            for (int w = 0; w < 8; w++) {
+                const int base = w * 32;
+                if (P - base < 32) bits[w] |= (P - base <= 0) ? 0xffffffffu : (0xffffffffu << (P - base));
+                if (A - base < 32) bits[w] &= (A - base <= 0) ? 0u : ~(0xffffffffu << (A - base));
+                if ((cur >> 5) == w && cur < A) bits[w] &= ~(1u << (cur & 31));
+                if (cur < P && (P >> 5) == w) bits[w] &= ~(1u << (P & 31));
+            }
+        } else {
+            #pragma unroll
+            for (int w = 0; w < 8; w++) bits[w] = 0u;
+        }
+        if (p.migration_ratio >= 0.f) {
+            // ppo.py:153-155: if count_nonzero(invalid_row) > 1 and not invalid_row[P] and rand() > migration_ratio
+            int cnt = 0;
+            #pragma unroll
+            for (int w = 0; w < 8; w++) cnt += (w < W) ? __popc(bits[w]) : 0;
+            uint32_t wait_inv = 0;
+            #pragma unroll
+            for (int w = 0; w < 8; w++) if ((P >> 5) == w) wait_inv = (bits[w] >> (P & 31)) & 1u;
+            if (cnt > 1 && !wait_inv) {
+                const Philox4 r = philox4x32_10((uint32_t)v, (uint32_t)env, 3u, (uint32_t)p.counter, (uint32_t)p.seed,
+                                                (uint32_t)(p.seed >> 32));
+                const float u = (float)(r.x >> 8) * (1.0f / 16777216.0f);
+                if (u > p.migration_ratio) {
+                    #pragma unroll
+                    for (int w = 0; w < 8; w++) if ((P >> 5) == w) bits[w] |= 1u << (P & 31);
+                }
+            }
+        }
+        #pragma unroll
+        for (int w = 0; w < 8; w++) if (w < W) s_out[v * W + w] = bits[w];
+    }
+    __syncthreads();
+    uint32_t* mo = p.mask_out + env * (long long)V * W;
+    for (int i = threadIdx.x; i < V * W; i += blockDim.x) mo[i] = s_out[i];
+}
+
 // GAE (ppo.py:237-242) per env along T:  A_t = delta_t + gamma*lambda*(1-done_t) * A_{t+1},
 // delta_t = r_t + gamma*(1-done_t)*V(s_{t+1}) - V(s_t);  returns = A + V.   Tensors are [T, N] (time-major).
 // One warp per env: the recurrence is a composition of affine maps x -> c*x + d, scanned in reverse with shuffles,
@@ -268,6 +370,21 @@ static int heads_launch(HeadParams& hp, const vmgym_config* cfg, bool backward, 
     const size_t smem = (size_t)16 * L.Pp + 2 * (threads / 32) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
     const bool small = L.P <= 253;
+    if (!backward && !hp.logits && hp.state) {
+        // mask-only call: thread-per-row kernel
+        const size_t msmem = 128 * sizeof(double) + 128 * sizeof(uint32_t) + (size_t)L.V * ((L.A + 31) / 32) * sizeof(uint32_t);
+        if (msmem > 200 * 1024) return pfail(VMGYM_EUNSUPPORTED, "vms too large for the mask kernel");
+        if (small) {
+            if (msmem > 48 * 1024) cudaFuncSetAttribute(mask_bits_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+            mask_bits_kernel<uint8_t><<<(unsigned)hp.n_envs, 128, msmem, st>>>(hp);
+        } else {
+            if (msmem > 48 * 1024) cudaFuncSetAttribute(mask_bits_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+            mask_bits_kernel<uint16_t><<<(unsigned)hp.n_envs, 128, msmem, st>>>(hp);
+        }
+        cudaError_t merr = cudaGetLastError();
+        if (merr != cudaSuccess) return pfail(VMGYM_ECUDA, cudaGetErrorString(merr));
+        return VMGYM_OK;
+    }
     if (backward) {
         if (small) heads_kernel<uint8_t, true><<<(unsigned)hp.n_envs, threads, smem, st>>>(hp);
         else heads_kernel<uint16_t, true><<<(unsigned)hp.n_envs, threads, smem, st>>>(hp);
