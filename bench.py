@@ -2,8 +2,9 @@
 """bench.py — env-steps/sec of the batched VM-placement hot path (BASELINE.json metric).
 
 Workload (N=1): BASELINE.json configs[1] — config/100.yml, best-fit evaluation, 100 PMs / 300 VM slots, uniform VM
-sizes, 4096 envs per GPU.  One "step" = agent.act + env.step for every env of the batch (one launch of the fused
-kernel, observation written to HBM every step as the gym API does).
+sizes, 4096 envs per GPU.  One "step" = agent.act + env.step for every env of a 4096-env batch (one launch of the fused
+kernel, observation written to HBM every step as the gym API does); launches rotate over --batches independent batches
+so that the records of a launch are never L2-resident (inputs larger than L2).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--envs E]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -146,10 +147,35 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up: saturate the envs, then W untimed steps of exactly the timed call ----
-    vec.agent_step("bestfit", n_steps=WARM_STEPS, want_obs=False, want_action=False, want_valid=False)
-    for _ in range(max(3, args.warmup)):
-        vec.agent_step("bestfit", 1, want_obs=True, want_action=False, want_valid=False)
+    # ---- batches: NB independent batches of E envs each; a timed "step" is one fused act+step launch over ONE batch,
+    # launches rotate over the batches.  Working set per launch = 14 MB records read + 14 MB written + 18 MB observations;
+    # NB launches touch NB x 46 MB >> 126 MB L2 before a batch comes round again, so every launch reads its records from
+    # HBM (inputs larger than L2; no flush kernel and no per-step event pair inside the timed region).
+    # Service times are Poisson(1000): departures come in waves one service period apart and a step costs more inside a
+    # wave.  Batch b is therefore warmed up to phase b * PERIOD / NB of the period, so the rotation samples all phases.
+    NB = args.batches
+    vecs = [vec]
+    for b in range(1, NB):
+        sb = cfg["seed"] + (b * world + rank) * E + np.arange(E, dtype=np.int64)      # distinct seeds per batch and rank
+        vecs.append(VecVmEnv(Config(**cfg), E, device=dev, rng="philox", seeds=sb))
+    for b, vb_ in enumerate(vecs):
+        vb_.agent_step("bestfit", n_steps=WARM_STEPS + (b * PERIOD) // NB, want_obs=False, want_action=False, want_valid=False)
+
+    def rotate(n, start=0):
+        for k in range(n):
+            vecs[(start + k) % NB].agent_step("bestfit", 1, want_obs=True, want_action=False, want_valid=False)
+
+    K, W = args.steps, max(3, args.warmup)
+    with vec._on_device():
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            rotate(NB)                                  # allocations / plan caches before capture
+        torch.cuda.current_stream(dev).wait_stream(side)
+        timed_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(timed_graph):
+            rotate(K, start=W)                          # exactly K launches of the fused step kernel
+    rotate(W)                                           # W untimed warm-up steps of exactly the timed call
     barrier()
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -157,26 +183,31 @@ def gpu_arm(args):
         sampler.start()
         time.sleep(0.3)
 
-    # ---- timed region A (value): K fused steps, state + outputs resident in HBM, L2 flushed between steps ----
-    K = args.steps
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    one_step = vec.capture(lambda: vec.agent_step("bestfit", 1, want_obs=True, want_action=False, want_valid=False))
-    # Service times are Poisson(1000): departures come in waves one service period apart, so the cost of a step
-    # depends on the phase.  The K timed steps are therefore spread evenly over one period (SPREAD untimed steps of the
-    # same fused kernel between consecutive timed steps) instead of sampling one phase.
-    spread = max(0, PERIOD // K - 1)
+    # ---- timed region A (value): K fused steps, records + outputs resident in HBM ----
+    t_a0, t_a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    for k in range(K):
-        if spread:
-            vec.agent_step("bestfit", spread, want_obs=False, want_action=False, want_valid=False)
+    t_a0.record()
+    timed_graph.replay()
+    t_a1.record()
+    barrier()
+    total_ms = float(t_a0.elapsed_time(t_a1))
+
+    # ---- timed region A' (single_launch_flushed): the round-1 protocol, one batch, L2 flushed before every timed launch,
+    # one event pair per launch (adds ~6 us of event/launch latency to every step); kept for comparison ----
+    Kf = 20
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(Kf)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(Kf)]
+    one_step = vec.capture(lambda: vec.agent_step("bestfit", 1, want_obs=True, want_action=False, want_valid=False))
+    spread = max(0, PERIOD // Kf - 1)
+    barrier()
+    for k in range(Kf):
+        vec.agent_step("bestfit", spread, want_obs=False, want_action=False, want_valid=False)
         flush.fill_(k & 0xff)                      # evict state/obs from L2 (outside the event pair)
         starts[k].record()
-        one_step.replay()                          # the fused step kernel, launched as a 1-node CUDA graph
+        one_step.replay()
         ends[k].record()
     barrier()
-    dev_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    total_ms = float(sum(dev_ms))
+    flushed_ms = float(np.mean([s_.elapsed_time(e_) for s_, e_ in zip(starts, ends)]))
 
     # ---- timed region B (rollout): same work, 100 steps per launch with the state resident in shared memory ----
     chunk, n_chunks = 100, 10                   # 1000 steps = one full service period
@@ -274,9 +305,10 @@ def gpu_arm(args):
 
     if world > 1:
         t = torch.tensor([total_ms, rollout_ms, e2e_s, big["ms_per_step"] if big else 0.0, ppo["seconds"] if ppo else 0.0,
-                          ppo["eval_ms_per_step"] if ppo else 0.0], dtype=torch.float64, device=dev)
+                          ppo["eval_ms_per_step"] if ppo else 0.0, flushed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, rollout_ms, e2e_s = t.tolist()[:3]
+        flushed_ms = t[6].item()
         if big:
             big["ms_per_step"] = t[3].item()
         if ppo:
@@ -295,30 +327,36 @@ def gpu_arm(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     B = algorithmic_bytes(P, V)
-    avg_launch_s = (sum(dev_ms) / K) * 1e-3
+    avg_launch_s = (total_ms / K) * 1e-3
     achieved = B * E / avg_launch_s / 1e9
     value = world * E * K / (total_ms * 1e-3)
     h2d = E * D * 4 + E * V * h_act.element_size()
     d2h = E * V * h_act.element_size() + E * D * 4 + E * 8 + E
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic (Philox arrivals, uniform sizes)",
         "config": {"workload": "config/100.yml best-fit evaluation: 100 PMs, 300 VM slots, uniform sizes, "
                                f"{E} envs per GPU, reward wr, saturated after {WARM_STEPS} warm-up steps",
-                   "envs_per_gpu": E, "l2": "flushed between timed steps (256 MiB fill outside the event pairs)",
-                   "phase_sampling": f"timed steps spread over one service period ({spread} untimed fused steps between them)",
+                   "envs_per_gpu": E, "batches": NB,
+                   "l2": f"inputs larger than L2: launches rotate over {NB} independent {E}-env batches "
+                         f"({NB} x {(2 * 3456 * E + 4 * D * E) / 1e6:.0f} MB touched between two visits of a batch, L2 = 126 MB)",
+                   "phase_sampling": f"batch b warmed up to phase b*{PERIOD}/{NB} of the service period (departure waves)",
+                   "timing": "one CUDA-event pair around a CUDA graph of exactly K step-kernel launches",
                    "rng": "philox", "tiebreak": "stable", "obs_written": True,
                    "state_types": "f64 PM accumulators, u8 placements / size codes, u16 runtimes, f32 observation"},
         "gpu_launches": K,
         "e2e": {"value": world * E * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "path": "BestFitAgent.act(host obs) + VecVmEnv.step(host action) with pinned host buffers"},
+        "single_launch_flushed": {"value": world * E / (flushed_ms * 1e-3), "unit": UNIT, "ms_per_step": flushed_ms, "steps": Kf,
+                                  "note": "one batch, 256 MiB L2 flush before and one event pair around every launch "
+                                          "(includes ~6 us event/launch latency per step), steps spread over one service period"},
         "rollout": {"value": world * E * chunk * n_chunks / (rollout_ms * 1e-3), "unit": UNIT,
                     "steps_per_launch": chunk, "note": "same fused kernel, env state resident in shared memory across steps"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_TRAFFIC_PER_LAUNCH if E == 4096 else None,
                      "traffic_note": "profiles/r1_step_kernel_full.md: dram__bytes_read 14.23 MB + dram__bytes_write 0.02 MB per "
-                                     "launch; the 32 MB the kernel stores stay in the 126 MB L2 until the benchmark's flush",
+                                     "launch; the 32 MB the kernel stores stay in the 126 MB L2 until later launches evict them",
                      "kernel": "vmgym::step_kernel<u8,100,300> (fused best-fit + step)",
                      "bytes_per_env_step": B, "peak_source": peak_src},
         "clocks": clocks,
@@ -376,7 +414,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (per batch)")
+    ap.add_argument("--batches", type=int, default=20, help="independent env batches the timed launches rotate over")
     ap.add_argument("--cpu-steps", type=int, default=6000, help="timed CPU steps per env in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the large-batch and PPO extras")

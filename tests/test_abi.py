@@ -63,3 +63,16 @@ def test_env_requires_cuda():
     from vmgym._native import VmgymError
     with pytest.raises(VmgymError):
         VecVmEnv(Config(), 4)
+
+
+def test_code_to_f64_table():
+    """vmgym_device.cuh code_to_f64: q0 = k*0.01; r = fma(-q0, 100, k); q = fma(r, 0.01, q0) equals the correctly rounded
+    k / 100.0 (== np.around(u, 2), env.py:212-219) for every size code; fma restated with exact rationals."""
+    from fractions import Fraction as F
+
+    def fma(a, b, c):
+        return float(F(a) * F(b) + F(c))
+    for k in range(256):
+        q0 = k * 0.01
+        q = fma(fma(-q0, 100.0, float(k)), 0.01, q0)
+        assert q == k / 100.0, k

@@ -14,8 +14,9 @@ cfg = yaml.safe_load(open(os.path.join(ROOT, "configs", "100.yml")))["environmen
 cfg["reward_function"] = "wr"
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 agent = sys.argv[2] if len(sys.argv) > 2 else "bestfit"
+warm = int(sys.argv[3]) if len(sys.argv) > 3 else 3000     # 3000: departure-wave phase, 3500: quiet phase
 vec = VecVmEnv(Config(**cfg), E, rng="philox")
-vec.agent_step(agent, n_steps=3000, want_obs=False, want_action=False, want_valid=False)
+vec.agent_step(agent, n_steps=warm, want_obs=False, want_action=False, want_valid=False)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for i in range(3):
     flush.fill_(i)

@@ -145,6 +145,18 @@ static __device__ __noinline__ double np_sum(const SumSrc f, int n)
     return ret;
 }
 
+// k / 100.0 (correctly rounded, == np.around(u, 2) for the size code k) without the fp64 division routine: one
+// Newton-style correction of k * 0.01 with exact fma residuals.  Checked against k / 100.0 for every k < 256
+// (tests/test_abi.py::test_code_to_f64_table restates it with exact rationals; the parity tests cover it on the GPU).
+__device__ __forceinline__ double code_to_f64(int k)
+{
+    const double kd = (double)k;
+    const double q0 = __dmul_rn(kd, 0.01);
+    const double r = __fma_rn(-q0, 100.0, kd);
+    return __fma_rn(r, 0.01, q0);
+}
+
+
 // ---------------------------------------------------------------------------------------------------
 // Philox4x32-10 (counter-based RNG; Salmon et al. SC'11).  Used in VMGYM_TRACE_PHILOX mode.
 // ---------------------------------------------------------------------------------------------------

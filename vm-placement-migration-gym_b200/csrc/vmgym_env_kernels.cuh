@@ -753,10 +753,10 @@ __device__ __forceinline__ void write_obs(const Env<PT>& e, float* __restrict__ 
     write_obs_generic(e, o);
 }
 
-static __device__ __noinline__ void fill_tables(double* sz64, float* sz32)
+__device__ __forceinline__ void fill_tables(double* sz64, float* sz32)
 {
     for (int k = threadIdx.x; k < SIZE_TABLE; k += blockDim.x) {
-        const double x = (double)k / 100.0;      // == np.around(u, 2) for the code k (env.py:212-219)
+        const double x = code_to_f64(k);         // == k / 100.0 == np.around(u, 2) for the code k (env.py:212-219)
         sz64[k] = x;
         sz32[k] = (float)x;                        // env.py:296 float32 cast
     }
@@ -827,17 +827,34 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
             bulk_g2s(base, p.state + env0 * (long long)L.rec_bytes, (uint32_t)L.rec_bytes, bar);
         }
     }
-    fill_tables(sz64, sz32);
     const bool philox = (MODE_CT >= 0 ? MODE_CT : p.tr.mode) == VMGYM_TRACE_PHILOX;
     const bool arr_in_smem = philox && p.tr.arrival_cdf_len <= ARR_CDF_SMEM;
     const bool svc_in_smem = philox && p.tr.service_cdf_len <= L.svc_cdf_smem;
-    if (arr_in_smem)
-        for (int k = threadIdx.x; k < p.tr.arrival_cdf_len; k += blockDim.x) arr_cdf_s[k] = (uint32_t)(p.tr.d_arrival_cdf[k] >> 32);
-    if (svc_in_smem)
-        for (int k = threadIdx.x; k < p.tr.service_cdf_len; k += blockDim.x) svc_cdf_s[k] = p.tr.d_service_cdf[k];
     const bool have_bracket = philox && p.tr.d_service_bracket != nullptr;
-    if (have_bracket)
-        for (int k = threadIdx.x; k < SVC_BRACKETS + 1; k += blockDim.x) svc_bracket_s[k] = p.tr.d_service_bracket[k];
+    {
+        // CTA-wide tables: every global load is issued before the first shared-memory store so that the round trips
+        // overlap each other (and the record's bulk copy) instead of queueing behind one another
+        const int t = threadIdx.x, nt = blockDim.x;
+        const uint64_t a0 = (arr_in_smem && t < p.tr.arrival_cdf_len) ? p.tr.d_arrival_cdf[t] : 0ull;
+        const uint16_t b0 = (have_bracket && t < SVC_BRACKETS + 1) ? p.tr.d_service_bracket[t] : (uint16_t)0;
+        uint64_t s0[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) s0[i] = (svc_in_smem && t + i * nt < p.tr.service_cdf_len) ? p.tr.d_service_cdf[t + i * nt] : 0ull;
+        fill_tables(sz64, sz32);
+        if (arr_in_smem) {
+            if (t < p.tr.arrival_cdf_len) arr_cdf_s[t] = (uint32_t)(a0 >> 32);
+            for (int k = t + nt; k < p.tr.arrival_cdf_len; k += nt) arr_cdf_s[k] = (uint32_t)(p.tr.d_arrival_cdf[k] >> 32);
+        }
+        if (have_bracket) {
+            if (t < SVC_BRACKETS + 1) svc_bracket_s[t] = b0;
+            for (int k = t + nt; k < SVC_BRACKETS + 1; k += nt) svc_bracket_s[k] = p.tr.d_service_bracket[k];
+        }
+        if (svc_in_smem) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) if (t + i * nt < p.tr.service_cdf_len) svc_cdf_s[t + i * nt] = s0[i];
+            for (int k = t + 4 * nt; k < p.tr.service_cdf_len; k += nt) svc_cdf_s[k] = p.tr.d_service_cdf[k];
+        }
+    }
     __syncthreads();
 
     Env<PT> e;
@@ -1076,7 +1093,7 @@ __global__ void act_kernel(DevLayout Lg, int agent, int tiebreak, const float* o
     __shared__ DevLayout L;                       // per-CTA layout whose scratch offsets point into the act layout
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     float* sz32 = reinterpret_cast<float*>(smem);
-    for (int k = threadIdx.x; k < SIZE_TABLE; k += blockDim.x) sz32[k] = (float)((double)k / 100.0);
+    for (int k = threadIdx.x; k < SIZE_TABLE; k += blockDim.x) sz32[k] = (float)code_to_f64(k);
     const ActLayout al = act_layout(Lg);
     if (threadIdx.x == 0) {
         L = Lg;

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(128) mask_bits_kernel(const HeadParams p)
     uint32_t* s_out = s_km + 64;                                  // [V * W]
     const long long env = blockIdx.x;
     const unsigned char* rec = p.state + env * (long long)L.rec_bytes;
-    for (int k = threadIdx.x; k < 128; k += blockDim.x) s_tab[k] = (double)k / 100.0;
+    for (int k = threadIdx.x; k < 128; k += blockDim.x) s_tab[k] = code_to_f64(k);
     for (int q = threadIdx.x; q < 128; q += blockDim.x) s_kc[q] = 0;          // zeroes s_kc and s_km (pad PMs admit nothing)
     __syncthreads();
     const double* g_cpu = reinterpret_cast<const double*>(rec);
