@@ -125,7 +125,6 @@ def gpu_arm(args):
     import torch
     import torch.distributed as dist
     from vmgym import Config, VecVmEnv
-    from vmgym.agents import BestFitAgent
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -220,39 +219,34 @@ def gpu_arm(args):
     barrier()
     rollout_ms = r0.elapsed_time(r1)
 
-    # ---- timed region C (e2e): the reference-facing calls with HOST buffers, copies inside the timed region ----
-    agent = BestFitAgent(vec)
+    # ---- timed region C (e2e): the reference-facing loop `action = agent.act(obs); obs, r, done = env.step(action)` with
+    # HOST (pinned) observation / action / reward buffers: every step moves obs + action over PCIe in both directions
+    # inside the timed region.  HostVecEnv splits the E envs into groups on separate streams so that one group's
+    # device->host copies overlap another group's host->device copies (PCIe is full duplex). ----
+    from vmgym.host_vec import HostVecEnv
     Ke = max(3, min(K, 20))
-    h_obs = torch.empty((E, D), dtype=torch.float32).pin_memory()
-    h_act = torch.empty((E, V), dtype=vec.place_dtype).pin_memory()
-    h_rew = torch.empty(E, dtype=torch.float64).pin_memory()
-    h_term = torch.empty(E, dtype=torch.uint8).pin_memory()
-    h_obs.copy_(vec.observe())
-    d_obs_in = torch.empty((E, D), dtype=torch.float32, device=dev)
-    d_act_in = torch.empty((E, V), dtype=vec.place_dtype, device=dev)
-
-    def e2e_step():
-        # action = agent.act(obs): host obs -> device, scan kernel, action -> host
-        d_obs_in.copy_(h_obs, non_blocking=True)
-        act = agent.act(d_obs_in)
-        h_act.copy_(act, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        # obs, reward, done = env.step(action): host action -> device, step kernel, results -> host
-        d_act_in.copy_(h_act, non_blocking=True)
-        obs, rew, term, _, _ = vec.step(d_act_in, want_valid=False)
-        h_obs.copy_(obs, non_blocking=True)
-        h_rew.copy_(rew, non_blocking=True)
-        h_term.copy_(vec.terminated_u8, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-
-    for _ in range(3):
-        e2e_step()
+    hv = HostVecEnv(Config(**cfg), E, groups=args.e2e_groups, device=dev, rng="philox", agent="bestfit",
+                    seeds=cfg["seed"] + 3 * 10**6 + rank * E + np.arange(E, dtype=np.int64))
+    hv.fast_forward(WARM_STEPS)
+    hv.run_pipelined(3)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(Ke):
-        e2e_step()
+    hv.run_pipelined(Ke)
     barrier()
     e2e_s = time.perf_counter() - t0
+    # the same loop without group overlap (one group): what the round-1 bench reported
+    hv1 = HostVecEnv(Config(**cfg), E, groups=1, device=dev, rng="philox", agent="bestfit",
+                     seeds=cfg["seed"] + 3 * 10**6 + rank * E + np.arange(E, dtype=np.int64))
+    hv1.fast_forward(WARM_STEPS)
+    hv1.run_pipelined(3)
+    barrier()
+    t0 = time.perf_counter()
+    hv1.run_pipelined(Ke)
+    barrier()
+    e2e1_s = time.perf_counter() - t0
+    h2d, d2h = hv.h2d_bytes_per_step, hv.d2h_bytes_per_step
+    hv.close(); hv1.close()
+    del hv, hv1
     clocks = sampler.finish() if sampler else None
 
     # ---- extra A: the same kernel with 8x the envs (several resident waves per SM -> load/compute/store overlap) ----
@@ -305,10 +299,11 @@ def gpu_arm(args):
 
     if world > 1:
         t = torch.tensor([total_ms, rollout_ms, e2e_s, big["ms_per_step"] if big else 0.0, ppo["seconds"] if ppo else 0.0,
-                          ppo["eval_ms_per_step"] if ppo else 0.0, flushed_ms], dtype=torch.float64, device=dev)
+                          ppo["eval_ms_per_step"] if ppo else 0.0, flushed_ms, e2e1_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, rollout_ms, e2e_s = t.tolist()[:3]
         flushed_ms = t[6].item()
+        e2e1_s = t[7].item()
         if big:
             big["ms_per_step"] = t[3].item()
         if ppo:
@@ -330,8 +325,6 @@ def gpu_arm(args):
     avg_launch_s = (total_ms / K) * 1e-3
     achieved = B * E / avg_launch_s / 1e9
     value = world * E * K / (total_ms * 1e-3)
-    h2d = E * D * 4 + E * V * h_act.element_size()
-    d2h = E * V * h_act.element_size() + E * D * 4 + E * 8 + E
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -347,7 +340,9 @@ def gpu_arm(args):
                    "state_types": "f64 PM accumulators, u8 placements / size codes, u16 runtimes, f32 observation"},
         "gpu_launches": K,
         "e2e": {"value": world * E * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": Ke, "path": "BestFitAgent.act(host obs) + VecVmEnv.step(host action) with pinned host buffers"},
+                "steps": Ke, "groups": args.e2e_groups, "single_group_value": world * E * Ke / e2e1_s,
+                "path": "HostVecEnv: BestFitAgent.act(host obs) -> host action -> VecVmEnv.step(host action) -> host obs/reward/done, "
+                        "pinned host buffers, envs split into groups whose PCIe transfers overlap"},
         "single_launch_flushed": {"value": world * E / (flushed_ms * 1e-3), "unit": UNIT, "ms_per_step": flushed_ms, "steps": Kf,
                                   "note": "one batch, 256 MiB L2 flush before and one event pair around every launch "
                                           "(includes ~6 us event/launch latency per step), steps spread over one service period"},
@@ -415,6 +410,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (per batch)")
+    ap.add_argument("--e2e-groups", type=int, default=8, help="env groups (streams) of the host-buffer e2e loop")
     ap.add_argument("--batches", type=int, default=20, help="independent env batches the timed launches rotate over")
     ap.add_argument("--cpu-steps", type=int, default=6000, help="timed CPU steps per env in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")

@@ -37,7 +37,9 @@ class HeuristicAgent:
     def eval(self, model=True):
         pass
 
-    def act(self, observation):
+    def act(self, observation, out=None):
+        """`out`: optional [n, V] tensor the kernel writes the actions into — a device tensor, or a PINNED host tensor
+        (device-mapped under UVA: the kernel stores over PCIe directly, no copy-engine transfer)."""
         vec = self.vec
         single = False
         if isinstance(observation, np.ndarray):
@@ -50,7 +52,11 @@ class HeuristicAgent:
         n = obs.shape[0]
         host_out = isinstance(observation, np.ndarray)
         dtype = torch.int64 if host_out else vec.place_dtype
-        action = torch.empty((n, vec.V), dtype=dtype, device=vec.device)
+        if out is not None:
+            if out.shape != (n, vec.V) or not out.is_contiguous() or not (out.is_cuda or out.is_pinned()):
+                raise ValueError("out must be a contiguous [n, V] device or pinned-host tensor")
+            dtype, host_out = out.dtype, False
+        action = out if out is not None else torch.empty((n, vec.V), dtype=dtype, device=vec.device)
         code = {torch.uint8: nv.U8, torch.int16: nv.I16, torch.int64: nv.I64}[dtype]
         with torch.cuda.device(vec.device):
             nv.check(nv.lib().vmgym_agent_act(C.byref(vec._ccfg()), self.kind, nv.TIE_IDS[self.tiebreak], obs.data_ptr(), n,

@@ -1,0 +1,232 @@
+"""Host-buffer front end of the batched env: the gym loop of the reference (`action = agent.act(obs)`;
+`obs, reward, done, _, info = env.step(action)`, src/agents/base.py:71-86) for N envs whose observations and actions
+live in HOST memory, as they do for a caller that is not on the GPU.
+
+Every call moves its operands over PCIe (observations 4(3V+2P) B and actions V B per env, each way), which is what
+bounds this path.  PCIe is full duplex, so the N envs are split into G groups with one CUDA stream each and a
+split-phase API in the style of gym's AsyncVectorEnv (`*_async(g)` enqueues, `*_wait(g)` blocks on that group only):
+while one group's observations travel device->host, another group's travel host->device.  Each phase of a group
+(copy in -> kernel -> copy out) is one CUDA graph, so issuing it costs one launch on the host.
+
+    hv = HostVecEnv(Config(**cfg), 4096, groups=8, agent="bestfit")
+    obs = hv.reset()                                   # pinned float32 [N, 3V+2P]
+    for _ in range(steps):                             # plain loop
+        action = hv.act()                              # pinned uint8/int16 [N, V]
+        obs, reward, terminated = hv.step()
+    hv.run_pipelined(steps)                            # same result, groups overlapped
+
+The envs, the agent scan and the step are the same kernels as VecVmEnv's (vmgym_agent_act, vmgym_step); this file is
+host-side orchestration only.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .agents import BestFitAgent, FirstFitAgent
+from .config import Config
+from .vec_env import VecVmEnv
+
+
+class _Group:
+    __slots__ = ("lo", "hi", "vec", "agent", "stream", "d_obs_in", "d_act_in", "g_act", "g_step", "ev_act", "ev_step")
+
+
+class HostVecEnv:
+    def __init__(self, config: Config, num_envs: int, groups: int = 8, device="cuda", rng: str = "philox", seeds=None,
+                 agent: str | None = "bestfit", tiebreak: str | None = None, use_graphs: bool = True, zero_copy: bool = True,
+                 **vec_kwargs):
+        if num_envs < 1 or groups < 1:
+            raise ValueError("num_envs and groups must be positive")
+        groups = min(groups, num_envs)
+        self.config, self.num_envs, self.device = config, int(num_envs), torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        base = np.asarray(seeds, dtype=np.int64) if seeds is not None else config.seed + np.arange(num_envs, dtype=np.int64)
+        if base.shape != (num_envs,):
+            raise ValueError("seeds must have shape (num_envs,)")
+        bounds = np.linspace(0, num_envs, groups + 1).astype(np.int64)
+        self.groups: list[_Group] = []
+        for gi in range(groups):
+            g = _Group()
+            g.lo, g.hi = int(bounds[gi]), int(bounds[gi + 1])
+            g.vec = VecVmEnv(config, g.hi - g.lo, device=self.device, rng=rng, seeds=base[g.lo:g.hi], **vec_kwargs)
+            g.agent = None
+            if agent is not None:
+                g.agent = {"bestfit": BestFitAgent, "firstfit": FirstFitAgent}[agent](g.vec, tiebreak=tiebreak)
+            g.stream = torch.cuda.Stream(device=self.device)
+            g.g_act = g.g_step = None
+            g.ev_act, g.ev_step = torch.cuda.Event(), torch.cuda.Event()
+            self.groups.append(g)
+        v0 = self.groups[0].vec
+        self.P, self.V, self.obs_dim, self.place_dtype = v0.P, v0.V, v0.obs_dim, v0.place_dtype
+        N = self.num_envs
+        # pinned host buffers of the whole batch; groups own contiguous row ranges
+        self.obs = torch.empty((N, self.obs_dim), dtype=torch.float32).pin_memory()
+        self.action = torch.empty((N, self.V), dtype=self.place_dtype).pin_memory()
+        self.reward = torch.empty(N, dtype=torch.float64).pin_memory()
+        self.terminated = torch.empty(N, dtype=torch.uint8).pin_memory()
+        for g in self.groups:
+            n = g.hi - g.lo
+            g.d_obs_in = torch.empty((n, self.obs_dim), dtype=torch.float32, device=self.device)
+            g.d_act_in = torch.empty((n, self.V), dtype=self.place_dtype, device=self.device)
+        self.use_graphs, self.zero_copy = use_graphs, zero_copy
+        self.h2d_bytes_per_step = N * self.obs_dim * 4 + N * self.V * self.action.element_size()
+        self.d2h_bytes_per_step = N * self.V * self.action.element_size() + N * self.obs_dim * 4 + N * 8 + N
+        torch.cuda.synchronize(self.device)          # construction-time resets ran on the caller's stream
+
+    # ---- per-group phases (stream-ordered; captured into one graph each) ------------------------------------
+    # With zero_copy (default) the SMALL operands — actions, rewards, done flags — never touch the copy engines: the
+    # kernels read / write the pinned host buffers directly over PCIe.  A copy engine serves its direction in FIFO
+    # order across streams, so a 0.3 MB action copy queued behind another group's 4.7 MB observation copy would stall
+    # its whole chain (measured: the groups' chains then run back to back instead of overlapping).
+    def _act_chain(self, g: _Group):
+        g.d_obs_in.copy_(self.obs[g.lo:g.hi], non_blocking=True)          # host obs -> device (copy engine)
+        if self.zero_copy:
+            g.agent.act(g.d_obs_in, out=self.action[g.lo:g.hi])            # vmgym_agent_act stores actions to host memory
+        else:
+            self.action[g.lo:g.hi].copy_(g.agent.act(g.d_obs_in), non_blocking=True)
+
+    def _step_chain(self, g: _Group):
+        if self.zero_copy:
+            obs, _, _, _, _ = g.vec.step(self.action[g.lo:g.hi], want_valid=False,          # vmgym_step loads actions from,
+                                         host_outputs=(self.reward[g.lo:g.hi], self.terminated[g.lo:g.hi]))   # stores r/done to host
+            self.obs[g.lo:g.hi].copy_(obs, non_blocking=True)             # obs -> host (copy engine)
+        else:
+            g.d_act_in.copy_(self.action[g.lo:g.hi], non_blocking=True)
+            obs, rew, _, _, _ = g.vec.step(g.d_act_in, want_valid=False)
+            self.obs[g.lo:g.hi].copy_(obs, non_blocking=True)
+            self.reward[g.lo:g.hi].copy_(rew, non_blocking=True)
+            self.terminated[g.lo:g.hi].copy_(g.vec.terminated_u8, non_blocking=True)
+
+    def _graph(self, g: _Group, chain):
+        with torch.cuda.device(self.device):
+            with torch.cuda.stream(g.stream):
+                chain(g)                                                   # allocations / plan caches before capture
+            g.stream.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=g.stream):
+                chain(g)
+        return graph
+
+    def _run(self, g: _Group, which: str):
+        chain = self._act_chain if which == "act" else self._step_chain
+        with torch.cuda.device(self.device), torch.cuda.stream(g.stream):
+            if self.use_graphs:
+                graph = g.g_act if which == "act" else g.g_step
+                if graph is None:
+                    # capturing replays nothing: run the chain once for real afterwards
+                    state = g.vec.state.clone() if which == "step" else None
+                    graph = self._graph(g, chain)
+                    if state is not None:
+                        g.vec.state.copy_(state)                           # undo the warm-up step taken before capture
+                    if which == "act":
+                        g.g_act = graph
+                    else:
+                        g.g_step = graph
+                graph.replay()
+            else:
+                chain(g)
+            (g.ev_act if which == "act" else g.ev_step).record(g.stream)
+
+    # ---- split-phase API ------------------------------------------------------------------------------------
+    def act_async(self, gi: int):
+        if self.groups[gi].agent is None:
+            raise RuntimeError("HostVecEnv was built without an agent")
+        self._run(self.groups[gi], "act")
+
+    def act_wait(self, gi: int):
+        g = self.groups[gi]
+        g.ev_act.synchronize()
+        return self.action[g.lo:g.hi]
+
+    def step_async(self, gi: int):
+        self._run(self.groups[gi], "step")
+
+    def step_wait(self, gi: int):
+        g = self.groups[gi]
+        g.ev_step.synchronize()
+        return self.obs[g.lo:g.hi], self.reward[g.lo:g.hi], self.terminated[g.lo:g.hi]
+
+    # ---- whole-batch calls (reference-shaped) ----------------------------------------------------------------
+    def eval(self, eval_mode: bool = True):
+        for g in self.groups:
+            g.vec.eval(eval_mode)
+
+    def reset(self, seed=None):
+        """Resets every env (seeds as given at construction, or `seed` + global env index); returns the pinned obs."""
+        for g in self.groups:
+            with torch.cuda.device(self.device), torch.cuda.stream(g.stream):
+                s = None if seed is None else int(seed) + np.arange(g.lo, g.hi, dtype=np.int64)
+                obs, _ = g.vec.reset(seed=s)
+                self.obs[g.lo:g.hi].copy_(obs, non_blocking=True)
+                g.ev_step.record(g.stream)
+        for g in self.groups:
+            g.ev_step.synchronize()
+        return self.obs
+
+    def act(self):
+        """agent.act on the host observations -> host actions (all groups)."""
+        for gi in range(len(self.groups)):
+            self.act_async(gi)
+        for gi in range(len(self.groups)):
+            self.act_wait(gi)
+        return self.action
+
+    def step(self, action=None):
+        """env.step on host actions (`action`: [N, V] array copied into the pinned buffer, or None = use `self.action`)."""
+        if action is not None:
+            self.action.copy_(torch.as_tensor(np.asarray(action)).to(self.action.dtype))
+        for gi in range(len(self.groups)):
+            self.step_async(gi)
+        for gi in range(len(self.groups)):
+            self.step_wait(gi)
+        return self.obs, self.reward, self.terminated
+
+    def run_pipelined(self, n_steps: int):
+        """n_steps of act + step for every env with the groups free-running: whenever a group's current phase has
+        completed (its event is done, i.e. the host has the action / the observation), its next phase is enqueued.
+        Groups drift apart by themselves, so host->device copies of some overlap device->host copies of others.
+        Per env the sequence of calls is exactly the plain loop's; returns (obs, reward, terminated) after the last step."""
+        G = len(self.groups)
+        if n_steps <= 0:
+            return self.obs, self.reward, self.terminated
+        phase = [0] * G                                 # completed phases of each group: 2 per step (act, step)
+        for gi in range(G):
+            self.act_async(gi)
+        live = G
+        while live:                                     # polls the groups' events (cudaEventQuery), like a blocking sync would
+            for gi, g in enumerate(self.groups):
+                ph = phase[gi]
+                if ph >= 2 * n_steps:
+                    continue
+                if not (g.ev_act if ph % 2 == 0 else g.ev_step).query():
+                    continue
+                phase[gi] = ph = ph + 1
+                if ph >= 2 * n_steps:
+                    live -= 1
+                elif ph % 2 == 1:
+                    self.step_async(gi)                # the host has the action: hand it to env.step
+                else:
+                    self.act_async(gi)                 # the host has obs / reward / done: next act
+        return self.obs, self.reward, self.terminated
+
+    def fast_forward(self, n_steps: int, agent: str = "bestfit"):
+        """Advance every env n_steps with the fused device-side agent (no host traffic), then refresh the host obs."""
+        for g in self.groups:
+            with torch.cuda.device(self.device), torch.cuda.stream(g.stream):
+                obs, _, _ = g.vec.agent_step(agent, n_steps, want_obs=True, want_action=False, want_valid=False)
+                self.obs[g.lo:g.hi].copy_(obs, non_blocking=True)
+                g.ev_step.record(g.stream)
+        for g in self.groups:
+            g.ev_step.synchronize()
+        return self.obs
+
+    def counters(self):
+        cs = [g.vec.counters() for g in self.groups]
+        return {k: np.concatenate([np.asarray(c[k]) for c in cs]) for k in cs[0]}
+
+    def close(self):
+        for g in self.groups:
+            g.g_act = g.g_step = None
+            g.vec.close()

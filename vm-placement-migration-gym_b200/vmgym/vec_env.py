@@ -187,16 +187,33 @@ class VecVmEnv:
             self._out_cache[key] = out
         return out
 
-    def step(self, action, want_obs: bool = True, want_valid: bool = True):
-        """env.py:66-103 for all envs.  `action`: [N, V] device tensor (uint8 / int16 / int64) or numpy int array."""
+    def step(self, action, want_obs: bool = True, want_valid: bool = True, host_outputs=None):
+        """env.py:66-103 for all envs.  `action`: [N, V] device tensor (uint8 / int16 / int64), numpy int array, or a
+        PINNED host tensor (device-mapped under UVA: the kernel reads it over PCIe, no copy-engine transfer).
+        `host_outputs`: optional (reward f64 [N], terminated u8 [N]) pinned host tensors the kernel writes directly,
+        instead of the env's device buffers."""
         if not isinstance(action, torch.Tensor):
             action = torch.from_numpy(np.ascontiguousarray(action, dtype=np.int64)).to(self.device, non_blocking=True)
+        elif not action.is_cuda and not action.is_pinned():
+            action = action.to(self.device, non_blocking=True)
         if action.shape != (self.num_envs, self.V):
             raise ValueError(f"action must have shape {(self.num_envs, self.V)}, got {tuple(action.shape)}")
         if action.dtype not in _TORCH_ACTION_DTYPES:
             action = action.to(torch.int64)
         action = action.contiguous()
         out = self._outputs(want_obs=want_obs, want_valid=want_valid)
+        if host_outputs is not None:
+            rew_h, term_h = host_outputs
+            if not (rew_h.is_pinned() and term_h.is_pinned() and rew_h.dtype == torch.float64 and term_h.dtype == torch.uint8
+                    and rew_h.numel() == self.num_envs and term_h.numel() == self.num_envs):
+                raise ValueError("host_outputs must be pinned (float64 [N], uint8 [N]) tensors")
+            key = ("host", rew_h.data_ptr(), term_h.data_ptr(), want_obs, want_valid)
+            hout = self._out_cache.get(key)
+            if hout is None:
+                hout = nv.Outputs(d_obs=out.d_obs, d_reward=rew_h.data_ptr(), d_terminated=term_h.data_ptr(), d_valid=out.d_valid,
+                                  d_action=None, d_stats=None)
+                self._out_cache[key] = hout
+            out = hout
         with self._on_device():
             nv.check(self._lib.vmgym_step(C.byref(self._ccfg()), self.state.data_ptr(), self.num_envs,
                                           C.byref(self._trace), action.data_ptr(), _TORCH_ACTION_DTYPES[action.dtype],
