@@ -47,6 +47,8 @@ def lib():
         L.vmo_set_trace.argtypes = [C.c_void_p, i32p, C.c_int64, f64p, f64p, i64p, C.c_int64]
         L.vmo_set_eval.argtypes = [C.c_void_p, C.c_int]
         L.vmo_reset.argtypes = [C.c_void_p]
+        L.vmo_set_record.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+        L.vmo_record_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.vmo_invalid_action_mask.argtypes = [C.c_void_p, C.c_int, u8p]
         L.vmo_get_obs.argtypes = [C.c_void_p, f32p]
         L.vmo_step.restype = C.c_int
@@ -227,6 +229,64 @@ class OracleVmEnv:
     def counters(self):
         s = self.state()
         return {k: v for k, v in s.items() if isinstance(v, int)}
+
+    # -- Record (src/record.py) --------------------------------------------------------------------
+    def enable_record(self, max_steps: int, max_arrivals: int | None = None):
+        """Keep what Base.record_testing_step keeps for the per-VM statistics (base.py:135,140): the placement vector
+        after every step and the env's vm_arrival_steps lists.  Rewound by reset()."""
+        self._rec_log = np.zeros((int(max_steps), self.V), np.int16)
+        self._arr_log = np.zeros((int(max_arrivals or 4 * max_steps + self.V), 2), np.int32)
+        lib().vmo_set_record(self._h, self._rec_log.ctypes.data, self._rec_log.shape[0], self._arr_log.ctypes.data,
+                             self._arr_log.shape[0])
+
+    def record_lists(self):
+        """Record.unique_vms_placement / pending_rates / slowdown_rates / vm_lifetime (record.py:34-96), restated
+        line by line on the logged samples.  Returns (pending list, slowdown list, lifetime list)."""
+        n_steps, n_arr = C.c_int64(), C.c_int64()
+        lib().vmo_record_counts(self._h, C.byref(n_steps), C.byref(n_arr))
+        assert n_steps.value <= self._rec_log.shape[0] and n_arr.value < self._arr_log.shape[0], "record log overflow"
+        placements = np.transpose(self._rec_log[:n_steps.value].astype(np.int64))     # row is vm, col is timestep (:37)
+        arrival_steps = [[] for _ in range(self.V)]
+        for slot, step in self._arr_log[:n_arr.value]:
+            arrival_steps[int(slot)].append(int(step))
+        WAIT = self.WAIT_STATUS
+        unique = []
+        for vm, vm_status in enumerate(placements):                                   # :38-51
+            if len(arrival_steps[vm]) == 0:
+                continue
+            start = 0
+            for end in arrival_steps[vm][1:]:
+                end -= 2                                                              # vm_placements starts at timestep 2
+                spline = vm_status[start:end]
+                unique.append(spline[spline <= WAIT])
+                start = end
+            spline = vm_status[start:]
+            unique.append(spline[spline <= WAIT])
+        pending, slowdown, life = [], [], []
+        for status in unique:
+            running = np.where(status < WAIT)[0]
+            allocated_at = running[0] if running.size > 0 else None
+            if allocated_at:                                                          # :60,75,91 (index 0 counts as None)
+                pending.append(np.around((allocated_at + 1.0) / len(status), 3))
+                slowdown_steps = np.count_nonzero(status[allocated_at:] == WAIT)
+                vm_life = len(status) - allocated_at - 1
+                slowdown.append(0 if vm_life == 0 else np.around(slowdown_steps / vm_life, 3))
+                life.append(len(status) - allocated_at - 1)
+            else:
+                pending.append(1.0)
+                life.append(0)
+        if len(slowdown) == 0:
+            slowdown = [0]                                                            # :83-84
+        return pending, slowdown, life
+
+    def record_summary(self):
+        """The per-VM keys of Record.get_summary (record.py:118-125)."""
+        pending, slowdown, life = self.record_lists()
+        return {"average VM life": np.round(np.mean(life), 3), "average pending": np.round(np.mean(pending), 3),
+                "median pending": np.round(np.median(pending), 3),
+                "max pending": np.round(np.max(pending), 3) if len(pending) > 0 else 0,
+                "average slowdown": np.round(np.mean(slowdown), 3), "median slowdown": np.round(np.median(slowdown), 3),
+                "max slowdown": np.round(np.max(slowdown), 3)}
 
     def rollout(self, agent: int, steps: int, tiebreak: int = TIE_STABLE):
         """Base.test-style loop in C.  Returns (steps_run, stats dict)."""

@@ -130,3 +130,40 @@ def test_published_rows(kat):
     assert "%.3f" % m["cpu_var"] == "%.3f" % row["var"]
     assert "%.3f" % m["mem_mean"] == "%.3f" % row["mem"]
     assert "%.3f" % m["waiting_ratio_mean"] == "%.3f" % row["wait"]
+
+
+RECORD_CASES = ["rec_busy_firstfit", "rec_busy_suspend", "rec_p37_v70", "rec_s10_sparse", "rec_s100_bestfit"]
+
+
+def load_record_case(name):
+    import json
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "record.npz"))
+    return dict(cfg=json.loads(str(z[f"{name}.cfg_json"])), actions=z[f"{name}.actions"], pending=z[f"{name}.pending"],
+                slowdown=z[f"{name}.slowdown"], lifetime=z[f"{name}.lifetime"], summary=json.loads(str(z[f"{name}.summary_json"])),
+                agent=str(z[f"{name}.agent"]), perturb=float(z[f"{name}.perturb"]))
+
+
+@pytest.mark.parametrize("name", RECORD_CASES)
+def test_oracle_record_lists_match_reference_record(name):
+    """The oracle's restatement of Record (record.py:34-96) on its own episode log == the lists the reference's Record
+    produced for the same action stream (tests/golden/make_golden_record.py): order and values identical."""
+    import vmoracle as vo
+    g = load_record_case(name)
+    env = vo.OracleVmEnv(vo.OracleConfig(**g["cfg"]))
+    env.eval()
+    T = g["actions"].shape[0]
+    env.enable_record(T)
+    env.reset(seed=g["cfg"]["seed"])
+    done = False
+    for t in range(T):
+        assert not done
+        _, _, done, _, _ = env.step(g["actions"][t].astype(np.int64))
+    assert done
+    pending, slowdown, life = env.record_lists()
+    assert np.array_equal(np.asarray(pending, np.float64), g["pending"])
+    assert np.array_equal(np.asarray(slowdown, np.float64), g["slowdown"])
+    assert np.array_equal(np.asarray(life, np.int64), g["lifetime"])
+    s = env.record_summary()
+    for k, v in s.items():
+        assert float(v) == g["summary"][k], k
