@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define VMGYM_ABI_VERSION 1
+#define VMGYM_ABI_VERSION 2
 
 enum vmgym_status {
     VMGYM_OK = 0,
@@ -119,7 +119,16 @@ typedef struct vmgym_outputs {
     uint8_t* d_valid;        /* [n_envs, V] info["valid"] (env.py:69-74,91-94) */
     void* d_action;          /* [n_envs, V] actions chosen by a fused agent, element type = placement type */
     double* d_stats;         /* [n_envs, 8] running sums for the eval summary (src/record.py:98-134), see DESIGN.md */
+    /* Per-VM episode statistics of Record (src/record.py:34-96: pending rate, slowdown rate, lifetime of every VM that
+     * occupied a slot), all three NULL or all three set.  The step kernels keep four clocks per slot and add a VM to
+     * the histograms when it departs; vmgym_vmstats_finalize adds the VMs that still exist.  Zero the three buffers
+     * when the envs are reset. */
+    uint32_t* d_vm_slots;    /* [n_envs, V, 4] arrival step, first-placement step (0 = never), waiting steps after the
+                                first placement, step of the pending suspension (0 = none) */
+    uint32_t* d_vm_hist;     /* [n_envs, 2, VMGYM_VMSTAT_BINS] counts of rint(1000 * rate): [0] pending, [1] slowdown */
+    uint64_t* d_vm_totals;   /* [n_envs, 4] VMs seen, VMs ever placed, sum of lifetimes, reserved */
 } vmgym_outputs;
+#define VMGYM_VMSTAT_BINS 1024   /* rates are rounded to 3 decimals (record.py:61,79): bins 0..1000 are used */
 
 const char* vmgym_last_error(void);
 int vmgym_abi_version(void);
@@ -140,6 +149,14 @@ int vmgym_reset(const vmgym_config* cfg, void* d_state, int64_t n_envs, const ui
  * Out-of-range action values are invalid no-ops, as in validate() (:35-42). */
 int vmgym_step(const vmgym_config* cfg, void* d_state, int64_t n_envs, const vmgym_trace* trace,
                const void* d_action, int action_dtype, const vmgym_outputs* out, void* stream);
+
+/* Record's per-VM lists at this moment (record.py:34-96 evaluated on the episode so far): copies the histograms /
+ * totals the step kernels accumulated for departed VMs into d_hist_out [n_envs, 2, VMGYM_VMSTAT_BINS] /
+ * d_totals_out [n_envs, 4] and adds every VM that still occupies a slot (its sample list ends at the last step).
+ * Does not modify the env state or the running buffers. */
+int vmgym_vmstats_finalize(const vmgym_config* cfg, const void* d_state, int64_t n_envs, const uint32_t* d_vm_slots,
+                           const uint32_t* d_vm_hist, const uint64_t* d_vm_totals, uint32_t* d_hist_out,
+                           uint64_t* d_totals_out, void* stream);
 
 /* Fused agent.act(obs) + env.step(action) (the body of Base.test's loop, src/agents/base.py:71-86) for the
  * heuristic agents, n_steps times per launch with the env state resident in shared memory.

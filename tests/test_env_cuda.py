@@ -305,16 +305,16 @@ GPU_KATS = {
     # arrival_rate = round(pms / 0.55 / service_length, 4) (exp_performance.py:26, exp_performance_small.py:23)
     "KAT1_firstfit_s10": ("10", 0.0182, "ut", "firstfit", "stable", [1, 2, 3, 4, 5],
                           [702661.695, 690616.030, 695187.965, 695977.240, 700256.885],
-                          dict(ret=696939.963, drop=0.241, served=1258, cpu=0.697, var=0.051, mem=0.697, wait=0.539)),
+                          dict(ret=696939.963, drop=0.241, served=1258, cpu=0.697, var=0.051, mem=0.697, wait=0.539, pend=0.183, slow=0.000)),
     "KAT2_firstfit_s100": ("100", 0.1818, "wr", "firstfit", "stable", [0, 1, 2, 3, 4],
                            [-53615.794, -53208.140, -53318.037, -52963.827, -53735.479],
-                           dict(ret=-53368.255, drop=0.203, served=13394, cpu=0.737, var=0.052, mem=0.736, wait=0.534)),
+                           dict(ret=-53368.255, drop=0.203, served=13394, cpu=0.737, var=0.052, mem=0.736, wait=0.534, pend=0.070, slow=0.000)),
     "KAT3_bestfit_s10": ("10", 0.0182, "ut", "bestfit", "stable", [1, 2, 3, 4, 5],
                          [699859.415, 694840.720, 698802.250, 697559.640, 703166.045],
-                         dict(ret=698845.614, drop=0.242, served=1260, cpu=0.699, var=0.053, mem=0.699, wait=0.537)),
+                         dict(ret=698845.614, drop=0.242, served=1260, cpu=0.699, var=0.053, mem=0.699, wait=0.537, pend=0.178, slow=0.000)),
     "KAT4_bestfit_s100": ("100", 0.1818, "wr", "bestfit", "numpy_introsort", [0, 1, 2, 3, 4],
                           [-52064.658, -51690.685, -51570.904, -51202.317, -51729.035],
-                          dict(ret=-51651.520, drop=0.182, served=13862, cpu=0.763, var=0.057, mem=0.762, wait=0.517)),
+                          dict(ret=-51651.520, drop=0.182, served=13862, cpu=0.763, var=0.057, mem=0.762, wait=0.517, pend=0.068, slow=0.000)),
 }
 
 
@@ -327,7 +327,7 @@ def test_published_rows_on_the_cuda_path(kat):
     P, V = (10, 30) if base == "10" else (100, 300)
     cfg = _cfg(pms=P, vms=V, service_length=1000, arrival_rate=lam, training_steps=10000, eval_steps=100000,
                reward_function=reward, cap_target_util=True, sequence="uniform", beta=0.5, allow_null_action=True)
-    vec = VecVmEnv(cfg, len(seeds), seeds=seeds, tiebreak=tie)
+    vec = VecVmEnv(cfg, len(seeds), seeds=seeds, tiebreak=tie).enable_vm_stats()
     s = vec.evaluate(agent, seeds=seeds)
     assert np.all(s["steps"] == 100000)
     for got, want in zip(s["total rewards"], per_seed):
@@ -339,6 +339,90 @@ def test_published_rows_on_the_cuda_path(kat):
     assert "%.3f" % s["cpu var"].mean() == "%.3f" % row["var"]
     assert "%.3f" % s["memory mean"].mean() == "%.3f" % row["mem"]
     assert "%.3f" % s["waiting ratio"].mean() == "%.3f" % row["wait"]
+    # Pending Rate / Slowdown Rate columns (exp_performance.py:104-105,139-141): mean over seeds of np.mean(record lists)
+    assert "%.3f" % s["average pending"].mean() == "%.3f" % row["pend"]
+    assert "%.3f" % s["average slowdown"].mean() == "%.3f" % row["slow"]
+
+
+@pytest.mark.parametrize("name", ["rec_busy_firstfit", "rec_busy_suspend", "rec_p37_v70", "rec_s10_sparse", "rec_s100_bestfit"])
+def test_per_vm_statistics_match_reference_record(name):
+    """Record's per-VM lists (record.py:34-96) from the kernel's four clocks per slot + histograms == the lists the
+    reference's own Record produced for the same episode (tests/golden/record.npz): same multiset of pending rates,
+    slowdown rates and lifetimes, hence the same mean / median / max."""
+    import json
+    import os
+    from vmgym import VecVmEnv
+    from vmgym import _native as nv
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "record.npz"))
+    cfgd = json.loads(str(z[f"{name}.cfg_json"]))
+    actions, pending, slowdown, life = (z[f"{name}.{k}"] for k in ("actions", "pending", "slowdown", "lifetime"))
+    summary = json.loads(str(z[f"{name}.summary_json"]))
+    T = actions.shape[0]
+    vec = VecVmEnv(_cfg(**cfgd), 1, seeds=[cfgd["seed"]], trace_steps=T + 8, max_admissions=4 * T + 512).enable_vm_stats()
+    vec.eval(True)
+    vec.reset(seed=np.array([cfgd["seed"]]))
+    for t in range(T):
+        _, _, term, _, _ = vec.step(actions[t:t + 1].astype(np.int64))
+    assert bool(term[0])
+    s = vec.vm_stats()
+    assert int(s["vms"][0]) == pending.size
+    assert int(s["placed vms"][0]) in ((slowdown.size,) if slowdown.size != 1 else (0, 1))     # record.py:83-84: [0] when none
+    # the histograms are the multisets of the golden lists
+    torch = _torch()
+    hist = torch.empty_like(vec._vm_hist); totals = torch.empty_like(vec._vm_totals)
+    import ctypes as C
+    nv.check(nv.lib().vmgym_vmstats_finalize(C.byref(vec._ccfg()), vec.state.data_ptr(), 1, vec._vm_slots.data_ptr(),
+                                             vec._vm_hist.data_ptr(), vec._vm_totals.data_ptr(), hist.data_ptr(), totals.data_ptr(),
+                                             vec._stream()), "finalize")
+    h = hist.cpu().numpy()[0]
+    want_p = np.bincount(np.rint(pending * 1000).astype(np.int64), minlength=nv.VMSTAT_BINS)
+    assert np.array_equal(h[0], want_p)
+    if int(s["placed vms"][0]) > 0:
+        want_s = np.bincount(np.rint(slowdown * 1000).astype(np.int64), minlength=nv.VMSTAT_BINS)
+        assert np.array_equal(h[1], want_s)
+    assert int(totals[0, 2]) == int(life.sum())
+    for k in ("average VM life", "average pending", "median pending", "max pending", "average slowdown", "median slowdown",
+              "max slowdown"):
+        assert float(np.round(s[k][0], 3)) == summary[k], k        # np.round as in record.py:118-125
+
+
+def test_per_vm_statistics_batch_vs_oracle_record():
+    """Philox traces, 6 envs, random suspend / re-place actions mixed into first-fit for 700 steps (no episode end: the
+    statistics include the VMs still in their slots) == the oracle's Record restatement on the same traces."""
+    torch = _torch()
+    import vmoracle as vo
+    from vmgym import VecVmEnv
+    from vmgym.agents import FirstFitAgent
+    kw = dict(pms=10, vms=30, arrival_rate=0.45, service_length=35, training_steps=5000, eval_steps=5000, reward_function="wr",
+              allow_null_action=True)
+    N, T = 6, 700
+    vec = VecVmEnv(_cfg(**kw), N, rng="philox").enable_vm_stats()
+    vec.reset(seed=100 + np.arange(N))
+    agent = FirstFitAgent(vec)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    ka, ta, ks, ts, lo, hi = vec.philox_tables
+    oracles = []
+    for i in range(N):
+        o = vo.OracleVmEnv(vo.OracleConfig(**kw))
+        o.enable_record(T)
+        o.reset(trace=vo.philox_trace(100 + i, T + 8, 4 * T + 64, ka, ta, ks, ts, lo, hi))
+        oracles.append(o)
+    obs = vec.observe()
+    for t in range(T):
+        act = agent.act(obs).to(torch.int64)
+        u = torch.rand(act.shape, generator=g).to(act.device)
+        act = torch.where(u < 0.08, torch.full_like(act, kw["pms"]), act)
+        obs, _, _, _, _ = vec.step(act)
+        a = act.cpu().numpy()
+        for i, o in enumerate(oracles):
+            o.step(a[i])
+    s = vec.vm_stats()
+    for i, o in enumerate(oracles):
+        want = o.record_summary()
+        pending, slowdown, life = o.record_lists()
+        assert int(s["vms"][i]) == len(pending)
+        for k, v in want.items():
+            assert float(np.round(s[k][i], 3)) == float(v), (i, k)
 
 
 def test_empty_batch_and_bad_arguments():

@@ -120,7 +120,7 @@ static int launch_step(StepParams& sp, cudaStream_t st)
     if (specialise && sizeof(PT) == 1 && L.P == 100 && L.V == 300) {                        // config/100.yml
         kern = step_kernel<PT, 100, 300, -1>;
         // the benchmark configurations of this shape: fused heuristic agents / external actions, reward wr, stable ties
-        if (sp.reward_fn == VMGYM_REWARD_WR && sp.tiebreak == VMGYM_TIE_STABLE) {
+        if (sp.reward_fn == VMGYM_REWARD_WR && sp.tiebreak == VMGYM_TIE_STABLE && !sp.out.d_vm_slots) {   // per-VM stats: generic kernel
             const int mode = sp.tr.mode;
             if (sp.agent == VMGYM_AGENT_BESTFIT && mode == VMGYM_TRACE_PHILOX)
                 kern = step_kernel<PT, 100, 300, make_spec(VMGYM_AGENT_BESTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>;
@@ -172,6 +172,8 @@ static int fill_params(StepParams* sp, const vmgym_config* cfg, void* d_state, i
     sp->beta = cfg->beta;
     sp->state = (unsigned char*)d_state; sp->n_envs = n_envs; sp->tr = *trace;
     if (out) sp->out = *out; else memset(&sp->out, 0, sizeof(sp->out));
+    const int n_vm = (sp->out.d_vm_slots != nullptr) + (sp->out.d_vm_hist != nullptr) + (sp->out.d_vm_totals != nullptr);
+    if (n_vm != 0 && n_vm != 3) return fail(VMGYM_EINVAL, "d_vm_slots / d_vm_hist / d_vm_totals must be all set or all NULL");
     sp->action = nullptr; sp->action_dtype = VMGYM_U8; sp->use_bulk = 1; sp->agent = VMGYM_AGENT_NONE; sp->tiebreak = 0; sp->n_steps = 1;
     return VMGYM_OK;
 }
@@ -308,6 +310,29 @@ int vmgym_invalid_action_mask(const vmgym_config* cfg, const void* d_state, int6
     if (L.P <= 253) mask_kernel<uint8_t><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(L, (const unsigned char*)d_state, n_envs, d_mask);
     else mask_kernel<uint16_t><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(L, (const unsigned char*)d_state, n_envs, d_mask);
     return check_cuda(cudaGetLastError(), "mask_kernel launch");
+}
+
+int vmgym_vmstats_finalize(const vmgym_config* cfg, const void* d_state, int64_t n_envs, const uint32_t* d_vm_slots,
+                           const uint32_t* d_vm_hist, const uint64_t* d_vm_totals, uint32_t* d_hist_out,
+                           uint64_t* d_totals_out, void* stream)
+{
+    DevLayout L;
+    int rc = make_layout(cfg, &L, nullptr);
+    if (rc) return rc;
+    if (n_envs == 0) return VMGYM_OK;
+    if (!d_state || !d_vm_slots || !d_vm_hist || !d_vm_totals || !d_hist_out || !d_totals_out || n_envs < 0)
+        return fail(VMGYM_EINVAL, "null per-VM statistics buffer");
+    const int threads = 128;
+    const long long blocks = (n_envs * 32 + threads - 1) / threads;
+    if (L.P <= 253)
+        vmstats_finalize_kernel<uint8_t><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+            L, (const unsigned char*)d_state, n_envs, d_vm_slots, d_vm_hist, (const unsigned long long*)d_vm_totals, d_hist_out,
+            (unsigned long long*)d_totals_out);
+    else
+        vmstats_finalize_kernel<uint16_t><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+            L, (const unsigned char*)d_state, n_envs, d_vm_slots, d_vm_hist, (const unsigned long long*)d_vm_totals, d_hist_out,
+            (unsigned long long*)d_totals_out);
+    return check_cuda(cudaGetLastError(), "vmstats_finalize_kernel launch");
 }
 
 }  // extern "C"

@@ -306,6 +306,43 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Per-VM episode statistics (src/record.py:34-96).  Record rebuilds, for every VM that ever occupied a slot, the list
+// of its post-step placement samples from arrival to departure and derives
+//   pending rate  = around((first running sample index + 1) / len, 3)        (1.0 if never placed)
+//   slowdown rate = around(#WAIT samples after the first placement / (len - index - 1), 3)   (placed VMs only)
+//   lifetime      = len - index - 1                                            (0 if never placed)
+// With t_a / t_p / t_d the steps of arrival, first placement and departure: index = t_p - t_a (arrivals follow the
+// apply loop, so index >= 1), len = t_d - t_a, and the WAIT samples after the first placement are the lengths of the
+// suspension intervals.  Four clocks per slot therefore replace the V x T sample matrix; rates are binned by
+// rint(1000 * rate), which is exactly what np.around(., 3) keeps.
+// ---------------------------------------------------------------------------------------------------
+struct VmStat {
+    uint32_t* slots;      // this env's [V][4]
+    uint32_t* hist;       // this env's [2][VMGYM_VMSTAT_BINS]
+    unsigned long long* totals;   // this env's [4]
+};
+
+// the VM in `s` ends its sample list after `len` samples; `wait_extra`: WAIT samples of a still-open suspension
+__device__ __forceinline__ void vmstat_close(const uint32_t* s, uint32_t len, uint32_t wait_extra, uint32_t* hist,
+                                             unsigned long long* totals)
+{
+    totals[0] += 1ull;
+    if (s[1] != 0u) {
+        const uint32_t idx = s[1] - s[0];                                     // allocated_at (record.py:59)
+        const uint32_t life = len - idx - 1u;
+        const int kp = (int)rint(((double)idx + 1.0) / (double)len * 1000.0);
+        const uint32_t wait = s[2] + wait_extra;
+        const int ks = life == 0u ? 0 : (int)rint((double)wait / (double)life * 1000.0);
+        hist[min(max(kp, 0), VMGYM_VMSTAT_BINS - 1)] += 1u;
+        hist[VMGYM_VMSTAT_BINS + min(max(ks, 0), VMGYM_VMSTAT_BINS - 1)] += 1u;
+        totals[1] += 1ull;
+        totals[2] += (unsigned long long)life;
+    } else {
+        hist[1000] += 1u;                                                      // never placed: pending rate 1.0
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Rewards `ut` (env.py:151-152) and `kl` (env.py:125-150, kl_divergence :8-17).  All reductions use numpy's
 // summation order so the fp64 values (and the exact-zero variance tests) are those of the reference.
 // ---------------------------------------------------------------------------------------------------
@@ -427,10 +464,17 @@ __device__ __noinline__ void stats_update(const Env<PT> e, const StepResult res,
 // common quiet step (nothing placed, nothing departs, nothing admitted) costs only the service countdown, one
 // arrival draw and the outputs.
 // ---------------------------------------------------------------------------------------------------
-template <typename PT, int REWARD_CT, int MODE_CT>
+template <typename PT, int REWARD_CT, int MODE_CT, bool VMSTAT>
 __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParams& p, long long env_id, uint8_t* valid_g,
                                                bool have_actions)
 {
+    // per-VM statistics are compiled into the generic instantiations only (the specialised throughput kernels skip them)
+    const bool vmstat = VMSTAT && p.out.d_vm_slots != nullptr;
+    VmStat vs;
+    vs.slots = vmstat ? p.out.d_vm_slots + env_id * (long long)e.V * 4 : nullptr;
+    vs.hist = vmstat ? p.out.d_vm_hist + env_id * 2ll * VMGYM_VMSTAT_BINS : nullptr;
+    vs.totals = vmstat ? reinterpret_cast<unsigned long long*>(p.out.d_vm_totals) + env_id * 4 : nullptr;
+    const uint32_t tnow = (uint32_t)e.sc()->timestep;                  // the step being executed (1-based, env.py:101)
     const int reward_fn = REWARD_CT ? REWARD_CT : p.reward_fn;            // compile-time in the specialised kernels
     const int trace_mode = MODE_CT >= 0 ? MODE_CT : p.tr.mode;
     const int P = e.P, V = e.V, lane = e.lane;
@@ -466,6 +510,11 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                             if (lane == 0) {                                                                   // :82-85
                                 cpu[a] = nc; mem[a] = nm; place[vv] = (PT)a; cpuc[vv] &= 0x7f;
                                 e.rcap()[a] = (uint16_t)(max_code(e.sz32, (float)nc) | (max_code(e.sz32, (float)nm) << 8));
+                                if (vmstat) {
+                                    uint32_t* s = vs.slots + vv * 4;
+                                    if (s[1] == 0u) s[1] = tnow;                               // first placement
+                                    else { s[2] += tnow - s[3]; s[3] = 0u; }                   // end of a suspension
+                                }
                             }
                         }
                     }
@@ -479,6 +528,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                         if (lane == 0) {
                             cpu[cv] = nc; mem[cv] = nm; place[vv] = (PT)P; cpuc[vv] |= 0x80;
                             e.rcap()[cv] = (uint16_t)(max_code(e.sz32, (float)nc) | (max_code(e.sz32, (float)nm) << 8));
+                            if (vmstat) vs.slots[vv * 4 + 3] = tnow;                           // WAIT samples start at this step
                         }
                     }
                 }
@@ -542,6 +592,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                             if (mem[pm] < 1e-7) mem[pm] = 0.0;
                             refresh_cap(e, pm);
                             place[vv] = (PT)(P + 1); cpuc[vv] = 0; memc[vv] = 0; rem[vv] = 0;
+                            if (vmstat) vmstat_close(vs.slots + vv * 4, tnow - vs.slots[vv * 4], 0u, vs.hist, vs.totals);
                         }
                     }
                 }
@@ -567,6 +618,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                         const int vv = c0 + b, pm = (int)place[vv];
                         cpu[pm] -= e.sz64[cpuc[vv] & 0x7f];
                         mem[pm] -= e.sz64[memc[vv]];
+                        if (vmstat) vmstat_close(vs.slots + vv * 4, tnow - vs.slots[vv * 4], 0u, vs.hist, vs.totals);
                     }
                 }
                 __syncwarp();
@@ -650,6 +702,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                 place[v] = (PT)P;
                 cpuc[v] = (uint8_t)cc; memc[v] = (uint8_t)mc; rem[v] = (uint16_t)svc;
                 csum += cc; msum += mc;
+                if (vmstat) *reinterpret_cast<uint4*>(vs.slots + v * 4) = make_uint4(tnow, 0u, 0u, 0u);   // arrival (env.py:293)
             }
             admitted += __popc(m);
         }
@@ -933,7 +986,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
                 __syncwarp();
                 have_actions = any != 0;
             }
-            res = env_step<PT, REWARD_CT, MODE_CT>(e, p, env, valid_g, have_actions);
+            res = env_step<PT, REWARD_CT, MODE_CT, (SPEC < 0)>(e, p, env, valid_g, have_actions);
             if (res.changed) {
                 quiet = false;
             } else if (evaluated) {
@@ -972,6 +1025,35 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
             __syncwarp();
         } else {
             copy16(grec, base, L.rec_bytes, lane);
+        }
+    }
+}
+
+
+// Record's per-VM lists as of now: running histograms + the VMs that still occupy a slot (one warp per env).
+template <typename PT>
+__global__ void vmstats_finalize_kernel(DevLayout L, const unsigned char* state, long long n_envs, const uint32_t* slots,
+                                        const uint32_t* hist, const unsigned long long* totals, uint32_t* hist_out,
+                                        unsigned long long* totals_out)
+{
+    const int lane = threadIdx.x & 31;
+    const long long env = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (env >= n_envs) return;
+    const unsigned char* rec = state + env * (long long)L.rec_bytes;
+    const PT* place = reinterpret_cast<const PT*>(rec + L.off_place);
+    const vmgym_env_scalars* sc = reinterpret_cast<const vmgym_env_scalars*>(rec + L.off_scal);
+    uint32_t* ho = hist_out + env * 2ll * VMGYM_VMSTAT_BINS;
+    const uint32_t* hi = hist + env * 2ll * VMGYM_VMSTAT_BINS;
+    for (int i = lane; i < 2 * VMGYM_VMSTAT_BINS; i += 32) ho[i] = hi[i];
+    unsigned long long* to = totals_out + env * 4;
+    if (lane < 4) to[lane] = totals[env * 4 + lane];
+    __syncwarp();
+    if (lane == 0) {
+        const uint32_t next = (uint32_t)sc->timestep;            // last executed step + 1: samples run through step next - 1
+        const uint32_t* s = slots + env * (long long)L.V * 4;
+        for (int v = 0; v < L.V; v++) {
+            if ((int)place[v] <= L.P)
+                vmstat_close(s + v * 4, next - s[v * 4], s[v * 4 + 3] ? next - s[v * 4 + 3] : 0u, ho, to);
         }
     }
 }

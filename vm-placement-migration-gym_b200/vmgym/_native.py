@@ -52,7 +52,11 @@ class Trace(C.Structure):
 
 class Outputs(C.Structure):
     _fields_ = [("d_obs", C.c_void_p), ("d_reward", C.c_void_p), ("d_terminated", C.c_void_p),
-                ("d_valid", C.c_void_p), ("d_action", C.c_void_p), ("d_stats", C.c_void_p)]
+                ("d_valid", C.c_void_p), ("d_action", C.c_void_p), ("d_stats", C.c_void_p),
+                ("d_vm_slots", C.c_void_p), ("d_vm_hist", C.c_void_p), ("d_vm_totals", C.c_void_p)]
+
+
+VMSTAT_BINS = 1024
 
 
 # offsets inside struct vmgym_env_scalars (include/vmgym.h)
@@ -63,7 +67,7 @@ SCALARS_BYTES = 80
 EXPORTS = ["vmgym_last_error", "vmgym_abi_version", "vmgym_get_layout", "vmgym_reset", "vmgym_step",
            "vmgym_agent_step", "vmgym_agent_act", "vmgym_observe", "vmgym_invalid_action_mask", "vmgym_set_tuning",
            "vmgym_policy_heads", "vmgym_policy_heads_backward", "vmgym_gae", "vmgym_drlvmp_choice", "vmgym_linear_bf16", "vmgym_policy_fused", "vmgym_segtree_update",
-           "vmgym_segtree_retrieve"]
+           "vmgym_segtree_retrieve", "vmgym_vmstats_finalize"]
 
 
 class VmgymError(RuntimeError):
@@ -110,6 +114,8 @@ def lib():
     L.vmgym_agent_act.argtypes = [C.POINTER(Config), i32, i32, vp, i64, vp, i32, vp]
     L.vmgym_observe.argtypes = [C.POINTER(Config), vp, i64, vp, vp]
     L.vmgym_invalid_action_mask.argtypes = [C.POINTER(Config), vp, i64, vp, vp]
+    L.vmgym_vmstats_finalize.restype = i32
+    L.vmgym_vmstats_finalize.argtypes = [C.POINTER(Config), vp, i64, vp, vp, vp, vp, vp, vp]
     L.vmgym_set_tuning.argtypes = [i32, i32]
     f32, u64 = C.c_float, C.c_uint64
     L.vmgym_policy_heads.argtypes = [C.POINTER(Config), vp, vp, i32, vp, i64, vp, i32, f32, u64, u64, vp, vp, vp, vp, vp]

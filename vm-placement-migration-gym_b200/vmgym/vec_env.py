@@ -29,6 +29,37 @@ _TORCH_ACTION_DTYPES = {torch.uint8: nv.U8, torch.int16: nv.I16, torch.int64: nv
 _NULL_CTX = contextlib.nullcontext()
 
 
+def _hist_stats(h):
+    """mean / median / max of the list that has h[k] copies of k / 1000.0 (np.mean / np.median / np.max semantics)."""
+    n = int(h.sum())
+    if n == 0:
+        return 0.0, 0.0, 0.0
+    ks = np.nonzero(h)[0]
+    vals = ks / 1000.0
+    mean = float(np.dot(h[ks], vals) / n)
+    cum = np.cumsum(h)
+    lo = int(np.searchsorted(cum, (n - 1) // 2 + 1))        # value at sorted index (n-1)//2
+    hi = int(np.searchsorted(cum, n // 2 + 1))              # value at sorted index n//2
+    median = (lo / 1000.0 + hi / 1000.0) / 2.0 if n % 2 == 0 else hi / 1000.0
+    return mean, float(median), float(ks[-1] / 1000.0)
+
+
+def vm_stats_from_histograms(hist, totals):
+    """hist int64 [N, 2, BINS] (pending, slowdown), totals int64 [N, 4] (VMs, placed VMs, sum of lifetimes) ->
+    Record.get_summary's per-VM keys (record.py:118-125) per env, unrounded."""
+    N = hist.shape[0]
+    out = {k: np.zeros(N) for k in ("average VM life", "average pending", "median pending", "max pending",
+                                     "average slowdown", "median slowdown", "max slowdown", "vms", "placed vms")}
+    for i in range(N):
+        n_vms, n_placed, life = int(totals[i, 0]), int(totals[i, 1]), int(totals[i, 2])
+        out["vms"][i], out["placed vms"][i] = n_vms, n_placed
+        out["average VM life"][i] = life / n_vms if n_vms else float("nan")        # np.mean([]) is nan in the reference too
+        out["average pending"][i], out["median pending"][i], out["max pending"][i] = _hist_stats(hist[i, 0])
+        # record.py:83-84: no placed VM -> the slowdown list is [0]
+        out["average slowdown"][i], out["median slowdown"][i], out["max slowdown"][i] = _hist_stats(hist[i, 1])
+    return out
+
+
 class VecVmEnv:
     def __init__(self, config: Config, num_envs: int, device="cuda", rng: str = "numpy", seeds=None,
                  trace_steps: int | None = None, max_admissions: int | None = None, tiebreak: str = "stable"):
@@ -51,6 +82,7 @@ class VecVmEnv:
         self._lib = nv.lib()
         self._ccfg_cache = {}
         self._out_cache = {}
+        self._vm_slots = self._vm_hist = self._vm_totals = None      # per-VM statistics buffers (enable_vm_stats)
         self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.device = torch.device("cuda", self._dev_index)
         self._layout = nv.Layout()
@@ -170,6 +202,8 @@ class VecVmEnv:
                     rewind = 0
             self._reseeded = False
             self.stats.zero_()
+            if self._vm_slots is not None:
+                self._vm_slots.zero_(); self._vm_hist.zero_(); self._vm_totals.zero_()
             nv.check(self._lib.vmgym_reset(C.byref(self._ccfg()), self.state.data_ptr(), self.num_envs, None,
                                            d_seeds.data_ptr() if d_seeds is not None else None, rewind,
                                            self.obs.data_ptr(), self._stream()), "vmgym_reset")
@@ -183,7 +217,10 @@ class VecVmEnv:
                              d_terminated=self.terminated_u8.data_ptr(),
                              d_valid=self.valid.data_ptr() if want_valid else None,
                              d_action=self.agent_action.data_ptr() if want_action else None,
-                             d_stats=self.stats.data_ptr() if want_stats else None)
+                             d_stats=self.stats.data_ptr() if want_stats else None,
+                             d_vm_slots=self._vm_slots.data_ptr() if self._vm_slots is not None else None,
+                             d_vm_hist=self._vm_hist.data_ptr() if self._vm_slots is not None else None,
+                             d_vm_totals=self._vm_totals.data_ptr() if self._vm_slots is not None else None)
             self._out_cache[key] = out
         return out
 
@@ -211,7 +248,8 @@ class VecVmEnv:
             hout = self._out_cache.get(key)
             if hout is None:
                 hout = nv.Outputs(d_obs=out.d_obs, d_reward=rew_h.data_ptr(), d_terminated=term_h.data_ptr(), d_valid=out.d_valid,
-                                  d_action=None, d_stats=None)
+                                  d_action=None, d_stats=None, d_vm_slots=out.d_vm_slots, d_vm_hist=out.d_vm_hist,
+                                  d_vm_totals=out.d_vm_totals)
                 self._out_cache[key] = hout
             out = hout
         with self._on_device():
@@ -249,12 +287,42 @@ class VecVmEnv:
         c = self.counters()
         st = self.stats.cpu().numpy()
         steps = np.maximum(st[:, 7], 1.0)
-        return {"total rewards": c["episode_return"], "total served VMs": c["served_requests"], "total requests": c["total_requests"],
+        per_vm = self.vm_stats() if self._vm_slots is not None else {}
+        return {**per_vm, "total rewards": c["episode_return"], "total served VMs": c["served_requests"], "total requests": c["total_requests"],
                 "total cpu requested": c["total_cpu_requested"], "total memory requested": c["total_memory_requested"],
                 "total suspend actions": c["suspend_actions"], "total place actions": c["place_actions"],
                 "dropped requests": c["dropped_requests"], "drop rate": st[:, 0] / steps, "waiting ratio": st[:, 1] / steps,
                 "cpu mean": st[:, 2] / steps, "cpu var": st[:, 3] / steps, "memory mean": st[:, 4] / steps,
                 "memory var": st[:, 5] / steps, "rejected actions": st[:, 6], "steps": st[:, 7]}
+
+    # ---- Record's per-VM statistics (src/record.py:34-96,110-134) -------------------------------------------
+    def enable_vm_stats(self):
+        """Track, for every VM that occupies a slot, what Record derives from the V x T placement samples: pending rate,
+        slowdown rate and lifetime.  Takes effect from the next reset() (buffers are zeroed there); the step kernels keep
+        four clocks per slot and bin a VM's rates when it departs.  Steps then run through the generic kernel."""
+        if self._vm_slots is None:
+            N, V = self.num_envs, self.V
+            self._vm_slots = torch.zeros((N, V, 4), dtype=torch.int32, device=self.device)
+            self._vm_hist = torch.zeros((N, 2, nv.VMSTAT_BINS), dtype=torch.int32, device=self.device)
+            self._vm_totals = torch.zeros((N, 4), dtype=torch.int64, device=self.device)
+            self._out_cache.clear()
+        return self
+
+    def vm_stats(self):
+        """The per-VM keys of Record.get_summary for the episode so far, per env (float64 numpy arrays [N]): VMs that
+        departed plus the ones still in a slot (their sample list ends at the last step, as in Record)."""
+        if self._vm_slots is None:
+            raise RuntimeError("call enable_vm_stats() (before reset) first")
+        N = self.num_envs
+        hist = torch.empty_like(self._vm_hist)
+        totals = torch.empty_like(self._vm_totals)
+        with self._on_device():
+            nv.check(self._lib.vmgym_vmstats_finalize(C.byref(self._ccfg()), self.state.data_ptr(), N, self._vm_slots.data_ptr(),
+                                                      self._vm_hist.data_ptr(), self._vm_totals.data_ptr(), hist.data_ptr(),
+                                                      totals.data_ptr(), self._stream()), "vmgym_vmstats_finalize")
+        h = hist.cpu().numpy().astype(np.int64)
+        t = totals.cpu().numpy()
+        return vm_stats_from_histograms(h, t)
 
     def capture(self, fn, warmup: int = 2):
         """Capture `fn` (a callable issuing env calls with fixed arguments, e.g. one fused agent step) into a CUDA
