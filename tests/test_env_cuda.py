@@ -481,3 +481,53 @@ def test_host_vec_env_pipelined_equals_fused_device_rollout(use_graphs, zero_cop
     o2, _, _ = hv.step(act)
     ref.step(ref.vm_placement.clone())
     assert torch.equal(o2, ref.observe().cpu())
+
+
+# ---- the reference's sweep drivers as one batch per agent (vmgym.sweep) --------------------------------------------
+S100_BASE = dict(pms=100, vms=300, service_length=1000, arrival_rate=1.8182, training_steps=10000, eval_steps=100000, seed=0,
+                 reward_function="kl", cap_target_util=True, sequence="uniform", beta=0.5, allow_null_action=True)   # config/100.yml
+SUSPENSION_ROWS = [          # data/exp_suspension/data.csv of the reference, first-fit / best-fit rows
+    "bestfit,0.5,1000,9123,0,9223,993,0.002,0.000,0.000", "bestfit,0.6,1000,10879,0,10977,994,0.003,0.000,0.000",
+    "bestfit,0.7,1000,12592,0,12718,994,0.009,0.000,0.000", "bestfit,0.8,1000,13808,0,13943,983,0.073,0.000,0.000",
+    "bestfit,0.9,1000,13803,0,13937,983,0.069,0.000,0.000", "bestfit,1.0,100,137105,0,137243,98,0.062,0.000,0.000",
+    "bestfit,1.0,1000,13802,0,13935,983,0.072,0.000,0.000", "bestfit,1.0,1100,12523,0,12664,1080,0.072,0.000,0.000",
+    "bestfit,1.0,2100,6588,0,6731,2030,0.087,0.000,0.000", "bestfit,1.0,3100,4466,0,4603,2948,0.094,0.000,0.000",
+    "bestfit,1.0,4100,3376,0,3512,3840,0.107,0.000,0.000", "bestfit,1.1,1000,13853,0,13991,982,0.073,0.000,0.000",
+    "firstfit,0.5,1000,9123,0,9223,993,0.002,0.000,0.000", "firstfit,0.6,1000,10878,0,10976,994,0.004,0.000,0.000",
+    "firstfit,0.7,1000,12592,0,12716,994,0.025,0.000,0.000", "firstfit,0.8,1000,13362,0,13499,982,0.071,0.000,0.000",
+    "firstfit,0.9,1000,13368,0,13505,983,0.069,0.000,0.000", "firstfit,1.0,100,130390,0,130515,98,0.064,0.000,0.000",
+    "firstfit,1.0,1000,13367,0,13509,982,0.076,0.000,0.000", "firstfit,1.0,1100,12180,0,12313,1079,0.072,0.000,0.000",
+    "firstfit,1.0,2100,6404,0,6533,2028,0.095,0.000,0.000", "firstfit,1.0,3100,4332,0,4464,2944,0.101,0.000,0.000",
+    "firstfit,1.0,4100,3296,0,3422,3834,0.111,0.000,0.000", "firstfit,1.1,1000,13388,0,13527,982,0.069,0.000,0.000",
+]
+
+
+@pytest.mark.parametrize("agent", ["firstfit", "bestfit"])
+def test_suspension_sweep_reproduces_published_table(agent):
+    """exp_suspension.py's (load, service length) grid as ONE 12-env batch per agent: every printed digit of the 24
+    first-fit / best-fit rows of data/exp_suspension/data.csv (served, valid actions, mean life, pending, slowdown)."""
+    from vmgym.sweep import suspension_points, suspension_rows
+    pts = suspension_points(100, service_lengths=np.arange(100, 4200, 1000), loads=np.arange(0.5, 1.15, 0.1))
+    rows = suspension_rows(S100_BASE, agent, points=pts)
+    want = sorted(r for r in SUSPENSION_ROWS if r.startswith(agent))
+    assert sorted(rows) == want
+
+
+VM_SIZE_ROWS = {             # data/exp_vm_size/summary.csv of the reference (reward kl, seeds 0..4): lowuniform, highuniform
+    "firstfit": ["firstfit,22539.4184,0.1232,22602,0,0.8504,0.0179,0.8497,0.0180,0.2226",
+                 "firstfit,-73517.7000,0.2224,11454,0,0.7175,0.0435,0.7174,0.0437,0.5992"],
+    "bestfit": ["bestfit,51673.7852,0.1093,23057,0,0.8677,0.0189,0.8672,0.0190,0.2056",
+                "bestfit,-56063.0182,0.2159,11600,0,0.7267,0.0467,0.7266,0.0467,0.5939"],
+}
+
+
+@pytest.mark.parametrize("agent", ["firstfit", "bestfit"])
+def test_vm_size_sweep_reproduces_published_table(agent):
+    """exp_vm_size.py (lowuniform / highuniform size mixes, reward kl, 5 seeds averaged) through vmgym.sweep: all columns
+    as printed; the kl return (a sum of 500 000 log-containing rewards) to 2e-3 absolute."""
+    from vmgym.sweep import vm_size_rows
+    rows = vm_size_rows(S100_BASE, agent)
+    for got, want in zip(rows, VM_SIZE_ROWS[agent]):
+        g, w = got.split(","), want.split(",")
+        assert g[0] == w[0] and g[2:] == w[2:], (got, want)
+        assert abs(float(g[1]) - float(w[1])) <= 2e-3, (got, want)

@@ -167,3 +167,48 @@ def test_oracle_record_lists_match_reference_record(name):
     s = env.record_summary()
     for k, v in s.items():
         assert float(v) == g["summary"][k], k
+
+
+S100_BASE = dict(pms=100, vms=300, service_length=1000, arrival_rate=1.8182, training_steps=10000, eval_steps=100000, seed=0,
+                 reward_function="kl", cap_target_util=True, sequence="uniform", beta=0.5, allow_null_action=True)   # config/100.yml
+
+
+@pytest.mark.parametrize("row", ["firstfit,1.0,2100,6404,0,6533,2028,0.095,0.000,0.000",
+                                 "bestfit,0.8,1000,13808,0,13943,983,0.073,0.000,0.000"])
+def test_oracle_reproduces_exp_suspension_rows(row):
+    """data/exp_suspension/data.csv (exp_suspension.py:12-60: reward wr, arrival = round(pms/0.55/sl*load, 3), seed 0, 100 000
+    eval steps): served, valid actions, mean VM life, mean pending, mean / max slowdown — every printed digit; the best-fit
+    row only on numpy's scalar introsort tie order (SURVEY §8c ruling ii)."""
+    import vmoracle as vo
+    agent, load, sl, *_ = row.split(",")
+    c = dict(S100_BASE, reward_function="wr", service_length=int(sl),
+             arrival_rate=float(np.round(100 / 0.55 / int(sl) * float(load), 3)))
+    env = vo.OracleVmEnv(vo.OracleConfig(**c))
+    env.eval()
+    env.enable_record(100000, 400000)
+    env.reset(seed=c["seed"])
+    n, st = env.rollout(vo.AGENT_FIRSTFIT if agent == "firstfit" else vo.AGENT_BESTFIT, 100000,
+                        vo.TIE_STABLE if agent == "firstfit" else vo.TIE_NUMPY_INTROSORT)
+    assert n == 100000
+    p, s, life = env.record_lists()
+    got = "%s,%.1f,%d,%d,%d,%d,%d,%.3f,%.3f,%.3f" % (agent, float(load), int(sl), st["served"], st["suspend"],
+                                                     st["suspend"] + st["place"], np.mean(life), np.mean(p), np.mean(s), np.max(s))
+    assert got == row
+
+
+def test_oracle_reproduces_exp_vm_size_row():
+    """data/exp_vm_size/summary.csv:3 (first-fit, lowuniform sizes at arrival pms/0.375/sl, reward kl, seeds 0..4)."""
+    import vmoracle as vo
+    rows = []
+    for seed in range(5):
+        c = dict(S100_BASE, sequence="lowuniform", arrival_rate=100 / 0.375 / 1000, seed=seed)
+        env = vo.OracleVmEnv(vo.OracleConfig(**c))
+        env.eval()
+        env.reset(seed=seed)
+        n, st = env.rollout(vo.AGENT_FIRSTFIT, 100000, vo.TIE_STABLE)
+        rows.append(st)
+    m = lambda k: np.mean([r[k] for r in rows])                                          # noqa: E731
+    got = "firstfit,%.4f,%.4f,%d,%d,%.4f,%.4f,%.4f,%.4f,%.4f" % (
+        np.mean([np.round(r["return"], 3) for r in rows]), m("drop_rate_mean"), m("served"), m("suspend"), m("cpu_mean"),
+        m("cpu_var"), m("mem_mean"), m("mem_var"), m("waiting_ratio_mean"))
+    assert got == "firstfit,22539.4184,0.1232,22602,0,0.8504,0.0179,0.8497,0.0180,0.2226"

@@ -71,13 +71,17 @@ def pack_trace(per_env, n_steps: int):
 
 
 def sample_numpy_traces(cfg, streams, n_steps: int, n_adm: int | None, threads: int = 8):
-    def one(s):
-        return s.draw(cfg, n_steps, n_adm)
+    """`cfg`: one Config for all envs, or a list with one Config per env (sweeps over arrival_rate / service_length /
+    sequence mapped onto the batch axis: in pre-sampled mode those parameters only shape the traces)."""
+    cfgs = list(cfg) if isinstance(cfg, (list, tuple)) else [cfg] * len(streams)
+
+    def one(i):
+        return streams[i].draw(cfgs[i], n_steps, n_adm)
     if len(streams) > 4 and threads > 1:
         with ThreadPoolExecutor(threads) as ex:
-            per_env = list(ex.map(one, streams))
+            per_env = list(ex.map(one, range(len(streams))))
     else:
-        per_env = [one(s) for s in streams]
+        per_env = [one(i) for i in range(len(streams))]
     return pack_trace(per_env, n_steps)
 
 

@@ -62,7 +62,12 @@ def vm_stats_from_histograms(hist, totals):
 
 class VecVmEnv:
     def __init__(self, config: Config, num_envs: int, device="cuda", rng: str = "numpy", seeds=None,
-                 trace_steps: int | None = None, max_admissions: int | None = None, tiebreak: str = "stable"):
+                 trace_steps: int | None = None, max_admissions: int | None = None, tiebreak: str = "stable",
+                 env_configs=None):
+        """`env_configs`: optional list of num_envs Configs that may differ from `config` in arrival_rate,
+        service_length, sequence and seed only (rng="numpy"): each env draws its traces from its own parameters, so a
+        sweep over load / service length / VM size mix / seed is ONE batch (exp_suspension.py:75-85,
+        exp_vm_size.py:13-20, exp_performance.py:26,37 run one process per point)."""
         if not torch.cuda.is_available():
             raise nv.VmgymError("VecVmEnv needs a CUDA device (sm_100a); there is no CPU path")
         self.config = config.validate()
@@ -73,6 +78,17 @@ class VecVmEnv:
         self.rng_mode = rng
         if rng not in ("numpy", "philox"):
             raise ValueError("rng must be 'numpy' (reference-exact pre-sampled traces) or 'philox'")
+        self.env_configs = None
+        if env_configs is not None:
+            if rng != "numpy" or len(env_configs) != int(num_envs):
+                raise ValueError("env_configs needs rng='numpy' and one Config per env")
+            same = ("pms", "vms", "training_steps", "eval_steps", "reward_function", "cap_target_util", "beta", "allow_null_action")
+            for c in env_configs:
+                if any(getattr(c, k) != getattr(config, k) for k in same):
+                    raise ValueError(f"env_configs may only differ in arrival_rate / service_length / sequence / seed (not {same})")
+            self.env_configs = [c.validate() for c in env_configs]
+            if seeds is None:
+                seeds = [int(c.seed) for c in env_configs]
         self.tiebreak = tiebreak
         self.eval_mode = False
         self.P, self.V = int(config.pms), int(config.vms)
@@ -173,10 +189,10 @@ class VecVmEnv:
             if self.rng_mode == "numpy":
                 if not getattr(self, "_reseeded", False) and self._trace is not None:
                     pos = self._scalars_i32[:, 6:8].cpu().numpy().astype(np.int64)
-                    for s, (a, j) in zip(self._streams, pos):
-                        s.rewind_to(self.config, a, j)
+                    for i, (s, (a, j)) in enumerate(zip(self._streams, pos)):
+                        s.rewind_to(self.env_configs[i] if self.env_configs else self.config, a, j)
                 T = self._trace_steps or max(int(self.config.training_steps), int(self.config.eval_steps))
-                arr, adm = sample_numpy_traces(self.config, self._streams, T, self._max_admissions)
+                arr, adm = sample_numpy_traces(self.env_configs or self.config, self._streams, T, self._max_admissions)
                 d_arr = torch.from_numpy(arr.view(np.int16)).to(self.device)
                 d_adm = torch.from_numpy(adm.view(np.int32)).to(self.device)
                 self._trace_tensors = (d_arr, d_adm)
@@ -276,7 +292,9 @@ class VecVmEnv:
         (src/record.py:110-134) and the columns of the published tables (exp_performance.py:104-147) accumulated in the
         kernel.  Returns a dict of numpy arrays [N]."""
         self.eval(True)
-        self.reset(seed=self.config.seed + np.arange(self.num_envs) if seeds is None else np.asarray(seeds, np.int64))
+        if seeds is None:
+            seeds = [int(c.seed) for c in self.env_configs] if self.env_configs else self.config.seed + np.arange(self.num_envs)
+        self.reset(seed=np.asarray(seeds, np.int64))
         limit = int(self.config.eval_steps)
         done = 0
         while done < limit:
