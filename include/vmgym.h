@@ -235,6 +235,17 @@ int vmgym_segtree_retrieve(const double* d_sum_tree, int64_t capacity, const dou
  * (cp.async.bulk) on/off.  For experiments; defaults are chosen per config. */
 int vmgym_set_tuning(int warps_per_cta, int use_bulk_copy);
 
+/* PrioritizedReplayBuffer.sample_batch (src/agents/drlvmp.py:178-241, src/segment_tree.py:35-62,103-118): stratified
+ * proportional sampling from the sum tree with caller-supplied uniforms d_u[batch] in [0, 1) (the reference draws
+ * random.uniform(a, b) = a + (b - a) * u), plus the importance weights.  len = number of stored transitions. */
+int vmgym_per_sample(const double* d_sum_tree, const double* d_min_tree, int64_t capacity, int64_t len, int32_t batch,
+                     const double* d_u, double beta, int64_t* d_idx_out, double* d_weight_out, void* stream);
+
+/* Categorical-DQN target projection (src/agents/drlvmp.py:676-699): d_next_dist [n, atoms] (the target net's distribution of
+ * the double-DQN action), d_reward f32[n], d_done i32[n], d_support f32[atoms] -> d_proj f32[n, atoms]. */
+int vmgym_c51_project(const float* d_next_dist, const float* d_reward, const int32_t* d_done, const float* d_support,
+                      float gamma, float v_min, float v_max, int32_t atoms, int64_t n, float* d_proj, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,3 +98,110 @@ def test_device_segment_trees_match_reference():
         assert np.array_equal(got, g["st_ret"][b]), b
     with pytest.raises(AssertionError):
         DeviceSegmentTrees(1000)
+
+
+# ---- training internals (vmgym/drlvmp_train.py) against golden vectors from the reference classes ---------------------
+def _train_golden():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "drlvmp_train.npz"))
+
+
+@pytest.mark.gpu
+def test_c51_loss_matches_reference():
+    """_compute_dqn_loss (drlvmp.py:661-706) for the 1-step and the n-step gamma: projection kernel + torch layers vs the
+    reference agent's own losses (float32: 2e-5 relative, 1e-6 absolute — the projection itself is checked exactly below)."""
+    import torch
+    from vmgym.drlvmp import Network
+    from vmgym.drlvmp_train import c51_project, dqn_loss
+    z = _train_golden()
+    support = torch.linspace(0.0, 200.0, 51, device="cuda")
+    nets = {}
+    for name in ("dqn", "tgt"):
+        net = Network(110, 24, 4, 51, support).cuda()
+        net.load_state_dict({k[len(f"c51_{name}."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(f"c51_{name}.")})
+        nets[name] = net
+    samples = {k: torch.from_numpy(z["c51_" + k]).cuda() for k in ("obs", "next_obs", "acts", "rews", "done")}
+    for tag in ("g1", "g3"):
+        loss = dqn_loss(nets["dqn"], nets["tgt"], samples, float(z["c51_gamma_" + tag]), 0.0, 200.0)
+        assert torch.allclose(loss.cpu(), torch.from_numpy(z["c51_loss_" + tag]), rtol=2e-5, atol=1e-6), tag
+    assert float(loss[3].detach()) == 0.0   # reward 250: every atom clamps onto the top grid point and the mass is dropped (:683-699)
+    # the projection alone, bit for bit against the reference's formula evaluated by torch on the CPU
+    g = torch.Generator().manual_seed(9)
+    B, A = 257, 51
+    nd = torch.softmax(torch.randn(B, A, generator=g), -1).clamp(min=1e-3)
+    rew = (torch.rand(B, generator=g) * 260 - 20).float()
+    rew[:40] = torch.arange(40).float() * 4.0                                # integral b values
+    done = (torch.rand(B, generator=g) < 0.3).int()
+    sup = torch.linspace(0.0, 200.0, A)
+    for gamma in (0.99, 0.99 ** 3):
+        t_z = (rew.reshape(-1, 1) + (1 - done.reshape(-1, 1)) * gamma * sup).clamp(min=0.0, max=200.0)
+        b = (t_z - 0.0) / (200.0 / (A - 1))
+        lo, up = b.floor().long(), b.ceil().long()
+        off = torch.linspace(0, (B - 1) * A, B).long().unsqueeze(1).expand(B, A)
+        want = torch.zeros(B, A)
+        want.view(-1).index_add_(0, (lo + off).view(-1), (nd * (up.float() - b)).view(-1))
+        want.view(-1).index_add_(0, (up + off).view(-1), (nd * (b - lo.float())).view(-1))
+        got = c51_project(nd.cuda(), rew.cuda(), done.cuda(), sup.cuda(), gamma, 0.0, 200.0).cpu()
+        assert torch.equal(got, want), gamma
+
+
+@pytest.mark.gpu
+def test_n_step_buffer_matches_reference():
+    """ReplayBuffer.store / _get_n_step_info (drlvmp.py:46-113), one env: the ring contents after 40 transitions with dones."""
+    import torch
+    from vmgym.drlvmp_train import NStepReplay
+    z = _train_golden()
+    rb = NStepReplay(4, 32, num_envs=1, n_step=3, gamma=0.99)
+    obs = torch.from_numpy(z["ns_obs"]).cuda()
+    for t in range(z["ns_acts"].size):
+        rb.store(obs[t:t + 1], torch.tensor([int(z["ns_acts"][t])], device="cuda"), torch.tensor([z["ns_rews"][t]], device="cuda"),
+                 obs[t + 1:t + 2], torch.tensor([bool(z["ns_dones"][t])], device="cuda"))
+    assert rb.ptr == int(z["ns_ptr"]) and rb.size == int(z["ns_size"])
+    assert torch.equal(rb.obs_buf.cpu(), torch.from_numpy(z["ns_obs_buf"]))
+    assert torch.equal(rb.next_obs_buf.cpu(), torch.from_numpy(z["ns_next_obs_buf"]))
+    assert torch.equal(rb.acts_buf.cpu(), torch.from_numpy(z["ns_acts_buf"]))
+    assert torch.equal(rb.rews_buf.cpu(), torch.from_numpy(z["ns_rews_buf"]))
+    assert torch.equal(rb.done_buf.cpu(), torch.from_numpy(z["ns_done_buf"]))
+
+
+@pytest.mark.gpu
+def test_prioritized_replay_matches_reference():
+    """PrioritizedReplayBuffer (drlvmp.py:118-241): stratified sampling with the reference's uniforms picks the same
+    indices, importance weights agree to 1e-12, priorities / max_priority / tree sums evolve identically."""
+    import torch
+    from vmgym.drlvmp_train import PrioritizedReplay
+    z = _train_golden()
+    per = PrioritizedReplay(4, 48, num_envs=1, alpha=float(z["per_alpha"]))
+    o = torch.zeros(1, 4, device="cuda")
+    for t in range(int(z["per_n"])):
+        per.store(o, torch.tensor([1], device="cuda"), torch.tensor([0.0], device="cuda"), o, torch.tensor([False], device="cuda"))
+    for r in range(z["per_u"].shape[0]):
+        s = per.sample_batch(8, beta=0.5 + 0.05 * r, u=z["per_u"][r])
+        assert np.array_equal(s["indices"].cpu().numpy(), z["per_idx"][r]), r
+        assert np.allclose(s["weights"].cpu().numpy(), z["per_w"][r], rtol=1e-12, atol=0), r
+        per.update_priorities(s["indices"], torch.from_numpy(z["per_upd_pri"][r]))
+    assert float(per.max_priority) == float(z["per_max_priority"])
+    # priority ** alpha is CUDA's fp64 pow here and libm's in the reference: 2 ulp
+    assert float(per.trees.sum()) == pytest.approx(float(z["per_sum"]), rel=1e-14)
+    assert float(per.trees.min()) == pytest.approx(float(z["per_min"]), rel=1e-14)
+
+
+@pytest.mark.gpu
+def test_drlvmp_learn_runs_and_updates():
+    """DRLVMPAgent.learn over a batch of envs: buffers fill, losses are finite, the online net changes, the target net is
+    synchronised every target_update optimisation steps."""
+    import torch
+    from vmgym import Config, VecVmEnv
+    from vmgym.drlvmp import DRLVMPAgent, DRLVMPConfig
+    kw = dict(pms=10, vms=30, arrival_rate=0.4, service_length=30, training_steps=60, eval_steps=100, reward_function="wr",
+              allow_null_action=True)
+    vec = VecVmEnv(Config(**kw), 8, rng="philox")
+    torch.manual_seed(0)
+    agent = DRLVMPAgent(vec, DRLVMPConfig(hidden_size=32, batch_size=16, memory_size=512, episodes=2, n_step=3, target_update=5))
+    before = [p.detach().clone() for p in agent.dqn.parameters()]
+    returns = agent.learn(episodes=2)
+    tr = agent.trainer
+    assert returns.shape == (2, 8) and np.isfinite(returns).all()
+    assert len(tr.memory) == len(tr.memory_n) == min(512, 8 * (2 * 60 - 2))
+    assert len(tr.losses) > 50 and all(torch.isfinite(l) for l in tr.losses)
+    assert any(not torch.equal(a, b) for a, b in zip(agent.dqn.parameters(), before))
+    assert vec.counters()["place_actions"].sum() > 0

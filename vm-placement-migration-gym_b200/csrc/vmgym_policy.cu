@@ -576,3 +576,124 @@ extern "C" int vmgym_segtree_retrieve(const double* d_sum_tree, int64_t capacity
     if (err != cudaSuccess) return pfail(VMGYM_ECUDA, cudaGetErrorString(err));
     return VMGYM_OK;
 }
+
+namespace vmgym {
+
+// SegmentTree.operate(start, end) (segment_tree.py:35-62): the recursive range query with its own association order
+// (left part `op` right part), so that a range sum is the same fp64 value as the reference's.  `end` is INCLUSIVE here
+// (operate() has already done `end -= 1`).  Depth <= log2(capacity); one thread.
+__device__ double segtree_range(const double* tree, long long start, long long end, long long node, long long node_start,
+                                long long node_end, int is_min)
+{
+    if (start == node_start && end == node_end) return tree[node];
+    const long long mid = (node_start + node_end) / 2;
+    if (end <= mid) return segtree_range(tree, start, end, 2 * node, node_start, mid, is_min);
+    if (mid + 1 <= start) return segtree_range(tree, start, end, 2 * node + 1, mid + 1, node_end, is_min);
+    const double a = segtree_range(tree, start, mid, 2 * node, node_start, mid, is_min);
+    const double b = segtree_range(tree, mid + 1, end, 2 * node + 1, mid + 1, node_end, is_min);
+    return is_min ? fmin(a, b) : a + b;
+}
+
+// PrioritizedReplayBuffer.sample_batch (drlvmp.py:178-241): stratified proportional sampling + importance weights.
+//   p_total = sum_tree.sum(0, len - 1)   -> operate() turns that into the INCLUSIVE range [0, len - 2] (segment_tree.py:55-59):
+//                                           the newest element is left out of the total, as in the reference
+//   upperbound_i = a + (b - a) * u_i,  a = segment * i,  b = segment * (i + 1),  segment = p_total / batch      (:216-224)
+//   weight_i = (leaf_i / sum * len)^-beta / (min / sum * len)^-beta                                             (:229-241)
+__global__ void per_sample_kernel(const double* sum_tree, const double* min_tree, long long capacity, long long len, int batch,
+                                  const double* u, double beta, long long* idx_out, double* w_out)
+{
+    __shared__ double s_total;
+    if (threadIdx.x == 0) {
+        long long end = len - 1;
+        if (end <= 0) end += capacity;
+        end -= 1;
+        s_total = segtree_range(sum_tree, 0, end, 1, 0, capacity - 1, 0);
+    }
+    __syncthreads();
+    const double segment = s_total / (double)batch;
+    const double sum_all = sum_tree[1], min_all = min_tree[1];
+    const double max_weight = pow(min_all / sum_all * (double)len, -beta);
+    for (int i = threadIdx.x; i < batch; i += blockDim.x) {
+        const double a = segment * (double)i, b = segment * (double)(i + 1);
+        double ub = a + (b - a) * u[i];
+        long long node = 1;
+        while (node < capacity) {                                        // retrieve (segment_tree.py:103-118)
+            const long long left = 2 * node;
+            const double l = sum_tree[left];
+            if (l > ub) node = left;
+            else { ub -= l; node = left + 1; }
+        }
+        idx_out[i] = node - capacity;
+        w_out[i] = pow(sum_tree[node] / sum_all * (double)len, -beta) / max_weight;
+    }
+}
+
+// Categorical-DQN projection (drlvmp.py:676-699), float32 like the reference: for sample i and atom j
+//   t_z = clamp(r + (1 - done) * gamma * z_j, v_min, v_max);  b = (t_z - v_min) / delta_z;  l = floor(b), u = ceil(b)
+//   proj[l] += p_j * (u - b)   (first index_add_, j ascending)   then   proj[u] += p_j * (b - l)   (second index_add_)
+// When b is integral l == u and both weights are 0 — that probability mass is dropped, as in the reference.
+// One warp per sample; each output atom gathers its contributions in j order = the order of the reference's sequential
+// index_add_ on the CPU (deterministic, no atomics).
+__global__ void c51_project_kernel(const float* next_dist, const float* reward, const int* done, const float* support,
+                                   float gamma, float v_min, float v_max, float delta_z, int atoms, long long n, float* proj)
+{
+    extern __shared__ float c51s[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const long long i = (long long)blockIdx.x * wpc + warp;
+    if (i >= n) return;
+    float* lo_w = c51s + (size_t)warp * 4 * atoms;        // p_j * (u - b)
+    float* up_w = lo_w + atoms;                            // p_j * (b - l)
+    int* lo_i = reinterpret_cast<int*>(up_w + atoms);
+    int* up_i = lo_i + atoms;
+    const float r = reward[i];
+    const float ndg = (float)(1 - done[i]) * gamma;        // (1 - done) * gamma
+    const float* pd = next_dist + i * atoms;
+    for (int j = lane; j < atoms; j += 32) {
+        float tz = r + ndg * support[j];
+        tz = fminf(fmaxf(tz, v_min), v_max);
+        const float b = (tz - v_min) / delta_z;
+        const float l = floorf(b), u = ceilf(b);
+        lo_i[j] = (int)l; up_i[j] = (int)u;
+        lo_w[j] = pd[j] * (u - b);
+        up_w[j] = pd[j] * (b - l);
+    }
+    __syncwarp();
+    for (int k = lane; k < atoms; k += 32) {
+        float acc = 0.f;
+        for (int j = 0; j < atoms; j++) if (lo_i[j] == k) acc += lo_w[j];
+        for (int j = 0; j < atoms; j++) if (up_i[j] == k) acc += up_w[j];
+        proj[i * atoms + k] = acc;
+    }
+}
+
+}  // namespace vmgym
+
+extern "C" int vmgym_per_sample(const double* d_sum_tree, const double* d_min_tree, int64_t capacity, int64_t len, int32_t batch,
+                                const double* d_u, double beta, int64_t* d_idx_out, double* d_weight_out, void* stream)
+{
+    if (!d_sum_tree || !d_min_tree || !d_u || !d_idx_out || !d_weight_out || batch < 0 || len < 1 || capacity < 1 ||
+        (capacity & (capacity - 1)) || len > capacity)
+        return pfail(VMGYM_EINVAL, "prioritized replay: bad operand");
+    if (batch == 0) return VMGYM_OK;
+    per_sample_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(d_sum_tree, d_min_tree, capacity, len, batch, d_u, beta,
+                                                         (long long*)d_idx_out, d_weight_out);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return pfail(VMGYM_ECUDA, cudaGetErrorString(err));
+    return VMGYM_OK;
+}
+
+extern "C" int vmgym_c51_project(const float* d_next_dist, const float* d_reward, const int32_t* d_done, const float* d_support,
+                                 float gamma, float v_min, float v_max, int32_t atoms, int64_t n, float* d_proj, void* stream)
+{
+    if (!d_next_dist || !d_reward || !d_done || !d_support || !d_proj || atoms < 2 || atoms > 1024 || n < 0 || !(v_max > v_min))
+        return pfail(VMGYM_EINVAL, "c51 projection: bad operand");
+    if (n == 0) return VMGYM_OK;
+    const int wpc = 4;
+    const size_t smem = (size_t)wpc * 4 * atoms * sizeof(float);
+    const float delta_z = (float)((double)(v_max - v_min) / (double)(atoms - 1));        // drlvmp.py:672, python float -> float32
+    c51_project_kernel<<<(unsigned)((n + wpc - 1) / wpc), wpc * 32, smem, (cudaStream_t)stream>>>(
+        d_next_dist, d_reward, d_done, d_support, gamma, v_min, v_max, delta_z, atoms, n, d_proj);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return pfail(VMGYM_ECUDA, cudaGetErrorString(err));
+    return VMGYM_OK;
+}

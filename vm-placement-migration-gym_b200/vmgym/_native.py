@@ -67,7 +67,7 @@ SCALARS_BYTES = 80
 EXPORTS = ["vmgym_last_error", "vmgym_abi_version", "vmgym_get_layout", "vmgym_reset", "vmgym_step",
            "vmgym_agent_step", "vmgym_agent_act", "vmgym_observe", "vmgym_invalid_action_mask", "vmgym_set_tuning",
            "vmgym_policy_heads", "vmgym_policy_heads_backward", "vmgym_gae", "vmgym_drlvmp_choice", "vmgym_linear_bf16", "vmgym_policy_fused", "vmgym_segtree_update",
-           "vmgym_segtree_retrieve", "vmgym_vmstats_finalize"]
+           "vmgym_segtree_retrieve", "vmgym_vmstats_finalize", "vmgym_per_sample", "vmgym_c51_project"]
 
 
 class VmgymError(RuntimeError):
@@ -114,6 +114,10 @@ def lib():
     L.vmgym_agent_act.argtypes = [C.POINTER(Config), i32, i32, vp, i64, vp, i32, vp]
     L.vmgym_observe.argtypes = [C.POINTER(Config), vp, i64, vp, vp]
     L.vmgym_invalid_action_mask.argtypes = [C.POINTER(Config), vp, i64, vp, vp]
+    L.vmgym_per_sample.restype = i32
+    L.vmgym_per_sample.argtypes = [vp, vp, i64, i64, i32, vp, C.c_double, vp, vp, vp]
+    L.vmgym_c51_project.restype = i32
+    L.vmgym_c51_project.argtypes = [vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, i32, i64, vp, vp]
     L.vmgym_vmstats_finalize.restype = i32
     L.vmgym_vmstats_finalize.argtypes = [C.POINTER(Config), vp, i64, vp, vp, vp, vp, vp, vp]
     L.vmgym_set_tuning.argtypes = [i32, i32]

@@ -4,8 +4,8 @@ written into the observation copy (PM loads are NOT updated, drlvmp.py:557-565) 
 
 State-dict keys mirror the reference's modules (`feature_layer.0.*`, `advantage_hidden_layer.weight_mu` ...), with or
 without the `_orig_mod.` prefix of torch.compile, so reference checkpoints load.  The heuristic selection runs in the
-`vmgym_drlvmp_choice` kernel; the network layers run through torch.  Training internals (PER segment trees, n-step
-buffer, C51 projection) are not part of this round."""
+`vmgym_drlvmp_choice` kernel; the network layers run through torch.  Training internals (n-step buffer, prioritized
+replay on the device segment trees, C51 projection kernel, batched learn loop) live in vmgym/drlvmp_train.py."""
 from __future__ import annotations
 
 import ctypes as C
@@ -115,8 +115,11 @@ class DRLVMPAgent:
     def eval(self, mode=True):
         self.dqn.train(not mode)
 
-    def learn(self):
-        raise NotImplementedError("DRL-VMP training (PER, n-step, C51 projection) is not part of this round; see DESIGN.md §9")
+    def learn(self, episodes: int | None = None, max_steps: int | None = None, updates_per_step: int = 1):
+        """drlvmp.py:433-500 over all envs of the batch (vmgym/drlvmp_train.py)."""
+        from .drlvmp_train import DRLVMPTrainer
+        self.trainer = DRLVMPTrainer(self, updates_per_step=updates_per_step)
+        return self.trainer.learn(episodes=episodes, max_steps=max_steps)
 
     def save_model(self, modelpath):
         if modelpath:
