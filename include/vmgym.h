@@ -232,7 +232,7 @@ int vmgym_segtree_retrieve(const double* d_sum_tree, int64_t capacity, const dou
                            void* stream);
 
 /* Tuning knobs (process-wide): warps per CTA of the step kernels (0 = auto) and bulk-async record copies
- * (cp.async.bulk) on/off.  For experiments; defaults are chosen per config. */
+ * (cp.async.bulk): use_bulk_copy bit 0 = loads, bit 1 = stores (default 3).  For experiments. */
 int vmgym_set_tuning(int warps_per_cta, int use_bulk_copy);
 
 /* PrioritizedReplayBuffer.sample_batch (src/agents/drlvmp.py:178-241, src/segment_tree.py:35-62,103-118): stratified

@@ -22,7 +22,7 @@ namespace vmgym {
 // ---------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 static int g_warps_per_cta = 0;
-static int g_use_bulk = 1;
+static int g_use_bulk = 3;      // bit 0: bulk-async record loads, bit 1: bulk-async record stores
 
 static int fail(int code, const char* fmt, const char* detail = "")
 {
@@ -188,7 +188,7 @@ int vmgym_set_tuning(int warps_per_cta, int use_bulk_copy)
 {
     if (warps_per_cta < 0 || warps_per_cta > 4) return fail(VMGYM_EINVAL, "warps_per_cta must be 0..4");
     g_warps_per_cta = warps_per_cta;
-    g_use_bulk = use_bulk_copy ? 1 : 0;
+    g_use_bulk = use_bulk_copy & 3;
     return VMGYM_OK;
 }
 

@@ -25,7 +25,7 @@ struct StepParams {
     int action_dtype;
     vmgym_outputs out;
     int agent, tiebreak, n_steps;
-    int use_bulk;             // stage records with cp.async.bulk (1) or 128-bit loads/stores (0)
+    int use_bulk;             // bit 0: load records with cp.async.bulk, bit 1: store them with cp.async.bulk (else 128-bit ld/st)
 };
 
 constexpr uint32_t STATUS_EXHAUSTED = 1u;   // pre-sampled trace ran out (the reference would raise, env.py:282)
@@ -867,7 +867,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     unsigned char* base = smem + L.sm_tables + (size_t)warp * L.sm_stride;
     uint64_t* bar = reinterpret_cast<uint64_t*>(base + L.sm_bar);
-    const bool BULK = p.use_bulk != 0;
+    const bool BULK = (p.use_bulk & 1) != 0, BULK_ST = (p.use_bulk & 2) != 0;
     const long long stride = (long long)gridDim.x * wpc;
     const long long env0 = (long long)blockIdx.x * wpc + warp;
     // Start staging this warp's first record before anything else: the bulk copy only needs the warp's own mbarrier, so
@@ -1014,7 +1014,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
         }
 
         // ---- write the record back ----
-        if (BULK) {
+        if (BULK_ST) {
             fence_proxy_async();          // generic-proxy writes to smem -> visible to the async proxy
             __syncwarp();
             if (lane == 0) {
@@ -1025,6 +1025,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
             __syncwarp();
         } else {
             copy16(grec, base, L.rec_bytes, lane);
+            if (BULK) fence_proxy_async();        // generic-proxy reads of smem before the next record's async-proxy write
         }
     }
 }
