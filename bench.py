@@ -273,10 +273,10 @@ def gpu_arm(args):
     ppo = None
     if not args.no_extras:
         from vmgym.ppo import PPOAgent, PPOConfig
-        Np, Tp = 512, 16
+        Np, Tp = args.ppo_envs, 16
         vp = VecVmEnv(Config(**cfg), Np, device=dev, rng="philox", seeds=cfg["seed"] + 2 * 10**6 + rank * Np + np.arange(Np, dtype=np.int64))
         torch.set_float32_matmul_precision("high")      # as the reference does (main.py:45): TF32 for the fp32 layers
-        agent_p = PPOAgent(vp, PPOConfig(hidden_size=512, batch_size=Tp, minibatch_size=Tp // 4, episodes=1, env_chunk=512,
+        agent_p = PPOAgent(vp, PPOConfig(hidden_size=512, batch_size=Tp, minibatch_size=Tp // 4, episodes=1, env_chunk=32768,
                                          masked=True, kl_max=1e9, fused_rollout=True))
         if world > 1:
             for p_ in agent_p.model.parameters():
@@ -366,8 +366,10 @@ def gpu_arm(args):
                               "note": "same kernel and timing protocol, 8x the envs (10 timed steps, 100 apart)"}
     if ppo:
         out["ppo_train"] = {"value": world * ppo["env_steps"] / ppo["seconds"], "unit": "PPO train env-steps/s",
-                            "config": "config/100.yml, 512 envs/GPU, rollout T=16, k_epochs=4, 4 minibatches, H=512, "
-                                      "rollout: fused tcgen05 actor head (bf16), update: cuBLAS TF32 layers + masked-heads/GAE kernels",
+                            "config": f"config/100.yml, {args.ppo_envs} envs/GPU (BASELINE config 4's per-GPU share), rollout T=16 "
+                                      "(reference batch_size 100 shortened to bound the bench), k_epochs=4, 4 sequential minibatches, H=512, "
+                                      "rollout: fused tcgen05 actor head (bf16), update: cuBLAS TF32 layers + masked-heads/GAE kernels, "
+                                      "NCCL gradient all-reduce per optimiser step when N > 1",
                             "seconds": ppo["seconds"]}
         out["ppo_eval"] = {"value": world * E / (ppo["eval_ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": ppo["eval_ms_per_step"],
                            "config": f"config/100.yml PPO evaluation rollouts, {E} envs/GPU, reference-shaped MLP (H=512, random init: the "
@@ -413,6 +415,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (per batch)")
+    ap.add_argument("--ppo-envs", type=int, default=8192, help="envs per GPU of the ppo_train extra")
     ap.add_argument("--bulk", type=int, default=None, help="vmgym_set_tuning use_bulk_copy bits (experiments)")
     ap.add_argument("--e2e-groups", type=int, default=8, help="env groups (streams) of the host-buffer e2e loop")
     ap.add_argument("--batches", type=int, default=20, help="independent env batches the timed launches rotate over")

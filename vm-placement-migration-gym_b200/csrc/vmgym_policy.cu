@@ -76,7 +76,8 @@ __device__ __forceinline__ unsigned row_invalid_bits(const unsigned char* rec, c
 
 // One CTA per env; each warp walks rows v = warp, warp + W, ...  Per row: mask (+ gating), log-softmax, entropy,
 // Gumbel-max sample or evaluation of a given action.  Per-env sums are reduced in a fixed order (deterministic).
-template <typename PT, bool BACKWARD>
+// NIC: compile-time number of 32-column groups per row (0 = run time, <= 8) so that the per-lane arrays stay in registers
+template <typename PT, bool BACKWARD, int NIC>
 __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
 {
     extern __shared__ __align__(16) unsigned char hs[];
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
     }
     __syncthreads();
     const int W = (A + 31) / 32;                  // mask words per row
-    const int NI = W;                             // columns per lane
+    const int NI = NIC ? NIC : W;                 // columns per lane
     float lp_sum = 0.f, ent_sum = 0.f;
     const float glp = BACKWARD ? p.g_logprob[env] : 0.f, gent = BACKWARD ? p.g_entropy[env] : 0.f;
     for (int v = warp; v < V; v += nwarps) {
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
             if (rec) inv = row_invalid_bits<PT>(rec, L, s_cpu, s_mem, v, lane, A);
             else if (p.mask_in) {
                 const uint32_t* mw = p.mask_in + (env * V + v) * (long long)W;
-                for (int i = 0; i < NI; i++) inv |= ((mw[i] >> lane) & 1u) << i;
+                _Pragma("unroll") for (int i = 0; i < 8; i++) if (i < NI) inv |= ((mw[i] >> lane) & 1u) << i;
             }
         }
         if (p.migration_ratio >= 0.f && rec) {
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
         }
         if (p.mask_out) {
             uint32_t* mo = p.mask_out + (env * V + v) * (long long)W;
-            for (int i = 0; i < NI; i++) {
+            _Pragma("unroll") for (int i = 0; i < 8; i++) if (i < NI) {
                 const unsigned word = __ballot_sync(FULL, (inv >> i) & 1u);
                 if (lane == 0) mo[i] = word;
             }
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
         const float* z = p.logits + (env * V + v) * (long long)A;
         float zl[8];
         float mx = -INFINITY;
-        for (int i = 0; i < NI; i++) {
+        _Pragma("unroll") for (int i = 0; i < 8; i++) if (i < NI) {
             const int a = i * 32 + lane;
             float x = -INFINITY;
             if (a < A) x = ((inv >> i) & 1u) ? MASK_LOGIT : z[a];
@@ -142,18 +143,24 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
             mx = fmaxf(mx, x);
         }
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
-        float se = 0.f;
-        for (int i = 0; i < NI; i++) se += (i * 32 + lane < A) ? expf(zl[i] - mx) : 0.f;
-        for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(FULL, se, o);
-        const float lse = mx + logf(se);
-        float ent = 0.f;
-        for (int i = 0; i < NI; i++) {
+        // one exponential per element: e = exp(z - max);  p = e / S;  log p = (z - max) - log S;
+        // entropy = -sum p log p = log S - (sum e (z - max)) / S        (masked columns: e = 0, contribute 0)
+        float el[8];
+        float se = 0.f, sez = 0.f;
+        _Pragma("unroll") for (int i = 0; i < 8; i++) if (i < NI) {
+            float e = 0.f;
             if (i * 32 + lane < A) {
-                const float l = zl[i] - lse, pr = expf(l);
-                ent -= pr * l;                                   // Categorical.entropy: -sum p * logp (0 for masked)
+                const float d = zl[i] - mx;
+                e = __expf(d);
+                sez += e * d;
             }
+            el[i] = e;
+            se += e;
         }
-        for (int o = 16; o > 0; o >>= 1) ent += __shfl_xor_sync(FULL, ent, o);
+        for (int o = 16; o > 0; o >>= 1) { se += __shfl_xor_sync(FULL, se, o); sez += __shfl_xor_sync(FULL, sez, o); }
+        const float log_se = logf(se), inv_se = 1.0f / se;
+        const float lse = mx + log_se;
+        const float ent = log_se - sez * inv_se;               // Categorical.entropy (0 contribution from masked columns)
         // ---- action: given or Gumbel-max sample ----
         int act;
         if (p.action_in) {
@@ -162,7 +169,7 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
         } else {
             float best = -INFINITY;
             int besta = 0;
-            for (int i = 0; i < NI; i++) {
+            _Pragma("unroll") for (int i = 0; i < 8; i++) if (i < NI) {
                 const int a = i * 32 + lane;
                 if (a < A) {
                     const Philox4 r = sample_block(v, a >> 2, (uint32_t)env, p.seed, (uint32_t)p.counter);
@@ -180,16 +187,21 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
             if (p.action_out && lane == 0) reinterpret_cast<PT*>(p.action_out)[env * V + v] = (PT)act;
         }
         float lpa = 0.f;
-        if ((unsigned)act < (unsigned)A) lpa = __shfl_sync(FULL, zl[act >> 5], act & 31) - lse;
+        if ((unsigned)act < (unsigned)A) {
+            // z[act] again from memory (a broadcast L1 hit) rather than zl[act >> 5]: a dynamic index would push the
+            // per-lane arrays into local memory
+            const unsigned inv_a = __shfl_sync(FULL, inv, act & 31);
+            lpa = (((inv_a >> (act >> 5)) & 1u) ? MASK_LOGIT : z[act]) - lse;
+        }
         lp_sum += lpa;
         ent_sum += ent;
         if (BACKWARD) {
             // d(sum logprob)/dz_j = [j == a] - p_j ; d(sum entropy)/dz_j = -p_j (logp_j + H); masked columns get 0
             float* gz = p.g_logits + (env * V + v) * (long long)A;
-            for (int i = 0; i < NI; i++) {
+            _Pragma("unroll") for (int i = 0; i < 8; i++) if (i < NI) {
                 const int a = i * 32 + lane;
                 if (a < A) {
-                    const float l = zl[i] - lse, pr = expf(l);
+                    const float l = zl[i] - lse, pr = el[i] * inv_se;
                     float g = glp * ((a == act ? 1.f : 0.f) - pr) - gent * pr * (l + ent);
                     if ((inv >> i) & 1u) g = 0.f;
                     gz[a] = g;
@@ -203,6 +215,101 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
         if (threadIdx.x == 0) {
             float a = 0.f, b = 0.f;
             for (int w = 0; w < nwarps; w++) { a += s_part[w]; b += s_part[nwarps + w]; }
+            if (p.logprob) p.logprob[env] = a;
+            if (p.entropy) p.entropy[env] = b;
+        }
+    }
+}
+
+// Evaluate-mode heads (the PPO update: log-prob / entropy of STORED actions under a PACKED mask, and their backward)
+// with 8 lanes per VM row and 4 rows per warp in flight: a row of A <= 128 logits is 4 x 32-byte segments per load
+// instruction, reductions take 3 shuffle steps instead of 5, and four independent rows hide each other's latency.
+// Same arithmetic per row as heads_kernel (one exponential per element); per-env sums are reduced in a fixed order.
+template <typename PT, bool BACKWARD, int NEL>
+__global__ void __launch_bounds__(256) heads_eval_kernel(const HeadParams p)
+{
+    __shared__ float s_part[2][8];
+    const int V = p.L.V, A = p.L.A;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int sub = lane & 7, grp = lane >> 3;
+    const long long env = blockIdx.x;
+    const int W = (A + 31) / 32;
+    float lp_sum = 0.f, ent_sum = 0.f;
+    const float glp = BACKWARD ? p.g_logprob[env] : 0.f, gent = BACKWARD ? p.g_entropy[env] : 0.f;
+    const unsigned char* arow = reinterpret_cast<const unsigned char*>(p.action_in) + env * (long long)V * dtype_bytes(p.action_dtype);
+    for (int v0 = warp * 4; v0 < V; v0 += nwarps * 4) {
+        const int v = v0 + grp;
+        const bool live = v < V;
+        const float* z = p.logits + (env * V + (live ? v : 0)) * (long long)A;
+        uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+        if (p.masked && p.mask_in && live) {
+            const uint32_t* mw = p.mask_in + (env * V + v) * (long long)W;
+            m0 = mw[0];
+            if (W > 1) m1 = mw[1];
+            if (W > 2) m2 = mw[2];
+            if (W > 3) m3 = mw[3];
+        }
+        float zl[NEL], el[NEL];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < NEL; i++) {
+            const int a = sub + 8 * i;
+            const uint32_t mwd = (i >> 2) == 0 ? m0 : ((i >> 2) == 1 ? m1 : ((i >> 2) == 2 ? m2 : m3));   // word a >> 5 == i >> 2
+            float x = -INFINITY;
+            if (a < A && live) x = ((mwd >> (8 * (i & 3) + sub)) & 1u) ? MASK_LOGIT : z[a];
+            zl[i] = x;
+            mx = fmaxf(mx, x);
+        }
+        for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+        float se = 0.f, sez = 0.f;
+#pragma unroll
+        for (int i = 0; i < NEL; i++) {
+            float e = 0.f;
+            if (sub + 8 * i < A && live) {
+                const float d = zl[i] - mx;
+                e = __expf(d);
+                sez += e * d;
+            }
+            el[i] = e;
+            se += e;
+        }
+        for (int o = 4; o > 0; o >>= 1) { se += __shfl_xor_sync(FULL, se, o); sez += __shfl_xor_sync(FULL, sez, o); }
+        if (!live) continue;                           // whole groups only; no shuffles below
+        const float log_se = logf(se), inv_se = 1.0f / se;
+        const float lse = mx + log_se;
+        const float ent = log_se - sez * inv_se;
+        const int act = load_action(arow, p.action_dtype, v);
+        float lpa = 0.f;
+        if ((unsigned)act < (unsigned)A) {
+            const int wa = act >> 5;
+            const uint32_t mwa = wa == 0 ? m0 : (wa == 1 ? m1 : (wa == 2 ? m2 : m3));
+            lpa = (((mwa >> (act & 31)) & 1u) ? MASK_LOGIT : z[act]) - lse;
+        }
+        if (sub == 0) { lp_sum += lpa; ent_sum += ent; }
+        if (BACKWARD) {
+            float* gz = p.g_logits + (env * V + v) * (long long)A;
+#pragma unroll
+            for (int i = 0; i < NEL; i++) {
+                const int a = sub + 8 * i;
+                if (a < A) {
+                    const uint32_t mwd = (i >> 2) == 0 ? m0 : ((i >> 2) == 1 ? m1 : ((i >> 2) == 2 ? m2 : m3));
+                    const float l = zl[i] - lse, pr = el[i] * inv_se;
+                    float g = glp * ((a == act ? 1.f : 0.f) - pr) - gent * pr * (l + ent);
+                    if ((mwd >> (8 * (i & 3) + sub)) & 1u) g = 0.f;
+                    gz[a] = g;
+                }
+            }
+        }
+    }
+    if (!BACKWARD) {
+        // fixed-order reduction: groups of a warp (lanes 0, 8, 16, 24), then warps
+        lp_sum += __shfl_xor_sync(FULL, lp_sum, 8);  ent_sum += __shfl_xor_sync(FULL, ent_sum, 8);
+        lp_sum += __shfl_xor_sync(FULL, lp_sum, 16); ent_sum += __shfl_xor_sync(FULL, ent_sum, 16);
+        if (lane == 0) { s_part[0][warp] = lp_sum; s_part[1][warp] = ent_sum; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float a = 0.f, b = 0.f;
+            for (int w = 0; w < nwarps; w++) { a += s_part[0][w]; b += s_part[1][w]; }
             if (p.logprob) p.logprob[env] = a;
             if (p.entropy) p.entropy[env] = b;
         }
@@ -385,13 +492,28 @@ static int heads_launch(HeadParams& hp, const vmgym_config* cfg, bool backward, 
         if (merr != cudaSuccess) return pfail(VMGYM_ECUDA, cudaGetErrorString(merr));
         return VMGYM_OK;
     }
-    if (backward) {
-        if (small) heads_kernel<uint8_t, true><<<(unsigned)hp.n_envs, threads, smem, st>>>(hp);
-        else heads_kernel<uint16_t, true><<<(unsigned)hp.n_envs, threads, smem, st>>>(hp);
-    } else {
-        if (small) heads_kernel<uint8_t, false><<<(unsigned)hp.n_envs, threads, smem, st>>>(hp);
-        else heads_kernel<uint16_t, false><<<(unsigned)hp.n_envs, threads, smem, st>>>(hp);
+    if (hp.action_in && hp.logits && !hp.state && !hp.mask_out && L.A <= 128 && (!hp.masked || hp.mask_in)) {
+        // evaluate mode on a packed mask (the PPO update): 8 lanes per row
+#define VMGYM_EVAL_LAUNCH(PT_, BW_) do { if (L.A <= 104) heads_eval_kernel<PT_, BW_, 13><<<(unsigned)hp.n_envs, 256, 0, st>>>(hp); \
+                                         else heads_eval_kernel<PT_, BW_, 16><<<(unsigned)hp.n_envs, 256, 0, st>>>(hp); } while (0)
+        if (backward) { if (small) VMGYM_EVAL_LAUNCH(uint8_t, true); else VMGYM_EVAL_LAUNCH(uint16_t, true); }
+        else { if (small) VMGYM_EVAL_LAUNCH(uint8_t, false); else VMGYM_EVAL_LAUNCH(uint16_t, false); }
+#undef VMGYM_EVAL_LAUNCH
+        cudaError_t eerr = cudaGetLastError();
+        if (eerr != cudaSuccess) return pfail(VMGYM_ECUDA, cudaGetErrorString(eerr));
+        return VMGYM_OK;
     }
+    const int W = (L.A + 31) / 32;
+#define VMGYM_HEADS_LAUNCH(PT_, BW_, NIC_) heads_kernel<PT_, BW_, NIC_><<<(unsigned)hp.n_envs, threads, smem, st>>>(hp)
+#define VMGYM_HEADS_PICK(PT_, BW_) do { if (W == 4) VMGYM_HEADS_LAUNCH(PT_, BW_, 4); else if (W == 1) VMGYM_HEADS_LAUNCH(PT_, BW_, 1); \
+                                        else VMGYM_HEADS_LAUNCH(PT_, BW_, 0); } while (0)
+    if (backward) {
+        if (small) VMGYM_HEADS_PICK(uint8_t, true); else VMGYM_HEADS_PICK(uint16_t, true);
+    } else {
+        if (small) VMGYM_HEADS_PICK(uint8_t, false); else VMGYM_HEADS_PICK(uint16_t, false);
+    }
+#undef VMGYM_HEADS_PICK
+#undef VMGYM_HEADS_LAUNCH
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return pfail(VMGYM_ECUDA, cudaGetErrorString(err));
     return VMGYM_OK;

@@ -48,7 +48,7 @@ class PPOConfig:
     reward_scaling: bool = False
     training_progress_bar: bool = True
     device: str = "cuda"
-    env_chunk: int = 256           # envs per forward/backward chunk inside a minibatch (gradient accumulation)
+    env_chunk: int = 2048          # samples (env-steps) per forward/backward chunk inside a minibatch (gradient accumulation)
     fused_rollout: bool = False    # rollouts through the fused tcgen05 actor head (bf16 operands; action_dim <= 128)
 
 
@@ -193,7 +193,7 @@ class PPOAgent:
         self.device = vec.device
         self.obs_dim, self.V, self.A = vec.obs_dim, vec.V, vec.action_dim
         self.model = Network(self.obs_dim, self.V, self.A, self.config.hidden_size).to(self.device)
-        self.optimizer = torch.optim.AdamW(self.model.parameters(), lr=self.config.lr)
+        self.optimizer = torch.optim.AdamW(self.model.parameters(), lr=self.config.lr, fused=self.device.type == "cuda")
         self.mask_words = (self.A + 31) // 32
         self.seed = int(vec.config.seed if seed is None else seed)
         self._calls = 0
@@ -356,40 +356,47 @@ class PPOAgent:
         ccfg = vec._ccfg()
         world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
         stats = {}
+        D = obs.shape[-1]
         for epoch in range(cfg.k_epochs):
             for t0 in range(0, T, cfg.minibatch_size):                 # sequential minibatches (ppo.py:251-252)
                 t1 = min(T, t0 + cfg.minibatch_size)
                 adv_mb = advantages[t0:t1]
-                adv_mb = (adv_mb - adv_mb.mean()) / (adv_mb.std() + 1e-10)      # unbiased std (ppo.py:256)
-                # pass 1 (no grad): KL early stop is decided on the whole minibatch (ppo.py:263-264)
+                adv_mb = ((adv_mb - adv_mb.mean()) / (adv_mb.std() + 1e-10)).reshape(-1)      # unbiased std (ppo.py:256)
                 n_mb = (t1 - t0) * N
+                # the minibatch as one flat list of samples (time-major rollout -> these are views), processed in chunks of
+                # cfg.env_chunk samples with gradient accumulation; one forward per sample per minibatch
+                obs_mb, act_mb = obs[t0:t1].reshape(n_mb, D), action[t0:t1].reshape(n_mb, self.V)
+                mask_mb = mask[t0:t1].reshape(n_mb, self.V, self.mask_words)
+                lp_mb, val_mb, ret_mb = logprob[t0:t1].reshape(-1), values[t0:t1].reshape(-1), returns[t0:t1].reshape(-1)
                 self.optimizer.zero_grad(set_to_none=True)
                 logratio_sum = torch.zeros((), dtype=torch.float64, device=self.device)
-                chunks = []
-                for t in range(t0, t1):
-                    for e0 in range(0, N, cfg.env_chunk):
-                        chunks.append((t, e0, min(N, e0 + cfg.env_chunk)))
-                with torch.no_grad():
-                    for t, e0, e1 in chunks:
-                        lg = self.model.actor(obs[t, e0:e1])
-                        nlp, _ = _MaskedHeads.apply(lg, mask[t, e0:e1].contiguous(), action[t, e0:e1].contiguous(), ccfg, cfg.masked)
-                        logratio_sum += (nlp - logprob[t, e0:e1]).double().sum()
-                if -(logratio_sum / n_mb).item() > cfg.kl_max:
-                    break
-                for t, e0, e1 in chunks:
-                    o = obs[t, e0:e1]
+                for s0 in range(0, n_mb, cfg.env_chunk):
+                    s1 = min(n_mb, s0 + cfg.env_chunk)
+                    o = obs_mb[s0:s1]
                     lg = self.model.actor(o)
-                    nlp, ent = _MaskedHeads.apply(lg, mask[t, e0:e1].contiguous(), action[t, e0:e1].contiguous(), ccfg, cfg.masked)
-                    ratios = torch.exp(nlp - logprob[t, e0:e1])
-                    a = adv_mb[t - t0, e0:e1]
+                    nlp, ent = _MaskedHeads.apply(lg, mask_mb[s0:s1], act_mb[s0:s1], ccfg, cfg.masked)
+                    logratio = nlp - lp_mb[s0:s1]
+                    logratio_sum += logratio.detach().double().sum()
+                    ratios = torch.exp(logratio)
+                    a = adv_mb[s0:s1]
                     loss_clipped = torch.max(-ratios * a, -torch.clamp(ratios, 1 - cfg.eps_clip, 1 + cfg.eps_clip) * a).sum()
                     newv = self.model.get_value(o).flatten()
-                    v_old, ret = values[t, e0:e1], returns[t, e0:e1]
+                    v_old, ret = val_mb[s0:s1], ret_mb[s0:s1]
                     l_un = torch.square(newv - ret)
                     l_cl = torch.square(v_old + torch.clamp(newv - v_old, -cfg.eps_clip, cfg.eps_clip) - ret)
                     loss_vf = 0.5 * (torch.max(l_un, l_cl) if cfg.vf_loss_clip else l_un).sum()
                     loss = (loss_clipped - cfg.ent_coef * ent.sum() + cfg.vf_coef * loss_vf) / n_mb   # means over the minibatch
                     loss.backward()
+                # KL early stop on the whole minibatch (ppo.py:263-264): the reference breaks before its backward; here the
+                # accumulated gradients of this minibatch are dropped instead (same parameters afterwards)
+                kl = -(logratio_sum / n_mb)
+                if world > 1:
+                    torch.distributed.all_reduce(kl)
+                    kl /= world
+                stats = {"kl": kl.item()}
+                if cfg.kl_max is not None and stats["kl"] > cfg.kl_max:
+                    self.optimizer.zero_grad(set_to_none=True)
+                    break                                              # only the minibatch loop; the next epoch still runs
                 if world > 1:                                          # data parallel: average gradients over ranks (NCCL)
                     flat = torch.cat([p.grad.flatten() for p in self.model.parameters()])
                     torch.distributed.all_reduce(flat)
@@ -400,5 +407,4 @@ class PPOAgent:
                         off += p.numel()
                 nn.utils.clip_grad_norm_(self.model.parameters(), cfg.max_grad_norm)
                 self.optimizer.step()
-                stats = {"kl": -(logratio_sum / n_mb).item()}
         return stats
