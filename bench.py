@@ -300,13 +300,34 @@ def gpu_arm(args):
         ppo["eval_ms_per_step"] = e0.elapsed_time(e1) / 20
         del agent_e
 
+    # ---- extra C: the synthetic 1000-PM shape (BASELINE config 5: highuniform sizes at 100 % load, V = 3P) ----
+    s1000 = None
+    if not args.no_extras:
+        kw1000 = dict(cfg, pms=1000, vms=3000, sequence="highuniform", arrival_rate=1000 / 0.625 / cfg["service_length"])
+        E1 = 1024
+        v1 = VecVmEnv(Config(**kw1000), E1, device=dev, rng="philox", seeds=cfg["seed"] + 4 * 10**6 + rank * E1 + np.arange(E1, dtype=np.int64))
+        v1.agent_step("bestfit", n_steps=WARM_STEPS, want_obs=False, want_action=False, want_valid=False)
+        v1.agent_step("bestfit", 1, want_obs=True, want_action=False, want_valid=False)
+        barrier()
+        s0_, s1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0_.record()
+        for _ in range(10):
+            v1.agent_step("bestfit", 1, want_obs=True, want_action=False, want_valid=False)
+        s1_.record()
+        barrier()
+        s1000 = {"envs_per_gpu": E1, "ms_per_step": s0_.elapsed_time(s1_) / 10}
+        del v1
+
     if world > 1:
         t = torch.tensor([total_ms, rollout_ms, e2e_s, big["ms_per_step"] if big else 0.0, ppo["seconds"] if ppo else 0.0,
-                          ppo["eval_ms_per_step"] if ppo else 0.0, flushed_ms, e2e1_s], dtype=torch.float64, device=dev)
+                          ppo["eval_ms_per_step"] if ppo else 0.0, flushed_ms, e2e1_s, s1000["ms_per_step"] if s1000 else 0.0],
+                         dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, rollout_ms, e2e_s = t.tolist()[:3]
         flushed_ms = t[6].item()
         e2e1_s = t[7].item()
+        if s1000:
+            s1000["ms_per_step"] = t[8].item()
         if big:
             big["ms_per_step"] = t[3].item()
         if ppo:
@@ -374,6 +395,13 @@ def gpu_arm(args):
         out["ppo_eval"] = {"value": world * E / (ppo["eval_ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": ppo["eval_ms_per_step"],
                            "config": f"config/100.yml PPO evaluation rollouts, {E} envs/GPU, reference-shaped MLP (H=512, random init: the "
                                      "100-PM weights are not shipped), masked, migration_ratio 0.002, fused tcgen05 actor head (bf16)"}
+    if s1000:
+        B1 = algorithmic_bytes(1000, 3000)
+        out["s1000"] = {"value": world * s1000["envs_per_gpu"] / (s1000["ms_per_step"] * 1e-3), "unit": UNIT,
+                        "ms_per_step": s1000["ms_per_step"], "envs_per_gpu": s1000["envs_per_gpu"],
+                        "roofline_frac": B1 * s1000["envs_per_gpu"] / (s1000["ms_per_step"] * 1e-3) / 1e9 / peak,
+                        "config": "synthetic 1000 PMs / 3000 VM slots, highuniform sizes, arrival 1.6 (100 % load), fused best-fit act+step, "
+                                  "one launch per step, same warp-per-env kernel (a CTA-per-env mapping for this shape is future work)"}
     if not args.no_cpu:
         out["cpu_baseline"] = cpu_arm(steps_per_env=args.cpu_steps)
     print(json.dumps(out), flush=True)
