@@ -314,8 +314,11 @@ __global__ void __launch_bounds__(THREADS, 1) policy_fused_kernel(const __grid_c
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // log-softmax statistics relative to the running max m:  s = sum e^(z-m),  t = sum e^(z-m) (z-m), merged chunk by
         // chunk (32 columns): one max + one rescale per chunk, then 32 independent exponentials (instruction-level parallelism)
-        float m = -1e30f, ssum = 0.f, tsum = 0.f, best = -INFINITY, best_z = 0.f, z_given = 0.f;
+        float m = -1e30f, ssum = 0.f, tsum = 0.f, best_z = 0.f, z_given = 0.f;
         int best_a = 0;
+        // sampling: one Philox call per row, word c = the uniform of chunk c (vmgym_sample.cuh)
+        vmgym::Philox4 rnd = {0u, 0u, 0u, 0u};
+        if (!fo.action_in) rnd = vmgym::sample_block(v, 0, (uint32_t)e, fo.seed, fo.counter);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN && c0 < A; c0 += 32) {
             uint32_t r[32];
@@ -346,33 +349,58 @@ __global__ void __launch_bounds__(THREADS, 1) policy_fused_kernel(const __grid_c
                 if (c0 > 0) { const float d = cm - m, sc = __expf(-d); tsum = (tsum - d * ssum) * sc; ssum *= sc; }
                 m = cm;
             }
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+            // e^(z - m) summed as a binary tree over 8 groups of 4 columns (= the order of a warp butterfly, which is what
+            // the stand-alone heads kernel uses): group sums g[t], chunk weight w
+            float g[8];
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float x0 = z[j] - m, x1 = z[j + 1] - m, x2 = z[j + 2] - m, x3 = z[j + 3] - m;
+            for (int t = 0; t < 8; t++) {
+                const float x0 = z[4 * t] - m, x1 = z[4 * t + 1] - m, x2 = z[4 * t + 2] - m, x3 = z[4 * t + 3] - m;
                 const float e0 = __expf(x0), e1 = __expf(x1), e2 = __expf(x2), e3 = __expf(x3);
-                s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+                g[t] = (e0 + e1) + (e2 + e3);
                 t0 += e0 * x0; t1 += e1 * x1; t2 += e2 * x2; t3 += e3 * x3;
             }
-            ssum += (s0 + s1) + (s2 + s3);
+            const float w = ((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]));
+            const float ssum_new = ssum + w;
             tsum += (t0 + t1) + (t2 + t3);
             if (fo.action_in) {
 #pragma unroll
                 for (int j = 0; j < 32; j++) if (c0 + j == act_given) z_given = z[j];
             } else {
+                // streaming inverse-CDF (vmgym_sample.cuh): this chunk replaces the choice iff u * S < w; the column is
+                // where the cumulative sum passes u * S — first over the groups, then inside the group.  Branch-free.
+                const float target = vmgym::chunk_uniform(rnd, c0 >> 5) * ssum_new;
+                float cum = 0.f, base = 0.f, blast = 0.f;
+                int tsel = -1, tlast = 0;
 #pragma unroll
-                for (int j4 = 0; j4 < 32; j4 += 4) {
-                    if (c0 + j4 < A) {
-                        const vmgym::Philox4 rnd = vmgym::sample_block(v, (c0 + j4) >> 2, (uint32_t)e, fo.seed, fo.counter);
+                for (int t = 0; t < 8; t++) {
+                    const float prev = cum;
+                    cum += g[t];
+                    if (g[t] > 0.f) { tlast = t; blast = prev; }
+                    if (tsel < 0 && cum > target) { tsel = t; base = prev; }
+                }
+                if (tsel < 0) { tsel = tlast; base = blast; }
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;          // the 4 logits of group tsel, without a dynamic register index
 #pragma unroll
-                        for (int jj = 0; jj < 4; jj++) {
-                            const int a = c0 + j4 + jj;
-                            const float sc2 = z[j4 + jj] + vmgym::gumbel_from(rnd, jj);
-                            if (a < A && sc2 > best) { best = sc2; best_a = a; best_z = z[j4 + jj]; }
-                        }
-                    }
+                for (int t = 0; t < 8; t++) {
+                    const bool hit = t == tsel;
+                    a0 = hit ? z[4 * t] : a0; a1 = hit ? z[4 * t + 1] : a1; a2 = hit ? z[4 * t + 2] : a2; a3 = hit ? z[4 * t + 3] : a3;
+                    asm volatile("" : "+f"(a0), "+f"(a1), "+f"(a2), "+f"(a3));      // keep the select chain a select chain
+                }
+                const float e0 = __expf(a0 - m), e1 = __expf(a1 - m), e2 = __expf(a2 - m), e3 = __expf(a3 - m);
+                int k = -1, klast = 0;
+                float c2 = base + e0;
+                if (c2 > target) k = 0;
+                c2 += e1; if (e1 > 0.f) klast = 1; if (k < 0 && c2 > target) k = 1;
+                c2 += e2; if (e2 > 0.f) klast = 2; if (k < 0 && c2 > target) k = 2;
+                c2 += e3; if (e3 > 0.f) klast = 3; if (k < 0 && c2 > target) k = 3;
+                if (k < 0) k = klast;
+                if (target < w) {
+                    best_a = c0 + 4 * tsel + k;
+                    best_z = k == 0 ? a0 : (k == 1 ? a1 : (k == 2 ? a2 : a3));
                 }
             }
+            ssum = ssum_new;
         }
         if (e < M) {
             const float ls = __logf(ssum);

@@ -167,21 +167,51 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
             const unsigned char* arow = reinterpret_cast<const unsigned char*>(p.action_in) + env * (long long)V * dtype_bytes(p.action_dtype);
             act = load_action(arow, p.action_dtype, v);
         } else {
-            float best = -INFINITY;
+            // streaming inverse-CDF sampling (vmgym_sample.cuh), the same arithmetic as the fused tcgen05 epilogue: chunk =
+            // the 32 columns i*32 .. i*32+31 (one per lane), running max / sum with rescaling, butterfly sums = the fused
+            // kernel's tree sums, group and in-group scans in the same sequential order
+            float m_run = -1e30f, s_run = 0.f;
             int besta = 0;
+            const Philox4 rnd0 = sample_block(v, 0, (uint32_t)env, p.seed, (uint32_t)p.counter);
+            const Philox4 rnd1 = NI > 4 ? sample_block(v, 1, (uint32_t)env, p.seed, (uint32_t)p.counter) : rnd0;
             _Pragma("unroll") for (int i = 0; i < 8; i++) if (i < NI) {
-                const int a = i * 32 + lane;
-                if (a < A) {
-                    const Philox4 r = sample_block(v, a >> 2, (uint32_t)env, p.seed, (uint32_t)p.counter);
-                    const float g = gumbel_from(r, a & 3);
-                    const float s = zl[i] + g;
-                    if (s > best) { best = s; besta = a; }
+                const float x = (i * 32 + lane < A) ? zl[i] : -1e30f;
+                float cm = x;
+                for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(FULL, cm, o));
+                if (cm > m_run) {
+                    if (i > 0) s_run *= __expf(-(cm - m_run));
+                    m_run = cm;
                 }
-            }
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ob = __shfl_xor_sync(FULL, best, o);
-                const int oa = __shfl_xor_sync(FULL, besta, o);
-                if (ob > best || (ob == best && oa < besta)) { best = ob; besta = oa; }
+                const float e = __expf(x - m_run);
+                float sm = e;
+                sm += __shfl_xor_sync(FULL, sm, 1);
+                sm += __shfl_xor_sync(FULL, sm, 2);
+                const float gsum = sm;                                  // sum of this lane's group of 4 columns
+                sm += __shfl_xor_sync(FULL, sm, 4);
+                sm += __shfl_xor_sync(FULL, sm, 8);
+                sm += __shfl_xor_sync(FULL, sm, 16);
+                const float w = sm, s_new = s_run + w;
+                const float target = chunk_uniform(i < 4 ? rnd0 : rnd1, i) * s_new;
+                float cum = 0.f, base = 0.f, blast = 0.f;
+                int tsel = -1, tlast = 0;
+                for (int t = 0; t < 8; t++) {
+                    const float gt = __shfl_sync(FULL, gsum, 4 * t), prev = cum;
+                    cum += gt;
+                    if (gt > 0.f) { tlast = t; blast = prev; }
+                    if (tsel < 0 && cum > target) { tsel = t; base = prev; }
+                }
+                if (tsel < 0) { tsel = tlast; base = blast; }
+                int k = -1, klast = 0;
+                float c2 = base;
+                for (int kk = 0; kk < 4; kk++) {
+                    const float ek = __shfl_sync(FULL, e, 4 * tsel + kk);
+                    c2 += ek;
+                    if (kk > 0 && ek > 0.f) klast = kk;
+                    if (k < 0 && c2 > target) k = kk;
+                }
+                if (k < 0) k = klast;
+                if (target < w) besta = i * 32 + 4 * tsel + k;
+                s_run = s_new;
             }
             act = besta;
             if (p.action_out && lane == 0) reinterpret_cast<PT*>(p.action_out)[env * V + v] = (PT)act;

@@ -1,5 +1,12 @@
-// vmgym_sample.cuh — the Gumbel noise of the multi-categorical sampler, shared by the stand-alone heads kernel
+// vmgym_sample.cuh — random numbers of the multi-categorical sampler, shared by the stand-alone heads kernel
 // (vmgym_policy.cu) and the fused GEMM epilogue (vmgym_gemm.cu) so both draw the same actions from the same logits.
+//
+// Sampling scheme (both kernels, identical arithmetic): STREAMING INVERSE-CDF.  A row's columns are visited in chunks
+// of 32 with a running maximum m and running sum S of e^(z - m).  Chunk c with weight w_c replaces the current choice
+// with probability w_c / S (one uniform u_c: take iff u_c * S < w_c — weighted reservoir sampling), and the column
+// inside the chunk is found by inverse CDF with the SAME uniform (conditionally on being taken, u_c * S is uniform on
+// [0, w_c)): first over the 8 groups of 4 columns, then inside the group.  P(column a) = e_a / S exactly; one Philox
+// call per row instead of one Gumbel variate (two logarithms + a quarter Philox call) per column.
 #pragma once
 #include <stdint.h>
 
@@ -27,6 +34,13 @@ __device__ __forceinline__ float gumbel_from(const Philox4& r, int sub)
     const uint32_t bits = sub == 0 ? r.x : (sub == 1 ? r.y : (sub == 2 ? r.z : r.w));
     const float u = ((float)(bits >> 8) + 0.5f) * (1.0f / 16777216.0f);     // (0,1)
     return -__logf(-__logf(u));
+}
+
+// uniform in [0, 1) for chunk c of a row, from the row's block(s): 24 bits of word c & 3
+__device__ __forceinline__ float chunk_uniform(const Philox4& r, int c)
+{
+    const uint32_t bits = (c & 3) == 0 ? r.x : ((c & 3) == 1 ? r.y : ((c & 3) == 2 ? r.z : r.w));
+    return (float)(bits >> 8) * (1.0f / 16777216.0f);
 }
 
 }  // namespace vmgym
