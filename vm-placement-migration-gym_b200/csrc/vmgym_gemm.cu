@@ -85,79 +85,124 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- the main loop both kernels share: one 128x128 fp32 accumulator tile in TMEM per CTA --------------------------------
+// shared-memory carve-up: STAGES x (A tile | W tile), then the barriers, the TMEM base address and 1 KiB of kernel-specific tail
+struct Pipe {
+    unsigned char* smem;              // 1024-aligned stage ring
+    uint64_t *full_bar, *empty_bar, *tmem_full_bar;
+    uint32_t* tmem_ptr;
+};
+__device__ __forceinline__ Pipe pipe_carve(unsigned char* smem_raw)
+{
+    Pipe p;
+    p.smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    p.full_bar = reinterpret_cast<uint64_t*>(p.smem + (size_t)STAGES * STAGE_BYTES);
+    p.empty_bar = p.full_bar + STAGES;
+    p.tmem_full_bar = p.empty_bar + STAGES;
+    p.tmem_ptr = reinterpret_cast<uint32_t*>(p.tmem_full_bar + 1);
+    return p;
+}
+// descriptor prefetch (warp 0), barrier init (warp 1), TMEM allocation (warp 2); the caller syncs the CTA afterwards
+__device__ __forceinline__ void pipe_setup(const Pipe& p, const CUtensorMap* map_a, const CUtensorMap* map_w, int warp, int lane)
+{
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(map_w) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&p.full_bar[s], 1); mbar_init(&p.empty_bar[s], 1); }
+        mbar_init(p.tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {   // one warp allocates the accumulator columns and publishes the TMEM base address
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(p.tmem_ptr)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+}
+__device__ __forceinline__ uint32_t pipe_sync_tmem_base(const Pipe& p)
+{
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    return *p.tmem_ptr;
+}
+// TMA producer (one thread): K slices of the A rows [m0, m0+128) and the W rows [n0, n0+128) into the stage ring
+__device__ __forceinline__ void pipe_produce(const Pipe& p, const CUtensorMap* map_a, const CUtensorMap* map_w, int m0, int n0, int k_blocks)
+{
+    for (int kb = 0; kb < k_blocks; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&p.empty_bar[s], ph ^ 1u);                    // slot free (passes immediately on the first round)
+        unsigned char* sa = p.smem + (size_t)s * STAGE_BYTES;
+        unsigned char* sb = sa + BM * BK * 2;
+        mbar_expect_tx(&p.full_bar[s], STAGE_BYTES);
+        tma_load_2d(sa, map_a, kb * BK, m0, &p.full_bar[s]);
+        tma_load_2d(sb, map_w, kb * BK, n0, &p.full_bar[s]);
+    }
+}
+// MMA issuer (one thread): 4 x (M128 N128 K16) per stage into the TMEM accumulator, stage release and final commit
+__device__ __forceinline__ void pipe_mma(const Pipe& p, uint32_t tmem_base, int k_blocks)
+{
+    const uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+    for (int kb = 0; kb < k_blocks; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&p.full_bar[s], ph);                          // TMA bytes have landed
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_u32(p.smem + (size_t)s * STAGE_BYTES);
+        const uint32_t sb = sa + BM * BK * 2;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; k++) {
+            // advance 16 bf16 = 32 B inside the 128-B swizzle row
+            umma_bf16(tmem_base, umma_desc_sw128(sa + k * UMMA_K * 2), umma_desc_sw128(sb + k * UMMA_K * 2), idesc, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(&p.empty_bar[s]);                           // frees the smem stage when these MMAs retire
+    }
+    umma_commit(p.tmem_full_bar);                               // accumulator complete
+}
+// 32 consecutive accumulator columns of this thread's row (TMEM lane) into registers
+__device__ __forceinline__ void tmem_ld_row32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void pipe_teardown(uint32_t tmem_base, int warp)
+{
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+}
+
 __global__ void __launch_bounds__(THREADS, 1) linear_bf16_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                   const __grid_constant__ CUtensorMap map_w,
                                                                   const float* __restrict__ bias, float* __restrict__ C, int M,
                                                                   int N, int K, long long ldc)
 {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-
+    const Pipe pipe = pipe_carve(smem_raw);
+    unsigned char* smem = pipe.smem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int k_blocks = (K + BK - 1) / BK;
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 2) {   // one warp allocates the accumulator columns and publishes the TMEM base address
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_ptr;
+    pipe_setup(pipe, &map_a, &map_w, warp, lane);
+    const uint32_t tmem_base = pipe_sync_tmem_base(pipe);
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            for (int kb = 0; kb < k_blocks; kb++) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(&empty_bar[s], ph ^ 1u);                    // slot free (passes immediately on the first round)
-                unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
-                unsigned char* sb = sa + BM * BK * 2;
-                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                tma_load_2d(sa, &map_a, kb * BK, m0, &full_bar[s]);
-                tma_load_2d(sb, &map_w, kb * BK, n0, &full_bar[s]);
-            }
-        }
+        if (lane == 0) pipe_produce(pipe, &map_a, &map_w, m0, n0, k_blocks);
     } else if (warp == 1) {
-        // ===== MMA issuer (single thread) =====
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
-            for (int kb = 0; kb < k_blocks; kb++) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(&full_bar[s], ph);                          // TMA bytes have landed
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-                const uint32_t sb = sa + BM * BK * 2;
-#pragma unroll
-                for (int k = 0; k < BK / UMMA_K; k++) {
-                    // advance 16 bf16 = 32 B inside the 128-B swizzle row
-                    umma_bf16(tmem_base, umma_desc_sw128(sa + k * UMMA_K * 2), umma_desc_sw128(sb + k * UMMA_K * 2), idesc,
-                              (kb | k) ? 1u : 0u);
-                }
-                umma_commit(&empty_bar[s]);                           // frees the smem stage when these MMAs retire
-            }
-            umma_commit(tmem_full_bar);                               // accumulator complete
-        }
+        if (lane == 0) pipe_mma(pipe, tmem_base, k_blocks);
     } else {
         // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 (= rows of the tile) =====
         const int q = warp & 3;
-        mbar_wait(tmem_full_bar, 0);
+        mbar_wait(pipe.tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // All smem stages are free once the accumulator is complete (one tile per CTA): each epilogue warp uses
         // 32 rows x 36 floats of it to turn "thread = row" (TMEM layout) into "lanes = consecutive columns" so the
@@ -168,16 +213,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_bf16_kernel(const __grid_co
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tmem_ld_row32(taddr, r);
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -210,11 +246,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_bf16_kernel(const __grid_co
             }
         }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
-    }
+    pipe_teardown(tmem_base, warp);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -240,67 +272,19 @@ __global__ void __launch_bounds__(THREADS, 1) policy_fused_kernel(const __grid_c
                                                                    const __grid_constant__ CUtensorMap map_w, FusedOut fo, int M, int K)
 {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-    float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);          // 128 floats (inside the 1 KiB tail region)
-
+    const Pipe pipe = pipe_carve(smem_raw);
+    float* s_bias = reinterpret_cast<float*>(pipe.tmem_ptr + 4);     // 128 floats (inside the 1 KiB tail region)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int v = blockIdx.x, m0 = blockIdx.y * BM, n0 = v * BN;
     const int k_blocks = (K + BK - 1) / BK;
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    pipe_setup(pipe, &map_a, &map_w, warp, lane);
     if (warp >= 2) { const int t = threadIdx.x - 64; s_bias[t] = fo.bias_pad[n0 + t]; }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = pipe_sync_tmem_base(pipe);
 
     if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < k_blocks; kb++) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
-                unsigned char* sb = sa + BM * BK * 2;
-                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                tma_load_2d(sa, &map_a, kb * BK, m0, &full_bar[s]);
-                tma_load_2d(sb, &map_w, kb * BK, n0, &full_bar[s]);
-            }
-        }
+        if (lane == 0) pipe_produce(pipe, &map_a, &map_w, m0, n0, k_blocks);
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
-            for (int kb = 0; kb < k_blocks; kb++) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(&full_bar[s], ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-                const uint32_t sb = sa + BM * BK * 2;
-#pragma unroll
-                for (int k = 0; k < BK / UMMA_K; k++)
-                    umma_bf16(tmem_base, umma_desc_sw128(sa + k * UMMA_K * 2), umma_desc_sw128(sb + k * UMMA_K * 2), idesc,
-                              (kb | k) ? 1u : 0u);
-                umma_commit(&empty_bar[s]);
-            }
-            umma_commit(tmem_full_bar);
-        }
+        if (lane == 0) pipe_mma(pipe, tmem_base, k_blocks);
     } else {
         // ===== fused epilogue: thread = env row, registers = this VM's logits =====
         const int q = warp & 3;
@@ -310,7 +294,7 @@ __global__ void __launch_bounds__(THREADS, 1) policy_fused_kernel(const __grid_c
         if (fo.mask_bits && e < M) inv = reinterpret_cast<const uint4*>(fo.mask_bits)[(long long)e * fo.V + v];
         int act_given = -1;
         if (fo.action_in && e < M) act_given = reinterpret_cast<const uint8_t*>(fo.action_in)[(long long)e * fo.V + v];
-        mbar_wait(tmem_full_bar, 0);
+        mbar_wait(pipe.tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // log-softmax statistics relative to the running max m:  s = sum e^(z-m),  t = sum e^(z-m) (z-m), merged chunk by
         // chunk (32 columns): one max + one rescale per chunk, then 32 independent exponentials (instruction-level parallelism)
@@ -323,16 +307,7 @@ __global__ void __launch_bounds__(THREADS, 1) policy_fused_kernel(const __grid_c
         for (int c0 = 0; c0 < BN && c0 < A; c0 += 32) {
             uint32_t r[32];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tmem_ld_row32(taddr, r);
             const uint32_t iw = c0 == 0 ? inv.x : (c0 == 32 ? inv.y : (c0 == 64 ? inv.z : inv.w));
             float z[32];
             float cm = -1e30f;
@@ -412,11 +387,7 @@ __global__ void __launch_bounds__(THREADS, 1) policy_fused_kernel(const __grid_c
             fo.entropy[o] = ls - tsum / ssum;                            // -sum p log p
         }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
-    }
+    pipe_teardown(tmem_base, warp);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
