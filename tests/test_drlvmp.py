@@ -71,7 +71,11 @@ def test_act_loop_equals_sequential_restatement():
     obs, *_ = vec.step(act)
     obs = obs.clone()
     agent = DRLVMPAgent(vec, DRLVMPConfig(hidden_size=16))
-    batched = agent.act(obs).cpu().numpy()
+    batched = agent.act(obs).cpu().numpy()                       # incremental feature update (default)
+    assert np.array_equal(batched, agent.act(obs, incremental=False).cpu().numpy())
+    assert np.array_equal(batched, agent.act(obs, refresh=3).cpu().numpy())
+    assert np.array_equal(batched, agent.act(obs, graph=True).cpu().numpy())            # CUDA-graph replay per waiting VM
+    assert np.array_equal(batched, agent.act(obs, graph=True, refresh=2).cpu().numpy())  # cached graph, second call
     for i in range(7):
         o = obs[i:i + 1].clone()
         for v in torch.nonzero(obs[i, :30] == 10.0).flatten().tolist():

@@ -24,6 +24,8 @@ from vmgym.drlvmp import DRLVMPAgent, DRLVMPConfig
 agent = DRLVMPAgent(vec, DRLVMPConfig(hidden_size=512))
 agent.eval()
 obs = vec.observe()
+a = agent.act(obs); obs, *_ = vec.step(a, want_valid=False)      # graph capture / allocations
+torch.cuda.synchronize()
 t0 = time.perf_counter()
 for _ in range(2):
     a = agent.act(obs)

@@ -94,6 +94,24 @@ class Network(nn.Module):
     def forward(self, x):
         return torch.sum(self.dist(x) * self.support, dim=2)
 
+    def effective_heads(self):
+        """(weight, bias) of the four noisy layers with the current noise folded in (constant between reset_noise calls)."""
+        return [(m.weight_mu + m.weight_sigma * m.weight_epsilon, m.bias_mu + m.bias_sigma * m.bias_epsilon)
+                for m in (self.advantage_hidden_layer, self.advantage_layer, self.value_hidden_layer, self.value_layer)]
+
+    def q_from_pre(self, pre, eff=None):
+        """q-values from the feature layer's PRE-activation (x W1^T + b1): lets a caller that changes one input column
+        at a time update `pre` by a rank-1 term instead of redoing the D x H product (DRLVMPAgent.act).  `eff`: the
+        result of effective_heads(), to fold the noise once per act() call instead of once per waiting VM."""
+        f = F.relu(pre)
+        if eff is None:
+            eff = self.effective_heads()
+        (wah, bah), (wa, ba), (wvh, bvh), (wv, bv) = eff
+        adv = F.linear(F.relu(F.linear(f, wah, bah)), wa, ba).view(-1, self.out_dim, self.atom_size)
+        val = F.linear(F.relu(F.linear(f, wvh, bvh)), wv, bv).view(-1, 1, self.atom_size)
+        dist = F.softmax(val + adv - adv.mean(dim=1, keepdim=True), dim=-1).clamp(min=1e-3)
+        return torch.sum(dist * self.support, dim=2)
+
     def reset_noise(self):
         for m in (self.advantage_hidden_layer, self.advantage_layer, self.value_hidden_layer, self.value_layer):
             m.reset_noise()
@@ -141,31 +159,113 @@ class DRLVMPAgent:
         return pm
 
     @torch.no_grad()
-    def act(self, observation):
-        """drlvmp.py:504-512 for a batch of observations [n, D] (or one numpy observation)."""
+    def act(self, observation, incremental: bool = True, refresh: int = 128, graph: bool | None = None):
+        """drlvmp.py:504-512 for a batch of observations [n, D] (or one numpy observation).
+
+        The reference re-evaluates the whole network for every waiting VM although only ONE observation entry changed
+        (the VM's placement, WAIT -> chosen PM).  With `incremental` the feature layer's pre-activation is carried along
+        and corrected by that entry's weight column (rank-1 update per env), and recomputed from scratch every `refresh`
+        VMs; the difference to the full product is fp32 rounding (~1e-6 relative, inside the 1e-4 network tolerance).
+        `graph` (default: batches of >= 64 envs) replays one CUDA graph per waiting VM instead of ~40 eager launches; the
+        VM counter lives on the device, so every replay is the same graph."""
         vec = self.vec
         host = isinstance(observation, np.ndarray)
-        obs = torch.from_numpy(np.ascontiguousarray(observation, np.float32)).to(self.device) if host else observation
-        single = obs.dim() == 1
-        obs = obs.reshape(-1, vec.obs_dim).float().contiguous().clone()       # the working observation copy
-        n, V, P = obs.shape[0], vec.V, vec.P
+        obs_in = torch.from_numpy(np.ascontiguousarray(observation, np.float32)).to(self.device) if host else observation
+        single = obs_in.dim() == 1
+        obs_in = obs_in.reshape(-1, vec.obs_dim).float()
+        n, V, P = obs_in.shape[0], vec.V, vec.P
+        if graph is None:
+            graph = incremental and n >= 64
+        st = self._act_state(n) if graph else None
+        obs = st["obs"] if graph else obs_in.contiguous().clone()             # the working observation copy
+        if graph:
+            obs.copy_(obs_in)
         waiting = obs[:, :V] == float(P)                                       # fixed at entry (drlvmp.py:507)
         n_wait = waiting.sum(1)
         # k-th waiting slot of every env, in slot order
-        order = torch.argsort((~waiting).to(torch.int8), dim=1, stable=True).to(torch.int32)
+        order = torch.argsort((~waiting).to(torch.int8), dim=1, stable=True)
         rows = torch.arange(n, device=self.device)
-        for k in range(int(n_wait.max().item()) if n else 0):
-            active = n_wait > k
-            idx = torch.where(active, order[:, k], torch.full_like(order[:, k], -1)).contiguous()
-            choice = self.dqn(obs).argmax(dim=1).to(torch.int32).contiguous()   # drlvmp.py:514-515
+        lin = self.dqn.feature_layer[0]
+        n_iter = int(n_wait.max().item()) if n else 0
+
+        eff = self.dqn.effective_heads() if incremental else None            # noise is fixed during act (no reset_noise)
+        if graph:
+            if "eff" not in st:
+                st["eff"] = [(w.clone(), b.clone()) for w, b in eff]
+            for (sw, sb), (w, b) in zip(st["eff"], eff):
+                sw.copy_(w); sb.copy_(b)
+            eff = st["eff"]
+
+        def iteration(pre, kdev, w_cols):
+            """One waiting VM per env: k-th waiting slot (k on the device), network choice, heuristic, write-back."""
+            active = n_wait > kdev
+            col = order.gather(1, kdev.clamp(max=V - 1).expand(n, 1)).squeeze(1)
+            idx = torch.where(active, col, torch.full_like(col, -1)).to(torch.int32).contiguous()
+            q = self.dqn.q_from_pre(pre, eff) if pre is not None else self.dqn(obs)
+            choice = q.argmax(dim=1).to(torch.int32).contiguous()              # drlvmp.py:514-515
             pm = self.heuristic(obs, idx, choice)
             upd = active & (pm >= 0)
-            obs[rows[upd], idx[upd].long()] = pm[upd].float()                   # placement written into the obs copy only
+            # masked scatter with fixed shapes (no boolean indexing: that would synchronise with the host every VM)
+            c = idx.clamp(min=0).long()
+            old = obs[rows, c]
+            new = torch.where(upd, pm.float(), old)
+            obs[rows, c] = new                                                  # placement written into the obs copy only
+            if pre is not None:
+                pre += w_cols[c] * (new - old).unsqueeze(1)                     # old is WAIT (= P) wherever upd holds
+            kdev += 1
+
+        if not graph:
+            kdev = torch.zeros((), dtype=torch.int64, device=self.device)
+            w_cols = lin.weight.t().contiguous() if incremental else None      # [D, H]: row j = weight column of input j
+            pre = None
+            for k in range(n_iter):
+                if incremental and k % refresh == 0:
+                    pre = lin(obs)
+                iteration(pre, kdev, w_cols)
+        else:
+            # static buffers + one captured iteration; the graph reads n_wait / order through these buffers
+            st["n_wait"].copy_(n_wait); st["order"].copy_(order); st["kdev"].zero_()
+            st["w_cols"].copy_(lin.weight.t())
+            n_wait, order = st["n_wait"], st["order"]
+            pre, kdev, w_cols = st["pre"], st["kdev"], st["w_cols"]
+            if st["graph"] is None and n_iter > 0:
+                pre.copy_(lin(obs))
+                keep = obs.clone()
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    iteration(pre, kdev, w_cols)                               # warm-up (allocations) outside the capture
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                obs.copy_(keep); kdev.zero_()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    iteration(pre, kdev, w_cols)
+                st["graph"] = g
+            for k in range(n_iter):
+                if k % refresh == 0:
+                    pre.copy_(lin(obs))
+                st["graph"].replay()
         action = obs[:, :V].to(torch.int64)
         if host:
             a = action.cpu().numpy()
             return a[0] if single else a
         return action[0] if single else action
+
+    def _act_state(self, n: int):
+        """Static buffers (and, lazily, the captured graph) of act() for a batch of n observations."""
+        cache = self.__dict__.setdefault("_act_cache", {})
+        st = cache.get(n)
+        if st is None:
+            vec, dev = self.vec, self.device
+            H = self.dqn.feature_layer[0].out_features
+            st = dict(obs=torch.empty((n, vec.obs_dim), dtype=torch.float32, device=dev),
+                      pre=torch.empty((n, H), dtype=torch.float32, device=dev),
+                      n_wait=torch.empty(n, dtype=torch.int64, device=dev),
+                      order=torch.empty((n, vec.V), dtype=torch.int64, device=dev),
+                      kdev=torch.zeros((), dtype=torch.int64, device=dev),
+                      w_cols=torch.empty((vec.obs_dim, H), dtype=torch.float32, device=dev), graph=None)
+            cache[n] = st
+        return st
 
 
 class DeviceSegmentTrees:
