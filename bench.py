@@ -316,11 +316,24 @@ def gpu_arm(args):
         s1_.record()
         barrier()
         s1000 = {"envs_per_gpu": E1, "ms_per_step": s0_.elapsed_time(s1_) / 10}
-        del v1
+        # DRL-VMP rollout at this shape (drlvmp.py:504-512: one network evaluation + heuristic per WAITING VM, sequentially)
+        from vmgym.drlvmp import DRLVMPAgent, DRLVMPConfig
+        ag1 = DRLVMPAgent(v1, DRLVMPConfig(hidden_size=512))
+        ag1.eval()
+        o1 = v1.observe()
+        o1, *_ = v1.step(ag1.act(o1), want_valid=False)            # graph capture / allocations
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            o1, *_ = v1.step(ag1.act(o1), want_valid=False)
+        barrier()
+        s1000["drlvmp_s_per_step"] = (time.perf_counter() - t0) / 2
+        del v1, ag1
 
     if world > 1:
         t = torch.tensor([total_ms, rollout_ms, e2e_s, big["ms_per_step"] if big else 0.0, ppo["seconds"] if ppo else 0.0,
-                          ppo["eval_ms_per_step"] if ppo else 0.0, flushed_ms, e2e1_s, s1000["ms_per_step"] if s1000 else 0.0],
+                          ppo["eval_ms_per_step"] if ppo else 0.0, flushed_ms, e2e1_s, s1000["ms_per_step"] if s1000 else 0.0,
+                          s1000["drlvmp_s_per_step"] if s1000 else 0.0],
                          dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, rollout_ms, e2e_s = t.tolist()[:3]
@@ -328,6 +341,7 @@ def gpu_arm(args):
         e2e1_s = t[7].item()
         if s1000:
             s1000["ms_per_step"] = t[8].item()
+            s1000["drlvmp_s_per_step"] = t[9].item()
         if big:
             big["ms_per_step"] = t[3].item()
         if ppo:
@@ -400,6 +414,9 @@ def gpu_arm(args):
         out["s1000"] = {"value": world * s1000["envs_per_gpu"] / (s1000["ms_per_step"] * 1e-3), "unit": UNIT,
                         "ms_per_step": s1000["ms_per_step"], "envs_per_gpu": s1000["envs_per_gpu"],
                         "roofline_frac": B1 * s1000["envs_per_gpu"] / (s1000["ms_per_step"] * 1e-3) / 1e9 / peak,
+                        "drlvmp_rollout": {"value": world * s1000["envs_per_gpu"] / s1000["drlvmp_s_per_step"], "unit": UNIT,
+                                           "note": "DRLVMPAgent.act (H=512 dueling C51 net, one evaluation + heuristic kernel per waiting "
+                                                   "VM, ~900 per env and step at this load) + env.step"},
                         "config": "synthetic 1000 PMs / 3000 VM slots, highuniform sizes, arrival 1.6 (100 % load), fused best-fit act+step, "
                                   "one launch per step, same warp-per-env kernel (a CTA-per-env mapping for this shape is future work)"}
     if not args.no_cpu:
