@@ -55,3 +55,41 @@ def test_poisson_cdf_table(lam):
     want = np.exp(ks * math.log(lam) - lam - np.array([math.lgamma(k + 1.0) for k in ks]))
     assert np.allclose(p[:-1], want[:-1], atol=1e-12)
     assert abs((p * ks).sum() - lam) < 1e-6 * max(1.0, lam)
+
+
+def test_histogram_statistics_equal_numpy_on_the_lists():
+    """vec_env._hist_stats / vm_stats_from_histograms: mean, median and max of the rate lists reconstructed from the
+    1001-bin histograms the kernel keeps == np.mean / np.median / np.max of the lists themselves (record.py:118-125)."""
+    import importlib.util
+    import os
+    import sys
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "vm-placement-migration-gym_b200")
+    sys.path.insert(0, root)
+    from vmgym.vec_env import _hist_stats, vm_stats_from_histograms
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 10, 11, 500, 501):
+        for skew in (1.0, 4.0):
+            rates = np.around(rng.random(n) ** skew, 3)
+            h = np.bincount(np.rint(rates * 1000).astype(np.int64), minlength=1024)
+            mean, median, mx = _hist_stats(h)
+            assert abs(mean - np.mean(rates)) < 1e-12 and median == np.median(rates) and mx == np.max(rates), (n, skew)
+    assert _hist_stats(np.zeros(1024, np.int64)) == (0.0, 0.0, 0.0)           # record.py:83-84: empty slowdown list -> [0]
+    hist = np.zeros((2, 2, 1024), np.int64)
+    hist[0, 0, [100, 300, 1000]] = [2, 1, 1]; hist[0, 1, [0, 250]] = [2, 1]
+    totals = np.array([[4, 3, 90, 0], [0, 0, 0, 0]], np.int64)
+    s = vm_stats_from_histograms(hist, totals)
+    assert s["average pending"][0] == np.mean([0.1, 0.1, 0.3, 1.0]) and s["median pending"][0] == 0.2 and s["max pending"][0] == 1.0
+    assert s["average VM life"][0] == 22.5 and s["average slowdown"][0] == np.mean([0.0, 0.0, 0.25]) and np.isnan(s["average VM life"][1])
+
+
+def test_suspension_grid_matches_reference_script():
+    """vmgym.sweep.suspension_points: the (load, service length, arrival rate) grid of exp_suspension.py:75-85,19."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "vm-placement-migration-gym_b200"))
+    from vmgym.sweep import suspension_points
+    pts = suspension_points(100)
+    assert len(pts) == 20 + 9
+    assert pts[0] == dict(service_length=100, arrival_rate=float(np.round(100 / 0.55 / 100, 3)), _load=1.0)
+    assert pts[19]["service_length"] == 3900 and pts[20]["service_length"] == 1000 and abs(pts[20]["_load"] - 0.2) < 1e-12
+    assert pts[-1]["arrival_rate"] == float(np.round(100 / 0.55 / 1000 * np.arange(0.2, 1.1, 0.1)[-1], 3))
