@@ -135,9 +135,9 @@ def gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     cfg = load_env_cfg()
     E = args.envs
-    if args.bulk is not None:
+    if args.bulk is not None or args.warps:
         from vmgym import _native as nv
-        nv.lib().vmgym_set_tuning(0, int(args.bulk))
+        nv.lib().vmgym_set_tuning(int(args.warps), 3 if args.bulk is None else int(args.bulk))
     # envs shard contiguously: rank g owns global env ids [g*E, (g+1)*E); seeds derive from the global id
     seeds = cfg["seed"] + rank * E + np.arange(E, dtype=np.int64)
     vec = VecVmEnv(Config(**cfg), E, device=dev, rng="philox", seeds=seeds)
@@ -461,6 +461,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (per batch)")
     ap.add_argument("--ppo-envs", type=int, default=8192, help="envs per GPU of the ppo_train extra")
+    ap.add_argument("--warps", type=int, default=0, help="vmgym_set_tuning warps per CTA, 0 = auto (experiments)")
     ap.add_argument("--bulk", type=int, default=None, help="vmgym_set_tuning use_bulk_copy bits (experiments)")
     ap.add_argument("--e2e-groups", type=int, default=8, help="env groups (streams) of the host-buffer e2e loop")
     ap.add_argument("--batches", type=int, default=20, help="independent env batches the timed launches rotate over")
