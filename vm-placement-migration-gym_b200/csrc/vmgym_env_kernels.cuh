@@ -39,6 +39,9 @@ __host__ __device__ static inline int align_up(int x, int a) { return (x + a - 1
 // Per-warp env context: one base pointer into shared memory + the layout (kernel-parameter constant bank), so the
 // dozen array pointers are recomputed from constants instead of living in (spilled) registers.
 // ---------------------------------------------------------------------------------------------------
+// every per-env array lives in shared memory: telling the compiler lets it emit LDS/STS instead of generic LD/ST
+#define VMGYM_SMEM(p) (__builtin_assume(__isShared(p)), (p))
+
 template <typename PT>
 struct Env {
     unsigned char* base;
@@ -51,24 +54,24 @@ struct Env {
     const uint16_t* svc_bracket;       // 65-entry search brackets of the service table (shared memory) or nullptr
     int P, V, lane;
 
-    __device__ __forceinline__ double* cpu() const { return reinterpret_cast<double*>(base); }           // env.py:190
-    __device__ __forceinline__ double* mem() const { return reinterpret_cast<double*>(base + L->off_mem); }
-    __device__ __forceinline__ uint16_t* rem() const { return reinterpret_cast<uint16_t*>(base + L->off_rem); }
-    __device__ __forceinline__ PT* place() const { return reinterpret_cast<PT*>(base + L->off_place); }
-    __device__ __forceinline__ uint8_t* cpuc() const { return base + L->off_cpuc; }                      // bit 7 = suspended
-    __device__ __forceinline__ uint8_t* memc() const { return base + L->off_memc; }
+    __device__ __forceinline__ double* cpu() const { return reinterpret_cast<double*>(VMGYM_SMEM(base)); }           // env.py:190
+    __device__ __forceinline__ double* mem() const { return reinterpret_cast<double*>(VMGYM_SMEM(base) + L->off_mem); }
+    __device__ __forceinline__ uint16_t* rem() const { return reinterpret_cast<uint16_t*>(VMGYM_SMEM(base) + L->off_rem); }
+    __device__ __forceinline__ PT* place() const { return reinterpret_cast<PT*>(VMGYM_SMEM(base) + L->off_place); }
+    __device__ __forceinline__ uint8_t* cpuc() const { return VMGYM_SMEM(base) + L->off_cpuc; }                      // bit 7 = suspended
+    __device__ __forceinline__ uint8_t* memc() const { return VMGYM_SMEM(base) + L->off_memc; }
     // capacity codes of every PM in the agents' float32 view, kept consistent with cpu()/mem() by every update:
     // rcap[p] = kc | km << 8 with kc = max{k : (float)cpu[p] + sz32[k] <= 1.0f} (likewise km for memory)
-    __device__ __forceinline__ uint16_t* rcap() const { return reinterpret_cast<uint16_t*>(base + L->off_cap); }
-    __device__ __forceinline__ vmgym_env_scalars* sc() const { return reinterpret_cast<vmgym_env_scalars*>(base + L->off_scal); }
+    __device__ __forceinline__ uint16_t* rcap() const { return reinterpret_cast<uint16_t*>(VMGYM_SMEM(base) + L->off_cap); }
+    __device__ __forceinline__ vmgym_env_scalars* sc() const { return reinterpret_cast<vmgym_env_scalars*>(VMGYM_SMEM(base) + L->off_scal); }
     // scratch (not part of the record)
-    __device__ __forceinline__ float* cpu32() const { return reinterpret_cast<float*>(base + L->sm_cpu32); }  // agents' fp32 view
-    __device__ __forceinline__ float* mem32() const { return reinterpret_cast<float*>(base + L->sm_mem32); }
-    __device__ __forceinline__ uint16_t* act() const { return reinterpret_cast<uint16_t*>(base + L->sm_act); }
-    __device__ __forceinline__ uint8_t* tmp() const { return base + L->sm_tmp; }
-    __device__ __forceinline__ unsigned* fitm() const { return reinterpret_cast<unsigned*>(base + L->sm_fit); }
-    __device__ __forceinline__ uint16_t* cap() const { return reinterpret_cast<uint16_t*>(base + L->sm_fit + 512); }
-    __device__ __forceinline__ unsigned* prop() const { return reinterpret_cast<unsigned*>(base + L->sm_prop); }
+    __device__ __forceinline__ float* cpu32() const { return reinterpret_cast<float*>(VMGYM_SMEM(base) + L->sm_cpu32); }  // agents' fp32 view
+    __device__ __forceinline__ float* mem32() const { return reinterpret_cast<float*>(VMGYM_SMEM(base) + L->sm_mem32); }
+    __device__ __forceinline__ uint16_t* act() const { return reinterpret_cast<uint16_t*>(VMGYM_SMEM(base) + L->sm_act); }
+    __device__ __forceinline__ uint8_t* tmp() const { return VMGYM_SMEM(base) + L->sm_tmp; }
+    __device__ __forceinline__ unsigned* fitm() const { return reinterpret_cast<unsigned*>(VMGYM_SMEM(base) + L->sm_fit); }
+    __device__ __forceinline__ uint16_t* cap() const { return reinterpret_cast<uint16_t*>(VMGYM_SMEM(base) + L->sm_fit + 512); }
+    __device__ __forceinline__ unsigned* prop() const { return reinterpret_cast<unsigned*>(VMGYM_SMEM(base) + L->sm_prop); }
 };
 
 // Where the agent reads the slots it decides on: arrays of placements and size codes (+ float sizes as the agent
