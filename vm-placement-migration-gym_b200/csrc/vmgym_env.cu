@@ -47,7 +47,7 @@ static int make_layout(const vmgym_config* c, DevLayout* L, vmgym_layout* pub)
     l.off_memc = l.off_cpuc + l.Vp;
     l.off_cap = l.off_memc + l.Vp;
     l.off_scal = l.off_cap + align_up(2 * l.Pp, 16);
-    l.rec_bytes = align_up(l.off_scal + (int)sizeof(vmgym_env_scalars), 128);
+    l.rec_bytes = align_up(l.off_scal + (int)sizeof(vmgym_env_scalars) + 16, 128);   // + 16 B: parked Philox words (arrival draws)
     l.sm_cpu32 = l.rec_bytes;
     l.sm_mem32 = l.sm_cpu32 + align_up(4 * l.P, 16);
     l.sm_act = l.sm_mem32 + align_up(4 * l.P, 16);

@@ -653,14 +653,28 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
         else exhausted = 1;
     } else {
         // one Philox call serves four consecutive steps: step t takes 32-bit word (t & 3) of block (t >> 2) and inverts
-        // the Poisson CDF on the top 32 bits of the thresholds (resolution 2^-32)
-        const Philox4 r = philox_dev(arrival_pos >> 2, 1u, k0, k1);
-        const uint32_t sub = arrival_pos & 3u;
-        const uint32_t u32 = sub == 0 ? r.x : (sub == 1 ? r.y : (sub == 2 ? r.z : r.w));
-        int lo = 0, hi = tr.arrival_cdf_len;
-        if (e.arr_cdf32) {
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (e.arr_cdf32[mid] <= u32) lo = mid + 1; else hi = mid; }
+        // the Poisson CDF on the top 32 bits of the thresholds (resolution 2^-32).  Words 1..3 of the block are parked in
+        // the record's padding behind the scalars (tag = block index + 1) so three steps out of four skip the 10 rounds.
+        const uint32_t sub = arrival_pos & 3u, blk = arrival_pos >> 2;
+        uint32_t* park = reinterpret_cast<uint32_t*>(e.sc() + 1);             // 16 B: tag, y, z, w
+        uint32_t u32;
+        if (sub != 0u && park[0] == blk + 1u) {
+            u32 = park[sub];
         } else {
+            const Philox4 r = philox_dev(blk, 1u, k0, k1);
+            u32 = sub == 0 ? r.x : (sub == 1 ? r.y : (sub == 2 ? r.z : r.w));
+            __syncwarp();
+            if (lane == 0) { park[0] = blk + 1u; park[1] = r.y; park[2] = r.z; park[3] = r.w; }
+        }
+        int lo;
+        if (e.arr_cdf32 && tr.arrival_cdf_len <= 64) {
+            // #{i : cdf[i] <= u} with one table entry per lane (the table is sorted, so this is the search result)
+            lo = __popc(__ballot_sync(FULL, lane < tr.arrival_cdf_len && e.arr_cdf32[lane] <= u32));
+            if (tr.arrival_cdf_len > 32)
+                lo += __popc(__ballot_sync(FULL, lane + 32 < tr.arrival_cdf_len && e.arr_cdf32[lane + 32] <= u32));
+        } else {
+            int hi = tr.arrival_cdf_len;
+            lo = 0;
             while (lo < hi) { const int mid = (lo + hi) >> 1; if ((uint32_t)(e.arr_cdf[mid] >> 32) <= u32) lo = mid + 1; else hi = mid; }
         }
         n_arr = tr.arrival_kmin + min(lo, tr.arrival_cdf_len - 1);
@@ -865,8 +879,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
     double* sz64 = reinterpret_cast<double*>(smem);
     float* sz32 = reinterpret_cast<float*>(smem + SIZE_TABLE * 8);
     uint32_t* arr_cdf_s = reinterpret_cast<uint32_t*>(smem + SIZE_TABLE * 12);
-    uint64_t* svc_cdf_s = reinterpret_cast<uint64_t*>(smem + SIZE_TABLE * 12) + ARR_CDF_SMEM;
-    uint16_t* svc_bracket_s = reinterpret_cast<uint16_t*>(svc_cdf_s + L.svc_cdf_smem);
+    uint16_t* svc_bracket_s = reinterpret_cast<uint16_t*>(reinterpret_cast<uint64_t*>(smem + SIZE_TABLE * 12) + ARR_CDF_SMEM);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     unsigned char* base = smem + L.sm_tables + (size_t)warp * L.sm_stride;
     uint64_t* bar = reinterpret_cast<uint64_t*>(base + L.sm_bar);
@@ -885,7 +898,6 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
     }
     const bool philox = (MODE_CT >= 0 ? MODE_CT : p.tr.mode) == VMGYM_TRACE_PHILOX;
     const bool arr_in_smem = philox && p.tr.arrival_cdf_len <= ARR_CDF_SMEM;
-    const bool svc_in_smem = philox && p.tr.service_cdf_len <= L.svc_cdf_smem;
     const bool have_bracket = philox && p.tr.d_service_bracket != nullptr;
     {
         // CTA-wide tables: every global load is issued before the first shared-memory store so that the round trips
@@ -893,9 +905,6 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
         const int t = threadIdx.x, nt = blockDim.x;
         const uint64_t a0 = (arr_in_smem && t < p.tr.arrival_cdf_len) ? p.tr.d_arrival_cdf[t] : 0ull;
         const uint16_t b0 = (have_bracket && t < SVC_BRACKETS + 1) ? p.tr.d_service_bracket[t] : (uint16_t)0;
-        uint64_t s0[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) s0[i] = (svc_in_smem && t + i * nt < p.tr.service_cdf_len) ? p.tr.d_service_cdf[t + i * nt] : 0ull;
         fill_tables(sz64, sz32);
         if (arr_in_smem) {
             if (t < p.tr.arrival_cdf_len) arr_cdf_s[t] = (uint32_t)(a0 >> 32);
@@ -905,11 +914,6 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
             if (t < SVC_BRACKETS + 1) svc_bracket_s[t] = b0;
             for (int k = t + nt; k < SVC_BRACKETS + 1; k += nt) svc_bracket_s[k] = p.tr.d_service_bracket[k];
         }
-        if (svc_in_smem) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) if (t + i * nt < p.tr.service_cdf_len) svc_cdf_s[t + i * nt] = s0[i];
-            for (int k = t + 4 * nt; k < p.tr.service_cdf_len; k += nt) svc_cdf_s[k] = p.tr.d_service_cdf[k];
-        }
     }
     __syncthreads();
 
@@ -917,7 +921,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
     e.base = base; e.L = &p.L; e.sz64 = sz64; e.sz32 = sz32; e.P = cP; e.V = cV; e.lane = lane;
     e.arr_cdf = p.tr.d_arrival_cdf;
     e.arr_cdf32 = arr_in_smem ? arr_cdf_s : nullptr;
-    e.svc_cdf = svc_in_smem ? svc_cdf_s : p.tr.d_service_cdf;
+    e.svc_cdf = p.tr.d_service_cdf;                  // searched from a 64-way bracket, on admissions only
     e.svc_bracket = have_bracket ? svc_bracket_s : nullptr;
     uint32_t phase = 0;
     for (long long env = env0; env < p.n_envs; env += stride) {
