@@ -118,7 +118,9 @@ typedef struct vmgym_outputs {
     uint8_t* d_terminated;   /* [n_envs] (env.py:160-163) */
     uint8_t* d_valid;        /* [n_envs, V] info["valid"] (env.py:69-74,91-94) */
     void* d_action;          /* [n_envs, V] actions chosen by a fused agent, element type = placement type */
-    double* d_stats;         /* [n_envs, 8] running sums for the eval summary (src/record.py:98-134), see DESIGN.md */
+    double* d_stats;         /* [n_envs, VMGYM_STATS] running sums over the steps of the call for Record.get_summary (src/record.py:
+                                98-134): drop rate, waiting ratio, mean_p cpu, var_p cpu, mean_p mem, var_p mem, rejected actions,
+                                steps, (mean_p cpu)^2, (mean_p mem)^2, target cpu mean, target mem mean, used PMs (rank), 3 reserved */
     /* Per-VM episode statistics of Record (src/record.py:34-96: pending rate, slowdown rate, lifetime of every VM that
      * occupied a slot), all three NULL or all three set.  The step kernels keep four clocks per slot and add a VM to
      * the histograms when it departs; vmgym_vmstats_finalize adds the VMs that still exist.  Zero the three buffers
@@ -128,6 +130,7 @@ typedef struct vmgym_outputs {
     uint32_t* d_vm_hist;     /* [n_envs, 2, VMGYM_VMSTAT_BINS] counts of rint(1000 * rate): [0] pending, [1] slowdown */
     uint64_t* d_vm_totals;   /* [n_envs, 4] VMs seen, VMs ever placed, sum of lifetimes, reserved */
 } vmgym_outputs;
+#define VMGYM_STATS 16
 #define VMGYM_VMSTAT_BINS 1024   /* rates are rounded to 3 decimals (record.py:61,79): bins 0..1000 are used */
 
 const char* vmgym_last_error(void);

@@ -30,6 +30,10 @@ CASES = {
                                              seed=5, eval_steps=900), agent="bestfit", perturb=0.05),
     "rec_s10_sparse": dict(base="10", over=dict(reward_function="wr", eval_steps=6000), agent="firstfit"),
     "rec_s100_bestfit": dict(base="100", over=dict(reward_function="wr", eval_steps=2300), agent="bestfit"),
+    # `python main.py -a firstfit -e -c config/10.yml` (BASELINE configs[0]; CLI default reward wr) and the best-fit / ut
+    # variant: full 100 000-step episodes with the real placement-matrix rank (SVD) — summaries only, no action stream
+    "main_s10_firstfit_wr": dict(base="10", over=dict(reward_function="wr"), agent="firstfit", real_rank=True, keep_actions=False),
+    "main_s10_bestfit_ut": dict(base="10", over=dict(reward_function="ut"), agent="bestfit", real_rank=True, keep_actions=False),
 }
 
 
@@ -43,7 +47,8 @@ def run_case(name, spec):
     bestfit_mod.np = _StableArgsortNumpy()
     env = VmEnv(Config(**cfg))
     agent = FirstFitAgent(env) if spec["agent"] == "firstfit" else bestfit_mod.BestFitAgent(env)
-    env._get_rank = lambda: 0                      # only feeds info['rank'] (env.py:317); skips the per-step SVD
+    if not spec.get("real_rank"):
+        env._get_rank = lambda: 0                  # only feeds info['rank'] (env.py:317); skips the per-step SVD
     P, V, A = cfg["pms"], cfg["vms"], env.action_dim
     perturb = spec.get("perturb", 0.0)
     prng = np.random.default_rng(77)
@@ -58,18 +63,19 @@ def run_case(name, spec):
         if perturb:
             u = prng.random(V)
             action = np.where(u < perturb, P, action)              # suspend running VMs / keep waiting VMs waiting
-        actions.append(action.astype(np.int16))
+        if spec.get("keep_actions", True):
+            actions.append(action.astype(np.int16))
         obs, reward, done, truncated, info = env.step(action)
         agent.record_testing_step(reward, info)
     rec = agent.record
     summary = {k: (float(v) if np.ndim(v) == 0 else np.asarray(v, dtype=float).tolist()) for k, v in rec.get_summary().items()}
     out = {f"{name}.cfg_json": json.dumps(cfg), f"{name}.agent": spec["agent"], f"{name}.perturb": perturb,
-           f"{name}.actions": np.array(actions, np.int16),
+           f"{name}.actions": np.array(actions, np.int16).reshape(-1, V),
            f"{name}.pending": np.array(rec.pending_rates, np.float64),
            f"{name}.slowdown": np.array(rec.slowdown_rates, np.float64),
            f"{name}.lifetime": np.array(rec.vm_lifetime, np.int64),
            f"{name}.summary_json": json.dumps(summary)}
-    print(f"{name}: T={len(actions)} vms={len(rec.pending_rates)} allocated={len(rec.slowdown_rates)} "
+    print(f"{name}: T={env.timestep - 1} vms={len(rec.pending_rates)} allocated={len(rec.slowdown_rates)} "
           f"avg pending {summary['average pending']} median {summary['median pending']} slowdown {summary['average slowdown']} "
           f"life {summary['average VM life']}", flush=True)
     return out

@@ -531,3 +531,27 @@ def test_vm_size_sweep_reproduces_published_table(agent):
         g, w = got.split(","), want.split(",")
         assert g[0] == w[0] and g[2:] == w[2:], (got, want)
         assert abs(float(g[1]) - float(w[1])) <= 2e-3, (got, want)
+
+
+@pytest.mark.parametrize("case,agent,reward", [("main_s10_firstfit_wr", "firstfit", "wr"), ("main_s10_bestfit_ut", "bestfit", "ut")])
+def test_main_entry_reproduces_reference_summary(case, agent, reward, tmp_path):
+    """`python -m vmgym.main -a <agent> -r <reward> -e -c configs/10.yml` (the reference's main.py:31-87 flow: seed, env, agent,
+    Base.test, Record) prints the summary the reference's own Record produced for the same command (tests/golden/record.npz,
+    100 000 steps, real SVD rank): all 22 keys of Record.get_summary, as rounded by the reference."""
+    import json
+    import os
+    import yaml
+    from vmgym.main import Args, run
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    z = np.load(os.path.join(root, "tests", "golden", "record.npz"))
+    want = json.loads(str(z[f"{case}.summary_json"]))
+    cfg = yaml.safe_load(open(os.path.join(root, "configs", "10.yml")))
+    out = tmp_path / "record.json"
+    rec = run(Args(agent=agent, reward=reward, config=cfg, eval=True, silent=True, output=str(out)))
+    got = rec.get_summary()
+    assert list(got) == list(want)                               # same keys, same order
+    for k, v in want.items():
+        assert got[k] == pytest.approx(v, abs=1e-9 if isinstance(got[k], int) else 5e-4), (k, got[k], v)
+    exact = sum(1 for k, v in want.items() if got[k] == v)
+    assert exact >= len(want) - 1, {k: (got[k], v) for k, v in want.items() if got[k] != v}      # at most one last-digit flip
+    assert json.load(open(out))["summary"] == got

@@ -212,3 +212,24 @@ def test_oracle_reproduces_exp_vm_size_row():
         np.mean([np.round(r["return"], 3) for r in rows]), m("drop_rate_mean"), m("served"), m("suspend"), m("cpu_mean"),
         m("cpu_var"), m("mem_mean"), m("mem_var"), m("waiting_ratio_mean"))
     assert got == "firstfit,22539.4184,0.1232,22602,0,0.8504,0.0179,0.8497,0.0180,0.2226"
+
+
+def test_oracle_record_on_the_main_py_episode():
+    """`python main.py -a firstfit -e -c config/10.yml` (BASELINE configs[0]): the oracle's Record restatement on the full
+    100 000-step episode == the reference Record's per-VM keys and counters (golden: make_golden_record.py, real run)."""
+    import vmoracle as vo
+    g = load_record_case("main_s10_firstfit_wr")
+    env = vo.OracleVmEnv(vo.OracleConfig(**g["cfg"]))
+    env.eval()
+    env.enable_record(100000, 8192)
+    env.reset(seed=g["cfg"]["seed"])
+    n, st = env.rollout(vo.AGENT_FIRSTFIT, 100000, vo.TIE_STABLE)
+    assert n == 100000
+    pending, slowdown, life = env.record_lists()
+    assert np.array_equal(np.asarray(pending, np.float64), g["pending"])
+    assert np.array_equal(np.asarray(slowdown, np.float64), g["slowdown"])
+    assert np.array_equal(np.asarray(life, np.int64), g["lifetime"])
+    s = g["summary"]
+    assert int(st["served"]) == s["total served VMs"] and int(st["total_requests"]) == s["total requests"]
+    assert int(st["place"]) == s["total place actions"] and float(np.round(st["return"], 3)) == s["total rewards"]
+    assert float(np.round(st["drop_rate_mean"], 3)) == s["drop rate"] and float(np.round(st["cpu_mean"], 3)) == s["cpu mean"]

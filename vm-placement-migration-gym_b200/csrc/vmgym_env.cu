@@ -55,8 +55,8 @@ static int make_layout(const vmgym_config* c, DevLayout* L, vmgym_layout* pub)
     const int tmp_bytes = align_up((2 * l.Vp > 6 * l.Pp) ? 2 * l.Vp : 6 * l.Pp, 16);
     l.sm_fit = l.sm_tmp + tmp_bytes;                       // u32 fitm[128] | u16 cap[Pp]
     l.sm_prop = l.sm_fit + 512 + align_up(2 * l.Pp, 16);      // u32 prop[ceil(Vp/32)]: slots whose action differs
-    l.sm_stats = l.sm_prop + align_up(4 * ((l.Vp + 31) / 32), 16);   // f64[8] eval-summary sums of the launch
-    l.sm_bar = l.sm_stats + 64;
+    l.sm_stats = l.sm_prop + align_up(4 * ((l.Vp + 31) / 32), 16);   // f64[VMGYM_STATS] eval-summary sums of the launch
+    l.sm_bar = l.sm_stats + 8 * VMGYM_STATS;
     l.sm_stride = align_up(l.sm_bar + 16, 128);
     l.svc_cdf_smem = 0;                                    // service table stays in global memory (used on admissions only)
     l.sm_tables = align_up(SIZE_TABLE * 8 + SIZE_TABLE * 4 + ARR_CDF_SMEM * 8 + l.svc_cdf_smem * 8 + (SVC_BRACKETS + 1) * 2, 128);

@@ -437,7 +437,7 @@ struct StepResult { double reward; int terminated; int rejected; int waiting, ar
 // running sums for the eval summary (record.py:98-134, exp_performance.py:104-113): drop rate, waiting ratio,
 // per-step mean / population variance of PM cpu and memory, rejected actions, step count
 template <typename PT>
-__device__ __noinline__ void stats_update(const Env<PT> e, const StepResult res, double* st_acc)
+__device__ __noinline__ void stats_update(const Env<PT> e, const StepResult res, double* st_acc, int cap_target)
 {
     const int P = e.P, lane = e.lane;
     const double* cpu = e.cpu();
@@ -451,12 +451,30 @@ __device__ __noinline__ void stats_update(const Env<PT> e, const StepResult res,
         vc += dc * dc; vm += dm * dm;
     }
     vc = warp_sum(vc) / P; vm = warp_sum(vm) / P;
+    // what Record additionally averages over the episode (record.py:127-133): target means (env.py:116-121: size sums of
+    // the existing VMs over P, capped), and the rank of the placement matrix = number of PMs hosting a VM (env.py:319-325)
+    int used = 0;
+    for (int q = lane; q < P; q += 32) used += cpu[q] != 0.0 ? 1 : 0;
+    used = __reduce_add_sync(FULL, used);
+    unsigned csum = 0, msum = 0;
+    const PT* place = e.place();
+    const uint8_t* cc = e.cpuc();
+    const uint8_t* mcode = e.memc();
+    for (int v = lane; v < e.V; v += 32)
+        if ((int)place[v] <= P) { csum += cc[v] & 0x7f; msum += mcode[v]; }
+    csum = __reduce_add_sync(FULL, csum); msum = __reduce_add_sync(FULL, msum);
     if (lane == 0) {
         const int tot = e.sc()->total_requests;
         st_acc[0] += tot ? (double)e.sc()->dropped_requests / (double)tot : 0.0;
         st_acc[1] += res.arrived ? (double)res.waiting / (double)res.arrived : 0.0;
         st_acc[2] += mc; st_acc[3] += vc; st_acc[4] += mm; st_acc[5] += vm;
         st_acc[6] += res.rejected; st_acc[7] += 1;
+        st_acc[8] += mc * mc; st_acc[9] += mm * mm;                 // with [3] / [5]: E[x^2] for the global std (np.std over T x P)
+        double tc = (double)csum / 100.0 / P, tm = (double)msum / 100.0 / P;
+        if (cap_target && tc > 1.0) tc = 1.0;
+        if (cap_target && tm > 1.0) tm = 1.0;
+        st_acc[10] += tc; st_acc[11] += tm;
+        st_acc[12] += used;
     }
 }
 
@@ -942,7 +960,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
         StepResult res;
         res.reward = 0.0; res.terminated = 0; res.rejected = 0; res.waiting = 0; res.arrived = 0; res.changed = 0;
         double* st_acc = reinterpret_cast<double*>(base + L.sm_stats);     // per-launch stats sums (lane 0)
-        if (p.out.d_stats && lane < 8) st_acc[lane] = 0.0;
+        if (p.out.d_stats && lane < VMGYM_STATS) st_acc[lane] = 0.0;
         // STATUS_QUIET: "a fused agent's act() followed by the env's apply loop would change nothing".  It is
         // established by a full evaluation after which the step changed no placement (the agent proposed nothing, or
         // every proposal was rejected by the fp64 capacity check — SURVEY App. B-2) and nothing departed or was
@@ -1003,7 +1021,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
             } else if (quiet && agent_k != VMGYM_AGENT_NONE) {
                 res.rejected = quiet_rejected;        // the skipped proposals would have been rejected again
             }
-            if (p.out.d_stats) stats_update(e, res, st_acc);
+            if (p.out.d_stats) stats_update(e, res, st_acc, p.cap_target);
             if (res.terminated) break;
         }
 
@@ -1015,8 +1033,8 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
             if (p.out.d_reward) p.out.d_reward[env] = res.reward;
             if (p.out.d_terminated) p.out.d_terminated[env] = (uint8_t)res.terminated;
             if (p.out.d_stats) {
-                double* st = p.out.d_stats + env * 8;
-                for (int k = 0; k < 8; k++) st[k] += st_acc[k];
+                double* st = p.out.d_stats + env * VMGYM_STATS;
+                for (int k = 0; k < VMGYM_STATS; k++) st[k] += st_acc[k];
             }
         }
 

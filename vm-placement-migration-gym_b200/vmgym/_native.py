@@ -57,6 +57,7 @@ class Outputs(C.Structure):
 
 
 VMSTAT_BINS = 1024
+STATS = 16          # doubles per env in vmgym_outputs.d_stats (VMGYM_STATS)
 
 
 # offsets inside struct vmgym_env_scalars (include/vmgym.h)

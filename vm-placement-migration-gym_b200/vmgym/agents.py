@@ -13,7 +13,66 @@ import torch
 from . import _native as nv
 
 
-class HeuristicAgent:
+class AgentBase:
+    """The parts of the reference's Base (src/agents/base.py:15-149) every agent shares: optional TensorBoard log,
+    and `test` — one evaluation episode (eval mode, reset(seed), act/step until done) returning a Record."""
+    name = "Agent"
+    writer = None
+
+    def set_log(self, jobname, logdir):                      # base.py:27-41
+        if logdir:
+            try:
+                from time import gmtime, strftime
+                from torch.utils.tensorboard import SummaryWriter
+                self.writer = SummaryWriter(f"{logdir}/{strftime('%Y%m%d', gmtime())}-{self.name}-{jobname}")
+            except Exception:
+                self.writer = None
+
+    def end_log(self):                                       # base.py:127-129
+        if self.writer:
+            self.writer.close()
+
+    def _fused_kind(self):
+        return None                                          # heuristic agents: the name of the fused device agent
+
+    def test(self, show: bool = False, output: str | None = None, debug: bool = False):
+        """base.py:63-124 on every env of the batch.  Heuristic agents run the whole episode in the fused kernel; learned
+        agents loop act/step.  The episode statistics (Record.get_summary) are accumulated on the device."""
+        from .record import Record
+        vec = getattr(self.env, "vec", self.env)
+        vec.enable_vm_stats()
+        self.eval()
+        kind = self._fused_kind()
+        if kind is not None and not debug:
+            summary = vec.evaluate(kind, seeds=self._test_seeds(vec), tiebreak=getattr(self, "tiebreak", None))
+        else:
+            vec.eval(True)
+            obs, _ = vec.reset(seed=self._test_seeds(vec))
+            done = False
+            while not done:
+                if debug and hasattr(self.env, "render"):
+                    self.env.render()
+                action = self.act(obs)
+                obs, reward, term, _, info = vec.step(action, want_stats=True)
+                done = bool(term.all().item())
+            summary = vec.summary()
+        record = Record(self.name, vec.config, getattr(self, "config", None), summary)
+        if show:
+            print(vec.config)
+            for k, v in record.get_summary().items():
+                print("%s: %.2f" % (k, v))
+        if output:
+            record.save(output)
+        self.record = record
+        return record
+
+    @staticmethod
+    def _test_seeds(vec):
+        return np.asarray([int(c.seed) for c in vec.env_configs] if getattr(vec, "env_configs", None)
+                          else int(vec.config.seed) + np.arange(vec.num_envs), np.int64)
+
+
+class HeuristicAgent(AgentBase):
     kind = nv.AGENT_NONE
     name = "HeuristicAgent"
 
@@ -66,17 +125,8 @@ class HeuristicAgent:
             return a[0] if single else a
         return action[0] if single else action
 
-    def test(self, steps: int | None = None):
-        """Base.test (base.py:63-86) through the gym surface: eval mode, reset(seed), act/step until done."""
-        env = self.env
-        env.eval()
-        obs, _ = env.reset(seed=env.config.seed)
-        done, ret, n = False, 0.0, 0
-        while not done and (steps is None or n < steps):
-            obs, reward, done, _, info = env.step(self.act(obs))
-            ret += reward
-            n += 1
-        return ret, n
+    def _fused_kind(self):
+        return {nv.AGENT_FIRSTFIT: "firstfit", nv.AGENT_BESTFIT: "bestfit"}.get(self.kind)
 
 
 class FirstFitAgent(HeuristicAgent):

@@ -18,6 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _native as nv
+from .agents import AgentBase
 
 
 @dataclass
@@ -117,7 +118,7 @@ class Network(nn.Module):
             m.reset_noise()
 
 
-class DRLVMPAgent:
+class DRLVMPAgent(AgentBase):
     name = "DRLVMPAgent"
 
     def __init__(self, env, config: DRLVMPConfig | None = None):

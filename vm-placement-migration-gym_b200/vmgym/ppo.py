@@ -23,6 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import _native as nv
+from .agents import AgentBase
 
 
 @dataclass
@@ -180,7 +181,7 @@ def gae(rewards, values, next_values, dones, gamma: float, lamda: float):
     return adv, ret
 
 
-class PPOAgent:
+class PPOAgent(AgentBase):
     """Reference-shaped agent (Base API: learn / act / save_model / load_model / eval) over a VecVmEnv or VmEnv."""
 
     name = "PPOAgent"

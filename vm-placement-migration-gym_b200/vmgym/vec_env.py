@@ -115,7 +115,7 @@ class VecVmEnv:
             self.truncated = torch.zeros(N, dtype=torch.bool, device=self.device)   # always False (env.py:102)
             self.valid = torch.zeros((N, self.V), dtype=torch.uint8, device=self.device)
             self.agent_action = torch.zeros((N, self.V), dtype=self.place_dtype, device=self.device)
-            self.stats = torch.zeros((N, 8), dtype=torch.float64, device=self.device)
+            self.stats = torch.zeros((N, nv.STATS), dtype=torch.float64, device=self.device)
         self._trace_steps = trace_steps
         self._max_admissions = max_admissions
         self._streams = None
@@ -240,11 +240,11 @@ class VecVmEnv:
             self._out_cache[key] = out
         return out
 
-    def step(self, action, want_obs: bool = True, want_valid: bool = True, host_outputs=None):
+    def step(self, action, want_obs: bool = True, want_valid: bool = True, host_outputs=None, want_stats: bool = False):
         """env.py:66-103 for all envs.  `action`: [N, V] device tensor (uint8 / int16 / int64), numpy int array, or a
         PINNED host tensor (device-mapped under UVA: the kernel reads it over PCIe, no copy-engine transfer).
         `host_outputs`: optional (reward f64 [N], terminated u8 [N]) pinned host tensors the kernel writes directly,
-        instead of the env's device buffers."""
+        instead of the env's device buffers.  `want_stats`: accumulate the episode sums behind summary()."""
         if not isinstance(action, torch.Tensor):
             action = torch.from_numpy(np.ascontiguousarray(action, dtype=np.int64)).to(self.device, non_blocking=True)
         elif not action.is_cuda and not action.is_pinned():
@@ -254,7 +254,7 @@ class VecVmEnv:
         if action.dtype not in _TORCH_ACTION_DTYPES:
             action = action.to(torch.int64)
         action = action.contiguous()
-        out = self._outputs(want_obs=want_obs, want_valid=want_valid)
+        out = self._outputs(want_obs=want_obs, want_valid=want_valid, want_stats=want_stats)
         if host_outputs is not None:
             rew_h, term_h = host_outputs
             if not (rew_h.is_pinned() and term_h.is_pinned() and rew_h.dtype == torch.float64 and term_h.dtype == torch.uint8
@@ -302,6 +302,11 @@ class VecVmEnv:
             self.agent_step(agent, n_steps=n, want_obs=False, want_action=False, want_valid=False, want_stats=True,
                             tiebreak=tiebreak)
             done += n
+        return self.summary()
+
+    def summary(self):
+        """Record.get_summary (src/record.py:110-134) of the episode so far, per env (unrounded float64 / int64 numpy arrays
+        [N]); needs the steps to have run with want_stats (evaluate does) and, for the per-VM keys, enable_vm_stats()."""
         c = self.counters()
         st = self.stats.cpu().numpy()
         steps = np.maximum(st[:, 7], 1.0)
@@ -311,7 +316,11 @@ class VecVmEnv:
                 "total suspend actions": c["suspend_actions"], "total place actions": c["place_actions"],
                 "dropped requests": c["dropped_requests"], "drop rate": st[:, 0] / steps, "waiting ratio": st[:, 1] / steps,
                 "cpu mean": st[:, 2] / steps, "cpu var": st[:, 3] / steps, "memory mean": st[:, 4] / steps,
-                "memory var": st[:, 5] / steps, "rejected actions": st[:, 6], "steps": st[:, 7]}
+                "memory var": st[:, 5] / steps, "rejected actions": st[:, 6], "steps": st[:, 7],
+                # np.std over the whole T x P matrix (record.py:128,131): E[x^2] - mean^2 with E[x^2] = mean_t(var_p + mean_p^2)
+                "cpu std": np.sqrt(np.maximum((st[:, 3] + st[:, 8]) / steps - (st[:, 2] / steps) ** 2, 0.0)),
+                "memory std": np.sqrt(np.maximum((st[:, 5] + st[:, 9]) / steps - (st[:, 4] / steps) ** 2, 0.0)),
+                "cpu mean target": st[:, 10] / steps, "memory mean target": st[:, 11] / steps, "rank mean": st[:, 12] / steps}
 
     # ---- Record's per-VM statistics (src/record.py:34-96,110-134) -------------------------------------------
     def enable_vm_stats(self):
