@@ -302,3 +302,31 @@ def test_ppo_eval_rollout_fused_and_unfused():
         assert ret.shape == (32,) and torch.isfinite(ret).all() and (ret <= 0).all()
         assert c["timestep"].min() == 13 and c["place_actions"].sum() > 0
         assert torch.allclose(ret, torch.from_numpy(c["episode_return"]).to(ret.device))
+
+
+@pytest.mark.parametrize("which", ["ppo", "drlvmp"])
+def test_learned_agents_test_returns_a_record(which, tmp_path):
+    """Base.test (base.py:63-124) for the learned agents: act/step loop until the episode ends, Record summary from the
+    device-side sums (steps, requests, per-VM keys), JSON output."""
+    import json
+    import torch
+    from vmgym import Config, VmEnv
+    kw = dict(pms=10, vms=30, arrival_rate=0.4, service_length=20, training_steps=50, eval_steps=80, reward_function="wr",
+              allow_null_action=True, seed=3)
+    env = VmEnv(Config(**kw), rng="philox")
+    torch.manual_seed(0)
+    if which == "ppo":
+        from src.agents.ppo import PPOAgent, PPOConfig
+        agent = PPOAgent(env, PPOConfig(hidden_size=32, migration_ratio=0.3))
+    else:
+        from src.agents.drlvmp import DRLVMPAgent, DRLVMPConfig
+        agent = DRLVMPAgent(env, DRLVMPConfig(hidden_size=16))
+    out = tmp_path / "r.json"
+    rec = agent.test(output=str(out))
+    s = rec.get_summary()
+    assert len(s) == 22 and s["total requests"] > 0 and s["total place actions"] >= 0
+    assert float(rec.raw["steps"][0]) == 80
+    c = env.vec.counters()
+    assert s["total served VMs"] == int(c["served_requests"][0]) and s["total suspend actions"] == int(c["suspend_actions"][0])
+    assert json.load(open(out))["summary"] == s
+    agent.set_log("job", None); agent.end_log()
