@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/vmgym.h"
 #include "vmgym_sample.cuh"
@@ -268,6 +269,152 @@ struct FusedOut {
     uint32_t counter;
 };
 
+// Per-row running state of the fused epilogue.
+struct RowState {
+    float m, ssum, tsum, best_z, z_given;
+    int best_a;
+};
+
+// One chunk of 32 accumulator columns of this thread's row.  FULL: all 32 columns are real actions — straight-line code,
+// 32 independent exponentials in flight.  !FULL (the last chunk when A is not a multiple of 32): only the groups of 4
+// columns that hold real actions are touched (A = 102: 2 of 8 groups).
+template <bool FULL>
+__device__ __forceinline__ void fused_chunk(const FusedOut& fo, const float* s_bias, const uint32_t (&r)[32], uint32_t iw, int c0, int A,
+                                            int act_given, const vmgym::Philox4& rnd, RowState& st)
+{
+    const int ncol = FULL ? 32 : min(32, A - c0), ngr = FULL ? 8 : (ncol + 3) >> 2;
+    float z[32];
+    float cm = -1e30f;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        if (FULL || t < ngr) {
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const int j = 4 * t + jj;
+                float x = __uint_as_float(r[j]) + s_bias[c0 + j];
+                if ((iw >> j) & 1u) x = -1e7f;                       // ppo.py:119
+                if (!FULL && j >= ncol) x = -1e30f;                  // padding columns inside the last group
+                z[j] = x;
+                cm = fmaxf(cm, x);
+            }
+        } else {
+            z[4 * t] = z[4 * t + 1] = z[4 * t + 2] = z[4 * t + 3] = -1e30f;
+        }
+    }
+    float m = st.m, ssum = st.ssum, tsum = st.tsum;
+    if (cm > m) {
+        if (c0 > 0) { const float d = cm - m, sc = vmgym::fast_exp(-d); tsum = (tsum - d * ssum) * sc; ssum *= sc; }
+        m = cm;
+    }
+    // e^(z - m) summed as a binary tree over 8 groups of 4 columns (= the order of a warp butterfly, which is what the
+    // stand-alone heads kernel uses): group sums g[t], chunk weight w
+    float g[8];
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        g[t] = 0.f;
+        if (FULL || t < ngr) {
+            const float x0 = z[4 * t] - m, x1 = z[4 * t + 1] - m, x2 = z[4 * t + 2] - m, x3 = z[4 * t + 3] - m;
+            const float e0 = vmgym::fast_exp(x0), e1 = vmgym::fast_exp(x1), e2 = vmgym::fast_exp(x2), e3 = vmgym::fast_exp(x3);
+            g[t] = (e0 + e1) + (e2 + e3);
+            t0 += e0 * x0; t1 += e1 * x1; t2 += e2 * x2; t3 += e3 * x3;
+        }
+    }
+    const float w = ((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]));
+    const float ssum_new = ssum + w;
+    tsum += (t0 + t1) + (t2 + t3);
+    if (fo.action_in) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) if (c0 + j == act_given) st.z_given = z[j];
+    } else {
+        // streaming inverse-CDF (vmgym_sample.cuh): this chunk replaces the choice iff u * S < w; the column is where the
+        // cumulative sum passes u * S — first over the groups, then inside the group.  Branch-free.
+        const float target = vmgym::chunk_uniform(rnd, c0 >> 5) * ssum_new;
+        float cum = 0.f, base = 0.f, blast = 0.f;
+        int tsel = -1, tlast = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const float prev = cum;
+            cum += g[t];
+            if (g[t] > 0.f) { tlast = t; blast = prev; }
+            if (tsel < 0 && cum > target) { tsel = t; base = prev; }
+        }
+        if (tsel < 0) { tsel = tlast; base = blast; }
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;          // the 4 logits of group tsel, without a dynamic register index
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const bool hit = t == tsel;
+            a0 = hit ? z[4 * t] : a0; a1 = hit ? z[4 * t + 1] : a1; a2 = hit ? z[4 * t + 2] : a2; a3 = hit ? z[4 * t + 3] : a3;
+            asm volatile("" : "+f"(a0), "+f"(a1), "+f"(a2), "+f"(a3));      // keep the select chain a select chain
+        }
+        const float e0 = vmgym::fast_exp(a0 - m), e1 = vmgym::fast_exp(a1 - m), e2 = vmgym::fast_exp(a2 - m), e3 = vmgym::fast_exp(a3 - m);
+        int k = -1, klast = 0;
+        float c2 = base + e0;
+        if (c2 > target) k = 0;
+        c2 += e1; if (e1 > 0.f) klast = 1; if (k < 0 && c2 > target) k = 1;
+        c2 += e2; if (e2 > 0.f) klast = 2; if (k < 0 && c2 > target) k = 2;
+        c2 += e3; if (e3 > 0.f) klast = 3; if (k < 0 && c2 > target) k = 3;
+        if (k < 0) k = klast;
+        if (target < w) {
+            st.best_a = c0 + 4 * tsel + k;
+            st.best_z = k == 0 ? a0 : (k == 1 ? a1 : (k == 2 ? a2 : a3));
+        }
+    }
+    st.m = m; st.ssum = ssum_new; st.tsum = tsum;
+}
+
+// The fused epilogue for ONE row (thread = env row e) of ONE VM tile: masked log-softmax statistics relative to a running
+// max (s = sum e^(z-m), t = sum e^(z-m) (z-m), merged chunk by chunk with one rescale per chunk), streaming inverse-CDF
+// sample (or evaluation of a stored action), log-prob and entropy, straight out of the TMEM accumulator `tmem_acc`
+// (column 0 of this tile's accumulator; the lane offset of the calling warp is added here).
+// What a row's epilogue needs from global memory and the RNG — fetched BEFORE waiting for the accumulator so that the
+// loads (one 16-byte mask word and one action byte per row, 4.8 KB apart between rows) overlap the MMA.
+struct RowIn {
+    uint4 inv;
+    int act_given;
+    vmgym::Philox4 rnd;
+};
+__device__ __forceinline__ RowIn fused_epilogue_prefetch(const FusedOut& fo, int q, int lane, int m0, int v, int M)
+{
+    const int e = m0 + q * 32 + lane;
+    RowIn in;
+    in.inv = make_uint4(0u, 0u, 0u, 0u);
+    if (fo.mask_bits && e < M) in.inv = reinterpret_cast<const uint4*>(fo.mask_bits)[(long long)e * fo.V + v];
+    in.act_given = -1;
+    if (fo.action_in && e < M) in.act_given = reinterpret_cast<const uint8_t*>(fo.action_in)[(long long)e * fo.V + v];
+    // sampling: one Philox call per row, word c = the uniform of chunk c (vmgym_sample.cuh)
+    in.rnd = vmgym::Philox4{0u, 0u, 0u, 0u};
+    if (!fo.action_in) in.rnd = vmgym::sample_block(v, 0, (uint32_t)e, fo.seed, fo.counter);
+    return in;
+}
+__device__ __forceinline__ void fused_epilogue_row(const FusedOut& fo, const float* s_bias, uint32_t tmem_acc, const RowIn& in, int q,
+                                                   int lane, int m0, int v, int M)
+{
+    const int e = m0 + q * 32 + lane;
+    const int A = fo.A;
+    const uint4 inv = in.inv;
+    const int act_given = in.act_given;
+    const vmgym::Philox4 rnd = in.rnd;
+    RowState st = {-1e30f, 0.f, 0.f, 0.f, 0.f, 0};
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN && c0 < A; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_row32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        const uint32_t iw = c0 == 0 ? inv.x : (c0 == 32 ? inv.y : (c0 == 64 ? inv.z : inv.w));
+        if (c0 + 32 <= A) fused_chunk<true>(fo, s_bias, r, iw, c0, A, act_given, rnd, st);
+        else fused_chunk<false>(fo, s_bias, r, iw, c0, A, act_given, rnd, st);
+    }
+    if (e < M) {
+        const float ls = __logf(st.ssum);
+        const int act = fo.action_in ? act_given : st.best_a;
+        const float za = fo.action_in ? st.z_given : st.best_z;
+        const long long o = (long long)e * fo.V + v;
+        if (fo.action_out) fo.action_out[o] = (uint8_t)act;
+        fo.logprob[o] = ((unsigned)act < (unsigned)A) ? (za - st.m) - ls : 0.f;
+        fo.entropy[o] = ls - st.tsum / st.ssum;                      // -sum p log p
+    }
+}
+
 __global__ void __launch_bounds__(THREADS, 1) policy_fused_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                    const __grid_constant__ CUtensorMap map_w, FusedOut fo, int M, int K)
 {
@@ -287,108 +434,156 @@ __global__ void __launch_bounds__(THREADS, 1) policy_fused_kernel(const __grid_c
         if (lane == 0) pipe_mma(pipe, tmem_base, k_blocks);
     } else {
         // ===== fused epilogue: thread = env row, registers = this VM's logits =====
-        const int q = warp & 3;
-        const int e = m0 + q * 32 + lane;
-        const int A = fo.A;
-        uint4 inv = make_uint4(0u, 0u, 0u, 0u);
-        if (fo.mask_bits && e < M) inv = reinterpret_cast<const uint4*>(fo.mask_bits)[(long long)e * fo.V + v];
-        int act_given = -1;
-        if (fo.action_in && e < M) act_given = reinterpret_cast<const uint8_t*>(fo.action_in)[(long long)e * fo.V + v];
+        const RowIn in = fused_epilogue_prefetch(fo, warp & 3, lane, m0, v, M);
         mbar_wait(pipe.tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // log-softmax statistics relative to the running max m:  s = sum e^(z-m),  t = sum e^(z-m) (z-m), merged chunk by
-        // chunk (32 columns): one max + one rescale per chunk, then 32 independent exponentials (instruction-level parallelism)
-        float m = -1e30f, ssum = 0.f, tsum = 0.f, best_z = 0.f, z_given = 0.f;
-        int best_a = 0;
-        // sampling: one Philox call per row, word c = the uniform of chunk c (vmgym_sample.cuh)
-        vmgym::Philox4 rnd = {0u, 0u, 0u, 0u};
-        if (!fo.action_in) rnd = vmgym::sample_block(v, 0, (uint32_t)e, fo.seed, fo.counter);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN && c0 < A; c0 += 32) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            tmem_ld_row32(taddr, r);
-            const uint32_t iw = c0 == 0 ? inv.x : (c0 == 32 ? inv.y : (c0 == 64 ? inv.z : inv.w));
-            float z[32];
-            float cm = -1e30f;
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const int a = c0 + j;
-                float x = __uint_as_float(r[j]) + s_bias[a];
-                if ((iw >> j) & 1u) x = -1e7f;                           // ppo.py:119
-                if (a >= A) x = -1e30f;                                  // padding columns of the 128-wide tile
-                z[j] = x;
-                cm = fmaxf(cm, x);
-            }
-            if (cm > m) {
-                if (c0 > 0) { const float d = cm - m, sc = __expf(-d); tsum = (tsum - d * ssum) * sc; ssum *= sc; }
-                m = cm;
-            }
-            // e^(z - m) summed as a binary tree over 8 groups of 4 columns (= the order of a warp butterfly, which is what
-            // the stand-alone heads kernel uses): group sums g[t], chunk weight w
-            float g[8];
-            float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-#pragma unroll
-            for (int t = 0; t < 8; t++) {
-                const float x0 = z[4 * t] - m, x1 = z[4 * t + 1] - m, x2 = z[4 * t + 2] - m, x3 = z[4 * t + 3] - m;
-                const float e0 = __expf(x0), e1 = __expf(x1), e2 = __expf(x2), e3 = __expf(x3);
-                g[t] = (e0 + e1) + (e2 + e3);
-                t0 += e0 * x0; t1 += e1 * x1; t2 += e2 * x2; t3 += e3 * x3;
-            }
-            const float w = ((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]));
-            const float ssum_new = ssum + w;
-            tsum += (t0 + t1) + (t2 + t3);
-            if (fo.action_in) {
-#pragma unroll
-                for (int j = 0; j < 32; j++) if (c0 + j == act_given) z_given = z[j];
-            } else {
-                // streaming inverse-CDF (vmgym_sample.cuh): this chunk replaces the choice iff u * S < w; the column is
-                // where the cumulative sum passes u * S — first over the groups, then inside the group.  Branch-free.
-                const float target = vmgym::chunk_uniform(rnd, c0 >> 5) * ssum_new;
-                float cum = 0.f, base = 0.f, blast = 0.f;
-                int tsel = -1, tlast = 0;
-#pragma unroll
-                for (int t = 0; t < 8; t++) {
-                    const float prev = cum;
-                    cum += g[t];
-                    if (g[t] > 0.f) { tlast = t; blast = prev; }
-                    if (tsel < 0 && cum > target) { tsel = t; base = prev; }
-                }
-                if (tsel < 0) { tsel = tlast; base = blast; }
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;          // the 4 logits of group tsel, without a dynamic register index
-#pragma unroll
-                for (int t = 0; t < 8; t++) {
-                    const bool hit = t == tsel;
-                    a0 = hit ? z[4 * t] : a0; a1 = hit ? z[4 * t + 1] : a1; a2 = hit ? z[4 * t + 2] : a2; a3 = hit ? z[4 * t + 3] : a3;
-                    asm volatile("" : "+f"(a0), "+f"(a1), "+f"(a2), "+f"(a3));      // keep the select chain a select chain
-                }
-                const float e0 = __expf(a0 - m), e1 = __expf(a1 - m), e2 = __expf(a2 - m), e3 = __expf(a3 - m);
-                int k = -1, klast = 0;
-                float c2 = base + e0;
-                if (c2 > target) k = 0;
-                c2 += e1; if (e1 > 0.f) klast = 1; if (k < 0 && c2 > target) k = 1;
-                c2 += e2; if (e2 > 0.f) klast = 2; if (k < 0 && c2 > target) k = 2;
-                c2 += e3; if (e3 > 0.f) klast = 3; if (k < 0 && c2 > target) k = 3;
-                if (k < 0) k = klast;
-                if (target < w) {
-                    best_a = c0 + 4 * tsel + k;
-                    best_z = k == 0 ? a0 : (k == 1 ? a1 : (k == 2 ? a2 : a3));
-                }
-            }
-            ssum = ssum_new;
-        }
-        if (e < M) {
-            const float ls = __logf(ssum);
-            const int act = fo.action_in ? act_given : best_a;
-            const float za = fo.action_in ? z_given : best_z;
-            const long long o = (long long)e * fo.V + v;
-            if (fo.action_out) fo.action_out[o] = (uint8_t)act;
-            fo.logprob[o] = ((unsigned)act < (unsigned)A) ? (za - m) - ls : 0.f;
-            fo.entropy[o] = ls - tsum / ssum;                            // -sum p log p
-        }
+        fused_epilogue_row(fo, s_bias, tmem_base, in, warp & 3, lane, m0, v, M);
     }
     pipe_teardown(tmem_base, warp);
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Persistent fused actor head (K <= 512): one CTA per SM walks "units" = (env tile, chunk of VMs).
+//   * the 128 x K activation tile of the unit stays RESIDENT in shared memory (8 K-slices of 16 KB, loaded once per unit):
+//     only the W_v tiles stream through a 4-stage ring, which halves the L2 -> SMEM operand traffic of the tile-per-CTA kernel;
+//   * P_GROUPS accumulators in TMEM (128 columns each) and as many epilogue warpgroups: while group g samples tile t out
+//     of accumulator g, the MMA warp already fills the other accumulators with tiles t+1, ...
+// Roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2+4g .. 5+4g epilogue group g
+// (a warp may touch TMEM lanes 32 (warp % 4) .. +31, so both groups cover all 128 lanes).
+// ---------------------------------------------------------------------------------------------------
+constexpr int P_GROUPS = 3;                                    // epilogue warpgroups = TMEM accumulators in flight
+constexpr int P_THREADS = 64 + 128 * P_GROUPS;
+constexpr int P_TMEM_COLS = P_GROUPS <= 2 ? 256 : 512;         // power of two >= P_GROUPS * 128
+constexpr int P_WSTAGES = 5;
+constexpr int P_KSLICES = 8;                                   // K <= 512
+constexpr int P_SLICE_BYTES = BM * BK * 2;                     // 16 KiB: one K-slice of a 128-row operand tile
+constexpr int P_VCHUNK = 10;                                   // VM tiles per unit
+constexpr size_t P_SMEM_BYTES = (size_t)(P_KSLICES + P_WSTAGES) * P_SLICE_BYTES + 1024 /* alignment */ + 2048 /* barriers, bias x2 */;
+
+__global__ void __launch_bounds__(P_THREADS, 1) policy_fused_persistent_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                                const __grid_constant__ CUtensorMap map_w, FusedOut fo,
+                                                                                int M, int K)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* s_a = smem;                                              // P_KSLICES slices, resident per unit
+    unsigned char* s_w = smem + (size_t)P_KSLICES * P_SLICE_BYTES;          // ring of W K-slices
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + (size_t)P_WSTAGES * P_SLICE_BYTES);
+    uint64_t* w_full = bars;                 // [P_WSTAGES]
+    uint64_t* w_empty = bars + P_WSTAGES;    // [P_WSTAGES]
+    uint64_t* a_full = bars + 2 * P_WSTAGES; // [1]
+    uint64_t* a_empty = a_full + 1;          // [1]
+    uint64_t* acc_full = a_empty + 1;        // [P_GROUPS]
+    uint64_t* acc_empty = acc_full + P_GROUPS;   // [P_GROUPS]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + P_GROUPS);
+    float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);                 // [P_GROUPS][128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k_blocks = (K + BK - 1) / BK;
+    const int m_tiles = (M + BM - 1) / BM;
+    const int v_chunks = (fo.V + P_VCHUNK - 1) / P_VCHUNK;
+    const int n_units = m_tiles * v_chunks;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < P_WSTAGES; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        mbar_init(a_full, 1); mbar_init(a_empty, 1);
+        for (int g = 0; g < P_GROUPS; g++) { mbar_init(&acc_full[g], 1); mbar_init(&acc_empty[g], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(P_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t wcount = 0, ucount = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ucount++) {
+                const int mt = u / v_chunks, vc = u % v_chunks;
+                const int v0 = vc * P_VCHUNK, v1 = min(fo.V, v0 + P_VCHUNK);
+                mbar_wait(a_empty, (ucount & 1u) ^ 1u);                        // previous unit's MMAs have read A
+                mbar_expect_tx(a_full, (uint32_t)(k_blocks * P_SLICE_BYTES));
+                for (int kb = 0; kb < k_blocks; kb++) tma_load_2d(s_a + (size_t)kb * P_SLICE_BYTES, &map_a, kb * BK, mt * BM, a_full);
+                for (int v = v0; v < v1; v++) {
+                    for (int kb = 0; kb < k_blocks; kb++, wcount++) {
+                        const int s = wcount % P_WSTAGES;
+                        mbar_wait(&w_empty[s], ((wcount / P_WSTAGES) & 1u) ^ 1u);
+                        mbar_expect_tx(&w_full[s], P_SLICE_BYTES);
+                        tma_load_2d(s_w + (size_t)s * P_SLICE_BYTES, &map_w, kb * BK, v * BN, &w_full[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (single thread) =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+            uint32_t wcount = 0, ucount = 0, tcount = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ucount++) {
+                const int vc = u % v_chunks;
+                const int v0 = vc * P_VCHUNK, v1 = min(fo.V, v0 + P_VCHUNK);
+                mbar_wait(a_full, ucount & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int v = v0; v < v1; v++, tcount++) {
+                    const uint32_t g = tcount % P_GROUPS;
+                    mbar_wait(&acc_empty[g], ((tcount / P_GROUPS) & 1u) ^ 1u); // epilogue group g has drained its accumulator
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t acc = tmem_base + g * TMEM_COLS;
+                    for (int kb = 0; kb < k_blocks; kb++, wcount++) {
+                        const int s = wcount % P_WSTAGES;
+                        mbar_wait(&w_full[s], (wcount / P_WSTAGES) & 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t sa = smem_u32(s_a + (size_t)kb * P_SLICE_BYTES);
+                        const uint32_t sb = smem_u32(s_w + (size_t)s * P_SLICE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; k++)
+                            umma_bf16(acc, umma_desc_sw128(sa + k * UMMA_K * 2), umma_desc_sw128(sb + k * UMMA_K * 2), idesc, (kb | k) ? 1u : 0u);
+                        umma_commit(&w_empty[s]);
+                    }
+                    umma_commit(&acc_full[g]);
+                }
+                umma_commit(a_empty);                                          // all MMAs reading this unit's A have retired
+            }
+        }
+    } else {
+        // ===== epilogue groups: group g = warps 2+4g .. 5+4g handles the tiles with tile index % P_GROUPS == g =====
+        const int g = (warp - 2) >> 2;
+        const int q = warp & 3;
+        const int tg = threadIdx.x - 64 - g * 128;                             // 0..127 inside the group
+        float* bias_g = s_bias + g * 128;
+        uint32_t tcount = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int mt = u / v_chunks, vc = u % v_chunks;
+            const int v0 = vc * P_VCHUNK, v1 = min(fo.V, v0 + P_VCHUNK);
+            for (int v = v0; v < v1; v++, tcount++) {
+                if (tcount % P_GROUPS != (uint32_t)g) continue;
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");    // previous tile's readers of bias_g are done
+                bias_g[tg] = fo.bias_pad[v * BN + tg];
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+                const RowIn in = fused_epilogue_prefetch(fo, q, lane, mt * BM, v, M);
+                mbar_wait(&acc_full[g], (tcount / P_GROUPS) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                fused_epilogue_row(fo, bias_g, tmem_base + g * TMEM_COLS, in, q, lane, mt * BM, v, M);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[g])) : "memory");
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(P_TMEM_COLS) : "memory");
+}
+
+
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -480,6 +675,28 @@ extern "C" int vmgym_policy_fused(const void* d_h_bf16, const void* d_wpad_bf16,
     FusedOut fo;
     fo.mask_bits = d_mask_bits; fo.bias_pad = d_bias_pad; fo.action_in = d_action_in; fo.action_out = d_action_out;
     fo.logprob = d_logprob; fo.entropy = d_entropy; fo.A = (int)A; fo.V = (int)V; fo.seed = seed; fo.counter = (uint32_t)counter;
+    // default: the persistent kernel whenever the activation tile fits (K <= 512); VMGYM_FUSED_PERSISTENT=0 selects the
+    // tile-per-CTA kernel (A/B experiments, and the fallback for wider hidden layers)
+    static const int persistent = getenv("VMGYM_FUSED_PERSISTENT") ? atoi(getenv("VMGYM_FUSED_PERSISTENT")) : 1;
+    if (persistent && K <= P_KSLICES * BK) {
+        static bool pattr_set = false;
+        static int n_sm = 0;
+        if (!pattr_set) {
+            cudaError_t e2 = cudaFuncSetAttribute(policy_fused_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_BYTES);
+            if (e2 != cudaSuccess) { vmgym_internal_set_error(cudaGetErrorString(e2)); return VMGYM_ECUDA; }
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            if (n_sm <= 0) n_sm = 148;
+            pattr_set = true;
+        }
+        const long long units = ((M + BM - 1) / BM) * ((V + P_VCHUNK - 1) / P_VCHUNK);
+        const unsigned ctas = (unsigned)(units < n_sm ? units : n_sm);
+        policy_fused_persistent_kernel<<<ctas, P_THREADS, P_SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, fo, (int)M, (int)K);
+        cudaError_t e3 = cudaGetLastError();
+        if (e3 != cudaSuccess) { vmgym_internal_set_error(cudaGetErrorString(e3)); return VMGYM_ECUDA; }
+        return VMGYM_OK;
+    }
     dim3 grid((unsigned)V, (unsigned)((M + BM - 1) / BM));
     policy_fused_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, fo, (int)M, (int)K);
     cudaError_t e = cudaGetLastError();

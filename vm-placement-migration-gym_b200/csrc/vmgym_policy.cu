@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
             float e = 0.f;
             if (i * 32 + lane < A) {
                 const float d = zl[i] - mx;
-                e = __expf(d);
+                e = fast_exp(d);
                 sez += e * d;
             }
             el[i] = e;
@@ -179,10 +179,10 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
                 float cm = x;
                 for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(FULL, cm, o));
                 if (cm > m_run) {
-                    if (i > 0) s_run *= __expf(-(cm - m_run));
+                    if (i > 0) s_run *= fast_exp(-(cm - m_run));
                     m_run = cm;
                 }
-                const float e = __expf(x - m_run);
+                const float e = fast_exp(x - m_run);
                 float sm = e;
                 sm += __shfl_xor_sync(FULL, sm, 1);
                 sm += __shfl_xor_sync(FULL, sm, 2);
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(256) heads_eval_kernel(const HeadParams p)
             float e = 0.f;
             if (sub + 8 * i < A && live) {
                 const float d = zl[i] - mx;
-                e = __expf(d);
+                e = fast_exp(d);
                 sez += e * d;
             }
             el[i] = e;

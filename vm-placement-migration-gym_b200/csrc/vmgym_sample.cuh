@@ -36,6 +36,15 @@ __device__ __forceinline__ float gumbel_from(const Philox4& r, int sub)
     return -__logf(-__logf(u));
 }
 
+// e^x as ex2.approx.ftz(x * log2 e): two instructions (the `__expf` intrinsic adds denormal handling around the same MUFU).
+// Both samplers use THIS function so that they see identical weights.
+__device__ __forceinline__ float fast_exp(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+
 // uniform in [0, 1) for chunk c of a row, from the row's block(s): 24 bits of word c & 3
 __device__ __forceinline__ float chunk_uniform(const Philox4& r, int c)
 {
