@@ -555,3 +555,24 @@ def test_main_entry_reproduces_reference_summary(case, agent, reward, tmp_path):
     exact = sum(1 for k, v in want.items() if got[k] == v)
     assert exact >= len(want) - 1, {k: (got[k], v) for k, v in want.items() if got[k] != v}      # at most one last-digit flip
     assert json.load(open(out))["summary"] == got
+
+
+def test_bench_gpu_arm_prints_the_contract_line():
+    """`python bench.py --steps 6 --warmup 3 --no-cpu --no-extras`: one JSON line with every key of the bench contract."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "6", "--warmup", "3", "--no-cpu", "--no-extras",
+                          "--batches", "4", "--envs", "512"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "gpu_launches", "e2e", "roofline", "clocks"):
+        assert k in d, k
+    assert d["steps"] == 6 and d["warmup"] == 3 and d["gpu_launches"] == 6 and d["n_gpus"] == 1 and d["value"] > 0
+    assert d["unit"] == "env-steps/s" and d["dtype"] == "f64" and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"]) and d["roofline"]["bound"] == "hbm"
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9 and "workload" in d["config"]

@@ -134,15 +134,17 @@ static int launch_step(StepParams& sp, cudaStream_t st)
     }
     // per (kernel, smem, warps) launch plan, computed once (also keeps these calls out of CUDA-graph capture)
     static thread_local size_t plan_smem = 0;
-    static thread_local int plan_w = 0, plan_occ = 1;
+    static thread_local int plan_w = 0, plan_occ = 1, plan_dev = -1;
     static thread_local void (*plan_kern)(const StepParams) = nullptr;
-    if (plan_smem != smem || plan_w != w || plan_kern != kern) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (plan_smem != smem || plan_w != w || plan_kern != kern || plan_dev != dev) {
         int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute");
         if (rc) return rc;
         int occ = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, w * 32, smem);
         plan_occ = occ < 1 ? 1 : occ;
-        plan_smem = smem; plan_w = w; plan_kern = kern;
+        plan_smem = smem; plan_w = w; plan_kern = kern; plan_dev = dev;
     }
     const int occ = plan_occ;
     long long blocks = (sp.n_envs + w - 1) / w;

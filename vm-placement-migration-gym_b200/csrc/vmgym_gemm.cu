@@ -617,6 +617,17 @@ static int make_map(CUtensorMap* map, const void* ptr, int rows, int K, int box_
     return r == CUDA_SUCCESS ? 0 : -2;
 }
 
+// cudaFuncSetAttribute is per device: remember which devices have been configured for a kernel (slot 0..2)
+static bool attr_done(int slot, bool mark)
+{
+    static bool done[3][64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (mark) done[slot][dev] = true;
+    return done[slot][dev];
+}
+
 }  // namespace vmgym_gemm
 
 extern "C" int vmgym_linear_bf16(const void* d_a_bf16, const void* d_w_bf16, const float* d_bias, float* d_c, int64_t M, int64_t N,
@@ -634,11 +645,10 @@ extern "C" int vmgym_linear_bf16(const void* d_a_bf16, const void* d_w_bf16, con
         vmgym_internal_set_error("vmgym_linear_bf16: cuTensorMapEncodeTiled failed");
         return VMGYM_ECUDA;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!attr_done(0, false)) {
         cudaError_t e = cudaFuncSetAttribute(linear_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) { vmgym_internal_set_error(cudaGetErrorString(e)); return VMGYM_ECUDA; }
-        attr_set = true;
+        attr_done(0, true);
     }
     dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
     linear_bf16_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, d_bias, d_c, (int)M, (int)N, (int)K, ldc);
@@ -666,11 +676,10 @@ extern "C" int vmgym_policy_fused(const void* d_h_bf16, const void* d_wpad_bf16,
         vmgym_internal_set_error("vmgym_policy_fused: cuTensorMapEncodeTiled failed");
         return VMGYM_ECUDA;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!attr_done(1, false)) {
         cudaError_t e = cudaFuncSetAttribute(policy_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e != cudaSuccess) { vmgym_internal_set_error(cudaGetErrorString(e)); return VMGYM_ECUDA; }
-        attr_set = true;
+        attr_done(1, true);
     }
     FusedOut fo;
     fo.mask_bits = d_mask_bits; fo.bias_pad = d_bias_pad; fo.action_in = d_action_in; fo.action_out = d_action_out;
@@ -679,16 +688,15 @@ extern "C" int vmgym_policy_fused(const void* d_h_bf16, const void* d_wpad_bf16,
     // tile-per-CTA kernel (A/B experiments, and the fallback for wider hidden layers)
     static const int persistent = getenv("VMGYM_FUSED_PERSISTENT") ? atoi(getenv("VMGYM_FUSED_PERSISTENT")) : 1;
     if (persistent && K <= P_KSLICES * BK) {
-        static bool pattr_set = false;
         static int n_sm = 0;
-        if (!pattr_set) {
+        if (!attr_done(2, false)) {
             cudaError_t e2 = cudaFuncSetAttribute(policy_fused_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_BYTES);
             if (e2 != cudaSuccess) { vmgym_internal_set_error(cudaGetErrorString(e2)); return VMGYM_ECUDA; }
             int dev = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
             if (n_sm <= 0) n_sm = 148;
-            pattr_set = true;
+            attr_done(2, true);
         }
         const long long units = ((M + BM - 1) / BM) * ((V + P_VCHUNK - 1) / P_VCHUNK);
         const unsigned ctas = (unsigned)(units < n_sm ? units : n_sm);
