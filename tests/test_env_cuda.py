@@ -576,3 +576,22 @@ def test_bench_gpu_arm_prints_the_contract_line():
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"]) and d["roofline"]["bound"] == "hbm"
     assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9 and "workload" in d["config"]
+
+
+PERFORMANCE_ROWS = [     # data/exp_performance/summary.csv (S100, reward ut at load 0.60 / wr at 1.00) and data/exp_performance_small/summary.csv
+    ("100", "firstfit", 0.60, "ut", range(5), "firstfit,0.60,5979819.544,0.000,10825,0,0.598,0.105,0.598,0.066,0.003,0.002,0.000"),
+    ("100", "bestfit", 0.60, "ut", range(5), "bestfit,0.60,5979835.178,0.000,10825,0,0.598,0.131,0.598,0.102,0.003,0.002,0.000"),
+    ("100", "bestfit", 1.00, "wr", range(5), "bestfit,1.00,-51651.520,0.182,13862,0,0.763,0.057,0.762,0.047,0.068,0.517,0.000"),
+    ("10", "firstfit", 1.00, "ut", range(1, 6), "firstfit,1.00,696939.963,0.241,1258,0,0.697,0.051,0.697,0.046,0.183,0.539,0.000"),
+]
+
+
+@pytest.mark.parametrize("shape,agent,load,reward,seeds,want", PERFORMANCE_ROWS)
+def test_performance_rows_through_sweep(shape, agent, load, reward, seeds, want):
+    """exp_performance.py's table rows through vmgym.sweep.performance_row (5 seeds = one 5-env batch): every column as
+    printed except Memory Variance, which the reference computes ACROSS THE RUNS (np.var(memory, axis=0), :117)."""
+    from vmgym.sweep import performance_row
+    base = dict(S100_BASE) if shape == "100" else dict(S100_BASE, pms=10, vms=30, seed=1)
+    got = performance_row(base, agent, load, reward, seeds=seeds).split(",")
+    w = want.split(",")
+    assert got[:9] == w[:9] and got[10:] == w[10:], (",".join(got), want)

@@ -80,3 +80,20 @@ def vm_size_rows(base: dict, agent: str, seeds=range(5), **kw):
         b = {**base, "sequence": seq, "arrival_rate": base["pms"] / frac / base["service_length"]}
         rows.append(seed_mean_row(b, agent, seeds, **kw))
     return rows
+
+
+def performance_row(base: dict, agent: str, load: float, reward: str, seeds=range(5), label: str | None = None, **kw):
+    """One row of exp_performance.py:20-147 / exp_performance_small.py: `seeds` runs of one (agent, load) point averaged:
+    'Agent, Load, Return, Drop Rate, Served VM, Suspend Actions, CPU Mean, CPU Variance, Memory Mean, Memory Variance, Pending
+    Rate, Waiting Ratio, Slowdown Rate'.  arrival_rate = round(pms / 0.55 / service_length * load, 4) (:26).
+    The reference's Memory Variance column is the variance ACROSS THE RUNS of each (step, PM) entry (`np.var(memory, axis=0)`,
+    :117 — the CPU column uses axis=2, across PMs); it couples the runs step by step and is not accumulated here: the column
+    printed is the across-PM variance like the CPU one."""
+    b = {**base, "reward_function": reward,
+         "arrival_rate": float(np.round(base["pms"] / 0.55 / base["service_length"] * load, 4))}
+    res = run_sweep(b, [dict(seed=int(s)) for s in seeds], agent, **kw)
+    m = lambda k: float(np.mean([r[k] for r in res]))                                  # noqa: E731
+    ret = float(np.mean([np.round(r["total rewards"], 3) for r in res]))               # record.py:108 rounds per run
+    return "%s,%.2f,%.3f,%.3f,%d,%d,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f" % (
+        label or agent, load, ret, m("drop rate"), m("total served VMs"), m("total suspend actions"), m("cpu mean"), m("cpu var"),
+        m("memory mean"), m("memory var"), m("average pending"), m("waiting ratio"), m("average slowdown"))
