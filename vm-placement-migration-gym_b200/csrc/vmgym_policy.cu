@@ -117,9 +117,7 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
             const int wl = P & 31, wi = P >> 5;
             const unsigned wait_inv = __shfl_sync(FULL, (inv >> wi) & 1u, wl);
             if (cnt > 1 && !wait_inv) {
-                const Philox4 r = philox4x32_10((uint32_t)v, (uint32_t)env, 3u, (uint32_t)p.counter, (uint32_t)p.seed,
-                                                (uint32_t)(p.seed >> 32));
-                const float u = (float)(r.x >> 8) * (1.0f / 16777216.0f);
+                const float u = gate_uniform(v, (uint32_t)env, p.seed, (uint32_t)p.counter);
                 if (u > p.migration_ratio && lane == wl) inv |= 1u << wi;
             }
         }
@@ -431,9 +429,7 @@ __global__ void __launch_bounds__(128) mask_bits_kernel(const HeadParams p)
             #pragma unroll
             for (int w = 0; w < 8; w++) if ((P >> 5) == w) wait_inv = (bits[w] >> (P & 31)) & 1u;
             if (cnt > 1 && !wait_inv) {
-                const Philox4 r = philox4x32_10((uint32_t)v, (uint32_t)env, 3u, (uint32_t)p.counter, (uint32_t)p.seed,
-                                                (uint32_t)(p.seed >> 32));
-                const float u = (float)(r.x >> 8) * (1.0f / 16777216.0f);
+                const float u = gate_uniform(v, (uint32_t)env, p.seed, (uint32_t)p.counter);
                 if (u > p.migration_ratio) {
                     #pragma unroll
                     for (int w = 0; w < 8; w++) if ((P >> 5) == w) bits[w] |= 1u << (P & 31);

@@ -45,6 +45,22 @@ __device__ __forceinline__ float fast_exp(float x)
     return y;
 }
 
+// The migration-ratio gate of PPOAgent.act (ppo.py:153-155) draws one uniform per VM row: word v & 3 of the Philox4x32-7
+// block keyed (v >> 2, env, 3, call counter) — one call serves four rows.  Used by heads_kernel and mask_bits_kernel alike.
+__device__ __forceinline__ float gate_uniform(int v, uint32_t env, unsigned long long seed, uint32_t counter)
+{
+    uint32_t c0 = (uint32_t)(v >> 2), c1 = env, c2 = 3u, c3 = counter, k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 7; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0, hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const uint32_t bits = (v & 3) == 0 ? c0 : ((v & 3) == 1 ? c1 : ((v & 3) == 2 ? c2 : c3));
+    return (float)(bits >> 8) * (1.0f / 16777216.0f);
+}
+
 // uniform in [0, 1) for chunk c of a row, from the row's block(s): 24 bits of word c & 3
 __device__ __forceinline__ float chunk_uniform(const Philox4& r, int c)
 {
