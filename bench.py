@@ -133,6 +133,8 @@ def gpu_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    from vmgym.sharding import bind_to_gpu_numa_node
+    prev_affinity = bind_to_gpu_numa_node(local) if world > 1 else None
     cfg = load_env_cfg()
     E = args.envs
     if args.bulk is not None or args.warps:
@@ -419,6 +421,9 @@ def gpu_arm(args):
                                                    "VM, ~900 per env and step at this load) + env.step"},
                         "config": "synthetic 1000 PMs / 3000 VM slots, highuniform sizes, arrival 1.6 (100 % load), fused best-fit act+step, "
                                   "one launch per step, same warp-per-env kernel (a CTA-per-env mapping for this shape is future work)"}
+    if prev_affinity is not None:
+        os.sched_setaffinity(0, prev_affinity)             # the CPU baseline uses every host core
+    out["config"]["numa_bound"] = prev_affinity is not None
     if not args.no_cpu:
         out["cpu_baseline"] = cpu_arm(steps_per_env=args.cpu_steps)
     print(json.dumps(out), flush=True)
