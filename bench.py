@@ -239,8 +239,16 @@ def gpu_arm(args):
     hv.run_pipelined(Ke)
     barrier()
     e2e_s = time.perf_counter() - t0
-    # the same loop without group overlap (one group): what the round-1 bench reported
-    hv1 = HostVecEnv(Config(**cfg), E, groups=1, device=dev, rng="philox", agent="bestfit",
+    # bytes the step kernel actually stores to the host observation buffer per step (only entries that changed), counted on
+    # the device outside the timed region
+    changed = 0
+    for _ in range(10):
+        prev = [g.vec.obs.clone() for g in hv.groups]
+        hv.act(); hv.step()
+        changed += sum(int((g.vec.obs != p_).sum().item()) for g, p_ in zip(hv.groups, prev))
+    d2h_obs = changed / 10 * 4
+    # the same loop with the full observation copied device->host every step (copy engine) instead of the changed entries
+    hv1 = HostVecEnv(Config(**cfg), E, groups=8, device=dev, rng="philox", agent="bestfit", delta_obs=False,
                      seeds=cfg["seed"] + 3 * 10**6 + rank * E + np.arange(E, dtype=np.int64))
     hv1.fast_forward(WARM_STEPS)
     hv1.run_pipelined(3)
@@ -249,7 +257,8 @@ def gpu_arm(args):
     hv1.run_pipelined(Ke)
     barrier()
     e2e1_s = time.perf_counter() - t0
-    h2d, d2h = hv.h2d_bytes_per_step, hv.d2h_bytes_per_step
+    h2d = hv.h2d_bytes_per_step
+    d2h = int(E * V * hv.action.element_size() + d2h_obs + E * 9)
     hv.close(); hv1.close()
     del hv, hv1
     clocks = sampler.finish() if sampler else None
@@ -380,9 +389,11 @@ def gpu_arm(args):
                    "state_types": "f64 PM accumulators, u8 placements / size codes, u16 runtimes, f32 observation"},
         "gpu_launches": K,
         "e2e": {"value": world * E * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": Ke, "groups": args.e2e_groups, "single_group_value": world * E * Ke / e2e1_s,
-                "path": "HostVecEnv: BestFitAgent.act(host obs) -> host action -> VecVmEnv.step(host action) -> host obs/reward/done, "
-                        "pinned host buffers, envs split into groups whose PCIe transfers overlap"},
+                "steps": Ke, "groups": args.e2e_groups, "full_obs_copy_value": world * E * Ke / e2e1_s,
+                "path": "HostVecEnv: BestFitAgent.act(host obs) -> host action -> VecVmEnv.step(host action) -> host obs/reward/done in "
+                        "pinned host buffers; envs split into stream groups whose PCIe transfers overlap; the step kernel keeps the host "
+                        "observation buffer current by storing only the entries that changed (d2h_bytes_per_step = actions + measured "
+                        "changed observation entries + reward/done; full_obs_copy_value: the same loop copying all 4(3V+2P) bytes per env)"},
         "single_launch_flushed": {"value": world * E / (flushed_ms * 1e-3), "unit": UNIT, "ms_per_step": flushed_ms, "steps": Kf,
                                   "note": "one batch, 256 MiB L2 flush before and one event pair around every launch "
                                           "(includes ~6 us event/launch latency per step), steps spread over one service period"},
@@ -468,7 +479,7 @@ def main():
     ap.add_argument("--ppo-envs", type=int, default=8192, help="envs per GPU of the ppo_train extra")
     ap.add_argument("--warps", type=int, default=0, help="vmgym_set_tuning warps per CTA, 0 = auto (experiments)")
     ap.add_argument("--bulk", type=int, default=None, help="vmgym_set_tuning use_bulk_copy bits (experiments)")
-    ap.add_argument("--e2e-groups", type=int, default=8, help="env groups (streams) of the host-buffer e2e loop")
+    ap.add_argument("--e2e-groups", type=int, default=4, help="env groups (streams) of the host-buffer e2e loop")
     ap.add_argument("--batches", type=int, default=20, help="independent env batches the timed launches rotate over")
     ap.add_argument("--cpu-steps", type=int, default=6000, help="timed CPU steps per env in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")

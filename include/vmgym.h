@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define VMGYM_ABI_VERSION 2
+#define VMGYM_ABI_VERSION 3
 
 enum vmgym_status {
     VMGYM_OK = 0,
@@ -129,6 +129,11 @@ typedef struct vmgym_outputs {
                                 first placement, step of the pending suspension (0 = none) */
     uint32_t* d_vm_hist;     /* [n_envs, 2, VMGYM_VMSTAT_BINS] counts of rint(1000 * rate): [0] pending, [1] slowdown */
     uint64_t* d_vm_totals;   /* [n_envs, 4] VMs seen, VMs ever placed, sum of lifetimes, reserved */
+    /* Optional mirror of d_obs for a caller whose observations live in HOST memory (pinned, device-mapped): with it set,
+     * d_obs is treated as the persistent reference copy and an entry is stored to d_obs and to the mirror only when its value
+     * changed — a quiet step changes nothing, so the PCIe traffic is a few entries per env instead of 4(3V+2P) bytes.
+     * The mirror must hold the same contents as d_obs when the first such call is made (copy it once after reset). */
+    float* d_obs_mirror;     /* [n_envs, 3V+2P] or NULL */
 } vmgym_outputs;
 #define VMGYM_STATS 16
 #define VMGYM_VMSTAT_BINS 1024   /* rates are rounded to 3 decimals (record.py:61,79): bins 0..1000 are used */

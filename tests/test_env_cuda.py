@@ -448,8 +448,8 @@ def test_empty_batch_and_bad_arguments():
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("use_graphs,zero_copy", [(True, True), (False, True), (True, False)])
-def test_host_vec_env_pipelined_equals_fused_device_rollout(use_graphs, zero_copy):
+@pytest.mark.parametrize("use_graphs,zero_copy,delta_obs", [(True, True, True), (False, True, True), (True, True, False), (True, False, False)])
+def test_host_vec_env_pipelined_equals_fused_device_rollout(use_graphs, zero_copy, delta_obs):
     """HostVecEnv (host obs/action buffers, 3 groups on 3 streams, split-phase pipelining) runs the same envs as one
     VecVmEnv stepping the fused best-fit kernel: identical observations, rewards and counters after 60 steps."""
     import torch
@@ -458,7 +458,7 @@ def test_host_vec_env_pipelined_equals_fused_device_rollout(use_graphs, zero_cop
     cfg = Config(pms=100, vms=300, arrival_rate=1.8182, service_length=1000, training_steps=10000, eval_steps=100000,
                  reward_function="wr", allow_null_action=True)
     N = 50
-    hv = HostVecEnv(cfg, N, groups=3, agent="bestfit", use_graphs=use_graphs, zero_copy=zero_copy)
+    hv = HostVecEnv(cfg, N, groups=3, agent="bestfit", use_graphs=use_graphs, zero_copy=zero_copy, delta_obs=delta_obs)
     obs0 = hv.reset().clone()
     ref = VecVmEnv(cfg, N, rng="philox")
     assert torch.equal(obs0, ref.observe().cpu())

@@ -30,8 +30,8 @@ from vmgym.host_vec import HostVecEnv
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 cfg = yaml.safe_load(open(os.path.join(ROOT, "configs", "100.yml")))["environment"]; cfg["reward_function"] = "wr"
 E = 4096
-for groups, graphs, zc in ((1, True, True), (2, True, True), (4, True, True), (8, True, True), (4, False, True), (16, True, True), (4, True, False)):
-    hv = HostVecEnv(Config(**cfg), E, groups=groups, agent="bestfit", use_graphs=graphs, zero_copy=zc)
+for groups, graphs, zc, dl in ((1, True, True, True), (2, True, True, True), (4, True, True, True), (8, True, True, True), (8, True, True, False), (16, True, True, True), (4, True, False, False)):
+    hv = HostVecEnv(Config(**cfg), E, groups=groups, agent="bestfit", use_graphs=graphs, zero_copy=zc, delta_obs=dl)
     hv.fast_forward(3000)
     hv.run_pipelined(3)
     torch.cuda.synchronize()
@@ -39,7 +39,7 @@ for groups, graphs, zc in ((1, True, True), (2, True, True), (4, True, True), (8
     hv.run_pipelined(20)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / 20
-    print(f"groups={groups} graphs={graphs} zero_copy={zc}: {dt * 1e3:.3f} ms/step, {E / dt / 1e6:.2f} M env-steps/s, {(hv.h2d_bytes_per_step + hv.d2h_bytes_per_step) / dt / 1e9:.1f} GB/s")
+    print(f"groups={groups} graphs={graphs} zero_copy={zc} delta_obs={dl}: {dt * 1e3:.3f} ms/step, {E / dt / 1e6:.2f} M env-steps/s, {(hv.h2d_bytes_per_step + hv.d2h_bytes_per_step) / dt / 1e9:.1f} GB/s")
     hv.close()
     del hv
 # kernel times alone

@@ -806,6 +806,32 @@ __device__ __noinline__ void write_obs_generic(const Env<PT> e, float* __restric
     for (int q = e.lane; q < P; q += 32) { o[3 * V + q] = (float)cpu[q]; o[3 * V + P + q] = (float)mem[q]; }
 }
 
+// The observation row for a caller with HOST-resident observations: `o` (device) is the reference copy of the row, `host` its
+// device-mapped mirror in pinned host memory; an entry is stored to both only when its bit pattern changed.
+template <typename PT>
+__device__ __noinline__ void write_obs_mirrored(const Env<PT> e, float* o, float* host)
+{
+    const int P = e.P, V = e.V;
+    const PT* place = e.place();
+    const uint8_t* cpuc = e.cpuc();
+    const uint8_t* memc = e.memc();
+    const double* cpu = e.cpu();
+    const double* mem = e.mem();
+#pragma unroll 1
+    for (int v = e.lane; v < V; v += 32) {
+        const float a = (float)place[v], c = e.sz32[cpuc[v] & 0x7f], m = e.sz32[memc[v]];
+        if (__float_as_uint(o[v]) != __float_as_uint(a)) { o[v] = a; host[v] = a; }
+        if (__float_as_uint(o[V + v]) != __float_as_uint(c)) { o[V + v] = c; host[V + v] = c; }
+        if (__float_as_uint(o[2 * V + v]) != __float_as_uint(m)) { o[2 * V + v] = m; host[2 * V + v] = m; }
+    }
+#pragma unroll 1
+    for (int q = e.lane; q < P; q += 32) {
+        const float c = (float)cpu[q], m = (float)mem[q];
+        if (__float_as_uint(o[3 * V + q]) != __float_as_uint(c)) { o[3 * V + q] = c; host[3 * V + q] = c; }
+        if (__float_as_uint(o[3 * V + P + q]) != __float_as_uint(m)) { o[3 * V + P + q] = m; host[3 * V + P + q] = m; }
+    }
+}
+
 // observation row (env.py:295-296): f32[ placement | vm_cpu | vm_memory | cpu | memory ]
 template <typename PT>
 __device__ __forceinline__ void write_obs(const Env<PT>& e, float* __restrict__ o)
@@ -1026,7 +1052,14 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
         }
 
         // ---- outputs ----
-        if (p.out.d_obs) write_obs(e, p.out.d_obs + env * (long long)cD);
+        if (p.out.d_obs) {
+            // the mirrored variant is compiled where external actions are possible (generic kernels and the agent-NONE spec)
+            constexpr bool MIRROR_OK = SPEC < 0 || (SPEC & 0xf) == VMGYM_AGENT_NONE;
+            if (MIRROR_OK && p.out.d_obs_mirror)
+                write_obs_mirrored(e, p.out.d_obs + env * (long long)cD, p.out.d_obs_mirror + env * (long long)cD);
+            else
+                write_obs(e, p.out.d_obs + env * (long long)cD);
+        }
         if (lane == 0) {
             e.sc()->status = (e.sc()->status & STATUS_EXHAUSTED) |
                              (quiet ? (STATUS_QUIET | (quiet_key << STATUS_KEY_SHIFT) | ((uint32_t)quiet_rejected << 16)) : 0u);

@@ -240,11 +240,14 @@ class VecVmEnv:
             self._out_cache[key] = out
         return out
 
-    def step(self, action, want_obs: bool = True, want_valid: bool = True, host_outputs=None, want_stats: bool = False):
+    def step(self, action, want_obs: bool = True, want_valid: bool = True, host_outputs=None, want_stats: bool = False,
+             obs_mirror=None):
         """env.py:66-103 for all envs.  `action`: [N, V] device tensor (uint8 / int16 / int64), numpy int array, or a
         PINNED host tensor (device-mapped under UVA: the kernel reads it over PCIe, no copy-engine transfer).
         `host_outputs`: optional (reward f64 [N], terminated u8 [N]) pinned host tensors the kernel writes directly,
-        instead of the env's device buffers.  `want_stats`: accumulate the episode sums behind summary()."""
+        instead of the env's device buffers.  `want_stats`: accumulate the episode sums behind summary().
+        `obs_mirror`: optional pinned host tensor [N, 3V+2P] kept equal to self.obs by storing only the entries that changed
+        (it must already equal self.obs, e.g. copied once after reset)."""
         if not isinstance(action, torch.Tensor):
             action = torch.from_numpy(np.ascontiguousarray(action, dtype=np.int64)).to(self.device, non_blocking=True)
         elif not action.is_cuda and not action.is_pinned():
@@ -260,12 +263,15 @@ class VecVmEnv:
             if not (rew_h.is_pinned() and term_h.is_pinned() and rew_h.dtype == torch.float64 and term_h.dtype == torch.uint8
                     and rew_h.numel() == self.num_envs and term_h.numel() == self.num_envs):
                 raise ValueError("host_outputs must be pinned (float64 [N], uint8 [N]) tensors")
-            key = ("host", rew_h.data_ptr(), term_h.data_ptr(), want_obs, want_valid)
+            if obs_mirror is not None and not (obs_mirror.is_pinned() and obs_mirror.dtype == torch.float32 and want_obs
+                                               and obs_mirror.shape == (self.num_envs, self.obs_dim) and obs_mirror.is_contiguous()):
+                raise ValueError("obs_mirror must be a contiguous pinned float32 [N, 3V+2P] tensor (and want_obs)")
+            key = ("host", rew_h.data_ptr(), term_h.data_ptr(), want_obs, want_valid, obs_mirror.data_ptr() if obs_mirror is not None else 0)
             hout = self._out_cache.get(key)
             if hout is None:
                 hout = nv.Outputs(d_obs=out.d_obs, d_reward=rew_h.data_ptr(), d_terminated=term_h.data_ptr(), d_valid=out.d_valid,
                                   d_action=None, d_stats=None, d_vm_slots=out.d_vm_slots, d_vm_hist=out.d_vm_hist,
-                                  d_vm_totals=out.d_vm_totals)
+                                  d_vm_totals=out.d_vm_totals, d_obs_mirror=obs_mirror.data_ptr() if obs_mirror is not None else None)
                 self._out_cache[key] = hout
             out = hout
         with self._on_device():
