@@ -341,10 +341,29 @@ def gpu_arm(args):
         s1000["drlvmp_s_per_step"] = (time.perf_counter() - t0) / 2
         del v1, ag1
 
+    # ---- extra D: the small shape of BASELINE configs[0] (config/10.yml, first-fit) at 2^20 envs per GPU ----
+    s10 = None
+    if not args.no_extras:
+        cfg10 = yaml.safe_load(open(os.path.join(ROOT, "configs", "10.yml")))["environment"]
+        cfg10["reward_function"] = "wr"
+        E10 = 1 << 20
+        v10 = VecVmEnv(Config(**cfg10), E10, device=dev, rng="philox", seeds=cfg10["seed"] + 5 * 10**6 + rank * E10 + np.arange(E10, dtype=np.int64))
+        v10.agent_step("firstfit", n_steps=WARM_STEPS, want_obs=False, want_action=False, want_valid=False)
+        v10.agent_step("firstfit", 1, want_obs=True, want_action=False, want_valid=False)
+        barrier()
+        s0_, s1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0_.record()
+        for _ in range(10):
+            v10.agent_step("firstfit", 1, want_obs=True, want_action=False, want_valid=False)
+        s1_.record()
+        barrier()
+        s10 = {"envs_per_gpu": E10, "ms_per_step": s0_.elapsed_time(s1_) / 10}
+        del v10
+
     if world > 1:
         t = torch.tensor([total_ms, rollout_ms, e2e_s, big["ms_per_step"] if big else 0.0, ppo["seconds"] if ppo else 0.0,
                           ppo["eval_ms_per_step"] if ppo else 0.0, flushed_ms, e2e1_s, s1000["ms_per_step"] if s1000 else 0.0,
-                          s1000["drlvmp_s_per_step"] if s1000 else 0.0],
+                          s1000["drlvmp_s_per_step"] if s1000 else 0.0, s10["ms_per_step"] if s10 else 0.0],
                          dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, rollout_ms, e2e_s = t.tolist()[:3]
@@ -353,6 +372,8 @@ def gpu_arm(args):
         if s1000:
             s1000["ms_per_step"] = t[8].item()
             s1000["drlvmp_s_per_step"] = t[9].item()
+        if s10:
+            s10["ms_per_step"] = t[10].item()
         if big:
             big["ms_per_step"] = t[3].item()
         if ppo:
@@ -432,6 +453,12 @@ def gpu_arm(args):
                                                    "VM, ~900 per env and step at this load) + env.step"},
                         "config": "synthetic 1000 PMs / 3000 VM slots, highuniform sizes, arrival 1.6 (100 % load), fused best-fit act+step, "
                                   "one launch per step, same warp-per-env kernel (a CTA-per-env mapping for this shape is future work)"}
+    if s10:
+        B10 = algorithmic_bytes(10, 30)
+        out["s10"] = {"value": world * s10["envs_per_gpu"] / (s10["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": s10["ms_per_step"],
+                      "envs_per_gpu": s10["envs_per_gpu"], "roofline_frac": B10 * s10["envs_per_gpu"] / (s10["ms_per_step"] * 1e-3) / 1e9 / peak,
+                      "config": "config/10.yml shape (10 PMs / 30 VM slots, the CPU-runnable case of BASELINE configs[0]), first-fit fused "
+                                "act+step, 2^20 envs per GPU, one launch per step (working set 0.9 GB per launch > L2)"}
     if prev_affinity is not None:
         os.sched_setaffinity(0, prev_affinity)             # the CPU baseline uses every host core
     out["config"]["numa_bound"] = prev_affinity is not None
