@@ -139,7 +139,7 @@ def gpu_arm(args):
     E = args.envs
     if args.bulk is not None or args.warps:
         from vmgym import _native as nv
-        nv.lib().vmgym_set_tuning(int(args.warps), 3 if args.bulk is None else int(args.bulk))
+        nv.lib().vmgym_set_tuning(int(args.warps), 7 if args.bulk is None else int(args.bulk))
     # envs shard contiguously: rank g owns global env ids [g*E, (g+1)*E); seeds derive from the global id
     seeds = cfg["seed"] + rank * E + np.arange(E, dtype=np.int64)
     vec = VecVmEnv(Config(**cfg), E, device=dev, rng="philox", seeds=seeds)

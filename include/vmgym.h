@@ -240,7 +240,8 @@ int vmgym_segtree_retrieve(const double* d_sum_tree, int64_t capacity, const dou
                            void* stream);
 
 /* Tuning knobs (process-wide): warps per CTA of the step kernels (0 = auto) and bulk-async record copies
- * (cp.async.bulk): use_bulk_copy bit 0 = loads, bit 1 = stores (default 3).  For experiments. */
+ * (cp.async.bulk): use_bulk_copy bit 0 = loads, bit 1 = stores, bit 2 = programmatic dependent launch of the step kernels
+ * (default 7).  For experiments. */
 int vmgym_set_tuning(int warps_per_cta, int use_bulk_copy);
 
 /* PrioritizedReplayBuffer.sample_batch (src/agents/drlvmp.py:178-241, src/segment_tree.py:35-62,103-118): stratified

@@ -52,7 +52,7 @@ def test_errors_do_not_throw():
     bad = nv.Config(10, 30, 1, 9, 1, 100, 0.5)          # unknown reward (the reference asserts, env.py:155-156)
     assert lib.vmgym_get_layout(C.byref(bad), C.byref(lay)) == nv.EINVAL
     assert lib.vmgym_set_tuning(99, 1) == nv.EINVAL
-    assert lib.vmgym_set_tuning(0, 1) == 0
+    assert lib.vmgym_set_tuning(0, 7) == 0
 
 
 def test_env_requires_cuda():

@@ -104,7 +104,7 @@ SHAPES = {
 
 @pytest.mark.parametrize("shape,n_envs,steps", [("s10", 37, 450), ("s100", 8, 300), ("odd", 16, 400), ("wide", 4, 250),
                                                 ("p253", 3, 200), ("p254", 3, 200), ("s10", 1, 120)])
-@pytest.mark.parametrize("bulk", [1, 0])
+@pytest.mark.parametrize("bulk", [7, 3, 0])      # bits: bulk loads | bulk stores | programmatic dependent launch
 def test_batched_step_matches_oracle_random_actions(shape, n_envs, steps, bulk):
     """N envs with different seeds, adversarial random action streams (out-of-range values, suspend storms,
     simultaneous placements on one PM, NULL-slot actions): every env equals its own oracle after every step."""
@@ -144,7 +144,7 @@ def test_batched_step_matches_oracle_random_actions(shape, n_envs, steps, bulk):
             if t % 25 == 0 or t == steps - 1:
                 _compare_state(vec, oracles, t)
     finally:
-        nv.lib().vmgym_set_tuning(0, 1)
+        nv.lib().vmgym_set_tuning(0, 7)
 
 
 @pytest.mark.parametrize("agent,tie", [("firstfit", "stable"), ("bestfit", "stable"), ("bestfit", "numpy_introsort")])

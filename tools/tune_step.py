@@ -47,7 +47,7 @@ for bulk in (1,):
             print(f"E={E} bulk={bulk} warps={w} {name:16s} cold med {med*1e3:8.1f} us min {mn*1e3:8.1f} us | "
                   f"{E/med/1e3:8.2f} M env-steps/s | {B*E/med/1e6:7.1f} GB/s || L2-warm med {medh*1e3:8.1f} us "
                   f"{E/medh/1e3:8.2f} M/s", flush=True)
-nv.lib().vmgym_set_tuning(0, 1)
+nv.lib().vmgym_set_tuning(0, 7)
 for chunk in (10, 100):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     vec.agent_step("bestfit", chunk, want_obs=True, want_action=False, want_valid=False)

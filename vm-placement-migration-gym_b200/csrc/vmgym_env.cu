@@ -22,7 +22,7 @@ namespace vmgym {
 // ---------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 static int g_warps_per_cta = 0;
-static int g_use_bulk = 3;      // bit 0: bulk-async record loads, bit 1: bulk-async record stores
+static int g_use_bulk = 7;      // bit 0: bulk-async record loads, bit 1: bulk-async record stores, bit 2: programmatic dependent launch
 
 static int fail(int code, const char* fmt, const char* detail = "")
 {
@@ -150,6 +150,17 @@ static int launch_step(StepParams& sp, cudaStream_t st)
     long long blocks = (sp.n_envs + w - 1) / w;
     const long long cap = (long long)sm_count() * occ;
     if (blocks > cap) blocks = cap;
+    if (sp.use_bulk & 4) {
+        // programmatic stream serialization: this launch may begin before the previous kernel of the stream has finished; the
+        // kernel itself waits (griddepcontrol.wait) before it touches records or outputs
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)blocks); lc.blockDim = dim3((unsigned)(w * 32)); lc.dynamicSmemBytes = smem; lc.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = attr; lc.numAttrs = 1;
+        return check_cuda(cudaLaunchKernelEx(&lc, kern, sp), "step_kernel launch (PDL)");
+    }
     kern<<<(unsigned)blocks, w * 32, smem, st>>>(sp);
     return check_cuda(cudaGetLastError(), "step_kernel launch");
 }
@@ -190,7 +201,7 @@ int vmgym_set_tuning(int warps_per_cta, int use_bulk_copy)
 {
     if (warps_per_cta < 0 || warps_per_cta > 4) return fail(VMGYM_EINVAL, "warps_per_cta must be 0..4");
     g_warps_per_cta = warps_per_cta;
-    g_use_bulk = use_bulk_copy & 3;
+    g_use_bulk = use_bulk_copy & 7;
     return VMGYM_OK;
 }
 

@@ -25,7 +25,8 @@ struct StepParams {
     int action_dtype;
     vmgym_outputs out;
     int agent, tiebreak, n_steps;
-    int use_bulk;             // bit 0: load records with cp.async.bulk, bit 1: store them with cp.async.bulk (else 128-bit ld/st)
+    int use_bulk;             // bit 0: load records with cp.async.bulk, bit 1: store them with cp.async.bulk (else 128-bit ld/st),
+                              // bit 2: programmatic dependent launch
 };
 
 constexpr uint32_t STATUS_EXHAUSTED = 1u;   // pre-sampled trace ran out (the reference would raise, env.py:282)
@@ -930,12 +931,17 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
     const bool BULK = (p.use_bulk & 1) != 0, BULK_ST = (p.use_bulk & 2) != 0;
     const long long stride = (long long)gridDim.x * wpc;
     const long long env0 = (long long)blockIdx.x * wpc + warp;
+    // Programmatic dependent launch (use_bulk bit 2): let the NEXT kernel of the stream start launching right away (its CTAs
+    // take the slots this grid frees as its fast CTAs finish) ...
+    const bool PDL = (p.use_bulk & 4) != 0;
+    if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // Start staging this warp's first record before anything else: the bulk copy only needs the warp's own mbarrier, so
-    // its DRAM round trip overlaps the table set-up below instead of following it.
+    // its DRAM round trip overlaps the table set-up below instead of following it.  (With PDL the records may still be
+    // written by the previous grid: the load waits for it, after the tables.)
     if (BULK && lane == 0) {
         mbar_init(bar, 1);
         fence_barrier_init();
-        if (env0 < p.n_envs) {
+        if (!PDL && env0 < p.n_envs) {
             mbar_arrive_expect_tx(bar, (uint32_t)L.rec_bytes);
             bulk_g2s(base, p.state + env0 * (long long)L.rec_bytes, (uint32_t)L.rec_bytes, bar);
         }
@@ -960,6 +966,14 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
         }
     }
     __syncthreads();
+    if (PDL) {
+        // ... and wait here, tables built, for the previous grid to complete and flush before touching any record / output
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (BULK && lane == 0 && env0 < p.n_envs) {
+            mbar_arrive_expect_tx(bar, (uint32_t)L.rec_bytes);
+            bulk_g2s(base, p.state + env0 * (long long)L.rec_bytes, (uint32_t)L.rec_bytes, bar);
+        }
+    }
 
     Env<PT> e;
     e.base = base; e.L = &p.L; e.sz64 = sz64; e.sz32 = sz32; e.P = cP; e.V = cV; e.lane = lane;
