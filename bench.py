@@ -406,7 +406,8 @@ def gpu_arm(args):
                          f"({NB} x {(2 * 3456 * E + 4 * D * E) / 1e6:.0f} MB touched between two visits of a batch, L2 = 126 MB)",
                    "phase_sampling": f"batch b warmed up to phase b*{PERIOD}/{NB} of the service period (departure waves)",
                    "timing": "one CUDA-event pair around a CUDA graph of exactly K step-kernel launches",
-                   "rng": "philox", "tiebreak": "stable", "obs_written": True,
+                   "rng": "philox", "tiebreak": "stable",
+                   "obs_written": "every step into the env's persistent observation buffer; rows of envs whose state did not change are kept, not re-stored",
                    "state_types": "f64 PM accumulators, u8 placements / size codes, u16 runtimes, f32 observation"},
         "gpu_launches": K,
         "e2e": {"value": world * E * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

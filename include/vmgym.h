@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define VMGYM_ABI_VERSION 3
+#define VMGYM_ABI_VERSION 4
 
 enum vmgym_status {
     VMGYM_OK = 0,
@@ -134,6 +134,11 @@ typedef struct vmgym_outputs {
      * changed — a quiet step changes nothing, so the PCIe traffic is a few entries per env instead of 4(3V+2P) bytes.
      * The mirror must hold the same contents as d_obs when the first such call is made (copy it once after reset). */
     float* d_obs_mirror;     /* [n_envs, 3V+2P] or NULL */
+    /* 1: d_obs is the SAME buffer on every call for these envs (and is not written by anyone else): an env whose state did
+     * not change since its observation row was last stored keeps that row (identical contents, no store).  The env records
+     * carry the "changed since last stored" bit; vmgym_reset with a d_obs counts as a store.  0: every call stores. */
+    int32_t obs_persistent;
+    int32_t reserved0;
 } vmgym_outputs;
 #define VMGYM_STATS 16
 #define VMGYM_VMSTAT_BINS 1024   /* rates are rounded to 3 decimals (record.py:61,79): bins 0..1000 are used */

@@ -31,6 +31,7 @@ struct StepParams {
 
 constexpr uint32_t STATUS_EXHAUSTED = 1u;   // pre-sampled trace ran out (the reference would raise, env.py:282)
 constexpr uint32_t STATUS_QUIET = 2u;       // a fused agent's act()+apply would change nothing (see step_kernel)
+constexpr uint32_t STATUS_OBS_STALE = 4u;   // the state changed since the env's row of a persistent observation buffer was stored
 constexpr uint32_t STATUS_KEY_SHIFT = 8;    // bits 8..15: which (agent, tiebreak) established QUIET; 0 = any agent
 constexpr uint32_t STATUS_KEY_MASK = 0xff00u;
 
@@ -1010,6 +1011,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
         const bool need_vectors = p.out.d_action != nullptr || p.out.d_valid != nullptr;
         const uint32_t my_key = (uint32_t)(agent_k | (tiebreak_k << 4));
         const uint32_t status0 = e.sc()->status;
+        bool obs_stale = (status0 & STATUS_OBS_STALE) != 0;
         bool quiet = (status0 & STATUS_QUIET) != 0;
         uint32_t quiet_key = (status0 & STATUS_KEY_MASK) >> STATUS_KEY_SHIFT;
         int quiet_rejected = (int)(status0 >> 16);
@@ -1054,6 +1056,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
             res = env_step<PT, REWARD_CT, MODE_CT, (SPEC < 0)>(e, p, env, valid_g, have_actions);
             if (res.changed) {
                 quiet = false;
+                obs_stale = true;
             } else if (evaluated) {
                 quiet = true;
                 quiet_key = n_found == 0 ? 0u : my_key;
@@ -1067,15 +1070,20 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
 
         // ---- outputs ----
         if (p.out.d_obs) {
-            // the mirrored variant is compiled where external actions are possible (generic kernels and the agent-NONE spec)
+            // a persistent observation buffer keeps the rows of envs whose state did not change (a quiet step changes
+            // nothing: no 4(3V+2P)-byte store); the mirrored variant (host-resident observations) is persistent by definition
+            // and is compiled where external actions are possible (generic kernels and the agent-NONE spec)
             constexpr bool MIRROR_OK = SPEC < 0 || (SPEC & 0xf) == VMGYM_AGENT_NONE;
-            if (MIRROR_OK && p.out.d_obs_mirror)
-                write_obs_mirrored(e, p.out.d_obs + env * (long long)cD, p.out.d_obs_mirror + env * (long long)cD);
-            else
-                write_obs(e, p.out.d_obs + env * (long long)cD);
+            const bool mirrored = MIRROR_OK && p.out.d_obs_mirror != nullptr;
+            const bool persistent = p.out.obs_persistent != 0 || mirrored;
+            if (!persistent || obs_stale) {
+                if (mirrored) write_obs_mirrored(e, p.out.d_obs + env * (long long)cD, p.out.d_obs_mirror + env * (long long)cD);
+                else write_obs(e, p.out.d_obs + env * (long long)cD);
+            }
+            if (persistent) obs_stale = false;
         }
         if (lane == 0) {
-            e.sc()->status = (e.sc()->status & STATUS_EXHAUSTED) |
+            e.sc()->status = (e.sc()->status & STATUS_EXHAUSTED) | (obs_stale ? STATUS_OBS_STALE : 0u) |
                              (quiet ? (STATUS_QUIET | (quiet_key << STATUS_KEY_SHIFT) | ((uint32_t)quiet_rejected << 16)) : 0u);
             if (p.out.d_reward) p.out.d_reward[env] = res.reward;
             if (p.out.d_terminated) p.out.d_terminated[env] = (uint8_t)res.terminated;
@@ -1160,7 +1168,7 @@ __global__ void reset_kernel(DevLayout L, unsigned char* state, long long n_envs
         sc->seed = seeds ? seeds[env] : keep.seed;
         sc->arrival_pos = rewind ? 0u : keep.arrival_pos;
         sc->admission_pos = rewind ? 0u : keep.admission_pos;
-        sc->status = rewind ? 0u : (keep.status & STATUS_EXHAUSTED);
+        sc->status = (rewind ? 0u : (keep.status & STATUS_EXHAUSTED)) | (obs ? 0u : STATUS_OBS_STALE);
     }
     if (obs) {
         float* o = obs + env * (long long)L.D;

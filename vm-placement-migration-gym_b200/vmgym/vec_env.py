@@ -236,7 +236,8 @@ class VecVmEnv:
                              d_stats=self.stats.data_ptr() if want_stats else None,
                              d_vm_slots=self._vm_slots.data_ptr() if self._vm_slots is not None else None,
                              d_vm_hist=self._vm_hist.data_ptr() if self._vm_slots is not None else None,
-                             d_vm_totals=self._vm_totals.data_ptr() if self._vm_slots is not None else None)
+                             d_vm_totals=self._vm_totals.data_ptr() if self._vm_slots is not None else None,
+                             obs_persistent=1)          # self.obs is this env's own buffer: unchanged envs keep their rows
             self._out_cache[key] = out
         return out
 
@@ -271,7 +272,8 @@ class VecVmEnv:
             if hout is None:
                 hout = nv.Outputs(d_obs=out.d_obs, d_reward=rew_h.data_ptr(), d_terminated=term_h.data_ptr(), d_valid=out.d_valid,
                                   d_action=None, d_stats=None, d_vm_slots=out.d_vm_slots, d_vm_hist=out.d_vm_hist,
-                                  d_vm_totals=out.d_vm_totals, d_obs_mirror=obs_mirror.data_ptr() if obs_mirror is not None else None)
+                                  d_vm_totals=out.d_vm_totals, d_obs_mirror=obs_mirror.data_ptr() if obs_mirror is not None else None,
+                                  obs_persistent=1)
                 self._out_cache[key] = hout
             out = hout
         with self._on_device():
