@@ -244,7 +244,8 @@ int vmgym_segtree_update(double* d_sum_tree, double* d_min_tree, int64_t capacit
 int vmgym_segtree_retrieve(const double* d_sum_tree, int64_t capacity, const double* d_upper, int32_t n, int64_t* d_out,
                            void* stream);
 
-/* Tuning knobs (process-wide): warps per CTA of the step kernels (0 = auto) and bulk-async record copies
+/* Tuning knobs (process-wide): warps per CTA of the step kernels (0 = auto; 1..8: byte-placement shapes run that many
+ * envs per CTA, at most 4; u16-placement shapes run ONE env per CTA with that many warps teaming on it) and bulk-async record copies
  * (cp.async.bulk): use_bulk_copy bit 0 = loads, bit 1 = stores, bit 2 = programmatic dependent launch of the step kernels
  * (default 7).  For experiments. */
 int vmgym_set_tuning(int warps_per_cta, int use_bulk_copy);

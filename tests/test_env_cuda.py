@@ -99,6 +99,9 @@ SHAPES = {
                  reward_function="ut", allow_null_action=True),                                # smallest u16-placement layout
     "wide": dict(pms=300, vms=700, arrival_rate=4.0, service_length=120, training_steps=10000, eval_steps=100000,
                  reward_function="kl", allow_null_action=True, sequence="lowuniform"),
+    # u16 placements with a short service time: departures, re-admissions and re-placements every step (team-mode kernel)
+    "big": dict(pms=400, vms=1100, arrival_rate=9.0, service_length=40, training_steps=10000, eval_steps=100000,
+                reward_function="wr", allow_null_action=True, sequence="highuniform"),
 }
 
 
@@ -149,7 +152,7 @@ def test_batched_step_matches_oracle_random_actions(shape, n_envs, steps, bulk):
 
 @pytest.mark.parametrize("agent,tie", [("firstfit", "stable"), ("bestfit", "stable"), ("bestfit", "numpy_introsort")])
 @pytest.mark.parametrize("shape,n_envs,steps,chunk", [("s100", 6, 1300, 1), ("s100", 6, 1300, 64), ("s10", 20, 380, 7),
-                                                       ("odd", 9, 500, 25), ("s1000", 2, 150, 50)])
+                                                       ("odd", 9, 500, 25), ("s1000", 2, 150, 50), ("big", 3, 240, 40)])
 @pytest.mark.parametrize("vectors", [True, False])
 def test_fused_agent_step_matches_oracle_rollout(agent, tie, shape, n_envs, steps, chunk, vectors):
     """agent.act + env.step fused in one kernel (chunk steps per launch) == oracle act()/step() loop.
@@ -183,6 +186,41 @@ def test_fused_agent_step_matches_oracle_rollout(agent, tie, shape, n_envs, step
         if done % 256 < chunk or done == steps:
             cnt = _compare_state(vec, oracles, done)
             assert np.allclose(cnt["episode_return"], returns, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("team_warps", [1, 3, 8])
+@pytest.mark.parametrize("shape,agent", [("big", "bestfit"), ("wide", "firstfit"), ("p254", "bestfit")])
+def test_team_mode_widths_match_oracle(team_warps, shape, agent):
+    """Large shapes (u16 placements) run one env per CTA with helper warps for the bulk phases: every team width gives the
+    oracle's trajectory (per-slot state, observation bytes, rewards), single- and multi-step launches."""
+    from vmgym import VecVmEnv
+    from vmgym import _native as nv
+    kw = SHAPES[shape]
+    n_envs, steps = 5, 230
+    seeds = 11 + 5 * np.arange(n_envs)
+    nv.lib().vmgym_set_tuning(team_warps, 7)
+    try:
+        vec = VecVmEnv(_cfg(**kw), n_envs, seeds=seeds, trace_steps=steps + 4, max_admissions=30000)
+        oracles = _oracle_batch(kw, seeds, steps + 4, 30000)
+        P, V = kw["pms"], kw["vms"]
+        done = 0
+        for n in [1, 1, 1, 7, 50, 1, 90, 79]:
+            vec.agent_step(agent, n_steps=n, want_action=False, want_valid=False)
+            obs_h, rew_h = vec.obs.cpu().numpy(), vec.reward.cpu().numpy()
+            for i, o in enumerate(oracles):
+                for _ in range(n):
+                    ob = o._obs()
+                    a = vo.firstfit_act(P, V, ob) if agent == "firstfit" else vo.bestfit_act(P, V, ob, vo.TIE_STABLE)
+                    o_obs, o_r, _, _, _ = o.step(a)
+                assert obs_h[i].tobytes() == o_obs.tobytes(), (i, done)
+                assert rew_h[i] == pytest.approx(o_r, rel=REWARD_RTOL, abs=1e-300)
+            done += n
+            _compare_state(vec, oracles, done)
+        assert done == steps
+        c = vec.counters()
+        assert int(c["served_requests"].sum()) > 0 and int(c["place_actions"].sum()) > 0
+    finally:
+        nv.lib().vmgym_set_tuning(0, 7)
 
 
 @pytest.mark.parametrize("name", ["s100_firstfit_wr", "s100_bestfit_stable_wr", "s100_bestfit_introsort_wr",

@@ -57,7 +57,10 @@ static int make_layout(const vmgym_config* c, DevLayout* L, vmgym_layout* pub)
     l.sm_prop = l.sm_fit + 512 + align_up(2 * l.Pp, 16);      // u32 prop[ceil(Vp/32)]: slots whose action differs
     l.sm_stats = l.sm_prop + align_up(4 * ((l.Vp + 31) / 32), 16);   // f64[VMGYM_STATS] eval-summary sums of the launch
     l.sm_bar = l.sm_stats + 8 * VMGYM_STATS;
-    l.sm_stride = align_up(l.sm_bar + 16, 128);
+    // team mode (u16 placements = large shapes, one env per CTA): command words + two slot-chunk bitmaps (departures, candidates)
+    l.sm_team = l.sm_bar + 16;
+    const int team_bytes = pb == 2 ? 16 + 2 * align_up(4 * ((l.Vp + 31) / 32), 16) : 0;
+    l.sm_stride = align_up(l.sm_team + team_bytes, 128);
     l.svc_cdf_smem = 0;                                    // service table stays in global memory (used on admissions only)
     l.sm_tables = align_up(SIZE_TABLE * 8 + SIZE_TABLE * 4 + ARR_CDF_SMEM * 8 + l.svc_cdf_smem * 8 + (SVC_BRACKETS + 1) * 2, 128);
     if (L) *L = l;
@@ -100,7 +103,7 @@ static int sm_count()
 // warps when it is large.
 static int pick_warps(long long n_envs, int smem_per_warp, int smem_fixed)
 {
-    if (g_warps_per_cta > 0) return g_warps_per_cta;
+    if (g_warps_per_cta > 0) return g_warps_per_cta > 4 ? 4 : g_warps_per_cta;
     int w = 4;                  // step_kernel is compiled for <= 128 threads per CTA (__launch_bounds__(128, 7))
     while (w > 1 && n_envs < (long long)sm_count() * w * 6) w >>= 1;
     while (w > 1 && smem_fixed + w * smem_per_warp > 200 * 1024) w >>= 1;
@@ -112,10 +115,25 @@ static int launch_step(StepParams& sp, cudaStream_t st)
 {
     sp.use_bulk = g_use_bulk;
     const DevLayout& L = sp.L;
-    const int w = pick_warps(sp.n_envs, L.sm_stride, L.sm_tables);
-    const size_t smem = (size_t)L.sm_tables + (size_t)w * L.sm_stride;
+    // u16 placements = large shapes: team mode, one env per CTA with `w` warps (warp 0 steps, the others join the bulk phases)
+    static const bool team_ok = getenv("VMGYM_NO_TEAM") == nullptr;                        // A/B switch for experiments
+    const bool team = team_ok && sizeof(PT) == 2;
+    int w;
+    if (team) {
+        const long long one = (long long)L.sm_tables + L.sm_stride + 1024;                  // + the per-CTA reservation
+        long long per_sm = (228 * 1024) / one;
+        const long long need = (sp.n_envs + sm_count() - 1) / sm_count();
+        if (per_sm > need) per_sm = need;
+        if (per_sm < 1) per_sm = 1;
+        w = g_warps_per_cta > 0 ? g_warps_per_cta : (int)(48 / per_sm);
+        w = w < 1 ? 1 : (w > 8 ? 8 : w);                                                    // compiled for <= 256 threads
+    } else {
+        w = pick_warps(sp.n_envs, L.sm_stride, L.sm_tables);
+    }
+    const size_t smem = (size_t)L.sm_tables + (size_t)(team ? 1 : w) * L.sm_stride;
     if (smem > 227 * 1024) return fail(VMGYM_EUNSUPPORTED, "env record does not fit in shared memory (pms/vms too large)");
     void (*kern)(const StepParams) = step_kernel<PT, 0, 0, -1>;
+    if (team) kern = step_kernel<PT, 0, 0, -1, (sizeof(PT) == 2)>;
     static const bool specialise = getenv("VMGYM_NO_SPECIALIZE") == nullptr;               // A/B switch for experiments
     if (specialise && sizeof(PT) == 1 && L.P == 100 && L.V == 300) {                        // config/100.yml
         kern = step_kernel<PT, 100, 300, -1>;
@@ -147,7 +165,7 @@ static int launch_step(StepParams& sp, cudaStream_t st)
         plan_smem = smem; plan_w = w; plan_kern = kern; plan_dev = dev;
     }
     const int occ = plan_occ;
-    long long blocks = (sp.n_envs + w - 1) / w;
+    long long blocks = team ? sp.n_envs : (sp.n_envs + w - 1) / w;
     const long long cap = (long long)sm_count() * occ;
     if (blocks > cap) blocks = cap;
     if (sp.use_bulk & 4) {
@@ -199,7 +217,7 @@ int vmgym_abi_version(void) { return VMGYM_ABI_VERSION; }
 
 int vmgym_set_tuning(int warps_per_cta, int use_bulk_copy)
 {
-    if (warps_per_cta < 0 || warps_per_cta > 4) return fail(VMGYM_EINVAL, "warps_per_cta must be 0..4");
+    if (warps_per_cta < 0 || warps_per_cta > 8) return fail(VMGYM_EINVAL, "warps_per_cta must be 0..8");
     g_warps_per_cta = warps_per_cta;
     g_use_bulk = use_bulk_copy & 7;
     return VMGYM_OK;

@@ -74,6 +74,13 @@ struct Env {
     __device__ __forceinline__ unsigned* fitm() const { return reinterpret_cast<unsigned*>(VMGYM_SMEM(base) + L->sm_fit); }
     __device__ __forceinline__ uint16_t* cap() const { return reinterpret_cast<uint16_t*>(VMGYM_SMEM(base) + L->sm_fit + 512); }
     __device__ __forceinline__ unsigned* prop() const { return reinterpret_cast<unsigned*>(VMGYM_SMEM(base) + L->sm_prop); }
+    // team mode scratch (large shapes only, see "Team mode" below): command words, departure / candidate bitmaps per 32 slots
+    __device__ __forceinline__ volatile int* ctl() const { return reinterpret_cast<volatile int*>(VMGYM_SMEM(base) + L->sm_team); }
+    __device__ __forceinline__ unsigned* tmask() const { return reinterpret_cast<unsigned*>(VMGYM_SMEM(base) + L->sm_team + 16); }
+    __device__ __forceinline__ unsigned* cmask() const
+    {
+        return reinterpret_cast<unsigned*>(VMGYM_SMEM(base) + L->sm_team + 16 + align_up(4 * ((L->Vp + 31) / 32), 16));
+    }
 };
 
 // Where the agent reads the slots it decides on: arrays of placements and size codes (+ float sizes as the agent
@@ -170,14 +177,108 @@ __device__ __forceinline__ unsigned cand_bits4(uint32_t pl4, uint32_t cc4, uint3
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Team mode (large shapes: u16 placements, e.g. the synthetic 1000-PM / 3000-slot shape).  A 40 KB record leaves room
+// for three envs per SM, so a warp per env runs at one warp per scheduler with nothing to hide its latencies behind.
+// Here a CTA owns one env: warp 0 (the "main" warp) runs the same sequential step logic as the warp-per-env kernel and
+// the other warps join it for the phases that are plain loops over all slots / PMs (observation row, float32 view +
+// capacity copy, candidate pre-filter, service countdown).  Hand-off is two named barriers around a command word in
+// shared memory; the results of a parallel phase that feed sequential logic (which slots finished, which 32-slot chunks
+// hold a candidate) are bitmaps, consumed by the main warp in slot order, so every decision is taken in the reference's order.
+// ---------------------------------------------------------------------------------------------------
+enum { TEAM_END = 0, TEAM_OBS = 1, TEAM_PREP = 2, TEAM_FILTER = 3, TEAM_COUNTDOWN = 4 };
+
+__device__ __forceinline__ void team_bar(int id, int nth) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nth) : "memory"); }
+
+template <typename PT>
+__device__ __forceinline__ void team_phase(const Env<PT>& e, int cmd, int tid, int nth)
+{
+    const int P = e.P, V = e.V;
+    if (cmd == TEAM_OBS) {
+        // observation row (env.py:295-296); the destination pointer travels in ctl[2..3]
+        const volatile int* ctl = e.ctl();
+        float* o = reinterpret_cast<float*>(((unsigned long long)(unsigned)ctl[3] << 32) | (unsigned long long)(unsigned)ctl[2]);
+        const PT* place = e.place();
+        const uint8_t* cpuc = e.cpuc();
+        const uint8_t* memc = e.memc();
+        const double* cpu = e.cpu();
+        const double* mem = e.mem();
+        for (int v = tid; v < V; v += nth) { o[v] = (float)place[v]; o[V + v] = e.sz32[cpuc[v] & 0x7f]; o[2 * V + v] = e.sz32[memc[v]]; }
+        for (int q = tid; q < P; q += nth) { o[3 * V + q] = (float)cpu[q]; o[3 * V + P + q] = (float)mem[q]; }
+    } else if (cmd == TEAM_PREP) {
+        // the agent's float32 view of the PM loads (env.py:296), its local copy of the capacity codes, no proposals yet
+        const double* cpu = e.cpu();
+        const double* mem = e.mem();
+        for (int q = tid; q < P; q += nth) { e.cpu32()[q] = (float)cpu[q]; e.mem32()[q] = (float)mem[q]; e.cap()[q] = e.rcap()[q]; }
+        for (int c = tid; c < (V + 31) / 32; c += nth) e.prop()[c] = 0u;
+    } else if (cmd == TEAM_FILTER) {
+        // which 32-slot chunks hold a waiting VM that fits on some PM under the capacities at the start of act()
+        // (capacities only shrink while the agent proposes, so this is a superset of the chunks worth visiting)
+        const PT* place = e.place();
+        const uint8_t* cc = e.cpuc();
+        const uint8_t* mc = e.memc();
+        const unsigned* fitm = e.fitm();
+        unsigned* cm = e.cmask();
+        for (int v0 = (tid & ~31); v0 < V; v0 += nth) {
+            const int v = v0 + (tid & 31);
+            const bool cand = v < V && (int)place[v] == P && (unsigned)mc[v] + 1u <= fitm[cc[v] & 0x7f];
+            const unsigned m = __ballot_sync(FULL, cand);
+            if ((tid & 31) == 0) cm[v0 >> 5] = m;
+        }
+    } else if (cmd == TEAM_COUNTDOWN) {
+        // running VMs: remaining -= 1 if > 0 (env.py:245-247); the slots that reach 0 are reported as a bitmap
+        const PT* place = e.place();
+        uint16_t* rem = e.rem();
+        unsigned* tmk = e.tmask();
+        for (int v0 = (tid & ~31); v0 < V; v0 += nth) {
+            const int v = v0 + (tid & 31);
+            bool term = false;
+            if (v < V && (int)place[v] < P) {
+                int r = (int)rem[v];
+                if (r > 0) { r -= 1; rem[v] = (uint16_t)r; }
+                term = r == 0;
+            }
+            const unsigned m = __ballot_sync(FULL, term);
+            if ((tid & 31) == 0) tmk[v0 >> 5] = m;
+        }
+    }
+}
+
+// main warp: run one phase with the whole team (all 32 lanes call this, converged)
+template <typename PT>
+__device__ __forceinline__ void team_run(const Env<PT>& e, int cmd, int nth)
+{
+    __syncwarp();
+    if (e.lane == 0) e.ctl()[0] = cmd;
+    team_bar(1, nth);
+    if (cmd != TEAM_END) team_phase(e, cmd, e.lane, nth);
+    team_bar(2, nth);
+}
+
+// helper warps: serve the main warp's phases of one env
+template <typename PT>
+__device__ __forceinline__ void team_serve(const Env<PT>& e, int tid, int nth)
+{
+    for (;;) {
+        team_bar(1, nth);
+        const int cmd = e.ctl()[0];
+        if (cmd != TEAM_END) {
+            team_phase(e, cmd, tid, nth);
+            fence_proxy_async();          // this thread's shared-memory writes vs the record's bulk-async store
+        }
+        team_bar(2, nth);
+        if (cmd == TEAM_END) break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Heuristic agents on the float32 view (firstfit.py:21-38, bestfit.py:21-40).  Lanes own PMs p = lane + 32 i.
 // For every waiting VM, in slot order: first-fit takes the lowest-index PM that fits, best-fit the fitting PM with
 // the largest cpu+memory (ties: see `tiebreak`); the local float32 loads are updated like the reference does
 // (first-fit: cpu only, firstfit.py:36).  Proposals are recorded as act[v] = pm plus a bit in prop[v / 32].
 // Returns the number of proposals.
 // ---------------------------------------------------------------------------------------------------
-template <typename PT>
-__device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& av, int agent, int tiebreak, bool have_rcap)
+template <typename PT, bool TM = false>
+__device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& av, int agent, int tiebreak, bool have_rcap, int nth = 32)
 {
     const int P = e.P, V = e.V, lane = e.lane;
     float* cpu32 = e.cpu32();
@@ -187,16 +288,20 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
     int n_found = 0;
     // local capacity codes: the record's (fused kernel) or computed from the observed loads (act_kernel); the agent's
     // own proposals then shrink this local copy only, like the reference's local cpu/memory arrays
-    if (have_rcap) { for (int p = lane; p < P; p += 32) cap[p] = e.rcap()[p]; }
-    else { for (int p = lane; p < P; p += 32) cap[p] = (uint16_t)(max_code(e.sz32, cpu32[p]) | (max_code(e.sz32, mem32[p]) << 8)); }
-    for (int c = lane; c < (V + 31) / 32; c += 32) e.prop()[c] = 0u;
+    if constexpr (TM) {
+        team_run(e, TEAM_PREP, nth);      // float32 view, cap[] = rcap[] (the fused kernel always has the record's codes), prop[] = 0
+    } else {
+        if (have_rcap) { for (int p = lane; p < P; p += 32) cap[p] = e.rcap()[p]; }
+        else { for (int p = lane; p < P; p += 32) cap[p] = (uint16_t)(max_code(e.sz32, cpu32[p]) | (max_code(e.sz32, mem32[p]) << 8)); }
+        for (int c = lane; c < (V + 31) / 32; c += 32) e.prop()[c] = 0u;
+    }
     unsigned kmax = rebuild_fit_table(e);
 
     // slots are visited in groups: 4 per lane (128 per pass) for byte placements, 1 per lane otherwise
     constexpr int SPL = sizeof(PT) == 1 ? 4 : 1;
     const uint32_t P4 = (uint32_t)P * 0x01010101u;
     const int n_units = (V + SPL - 1) / SPL;
-    for (int u0 = 0; u0 < n_units; u0 += 32) {
+    auto visit = [&](const int u0) {
         const int u = u0 + lane;
         unsigned cb = 0;                      // candidate bits of this lane's SPL slots
         if (u < n_units) {
@@ -305,6 +410,23 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
                 m &= __ballot_sync(FULL, cb != 0);
             }
         }
+    };
+    if constexpr (TM && SPL == 1) {
+        // the team marks the 32-slot chunks that hold a candidate; the main warp visits only those, in slot order, and
+        // re-tests their slots against the current capacities (visit() evaluates the chunk afresh)
+        team_run(e, TEAM_FILTER, nth);
+        const unsigned* cm = e.cmask();
+        const int n_chunks = (V + 31) / 32;
+        for (int cb0 = 0; cb0 < n_chunks; cb0 += 32) {
+            unsigned nz = __ballot_sync(FULL, cb0 + lane < n_chunks && cm[cb0 + lane] != 0u);
+            while (nz) {
+                const int c = cb0 + __ffs(nz) - 1;
+                nz &= nz - 1;
+                visit(32 * c);
+            }
+        }
+    } else {
+        for (int u0 = 0; u0 < n_units; u0 += 32) visit(u0);
     }
     __syncwarp();
     return n_found;
@@ -487,9 +609,9 @@ __device__ __noinline__ void stats_update(const Env<PT> e, const StepResult res,
 // common quiet step (nothing placed, nothing departs, nothing admitted) costs only the service countdown, one
 // arrival draw and the outputs.
 // ---------------------------------------------------------------------------------------------------
-template <typename PT, int REWARD_CT, int MODE_CT, bool VMSTAT>
+template <typename PT, int REWARD_CT, int MODE_CT, bool VMSTAT, bool TM = false>
 __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParams& p, long long env_id, uint8_t* valid_g,
-                                               bool have_actions)
+                                               bool have_actions, int nth = 32)
 {
     // per-VM statistics are compiled into the generic instantiations only (the specialised throughput kernels skip them)
     const bool vmstat = VMSTAT && p.out.d_vm_slots != nullptr;
@@ -514,7 +636,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
     if (have_actions) {
         const uint16_t* act = e.act();
         const unsigned* prop = e.prop();
-        for (int c0 = 0; c0 < V; c0 += 32) {
+        auto apply_chunk = [&](const int c0) {
             const unsigned pm = prop[c0 >> 5];
             unsigned m = pm, okbits = 0;
             while (m) {
@@ -560,6 +682,20 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
             }
             rejected += __popc(pm & ~okbits);
             if (valid_g && c0 + lane < V) valid_g[c0 + lane] = ((pm & ~okbits) >> lane) & 1u ? 0 : 1;
+        };
+        if (TM && !valid_g) {
+            // large shapes: only the 32-slot chunks that carry a proposal, in slot order
+            const int n_chunks = (V + 31) / 32;
+            for (int cb0 = 0; cb0 < n_chunks; cb0 += 32) {
+                unsigned nz = __ballot_sync(FULL, cb0 + lane < n_chunks && prop[cb0 + lane] != 0u);
+                while (nz) {
+                    const int c = cb0 + __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    apply_chunk(32 * c);
+                }
+            }
+        } else {
+            for (int c0 = 0; c0 < V; c0 += 32) apply_chunk(c0);
         }
     } else if (valid_g) {
         for (int v = lane; v < V; v += 32) valid_g[v] = 1;
@@ -622,6 +758,35 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                 __syncwarp();
             }
         }
+    } else if (TM) {
+        // team countdown -> bitmap of the slots that finished; the main warp retires them in slot order exactly like the
+        // byte-placement path above (per-PM subtraction, 1e-7 clamp and capacity-code refresh)
+        team_run(e, TEAM_COUNTDOWN, nth);
+        const unsigned* tmk = e.tmask();
+        const int n_chunks = (V + 31) / 32;
+        for (int cb0 = 0; cb0 < n_chunks; cb0 += 32) {
+            unsigned nz = __ballot_sync(FULL, cb0 + lane < n_chunks && tmk[cb0 + lane] != 0u);
+            while (nz) {
+                const int c = cb0 + __ffs(nz) - 1;
+                nz &= nz - 1;
+                unsigned mm = tmk[c];
+                served += __popc(mm);
+                if (lane == 0) {
+                    while (mm) {
+                        const int vv = 32 * c + __ffs(mm) - 1, pm = (int)place[vv];
+                        mm &= mm - 1;
+                        cpu[pm] -= e.sz64[cpuc[vv] & 0x7f];
+                        mem[pm] -= e.sz64[memc[vv]];
+                        if (cpu[pm] < 1e-7) cpu[pm] = 0.0;           // :267-268 clamp, applied here for this PM
+                        if (mem[pm] < 1e-7) mem[pm] = 0.0;
+                        refresh_cap(e, pm);
+                        place[vv] = (PT)(P + 1); cpuc[vv] = 0; memc[vv] = 0; rem[vv] = 0;
+                        if (vmstat) vmstat_close(vs.slots + vv * 4, tnow - vs.slots[vv * 4], 0u, vs.hist, vs.totals);
+                    }
+                }
+                __syncwarp();
+            }
+        }
     } else {
         for (int c0 = 0; c0 < V; c0 += 32) {
             const int v = c0 + lane;
@@ -652,7 +817,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
     }
     __syncwarp();
     // ---- 4. clamp (env.py:267-268): values only shrink when something was subtracted this step ----
-    if (served > 0 || n_susp > 0) {
+    if ((served > 0 && !(TM && sizeof(PT) != 1)) || n_susp > 0) {      // (the team path clamps at each departure)
         for (int q = lane; q < P; q += 32) {
             bool ch = need_full_refresh;
             if (cpu[q] < 1e-7 && cpu[q] != 0.0) { cpu[q] = 0.0; ch = true; }
@@ -912,8 +1077,9 @@ __host__ __device__ __forceinline__ int dtype_bytes(int dtype) { return dtype ==
 // SPEC >= 0 additionally fixes (agent, tiebreak, reward, trace mode) = spec_* fields at compile time (SPEC < 0: run time).
 constexpr int make_spec(int agent, int tiebreak, int reward, int mode) { return agent | (tiebreak << 4) | (reward << 8) | (mode << 12); }
 
-template <typename PT, int PC, int VC, int SPEC>
-__global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ StepParams p)
+// TM: team mode (one env per CTA, warp 0 + helper warps; see "Team mode" above) — instantiated for u16 placements.
+template <typename PT, int PC, int VC, int SPEC, bool TM = false>
+__global__ void __launch_bounds__(TM ? 256 : 128, TM ? 3 : 7) step_kernel(const __grid_constant__ StepParams p)
 {
     constexpr int REWARD_CT = SPEC >= 0 ? ((SPEC >> 8) & 0xf) : 0;
     constexpr int MODE_CT = SPEC >= 0 ? ((SPEC >> 12) & 0xf) : -1;
@@ -926,7 +1092,10 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
     float* sz32 = reinterpret_cast<float*>(smem + SIZE_TABLE * 8);
     uint32_t* arr_cdf_s = reinterpret_cast<uint32_t*>(smem + SIZE_TABLE * 12);
     uint16_t* svc_bracket_s = reinterpret_cast<uint16_t*>(reinterpret_cast<uint64_t*>(smem + SIZE_TABLE * 12) + ARR_CDF_SMEM);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    // team mode: every warp of the CTA works on the same env (region 0); otherwise a warp per env
+    const int lane = threadIdx.x & 31, warp = TM ? 0 : (int)(threadIdx.x >> 5), wpc = TM ? 1 : (int)(blockDim.x >> 5);
+    const bool helper = TM && threadIdx.x >= 32;
+    const int nth = TM ? (int)blockDim.x : 32;
     unsigned char* base = smem + L.sm_tables + (size_t)warp * L.sm_stride;
     uint64_t* bar = reinterpret_cast<uint64_t*>(base + L.sm_bar);
     const bool BULK = (p.use_bulk & 1) != 0, BULK_ST = (p.use_bulk & 2) != 0;
@@ -939,7 +1108,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
     // Start staging this warp's first record before anything else: the bulk copy only needs the warp's own mbarrier, so
     // its DRAM round trip overlaps the table set-up below instead of following it.  (With PDL the records may still be
     // written by the previous grid: the load waits for it, after the tables.)
-    if (BULK && lane == 0) {
+    if (BULK && lane == 0 && !helper) {
         mbar_init(bar, 1);
         fence_barrier_init();
         if (!PDL && env0 < p.n_envs) {
@@ -970,7 +1139,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
     if (PDL) {
         // ... and wait here, tables built, for the previous grid to complete and flush before touching any record / output
         asm volatile("griddepcontrol.wait;" ::: "memory");
-        if (BULK && lane == 0 && env0 < p.n_envs) {
+        if (BULK && lane == 0 && !helper && env0 < p.n_envs) {
             mbar_arrive_expect_tx(bar, (uint32_t)L.rec_bytes);
             bulk_g2s(base, p.state + env0 * (long long)L.rec_bytes, (uint32_t)L.rec_bytes, bar);
         }
@@ -983,6 +1152,14 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
     e.svc_cdf = p.tr.d_service_cdf;                  // searched from a 64-way bracket, on admissions only
     e.svc_bracket = have_bracket ? svc_bracket_s : nullptr;
     uint32_t phase = 0;
+    if (helper) {
+        // helper warps: wait for each record of this CTA, then serve the main warp's phases until it closes the env
+        for (long long env = env0; env < p.n_envs; env += stride) {
+            if (BULK) { mbar_wait(bar, phase); phase ^= 1; }
+            team_serve(e, (int)threadIdx.x, nth);
+        }
+        return;
+    }
     for (long long env = env0; env < p.n_envs; env += stride) {
         unsigned char* grec = p.state + env * (long long)L.rec_bytes;
         // ---- stage the record into shared memory ----
@@ -1021,13 +1198,15 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
             if (agent_k != VMGYM_AGENT_NONE) {
                 if (!(quiet && (quiet_key == 0 || quiet_key == my_key)) || need_vectors) {
                     // the agent sees the float32 observation of the current state (env.py:296)
-                    const double* cpu = e.cpu();
-                    const double* mem = e.mem();
-                    for (int q = lane; q < cP; q += 32) { e.cpu32()[q] = (float)cpu[q]; e.mem32()[q] = (float)mem[q]; }
-                    __syncwarp();
+                    if (!TM) {                   // (team mode: part of the team's PREP phase inside agent_act)
+                        const double* cpu = e.cpu();
+                        const double* mem = e.mem();
+                        for (int q = lane; q < cP; q += 32) { e.cpu32()[q] = (float)cpu[q]; e.mem32()[q] = (float)mem[q]; }
+                        __syncwarp();
+                    }
                     AgentView<PT> av;
                     av.place = e.place(); av.cc = e.cpuc(); av.mc = e.memc(); av.c32 = nullptr; av.m32 = nullptr; av.sz32 = sz32;
-                    n_found = agent_act(e, av, agent_k, tiebreak_k, true);
+                    n_found = agent_act<PT, TM>(e, av, agent_k, tiebreak_k, true, nth);
                     evaluated = true;
                     if (p.out.d_action) {        // the action vector: proposals, else the current placement (firstfit.py:29)
                         PT* ao = reinterpret_cast<PT*>(p.out.d_action) + env * (long long)cV;
@@ -1053,7 +1232,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
                 __syncwarp();
                 have_actions = any != 0;
             }
-            res = env_step<PT, REWARD_CT, MODE_CT, (SPEC < 0)>(e, p, env, valid_g, have_actions);
+            res = env_step<PT, REWARD_CT, MODE_CT, (SPEC < 0), TM>(e, p, env, valid_g, have_actions, nth);
             if (res.changed) {
                 quiet = false;
                 obs_stale = true;
@@ -1077,8 +1256,15 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
             const bool mirrored = MIRROR_OK && p.out.d_obs_mirror != nullptr;
             const bool persistent = p.out.obs_persistent != 0 || mirrored;
             if (!persistent || obs_stale) {
-                if (mirrored) write_obs_mirrored(e, p.out.d_obs + env * (long long)cD, p.out.d_obs_mirror + env * (long long)cD);
-                else write_obs(e, p.out.d_obs + env * (long long)cD);
+                float* orow = p.out.d_obs + env * (long long)cD;
+                if (mirrored) write_obs_mirrored(e, orow, p.out.d_obs_mirror + env * (long long)cD);
+                else if (TM) {
+                    if (lane == 0) {
+                        e.ctl()[2] = (int)(unsigned)((unsigned long long)orow & 0xffffffffull);
+                        e.ctl()[3] = (int)(unsigned)((unsigned long long)orow >> 32);
+                    }
+                    team_run(e, TEAM_OBS, nth);
+                } else write_obs(e, orow);
             }
             if (persistent) obs_stale = false;
         }
@@ -1093,6 +1279,7 @@ __global__ void __launch_bounds__(128, 7) step_kernel(const __grid_constant__ St
             }
         }
 
+        if (TM) team_run(e, TEAM_END, nth);       // helpers move on to the next record of this CTA
         // ---- write the record back ----
         if (BULK_ST) {
             fence_proxy_async();          // generic-proxy writes to smem -> visible to the async proxy
