@@ -7,12 +7,13 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 TEAM = int(sys.argv[2]) if len(sys.argv) > 2 else 0          # warps teaming on one env (0 = auto)
 DRL = (int(sys.argv[3]) if len(sys.argv) > 3 else 1) != 0
 from vmgym import _native as nv
-nv.lib().vmgym_set_tuning(TEAM, 7)
+BITS = int(sys.argv[4]) if len(sys.argv) > 4 else 7
+nv.lib().vmgym_set_tuning(TEAM, BITS)
 kw = dict(pms=1000, vms=3000, arrival_rate=1.6, service_length=1000, training_steps=10000, eval_steps=100000, seed=0,
           reward_function="wr", sequence="highuniform", allow_null_action=True)
 vec = VecVmEnv(Config(**kw), N, rng="philox")
 t0 = time.perf_counter(); vec.agent_step("bestfit", 3000, want_obs=False, want_action=False, want_valid=False); torch.cuda.synchronize()
-print(f"team {TEAM}: warm-up 3000 steps x {N} envs: {time.perf_counter() - t0:.2f} s")
+print(f"team {TEAM} bits {BITS}: warm-up 3000 steps x {N} envs: {time.perf_counter() - t0:.2f} s")
 for steps in (1, 100):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     vec.agent_step("bestfit", steps, want_obs=True, want_action=False, want_valid=False)

@@ -57,9 +57,9 @@ static int make_layout(const vmgym_config* c, DevLayout* L, vmgym_layout* pub)
     l.sm_prop = l.sm_fit + 512 + align_up(2 * l.Pp, 16);      // u32 prop[ceil(Vp/32)]: slots whose action differs
     l.sm_stats = l.sm_prop + align_up(4 * ((l.Vp + 31) / 32), 16);   // f64[VMGYM_STATS] eval-summary sums of the launch
     l.sm_bar = l.sm_stats + 8 * VMGYM_STATS;
-    // team mode (u16 placements = large shapes, one env per CTA): command words + two slot-chunk bitmaps (departures, candidates)
+    // team mode (u16 placements = large shapes, one env per CTA): command words + three slot-chunk bitmaps (departures, candidates, empty slots)
     l.sm_team = l.sm_bar + 16;
-    const int team_bytes = pb == 2 ? 16 + 2 * align_up(4 * ((l.Vp + 31) / 32), 16) : 0;
+    const int team_bytes = pb == 2 ? 16 + 3 * align_up(4 * ((l.Vp + 31) / 32), 16) : 0;
     l.sm_stride = align_up(l.sm_team + team_bytes, 128);
     l.svc_cdf_smem = 0;                                    // service table stays in global memory (used on admissions only)
     l.sm_tables = align_up(SIZE_TABLE * 8 + SIZE_TABLE * 4 + ARR_CDF_SMEM * 8 + l.svc_cdf_smem * 8 + (SVC_BRACKETS + 1) * 2, 128);
@@ -219,7 +219,7 @@ int vmgym_set_tuning(int warps_per_cta, int use_bulk_copy)
 {
     if (warps_per_cta < 0 || warps_per_cta > 8) return fail(VMGYM_EINVAL, "warps_per_cta must be 0..8");
     g_warps_per_cta = warps_per_cta;
-    g_use_bulk = use_bulk_copy & 7;
+    g_use_bulk = use_bulk_copy & 15;
     return VMGYM_OK;
 }
 

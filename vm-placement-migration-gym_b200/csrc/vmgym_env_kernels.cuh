@@ -26,7 +26,7 @@ struct StepParams {
     vmgym_outputs out;
     int agent, tiebreak, n_steps;
     int use_bulk;             // bit 0: load records with cp.async.bulk, bit 1: store them with cp.async.bulk (else 128-bit ld/st),
-                              // bit 2: programmatic dependent launch
+                              // bit 2: programmatic dependent launch, bit 3: team mode builds the fit table with the main warp alone (A/B)
 };
 
 constexpr uint32_t STATUS_EXHAUSTED = 1u;   // pre-sampled trace ran out (the reference would raise, env.py:282)
@@ -55,6 +55,7 @@ struct Env {
     const uint64_t* svc_cdf;
     const uint16_t* svc_bracket;       // 65-entry search brackets of the service table (shared memory) or nullptr
     int P, V, lane;
+    int tune;                          // StepParams::use_bulk (team-mode experiment bits); only read by the team-mode kernel
 
     __device__ __forceinline__ double* cpu() const { return reinterpret_cast<double*>(VMGYM_SMEM(base)); }           // env.py:190
     __device__ __forceinline__ double* mem() const { return reinterpret_cast<double*>(VMGYM_SMEM(base) + L->off_mem); }
@@ -80,6 +81,10 @@ struct Env {
     __device__ __forceinline__ unsigned* cmask() const
     {
         return reinterpret_cast<unsigned*>(VMGYM_SMEM(base) + L->sm_team + 16 + align_up(4 * ((L->Vp + 31) / 32), 16));
+    }
+    __device__ __forceinline__ unsigned* emask() const
+    {
+        return reinterpret_cast<unsigned*>(VMGYM_SMEM(base) + L->sm_team + 16 + 2 * align_up(4 * ((L->Vp + 31) / 32), 16));
     }
 };
 
@@ -185,7 +190,7 @@ __device__ __forceinline__ unsigned cand_bits4(uint32_t pl4, uint32_t cc4, uint3
 // shared memory; the results of a parallel phase that feed sequential logic (which slots finished, which 32-slot chunks
 // hold a candidate) are bitmaps, consumed by the main warp in slot order, so every decision is taken in the reference's order.
 // ---------------------------------------------------------------------------------------------------
-enum { TEAM_END = 0, TEAM_OBS = 1, TEAM_PREP = 2, TEAM_FILTER = 3, TEAM_COUNTDOWN = 4 };
+enum { TEAM_END = 0, TEAM_OBS = 1, TEAM_PREP = 2, TEAM_FILTER = 3, TEAM_COUNTDOWN = 4, TEAM_FIT = 5 };
 
 __device__ __forceinline__ void team_bar(int id, int nth) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nth) : "memory"); }
 
@@ -226,19 +231,40 @@ __device__ __forceinline__ void team_phase(const Env<PT>& e, int cmd, int tid, i
         }
     } else if (cmd == TEAM_COUNTDOWN) {
         // running VMs: remaining -= 1 if > 0 (env.py:245-247); the slots that reach 0 are reported as a bitmap
+        // (and the empty slots as a second bitmap, for the admission of arrivals)
         const PT* place = e.place();
         uint16_t* rem = e.rem();
         unsigned* tmk = e.tmask();
+        unsigned* emk = e.emask();
         for (int v0 = (tid & ~31); v0 < V; v0 += nth) {
             const int v = v0 + (tid & 31);
+            const int pl = v < V ? (int)place[v] : P;
             bool term = false;
-            if (v < V && (int)place[v] < P) {
+            if (pl < P) {
                 int r = (int)rem[v];
                 if (r > 0) { r -= 1; rem[v] = (uint16_t)r; }
                 term = r == 0;
             }
-            const unsigned m = __ballot_sync(FULL, term);
-            if ((tid & 31) == 0) tmk[v0 >> 5] = m;
+            const unsigned m = __ballot_sync(FULL, term), em = __ballot_sync(FULL, pl == P + 1);
+            if ((tid & 31) == 0) { tmk[v0 >> 5] = m; emk[v0 >> 5] = em; }
+        }
+    } else if (cmd == TEAM_FIT) {
+        // scatter pass of the fit table (see rebuild_fit_table): fitm[kc] = max(km + 1), plus the two global maxima in
+        // ctl[1] / ctl[2] (zeroed by the main warp)
+        unsigned* fitm = e.fitm();
+        const uint16_t* cap = e.cap();
+        if (tid < 128) fitm[tid] = 0u;
+        team_bar(3, nth);
+        unsigned kcmax = 0, kmmax = 0;
+        for (int q = tid; q < P; q += nth) {
+            const unsigned w = cap[q];
+            atomicMax(&fitm[w & 0xffu], (w >> 8) + 1u);
+            kcmax = max(kcmax, w & 0xffu); kmmax = max(kmmax, w >> 8);
+        }
+        kcmax = __reduce_max_sync(FULL, kcmax); kmmax = __reduce_max_sync(FULL, kmmax);
+        if ((tid & 31) == 0) {
+            atomicMax(reinterpret_cast<unsigned*>(const_cast<int*>(e.ctl())) + 1, kcmax);
+            atomicMax(reinterpret_cast<unsigned*>(const_cast<int*>(e.ctl())) + 2, kmmax);
         }
     }
 }
@@ -270,6 +296,32 @@ __device__ __forceinline__ void team_serve(const Env<PT>& e, int tid, int nth)
     }
 }
 
+// the fit table (rebuild_fit_table) built by the whole team: scatter pass in parallel, suffix maximum by the main warp
+template <typename PT>
+__device__ __forceinline__ unsigned rebuild_fit_table_team(const Env<PT>& e, int nth)
+{
+    const int lane = e.lane;
+    unsigned* fitm = e.fitm();
+    __syncwarp();
+    if (lane == 0) { e.ctl()[1] = 0; e.ctl()[2] = 0; }
+    team_run(e, TEAM_FIT, nth);
+    const unsigned kcmax = (unsigned)e.ctl()[1], kmmax = (unsigned)e.ctl()[2];
+    uint4 q = reinterpret_cast<uint4*>(fitm)[lane];            // lane owns codes 4*lane .. 4*lane+3
+    q.z = max(q.z, q.w); q.y = max(q.y, q.z); q.x = max(q.x, q.y);
+    unsigned s = q.x;                                          // suffix max over lanes >= lane
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_down_sync(FULL, s, o);
+        if (lane + o < 32) s = max(s, t);
+    }
+    unsigned ex = __shfl_down_sync(FULL, s, 1);
+    if (lane == 31) ex = 0u;
+    q.x = max(q.x, ex); q.y = max(q.y, ex); q.z = max(q.z, ex); q.w = max(q.w, ex);
+    reinterpret_cast<uint4*>(fitm)[lane] = q;
+    __syncwarp();
+    return kcmax | (kmmax << 8);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Heuristic agents on the float32 view (firstfit.py:21-38, bestfit.py:21-40).  Lanes own PMs p = lane + 32 i.
 // For every waiting VM, in slot order: first-fit takes the lowest-index PM that fits, best-fit the fitting PM with
@@ -295,7 +347,8 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
         else { for (int p = lane; p < P; p += 32) cap[p] = (uint16_t)(max_code(e.sz32, cpu32[p]) | (max_code(e.sz32, mem32[p]) << 8)); }
         for (int c = lane; c < (V + 31) / 32; c += 32) e.prop()[c] = 0u;
     }
-    unsigned kmax = rebuild_fit_table(e);
+    const bool team_fit = TM && (e.tune & 8) == 0;       // the team builds the fit table (use_bulk bit 3: main warp alone, for A/B runs)
+    unsigned kmax = team_fit ? rebuild_fit_table_team(e, nth) : rebuild_fit_table(e);
 
     // slots are visited in groups: 4 per lane (128 per pass) for byte placements, 1 per lane otherwise
     constexpr int SPL = sizeof(PT) == 1 ? 4 : 1;
@@ -385,7 +438,7 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
                     placed_any = true;
                     if (lane == 0) { e.act()[vv] = (uint16_t)found; e.prop()[vv >> 5] |= 1u << (vv & 31); }
                     __syncwarp();
-                    kmax = rebuild_fit_table(e);   // capacities shrank: the remaining candidates are re-tested
+                    kmax = team_fit ? rebuild_fit_table_team(e, nth) : rebuild_fit_table(e);   // capacities shrank: the remaining candidates are re-tested
                     if (bits) {
                         unsigned nb;
                         if (SPL == 4) {
@@ -781,6 +834,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                         if (mem[pm] < 1e-7) mem[pm] = 0.0;
                         refresh_cap(e, pm);
                         place[vv] = (PT)(P + 1); cpuc[vv] = 0; memc[vv] = 0; rem[vv] = 0;
+                        e.emask()[vv >> 5] |= 1u << (vv & 31);         // empty from now on (admissions below)
                         if (vmstat) vmstat_close(vs.slots + vv * 4, tnow - vs.slots[vv * 4], 0u, vs.hist, vs.totals);
                     }
                 }
@@ -876,13 +930,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
         // When no slot was empty before this step, the empty slots are exactly the ones this step's departures freed,
         // already known in slot order: lane k admits into the k-th of them.  Otherwise scan for the lowest-index empties.
         const bool known = sizeof(PT) == 1 && sc->n_empty == 0 && served <= 4;
-        for (int c0 = 0; c0 < (known ? 32 : V) && admitted < quota; c0 += 32) {
-            int v = c0 + lane;
-            bool empty = v < V && !known && (int)place[v] == P + 1;
-            if (known) {
-                v = lane == 0 ? freed0 : (lane == 1 ? freed1 : (lane == 2 ? freed2 : freed3));
-                empty = lane < served;
-            }
+        auto admit_chunk = [&](int v, bool empty) {
             const unsigned m = __ballot_sync(FULL, empty);
             const int rank = admitted + __popc(m & ((1u << lane) - 1u));
             if (empty && rank < quota) {                       // lowest-index empty slots (:275-277)
@@ -907,6 +955,30 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                 if (vmstat) *reinterpret_cast<uint4*>(vs.slots + v * 4) = make_uint4(tnow, 0u, 0u, 0u);   // arrival (env.py:293)
             }
             admitted += __popc(m);
+        };
+        if (TM && sizeof(PT) != 1) {
+            // team mode: the countdown phase left a bitmap of the empty slots (+ this step's departures): only the
+            // chunks that hold one are visited, lowest index first
+            const unsigned* emk = e.emask();
+            const int n_chunks = (V + 31) / 32;
+            for (int cb0 = 0; cb0 < n_chunks && admitted < quota; cb0 += 32) {
+                unsigned nz = __ballot_sync(FULL, cb0 + lane < n_chunks && emk[cb0 + lane] != 0u);
+                while (nz && admitted < quota) {
+                    const int c = cb0 + __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    admit_chunk(32 * c + lane, ((emk[c] >> lane) & 1u) != 0u);
+                }
+            }
+        } else {
+            for (int c0 = 0; c0 < (known ? 32 : V) && admitted < quota; c0 += 32) {
+                int v = c0 + lane;
+                bool empty = v < V && !known && (int)place[v] == P + 1;
+                if (known) {
+                    v = lane == 0 ? freed0 : (lane == 1 ? freed1 : (lane == 2 ? freed2 : freed3));
+                    empty = lane < served;
+                }
+                admit_chunk(v, empty);
+            }
         }
         admitted = min(admitted, quota);
         csum = (long long)__reduce_add_sync(FULL, (unsigned)csum);
@@ -1146,7 +1218,7 @@ __global__ void __launch_bounds__(TM ? 256 : 128, TM ? 3 : 7) step_kernel(const 
     }
 
     Env<PT> e;
-    e.base = base; e.L = &p.L; e.sz64 = sz64; e.sz32 = sz32; e.P = cP; e.V = cV; e.lane = lane;
+    e.base = base; e.L = &p.L; e.sz64 = sz64; e.sz32 = sz32; e.P = cP; e.V = cV; e.lane = lane; e.tune = p.use_bulk;
     e.arr_cdf = p.tr.d_arrival_cdf;
     e.arr_cdf32 = arr_in_smem ? arr_cdf_s : nullptr;
     e.svc_cdf = p.tr.d_service_cdf;                  // searched from a 64-way bracket, on admissions only
