@@ -190,7 +190,7 @@ __device__ __forceinline__ unsigned cand_bits4(uint32_t pl4, uint32_t cc4, uint3
 // shared memory; the results of a parallel phase that feed sequential logic (which slots finished, which 32-slot chunks
 // hold a candidate) are bitmaps, consumed by the main warp in slot order, so every decision is taken in the reference's order.
 // ---------------------------------------------------------------------------------------------------
-enum { TEAM_END = 0, TEAM_OBS = 1, TEAM_PREP = 2, TEAM_FILTER = 3, TEAM_COUNTDOWN = 4, TEAM_FIT = 5 };
+enum { TEAM_END = 0, TEAM_OBS = 1, TEAM_PREP = 2, TEAM_FILTER = 3, TEAM_COUNTDOWN = 4, TEAM_FIT = 5, TEAM_SCAN = 6 };
 
 __device__ __forceinline__ void team_bar(int id, int nth) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nth) : "memory"); }
 
@@ -266,6 +266,33 @@ __device__ __forceinline__ void team_phase(const Env<PT>& e, int cmd, int tid, i
             atomicMax(reinterpret_cast<unsigned*>(const_cast<int*>(e.ctl())) + 1, kcmax);
             atomicMax(reinterpret_cast<unsigned*>(const_cast<int*>(e.ctl())) + 2, kmmax);
         }
+    } else if (cmd == TEAM_SCAN) {
+        // the PM scan of one waiting VM (sizes in ctl[2] / ctl[3] as float bits, agent in ctl[1]) on the agent's float32
+        // view: first-fit -> lowest fitting index; best-fit -> largest cpu+memory among the fitting PMs, ties -> highest
+        // index.  Every warp leaves (key, index + 1) in tmp[]; the main warp combines them.
+        const volatile int* ctl = e.ctl();
+        const int agent = ctl[1];
+        const float c32 = __int_as_float(ctl[2]), m32 = __int_as_float(ctl[3]);
+        const float* cpu32 = e.cpu32();
+        const float* mem32 = e.mem32();
+        unsigned* res = reinterpret_cast<unsigned*>(e.tmp());
+        unsigned bestk = 0, bestp = 0;
+        if (agent == VMGYM_AGENT_FIRSTFIT) {
+            // key = ~index so that the maximum key is the lowest index
+            for (int q = tid; q < P; q += nth) {
+                const bool fit = (cpu32[q] + c32 <= 1.0f) && (mem32[q] + m32 <= 1.0f);
+                if (fit && bestk == 0u) { bestk = ~(unsigned)q; bestp = (unsigned)q + 1u; }
+            }
+        } else {
+            for (int q = tid; q < P; q += nth) {
+                const bool fit = (cpu32[q] + c32 <= 1.0f) && (mem32[q] + m32 <= 1.0f);
+                const unsigned kb = __float_as_uint(cpu32[q] + mem32[q]) + 1u;   // keys >= 0: bits order like values
+                if (fit && kb >= bestk) { bestk = kb; bestp = (unsigned)q + 1u; }
+            }
+        }
+        const unsigned gk = __reduce_max_sync(FULL, bestk);
+        const unsigned gi = __reduce_max_sync(FULL, bestk == gk ? bestp : 0u);
+        if ((tid & 31) == 0) { res[2 * (tid >> 5)] = gk; res[2 * (tid >> 5) + 1] = gi; }
     }
 }
 
@@ -322,6 +349,22 @@ __device__ __forceinline__ unsigned rebuild_fit_table_team(const Env<PT>& e, int
     return kcmax | (kmmax << 8);
 }
 
+// one waiting VM's PM scan by the whole team (see TEAM_SCAN); returns the chosen PM or -1
+template <typename PT>
+__device__ __forceinline__ int team_scan(const Env<PT>& e, int agent, float c32, float m32, int nth)
+{
+    __syncwarp();
+    if (e.lane == 0) { e.ctl()[1] = agent; e.ctl()[2] = __float_as_int(c32); e.ctl()[3] = __float_as_int(m32); }
+    team_run(e, TEAM_SCAN, nth);
+    const unsigned* res = reinterpret_cast<const unsigned*>(e.tmp());
+    const int nw = nth >> 5;
+    const unsigned k = e.lane < nw ? res[2 * e.lane] : 0u, ix = e.lane < nw ? res[2 * e.lane + 1] : 0u;
+    const unsigned gk = __reduce_max_sync(FULL, k);
+    const int found = (int)__reduce_max_sync(FULL, k == gk ? ix : 0u) - 1;      // gk == 0: every ix is 0 -> -1
+    __syncwarp();
+    return found;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Heuristic agents on the float32 view (firstfit.py:21-38, bestfit.py:21-40).  Lanes own PMs p = lane + 32 i.
 // For every waiting VM, in slot order: first-fit takes the lowest-index PM that fits, best-fit the fitting PM with
@@ -376,7 +419,21 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
                 const int vv = SPL * (u0 + b) + j;
                 const float c32 = av.cpu_size(vv), m32 = av.mem_size(vv);
                 int found = -1;
-                if (agent == VMGYM_AGENT_FIRSTFIT) {
+                if (TM && tiebreak != VMGYM_TIE_NUMPY_INTROSORT) {
+                    // team mode: all warps scan (the numpy-introsort tie rule stays on the main warp, below)
+                    found = team_scan(e, agent, c32, m32, nth);
+                    if (found >= 0 && lane == 0) {
+                        const float nc = cpu32[found] + c32;
+                        cpu32[found] = nc;                              // firstfit.py:36 / bestfit.py:37-38
+                        unsigned cw = (cap[found] & 0xff00u) | (unsigned)max_code(e.sz32, nc);
+                        if (agent != VMGYM_AGENT_FIRSTFIT) {
+                            const float nm = mem32[found] + m32;
+                            mem32[found] = nm;
+                            cw = (cw & 0xffu) | ((unsigned)max_code(e.sz32, nm) << 8);
+                        }
+                        cap[found] = (uint16_t)cw;
+                    }
+                } else if (agent == VMGYM_AGENT_FIRSTFIT) {
                     for (int i0 = 0; i0 < P; i0 += 32) {
                         const int p = i0 + lane;
                         const bool fit = p < P && (cpu32[p] + c32 <= 1.0f) && (mem32[p] + m32 <= 1.0f);
