@@ -218,6 +218,16 @@ int vmgym_gae(const float* d_rewards, const float* d_values, const float* d_next
 int vmgym_drlvmp_choice(const vmgym_config* cfg, const float* d_obs, const int32_t* d_vm_index, const int32_t* d_choice,
                         int64_t n_envs, int32_t* d_pm_out, void* stream);
 
+/* One iteration of DRLVMPAgent.act (src/agents/drlvmp.py:504-530) after the head GEMMs, for every env with a k-th waiting VM
+ * (k = *d_k + k_offset, the counter kept on the device so a captured graph can be replayed): d_heads [n, heads_ld >= (4 + 1) * atoms] = advantage atoms of the
+ * four actions followed by the value atoms (Network.dist, :355-368) -> q-values -> argmax -> heuristic PM choice on the
+ * working observation d_obs [n, 3V+2P] (as vmgym_drlvmp_choice) -> placement written into d_obs -> d_pre [n, hidden] (the
+ * feature layer's pre-activation) corrected by the changed entry's weight column (d_w_cols [3V+2P, hidden], row j = column j
+ * of the layer's weight) and d_feat = relu(d_pre).  d_order [n, V]: waiting slots first, in slot order; d_n_wait [n]. */
+int vmgym_drlvmp_iter(const vmgym_config* cfg, int32_t hidden, int32_t n_actions, int32_t atoms, const float* d_heads,
+                      int32_t heads_ld, const float* d_support, float* d_obs, const int64_t* d_order, const int64_t* d_n_wait, const int64_t* d_k,
+                      int32_t k_offset, const float* d_w_cols, float* d_pre, float* d_feat, int64_t n_envs, void* stream);
+
 /* The actor's output layer (src/agents/ppo.py:103-109, nn.Linear(hidden, V*A)) on tcgen05 tensor cores:
  * d_c[M, N] (fp32, row stride ldc) = d_a[M, K] (bf16) . d_w[N, K]^T (bf16, the nn.Linear weight layout) + d_bias[N].
  * K must be a multiple of 8, operands 16-byte aligned.  bf16 inputs are a throughput mode (rollouts); parity of

@@ -76,6 +76,8 @@ def test_act_loop_equals_sequential_restatement():
     assert np.array_equal(batched, agent.act(obs, refresh=3).cpu().numpy())
     assert np.array_equal(batched, agent.act(obs, graph=True).cpu().numpy())            # CUDA-graph replay per waiting VM
     assert np.array_equal(batched, agent.act(obs, graph=True, refresh=2).cpu().numpy())  # cached graph, second call
+    assert np.array_equal(batched, agent.act(obs, graph=True, fused=False).cpu().numpy())  # graph of torch ops + choice kernel
+    assert np.array_equal(batched, agent.act(obs, graph=True, fused=True, refresh=5).cpu().numpy())  # 2 GEMMs + vmgym_drlvmp_iter
     for i in range(7):
         o = obs[i:i + 1].clone()
         for v in torch.nonzero(obs[i, :30] == 10.0).flatten().tolist():

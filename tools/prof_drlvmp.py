@@ -9,6 +9,7 @@ kw = dict(pms=1000, vms=3000, arrival_rate=1.6, service_length=1000, training_st
           reward_function="wr", sequence="highuniform", allow_null_action=True)
 vec = VecVmEnv(Config(**kw), 1024, rng="philox")
 vec.agent_step("bestfit", 3000, want_obs=False, want_action=False, want_valid=False)
+torch.set_float32_matmul_precision("high")
 agent = DRLVMPAgent(vec, DRLVMPConfig(hidden_size=512)); agent.eval()
 obs = vec.observe()
 agent.act(obs)

@@ -28,6 +28,7 @@ print("waiting per env", float(np.mean(c["slot_counts"] & 0xffff)), "empty", flo
 if not DRL:
     sys.exit(0)
 from vmgym.drlvmp import DRLVMPAgent, DRLVMPConfig
+torch.set_float32_matmul_precision('high')      # as the reference's main.py:45
 agent = DRLVMPAgent(vec, DRLVMPConfig(hidden_size=512))
 agent.eval()
 obs = vec.observe()
@@ -40,3 +41,10 @@ for _ in range(2):
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / 2
 print(f"DRL-VMP act+step: {dt:.3f} s per step of {N} envs -> {N / dt:.0f} env-steps/s")
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(2):
+    a = agent.act(obs, fused=False)
+    obs, *_ = vec.step(a, want_valid=False)
+torch.cuda.synchronize()
+dt = (time.perf_counter() - t0) / 2
+print(f"DRL-VMP act+step (unfused graph of torch ops): {dt:.3f} s per step -> {N / dt:.0f} env-steps/s")

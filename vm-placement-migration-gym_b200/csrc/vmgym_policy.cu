@@ -649,6 +649,171 @@ extern "C" int vmgym_drlvmp_choice(const vmgym_config* cfg, const float* d_obs, 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// One iteration of DRLVMPAgent.act (src/agents/drlvmp.py:504-530) for every env of a batch, everything after the
+// head GEMMs in ONE kernel: dueling combination + softmax over the atoms + clamp + expectation (Network.dist/forward,
+// :355-372) -> argmax action (:514-515) -> heuristic PM choice on the working observation (:549-617, same arithmetic
+// as drlvmp_choice_kernel) -> placement written into the working observation -> rank-1 correction of the feature
+// layer's pre-activation for the changed input (the VM's placement entry) and its ReLU for the next iteration's GEMMs.
+// The waiting-VM counter k lives on the device (incremented by the caller between launches) so that a captured CUDA
+// graph of one iteration can be replayed for every waiting VM.  One warp per env.
+// ---------------------------------------------------------------------------------------------------
+namespace vmgym {
+
+__global__ void drlvmp_iter_kernel(int P, int V, int D, int H, int n_actions, int atoms, const float* __restrict__ heads, int heads_ld,
+                                   const float* __restrict__ support, float* obs, const long long* __restrict__ order,
+                                   const long long* __restrict__ n_wait, const long long* __restrict__ kdev, int k_offset,
+                                   const float* __restrict__ w_cols, float* pre, float* feat, long long n_envs)
+{
+    const int lane = threadIdx.x & 31;
+    const long long env = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (env >= n_envs) return;
+    const long long k = *kdev + k_offset;
+    if (!(n_wait[env] > k)) return;                                        // no k-th waiting VM in this env
+    const int v = (int)order[env * V + (k < V ? k : V - 1)];
+    if (v < 0 || v >= V) return;
+
+    // ---- q-values: softmax_j(val_j + adv_aj - mean_a adv_aj), clamped at 1e-3, dotted with the support ----
+    const float* hd = heads + env * (long long)heads_ld;                   // [n_actions][atoms] advantages, then [atoms] values
+    // all (4 + 1) x atoms head outputs of this env are loaded up front (<= 4 atoms per lane), the mean over actions once
+    constexpr int NA = 4;
+    float adv[NA][4], base[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int j = lane + 32 * i;
+        const bool in = j < atoms;
+#pragma unroll
+        for (int b = 0; b < NA; b++) adv[b][i] = in ? hd[b * atoms + j] : 0.f;
+        base[i] = in ? hd[NA * atoms + j] : 0.f;
+    }
+    float sup[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) sup[i] = lane + 32 * i < atoms ? support[lane + 32 * i] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float mean = 0.f;
+#pragma unroll
+        for (int b = 0; b < NA; b++) mean += adv[b][i];
+        base[i] -= mean / (float)NA;                                       // val_j - mean_a adv_aj
+    }
+    int best_a = 0;
+    float best_q = -INFINITY;
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+        float z[4];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            z[i] = -INFINITY;
+            if (lane + 32 * i < atoms) { z[i] = base[i] + adv[a][i]; mx = fmaxf(mx, z[i]); }
+        }
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (lane + 32 * i < atoms) { z[i] = expf(z[i] - mx); sum += z[i]; }
+        }
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (lane + 32 * i < atoms) q += fmaxf(z[i] / sum, 1e-3f) * sup[i];
+        }
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(FULL, q, o);
+        if (q > best_q) { best_q = q; best_a = a; }                        // first maximum, like torch.argmax
+    }
+    // heuristic of the chosen action only exists for the reference's four (worst-fit, dot, L2, best-fit)
+    const int ch = best_a;
+
+    // ---- heuristic PM choice on the working observation (see drlvmp_choice_kernel) ----
+    float* o = obs + env * (long long)D;
+    const float vc = o[V + v], vm = o[2 * V + v];
+    const float* cpu = o + 3 * V;
+    const float* mem = o + 3 * V + P;
+    float bestk = INFINITY;
+    int bestt = 0x7fffffff, bestp = -1;
+    // 8 PMs per lane and pass, all 16 loads issued before the first compare (the scan is latency-, not bandwidth-bound)
+    for (int p0 = 0; p0 < P; p0 += 256) {
+        float cl[8], ml[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int p = p0 + lane + 32 * i;
+            cl[i] = p < P ? cpu[p] : 0.f;
+            ml[i] = p < P ? mem[p] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int p = p0 + lane + 32 * i;
+            const float c = cl[i], m = ml[i];
+            float key;
+            int tie = p;
+            bool ok = p < P;
+            if (ch == 0) { key = c + m; ok = ok && (c + vc <= 1.0f) && (m + vm <= 1.0f); }
+            else if (ch == 3) { key = -(c + m); tie = -p; ok = ok && (c + vc <= 1.0f) && (m + vm <= 1.0f); }
+            else if (ch == 1) key = c * vc + m * vm;
+            else { const float dc = c - vc, dm = m - vm; key = sqrtf(dc * dc + dm * dm); }
+            if (ok && (key < bestk || (key == bestk && tie < bestt))) { bestk = key; bestt = tie; bestp = p; }
+        }
+    }
+    for (int o2 = 16; o2 > 0; o2 >>= 1) {
+        const float ok_ = __shfl_xor_sync(FULL, bestk, o2);
+        const int ot = __shfl_xor_sync(FULL, bestt, o2), op = __shfl_xor_sync(FULL, bestp, o2);
+        if (op >= 0 && (bestp < 0 || ok_ < bestk || (ok_ == bestk && ot < bestt))) { bestk = ok_; bestt = ot; bestp = op; }
+    }
+    if (bestp < 0) return;                                                 // nothing fits: the VM stays WAIT (:527-528)
+
+    // ---- write the placement into the observation copy, correct the pre-activation, refresh its ReLU ----
+    const float oldv = o[v], newv = (float)bestp;
+    __syncwarp();
+    if (lane == 0) o[v] = newv;
+    const float delta = newv - oldv;
+    const float* __restrict__ wc = w_cols + (long long)v * H;
+    float* __restrict__ pr = pre + env * (long long)H;
+    float* __restrict__ ft = feat + env * (long long)H;
+    for (int h0 = 0; h0 < H; h0 += 256) {
+        float a[8], w[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int h = h0 + lane + 32 * i;
+            a[i] = h < H ? pr[h] : 0.f;
+            w[i] = h < H ? wc[h] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int h = h0 + lane + 32 * i;
+            if (h < H) {
+                const float x = a[i] + w[i] * delta;
+                pr[h] = x;
+                ft[h] = fmaxf(x, 0.f);
+            }
+        }
+    }
+}
+
+}  // namespace vmgym
+
+extern "C" int vmgym_drlvmp_iter(const vmgym_config* cfg, int32_t hidden, int32_t n_actions, int32_t atoms, const float* d_heads,
+                                 int32_t heads_ld, const float* d_support, float* d_obs, const int64_t* d_order, const int64_t* d_n_wait,
+                                 const int64_t* d_k, int32_t k_offset, const float* d_w_cols, float* d_pre, float* d_feat, int64_t n_envs,
+                                 void* stream)
+{
+    if (!cfg || !d_heads || !d_support || !d_obs || !d_order || !d_n_wait || !d_k || !d_w_cols || !d_pre || !d_feat || n_envs < 0)
+        return pfail(VMGYM_EINVAL, "null operand");
+    if (n_actions != 4) return pfail(VMGYM_EINVAL, "DRL-VMP has exactly four heuristic actions (drlvmp.py:517-530)");
+    if (atoms < 1 || atoms > 128 || hidden < 1) return pfail(VMGYM_EINVAL, "atoms must be 1..128");
+    if (heads_ld < (n_actions + 1) * atoms) return pfail(VMGYM_EINVAL, "heads_ld smaller than (n_actions + 1) * atoms");
+    if (n_envs == 0) return VMGYM_OK;
+    const int P = cfg->pms, V = cfg->vms, D = 3 * V + 2 * P;
+    const int threads = 256;
+    const long long blocks = (n_envs * 32 + threads - 1) / threads;
+    vmgym::drlvmp_iter_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        P, V, D, hidden, n_actions, atoms, d_heads, heads_ld, d_support, d_obs, (const long long*)d_order, (const long long*)d_n_wait,
+        (const long long*)d_k, k_offset, d_w_cols, d_pre, d_feat, n_envs);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return pfail(VMGYM_ECUDA, cudaGetErrorString(err));
+    return VMGYM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Prioritized-replay segment trees (src/segment_tree.py:8-142, used by src/agents/drlvmp.py:157-241): array-backed
 // binary trees over `capacity` (power of two) leaves holding fp64 values, node i = op(node 2i, node 2i+1) with the
 // reference's association, so sums / minima / prefix-sum descents are bit-identical to the Python floats.

@@ -160,7 +160,7 @@ class DRLVMPAgent(AgentBase):
         return pm
 
     @torch.no_grad()
-    def act(self, observation, incremental: bool = True, refresh: int = 128, graph: bool | None = None):
+    def act(self, observation, incremental: bool = True, refresh: int = 128, graph: bool | None = None, fused: bool | None = None):
         """drlvmp.py:504-512 for a batch of observations [n, D] (or one numpy observation).
 
         The reference re-evaluates the whole network for every waiting VM although only ONE observation entry changed
@@ -168,7 +168,9 @@ class DRLVMPAgent(AgentBase):
         and corrected by that entry's weight column (rank-1 update per env), and recomputed from scratch every `refresh`
         VMs; the difference to the full product is fp32 rounding (~1e-6 relative, inside the 1e-4 network tolerance).
         `graph` (default: batches of >= 64 envs) replays one CUDA graph per waiting VM instead of ~40 eager launches; the
-        VM counter lives on the device, so every replay is the same graph."""
+        VM counter lives on the device, so every replay is the same graph.  `fused` (default with `graph`): the replayed
+        iteration is two GEMMs (both hidden heads side by side, both output heads block-diagonal) + ONE kernel for everything
+        else (`vmgym_drlvmp_iter`: dueling softmax -> q -> argmax -> heuristic -> observation / feature update)."""
         vec = self.vec
         host = isinstance(observation, np.ndarray)
         obs_in = torch.from_numpy(np.ascontiguousarray(observation, np.float32)).to(self.device) if host else observation
@@ -177,6 +179,9 @@ class DRLVMPAgent(AgentBase):
         n, V, P = obs_in.shape[0], vec.V, vec.P
         if graph is None:
             graph = incremental and n >= 64
+        if fused is None:
+            fused = graph
+        fused = bool(fused and graph and self.n_actions == 4 and self.config.atom_size <= 128)
         st = self._act_state(n) if graph else None
         obs = st["obs"] if graph else obs_in.contiguous().clone()             # the working observation copy
         if graph:
@@ -229,7 +234,9 @@ class DRLVMPAgent(AgentBase):
             st["w_cols"].copy_(lin.weight.t())
             n_wait, order = st["n_wait"], st["order"]
             pre, kdev, w_cols = st["pre"], st["kdev"], st["w_cols"]
-            if st["graph"] is None and n_iter > 0:
+            if fused:
+                self._act_fused(st, eff, obs, n, n_iter, refresh, lin)
+            elif st["graph"] is None and n_iter > 0:
                 pre.copy_(lin(obs))
                 keep = obs.clone()
                 side = torch.cuda.Stream(device=self.device)
@@ -242,7 +249,7 @@ class DRLVMPAgent(AgentBase):
                 with torch.cuda.graph(g):
                     iteration(pre, kdev, w_cols)
                 st["graph"] = g
-            for k in range(n_iter):
+            for k in range(n_iter if not fused else 0):
                 if k % refresh == 0:
                     pre.copy_(lin(obs))
                 st["graph"].replay()
@@ -251,6 +258,61 @@ class DRLVMPAgent(AgentBase):
             a = action.cpu().numpy()
             return a[0] if single else a
         return action[0] if single else action
+
+    def _act_fused(self, st, eff, obs, n, n_iter, refresh, lin):
+        """The per-VM iteration of act() as 2 GEMMs + `vmgym_drlvmp_iter`, captured once and replayed per waiting VM."""
+        vec, dev = self.vec, self.device
+        (wah, bah), (wa, ba), (wvh, bvh), (wv, bv) = eff
+        Hh, H, atoms, A = wah.shape[0], wah.shape[1], self.config.atom_size, self.n_actions
+        if "WhT" not in st:
+            st["WhT"] = torch.empty((H, 2 * Hh), dtype=torch.float32, device=dev)
+            st["bh"] = torch.empty(2 * Hh, dtype=torch.float32, device=dev)
+            ld = -(-(A + 1) * atoms // 64) * 64                                # output width padded for the GEMM's tile shapes
+            st["WoT"] = torch.zeros((2 * Hh, ld), dtype=torch.float32, device=dev)
+            st["bo"] = torch.zeros(ld, dtype=torch.float32, device=dev)
+            st["feat"] = torch.empty((n, H), dtype=torch.float32, device=dev)
+            st["graph_fused"] = None
+        # both hidden heads side by side; both output heads block-diagonal (advantage atoms | value atoms)
+        st["WhT"][:, :Hh].copy_(wah.t()); st["WhT"][:, Hh:].copy_(wvh.t())
+        st["bh"][:Hh].copy_(bah); st["bh"][Hh:].copy_(bvh)
+        st["WoT"][:Hh, :A * atoms].copy_(wa.t()); st["WoT"][Hh:, A * atoms:(A + 1) * atoms].copy_(wv.t())
+        st["bo"][:A * atoms].copy_(ba); st["bo"][A * atoms:(A + 1) * atoms].copy_(bv)
+        pre, feat, kdev = st["pre"], st["feat"], st["kdev"]
+        ccfg = vec._ccfg()
+
+        act_mm = getattr(torch, "_addmm_activation", None)                    # addmm with the ReLU in the GEMM epilogue
+
+        def iteration(k_offset=0):
+            h = act_mm(st["bh"], feat, st["WhT"]) if act_mm is not None else torch.addmm(st["bh"], feat, st["WhT"]).relu_()
+            heads = torch.addmm(st["bo"], h, st["WoT"])
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            nv.check(nv.lib().vmgym_drlvmp_iter(C.byref(ccfg), H, A, atoms, heads.data_ptr(), heads.shape[1], self.support.data_ptr(), obs.data_ptr(),
+                                                st["order"].data_ptr(), st["n_wait"].data_ptr(), kdev.data_ptr(), k_offset,
+                                                st["w_cols"].data_ptr(), pre.data_ptr(), feat.data_ptr(), n, stream), "vmgym_drlvmp_iter")
+
+        # several iterations per captured graph (fewer replays); iterations past an env's last waiting VM are no-ops
+        unroll = next(u for u in (8, 4, 2, 1) if refresh % u == 0)
+        if st["graph_fused"] is None:
+            st["graph_fused"] = {}
+        if unroll not in st["graph_fused"] and n_iter > 0:
+            pre.copy_(lin(obs)); torch.clamp(pre, min=0.0, out=feat)
+            keep = obs.clone()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                iteration()                                                    # warm-up (allocations) outside the capture
+            torch.cuda.current_stream(dev).wait_stream(side)
+            obs.copy_(keep); kdev.zero_()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for u in range(unroll):
+                    iteration(u)                                               # VM k = device counter + u
+                kdev.add_(unroll)
+            st["graph_fused"][unroll] = g
+        for k in range(0, n_iter, unroll):
+            if k % refresh == 0:
+                pre.copy_(lin(obs)); torch.clamp(pre, min=0.0, out=feat)
+            st["graph_fused"][unroll].replay()
 
     def _act_state(self, n: int):
         """Static buffers (and, lazily, the captured graph) of act() for a batch of n observations."""
