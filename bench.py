@@ -329,6 +329,7 @@ def gpu_arm(args):
         s1000 = {"envs_per_gpu": E1, "ms_per_step": s0_.elapsed_time(s1_) / 10}
         # DRL-VMP rollout at this shape (drlvmp.py:504-512: one network evaluation + heuristic per WAITING VM, sequentially)
         from vmgym.drlvmp import DRLVMPAgent, DRLVMPConfig
+        torch.set_float32_matmul_precision("high")      # as the reference does (main.py:45)
         ag1 = DRLVMPAgent(v1, DRLVMPConfig(hidden_size=512))
         ag1.eval()
         o1 = v1.observe()
@@ -452,10 +453,12 @@ def gpu_arm(args):
                         "ms_per_step": s1000["ms_per_step"], "envs_per_gpu": s1000["envs_per_gpu"],
                         "roofline_frac": B1 * s1000["envs_per_gpu"] / (s1000["ms_per_step"] * 1e-3) / 1e9 / peak,
                         "drlvmp_rollout": {"value": world * s1000["envs_per_gpu"] / s1000["drlvmp_s_per_step"], "unit": UNIT,
-                                           "note": "DRLVMPAgent.act (H=512 dueling C51 net, one evaluation + heuristic kernel per waiting "
-                                                   "VM, ~900 per env and step at this load) + env.step"},
+                                           "note": "DRLVMPAgent.act (H=512 dueling C51 net, one network evaluation + heuristic per waiting "
+                                                   "VM, ~900 sequential evaluations per env and step at this load; each = 2 TF32 GEMMs + "
+                                                   "the fused vmgym_drlvmp_iter kernel, 8 per CUDA-graph replay) + env.step"},
                         "config": "synthetic 1000 PMs / 3000 VM slots, highuniform sizes, arrival 1.6 (100 % load), fused best-fit act+step, "
-                                  "one launch per step, same warp-per-env kernel (a CTA-per-env mapping for this shape is future work)"}
+                                  "one launch per step, team-mode kernel (one env per CTA: warp 0 steps, 7 helper warps join the "
+                                  "slot / PM loops; 3 CTAs per SM by shared memory, so 1024 envs take 3 rounds)"}
     if s10:
         B10 = algorithmic_bytes(10, 30)
         out["s10"] = {"value": world * s10["envs_per_gpu"] / (s10["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": s10["ms_per_step"],
