@@ -87,6 +87,8 @@ def _compare_state(vec, oracles, t, check_reward=None):
 SHAPES = {
     "s10": dict(pms=10, vms=30, arrival_rate=0.3, service_length=30, training_steps=400, eval_steps=100000,
                 reward_function="kl", allow_null_action=True),
+    "s10wr": dict(pms=10, vms=30, arrival_rate=0.3, service_length=30, training_steps=400, eval_steps=100000,
+                  reward_function="wr", allow_null_action=True),       # config/10.yml shape on the specialised kernels
     "s100": dict(pms=100, vms=300, arrival_rate=1.8182, service_length=1000, training_steps=10000, eval_steps=100000,
                  reward_function="wr", allow_null_action=True),
     "odd": dict(pms=33, vms=65, arrival_rate=1.0, service_length=50, training_steps=10000, eval_steps=100000,
@@ -270,7 +272,8 @@ def test_invalid_action_mask_matches_oracle():
 
 
 @pytest.mark.parametrize("shape,n_envs,steps,agent", [("s100", 6, 900, "firstfit"), ("s10", 12, 390, "firstfit"),
-                                                       ("wide", 3, 300, "firstfit"), ("s100", 4, 4200, "bestfit")])
+                                                       ("wide", 3, 300, "firstfit"), ("s100", 4, 4200, "bestfit"),
+                                                       ("s10wr", 12, 390, "firstfit"), ("s10wr", 12, 390, "bestfit")])
 def test_philox_mode_matches_oracle_on_same_draws(shape, n_envs, steps, agent):
     """rng='philox': the kernel's in-flight Philox/inverse-CDF draws == the host restatement of the same
     counters fed to the oracle env as a pre-sampled trace (arrivals, sizes, service lengths, cursors)."""

@@ -135,7 +135,8 @@ static int launch_step(StepParams& sp, cudaStream_t st)
     void (*kern)(const StepParams) = step_kernel<PT, 0, 0, -1>;
     if (team) kern = step_kernel<PT, 0, 0, -1, (sizeof(PT) == 2)>;
     static const bool specialise = getenv("VMGYM_NO_SPECIALIZE") == nullptr;               // A/B switch for experiments
-    if (specialise && sizeof(PT) == 1 && L.P == 100 && L.V == 300) {                        // config/100.yml
+    if constexpr (sizeof(PT) == 1) {
+    if (specialise && L.P == 100 && L.V == 300) {                                           // config/100.yml
         kern = step_kernel<PT, 100, 300, -1>;
         // the benchmark configurations of this shape: fused heuristic agents / external actions, reward wr, stable ties
         if (sp.reward_fn == VMGYM_REWARD_WR && sp.tiebreak == VMGYM_TIE_STABLE && !sp.out.d_vm_slots) {   // per-VM stats: generic kernel
@@ -147,8 +148,15 @@ static int launch_step(StepParams& sp, cudaStream_t st)
             else if (sp.agent == VMGYM_AGENT_NONE && mode == VMGYM_TRACE_PHILOX)
                 kern = step_kernel<PT, 100, 300, make_spec(VMGYM_AGENT_NONE, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>;
         }
-    } else if (specialise && sizeof(PT) == 1 && L.P == 10 && L.V == 30) {
+    } else if (specialise && L.P == 10 && L.V == 30) {
         kern = step_kernel<PT, 10, 30, -1>;                                                // config/10.yml
+        if (sp.reward_fn == VMGYM_REWARD_WR && sp.tiebreak == VMGYM_TIE_STABLE && !sp.out.d_vm_slots && sp.tr.mode == VMGYM_TRACE_PHILOX) {
+            if (sp.agent == VMGYM_AGENT_FIRSTFIT)                                          // BASELINE configs[0]: first-fit evaluation
+                kern = step_kernel<PT, 10, 30, make_spec(VMGYM_AGENT_FIRSTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>;
+            else if (sp.agent == VMGYM_AGENT_BESTFIT)
+                kern = step_kernel<PT, 10, 30, make_spec(VMGYM_AGENT_BESTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>;
+        }
+    }
     }
     // per (kernel, smem, warps) launch plan, computed once (also keeps these calls out of CUDA-graph capture)
     static thread_local size_t plan_smem = 0;
