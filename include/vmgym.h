@@ -257,7 +257,8 @@ int vmgym_segtree_retrieve(const double* d_sum_tree, int64_t capacity, const dou
 /* Tuning knobs (process-wide): warps per CTA of the step kernels (0 = auto; 1..8: byte-placement shapes run that many
  * envs per CTA, at most 4; u16-placement shapes run ONE env per CTA with that many warps teaming on it) and bulk-async record copies
  * (cp.async.bulk): use_bulk_copy bit 0 = loads, bit 1 = stores, bit 2 = programmatic dependent launch of the step kernels
- * (default 7); bit 3 = team mode builds its fit table with the main warp alone.  For experiments. */
+ * (default 7); bit 3 = team mode builds its fit table with the main warp alone; bit 4 = no double-buffered records in
+ * multi-round launches, bit 5 = double-buffer records of any size (default: records up to 1 KB).  For experiments. */
 int vmgym_set_tuning(int warps_per_cta, int use_bulk_copy);
 
 /* PrioritizedReplayBuffer.sample_batch (src/agents/drlvmp.py:178-241, src/segment_tree.py:35-62,103-118): stratified

@@ -225,6 +225,59 @@ def test_team_mode_widths_match_oracle(team_warps, shape, agent):
         nv.lib().vmgym_set_tuning(0, 7)
 
 
+@pytest.mark.parametrize("shape,n_envs,agent,rng", [("s100", 9000, "bestfit", "philox"), ("s10wr", 12000, "firstfit", "philox"),
+                                                     ("odd", 7000, "bestfit", "numpy"), ("s100", 7000, "external", "philox")])
+def test_double_buffered_multi_round_launch(shape, n_envs, agent, rng):
+    """More envs than resident warps: the launch walks several envs per warp with double-buffered records (next record
+    prefetched, previous write-back draining).  Same records, observations and rewards as the single-buffered kernel
+    (use_bulk bit 4), and sampled envs equal the oracle."""
+    torch = _torch()
+    from vmgym import VecVmEnv
+    from vmgym import _native as nv
+    kw = SHAPES[shape]
+    steps = 45
+    seeds = 1000 + np.arange(n_envs)
+    sample = [0, 1, n_envs // 3, n_envs // 2 + 1, n_envs - 2, n_envs - 1]
+    results = []
+    try:
+        for bits in (7 + 32, 7 + 16):              # double-buffered for any record size / never
+            nv.lib().vmgym_set_tuning(0, bits)
+            if rng == "philox":
+                vec = VecVmEnv(_cfg(**kw), n_envs, rng="philox", seeds=seeds)
+            else:
+                vec = VecVmEnv(_cfg(**kw), n_envs, seeds=seeds, trace_steps=steps + 4, max_admissions=4000)
+            rewards = []
+            for n in (1, 3, 1, 17, 1, 22):
+                if agent == "external":
+                    for _ in range(n):
+                        a = vec.vm_placement.clone()
+                        a[:, ::3] = vec.P                                     # suspend / keep waiting every third slot
+                        a[:, 1::7] = (torch.arange(a[:, 1::7].shape[1], device=a.device) % vec.P).to(a.dtype)
+                        vec.step(a)
+                        rewards.append(vec.reward.clone())
+                else:
+                    vec.agent_step(agent, n_steps=n, want_action=False, want_valid=False)
+                    rewards.append(vec.reward.clone())
+            results.append((vec.state.clone(), vec.obs.clone(), torch.stack(rewards), vec))
+    finally:
+        nv.lib().vmgym_set_tuning(0, 7)
+    (s_a, o_a, r_a, vec_a), (s_b, o_b, r_b, _) = results
+    assert torch.equal(s_a, s_b) and torch.equal(o_a, o_b) and torch.equal(r_a, r_b)
+    if agent != "external":
+        # sampled envs against the oracle (an env's trajectory does not depend on the batch it is in)
+        P, V = kw["pms"], kw["vms"]
+        obs_h = o_a.cpu().numpy()
+        for i in sample:
+            if rng == "philox":
+                ka, ta, ks, ts, lo, hi = vec_a.philox_tables
+                o = vo.OracleVmEnv(vo.OracleConfig(**dict(kw, seed=0)), trace_steps=4, trace_adm=4)
+                o.reset(trace=vo.philox_trace(int(seeds[i]), steps + 4, 4000, ka, ta, ks, ts, lo, hi))
+            else:
+                o = _oracle_batch(kw, seeds[i:i + 1], steps + 4, 4000)[0]
+            o.rollout(vo.AGENT_FIRSTFIT if agent == "firstfit" else vo.AGENT_BESTFIT, steps)
+            assert obs_h[i].tobytes() == o._obs().tobytes(), i
+
+
 @pytest.mark.parametrize("name", ["s100_firstfit_wr", "s100_bestfit_stable_wr", "s100_bestfit_introsort_wr",
                                   "s10_bestfit_stable_ut", "odd_p37_v70_eval"])
 def test_agent_act_kernel_on_reference_observations(name):

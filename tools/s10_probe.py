@@ -7,6 +7,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 cfg = yaml.safe_load(open(os.path.join(ROOT, "configs", "10.yml")))["environment"]; cfg["reward_function"] = "wr"
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 agent = sys.argv[2] if len(sys.argv) > 2 else "firstfit"
+BITS = int(sys.argv[3]) if len(sys.argv) > 3 else 7           # vmgym_set_tuning use_bulk bits (16 = no double-buffered records)
+from vmgym import _native as nv
+nv.lib().vmgym_set_tuning(0, BITS)
 vec = VecVmEnv(Config(**cfg), N, rng="philox")
 vec.agent_step(agent, n_steps=3000, want_obs=False, want_action=False, want_valid=False)
 for steps in (1, 100):
@@ -17,4 +20,4 @@ for steps in (1, 100):
         vec.agent_step(agent, steps, want_obs=True, want_action=False, want_valid=False)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
-    print(f"{agent} N={N} {steps} step(s)/launch: {ms:.3f} ms -> {N * steps / ms / 1e6:.3f} G env-steps/s")
+    print(f"bits {BITS} {agent} N={N} {steps} step(s)/launch: {ms:.3f} ms -> {N * steps / ms / 1e6:.3f} G env-steps/s")

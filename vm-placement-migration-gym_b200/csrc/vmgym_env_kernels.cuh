@@ -46,7 +46,8 @@ __host__ __device__ static inline int align_up(int x, int a) { return (x + a - 1
 
 template <typename PT>
 struct Env {
-    unsigned char* base;
+    unsigned char* base;               // the warp's shared-memory region: scratch arrays (L->sm_*)
+    unsigned char* rec;                // the staged record (L->off_*): == base, or the second record buffer of a double-buffered kernel
     const DevLayout* L;
     const double* sz64;                // code -> k/100.0   (== np.around(u, 2), env.py:212-219)
     const float* sz32;                 // code -> (float)(k/100.0)   (env.py:296)
@@ -57,16 +58,16 @@ struct Env {
     int P, V, lane;
     int tune;                          // StepParams::use_bulk (team-mode experiment bits); only read by the team-mode kernel
 
-    __device__ __forceinline__ double* cpu() const { return reinterpret_cast<double*>(VMGYM_SMEM(base)); }           // env.py:190
-    __device__ __forceinline__ double* mem() const { return reinterpret_cast<double*>(VMGYM_SMEM(base) + L->off_mem); }
-    __device__ __forceinline__ uint16_t* rem() const { return reinterpret_cast<uint16_t*>(VMGYM_SMEM(base) + L->off_rem); }
-    __device__ __forceinline__ PT* place() const { return reinterpret_cast<PT*>(VMGYM_SMEM(base) + L->off_place); }
-    __device__ __forceinline__ uint8_t* cpuc() const { return VMGYM_SMEM(base) + L->off_cpuc; }                      // bit 7 = suspended
-    __device__ __forceinline__ uint8_t* memc() const { return VMGYM_SMEM(base) + L->off_memc; }
+    __device__ __forceinline__ double* cpu() const { return reinterpret_cast<double*>(VMGYM_SMEM(rec)); }           // env.py:190
+    __device__ __forceinline__ double* mem() const { return reinterpret_cast<double*>(VMGYM_SMEM(rec) + L->off_mem); }
+    __device__ __forceinline__ uint16_t* rem() const { return reinterpret_cast<uint16_t*>(VMGYM_SMEM(rec) + L->off_rem); }
+    __device__ __forceinline__ PT* place() const { return reinterpret_cast<PT*>(VMGYM_SMEM(rec) + L->off_place); }
+    __device__ __forceinline__ uint8_t* cpuc() const { return VMGYM_SMEM(rec) + L->off_cpuc; }                      // bit 7 = suspended
+    __device__ __forceinline__ uint8_t* memc() const { return VMGYM_SMEM(rec) + L->off_memc; }
     // capacity codes of every PM in the agents' float32 view, kept consistent with cpu()/mem() by every update:
     // rcap[p] = kc | km << 8 with kc = max{k : (float)cpu[p] + sz32[k] <= 1.0f} (likewise km for memory)
-    __device__ __forceinline__ uint16_t* rcap() const { return reinterpret_cast<uint16_t*>(VMGYM_SMEM(base) + L->off_cap); }
-    __device__ __forceinline__ vmgym_env_scalars* sc() const { return reinterpret_cast<vmgym_env_scalars*>(VMGYM_SMEM(base) + L->off_scal); }
+    __device__ __forceinline__ uint16_t* rcap() const { return reinterpret_cast<uint16_t*>(VMGYM_SMEM(rec) + L->off_cap); }
+    __device__ __forceinline__ vmgym_env_scalars* sc() const { return reinterpret_cast<vmgym_env_scalars*>(VMGYM_SMEM(rec) + L->off_scal); }
     // scratch (not part of the record)
     __device__ __forceinline__ float* cpu32() const { return reinterpret_cast<float*>(VMGYM_SMEM(base) + L->sm_cpu32); }  // agents' fp32 view
     __device__ __forceinline__ float* mem32() const { return reinterpret_cast<float*>(VMGYM_SMEM(base) + L->sm_mem32); }
@@ -1207,7 +1208,10 @@ __host__ __device__ __forceinline__ int dtype_bytes(int dtype) { return dtype ==
 constexpr int make_spec(int agent, int tiebreak, int reward, int mode) { return agent | (tiebreak << 4) | (reward << 8) | (mode << 12); }
 
 // TM: team mode (one env per CTA, warp 0 + helper warps; see "Team mode" above) — instantiated for u16 placements.
-template <typename PT, int PC, int VC, int SPEC, bool TM = false>
+// DB: double-buffered records for launches in which a warp steps several envs one after the other (grid capped at the
+// resident CTAs): the next env's record is fetched (bulk-async, second buffer + second mbarrier) while the current one is
+// stepped, and the write-back of the previous one drains in the background.  Needs bulk loads and stores (use_bulk bits 0, 1).
+template <typename PT, int PC, int VC, int SPEC, bool TM = false, bool DB = false>
 __global__ void __launch_bounds__(TM ? 256 : 128, TM ? 3 : 7) step_kernel(const __grid_constant__ StepParams p)
 {
     constexpr int REWARD_CT = SPEC >= 0 ? ((SPEC >> 8) & 0xf) : 0;
@@ -1225,9 +1229,10 @@ __global__ void __launch_bounds__(TM ? 256 : 128, TM ? 3 : 7) step_kernel(const 
     const int lane = threadIdx.x & 31, warp = TM ? 0 : (int)(threadIdx.x >> 5), wpc = TM ? 1 : (int)(blockDim.x >> 5);
     const bool helper = TM && threadIdx.x >= 32;
     const int nth = TM ? (int)blockDim.x : 32;
-    unsigned char* base = smem + L.sm_tables + (size_t)warp * L.sm_stride;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(base + L.sm_bar);
-    const bool BULK = (p.use_bulk & 1) != 0, BULK_ST = (p.use_bulk & 2) != 0;
+    const int wstride = DB ? align_up(L.sm_stride + L.rec_bytes, 128) : L.sm_stride;     // DB: + the second record buffer
+    unsigned char* base = smem + L.sm_tables + (size_t)warp * wstride;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(base + L.sm_bar);                        // DB: bar[1] belongs to the second buffer
+    const bool BULK = DB || (p.use_bulk & 1) != 0, BULK_ST = DB || (p.use_bulk & 2) != 0;
     const long long stride = (long long)gridDim.x * wpc;
     const long long env0 = (long long)blockIdx.x * wpc + warp;
     // Programmatic dependent launch (use_bulk bit 2): let the NEXT kernel of the stream start launching right away (its CTAs
@@ -1239,6 +1244,7 @@ __global__ void __launch_bounds__(TM ? 256 : 128, TM ? 3 : 7) step_kernel(const 
     // written by the previous grid: the load waits for it, after the tables.)
     if (BULK && lane == 0 && !helper) {
         mbar_init(bar, 1);
+        if (DB) mbar_init(bar + 1, 1);
         fence_barrier_init();
         if (!PDL && env0 < p.n_envs) {
             mbar_arrive_expect_tx(bar, (uint32_t)L.rec_bytes);
@@ -1275,7 +1281,7 @@ __global__ void __launch_bounds__(TM ? 256 : 128, TM ? 3 : 7) step_kernel(const 
     }
 
     Env<PT> e;
-    e.base = base; e.L = &p.L; e.sz64 = sz64; e.sz32 = sz32; e.P = cP; e.V = cV; e.lane = lane; e.tune = p.use_bulk;
+    e.base = base; e.rec = base; e.L = &p.L; e.sz64 = sz64; e.sz32 = sz32; e.P = cP; e.V = cV; e.lane = lane; e.tune = p.use_bulk;
     e.arr_cdf = p.tr.d_arrival_cdf;
     e.arr_cdf32 = arr_in_smem ? arr_cdf_s : nullptr;
     e.svc_cdf = p.tr.d_service_cdf;                  // searched from a 64-way bracket, on admissions only
@@ -1289,10 +1295,23 @@ __global__ void __launch_bounds__(TM ? 256 : 128, TM ? 3 : 7) step_kernel(const 
         }
         return;
     }
+    uint32_t phase1 = 0;
+    int cur = 0;                             // DB: which record buffer holds the current env
     for (long long env = env0; env < p.n_envs; env += stride) {
         unsigned char* grec = p.state + env * (long long)L.rec_bytes;
         // ---- stage the record into shared memory ----
-        if (BULK) {
+        if (DB) {
+            unsigned char* other = cur ? base : base + L.sm_stride;
+            e.rec = cur ? base + L.sm_stride : base;
+            const long long nxt = env + stride;
+            if (lane == 0 && nxt < p.n_envs) {
+                bulk_wait_read0();            // the other buffer's write-back (previous env) has left shared memory
+                mbar_arrive_expect_tx(bar + (cur ^ 1), (uint32_t)L.rec_bytes);
+                bulk_g2s(other, p.state + nxt * (long long)L.rec_bytes, (uint32_t)L.rec_bytes, bar + (cur ^ 1));
+            }
+            if (cur) { mbar_wait(bar + 1, phase1); phase1 ^= 1; }
+            else { mbar_wait(bar, phase); phase ^= 1; }
+        } else if (BULK) {
             if (lane == 0 && env != env0) {
                 mbar_arrive_expect_tx(bar, (uint32_t)L.rec_bytes);
                 bulk_g2s(base, grec, (uint32_t)L.rec_bytes, bar);
@@ -1410,7 +1429,16 @@ __global__ void __launch_bounds__(TM ? 256 : 128, TM ? 3 : 7) step_kernel(const 
 
         if (TM) team_run(e, TEAM_END, nth);       // helpers move on to the next record of this CTA
         // ---- write the record back ----
-        if (BULK_ST) {
+        if (DB) {
+            fence_proxy_async();          // generic-proxy writes to smem -> visible to the async proxy
+            __syncwarp();
+            if (lane == 0) {
+                bulk_s2g(grec, e.rec, (uint32_t)L.rec_bytes);
+                bulk_commit();            // drained before this buffer is loaded again (wait_group.read in front of the prefetch)
+            }
+            __syncwarp();
+            cur ^= 1;
+        } else if (BULK_ST) {
             fence_proxy_async();          // generic-proxy writes to smem -> visible to the async proxy
             __syncwarp();
             if (lane == 0) {
@@ -1424,6 +1452,7 @@ __global__ void __launch_bounds__(TM ? 256 : 128, TM ? 3 : 7) step_kernel(const 
             if (BULK) fence_proxy_async();        // generic-proxy reads of smem before the next record's async-proxy write
         }
     }
+    if (DB && lane == 0) bulk_wait_read0();       // shared memory must outlive the last write-backs
 }
 
 
@@ -1608,7 +1637,7 @@ __global__ void act_kernel(DevLayout Lg, int agent, int tiebreak, const float* o
     }
     __syncwarp();
     Env<PT> e;
-    e.base = base; e.L = &L; e.sz64 = nullptr; e.sz32 = sz32; e.arr_cdf = nullptr; e.arr_cdf32 = nullptr; e.svc_cdf = nullptr; e.svc_bracket = nullptr;
+    e.base = base; e.rec = base; e.L = &L; e.sz64 = nullptr; e.sz32 = sz32; e.arr_cdf = nullptr; e.arr_cdf32 = nullptr; e.svc_cdf = nullptr; e.svc_bracket = nullptr;
     e.P = P; e.V = V; e.lane = lane;
     AgentView<PT> av;
     av.place = place; av.cc = cc; av.mc = mc; av.c32 = row + V; av.m32 = row + 2 * V; av.sz32 = sz32;
