@@ -424,7 +424,7 @@ def gpu_arm(args):
                     "steps_per_launch": chunk, "note": "same fused kernel, env state resident in shared memory across steps"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_TRAFFIC_PER_LAUNCH if E == 4096 else None,
-                     "traffic_note": "profiles/r1_step_kernel_full.md: dram__bytes_read 14.23 MB + dram__bytes_write 0.02 MB per "
+                     "traffic_note": "profiles/r1d_step_kernel_quiet.md (final kernel) and r1_step_kernel_full.md (departure wave): dram__bytes_read 14.22-14.23 MB + dram__bytes_write < 0.03 MB per "
                                      "launch; what the kernel stores (14 MB of records + the observation rows of the envs that changed, at most 18 MB) stays in the "
                                      "126 MB L2 until later launches evict it; `achieved` counts the algorithmic bytes of every env-step incl. its "
                                      "observation row, also for envs whose unchanged row is kept instead of re-stored",
