@@ -457,8 +457,8 @@ def gpu_arm(args):
                                                    "VM, ~900 sequential evaluations per env and step at this load; each = 2 TF32 GEMMs + "
                                                    "the fused vmgym_drlvmp_iter kernel, 8 per CUDA-graph replay) + env.step"},
                         "config": "synthetic 1000 PMs / 3000 VM slots, highuniform sizes, arrival 1.6 (100 % load), fused best-fit act+step, "
-                                  "one launch per step, team-mode kernel (one env per CTA: warp 0 steps, 7 helper warps join the "
-                                  "slot / PM loops; 3 CTAs per SM by shared memory, so 1024 envs take 3 rounds)"}
+                                  "one launch per step, team-mode kernel (one env per CTA: warp 0 steps, the helper warps join the "
+                                  "slot / PM loops; 4 CTAs of 6 warps per SM by shared memory and registers, so 1024 envs take 2 rounds)"}
     if s10:
         B10 = algorithmic_bytes(10, 30)
         out["s10"] = {"value": world * s10["envs_per_gpu"] / (s10["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": s10["ms_per_step"],

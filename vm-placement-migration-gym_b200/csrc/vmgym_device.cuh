@@ -21,6 +21,7 @@ struct DevLayout {
     int off_mem, off_rem, off_place, off_cpuc, off_memc, off_cap, off_scal, rec_bytes;
     // per-warp shared memory (byte offsets from the warp's base)
     int sm_cpu32, sm_mem32, sm_act, sm_tmp, sm_fit, sm_prop, sm_stats, sm_bar, sm_team, sm_stride;
+    int sm_kl;       // scratch of the `kl` reward (compacted size codes of the existing VMs): sm_tmp, or the agent's float32 view (dead by then)
     // CTA-wide shared memory
     int sm_tables;   // bytes reserved in front of the per-warp regions
     int svc_cdf_smem;  // service inverse-CDF entries kept in shared memory (0 = read the global table)

@@ -30,6 +30,28 @@ static int fail(int code, const char* fmt, const char* detail = "")
     return code;
 }
 
+// per-env shared-memory scratch behind the record.  `tmp` holds the numpy-introsort keys / permutation (6 P bytes, inside
+// agent_act) or the `kl` reward's compacted size codes (2 V bytes, inside env_step).  small_tmp (team-mode launches that do not
+// sort): 64 bytes for the team's scan results, and the `kl` compaction moves onto the agent's float32 view, which is dead outside
+// agent_act — at 1000 PMs that is the 6 KB between three and four envs per SM.
+static void layout_scratch(DevLayout& l, int pb, bool small_tmp)
+{
+    l.sm_cpu32 = l.rec_bytes;
+    l.sm_mem32 = l.sm_cpu32 + align_up(4 * l.P, 16);
+    l.sm_act = l.sm_mem32 + align_up(4 * l.P, 16);
+    l.sm_tmp = l.sm_act + 2 * l.Vp;
+    const int tmp_bytes = small_tmp ? 64 : align_up((2 * l.Vp > 6 * l.Pp) ? 2 * l.Vp : 6 * l.Pp, 16);
+    l.sm_kl = small_tmp ? l.sm_cpu32 : l.sm_tmp;
+    l.sm_fit = l.sm_tmp + tmp_bytes;                       // u32 fitm[128] | u16 cap[Pp]
+    l.sm_prop = l.sm_fit + 512 + align_up(2 * l.Pp, 16);      // u32 prop[ceil(Vp/32)]: slots whose action differs
+    l.sm_stats = l.sm_prop + align_up(4 * ((l.Vp + 31) / 32), 16);   // f64[VMGYM_STATS] eval-summary sums of the launch
+    l.sm_bar = l.sm_stats + 8 * VMGYM_STATS;
+    // team mode (u16 placements = large shapes, one env per CTA): command words + three slot-chunk bitmaps (departures, candidates, empty slots)
+    l.sm_team = l.sm_bar + 16;
+    const int team_bytes = pb == 2 ? 16 + 3 * align_up(4 * ((l.Vp + 31) / 32), 16) : 0;
+    l.sm_stride = align_up(l.sm_team + team_bytes, 128);
+}
+
 static int make_layout(const vmgym_config* c, DevLayout* L, vmgym_layout* pub)
 {
     if (!c) return fail(VMGYM_EINVAL, "null config");
@@ -48,19 +70,7 @@ static int make_layout(const vmgym_config* c, DevLayout* L, vmgym_layout* pub)
     l.off_cap = l.off_memc + l.Vp;
     l.off_scal = l.off_cap + align_up(2 * l.Pp, 16);
     l.rec_bytes = align_up(l.off_scal + (int)sizeof(vmgym_env_scalars) + 16, 128);   // + 16 B: parked Philox words (arrival draws)
-    l.sm_cpu32 = l.rec_bytes;
-    l.sm_mem32 = l.sm_cpu32 + align_up(4 * l.P, 16);
-    l.sm_act = l.sm_mem32 + align_up(4 * l.P, 16);
-    l.sm_tmp = l.sm_act + 2 * l.Vp;
-    const int tmp_bytes = align_up((2 * l.Vp > 6 * l.Pp) ? 2 * l.Vp : 6 * l.Pp, 16);
-    l.sm_fit = l.sm_tmp + tmp_bytes;                       // u32 fitm[128] | u16 cap[Pp]
-    l.sm_prop = l.sm_fit + 512 + align_up(2 * l.Pp, 16);      // u32 prop[ceil(Vp/32)]: slots whose action differs
-    l.sm_stats = l.sm_prop + align_up(4 * ((l.Vp + 31) / 32), 16);   // f64[VMGYM_STATS] eval-summary sums of the launch
-    l.sm_bar = l.sm_stats + 8 * VMGYM_STATS;
-    // team mode (u16 placements = large shapes, one env per CTA): command words + three slot-chunk bitmaps (departures, candidates, empty slots)
-    l.sm_team = l.sm_bar + 16;
-    const int team_bytes = pb == 2 ? 16 + 3 * align_up(4 * ((l.Vp + 31) / 32), 16) : 0;
-    l.sm_stride = align_up(l.sm_team + team_bytes, 128);
+    layout_scratch(l, pb, false);
     l.svc_cdf_smem = 0;                                    // service table stays in global memory (used on admissions only)
     l.sm_tables = align_up(SIZE_TABLE * 8 + SIZE_TABLE * 4 + ARR_CDF_SMEM * 8 + l.svc_cdf_smem * 8 + (SVC_BRACKETS + 1) * 2, 128);
     if (L) *L = l;
@@ -129,10 +139,17 @@ template <typename PT>
 static int launch_step(StepParams& sp, cudaStream_t st)
 {
     sp.use_bulk = g_use_bulk;
-    const DevLayout& L = sp.L;
     // u16 placements = large shapes: team mode, one env per CTA with `w` warps (warp 0 steps, the others join the bulk phases)
     static const bool team_ok = getenv("VMGYM_NO_TEAM") == nullptr;                        // A/B switch for experiments
     const bool team = team_ok && sizeof(PT) == 2;
+    if (team) {
+        // launches that never sort (stable ties / first-fit / external actions) do without the sort scratch
+        const bool sorts = sp.agent == VMGYM_AGENT_BESTFIT && sp.tiebreak == VMGYM_TIE_NUMPY_INTROSORT;
+        const bool kl_fits = 2 * align_up(sp.L.V, 16) <= sp.L.sm_act - sp.L.sm_cpu32;
+        static const bool small_ok = getenv("VMGYM_TEAM_FULL_SCRATCH") == nullptr;          // A/B switch for experiments
+        if (small_ok && !sorts && kl_fits) layout_scratch(sp.L, 2, true);
+    }
+    const DevLayout& L = sp.L;
     int w;
     if (team) {
         const long long one = (long long)L.sm_tables + L.sm_stride + 1024;                  // + the per-CTA reservation
@@ -140,7 +157,13 @@ static int launch_step(StepParams& sp, cudaStream_t st)
         const long long need = (sp.n_envs + sm_count() - 1) / sm_count();
         if (per_sm > need) per_sm = need;
         if (per_sm < 1) per_sm = 1;
-        w = g_warps_per_cta > 0 ? g_warps_per_cta : (int)(48 / per_sm);
+        static int team_regs = 0;
+        if (team_regs == 0) {
+            cudaFuncAttributes fa;
+            team_regs = cudaFuncGetAttributes(&fa, step_kernel<PT, 0, 0, -1, (sizeof(PT) == 2)>) == cudaSuccess && fa.numRegs > 0 ? fa.numRegs : 80;
+        }
+        const long long by_regs = 65536 / (per_sm * 32 * team_regs);                        // warps per CTA the register file allows
+        w = g_warps_per_cta > 0 ? g_warps_per_cta : (int)(48 / per_sm < by_regs ? 48 / per_sm : by_regs);
         w = w < 1 ? 1 : (w > 8 ? 8 : w);                                                    // compiled for <= 256 threads
     } else {
         w = pick_warps(sp.n_envs, L.sm_stride, L.sm_tables);

@@ -640,8 +640,8 @@ __device__ __noinline__ double reward_kl_env(const Env<PT> e, int arrived, int c
 {
     const int P = e.P, V = e.V, lane = e.lane;
     const PT* place = e.place();
-    uint8_t* ex_cc = e.tmp();
-    uint8_t* ex_mc = e.tmp() + ((V + 15) & ~15);
+    uint8_t* ex_cc = VMGYM_SMEM(e.base) + e.L->sm_kl;
+    uint8_t* ex_mc = ex_cc + ((V + 15) & ~15);
     int pos0 = 0;
     for (int c0 = 0; c0 < V; c0 += 32) {
         const int v = c0 + lane;
