@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define VMGYM_ABI_VERSION 4
+#define VMGYM_ABI_VERSION 5
 
 enum vmgym_status {
     VMGYM_OK = 0,
