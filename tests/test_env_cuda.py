@@ -483,16 +483,17 @@ def test_per_vm_statistics_match_reference_record(name):
         assert float(np.round(s[k][0], 3)) == summary[k], k        # np.round as in record.py:118-125
 
 
-def test_per_vm_statistics_batch_vs_oracle_record():
-    """Philox traces, 6 envs, random suspend / re-place actions mixed into first-fit for 700 steps (no episode end: the
-    statistics include the VMs still in their slots) == the oracle's Record restatement on the same traces."""
+@pytest.mark.parametrize("P,V,rate,N,T", [(10, 30, 0.45, 6, 700), (260, 600, 9.0, 3, 260)])
+def test_per_vm_statistics_batch_vs_oracle_record(P, V, rate, N, T):
+    """Philox traces, random suspend / re-place actions mixed into first-fit (no episode end: the statistics include the
+    VMs still in their slots) == the oracle's Record restatement on the same traces.  Second case: u16 placements, i.e. the
+    team-mode kernel with per-VM clocks."""
     torch = _torch()
     import vmoracle as vo
     from vmgym import VecVmEnv
     from vmgym.agents import FirstFitAgent
-    kw = dict(pms=10, vms=30, arrival_rate=0.45, service_length=35, training_steps=5000, eval_steps=5000, reward_function="wr",
+    kw = dict(pms=P, vms=V, arrival_rate=rate, service_length=35, training_steps=5000, eval_steps=5000, reward_function="wr",
               allow_null_action=True)
-    N, T = 6, 700
     vec = VecVmEnv(_cfg(**kw), N, rng="philox").enable_vm_stats()
     vec.reset(seed=100 + np.arange(N))
     agent = FirstFitAgent(vec)
@@ -501,8 +502,8 @@ def test_per_vm_statistics_batch_vs_oracle_record():
     oracles = []
     for i in range(N):
         o = vo.OracleVmEnv(vo.OracleConfig(**kw))
-        o.enable_record(T)
-        o.reset(trace=vo.philox_trace(100 + i, T + 8, 4 * T + 64, ka, ta, ks, ts, lo, hi))
+        o.enable_record(T, max_arrivals=4 * T + V + int(2 * rate * T))
+        o.reset(trace=vo.philox_trace(100 + i, T + 8, 4 * T + 64 + int(2 * rate * T), ka, ta, ks, ts, lo, hi))
         oracles.append(o)
     obs = vec.observe()
     for t in range(T):
