@@ -330,3 +330,29 @@ def test_learned_agents_test_returns_a_record(which, tmp_path):
     assert s["total served VMs"] == int(c["served_requests"][0]) and s["total suspend actions"] == int(c["suspend_actions"][0])
     assert json.load(open(out))["summary"] == s
     agent.set_log("job", None); agent.end_log()
+
+
+@pytest.mark.gpu
+def test_out_linear_backward_matches_torch_linear():
+    """The update's output layer (bias gradient folded into the weight-gradient GEMM) == F.linear's autograd, fp32 matmuls."""
+    import torch
+    import torch.nn.functional as F
+    from vmgym.ppo import _OutLinear
+    prev = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision("highest")
+    try:
+        g = torch.Generator(device="cuda").manual_seed(5)
+        h = torch.randn(257, 48, device="cuda", generator=g, requires_grad=True)
+        w = torch.randn(1234, 48, device="cuda", generator=g, requires_grad=True)
+        b = torch.randn(1234, device="cuda", generator=g, requires_grad=True)
+        up = torch.randn(257, 1234, device="cuda", generator=g)
+        out1 = _OutLinear.apply(h, w, b)
+        g1 = torch.autograd.grad((out1 * up).sum(), (h, w, b))
+        out2 = F.linear(h, w, b)
+        g2 = torch.autograd.grad((out2 * up).sum(), (h, w, b))
+        assert torch.equal(out1, out2)
+        for a, c in zip(g1, g2):
+            assert a.shape == c.shape and a.is_contiguous()
+            assert torch.allclose(a, c, rtol=1e-4, atol=1e-4)          # summation order only
+    finally:
+        torch.set_float32_matmul_precision(prev)
