@@ -208,8 +208,31 @@ __device__ __forceinline__ void team_phase(const Env<PT>& e, int cmd, int tid, i
         const uint8_t* memc = e.memc();
         const double* cpu = e.cpu();
         const double* mem = e.mem();
-        for (int v = tid; v < V; v += nth) { o[v] = (float)place[v]; o[V + v] = e.sz32[cpuc[v] & 0x7f]; o[2 * V + v] = e.sz32[memc[v]]; }
-        for (int q = tid; q < P; q += nth) { o[3 * V + q] = (float)cpu[q]; o[3 * V + P + q] = (float)mem[q]; }
+        if (sizeof(PT) == 2 && (V & 3) == 0 && (P & 3) == 0) {
+            // four slots / PMs per thread and 128-bit stores: the row and its five segments are 16-byte aligned
+            float4* o4 = reinterpret_cast<float4*>(o);
+            const uint2* pl4 = reinterpret_cast<const uint2*>(place);          // 4 x u16 placements
+            const uint32_t* cc4 = reinterpret_cast<const uint32_t*>(cpuc);
+            const uint32_t* mc4 = reinterpret_cast<const uint32_t*>(memc);
+            const int vg = V >> 2, pg = P >> 2;
+            for (int g = tid; g < vg; g += nth) {
+                const uint2 a = pl4[g];
+                const uint32_t c = cc4[g] & 0x7f7f7f7fu, m = mc4[g];
+                o4[g] = make_float4((float)(a.x & 0xffffu), (float)(a.x >> 16), (float)(a.y & 0xffffu), (float)(a.y >> 16));
+                o4[vg + g] = make_float4(e.sz32[c & 0xff], e.sz32[(c >> 8) & 0xff], e.sz32[(c >> 16) & 0xff], e.sz32[c >> 24]);
+                o4[2 * vg + g] = make_float4(e.sz32[m & 0xff], e.sz32[(m >> 8) & 0xff], e.sz32[(m >> 16) & 0xff], e.sz32[m >> 24]);
+            }
+            const double2* c2 = reinterpret_cast<const double2*>(cpu);
+            const double2* m2 = reinterpret_cast<const double2*>(mem);
+            for (int g = tid; g < pg; g += nth) {
+                const double2 a = c2[2 * g], b = c2[2 * g + 1], c = m2[2 * g], d = m2[2 * g + 1];
+                o4[3 * vg + g] = make_float4((float)a.x, (float)a.y, (float)b.x, (float)b.y);
+                o4[3 * vg + pg + g] = make_float4((float)c.x, (float)c.y, (float)d.x, (float)d.y);
+            }
+        } else {
+            for (int v = tid; v < V; v += nth) { o[v] = (float)place[v]; o[V + v] = e.sz32[cpuc[v] & 0x7f]; o[2 * V + v] = e.sz32[memc[v]]; }
+            for (int q = tid; q < P; q += nth) { o[3 * V + q] = (float)cpu[q]; o[3 * V + P + q] = (float)mem[q]; }
+        }
     } else if (cmd == TEAM_PREP) {
         // the agent's float32 view of the PM loads (env.py:296), its local copy of the capacity codes, no proposals yet
         const double* cpu = e.cpu();
