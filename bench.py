@@ -455,7 +455,7 @@ def gpu_arm(args):
                         "drlvmp_rollout": {"value": world * s1000["envs_per_gpu"] / s1000["drlvmp_s_per_step"], "unit": UNIT,
                                            "note": "DRLVMPAgent.act (H=512 dueling C51 net, one network evaluation + heuristic per waiting "
                                                    "VM, ~900 sequential evaluations per env and step at this load; each = 2 TF32 GEMMs + "
-                                                   "the fused vmgym_drlvmp_iter kernel, 8 per CUDA-graph replay) + env.step"},
+                                                   "the fused vmgym_drlvmp_iter kernel, 32 per CUDA-graph replay) + env.step"},
                         "config": "synthetic 1000 PMs / 3000 VM slots, highuniform sizes, arrival 1.6 (100 % load), fused best-fit act+step, "
                                   "one launch per step, team-mode kernel (one env per CTA: warp 0 steps, the helper warps join the "
                                   "slot / PM loops; 4 CTAs of 6 warps per SM by shared memory and registers, so 1024 envs take 2 rounds)"}

@@ -291,7 +291,7 @@ class DRLVMPAgent(AgentBase):
                                                 st["w_cols"].data_ptr(), pre.data_ptr(), feat.data_ptr(), n, stream), "vmgym_drlvmp_iter")
 
         # several iterations per captured graph (fewer replays); iterations past an env's last waiting VM are no-ops
-        unroll = next(u for u in (8, 4, 2, 1) if refresh % u == 0)
+        unroll = next(u for u in (32, 16, 8, 4, 2, 1) if refresh % u == 0)       # 32: ~30 replays per act() at 1000 PMs (host-launch bound otherwise)
         if st["graph_fused"] is None:
             st["graph_fused"] = {}
         if unroll not in st["graph_fused"] and n_iter > 0:
