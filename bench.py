@@ -180,7 +180,8 @@ def gpu_arm(args):
         with torch.cuda.graph(timed_graph):
             rotate(K, start=W)                          # exactly K launches of the fused step kernel
     rotate(W)                                           # W untimed warm-up steps of exactly the timed call
-    barrier()
+    timed_graph.replay()                                # + one untimed replay of the timed graph itself: a graph's first launch
+    barrier()                                           #   uploads it to the device (~40 us, which a small K would carry)
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -406,7 +407,7 @@ def gpu_arm(args):
                    "l2": f"inputs larger than L2: launches rotate over {NB} independent {E}-env batches "
                          f"({NB} x {(2 * 3456 * E + 4 * D * E) / 1e6:.0f} MB touched between two visits of a batch, L2 = 126 MB)",
                    "phase_sampling": f"batch b warmed up to phase b*{PERIOD}/{NB} of the service period (departure waves)",
-                   "timing": "one CUDA-event pair around a CUDA graph of exactly K step-kernel launches",
+                   "timing": "one CUDA-event pair around a CUDA graph of exactly K step-kernel launches (second replay of the graph: the first, untimed one uploads it)",
                    "rng": "philox", "tiebreak": "stable",
                    "obs_written": "every step into the env's persistent observation buffer; rows of envs whose state did not change are kept, not re-stored",
                    "state_types": "f64 PM accumulators, u8 placements / size codes, u16 runtimes, f32 observation"},
