@@ -13,7 +13,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def fixture_names():
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if not n.startswith(("drlvmp", "record"))]      # own layouts (make_golden_drlvmp.py, make_golden_record.py)
+    return [n for n in names if not n.startswith(("drlvmp", "record", "info", "ppo"))]      # own layouts (make_golden_drlvmp.py, make_golden_record.py)
 
 
 def load(name):

@@ -382,7 +382,7 @@ def test_full_size_invariants(shape, N, T):
     assert np.allclose(cpu, onehot_cpu[:, :P], atol=1e-9) and np.allclose(mem, onehot_mem[:, :P], atol=1e-9)
     assert cpu.max() <= 1.0 and mem.max() <= 1.0 and cpu.min() >= 0.0
     # empty slots carry no size / runtime; running and waiting VMs have a positive remaining runtime
-    rem = vec.vm_remaining_runtime.cpu().numpy().astype(np.int64) & 0xFFFF
+    rem = vec.vm_remaining_runtime.cpu().numpy().astype(np.int64)
     assert np.all(cc[place == P + 1] == 0) and np.all(rem[place == P + 1] == 0)
     assert np.all(rem[place <= P] > 0) and np.all(cc[place <= P] >= (25 if kw.get("sequence") == "highuniform" else 10))
     # the observation is the float32 image of the state

@@ -233,3 +233,28 @@ def test_oracle_record_on_the_main_py_episode():
     assert int(st["served"]) == s["total served VMs"] and int(st["total_requests"]) == s["total requests"]
     assert int(st["place"]) == s["total place actions"] and float(np.round(st["return"], 3)) == s["total rewards"]
     assert float(np.round(st["drop_rate_mean"], 3)) == s["drop rate"] and float(np.round(st["cpu_mean"], 3)) == s["cpu mean"]
+
+
+@pytest.mark.parametrize("name", ["info_busy_suspend", "info_p37_v70"])
+def test_oracle_arrival_log_matches_reference_vm_arrival_steps(name):
+    """env.py:205,293: the oracle's arrival log rebuilt into per-slot lists == the reference env's vm_arrival_steps
+    (fixture from tests/golden/make_golden_info.py)."""
+    import json
+    z = np.load(os.path.join(gu.GOLDEN_DIR, "info.npz"))
+    fx = {k[len(name) + 1:]: z[k] for k in z.files if k.startswith(name + ".")}
+    cfg = json.loads(str(fx["cfg_json"]))
+    T, V = fx["actions"].shape
+    env = vo.OracleVmEnv(vo.OracleConfig(**cfg), trace_steps=T + 8, trace_adm=4096)
+    env.eval()
+    env.enable_record(T + 8)
+    env.reset(seed=cfg["seed"])
+    for t in range(T):
+        env.step(fx["actions"][t].astype(np.int64))
+    import ctypes as C
+    n_steps, n_arr = C.c_int64(), C.c_int64()
+    vo.lib().vmo_record_counts(env._h, C.byref(n_steps), C.byref(n_arr))
+    got = [[] for _ in range(V)]
+    for slot, step in env._arr_log[:n_arr.value]:
+        got[int(slot)].append(int(step))
+    off = fx["arrival_off"]
+    assert got == [fx["arrival_flat"][off[v]:off[v + 1]].tolist() for v in range(V)]

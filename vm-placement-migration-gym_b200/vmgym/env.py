@@ -33,7 +33,16 @@ class VmEnv:
         self.WAIT_STATUS, self.NULL_STATUS = config.pms, config.pms + 1
         self.vec = VecVmEnv(config, 1, device=device, rng=rng, seeds=[config.seed], trace_steps=trace_steps,
                             max_admissions=max_admissions, tiebreak=tiebreak)
+        # the per-slot arrival clocks of the device env feed vm_arrival_steps / vm_planned_runtime (env.py:203,205,289,293);
+        # nothing has stepped yet, so the freshly zeroed buffers are consistent with the reset state
+        self.vec.enable_vm_stats()
+        self._reset_host_logs()
         self.last_validity = self.last_action = self.last_reward = None
+
+    def _reset_host_logs(self):
+        V = self.config.vms
+        self.vm_planned_runtime = np.zeros(V, dtype=int)                     # env.py:203
+        self.vm_arrival_steps = [[] for _ in range(V)]                       # env.py:205
 
     @property
     def eval_mode(self):
@@ -47,19 +56,38 @@ class VmEnv:
 
     def reset(self, seed=None, options=None):
         obs, _ = self.vec.reset(None if seed is None else [int(seed)])
+        self._reset_host_logs()
         return obs[0].cpu().numpy(), self._get_info()
 
     def step(self, action):
         action = np.ascontiguousarray(action, dtype=np.int64).reshape(1, -1)
-        obs, reward, term, trunc, info = self.vec.step(torch.from_numpy(action).to(self.vec.device))
-        out = torch.cat([obs[0].double(), reward[:1], term[:1].double()]).cpu().numpy()   # one D2H (f32 -> f64 is exact)
-        valid = self.vec.valid[0].cpu().numpy().astype(np.int64)
+        vec = self.vec
+        obs, reward, term, trunc, info = vec.step(torch.from_numpy(action).to(vec.device))
+        D, V, P = vec.obs_dim, vec.V, vec.P
+        # one D2H (every value is exactly representable in float64): observation, reward, done, valid flags, the slots'
+        # arrival clocks, the step counter and the remaining runtimes (u16 stored in an int16 view)
+        out = torch.cat([obs[0].double(), reward[:1], term[:1].double(), vec.valid[0].double(), vec._vm_slots[0, :, 0].double(),
+                         vec._scalars_i32[0, :1].double(), vec.vm_remaining_runtime[0].double()]).cpu().numpy()
+        obs_np, rew, done = out[:D].astype(np.float32), float(out[D]), bool(out[D + 1])
+        valid = out[D + 2:D + 2 + V].astype(np.int64)
+        arrived_at = out[D + 2 + V:D + 2 + 2 * V].astype(np.int64)
+        t_exec = int(out[D + 2 + 2 * V]) - 1                       # the step just executed (the kernel has advanced the clock)
+        rem = out[D + 3 + 2 * V:D + 3 + 3 * V].astype(np.int64)
+        place = obs_np[:V].astype(np.int64)
+        # env.py:288-293: slots admitted in this step start with remaining == planned and log their arrival at step + 1;
+        # env.py:262: a departed slot's planned runtime is zeroed
+        for v in np.nonzero(arrived_at == t_exec)[0]:
+            self.vm_planned_runtime[v] = rem[v]
+            self.vm_arrival_steps[v].append(t_exec + 1)
+        self.vm_planned_runtime[place == P + 1] = 0
         info = {"action": action[0].copy(), "valid": valid}
         if self.eval_mode:
-            info = self._get_info() | info
+            full = self._get_info()
+            full["timestep"] -= 1                                   # env.py:165 builds info before `timestep += 1` (:101)
+            info = full | info
             self.last_validity, self.last_action = valid, action[0]
-            self.last_reward = np.round(out[-2], 3)
-        return out[:-2].astype(np.float32), float(out[-2]), bool(out[-1]), False, info
+            self.last_reward = np.round(rew, 3)
+        return obs_np, rew, done, False, info
 
     def get_invalid_action_mask(self, masked: bool = True):
         return self.vec.get_invalid_action_mask(masked)[0].cpu().numpy()
@@ -74,7 +102,8 @@ class VmEnv:
         return {"waiting_ratio": s["waiting_ratio"], "served_requests": s["served_requests"],
                 "suspend_actions": s["suspend_actions"], "place_actions": s["place_actions"],
                 "dropped_requests": s["dropped_requests"], "total_requests": s["total_requests"],
-                "timestep": s["timestep"], "vm_placement": s["vm_placement"], "cpu": s["cpu"], "memory": s["memory"],
+                "timestep": s["timestep"], "vm_arrival_steps": self.vm_arrival_steps,            # live list, as env.py:307
+                "vm_placement": s["vm_placement"], "cpu": s["cpu"], "memory": s["memory"],
                 "vm_cpu": s["vm_cpu"], "vm_memory": s["vm_memory"], "target_cpu_mean": s["target_cpu_mean"],
                 "target_memory_mean": s["target_memory_mean"], "total_cpu_requested": s["total_cpu_requested"],
                 "total_memory_requested": s["total_memory_requested"],

@@ -151,7 +151,7 @@ class VecVmEnv:
         s = self.state
         self.cpu = s[:, L.off_cpu:L.off_cpu + 8 * P].view(torch.float64)
         self.memory = s[:, L.off_memory:L.off_memory + 8 * P].view(torch.float64)
-        self.vm_remaining_runtime = s[:, L.off_remaining:L.off_remaining + 2 * V].view(torch.int16)
+        self._vm_remaining_u16 = s[:, L.off_remaining:L.off_remaining + 2 * V].view(torch.int16)   # raw u16 bits
         pb = L.place_bytes
         self.vm_placement = s[:, L.off_placement:L.off_placement + pb * V].view(self.place_dtype)
         self.vm_cpu_code = s[:, L.off_cpu_code:L.off_cpu_code + V]
@@ -160,6 +160,19 @@ class VecVmEnv:
         self._scalars_i32 = sc[:, :40].view(torch.int32)
         self._scalars_i64 = sc[:, 40:80].view(torch.int64)     # seed, cpu_code_sum, mem_code_sum, (f64 x2 as bits)
         self._scalars_f64 = sc[:, 64:80].view(torch.float64)   # episode_return, last_reward
+
+    @property
+    def vm_remaining_runtime(self):
+        """int32 [N, V] copy of the remaining runtimes (stored as u16 in the record: values above 32767 stay positive)."""
+        return self._vm_remaining_u16.to(torch.int32) & 0xffff
+
+    def vm_arrival_step(self):
+        """int64 [N, V]: the step at which the VM occupying each slot arrived, as the reference logs it
+        (`vm_arrival_steps[i].append(timestep + 1)`, env.py:293); 0 for slots never occupied.  Needs enable_vm_stats()."""
+        if self._vm_slots is None:
+            raise RuntimeError("call enable_vm_stats() (before reset) first")
+        a = self._vm_slots[:, :, 0].to(torch.int64)
+        return torch.where(a > 0, a + 1, a)
 
     # ------------------------------------------------------------------------------------------------
     # reference API
