@@ -52,6 +52,9 @@ class PPOConfig:
     device: str = "cuda"
     env_chunk: int = 2048          # samples (env-steps) per forward/backward chunk inside a minibatch (gradient accumulation)
     fused_rollout: bool = False    # rollouts through the fused tcgen05 actor head (bf16 operands; action_dim <= 128)
+    vf_broadcast: bool = False     # reference-exact value loss: ppo.py:274-277 subtracts returns [mb] from newvalues [mb, 1], which
+                                   # broadcasts to [mb, mb] (every value against every return); False = the elementwise loss it
+                                   # evidently means (DESIGN.md §2 "intentional deviations").  O(mb^2) memory: small batches only
 
 
 def _ortho(layer: nn.Linear, gain: float) -> nn.Linear:
@@ -372,8 +375,9 @@ class PPOAgent(AgentBase):
             returns.append(ep_ret.mean().item())
         return returns
 
-    def update(self, obs, next_obs, action, mask, logprob, reward, done):
-        """ppo.py:229-295 on a time-major rollout [T, N, ...]."""
+    def update(self, obs, next_obs, action, mask, logprob, reward, done, debug: bool = False):
+        """ppo.py:229-295 on a time-major rollout [T, N, ...].  `debug`: also return what the update computed on the way
+        (values, advantages, returns, and per attempted minibatch: KL, loss, pre-clip gradient norm, stepped) — host syncs."""
         cfg, vec = self.config, self.vec
         T, N = reward.shape
         with torch.no_grad():
@@ -383,6 +387,7 @@ class PPOAgent(AgentBase):
         ccfg = vec._ccfg()
         world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
         stats = {}
+        attempts = []
         D = obs.shape[-1]
         for epoch in range(cfg.k_epochs):
             for t0 in range(0, T, cfg.minibatch_size):                 # sequential minibatches (ppo.py:251-252)
@@ -397,6 +402,9 @@ class PPOAgent(AgentBase):
                 lp_mb, val_mb, ret_mb = logprob[t0:t1].reshape(-1), values[t0:t1].reshape(-1), returns[t0:t1].reshape(-1)
                 self.optimizer.zero_grad(set_to_none=True)
                 logratio_sum = torch.zeros((), dtype=torch.float64, device=self.device)
+                loss_sum = torch.zeros((), dtype=torch.float64, device=self.device)
+                if cfg.vf_broadcast and n_mb > cfg.env_chunk:
+                    raise nv.VmgymError("vf_broadcast needs the whole minibatch in one chunk (samples <= env_chunk)")
                 for s0 in range(0, n_mb, cfg.env_chunk):
                     s1 = min(n_mb, s0 + cfg.env_chunk)
                     o = obs_mb[s0:s1]
@@ -410,10 +418,19 @@ class PPOAgent(AgentBase):
                     loss_clipped = torch.max(-ratios * a, -torch.clamp(ratios, 1 - cfg.eps_clip, 1 + cfg.eps_clip) * a).sum()
                     newv = self.model.get_value(o).flatten()
                     v_old, ret = val_mb[s0:s1], ret_mb[s0:s1]
-                    l_un = torch.square(newv - ret)
-                    l_cl = torch.square(v_old + torch.clamp(newv - v_old, -cfg.eps_clip, cfg.eps_clip) - ret)
-                    loss_vf = 0.5 * (torch.max(l_un, l_cl) if cfg.vf_loss_clip else l_un).sum()
+                    if cfg.vf_broadcast:
+                        # ppo.py:272-277 as written: newvalues is [mb, 1], returns[minibatch] is [mb] -> [mb, mb] pairs, mean
+                        # (i, j) pairs new value i against old value j / return j
+                        nv2 = newv[:, None]
+                        l_un = torch.square(nv2 - ret)
+                        l_cl = torch.square(v_old + torch.clamp(nv2 - v_old, -cfg.eps_clip, cfg.eps_clip) - ret)
+                        loss_vf = 0.5 * (torch.max(l_un, l_cl) if cfg.vf_loss_clip else l_un).sum() / n_mb
+                    else:
+                        l_un = torch.square(newv - ret)
+                        l_cl = torch.square(v_old + torch.clamp(newv - v_old, -cfg.eps_clip, cfg.eps_clip) - ret)
+                        loss_vf = 0.5 * (torch.max(l_un, l_cl) if cfg.vf_loss_clip else l_un).sum()
                     loss = (loss_clipped - cfg.ent_coef * ent.sum() + cfg.vf_coef * loss_vf) / n_mb   # means over the minibatch
+                    loss_sum += loss.detach().double()
                     loss.backward()
                 # KL early stop on the whole minibatch (ppo.py:263-264): the reference breaks before its backward; here the
                 # accumulated gradients of this minibatch are dropped instead (same parameters afterwards)
@@ -422,6 +439,8 @@ class PPOAgent(AgentBase):
                     torch.distributed.all_reduce(kl)
                     kl /= world
                 stats = {"kl": kl.item()}
+                if debug:
+                    attempts.append(dict(epoch=epoch, mb=t0 // cfg.minibatch_size, kl=stats["kl"], loss=loss_sum.item(), stepped=0))
                 if cfg.kl_max is not None and stats["kl"] > cfg.kl_max:
                     self.optimizer.zero_grad(set_to_none=True)
                     break                                              # only the minibatch loop; the next epoch still runs
@@ -433,6 +452,10 @@ class PPOAgent(AgentBase):
                     for p in self.model.parameters():
                         p.grad.copy_(flat[off:off + p.numel()].view_as(p))
                         off += p.numel()
-                nn.utils.clip_grad_norm_(self.model.parameters(), cfg.max_grad_norm)
+                gnorm = nn.utils.clip_grad_norm_(self.model.parameters(), cfg.max_grad_norm)
                 self.optimizer.step()
+                if debug:
+                    attempts[-1].update(stepped=1, grad_norm=float(gnorm))
+        if debug:
+            stats.update(values=values, next_values=next_values, advantages=advantages, returns=returns, attempts=attempts)
         return stats
