@@ -33,7 +33,6 @@ METRIC = "env-steps/sec (100 PMs, best-fit act+step, whole job)"
 UNIT = "env-steps/s"
 WARM_STEPS = 3000          # reach saturation (~300/300 slots occupied) before timing, SURVEY §8d
 PERIOD = 1000              # service_length of config/100.yml: one departure wave per period
-NCU_TRAFFIC_PER_LAUNCH = 14.25e6   # bytes, ncu --set full capture of the 4096-env launch (profiles/r1_step_kernel_full.md)
 
 
 def load_env_cfg():
@@ -140,79 +139,83 @@ def gpu_arm(args):
     if args.bulk is not None or args.warps:
         from vmgym import _native as nv
         nv.lib().vmgym_set_tuning(int(args.warps), 7 if args.bulk is None else int(args.bulk))
-    # envs shard contiguously: rank g owns global env ids [g*E, (g+1)*E); seeds derive from the global id
-    seeds = cfg["seed"] + rank * E + np.arange(E, dtype=np.int64)
-    vec = VecVmEnv(Config(**cfg), E, device=dev, rng="philox", seeds=seeds)
-    P, V, D = vec.P, vec.V, vec.obs_dim
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- batches: NB independent batches of E envs each; a timed "step" is one fused act+step launch over ONE batch,
-    # launches rotate over the batches.  Working set per launch = 14 MB records read + 14 MB written + 18 MB observations;
-    # NB launches touch NB x 46 MB >> 126 MB L2 before a batch comes round again, so every launch reads its records from
-    # HBM (inputs larger than L2; no flush kernel and no per-step event pair inside the timed region).
+    # ---- batches: NB independent batches of E envs each, resident in ONE state buffer; a timed "step" is one fused
+    # act+step pass over ONE batch, consecutive steps rotate over the batches.  Working set per step = 14 MB records read +
+    # 14 MB written (+ the observation rows that changed); NB steps touch NB x 28 MB >> 126 MB L2 before a batch comes round
+    # again, so every step reads its records from HBM (inputs larger than L2; no flush kernel inside the timed region).
     # Service times are Poisson(1000): departures come in waves one service period apart and a step costs more inside a
     # wave.  Batch b is therefore warmed up to phase b * PERIOD / NB of the period, so the rotation samples all phases.
+    # Envs shard contiguously over ranks: batch b of rank g holds global env ids [(b * world + g) * E, +E).
     NB = args.batches
-    vecs = [vec]
-    for b in range(1, NB):
-        sb = cfg["seed"] + (b * world + rank) * E + np.arange(E, dtype=np.int64)      # distinct seeds per batch and rank
-        vecs.append(VecVmEnv(Config(**cfg), E, device=dev, rng="philox", seeds=sb))
-    for b, vb_ in enumerate(vecs):
-        vb_.agent_step("bestfit", n_steps=WARM_STEPS + (b * PERIOD) // NB, want_obs=False, want_action=False, want_valid=False)
+    seeds = np.concatenate([cfg["seed"] + (b * world + rank) * E + np.arange(E, dtype=np.int64) for b in range(NB)])
+    vec = VecVmEnv(Config(**cfg), NB * E, device=dev, rng="philox", seeds=seeds)
+    P, V, D = vec.P, vec.V, vec.obs_dim
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    quiet = dict(want_obs=False, want_action=False, want_valid=False)
+    for b in range(NB):
+        vec.agent_step("bestfit", n_steps=WARM_STEPS + (b * PERIOD) // NB, envs=(b * E, (b + 1) * E), **quiet)
 
-    def rotate(n, start=0):
-        for k in range(n):
-            vecs[(start + k) % NB].agent_step("bestfit", 1, want_obs=True, want_action=False, want_valid=False)
-
-    K, W = args.steps, max(3, args.warmup)
-    with vec._on_device():
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            rotate(NB)                                  # allocations / plan caches before capture
-        torch.cuda.current_stream(dev).wait_stream(side)
-        timed_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(timed_graph):
-            rotate(K, start=W)                          # exactly K launches of the fused step kernel
-    rotate(W)                                           # W untimed warm-up steps of exactly the timed call
-    timed_graph.replay()                                # + one untimed replay of the timed graph itself: a graph's first launch
-    barrier()                                           #   uploads it to the device (~40 us, which a small K would carry)
-
+    K, W, R = args.steps, max(3, args.warmup), max(1, args.replays)
+    # ---- timed region A (value): the rotation as ONE persistent launch of K batch steps (vmgym_agent_step_rotation): a warp
+    # owns env index i of every batch, the grid stays resident across the K steps.  W untimed warm-up steps of the same call
+    # (after one full untimed rotation, which also stores every observation row once), then R timed replays of the K-step
+    # launch, each with its own event pair; the rotation continues from replay to replay (all phases sampled).
+    nxt = vec.agent_step_rotation("bestfit", E, NB, first_batch=0)
+    nxt = vec.agent_step_rotation("bestfit", E, W, first_batch=nxt)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(R)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(R)]
+    barrier()
+    for r in range(R):
+        ev0[r].record()
+        nxt = vec.agent_step_rotation("bestfit", E, K, first_batch=nxt)
+        ev1[r].record()
+    barrier()
+    replay_ms = np.array([a_.elapsed_time(b_) for a_, b_ in zip(ev0, ev1)], dtype=np.float64)
+    total_ms = float(np.median(replay_ms))
 
-    # ---- timed region A (value): K fused steps, records + outputs resident in HBM ----
-    t_a0, t_a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_a0.record()
-    timed_graph.replay()
-    t_a1.record()
-    barrier()
-    total_ms = float(t_a0.elapsed_time(t_a1))
+    # observation rows the step kernel actually stores: a row is re-stored only when its env's state changed since the row was
+    # written; counted on the device, outside the timed region, over one full rotation (every batch once)
+    before = vec.obs.clone()
+    nxt = vec.agent_step_rotation("bestfit", E, NB, first_batch=nxt)
+    rows_changed = int((vec.obs != before).any(dim=1).sum().item())
+    del before
+    obs_rows_frac = rows_changed / float(NB * E)
 
-    # ---- timed region A' (single_launch_flushed): the round-1 protocol, one batch, L2 flushed before every timed launch,
-    # one event pair per launch (adds ~6 us of event/launch latency to every step); kept for comparison ----
-    Kf = 20
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(Kf)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(Kf)]
-    one_step = vec.capture(lambda: vec.agent_step("bestfit", 1, want_obs=True, want_action=False, want_valid=False))
-    spread = max(0, PERIOD // Kf - 1)
+    # ---- timed region A' (per_launch): the round-1 protocol — the same K batch steps as K separate launches of the fused step
+    # kernel (one CUDA graph, programmatic dependent launch between them), median of 10 replays ----
+    def rotate(n, start):
+        for k in range(n):
+            b_ = (start + k) % NB
+            vec.agent_step("bestfit", 1, want_obs=True, want_action=False, want_valid=False, envs=(b_ * E, (b_ + 1) * E))
+
+    with vec._on_device():
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            rotate(NB, nxt)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        launch_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(launch_graph):
+            rotate(K, nxt)
+    launch_graph.replay()
     barrier()
-    for k in range(Kf):
-        vec.agent_step("bestfit", spread, want_obs=False, want_action=False, want_valid=False)
-        flush.fill_(k & 0xff)                      # evict state/obs from L2 (outside the event pair)
-        starts[k].record()
-        one_step.replay()
-        ends[k].record()
-    barrier()
-    flushed_ms = float(np.mean([s_.elapsed_time(e_) for s_, e_ in zip(starts, ends)]))
+    pl = []
+    for _ in range(10):
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(); launch_graph.replay(); s1.record()
+        torch.cuda.synchronize()
+        pl.append(s0.elapsed_time(s1))
+    per_launch_ms = float(np.median(pl)) / K
 
     # ---- timed region B (rollout): same work, 100 steps per launch with the state resident in shared memory ----
     chunk, n_chunks = 100, 10                   # 1000 steps = one full service period
@@ -220,7 +223,7 @@ def gpu_arm(args):
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     r0.record()
     for _ in range(n_chunks):
-        vec.agent_step("bestfit", chunk, want_obs=True, want_action=False, want_valid=False)
+        vec.agent_step("bestfit", chunk, want_obs=True, want_action=False, want_valid=False, envs=(0, E))
     r1.record()
     barrier()
     rollout_ms = r0.elapsed_time(r1)
@@ -264,44 +267,31 @@ def gpu_arm(args):
     del hv, hv1
     clocks = sampler.finish() if sampler else None
 
-    # ---- extra A: the same kernel with 8x the envs (several resident waves per SM -> load/compute/store overlap) ----
-    big = None
-    if not args.no_extras:
-        Eb = 8 * E
-        vb = VecVmEnv(Config(**cfg), Eb, device=dev, rng="philox", seeds=cfg["seed"] + 10**6 + rank * Eb + np.arange(Eb, dtype=np.int64))
-        vb.agent_step("bestfit", n_steps=WARM_STEPS, want_obs=False, want_action=False, want_valid=False)
-        gb = vb.capture(lambda: vb.agent_step("bestfit", 1, want_obs=True, want_action=False, want_valid=False))
-        tb = []
-        for k in range(10):
-            vb.agent_step("bestfit", 99, want_obs=False, want_action=False, want_valid=False)
-            flush.fill_(k)
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record(); gb.replay(); s1.record(); torch.cuda.synchronize()
-            tb.append(s0.elapsed_time(s1))
-        big = {"envs_per_gpu": Eb, "ms_per_step": float(np.mean(tb))}
-        del vb, gb
-
-    # ---- extra B: PPO training throughput (rollout with the masked-heads kernel + GAE + k_epochs update) ----
+    # ---- extra A: PPO training throughput at BASELINE config 4's per-GPU share: 8192 envs, rollout T = batch_size = 100
+    # (config/100.yml), 4 sequential minibatches of 25 steps, k_epochs 4, NCCL gradient all-reduce per optimiser step ----
     ppo = None
     if not args.no_extras:
         from vmgym.ppo import PPOAgent, PPOConfig
-        Np, Tp = args.ppo_envs, 16
+        Np, Tp = args.ppo_envs, args.ppo_steps
         vp = VecVmEnv(Config(**cfg), Np, device=dev, rng="philox", seeds=cfg["seed"] + 2 * 10**6 + rank * Np + np.arange(Np, dtype=np.int64))
         torch.set_float32_matmul_precision("high")      # as the reference does (main.py:45): TF32 for the fp32 layers
-        agent_p = PPOAgent(vp, PPOConfig(hidden_size=512, batch_size=Tp, minibatch_size=Tp // 4, episodes=1, env_chunk=32768,
+        agent_p = PPOAgent(vp, PPOConfig(hidden_size=512, batch_size=Tp, minibatch_size=max(1, Tp // 4), episodes=1, env_chunk=32768,
                                          masked=True, kl_max=1e9, fused_rollout=True))
         if world > 1:
             for p_ in agent_p.model.parameters():
                 dist.broadcast(p_.data, 0)
-        agent_p.learn(episodes=1, max_updates=1)            # warm-up (allocations, cuBLAS heuristics)
+        vp.agent_step("bestfit", n_steps=WARM_STEPS, **quiet)          # saturated envs, as in training after the first episode steps
+        agent_p.learn(episodes=1, max_updates=1, reset=False)           # warm-up (allocations, kernel plans)
         barrier()
         t0 = time.perf_counter()
-        agent_p.learn(episodes=1, max_updates=2)
+        agent_p.learn(episodes=1, max_updates=1, reset=False)
         barrier()
-        ppo = {"seconds": time.perf_counter() - t0, "env_steps": 2 * Np * Tp}
+        ppo = {"seconds": time.perf_counter() - t0, "env_steps": Np * Tp, "T": Tp, "envs": Np}
         del vp, agent_p
         # PPO evaluation rollouts (BASELINE config 3 shape): mask + gating + fused tcgen05 actor head + env.step, E envs
-        agent_e = PPOAgent(vec, PPOConfig(hidden_size=512, masked=True, migration_ratio=0.002))
+        ve = VecVmEnv(Config(**cfg), E, device=dev, rng="philox", seeds=cfg["seed"] + 6 * 10**6 + rank * E + np.arange(E, dtype=np.int64))
+        ve.agent_step("bestfit", n_steps=WARM_STEPS, **quiet)
+        agent_e = PPOAgent(ve, PPOConfig(hidden_size=512, masked=True, migration_ratio=0.002))
         agent_e.rollout(3)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -310,15 +300,15 @@ def gpu_arm(args):
         e1.record()
         barrier()
         ppo["eval_ms_per_step"] = e0.elapsed_time(e1) / 20
-        del agent_e
+        del agent_e, ve
 
-    # ---- extra C: the synthetic 1000-PM shape (BASELINE config 5: highuniform sizes at 100 % load, V = 3P) ----
+    # ---- extra B: the synthetic 1000-PM shape (BASELINE config 5: highuniform sizes at 100 % load, V = 3P) ----
     s1000 = None
     if not args.no_extras:
         kw1000 = dict(cfg, pms=1000, vms=3000, sequence="highuniform", arrival_rate=1000 / 0.625 / cfg["service_length"])
         E1 = 1024
         v1 = VecVmEnv(Config(**kw1000), E1, device=dev, rng="philox", seeds=cfg["seed"] + 4 * 10**6 + rank * E1 + np.arange(E1, dtype=np.int64))
-        v1.agent_step("bestfit", n_steps=WARM_STEPS, want_obs=False, want_action=False, want_valid=False)
+        v1.agent_step("bestfit", n_steps=WARM_STEPS, **quiet)
         v1.agent_step("bestfit", 1, want_obs=True, want_action=False, want_valid=False)
         barrier()
         s0_, s1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -343,14 +333,14 @@ def gpu_arm(args):
         s1000["drlvmp_s_per_step"] = (time.perf_counter() - t0) / 2
         del v1, ag1
 
-    # ---- extra D: the small shape of BASELINE configs[0] (config/10.yml, first-fit) at 2^20 envs per GPU ----
+    # ---- extra C: the small shape of BASELINE configs[0] (config/10.yml, first-fit) at 2^20 envs per GPU ----
     s10 = None
     if not args.no_extras:
         cfg10 = yaml.safe_load(open(os.path.join(ROOT, "configs", "10.yml")))["environment"]
         cfg10["reward_function"] = "wr"
         E10 = 1 << 20
         v10 = VecVmEnv(Config(**cfg10), E10, device=dev, rng="philox", seeds=cfg10["seed"] + 5 * 10**6 + rank * E10 + np.arange(E10, dtype=np.int64))
-        v10.agent_step("firstfit", n_steps=WARM_STEPS, want_obs=False, want_action=False, want_valid=False)
+        v10.agent_step("firstfit", n_steps=WARM_STEPS, **quiet)
         v10.agent_step("firstfit", 1, want_obs=True, want_action=False, want_valid=False)
         barrier()
         s0_, s1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -363,24 +353,27 @@ def gpu_arm(args):
         del v10
 
     if world > 1:
-        t = torch.tensor([total_ms, rollout_ms, e2e_s, big["ms_per_step"] if big else 0.0, ppo["seconds"] if ppo else 0.0,
-                          ppo["eval_ms_per_step"] if ppo else 0.0, flushed_ms, e2e1_s, s1000["ms_per_step"] if s1000 else 0.0,
-                          s1000["drlvmp_s_per_step"] if s1000 else 0.0, s10["ms_per_step"] if s10 else 0.0],
+        t = torch.tensor([total_ms, rollout_ms, e2e_s, per_launch_ms, ppo["seconds"] if ppo else 0.0,
+                          ppo["eval_ms_per_step"] if ppo else 0.0, e2e1_s, s1000["ms_per_step"] if s1000 else 0.0,
+                          s1000["drlvmp_s_per_step"] if s1000 else 0.0, s10["ms_per_step"] if s10 else 0.0,
+                          float(np.percentile(replay_ms, 10)), float(np.percentile(replay_ms, 90)), float(replay_ms.mean())],
                          dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, rollout_ms, e2e_s = t.tolist()[:3]
-        flushed_ms = t[6].item()
-        e2e1_s = t[7].item()
+        tl = t.tolist()
+        total_ms, rollout_ms, e2e_s, per_launch_ms = tl[:4]
+        e2e1_s = tl[6]
         if s1000:
-            s1000["ms_per_step"] = t[8].item()
-            s1000["drlvmp_s_per_step"] = t[9].item()
+            s1000["ms_per_step"], s1000["drlvmp_s_per_step"] = tl[7], tl[8]
         if s10:
-            s10["ms_per_step"] = t[10].item()
-        if big:
-            big["ms_per_step"] = t[3].item()
+            s10["ms_per_step"] = tl[9]
         if ppo:
-            ppo["seconds"] = t[4].item()
-            ppo["eval_ms_per_step"] = t[5].item()
+            ppo["seconds"], ppo["eval_ms_per_step"] = tl[4], tl[5]
+        p10_ms, p90_ms, mean_ms = tl[10], tl[11], tl[12]
+        fr = torch.tensor([obs_rows_frac], dtype=torch.float64, device=dev)
+        dist.all_reduce(fr)
+        obs_rows_frac = fr.item() / world
+    else:
+        p10_ms, p90_ms, mean_ms = float(np.percentile(replay_ms, 10)), float(np.percentile(replay_ms, 90)), float(replay_ms.mean())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -393,84 +386,108 @@ def gpu_arm(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    B = algorithmic_bytes(P, V)
-    avg_launch_s = (total_ms / K) * 1e-3
-    achieved = B * E / avg_launch_s / 1e9
+    # Algorithmic bytes per env-step: the fused heuristic step reads and writes the state record once,
+    # B_fused = 2 S + 16 with S = 16 P + 5 V + 48, plus the observation bytes the kernel really stores (rows of envs whose
+    # state changed; unchanged rows are kept in the persistent observation buffer), measured above.
+    S = 16 * P + 5 * V + 48
+    B_fused = 2 * S + 16
+    obs_stored = obs_rows_frac * 4 * D
+    B = B_fused + obs_stored
+    step_s = (total_ms / K) * 1e-3
+    achieved = B * E / step_s / 1e9
     value = world * E * K / (total_ms * 1e-3)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_rotation_traffic.json")))
+        if int(tj.get("envs_per_batch", 0)) == E:
+            traffic, traffic_src = float(tj["dram_bytes_per_batch_step"]), tj.get("source")
+    except Exception:
+        pass
+    extras = {}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic (Philox arrivals, uniform sizes)",
         "config": {"workload": "config/100.yml best-fit evaluation: 100 PMs, 300 VM slots, uniform sizes, "
-                               f"{E} envs per GPU, reward wr, saturated after {WARM_STEPS} warm-up steps",
+                               f"{E} envs per GPU per batch, reward wr, saturated after {WARM_STEPS} warm-up steps",
                    "envs_per_gpu": E, "batches": NB,
-                   "l2": f"inputs larger than L2: launches rotate over {NB} independent {E}-env batches "
-                         f"({NB} x {(2 * 3456 * E + 4 * D * E) / 1e6:.0f} MB touched between two visits of a batch, L2 = 126 MB)",
+                   "l2": f"inputs larger than L2: consecutive steps rotate over {NB} independent {E}-env batches "
+                         f"({NB} x {2 * 3456 * E / 1e6:.0f} MB of records touched between two visits of a batch, L2 = 126 MB)",
                    "phase_sampling": f"batch b warmed up to phase b*{PERIOD}/{NB} of the service period (departure waves)",
-                   "timing": "one CUDA-event pair around a CUDA graph of exactly K step-kernel launches (second replay of the graph: the first, untimed one uploads it)",
+                   "timing": f"one step = one fused act+step pass over one {E}-env batch; K consecutive steps = ONE persistent launch "
+                             f"(vmgym_agent_step_rotation); {R} replays of the K-step launch, one CUDA-event pair each; "
+                             "ms_per_step = median replay / K",
                    "rng": "philox", "tiebreak": "stable",
-                   "obs_written": "every step into the env's persistent observation buffer; rows of envs whose state did not change are kept, not re-stored",
+                   "obs_written": "into the env's persistent observation buffer; rows of envs whose state did not change are kept, not re-stored",
                    "state_types": "f64 PM accumulators, u8 placements / size codes, u16 runtimes, f32 observation"},
-        "gpu_launches": K,
+        "gpu_launches": R,
+        "timing_stats": {"replays": R, "steps_per_replay": K, "median_ms": total_ms, "p10_ms": p10_ms, "p90_ms": p90_ms,
+                         "mean_ms": mean_ms, "spread": (p90_ms - p10_ms) / total_ms},
         "e2e": {"value": world * E * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "groups": args.e2e_groups, "full_obs_copy_value": world * E * Ke / e2e1_s,
                 "path": "HostVecEnv: BestFitAgent.act(host obs) -> host action -> VecVmEnv.step(host action) -> host obs/reward/done in "
                         "pinned host buffers; envs split into stream groups whose PCIe transfers overlap; the step kernel keeps the host "
                         "observation buffer current by storing only the entries that changed (d2h_bytes_per_step = actions + measured "
                         "changed observation entries + reward/done; full_obs_copy_value: the same loop copying all 4(3V+2P) bytes per env)"},
-        "single_launch_flushed": {"value": world * E / (flushed_ms * 1e-3), "unit": UNIT, "ms_per_step": flushed_ms, "steps": Kf,
-                                  "note": "one batch, 256 MiB L2 flush before and one event pair around every launch "
-                                          "(includes ~6 us event/launch latency per step), steps spread over one service period"},
+        "per_launch": {"value": world * E / (per_launch_ms * 1e-3), "unit": UNIT, "ms_per_step": per_launch_ms,
+                       "note": "round-1 protocol: the same rotation as K separate launches of the fused step kernel in one CUDA graph "
+                               "(programmatic dependent launch), median of 10 replays",
+                       "roofline_frac": B * E / (per_launch_ms * 1e-3) / 1e9 / peak},
         "rollout": {"value": world * E * chunk * n_chunks / (rollout_ms * 1e-3), "unit": UNIT,
                     "steps_per_launch": chunk, "note": "same fused kernel, env state resident in shared memory across steps"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_PER_LAUNCH if E == 4096 else None,
-                     "traffic_note": "profiles/r1d_step_kernel_quiet.md (final kernel) and r1_step_kernel_full.md (departure wave): dram__bytes_read 14.22-14.23 MB + dram__bytes_write < 0.03 MB per "
-                                     "launch; what the kernel stores (14 MB of records + the observation rows of the envs that changed, at most 18 MB) stays in the "
-                                     "126 MB L2 until later launches evict it; `achieved` counts the algorithmic bytes of every env-step incl. its "
-                                     "observation row, also for envs whose unchanged row is kept instead of re-stored",
-                     "kernel": "vmgym::step_kernel<u8,100,300> (fused best-fit + step)",
-                     "bytes_per_env_step": B, "peak_source": peak_src},
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "kernel": "vmgym::step_kernel<u8,100,300,bestfit/wr/philox> (rotation launch)",
+                     "bytes_per_env_step": B, "B_fused": B_fused, "obs_bytes_stored_per_env_step": obs_stored,
+                     "obs_rows_stored_frac": obs_rows_frac,
+                     "frac_B_fused_only": B_fused * E / step_s / 1e9 / peak,
+                     "frac_if_every_obs_row_counted": (B_fused + 4 * D) * E / step_s / 1e9 / peak,
+                     "note": "achieved = (B_fused + measured stored observation bytes) x envs per step / (median replay / K); "
+                             "B_fused = 2(16P+5V+48)+16 (SURVEY §8d); frac_if_every_obs_row_counted is the round-1 accounting, secondary",
+                     "peak_source": peak_src},
         "clocks": clocks,
     }
-    if big:
-        Eb, msb = big["envs_per_gpu"], big["ms_per_step"]
-        out["large_batch"] = {"envs_per_gpu": Eb, "value": world * Eb / (msb * 1e-3), "unit": UNIT, "ms_per_step": msb,
-                              "roofline_frac": B * Eb / (msb * 1e-3) / 1e9 / peak,
-                              "note": "same kernel and timing protocol, 8x the envs (10 timed steps, 100 apart)"}
+    extras["per_launch_M"] = round(world * E / (per_launch_ms * 1e-3) / 1e6, 1)
+    extras["rollout100_M"] = round(world * E * chunk * n_chunks / (rollout_ms * 1e-3) / 1e6, 1)
     if ppo:
         out["ppo_train"] = {"value": world * ppo["env_steps"] / ppo["seconds"], "unit": "PPO train env-steps/s",
-                            "config": f"config/100.yml, {args.ppo_envs} envs/GPU (BASELINE config 4's per-GPU share), rollout T=16 "
-                                      "(reference batch_size 100 shortened to bound the bench), k_epochs=4, 4 sequential minibatches, H=512, "
-                                      "rollout: fused tcgen05 actor head (bf16), update: cuBLAS TF32 layers + masked-heads/GAE kernels, "
+                            "config": f"config/100.yml, {ppo['envs']} envs/GPU (BASELINE config 4's per-GPU share), rollout T={ppo['T']} "
+                                      "(reference batch_size), k_epochs=4, 4 sequential minibatches, H=512, "
                                       "NCCL gradient all-reduce per optimiser step when N > 1",
-                            "seconds": ppo["seconds"]}
+                            "seconds": ppo["seconds"], "T": ppo["T"], "envs_per_gpu": ppo["envs"]}
         out["ppo_eval"] = {"value": world * E / (ppo["eval_ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": ppo["eval_ms_per_step"],
                            "config": f"config/100.yml PPO evaluation rollouts, {E} envs/GPU, reference-shaped MLP (H=512, random init: the "
                                      "100-PM weights are not shipped), masked, migration_ratio 0.002, fused tcgen05 actor head (bf16)"}
+        extras[f"ppo_train_T{ppo['T']}_M"] = round(out["ppo_train"]["value"] / 1e6, 3)
+        extras["ppo_eval_M"] = round(out["ppo_eval"]["value"] / 1e6, 2)
     if s1000:
-        B1 = algorithmic_bytes(1000, 3000)
+        B1 = 2 * (16 * 1000 + 6 * 3000 + 48) + 16
         out["s1000"] = {"value": world * s1000["envs_per_gpu"] / (s1000["ms_per_step"] * 1e-3), "unit": UNIT,
                         "ms_per_step": s1000["ms_per_step"], "envs_per_gpu": s1000["envs_per_gpu"],
-                        "roofline_frac": B1 * s1000["envs_per_gpu"] / (s1000["ms_per_step"] * 1e-3) / 1e9 / peak,
+                        "roofline_frac_B_fused": B1 * s1000["envs_per_gpu"] / (s1000["ms_per_step"] * 1e-3) / 1e9 / peak,
                         "drlvmp_rollout": {"value": world * s1000["envs_per_gpu"] / s1000["drlvmp_s_per_step"], "unit": UNIT,
                                            "note": "DRLVMPAgent.act (H=512 dueling C51 net, one network evaluation + heuristic per waiting "
-                                                   "VM, ~900 sequential evaluations per env and step at this load; each = 2 TF32 GEMMs + "
-                                                   "the fused vmgym_drlvmp_iter kernel, 32 per CUDA-graph replay) + env.step"},
+                                                   "VM) + env.step"},
                         "config": "synthetic 1000 PMs / 3000 VM slots, highuniform sizes, arrival 1.6 (100 % load), fused best-fit act+step, "
-                                  "one launch per step, team-mode kernel (one env per CTA: warp 0 steps, the helper warps join the "
-                                  "slot / PM loops; 4 CTAs of 6 warps per SM by shared memory and registers, so 1024 envs take 2 rounds)"}
+                                  "one launch per step, team-mode kernel"}
+        extras["s1000_M"] = round(out["s1000"]["value"] / 1e6, 2)
+        extras["s1000_drlvmp_k"] = round(out["s1000"]["drlvmp_rollout"]["value"] / 1e3, 1)
     if s10:
-        B10 = algorithmic_bytes(10, 30)
+        B10 = 2 * (16 * 10 + 5 * 30 + 48) + 16
         out["s10"] = {"value": world * s10["envs_per_gpu"] / (s10["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": s10["ms_per_step"],
-                      "envs_per_gpu": s10["envs_per_gpu"], "roofline_frac": B10 * s10["envs_per_gpu"] / (s10["ms_per_step"] * 1e-3) / 1e9 / peak,
-                      "config": "config/10.yml shape (10 PMs / 30 VM slots, the CPU-runnable case of BASELINE configs[0]), first-fit fused "
-                                "act+step, 2^20 envs per GPU, one launch per step (working set 0.9 GB per launch > L2)"}
+                      "envs_per_gpu": s10["envs_per_gpu"],
+                      "roofline_frac_B_fused": B10 * s10["envs_per_gpu"] / (s10["ms_per_step"] * 1e-3) / 1e9 / peak,
+                      "config": "config/10.yml shape (10 PMs / 30 VM slots, BASELINE configs[0]), first-fit fused act+step, 2^20 envs per GPU, "
+                                "one launch per step"}
+        extras["s10_G"] = round(out["s10"]["value"] / 1e9, 3)
     if prev_affinity is not None:
         os.sched_setaffinity(0, prev_affinity)             # the CPU baseline uses every host core
     out["config"]["numa_bound"] = prev_affinity is not None
     if not args.no_cpu:
         out["cpu_baseline"] = cpu_arm(steps_per_env=args.cpu_steps)
+    # compact copy of the secondary numbers, last in the line (survives a truncated tail) and inside the parsed `config`
+    out["config"]["extras"] = extras
+    out["extras"] = extras
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -511,6 +528,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (per batch)")
     ap.add_argument("--ppo-envs", type=int, default=8192, help="envs per GPU of the ppo_train extra")
+    ap.add_argument("--ppo-steps", type=int, default=100, help="rollout length T of the ppo_train extra (config/100.yml batch_size)")
+    ap.add_argument("--replays", type=int, default=50, help="timed replays of the K-step rotation launch (median reported)")
     ap.add_argument("--warps", type=int, default=0, help="vmgym_set_tuning warps per CTA, 0 = auto (experiments)")
     ap.add_argument("--bulk", type=int, default=None, help="vmgym_set_tuning use_bulk_copy bits (experiments)")
     ap.add_argument("--e2e-groups", type=int, default=4, help="env groups (streams) of the host-buffer e2e loop")

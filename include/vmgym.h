@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define VMGYM_ABI_VERSION 5
+#define VMGYM_ABI_VERSION 6
 
 enum vmgym_status {
     VMGYM_OK = 0,
@@ -177,6 +177,17 @@ int vmgym_vmstats_finalize(const vmgym_config* cfg, const void* d_state, int64_t
 int vmgym_agent_step(const vmgym_config* cfg, void* d_state, int64_t n_envs, const vmgym_trace* trace, int agent,
                      int tiebreak, int n_steps, const vmgym_outputs* out, void* stream);
 
+/* The same fused act + step for SEVERAL independent env batches resident in one state buffer (the seeds / load points / batches
+ * the reference's drivers fan out over processes, exp_performance.py:63-83), as ONE persistent launch: d_state holds
+ * n_batches x envs_per_batch records (batch b = records [b * envs_per_batch, (b + 1) * envs_per_batch)), outputs are sized for
+ * all of them, and the launch executes n_batch_steps consecutive "batch steps" — batch step k advances every env of batch
+ * (first_batch + k) % n_batches by n_steps steps of the Base.test loop (base.py:71-86).  Equivalent to n_batch_steps calls of
+ * vmgym_agent_step on the batches in rotation; a warp owns env index i of every batch, so the grid stays resident and no launch
+ * boundary separates the steps.  Results are identical to the per-batch calls (tested). */
+int vmgym_agent_step_rotation(const vmgym_config* cfg, void* d_state, int64_t envs_per_batch, int32_t n_batches, int32_t first_batch,
+                              int32_t n_batch_steps, const vmgym_trace* trace, int agent, int tiebreak, int n_steps,
+                              const vmgym_outputs* out, void* stream);
+
 /* agent.act(observation) on a batch of float32 observations (firstfit.py:21-38, bestfit.py:21-40,
  * drlvmp.py:549-617 heuristics).  d_action element type given by action_dtype. */
 int vmgym_agent_act(const vmgym_config* cfg, int agent, int tiebreak, const float* d_obs, int64_t n_envs,
@@ -206,6 +217,16 @@ int vmgym_policy_heads(const vmgym_config* cfg, const void* d_state, const uint3
 int vmgym_policy_heads_backward(const vmgym_config* cfg, const uint32_t* d_mask_in, int masked, const float* d_logits,
                                 int64_t n_envs, const void* d_action_in, int action_dtype, const float* d_g_logprob,
                                 const float* d_g_entropy, float* d_g_logits, void* stream);
+
+/* The optimiser step of PPOAgent.update (ppo.py:143,284-287) on flat fp32 buffers of n elements:
+ * nn.utils.clip_grad_norm_(max_grad_norm; <= 0 disables) on d_grad * grad_scale, then torch.optim.AdamW's update
+ * (decoupled weight decay, bias-corrected moments; formulas of torch's reference implementation).  Device-resident control:
+ * *d_step is the optimiser's step counter (incremented here), *d_skip != 0 (may be NULL) turns the whole call into a no-op —
+ * the KL early stop of ppo.py:263-264 decided without a host round trip.  d_workspace: >= 1024 doubles of scratch;
+ * d_grad_norm_out (may be NULL) receives the pre-clip global norm.  d_grad must be 16-byte aligned. */
+int vmgym_adamw_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, float max_grad_norm, float grad_scale,
+                     double* d_workspace, const int32_t* d_skip, int32_t* d_step, float* d_grad_norm_out, void* stream);
 
 /* GAE advantages and returns (ppo.py:237-243) for time-major tensors [T, n_envs]; `dones` masks both the bootstrap
  * and the recursion. */

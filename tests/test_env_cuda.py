@@ -693,3 +693,47 @@ def test_performance_rows_through_sweep(shape, agent, load, reward, seeds, want)
     got = performance_row(base, agent, load, reward, seeds=seeds).split(",")
     w = want.split(",")
     assert got[:9] == w[:9] and got[10:] == w[10:], (",".join(got), want)
+
+
+@pytest.mark.parametrize("shape,E,NB,K,n_steps,agent,bulk", [("s100", 300, 3, 8, 1, "bestfit", 7), ("s100", 4200, 2, 5, 1, "bestfit", 7),
+                                                            ("s10", 700, 4, 9, 2, "firstfit", 7 | 32), ("wide", 5, 3, 7, 1, "firstfit", 7),
+                                                            ("s100", 64, 5, 12, 3, "firstfit", 0)])
+def test_rotation_launch_equals_per_batch_launches(shape, E, NB, K, n_steps, agent, bulk):
+    """vmgym_agent_step_rotation: ONE persistent launch over NB sub-batches x K batch steps == K calls of the fused agent step on
+    the sub-batches in rotation (byte-identical records, observations, rewards, done flags), for record staging by bulk copies,
+    double-buffered records, plain loads, the team-mode kernel (wide) and more env indexes than resident warps (4200)."""
+    torch = _torch()
+    from vmgym import VecVmEnv
+    from vmgym import _native as nv
+    kw = SHAPES[shape]
+    N = E * NB
+    seeds = 900 + np.arange(N)
+    first = 1 % NB
+    nv.lib().vmgym_set_tuning(0, bulk)
+    try:
+        a = VecVmEnv(_cfg(**kw), N, rng="philox", seeds=seeds)
+        b = VecVmEnv(_cfg(**kw), N, rng="philox", seeds=seeds)
+        # different phases per sub-batch before the comparison (as the benchmark staggers its batches)
+        for vec in (a, b):
+            for s in range(NB):
+                vec.agent_step(agent, n_steps=30 + 7 * s, want_action=False, want_valid=False, envs=(s * E, (s + 1) * E))
+        nxt = a.agent_step_rotation(agent, E, K, first_batch=first, n_steps=n_steps)
+        assert nxt == (first + K) % NB
+        # reference: the same batch steps as separate launches on b's sub-batches
+        for k in range(K):
+            s = (first + k) % NB
+            b.agent_step(agent, n_steps=n_steps, want_action=False, want_valid=False, envs=(s * E, (s + 1) * E))
+        torch.cuda.synchronize()
+        L = a._layout
+        ra, rb = a.state.cpu().numpy(), b.state.cpu().numpy()
+        # everything in the record except the parked Philox words and derived caches must match; compare field by field
+        for name, lo, hi in (("cpu", L.off_cpu, L.off_cpu + 8 * a.P), ("memory", L.off_memory, L.off_memory + 8 * a.P),
+                             ("remaining", L.off_remaining, L.off_remaining + 2 * a.V),
+                             ("placement", L.off_placement, L.off_placement + L.place_bytes * a.V),
+                             ("codes", L.off_cpu_code, L.off_cpu_code + a.V), ("mcodes", L.off_mem_code, L.off_mem_code + a.V),
+                             ("scalars", L.off_scalars, L.off_scalars + nv.SCALARS_BYTES)):
+            assert np.array_equal(ra[:, lo:hi], rb[:, lo:hi]), name
+        assert torch.equal(a.obs, b.obs) and torch.equal(a.reward, b.reward) and torch.equal(a.terminated_u8, b.terminated_u8)
+        assert int(a.counters()["timestep"].max()) > 31
+    finally:
+        nv.lib().vmgym_set_tuning(0, 7)

@@ -97,16 +97,18 @@ static int check_cuda(cudaError_t err, const char* what)
     return VMGYM_ECUDA;
 }
 
-static int g_sm_count = 0;
+// SM count of the CURRENT device (cached per device: one process may drive several)
 static int sm_count()
 {
-    if (g_sm_count == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sm_count <= 0) g_sm_count = 148;
+    static int counts[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& c = counts[dev & 63];
+    if (c == 0) {
+        cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev);
+        if (c <= 0) c = 148;
     }
-    return g_sm_count;
+    return c;
 }
 
 // warps per CTA: keep >= ~6 CTAs of work per SM when the batch is small (balance across the 148 SMs), up to 8
@@ -150,11 +152,13 @@ static int launch_step(StepParams& sp, cudaStream_t st)
         if (small_ok && !sorts && kl_fits) layout_scratch(sp.L, 2, true);
     }
     const DevLayout& L = sp.L;
+    // env indexes the warps share out: a rotation launch schedules one batch's worth, each warp then walks all the batches
+    const long long n_sched = sp.rot_batches > 0 ? sp.rot_envs : sp.n_envs;
     int w;
     if (team) {
         const long long one = (long long)L.sm_tables + L.sm_stride + 1024;                  // + the per-CTA reservation
         long long per_sm = (228 * 1024) / one;
-        const long long need = (sp.n_envs + sm_count() - 1) / sm_count();
+        const long long need = (n_sched + sm_count() - 1) / sm_count();
         if (per_sm > need) per_sm = need;
         if (per_sm < 1) per_sm = 1;
         static int team_regs = 0;
@@ -166,7 +170,7 @@ static int launch_step(StepParams& sp, cudaStream_t st)
         w = g_warps_per_cta > 0 ? g_warps_per_cta : (int)(48 / per_sm < by_regs ? 48 / per_sm : by_regs);
         w = w < 1 ? 1 : (w > 8 ? 8 : w);                                                    // compiled for <= 256 threads
     } else {
-        w = pick_warps(sp.n_envs, L.sm_stride, L.sm_tables);
+        w = pick_warps(n_sched, L.sm_stride, L.sm_tables);
     }
     // double-buffered records once a warp steps several envs per launch (more envs than ~1.4 x the resident warps) — for
     // small records only: measured +7.5 % at the 10-PM shape (2^20 envs), but -6 % at 100 PMs, where the second 3.4 KB
@@ -174,7 +178,7 @@ static int launch_step(StepParams& sp, cudaStream_t st)
     // Needs bulk loads + stores; use_bulk bit 4 switches it off, bit 5 forces it for any record size (A/B runs, tests).
     const int wstride_db = align_up(L.sm_stride + L.rec_bytes, 128);
     const bool db = !team && (sp.use_bulk & 3) == 3 && (sp.use_bulk & 16) == 0 && (L.rec_bytes <= 1024 || (sp.use_bulk & 32) != 0) &&
-                    sp.n_envs * 10 > (long long)sm_count() * 7 * w * 14 && (size_t)L.sm_tables + (size_t)w * wstride_db <= 227 * 1024;
+                    n_sched * (sp.rot_batches > 0 ? sp.rot_steps : 1) * 10 > (long long)sm_count() * 7 * w * 14 && (size_t)L.sm_tables + (size_t)w * wstride_db <= 227 * 1024;
     const size_t smem = (size_t)L.sm_tables + (size_t)(team ? 1 : w) * (db ? wstride_db : L.sm_stride);
     if (smem > 227 * 1024) return fail(VMGYM_EUNSUPPORTED, "env record does not fit in shared memory (pms/vms too large)");
     void (*kern)(const StepParams) = pick_db<PT, 0, 0, -1>(db);
@@ -218,7 +222,7 @@ static int launch_step(StepParams& sp, cudaStream_t st)
         plan_smem = smem; plan_w = w; plan_kern = kern; plan_dev = dev;
     }
     const int occ = plan_occ;
-    long long blocks = team ? sp.n_envs : (sp.n_envs + w - 1) / w;
+    long long blocks = team ? n_sched : (n_sched + w - 1) / w;
     const long long cap = (long long)sm_count() * occ;
     if (blocks > cap) blocks = cap;
     if (sp.use_bulk & 4) {
@@ -259,6 +263,7 @@ static int fill_params(StepParams* sp, const vmgym_config* cfg, void* d_state, i
     const int n_vm = (sp->out.d_vm_slots != nullptr) + (sp->out.d_vm_hist != nullptr) + (sp->out.d_vm_totals != nullptr);
     if (n_vm != 0 && n_vm != 3) return fail(VMGYM_EINVAL, "d_vm_slots / d_vm_hist / d_vm_totals must be all set or all NULL");
     sp->action = nullptr; sp->action_dtype = VMGYM_U8; sp->use_bulk = 1; sp->agent = VMGYM_AGENT_NONE; sp->tiebreak = 0; sp->n_steps = 1;
+    sp->rot_batches = 0; sp->rot_steps = 0; sp->rot_first = 0; sp->rot_envs = 0;
     return VMGYM_OK;
 }
 
@@ -329,6 +334,26 @@ int vmgym_agent_step(const vmgym_config* cfg, void* d_state, int64_t n_envs, con
     if (n_steps < 1) return fail(VMGYM_EINVAL, "n_steps must be >= 1");
     if (n_envs == 0) return VMGYM_OK;
     sp.agent = agent; sp.tiebreak = tiebreak; sp.n_steps = n_steps;
+    cudaStream_t st = (cudaStream_t)stream;
+    return sp.L.P <= 253 ? launch_step<uint8_t>(sp, st) : launch_step<uint16_t>(sp, st);
+}
+
+int vmgym_agent_step_rotation(const vmgym_config* cfg, void* d_state, int64_t envs_per_batch, int32_t n_batches, int32_t first_batch,
+                              int32_t n_batch_steps, const vmgym_trace* trace, int agent, int tiebreak, int n_steps,
+                              const vmgym_outputs* out, void* stream)
+{
+    if (n_batches < 1 || n_batch_steps < 0 || first_batch < 0 || first_batch >= n_batches || envs_per_batch < 0)
+        return fail(VMGYM_EINVAL, "rotation: need n_batches >= 1, 0 <= first_batch < n_batches, n_batch_steps >= 0");
+    StepParams sp;
+    int rc = fill_params(&sp, cfg, d_state, envs_per_batch * n_batches, trace, out);
+    if (rc) return rc;
+    if (agent != VMGYM_AGENT_FIRSTFIT && agent != VMGYM_AGENT_BESTFIT)
+        return fail(VMGYM_EUNSUPPORTED, "fused agent must be firstfit or bestfit");
+    if (tiebreak != VMGYM_TIE_STABLE && tiebreak != VMGYM_TIE_NUMPY_INTROSORT) return fail(VMGYM_EINVAL, "unknown tiebreak");
+    if (n_steps < 1) return fail(VMGYM_EINVAL, "n_steps must be >= 1");
+    if (envs_per_batch == 0 || n_batch_steps == 0) return VMGYM_OK;
+    sp.agent = agent; sp.tiebreak = tiebreak; sp.n_steps = n_steps;
+    sp.rot_batches = n_batches; sp.rot_steps = n_batch_steps; sp.rot_first = first_batch; sp.rot_envs = envs_per_batch;
     cudaStream_t st = (cudaStream_t)stream;
     return sp.L.P <= 253 ? launch_step<uint8_t>(sp, st) : launch_step<uint16_t>(sp, st);
 }

@@ -27,6 +27,12 @@ struct StepParams {
     int agent, tiebreak, n_steps;
     int use_bulk;             // bit 0: load records with cp.async.bulk, bit 1: store them with cp.async.bulk (else 128-bit ld/st),
                               // bit 2: programmatic dependent launch, bit 3: team mode builds the fit table with the main warp alone (A/B)
+    // Rotation (rot_batches > 0): the state holds rot_batches batches of rot_envs envs each, back to back, and ONE launch executes
+    // rot_steps consecutive "batch steps": batch step k advances every env of batch (rot_first + k) % rot_batches by n_steps.
+    // A warp owns env index i of EVERY batch, so the steps of one record are always taken by the same warp, in order, and no
+    // warp ever waits for another: the grid stays resident across what would otherwise be rot_steps dependent launches.
+    int rot_batches, rot_steps, rot_first;
+    long long rot_envs;
 };
 
 constexpr uint32_t STATUS_EXHAUSTED = 1u;   // pre-sampled trace ran out (the reference would raise, env.py:282)
@@ -1258,6 +1264,13 @@ __global__ void __launch_bounds__(TM ? 256 : 896, TM ? 3 : 1) step_kernel(const 
     const bool BULK = DB || (p.use_bulk & 1) != 0, BULK_ST = DB || (p.use_bulk & 2) != 0;
     const long long stride = (long long)gridDim.x * wpc;
     const long long env0 = (long long)blockIdx.x * wpc + warp;
+    // the warp's work list.  Plain launches walk env0, env0 + stride, ...; a rotation launch takes the rot_steps batch steps of
+    // each env index it owns (batch rot_first, rot_first + 1, ... modulo rot_batches) before moving on to the next index
+    const bool ROT = p.rot_batches > 0;
+    const long long n_idx = ROT ? p.rot_envs : p.n_envs;
+    const int per_idx = ROT ? p.rot_steps : 1;
+    const bool any_item = env0 < n_idx && per_idx > 0;
+    const long long first_env = env0 + (ROT ? (long long)p.rot_first * p.rot_envs : 0ll);
     // Programmatic dependent launch (use_bulk bit 2): let the NEXT kernel of the stream start launching right away (its CTAs
     // take the slots this grid frees as its fast CTAs finish) ...
     const bool PDL = (p.use_bulk & 4) != 0;
@@ -1269,9 +1282,9 @@ __global__ void __launch_bounds__(TM ? 256 : 896, TM ? 3 : 1) step_kernel(const 
         mbar_init(bar, 1);
         if (DB) mbar_init(bar + 1, 1);
         fence_barrier_init();
-        if (!PDL && env0 < p.n_envs) {
+        if (!PDL && any_item) {
             mbar_arrive_expect_tx(bar, (uint32_t)L.rec_bytes);
-            bulk_g2s(base, p.state + env0 * (long long)L.rec_bytes, (uint32_t)L.rec_bytes, bar);
+            bulk_g2s(base, p.state + first_env * (long long)L.rec_bytes, (uint32_t)L.rec_bytes, bar);
         }
     }
     const bool philox = (MODE_CT >= 0 ? MODE_CT : p.tr.mode) == VMGYM_TRACE_PHILOX;
@@ -1297,9 +1310,9 @@ __global__ void __launch_bounds__(TM ? 256 : 896, TM ? 3 : 1) step_kernel(const 
     if (PDL) {
         // ... and wait here, tables built, for the previous grid to complete and flush before touching any record / output
         asm volatile("griddepcontrol.wait;" ::: "memory");
-        if (BULK && lane == 0 && !helper && env0 < p.n_envs) {
+        if (BULK && lane == 0 && !helper && any_item) {
             mbar_arrive_expect_tx(bar, (uint32_t)L.rec_bytes);
-            bulk_g2s(base, p.state + env0 * (long long)L.rec_bytes, (uint32_t)L.rec_bytes, bar);
+            bulk_g2s(base, p.state + first_env * (long long)L.rec_bytes, (uint32_t)L.rec_bytes, bar);
         }
     }
 
@@ -1312,22 +1325,29 @@ __global__ void __launch_bounds__(TM ? 256 : 896, TM ? 3 : 1) step_kernel(const 
     uint32_t phase = 0;
     if (helper) {
         // helper warps: wait for each record of this CTA, then serve the main warp's phases until it closes the env
-        for (long long env = env0; env < p.n_envs; env += stride) {
-            if (BULK) { mbar_wait(bar, phase); phase ^= 1; }
-            team_serve(e, (int)threadIdx.x, nth);
-        }
+        for (long long idx = env0; idx < n_idx; idx += stride)
+            for (int rk = 0; rk < per_idx; rk++) {
+                if (BULK) { mbar_wait(bar, phase); phase ^= 1; }
+                team_serve(e, (int)threadIdx.x, nth);
+            }
         return;
     }
     uint32_t phase1 = 0;
     int cur = 0;                             // DB: which record buffer holds the current env
-    for (long long env = env0; env < p.n_envs; env += stride) {
+    for (long long idx = env0; idx < n_idx; idx += stride)
+    for (int rk = 0, rb = ROT ? p.rot_first : 0; rk < per_idx; rk++, rb = (rb + 1 == p.rot_batches) ? 0 : rb + 1) {
+        const long long env = ROT ? (long long)rb * p.rot_envs + idx : idx;
+        const bool first_item = idx == env0 && rk == 0;
         unsigned char* grec = p.state + env * (long long)L.rec_bytes;
         // ---- stage the record into shared memory ----
         if (DB) {
             unsigned char* other = cur ? base : base + L.sm_stride;
             e.rec = cur ? base + L.sm_stride : base;
-            const long long nxt = env + stride;
-            if (lane == 0 && nxt < p.n_envs) {
+            // the next item of this warp: the same env index in the next batch of the rotation, else the next env index
+            const bool more_rot = rk + 1 < per_idx;
+            const long long nxt = more_rot ? (long long)((rb + 1 == p.rot_batches) ? 0 : rb + 1) * p.rot_envs + idx
+                                           : idx + stride + (ROT ? (long long)p.rot_first * p.rot_envs : 0ll);
+            if (lane == 0 && (more_rot || idx + stride < n_idx)) {
                 bulk_wait_read0();            // the other buffer's write-back (previous env) has left shared memory
                 mbar_arrive_expect_tx(bar + (cur ^ 1), (uint32_t)L.rec_bytes);
                 bulk_g2s(other, p.state + nxt * (long long)L.rec_bytes, (uint32_t)L.rec_bytes, bar + (cur ^ 1));
@@ -1335,7 +1355,7 @@ __global__ void __launch_bounds__(TM ? 256 : 896, TM ? 3 : 1) step_kernel(const 
             if (cur) { mbar_wait(bar + 1, phase1); phase1 ^= 1; }
             else { mbar_wait(bar, phase); phase ^= 1; }
         } else if (BULK) {
-            if (lane == 0 && env != env0) {
+            if (lane == 0 && !first_item) {
                 mbar_arrive_expect_tx(bar, (uint32_t)L.rec_bytes);
                 bulk_g2s(base, grec, (uint32_t)L.rec_bytes, bar);
             }

@@ -15,7 +15,7 @@ PKG_ROOT = os.path.dirname(_HERE)
 REPO_ROOT = os.path.dirname(PKG_ROOT)
 CSRC = os.path.join(PKG_ROOT, "csrc")
 LIB_PATH = os.path.join(_HERE, "libvmgym.so")
-SOURCES = ["vmgym_env.cu", "vmgym_policy.cu", "vmgym_gemm.cu"]
+SOURCES = ["vmgym_env.cu", "vmgym_policy.cu", "vmgym_gemm.cu", "vmgym_optim.cu"]
 # -fmad=false: the env kernels reproduce numpy's fp64/fp32 arithmetic exactly, so no FMA contraction anywhere
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -67,9 +67,9 @@ SCALARS_I32 = ["timestep", "total_requests", "served_requests", "dropped_request
 SCALARS_BYTES = 80
 
 EXPORTS = ["vmgym_last_error", "vmgym_abi_version", "vmgym_get_layout", "vmgym_reset", "vmgym_step",
-           "vmgym_agent_step", "vmgym_agent_act", "vmgym_observe", "vmgym_invalid_action_mask", "vmgym_set_tuning",
+           "vmgym_agent_step", "vmgym_agent_step_rotation", "vmgym_agent_act", "vmgym_observe", "vmgym_invalid_action_mask", "vmgym_set_tuning",
            "vmgym_policy_heads", "vmgym_policy_heads_backward", "vmgym_gae", "vmgym_drlvmp_choice", "vmgym_drlvmp_iter", "vmgym_linear_bf16", "vmgym_policy_fused", "vmgym_segtree_update",
-           "vmgym_segtree_retrieve", "vmgym_vmstats_finalize", "vmgym_per_sample", "vmgym_c51_project"]
+           "vmgym_segtree_retrieve", "vmgym_vmstats_finalize", "vmgym_per_sample", "vmgym_c51_project", "vmgym_adamw_step"]
 
 
 class VmgymError(RuntimeError):
@@ -113,6 +113,8 @@ def lib():
     L.vmgym_reset.argtypes = [C.POINTER(Config), vp, i64, vp, vp, i32, vp, vp]
     L.vmgym_step.argtypes = [C.POINTER(Config), vp, i64, C.POINTER(Trace), vp, i32, C.POINTER(Outputs), vp]
     L.vmgym_agent_step.argtypes = [C.POINTER(Config), vp, i64, C.POINTER(Trace), i32, i32, i32, C.POINTER(Outputs), vp]
+    L.vmgym_agent_step_rotation.argtypes = [C.POINTER(Config), vp, i64, i32, i32, i32, C.POINTER(Trace), i32, i32, i32,
+                                            C.POINTER(Outputs), vp]
     L.vmgym_agent_act.argtypes = [C.POINTER(Config), i32, i32, vp, i64, vp, i32, vp]
     L.vmgym_observe.argtypes = [C.POINTER(Config), vp, i64, vp, vp]
     L.vmgym_invalid_action_mask.argtypes = [C.POINTER(Config), vp, i64, vp, vp]
@@ -133,6 +135,7 @@ def lib():
     L.vmgym_segtree_update.argtypes = [vp, vp, i64, vp, vp, C.c_int32, vp]
     L.vmgym_segtree_retrieve.argtypes = [vp, i64, vp, C.c_int32, vp, vp]
     L.vmgym_policy_fused.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, u64, u64, vp, vp, vp, vp]
+    L.vmgym_adamw_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, f32, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L

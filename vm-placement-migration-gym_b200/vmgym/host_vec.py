@@ -50,6 +50,7 @@ class HostVecEnv:
         base = np.asarray(seeds, dtype=np.int64) if seeds is not None else config.seed + np.arange(num_envs, dtype=np.int64)
         if base.shape != (num_envs,):
             raise ValueError("seeds must have shape (num_envs,)")
+        self._seeds0 = base.copy()
         bounds = np.linspace(0, num_envs, groups + 1).astype(np.int64)
         self.groups: list[_Group] = []
         for gi in range(groups):
@@ -163,10 +164,11 @@ class HostVecEnv:
             g.vec.eval(eval_mode)
 
     def reset(self, seed=None):
-        """Resets every env (seeds as given at construction, or `seed` + global env index); returns the pinned obs."""
+        """Resets every env and returns the pinned obs.  `seed` None: the seeds given at construction (the episode of the
+        construction-time reset starts again); an int: `seed` + global env index."""
         for g in self.groups:
             with torch.cuda.device(self.device), torch.cuda.stream(g.stream):
-                s = None if seed is None else int(seed) + np.arange(g.lo, g.hi, dtype=np.int64)
+                s = self._seeds0[g.lo:g.hi] if seed is None else int(seed) + np.arange(g.lo, g.hi, dtype=np.int64)
                 obs, _ = g.vec.reset(seed=s)
                 self.obs[g.lo:g.hi].copy_(obs, non_blocking=True)
                 g.ev_step.record(g.stream)

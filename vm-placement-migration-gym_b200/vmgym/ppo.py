@@ -223,13 +223,51 @@ class PPOAgent(AgentBase):
         self.device = vec.device
         self.obs_dim, self.V, self.A = vec.obs_dim, vec.V, vec.action_dim
         self.model = Network(self.obs_dim, self.V, self.A, self.config.hidden_size).to(self.device)
-        self.optimizer = torch.optim.AdamW(self.model.parameters(), lr=self.config.lr, fused=self.device.type == "cuda")
+        self._flatten_parameters()
         self.mask_words = (self.A + 31) // 32
         self.seed = int(vec.config.seed if seed is None else seed)
         self._calls = 0
         self._fused = None
         self.total_steps = 0
         self.training = True
+        self.data_parallel = True      # use the initialised torch.distributed group (one rank per GPU) in update() / episode_seeds()
+
+    # ---- optimiser state: AdamW(lr) of ppo.py:143 on flat buffers (vmgym_adamw_step) ----------------------------
+    def _flatten_parameters(self):
+        """Every parameter becomes a view of ONE flat fp32 buffer and every gradient a view of a second one, so the
+        data-parallel all-reduce, the gradient-norm clip and the AdamW step each run once over contiguous memory (no
+        concatenate / copy-back).  load_state_dict copies in place, so the views survive it."""
+        params = list(self.model.parameters())
+        n = sum(p.numel() for p in params)
+        n_pad = (n + 3) // 4 * 4
+        dev = self.device
+        self._flat = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        self._flat_grad = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        off = 0
+        for p in params:
+            k = p.numel()
+            self._flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self._flat[off:off + k].view_as(p)
+            p.grad = self._flat_grad[off:off + k].view_as(p)
+            off += k
+        self._n_params = n
+        self._exp_avg = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        self._exp_avg_sq = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        self._opt_step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._opt_ws = torch.zeros(1024, dtype=torch.float64, device=dev)
+        self._opt_skip = torch.zeros(1, dtype=torch.int32, device=dev)           # sticky within an epoch (KL early stop)
+        self._grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.adam = dict(beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01)    # torch.optim.AdamW defaults (ppo.py:143)
+
+    def _optim_step(self, grad_scale: float = 1.0):
+        """clip_grad_norm_(max_grad_norm) + AdamW step (ppo.py:284-287) unless the device-side skip flag is set."""
+        cfg, a = self.config, self.adam
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        nv.check(nv.lib().vmgym_adamw_step(self._flat.data_ptr(), self._flat_grad.data_ptr(), self._exp_avg.data_ptr(),
+                                           self._exp_avg_sq.data_ptr(), self._n_params, float(cfg.lr), a["beta1"], a["beta2"], a["eps"],
+                                           a["weight_decay"], float(cfg.max_grad_norm or 0.0), float(grad_scale),
+                                           self._opt_ws.data_ptr(), self._opt_skip.data_ptr(), self._opt_step.data_ptr(),
+                                           self._grad_norm.data_ptr(), stream), "vmgym_adamw_step")
 
     # ---- reference API -------------------------------------------------------------------------------------
     def eval(self, mode=True):
@@ -328,28 +366,56 @@ class PPOAgent(AgentBase):
         return ret
 
     # ---- training ------------------------------------------------------------------------------------------
-    def learn(self, episodes: int | None = None, max_updates: int | None = None):
-        """ppo.py:172-226 with N envs stepping in lock-step: every `batch_size` steps one `update` on the [T, N] rollout.
-        Runs `episodes` episodes of `training_steps` steps (the reference's loop bound is a known slip)."""
+    def episode_seeds(self, ep: int):
+        """Seeds of episode `ep`.  One env: `config.seed + ep`, the reference's (ppo.py:192).  A batch: env g (global id =
+        construction seed - config.seed, so shards of a multi-GPU job stay distinct) gets `config.seed + 4 (ep * n_global + g)`:
+        the reference's four generators sit at seed .. seed + 3 (env.py:175-178), so a stride of 4 keeps every stream of every
+        env and episode disjoint (consecutive seeds would replay env i+1's arrival trace in env i one episode later, and alias
+        env i's memory-size stream with env i+1's cpu-size stream)."""
+        vec = self.vec
+        base = int(vec.config.seed)
+        world = torch.distributed.get_world_size() if self.data_parallel and torch.distributed.is_available() and \
+            torch.distributed.is_initialized() else 1
+        n_global = vec.num_envs * world
+        if n_global == 1:
+            return np.asarray([base + ep], np.int64)
+        gid = getattr(self, "_env_ids", None)
+        if gid is None:
+            s0 = np.asarray(vec._seeds, np.int64) if vec._seeds is not None else base + np.arange(vec.num_envs, dtype=np.int64)
+            gid = self._env_ids = s0 - base
+        return base + 4 * (ep * n_global + gid)
+
+    def learn(self, episodes: int | None = None, max_updates: int | None = None, reset: bool = True):
+        """ppo.py:172-226 with N envs stepping in lock-step: every `batch_size` steps one `update` on the [T, N] rollout; the
+        rollout cursor and buffers persist across episodes like the reference's `i_batch` (ppo.py:181,209-214).
+        Runs `episodes` episodes of `training_steps` steps (the reference's loop bound is a known slip).
+        `reset=False` continues from the envs' current state instead of resetting at the start of each episode (benchmarks)."""
         cfg, vec = self.config, self.vec
         T, N = cfg.batch_size, vec.num_envs
         dev = self.device
-        buf = dict(
-            obs=torch.empty((T, N, self.obs_dim), dtype=torch.float32, device=dev),
-            next_obs=torch.empty((T, N, self.obs_dim), dtype=torch.float32, device=dev),
-            action=torch.empty((T, N, self.V), dtype=vec.place_dtype, device=dev),
-            mask=torch.empty((T, N, self.V, self.mask_words), dtype=torch.int32, device=dev),
-            logprob=torch.empty((T, N), dtype=torch.float32, device=dev),
-            reward=torch.empty((T, N), dtype=torch.float32, device=dev),
-            done=torch.empty((T, N), dtype=torch.uint8, device=dev))
+        buf = getattr(self, "_rollout", None)
+        if buf is None or buf["reward"].shape != (T, N):
+            buf = self._rollout = dict(
+                obs=torch.empty((T, N, self.obs_dim), dtype=torch.float32, device=dev),
+                next_obs=torch.empty((T, N, self.obs_dim), dtype=torch.float32, device=dev),
+                action=torch.empty((T, N, self.V), dtype=vec.place_dtype, device=dev),
+                mask=torch.empty((T, N, self.V, self.mask_words), dtype=torch.int32, device=dev),
+                logprob=torch.empty((T, N), dtype=torch.float32, device=dev),
+                reward=torch.empty((T, N), dtype=torch.float32, device=dev),
+                done=torch.empty((T, N), dtype=torch.uint8, device=dev))
+            self._cursor = 0
         returns, updates = [], 0
         vec.eval(False)
         for ep in range(int(cfg.episodes if episodes is None else episodes)):
-            obs, _ = vec.reset(seed=int(vec.config.seed) + ep)        # ppo.py:192
+            if reset:
+                obs, _ = vec.reset(seed=self.episode_seeds(ep))      # ppo.py:192
+            else:
+                obs = vec.observe()
             obs = obs.clone()
             ep_ret = torch.zeros(N, dtype=torch.float64, device=dev)
-            done, i = False, 0
+            done = False
             while not done:
+                i = self._cursor
                 with torch.no_grad():
                     if cfg.fused_rollout:
                         action, logprob, _, mask = self.fused_sample(obs, -1.0)
@@ -361,101 +427,134 @@ class PPOAgent(AgentBase):
                 buf["logprob"][i], buf["reward"][i], buf["done"][i] = logprob, reward.float(), vec.terminated_u8
                 ep_ret += reward
                 obs = nobs.clone()
-                i += 1
+                self._cursor += 1
                 self.total_steps += 1
                 done = bool(term[0].item())                           # all envs share the step limit
-                if i >= T:
+                if self._cursor >= T:
                     self.update(**buf)
                     if self._fused is not None:
                         self._fused.refresh()
-                    i = 0
+                    self._cursor = 0
                     updates += 1
                     if max_updates is not None and updates >= max_updates:
                         return returns
             returns.append(ep_ret.mean().item())
         return returns
 
+    def _minibatch_backward(self, obs_mb, act_mb, mask_mb, lp_mb, adv_mb, val_mb, ret_mb, n_total: int):
+        """Forward + backward of one minibatch (ppo.py:255-285) in chunks of `env_chunk` samples, gradients accumulated into the
+        flat gradient buffer.  `adv_mb` is already normalised; `n_total` = samples of the minibatch over ALL ranks (the means of
+        ppo.py:269,277,282 are over the global minibatch).  Returns (sum of log-ratios, loss) as device scalars (this rank's part)."""
+        cfg = self.config
+        ccfg = self.vec._ccfg()
+        n_mb = obs_mb.shape[0]
+        self._flat_grad.zero_()
+        logratio_sum = torch.zeros((), dtype=torch.float64, device=self.device)
+        loss_sum = torch.zeros((), dtype=torch.float64, device=self.device)
+        if cfg.vf_broadcast and n_mb > cfg.env_chunk:
+            raise nv.VmgymError("vf_broadcast needs the whole minibatch in one chunk (samples <= env_chunk)")
+        out = self.model.actor[4]
+        for s0 in range(0, n_mb, cfg.env_chunk):
+            s1 = min(n_mb, s0 + cfg.env_chunk)
+            o = obs_mb[s0:s1]
+            lg = _OutLinear.apply(self.model.actor[:4](o), out.weight, out.bias)
+            nlp, ent = _MaskedHeads.apply(lg, mask_mb[s0:s1], act_mb[s0:s1], ccfg, cfg.masked)
+            logratio = nlp - lp_mb[s0:s1]
+            logratio_sum += logratio.detach().double().sum()
+            ratios = torch.exp(logratio)
+            a = adv_mb[s0:s1]
+            loss_clipped = torch.max(-ratios * a, -torch.clamp(ratios, 1 - cfg.eps_clip, 1 + cfg.eps_clip) * a).sum()
+            newv = self.model.get_value(o).flatten()
+            v_old, ret = val_mb[s0:s1], ret_mb[s0:s1]
+            if cfg.vf_broadcast:
+                # ppo.py:272-277 as written: newvalues is [mb, 1], returns[minibatch] is [mb] -> [mb, mb] pairs, mean;
+                # (i, j) pairs new value i against old value j / return j
+                nv2 = newv[:, None]
+                l_un = torch.square(nv2 - ret)
+                l_cl = torch.square(v_old + torch.clamp(nv2 - v_old, -cfg.eps_clip, cfg.eps_clip) - ret)
+                loss_vf = 0.5 * (torch.max(l_un, l_cl) if cfg.vf_loss_clip else l_un).sum() / n_mb
+            else:
+                l_un = torch.square(newv - ret)
+                l_cl = torch.square(v_old + torch.clamp(newv - v_old, -cfg.eps_clip, cfg.eps_clip) - ret)
+                loss_vf = 0.5 * (torch.max(l_un, l_cl) if cfg.vf_loss_clip else l_un).sum()
+            loss = (loss_clipped - cfg.ent_coef * ent.sum() + cfg.vf_coef * loss_vf) / n_total
+            loss_sum += loss.detach().double()
+            loss.backward()
+        return logratio_sum, loss_sum
+
+    def _normalise_advantages(self, adv, world: int):
+        """ppo.py:255-256 over the GLOBAL minibatch: (adv - mean) / (unbiased std + 1e-10).  With several ranks the three
+        sums (n, sum, sum of squares) are all-reduced, so k GPUs x N/k envs normalise exactly like one GPU x N envs."""
+        if world == 1:
+            return ((adv - adv.mean()) / (adv.std() + 1e-10)).reshape(-1)
+        a64 = adv.double()
+        st = torch.stack([torch.tensor(float(adv.numel()), dtype=torch.float64, device=adv.device), a64.sum(), (a64 * a64).sum()])
+        torch.distributed.all_reduce(st)
+        n, mean = st[0], st[1] / st[0]
+        var = (st[2] - n * mean * mean) / (n - 1.0)
+        return ((a64 - mean) / (var.clamp_min(0.0).sqrt() + 1e-10)).float().reshape(-1)
+
     def update(self, obs, next_obs, action, mask, logprob, reward, done, debug: bool = False):
-        """ppo.py:229-295 on a time-major rollout [T, N, ...].  `debug`: also return what the update computed on the way
-        (values, advantages, returns, and per attempted minibatch: KL, loss, pre-clip gradient norm, stepped) — host syncs."""
-        cfg, vec = self.config, self.vec
+        """ppo.py:229-295 on a time-major rollout [T, N, ...].  The minibatch loop enqueues without host synchronisation: the KL
+        early stop (ppo.py:263-264) is a device-side flag that turns the optimiser step of the offending minibatch — and of the
+        rest of its epoch — into a no-op; the host reads the flag one minibatch late (it is already known by then) and stops
+        enqueuing the epoch.  `debug`: also return what the update computed on the way (values, advantages, returns, and per
+        attempted minibatch: KL, loss, pre-clip gradient norm, stepped) — with a host synchronisation per minibatch."""
+        cfg = self.config
         T, N = reward.shape
+        dist = torch.distributed
+        world = dist.get_world_size() if self.data_parallel and dist.is_available() and dist.is_initialized() else 1
         with torch.no_grad():
             values = self.model.get_value(obs.reshape(T * N, -1)).reshape(T, N)
             next_values = self.model.get_value(next_obs.reshape(T * N, -1)).reshape(T, N)
             advantages, returns = gae(reward, values, next_values, done, cfg.gamma, cfg.lamda)
-        ccfg = vec._ccfg()
-        world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
         stats = {}
         attempts = []
         D = obs.shape[-1]
+        flag_host = getattr(self, "_skip_host", None)
+        if flag_host is None and not debug:
+            flag_host = self._skip_host = torch.zeros(2, dtype=torch.int32).pin_memory()      # ping-pong: minibatch j -> slot j & 1
+            self._skip_events = [torch.cuda.Event(), torch.cuda.Event()]
+        kl_dev = torch.zeros((), dtype=torch.float64, device=self.device)
         for epoch in range(cfg.k_epochs):
-            for t0 in range(0, T, cfg.minibatch_size):                 # sequential minibatches (ppo.py:251-252)
+            self._opt_skip.zero_()
+            for j, t0 in enumerate(range(0, T, cfg.minibatch_size)):   # sequential minibatches (ppo.py:251-252)
+                if not debug and cfg.kl_max is not None and j >= 2:
+                    # the flag of minibatch j - 2 (minibatch j - 1 is still queued, so the device never runs dry on this wait)
+                    self._skip_events[j & 1].synchronize()
+                    if int(flag_host[j & 1]) != 0:
+                        break                                          # the KL stop fired: the rest of the epoch would be no-ops
                 t1 = min(T, t0 + cfg.minibatch_size)
-                adv_mb = advantages[t0:t1]
-                adv_mb = ((adv_mb - adv_mb.mean()) / (adv_mb.std() + 1e-10)).reshape(-1)      # unbiased std (ppo.py:256)
                 n_mb = (t1 - t0) * N
-                # the minibatch as one flat list of samples (time-major rollout -> these are views), processed in chunks of
-                # cfg.env_chunk samples with gradient accumulation; one forward per sample per minibatch
+                adv_mb = self._normalise_advantages(advantages[t0:t1], world)
+                # the minibatch as one flat list of samples (time-major rollout -> these are views)
                 obs_mb, act_mb = obs[t0:t1].reshape(n_mb, D), action[t0:t1].reshape(n_mb, self.V)
                 mask_mb = mask[t0:t1].reshape(n_mb, self.V, self.mask_words)
                 lp_mb, val_mb, ret_mb = logprob[t0:t1].reshape(-1), values[t0:t1].reshape(-1), returns[t0:t1].reshape(-1)
-                self.optimizer.zero_grad(set_to_none=True)
-                logratio_sum = torch.zeros((), dtype=torch.float64, device=self.device)
-                loss_sum = torch.zeros((), dtype=torch.float64, device=self.device)
-                if cfg.vf_broadcast and n_mb > cfg.env_chunk:
-                    raise nv.VmgymError("vf_broadcast needs the whole minibatch in one chunk (samples <= env_chunk)")
-                for s0 in range(0, n_mb, cfg.env_chunk):
-                    s1 = min(n_mb, s0 + cfg.env_chunk)
-                    o = obs_mb[s0:s1]
-                    out = self.model.actor[4]
-                    lg = _OutLinear.apply(self.model.actor[:4](o), out.weight, out.bias)
-                    nlp, ent = _MaskedHeads.apply(lg, mask_mb[s0:s1], act_mb[s0:s1], ccfg, cfg.masked)
-                    logratio = nlp - lp_mb[s0:s1]
-                    logratio_sum += logratio.detach().double().sum()
-                    ratios = torch.exp(logratio)
-                    a = adv_mb[s0:s1]
-                    loss_clipped = torch.max(-ratios * a, -torch.clamp(ratios, 1 - cfg.eps_clip, 1 + cfg.eps_clip) * a).sum()
-                    newv = self.model.get_value(o).flatten()
-                    v_old, ret = val_mb[s0:s1], ret_mb[s0:s1]
-                    if cfg.vf_broadcast:
-                        # ppo.py:272-277 as written: newvalues is [mb, 1], returns[minibatch] is [mb] -> [mb, mb] pairs, mean
-                        # (i, j) pairs new value i against old value j / return j
-                        nv2 = newv[:, None]
-                        l_un = torch.square(nv2 - ret)
-                        l_cl = torch.square(v_old + torch.clamp(nv2 - v_old, -cfg.eps_clip, cfg.eps_clip) - ret)
-                        loss_vf = 0.5 * (torch.max(l_un, l_cl) if cfg.vf_loss_clip else l_un).sum() / n_mb
-                    else:
-                        l_un = torch.square(newv - ret)
-                        l_cl = torch.square(v_old + torch.clamp(newv - v_old, -cfg.eps_clip, cfg.eps_clip) - ret)
-                        loss_vf = 0.5 * (torch.max(l_un, l_cl) if cfg.vf_loss_clip else l_un).sum()
-                    loss = (loss_clipped - cfg.ent_coef * ent.sum() + cfg.vf_coef * loss_vf) / n_mb   # means over the minibatch
-                    loss_sum += loss.detach().double()
-                    loss.backward()
-                # KL early stop on the whole minibatch (ppo.py:263-264): the reference breaks before its backward; here the
-                # accumulated gradients of this minibatch are dropped instead (same parameters afterwards)
-                kl = -(logratio_sum / n_mb)
+                logratio_sum, loss_sum = self._minibatch_backward(obs_mb, act_mb, mask_mb, lp_mb, adv_mb, val_mb, ret_mb, n_mb * world)
+                # KL early stop on the whole (global) minibatch (ppo.py:263-264): the reference breaks before its backward;
+                # here the step is skipped on the device instead (same parameters afterwards)
                 if world > 1:
-                    torch.distributed.all_reduce(kl)
-                    kl /= world
-                stats = {"kl": kl.item()}
+                    red = torch.stack([logratio_sum, loss_sum])
+                    dist.all_reduce(red)
+                    logratio_sum, loss_sum = red[0], red[1]
+                    dist.all_reduce(self._flat_grad)                   # data parallel: sum of the ranks' gradient parts (NCCL), in place
+                kl_dev = -(logratio_sum / (n_mb * world))
+                if cfg.kl_max is not None:
+                    self._opt_skip.logical_or_(kl_dev > cfg.kl_max)    # sticky until the end of the epoch
+                self._optim_step()
                 if debug:
-                    attempts.append(dict(epoch=epoch, mb=t0 // cfg.minibatch_size, kl=stats["kl"], loss=loss_sum.item(), stepped=0))
-                if cfg.kl_max is not None and stats["kl"] > cfg.kl_max:
-                    self.optimizer.zero_grad(set_to_none=True)
-                    break                                              # only the minibatch loop; the next epoch still runs
-                if world > 1:                                          # data parallel: average gradients over ranks (NCCL)
-                    flat = torch.cat([p.grad.flatten() for p in self.model.parameters()])
-                    torch.distributed.all_reduce(flat)
-                    flat /= world
-                    off = 0
-                    for p in self.model.parameters():
-                        p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                        off += p.numel()
-                gnorm = nn.utils.clip_grad_norm_(self.model.parameters(), cfg.max_grad_norm)
-                self.optimizer.step()
-                if debug:
-                    attempts[-1].update(stepped=1, grad_norm=float(gnorm))
+                    torch.cuda.synchronize(self.device)
+                    skipped = int(self._opt_skip.item()) != 0
+                    attempts.append(dict(epoch=epoch, mb=t0 // cfg.minibatch_size, kl=float(kl_dev.item()), loss=float(loss_sum.item()),
+                                         stepped=0 if skipped else 1, grad_norm=float(self._grad_norm.item())))
+                    if skipped:
+                        break
+                elif cfg.kl_max is not None:
+                    flag_host[j & 1:(j & 1) + 1].copy_(self._opt_skip, non_blocking=True)
+                    self._skip_events[j & 1].record(torch.cuda.current_stream(self.device))
+        stats["kl"] = kl_dev                                           # device scalar of the last minibatch (no sync here)
         if debug:
-            stats.update(values=values, next_values=next_values, advantages=advantages, returns=returns, attempts=attempts)
+            stats.update(kl=float(kl_dev.item()), values=values, next_values=next_values, advantages=advantages, returns=returns,
+                         attempts=attempts)
         return stats

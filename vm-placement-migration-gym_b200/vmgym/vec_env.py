@@ -179,6 +179,15 @@ class VecVmEnv:
     # ------------------------------------------------------------------------------------------------
     def eval(self, eval_mode: bool = True):
         self.eval_mode = bool(eval_mode)
+        # pre-sampled traces cover the step limit of the mode they were drawn in (reset): a longer limit needs a reset
+        if self.rng_mode == "numpy" and self._trace is not None and self._trace_steps is None:
+            limit = int(self.config.eval_steps) if self.eval_mode else int(self.config.training_steps)
+            self._trace_short = limit > int(self._trace.arrivals_len)
+
+    def _check_trace(self):
+        if getattr(self, "_trace_short", False):
+            raise nv.VmgymError("eval() raised the step limit beyond the pre-sampled trace: call reset() (as Base.test does, "
+                                "base.py:65-67), or construct with trace_steps=..., or use rng='philox'")
 
     def seed(self, seed=None):
         """env.py:172-178 — (re)create the four generators of every env at seed_i .. seed_i+3."""
@@ -204,7 +213,10 @@ class VecVmEnv:
                     pos = self._scalars_i32[:, 6:8].cpu().numpy().astype(np.int64)
                     for i, (s, (a, j)) in enumerate(zip(self._streams, pos)):
                         s.rewind_to(self.env_configs[i] if self.env_configs else self.config, a, j)
-                T = self._trace_steps or max(int(self.config.training_steps), int(self.config.eval_steps))
+                # one arrival draw per step of the episode: the active mode's step limit (the size sequences keep the
+                # reference's 2 * max(training_steps, eval_steps) draws per generator, env.py:210-219)
+                T = self._trace_steps or (int(self.config.eval_steps) if self.eval_mode else int(self.config.training_steps))
+                self._trace_short = False
                 arr, adm = sample_numpy_traces(self.env_configs or self.config, self._streams, T, self._max_admissions)
                 d_arr = torch.from_numpy(arr.view(np.int16)).to(self.device)
                 d_adm = torch.from_numpy(adm.view(np.int32)).to(self.device)
@@ -238,21 +250,32 @@ class VecVmEnv:
                                            self.obs.data_ptr(), self._stream()), "vmgym_reset")
         return self.obs, {}
 
-    def _outputs(self, want_action=False, want_stats=False, want_obs=True, want_valid=True) -> nv.Outputs:
-        key = (want_action, want_stats, want_obs, want_valid)
+    def _outputs(self, want_action=False, want_stats=False, want_obs=True, want_valid=True, lo: int = 0) -> nv.Outputs:
+        """Output pointers of a launch over the envs [lo, ...): every per-env buffer offset to row `lo`."""
+        key = (want_action, want_stats, want_obs, want_valid, lo)
         out = self._out_cache.get(key)
         if out is None:
-            out = nv.Outputs(d_obs=self.obs.data_ptr() if want_obs else None, d_reward=self.reward.data_ptr(),
-                             d_terminated=self.terminated_u8.data_ptr(),
-                             d_valid=self.valid.data_ptr() if want_valid else None,
-                             d_action=self.agent_action.data_ptr() if want_action else None,
-                             d_stats=self.stats.data_ptr() if want_stats else None,
-                             d_vm_slots=self._vm_slots.data_ptr() if self._vm_slots is not None else None,
-                             d_vm_hist=self._vm_hist.data_ptr() if self._vm_slots is not None else None,
-                             d_vm_totals=self._vm_totals.data_ptr() if self._vm_slots is not None else None,
+            vm = self._vm_slots is not None
+            out = nv.Outputs(d_obs=self.obs[lo:].data_ptr() if want_obs else None, d_reward=self.reward[lo:].data_ptr(),
+                             d_terminated=self.terminated_u8[lo:].data_ptr(),
+                             d_valid=self.valid[lo:].data_ptr() if want_valid else None,
+                             d_action=self.agent_action[lo:].data_ptr() if want_action else None,
+                             d_stats=self.stats[lo:].data_ptr() if want_stats else None,
+                             d_vm_slots=self._vm_slots[lo:].data_ptr() if vm else None,
+                             d_vm_hist=self._vm_hist[lo:].data_ptr() if vm else None,
+                             d_vm_totals=self._vm_totals[lo:].data_ptr() if vm else None,
                              obs_persistent=1)          # self.obs is this env's own buffer: unchanged envs keep their rows
             self._out_cache[key] = out
         return out
+
+    def _trace_at(self, lo: int):
+        """The trace descriptor for a launch over the envs [lo, ...): pre-sampled rows are per env, Philox tables are shared."""
+        if lo == 0 or self.rng_mode != "numpy":
+            return self._trace
+        t = nv.Trace.from_buffer_copy(self._trace)
+        d_arr, d_adm = self._trace_tensors
+        t.d_arrivals, t.d_admissions = d_arr[lo:].data_ptr(), d_adm[lo:].data_ptr()
+        return t
 
     def step(self, action, want_obs: bool = True, want_valid: bool = True, host_outputs=None, want_stats: bool = False,
              obs_mirror=None):
@@ -271,6 +294,7 @@ class VecVmEnv:
         if action.dtype not in _TORCH_ACTION_DTYPES:
             action = action.to(torch.int64)
         action = action.contiguous()
+        self._check_trace()
         out = self._outputs(want_obs=want_obs, want_valid=want_valid, want_stats=want_stats)
         if host_outputs is not None:
             rew_h, term_h = host_outputs
@@ -296,16 +320,41 @@ class VecVmEnv:
         return self.obs, self.reward, self.terminated, self.truncated, {"action": action, "valid": self.valid}
 
     def agent_step(self, agent: str, n_steps: int = 1, want_obs: bool = True, want_action: bool = True,
-                   want_stats: bool = False, want_valid: bool = True, tiebreak: str | None = None):
+                   want_stats: bool = False, want_valid: bool = True, tiebreak: str | None = None, envs: tuple | None = None):
         """Fused heuristic agent.act + env.step, `n_steps` per launch (firstfit.py:21-38 / bestfit.py:21-40 +
-        env.py:66-103).  Returns (obs, reward, terminated) of the last executed step."""
+        env.py:66-103).  `envs=(lo, hi)` restricts the launch to that contiguous range of envs (the others are untouched).
+        Returns (obs, reward, terminated) of the last executed step."""
         kind = {"firstfit": nv.AGENT_FIRSTFIT, "bestfit": nv.AGENT_BESTFIT}[agent]
-        out = self._outputs(want_action=want_action, want_stats=want_stats, want_obs=want_obs, want_valid=want_valid)
+        self._check_trace()
+        lo, hi = (0, self.num_envs) if envs is None else (int(envs[0]), int(envs[1]))
+        if not 0 <= lo <= hi <= self.num_envs:
+            raise ValueError("envs must be a range inside [0, num_envs]")
+        out = self._outputs(want_action=want_action, want_stats=want_stats, want_obs=want_obs, want_valid=want_valid, lo=lo)
+        trace = self._trace_at(lo)
         with self._on_device():
-            nv.check(self._lib.vmgym_agent_step(C.byref(self._ccfg()), self.state.data_ptr(), self.num_envs,
-                                                C.byref(self._trace), kind, nv.TIE_IDS[tiebreak or self.tiebreak],
+            nv.check(self._lib.vmgym_agent_step(C.byref(self._ccfg()), self.state[lo:].data_ptr(), hi - lo,
+                                                C.byref(trace), kind, nv.TIE_IDS[tiebreak or self.tiebreak],
                                                 int(n_steps), C.byref(out), self._stream()), "vmgym_agent_step")
         return self.obs, self.reward, self.terminated
+
+    def agent_step_rotation(self, agent: str, batch_envs: int, batch_steps: int, first_batch: int = 0, n_steps: int = 1,
+                            want_obs: bool = True, want_action: bool = False, want_stats: bool = False, want_valid: bool = False,
+                            tiebreak: str | None = None):
+        """The env batch seen as num_envs / batch_envs independent sub-batches (e.g. the seeds or load points of a sweep,
+        exp_performance.py:63-83): ONE persistent launch runs `batch_steps` consecutive batch steps, batch step k advancing
+        sub-batch (first_batch + k) % n_batches by `n_steps` fused act + env.step.  Same results as calling agent_step on
+        the sub-batches in rotation, without a launch boundary per step.  Returns the index of the next sub-batch in turn."""
+        kind = {"firstfit": nv.AGENT_FIRSTFIT, "bestfit": nv.AGENT_BESTFIT}[agent]
+        if batch_envs < 1 or self.num_envs % batch_envs:
+            raise ValueError("batch_envs must divide num_envs")
+        nb = self.num_envs // batch_envs
+        out = self._outputs(want_action=want_action, want_stats=want_stats, want_obs=want_obs, want_valid=want_valid)
+        with self._on_device():
+            nv.check(self._lib.vmgym_agent_step_rotation(C.byref(self._ccfg()), self.state.data_ptr(), int(batch_envs), nb,
+                                                         int(first_batch) % nb, int(batch_steps), C.byref(self._trace), kind,
+                                                         nv.TIE_IDS[tiebreak or self.tiebreak], int(n_steps), C.byref(out),
+                                                         self._stream()), "vmgym_agent_step_rotation")
+        return (int(first_batch) + int(batch_steps)) % nb
 
     def evaluate(self, agent: str, seeds=None, chunk: int = 1000, tiebreak: str | None = None):
         """Base.test (src/agents/base.py:63-124) for a fused heuristic agent, entirely on the device: eval mode,
