@@ -663,13 +663,20 @@ def test_bench_gpu_arm_prints_the_contract_line():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "6", "--warmup", "3", "--no-cpu", "--no-extras",
-                          "--batches", "4", "--envs", "512"], capture_output=True, text=True, timeout=600, cwd=root)
+                          "--batches", "4", "--envs", "512", "--replays", "5"], capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
     d = json.loads(out.stdout.strip().splitlines()[-1])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
               "data", "config", "gpu_launches", "e2e", "roofline", "clocks"):
         assert k in d, k
-    assert d["steps"] == 6 and d["warmup"] == 3 and d["gpu_launches"] == 6 and d["n_gpus"] == 1 and d["value"] > 0
+    # gpu_launches: the timed region is 5 replays of ONE persistent launch of 6 batch steps (vmgym_agent_step_rotation)
+    assert d["steps"] == 6 and d["warmup"] == 3 and d["gpu_launches"] == 5 and d["n_gpus"] == 1 and d["value"] > 0
+    ts = d["timing_stats"]
+    assert ts["replays"] == 5 and ts["steps_per_replay"] == 6 and ts["p10_ms"] <= ts["median_ms"] <= ts["p90_ms"]
+    assert abs(d["ms_per_step"] - ts["median_ms"] / 6) < 1e-12
+    r = d["roofline"]
+    assert r["B_fused"] == 2 * (16 * 100 + 5 * 300 + 48) + 16 and 0.0 <= r["obs_rows_stored_frac"] <= 1.0
+    assert abs(r["bytes_per_env_step"] - (r["B_fused"] + r["obs_bytes_stored_per_env_step"])) < 1e-6
     assert d["unit"] == "env-steps/s" and d["dtype"] == "f64" and d["scaling"] == "weak" and d["vs_baseline"] is None
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"]) and d["roofline"]["bound"] == "hbm"

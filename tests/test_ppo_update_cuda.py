@@ -138,7 +138,9 @@ def test_update_default_value_loss_is_the_elementwise_form():
             # restate the elementwise loss of the first minibatch from the reference's own values / returns
             v, r = fx["values"][:25].astype(np.float64), fx["returns"][:25].astype(np.float64)
             vf = 0.5 * np.mean((v - r) ** 2)            # newvalues == values before the first step; clipped form equals it
-            vf_b = 0.5 * np.mean((v[:, None] - r[None, :]) ** 2)
+            un_b = (v[:, None] - r[None, :]) ** 2            # ppo.py:273: [mb, 1] - [mb] pairs every new value with every return
+            cl_b = (v[None, :] + np.clip(v[:, None] - v[None, :], -0.1, 0.1) - r[None, :]) ** 2      # ppo.py:274-275
+            vf_b = 0.5 * np.mean(np.maximum(un_b, cl_b))
             assert losses[False] - 0.5 * vf == pytest.approx(losses[True] - 0.5 * vf_b, rel=1e-3, abs=1e-3)
     assert losses[True] == pytest.approx(float(fx["step_loss"][0]), rel=2e-3)
 

@@ -238,19 +238,20 @@ class PPOAgent(AgentBase):
         data-parallel all-reduce, the gradient-norm clip and the AdamW step each run once over contiguous memory (no
         concatenate / copy-back).  load_state_dict copies in place, so the views survive it."""
         params = list(self.model.parameters())
-        n = sum(p.numel() for p in params)
-        n_pad = (n + 3) // 4 * 4
+        ALIGN = 64                       # floats: every parameter starts on a 256-byte boundary (GEMM / TMA operand alignment);
+        offs, n_pad = [], 0              # the gaps hold zeros, which AdamW leaves at zero
+        for p in params:
+            offs.append(n_pad)
+            n_pad += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
         dev = self.device
         self._flat = torch.zeros(n_pad, dtype=torch.float32, device=dev)
         self._flat_grad = torch.zeros(n_pad, dtype=torch.float32, device=dev)
-        off = 0
-        for p in params:
+        for p, off in zip(params, offs):
             k = p.numel()
             self._flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self._flat[off:off + k].view_as(p)
             p.grad = self._flat_grad[off:off + k].view_as(p)
-            off += k
-        self._n_params = n
+        self._n_params = n_pad
         self._exp_avg = torch.zeros(n_pad, dtype=torch.float32, device=dev)
         self._exp_avg_sq = torch.zeros(n_pad, dtype=torch.float32, device=dev)
         self._opt_step = torch.zeros(1, dtype=torch.int32, device=dev)
