@@ -218,6 +218,42 @@ int vmgym_policy_heads_backward(const vmgym_config* cfg, const uint32_t* d_mask_
                                 int64_t n_envs, const void* d_action_in, int action_dtype, const float* d_g_logprob,
                                 const float* d_g_entropy, float* d_g_logits, void* stream);
 
+/* The dense layers of PPOAgent.update (ppo.py:91-109 Network, :229-295) on tcgen05 tensor cores, bf16 operands, fp32 accumulate:
+ *   C[M, N] = sum_k A(m, k) B(n, k)
+ * Operand X is K-major (x_mn = 0: row-major [rows, K], row stride ldx) or MN-major (x_mn = 1: row-major [K, rows]) — the
+ * forward pass (activations x nn.Linear weights) is K-major x K-major, the input-gradient GEMM K-major x MN-major, the
+ * weight-gradient GEMM (contracting over samples) MN-major x MN-major; no transposed copies are needed.  Epilogue, fused:
+ * + d_bias[N], act (0 none, 1 tanh), * (1 - y^2) with d_mul_y bf16 [M, ldy] (tanh backward), fp32 output d_c_f32 (= or +=
+ * when `accumulate`) and / or bf16 output d_c_bf16, and d_row_sum[M] (= or +=) sum_k A(m, k) — the bias gradient of the
+ * weight-gradient GEMM.  ld* in elements, multiples of 8 for the operands; operand bases 16-byte aligned. */
+int vmgym_tc_gemm(const void* d_a, int32_t a_mn, int64_t lda, const void* d_b, int32_t b_mn, int64_t ldb, int64_t M, int64_t N,
+                  int64_t K, const float* d_bias, int32_t act, const void* d_mul_y, int64_t ldy, float* d_c_f32, int64_t ldc_f32,
+                  int32_t accumulate, void* d_c_bf16, int64_t ldc_bf16, float* d_row_sum, void* stream);
+
+/* fp32 [rows, cols] (row stride lds) -> bf16 [rows, cols_pad], zero padded (cols_pad % 8 == 0): the GEMMs' operand format. */
+int vmgym_cast_pad_bf16(const float* d_src, int64_t rows, int64_t cols, int64_t lds, void* d_dst_bf16, int64_t cols_pad, void* stream);
+
+/* The critic's last layer Linear(hidden, 1) (ppo.py:95-101) on bf16 activations, and its backward: d_dz = dv w (1 - h^2) as
+ * bf16 [rows, hidden], d_dw[hidden] += sum_m dv[m] h[m, :], *d_db += sum dv. */
+int vmgym_value_head(const void* d_h_bf16, int64_t rows, int32_t hidden, const float* d_w, const float* d_b, float* d_out, void* stream);
+int vmgym_value_head_backward(const void* d_h_bf16, int64_t rows, int32_t hidden, const float* d_w, const float* d_dv, void* d_dz_bf16,
+                              float* d_dw, float* d_db, void* stream);
+
+/* Per-sample PPO loss of ppo.py:259-282 (clipped surrogate, optionally clipped value loss, entropy bonus; means over
+ * 1 / inv_n_total samples) and its derivatives w.r.t. each sample's summed log-prob (d_c_logprob) and value (d_c_value);
+ * d_sums[0] += sum of log-ratios (the KL estimate of ppo.py:263), d_sums[1] += loss (fp64). */
+int vmgym_ppo_loss(const float* d_new_logprob, const float* d_old_logprob, const float* d_adv, const float* d_entropy, const float* d_value,
+                   const float* d_old_value, const float* d_return, int64_t n, float eps_clip, float ent_coef, float vf_coef,
+                   int32_t vf_loss_clip, float inv_n_total, float* d_c_logprob, float* d_c_value, double* d_sums, void* stream);
+
+/* Backward of the fused actor head (vmgym_policy_fused with stored actions): recomputes the logits of each (128 envs x 1 VM)
+ * tile in tensor memory and writes d/dlogits of sum_e c_logprob[e] logprob(e) + c_entropy entropy(e) as bf16
+ * d_g_bf16[M, ldg] (column 128 v + a; zeros for masked and padding columns) — the operand of the output layer's two backward
+ * GEMMs (vmgym_tc_gemm), and the only [samples, V x 128] tensor of the update that reaches HBM. */
+int vmgym_policy_fused_grad(const void* d_h_bf16, const void* d_wpad_bf16, const float* d_bias_pad, const uint32_t* d_mask_bits,
+                            const void* d_action_in, int64_t M, int64_t V, int64_t A, int64_t K, const float* d_c_logprob,
+                            float c_entropy, void* d_g_bf16, int64_t ldg, void* stream);
+
 /* The optimiser step of PPOAgent.update (ppo.py:143,284-287) on flat fp32 buffers of n elements:
  * nn.utils.clip_grad_norm_(max_grad_norm; <= 0 disables) on d_grad * grad_scale, then torch.optim.AdamW's update
  * (decoupled weight decay, bias-corrected moments; formulas of torch's reference implementation).  Device-resident control:

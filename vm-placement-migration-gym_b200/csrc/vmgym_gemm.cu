@@ -18,74 +18,11 @@
 
 #include "../../include/vmgym.h"
 #include "vmgym_sample.cuh"
+#include "vmgym_tc.cuh"
 
 extern "C" void vmgym_internal_set_error(const char* msg);
 
 namespace vmgym_gemm {
-
-constexpr int BM = 128, BN = 128, BK = 64;      // BK * sizeof(bf16) = 128 B = one swizzle row
-constexpr int UMMA_K = 16;
-constexpr int STAGES = 3;
-constexpr int STAGE_BYTES = (BM + BN) * BK * 2; // 32 KiB
-constexpr int TMEM_COLS = 128;                  // fp32 accumulator: 128 lanes x 128 columns
-constexpr int THREADS = 192;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 1024 /* barriers, TMEM ptr, bias tile */;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-// K-major, 128B-swizzled operand tile (rows of 128 B, 8-row groups 1024 B apart):
-// start>>4 | LBO=1 (unused for swizzled K-major) | SBO = 1024>>4 | version 1 (sm_100) | layout SWIZZLE_128B (2)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
-{
-    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9 / 10-12 = 1), K-major both, N>>3 at 17, M>>4 at 24
-__device__ __forceinline__ uint32_t umma_idesc_bf16_f32(int m, int n)
-{
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // ---- the main loop both kernels share: one 128x128 fp32 accumulator tile in TMEM per CTA --------------------------------
 // shared-memory carve-up: STAGES x (A tile | W tile), then the barriers, the TMEM base address and 1 KiB of kernel-specific tail
 struct Pipe {
@@ -160,20 +97,6 @@ __device__ __forceinline__ void pipe_mma(const Pipe& p, uint32_t tmem_base, int 
         umma_commit(&p.empty_bar[s]);                           // frees the smem stage when these MMAs retire
     }
     umma_commit(p.tmem_full_bar);                               // accumulator complete
-}
-// 32 consecutive accumulator columns of this thread's row (TMEM lane) into registers
-__device__ __forceinline__ void tmem_ld_row32(uint32_t taddr, uint32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void pipe_teardown(uint32_t tmem_base, int warp)
 {
@@ -267,6 +190,13 @@ struct FusedOut {
     int A, V;
     unsigned long long seed;
     uint32_t counter;
+    // gradient mode (PPOAgent.update, ppo.py:257-285): with action_in, additionally emit the gradient of
+    //   sum_e c_logprob[e] * logprob(e) + c_entropy * entropy(e)   w.r.t. the logits, as bf16 g_out[e, v * 128 + a]
+    // (d logp_act / dz_a = [a == act] - p_a;  dH / dz_a = -p_a (log p_a + H);  masked and padding columns get 0)
+    const float* c_logprob;      // [M] or nullptr
+    float c_entropy;
+    __nv_bfloat16* g_out;        // [M, ldg] or nullptr
+    long long ldg;
 };
 
 // Per-row running state of the fused epilogue.
@@ -404,14 +334,58 @@ __device__ __forceinline__ void fused_epilogue_row(const FusedOut& fo, const flo
         if (c0 + 32 <= A) fused_chunk<true>(fo, s_bias, r, iw, c0, A, act_given, rnd, st);
         else fused_chunk<false>(fo, s_bias, r, iw, c0, A, act_given, rnd, st);
     }
+    const float ls = __logf(st.ssum);
+    const float H = ls - st.tsum / st.ssum;                          // -sum p log p
     if (e < M) {
-        const float ls = __logf(st.ssum);
         const int act = fo.action_in ? act_given : st.best_a;
         const float za = fo.action_in ? st.z_given : st.best_z;
         const long long o = (long long)e * fo.V + v;
         if (fo.action_out) fo.action_out[o] = (uint8_t)act;
-        fo.logprob[o] = ((unsigned)act < (unsigned)A) ? (za - st.m) - ls : 0.f;
-        fo.entropy[o] = ls - st.tsum / st.ssum;                      // -sum p log p
+        if (fo.logprob) fo.logprob[o] = ((unsigned)act < (unsigned)A) ? (za - st.m) - ls : 0.f;
+        if (fo.entropy) fo.entropy[o] = H;
+    }
+    if (fo.g_out) {
+        // second pass over the accumulator: the logit gradients of this row, all 128 columns of the tile (zeros above A)
+        const float clp = e < M ? fo.c_logprob[e] : 0.f, cen = fo.c_entropy;
+        const float inv_s = 1.0f / st.ssum;
+        __nv_bfloat16* grow = fo.g_out + (long long)e * fo.ldg + (long long)v * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t gb[16];
+            if (c0 < A) {
+                uint32_t r[32];
+                tmem_ld_row32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                const uint32_t iw = c0 == 0 ? inv.x : (c0 == 32 ? inv.y : (c0 == 64 ? inv.z : inv.w));
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float gv[2];
+#pragma unroll
+                    for (int t = 0; t < 2; t++) {
+                        const int a = c0 + j + t;
+                        float x = __uint_as_float(r[j + t]) + s_bias[min(a, BN - 1)];
+                        // masked columns were overwritten by the constant -1e7 (ppo.py:119): no gradient reaches their logits
+                        const bool dead = ((iw >> (j + t)) & 1u) || a >= A;
+                        const float d = x - st.m;
+                        const float pa = dead ? 0.f : vmgym::fast_exp(d) * inv_s;
+                        const float lp = d - ls;
+                        const float gg = dead ? 0.f : clp * ((a == act_given ? 1.f : 0.f) - pa) + (pa > 0.f ? cen * (-pa * (lp + H)) : 0.f);
+                        gv[t] = gg;
+                    }
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(gv[0], gv[1]);
+                    gb[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j++) gb[j] = 0u;
+            }
+            if (e < M) {
+                uint4* dst = reinterpret_cast<uint4*>(grow + c0);
+                dst[0] = make_uint4(gb[0], gb[1], gb[2], gb[3]);
+                dst[1] = make_uint4(gb[4], gb[5], gb[6], gb[7]);
+                dst[2] = make_uint4(gb[8], gb[9], gb[10], gb[11]);
+                dst[3] = make_uint4(gb[12], gb[13], gb[14], gb[15]);
+            }
+        }
     }
 }
 
@@ -585,38 +559,6 @@ __global__ void __launch_bounds__(P_THREADS, 1) policy_fused_persistent_kernel(c
 
 
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
-
-// row-major [rows, K] bf16 matrix -> 2-D tensor map with a (BK x box_rows) box, 128B swizzle, zero fill out of bounds
-static int make_map(CUtensorMap* map, const void* ptr, int rows, int K, int box_rows)
-{
-    EncodeTiledFn enc = get_encode();
-    if (!enc) return -1;
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? 0 : -2;
-}
-
 // cudaFuncSetAttribute is per device: remember which devices have been configured for a kernel (slot 0..2)
 static bool attr_done(int slot, bool mark)
 {
@@ -657,23 +599,21 @@ extern "C" int vmgym_linear_bf16(const void* d_a_bf16, const void* d_w_bf16, con
     return VMGYM_OK;
 }
 
-extern "C" int vmgym_policy_fused(const void* d_h_bf16, const void* d_wpad_bf16, const float* d_bias_pad, const uint32_t* d_mask_bits,
-                                  const void* d_action_in, int64_t M, int64_t V, int64_t A, int64_t K, uint64_t seed,
-                                  uint64_t counter, uint8_t* d_action_out, float* d_logprob, float* d_entropy, void* stream)
+static int launch_policy_fused(const char* who, const void* d_h_bf16, const void* d_wpad_bf16, vmgym_gemm::FusedOut fo, int64_t M, int64_t V,
+                               int64_t A, int64_t K, void* stream)
 {
     using namespace vmgym_gemm;
-    if (!d_h_bf16 || !d_wpad_bf16 || !d_bias_pad || !d_logprob || !d_entropy || (!d_action_in && !d_action_out) || M < 0) {
-        vmgym_internal_set_error("vmgym_policy_fused: null operand");
-        return VMGYM_EINVAL;
-    }
-    if (A < 1 || A > 128 || K % 8 != 0 || ((uintptr_t)d_h_bf16 & 15) || ((uintptr_t)d_wpad_bf16 & 15) || ((uintptr_t)d_mask_bits & 15)) {
-        vmgym_internal_set_error("vmgym_policy_fused: needs action_dim <= 128, K % 8 == 0 and 16-byte aligned operands");
+    char msg[160];
+    if (A < 1 || A > 128 || K % 8 != 0 || ((uintptr_t)d_h_bf16 & 15) || ((uintptr_t)d_wpad_bf16 & 15) || ((uintptr_t)fo.mask_bits & 15)) {
+        snprintf(msg, sizeof(msg), "%s: needs action_dim <= 128, K %% 8 == 0 and 16-byte aligned operands", who);
+        vmgym_internal_set_error(msg);
         return VMGYM_EUNSUPPORTED;
     }
     if (M == 0 || V == 0) return VMGYM_OK;
     CUtensorMap map_a, map_w;
     if (make_map(&map_a, d_h_bf16, (int)M, (int)K, BM) || make_map(&map_w, d_wpad_bf16, (int)(V * BN), (int)K, BN)) {
-        vmgym_internal_set_error("vmgym_policy_fused: cuTensorMapEncodeTiled failed");
+        snprintf(msg, sizeof(msg), "%s: cuTensorMapEncodeTiled failed", who);
+        vmgym_internal_set_error(msg);
         return VMGYM_ECUDA;
     }
     if (!attr_done(1, false)) {
@@ -681,9 +621,6 @@ extern "C" int vmgym_policy_fused(const void* d_h_bf16, const void* d_wpad_bf16,
         if (e != cudaSuccess) { vmgym_internal_set_error(cudaGetErrorString(e)); return VMGYM_ECUDA; }
         attr_done(1, true);
     }
-    FusedOut fo;
-    fo.mask_bits = d_mask_bits; fo.bias_pad = d_bias_pad; fo.action_in = d_action_in; fo.action_out = d_action_out;
-    fo.logprob = d_logprob; fo.entropy = d_entropy; fo.A = (int)A; fo.V = (int)V; fo.seed = seed; fo.counter = (uint32_t)counter;
     // default: the persistent kernel whenever the activation tile fits (K <= 512); VMGYM_FUSED_PERSISTENT=0 selects the
     // tile-per-CTA kernel (A/B experiments, and the fallback for wider hidden layers)
     static const int persistent = getenv("VMGYM_FUSED_PERSISTENT") ? atoi(getenv("VMGYM_FUSED_PERSISTENT")) : 1;
@@ -692,12 +629,12 @@ extern "C" int vmgym_policy_fused(const void* d_h_bf16, const void* d_wpad_bf16,
         if (!attr_done(2, false)) {
             cudaError_t e2 = cudaFuncSetAttribute(policy_fused_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM_BYTES);
             if (e2 != cudaSuccess) { vmgym_internal_set_error(cudaGetErrorString(e2)); return VMGYM_ECUDA; }
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-            if (n_sm <= 0) n_sm = 148;
             attr_done(2, true);
         }
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
         const long long units = ((M + BM - 1) / BM) * ((V + P_VCHUNK - 1) / P_VCHUNK);
         const unsigned ctas = (unsigned)(units < n_sm ? units : n_sm);
         policy_fused_persistent_kernel<<<ctas, P_THREADS, P_SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_w, fo, (int)M, (int)K);
@@ -710,4 +647,37 @@ extern "C" int vmgym_policy_fused(const void* d_h_bf16, const void* d_wpad_bf16,
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { vmgym_internal_set_error(cudaGetErrorString(e)); return VMGYM_ECUDA; }
     return VMGYM_OK;
+}
+
+extern "C" int vmgym_policy_fused(const void* d_h_bf16, const void* d_wpad_bf16, const float* d_bias_pad, const uint32_t* d_mask_bits,
+                                  const void* d_action_in, int64_t M, int64_t V, int64_t A, int64_t K, uint64_t seed,
+                                  uint64_t counter, uint8_t* d_action_out, float* d_logprob, float* d_entropy, void* stream)
+{
+    using namespace vmgym_gemm;
+    if (!d_h_bf16 || !d_wpad_bf16 || !d_bias_pad || !d_logprob || !d_entropy || (!d_action_in && !d_action_out) || M < 0) {
+        vmgym_internal_set_error("vmgym_policy_fused: null operand");
+        return VMGYM_EINVAL;
+    }
+    FusedOut fo;
+    fo.mask_bits = d_mask_bits; fo.bias_pad = d_bias_pad; fo.action_in = d_action_in; fo.action_out = d_action_out;
+    fo.logprob = d_logprob; fo.entropy = d_entropy; fo.A = (int)A; fo.V = (int)V; fo.seed = seed; fo.counter = (uint32_t)counter;
+    fo.c_logprob = nullptr; fo.c_entropy = 0.f; fo.g_out = nullptr; fo.ldg = 0;
+    return launch_policy_fused("vmgym_policy_fused", d_h_bf16, d_wpad_bf16, fo, M, V, A, K, stream);
+}
+
+extern "C" int vmgym_policy_fused_grad(const void* d_h_bf16, const void* d_wpad_bf16, const float* d_bias_pad, const uint32_t* d_mask_bits,
+                                       const void* d_action_in, int64_t M, int64_t V, int64_t A, int64_t K, const float* d_c_logprob,
+                                       float c_entropy, void* d_g_bf16, int64_t ldg, void* stream)
+{
+    using namespace vmgym_gemm;
+    if (!d_h_bf16 || !d_wpad_bf16 || !d_bias_pad || !d_action_in || !d_c_logprob || !d_g_bf16 || M < 0 || ldg < V * BN || (ldg & 7) ||
+        ((uintptr_t)d_g_bf16 & 15)) {
+        vmgym_internal_set_error("vmgym_policy_fused_grad: null operand, or ldg < 128 V / not a multiple of 8, or unaligned output");
+        return VMGYM_EINVAL;
+    }
+    FusedOut fo;
+    fo.mask_bits = d_mask_bits; fo.bias_pad = d_bias_pad; fo.action_in = d_action_in; fo.action_out = nullptr;
+    fo.logprob = nullptr; fo.entropy = nullptr; fo.A = (int)A; fo.V = (int)V; fo.seed = 0; fo.counter = 0;
+    fo.c_logprob = d_c_logprob; fo.c_entropy = c_entropy; fo.g_out = (__nv_bfloat16*)d_g_bf16; fo.ldg = ldg;
+    return launch_policy_fused("vmgym_policy_fused_grad", d_h_bf16, d_wpad_bf16, fo, M, V, A, K, stream);
 }

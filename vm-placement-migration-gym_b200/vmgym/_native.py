@@ -15,7 +15,7 @@ PKG_ROOT = os.path.dirname(_HERE)
 REPO_ROOT = os.path.dirname(PKG_ROOT)
 CSRC = os.path.join(PKG_ROOT, "csrc")
 LIB_PATH = os.path.join(_HERE, "libvmgym.so")
-SOURCES = ["vmgym_env.cu", "vmgym_policy.cu", "vmgym_gemm.cu", "vmgym_optim.cu"]
+SOURCES = ["vmgym_env.cu", "vmgym_policy.cu", "vmgym_gemm.cu", "vmgym_optim.cu", "vmgym_train.cu"]
 # -fmad=false: the env kernels reproduce numpy's fp64/fp32 arithmetic exactly, so no FMA contraction anywhere
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -69,26 +69,41 @@ SCALARS_BYTES = 80
 EXPORTS = ["vmgym_last_error", "vmgym_abi_version", "vmgym_get_layout", "vmgym_reset", "vmgym_step",
            "vmgym_agent_step", "vmgym_agent_step_rotation", "vmgym_agent_act", "vmgym_observe", "vmgym_invalid_action_mask", "vmgym_set_tuning",
            "vmgym_policy_heads", "vmgym_policy_heads_backward", "vmgym_gae", "vmgym_drlvmp_choice", "vmgym_drlvmp_iter", "vmgym_linear_bf16", "vmgym_policy_fused", "vmgym_segtree_update",
-           "vmgym_segtree_retrieve", "vmgym_vmstats_finalize", "vmgym_per_sample", "vmgym_c51_project", "vmgym_adamw_step"]
+           "vmgym_segtree_retrieve", "vmgym_vmstats_finalize", "vmgym_per_sample", "vmgym_c51_project", "vmgym_adamw_step", "vmgym_tc_gemm", "vmgym_cast_pad_bf16",
+           "vmgym_value_head", "vmgym_value_head_backward", "vmgym_ppo_loss", "vmgym_policy_fused_grad"]
 
 
 class VmgymError(RuntimeError):
     pass
 
 
+HEADERS = ["vmgym_device.cuh", "vmgym_sort.cuh", "vmgym_env_kernels.cuh", "vmgym_sample.cuh", "vmgym_tc.cuh"]
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into vmgym/libvmgym.so (sm_100a, -lineinfo).  nvcc cross-compiles without a GPU."""
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in ("vmgym_device.cuh", "vmgym_sort.cuh", "vmgym_env_kernels.cuh", "vmgym_sample.cuh")] + \
-        [os.path.join(REPO_ROOT, "include", "vmgym.h")]
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
-        return LIB_PATH
+    """Compile csrc/*.cu into vmgym/libvmgym.so (sm_100a, -lineinfo).  nvcc cross-compiles without a GPU.  Each source is
+    compiled to its own object (in parallel, only when it or a header is newer), then linked."""
+    from concurrent.futures import ThreadPoolExecutor
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(REPO_ROOT, "include", "vmgym.h")]
+    obj_dir = os.path.join(CSRC, "_build")
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(REPO_ROOT, "include"), "-o", LIB_PATH] + srcs
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    newest_hdr = max(os.path.getmtime(h) for h in hdrs)
+    jobs, objs = [], []
+    for src_name in SOURCES:
+        src = os.path.join(CSRC, src_name)
+        obj = os.path.join(obj_dir, src_name[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), newest_hdr):
+            cmd = [nvcc] + flags + (["-Xptxas=-v"] if verbose else []) + ["-I", os.path.join(REPO_ROOT, "include"), "-c", src, "-o", obj]
+            jobs.append(cmd)
+    if not jobs and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(o) for o in objs):
+        return LIB_PATH
+    if jobs:
+        with ThreadPoolExecutor(len(jobs)) as ex:
+            list(ex.map(subprocess.check_call, jobs))
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH] + objs)
     return LIB_PATH
 
 
@@ -136,6 +151,12 @@ def lib():
     L.vmgym_segtree_retrieve.argtypes = [vp, i64, vp, C.c_int32, vp, vp]
     L.vmgym_policy_fused.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, u64, u64, vp, vp, vp, vp]
     L.vmgym_adamw_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, f32, vp, vp, vp, vp, vp]
+    L.vmgym_tc_gemm.argtypes = [vp, i32, i64, vp, i32, i64, i64, i64, i64, vp, i32, vp, i64, vp, i64, i32, vp, i64, vp, vp]
+    L.vmgym_cast_pad_bf16.argtypes = [vp, i64, i64, i64, vp, i64, vp]
+    L.vmgym_value_head.argtypes = [vp, i64, i32, vp, vp, vp, vp]
+    L.vmgym_value_head_backward.argtypes = [vp, i64, i32, vp, vp, vp, vp, vp, vp]
+    L.vmgym_ppo_loss.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, f32, f32, f32, i32, f32, vp, vp, vp, vp]
+    L.vmgym_policy_fused_grad.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, vp, f32, vp, i64, vp]
     for name in EXPORTS:
         getattr(L, name)
     _lib = L
