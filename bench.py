@@ -269,8 +269,9 @@ def gpu_arm(args):
 
     # ---- extra A: PPO training throughput at BASELINE config 4's per-GPU share: 8192 envs, rollout T = batch_size = 100
     # (config/100.yml), 4 sequential minibatches of 25 steps, k_epochs 4, NCCL gradient all-reduce per optimiser step ----
+    extras_on = set() if args.no_extras else set(args.extras.split(","))
     ppo = None
-    if not args.no_extras:
+    if "ppo" in extras_on:
         from vmgym.ppo import PPOAgent, PPOConfig
         Np, Tp = args.ppo_envs, args.ppo_steps
         vp = VecVmEnv(Config(**cfg), Np, device=dev, rng="philox", seeds=cfg["seed"] + 2 * 10**6 + rank * Np + np.arange(Np, dtype=np.int64))
@@ -280,6 +281,7 @@ def gpu_arm(args):
         if world > 1:
             for p_ in agent_p.model.parameters():
                 dist.broadcast(p_.data, 0)
+            agent_p.weights_changed()
         vp.agent_step("bestfit", n_steps=WARM_STEPS, **quiet)          # saturated envs, as in training after the first episode steps
         agent_p.learn(episodes=1, max_updates=1, reset=False)           # warm-up (allocations, kernel plans)
         barrier()
@@ -304,7 +306,7 @@ def gpu_arm(args):
 
     # ---- extra B: the synthetic 1000-PM shape (BASELINE config 5: highuniform sizes at 100 % load, V = 3P) ----
     s1000 = None
-    if not args.no_extras:
+    if "s1000" in extras_on:
         kw1000 = dict(cfg, pms=1000, vms=3000, sequence="highuniform", arrival_rate=1000 / 0.625 / cfg["service_length"])
         E1 = 1024
         v1 = VecVmEnv(Config(**kw1000), E1, device=dev, rng="philox", seeds=cfg["seed"] + 4 * 10**6 + rank * E1 + np.arange(E1, dtype=np.int64))
@@ -335,7 +337,7 @@ def gpu_arm(args):
 
     # ---- extra C: the small shape of BASELINE configs[0] (config/10.yml, first-fit) at 2^20 envs per GPU ----
     s10 = None
-    if not args.no_extras:
+    if "s10" in extras_on:
         cfg10 = yaml.safe_load(open(os.path.join(ROOT, "configs", "10.yml")))["environment"]
         cfg10["reward_function"] = "wr"
         E10 = 1 << 20
@@ -536,7 +538,9 @@ def main():
     ap.add_argument("--batches", type=int, default=20, help="independent env batches the timed launches rotate over")
     ap.add_argument("--cpu-steps", type=int, default=6000, help="timed CPU steps per env in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the large-batch and PPO extras")
+    ap.add_argument("--no-extras", action="store_true", help="skip the PPO / 1000-PM / 10-PM extras")
+    ap.add_argument("--extras", default="ppo,s1000,s10", help="comma list of the extras to run (ppo, s1000, s10)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e loop (experiments)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -233,6 +233,12 @@ int vmgym_tc_gemm(const void* d_a, int32_t a_mn, int64_t lda, const void* d_b, i
 /* fp32 [rows, cols] (row stride lds) -> bf16 [rows, cols_pad], zero padded (cols_pad % 8 == 0): the GEMMs' operand format. */
 int vmgym_cast_pad_bf16(const float* d_src, int64_t rows, int64_t cols, int64_t lds, void* d_dst_bf16, int64_t cols_pad, void* stream);
 
+/* fp32 [rows, cols] -> bf16 [rows, 3 cols_pad] = [hi | lo | hi] (order 0: activations) or [hi | hi | lo] (order 1: weights) with
+ * hi = bf16(x), lo = bf16(x - hi): one bf16 GEMM over the concatenated K then yields x w to ~2^-16 relative.  Used for the
+ * networks' first layer, whose inputs are raw observations (PM indices up to P + 1 next to sizes in [0, 1], env.py:295-296). */
+int vmgym_cast_split_bf16(const float* d_src, int64_t rows, int64_t cols, int64_t lds, void* d_dst_bf16, int64_t cols_pad, int32_t order,
+                          void* stream);
+
 /* The critic's last layer Linear(hidden, 1) (ppo.py:95-101) on bf16 activations, and its backward: d_dz = dv w (1 - h^2) as
  * bf16 [rows, hidden], d_dw[hidden] += sum_m dv[m] h[m, :], *d_db += sum dv. */
 int vmgym_value_head(const void* d_h_bf16, int64_t rows, int32_t hidden, const float* d_w, const float* d_b, float* d_out, void* stream);

@@ -68,7 +68,7 @@ def test_update_matches_reference(name):
     torch.backends.cuda.matmul.allow_tf32 = False
     try:
         vec = VecVmEnv(Config(**cfg), 1, rng="philox")
-        agent = PPOAgent(vec, PPOConfig(**pcfg, vf_broadcast=True))
+        agent = PPOAgent(vec, PPOConfig(**pcfg, vf_broadcast=True, update_math="fp32"))
         z = _weights()
         agent.model.load_state_dict(_state_dict(z, "ppo-wr", torch, vec.device))
         dev = vec.device
@@ -127,7 +127,7 @@ def test_update_default_value_loss_is_the_elementwise_form():
     dev = vec.device
     losses = {}
     for bc in (True, False):
-        agent = PPOAgent(vec, PPOConfig(hidden_size=512, vf_broadcast=bc, k_epochs=1))
+        agent = PPOAgent(vec, PPOConfig(hidden_size=512, vf_broadcast=bc, k_epochs=1, update_math="fp32"))
         agent.model.load_state_dict(_state_dict(z, "ppo-wr", torch, dev))
         t = lambda x, dt=None: torch.from_numpy(np.ascontiguousarray(x)).to(dev) if dt is None else torch.from_numpy(np.ascontiguousarray(x)).to(dev).to(dt)  # noqa: E731
         st = agent.update(obs=t(fx["obs"])[:, None], next_obs=t(fx["next_obs"])[:, None], action=t(fx["action"], torch.uint8)[:, None],
@@ -224,3 +224,145 @@ def test_fused_actor_head_vs_reference_get_action(tag):
     a_out, _, _ = head(h, torch.from_numpy(words).cuda(), seed=3, counter=7)
     a_out = a_out.cpu().numpy()
     assert not m0[np.arange(V), a_out[0]].any() and not m1[np.arange(V), a_out[1]].any()
+
+
+# ---- the hand-written tensor-core update (update_math="bf16", vmgym/ppo_tc.py) against the fp32 autograd path ------------------
+# bf16 operands / fp32 accumulation: per-layer gradients agree with the fp32 path to a few 1e-2 relative L2 (operand rounding
+# 2^-9 per factor, propagated through three layers and the softmax); stated per check below.
+
+def _layer_slices(agent):
+    out, off = {}, 0
+    for name, p in agent.model.named_parameters():
+        n = p.numel()
+        k = (n + 63) // 64 * 64
+        out[name] = slice(off, off + n)
+        off += k
+    return out
+
+
+def _one_minibatch_grads(agent, batch, t0, t1):
+    import torch
+    from vmgym.ppo import gae
+    cfg = agent.config
+    T, N = batch["reward"].shape
+    tc = agent._tc_network()
+    with torch.no_grad():
+        if tc is not None:
+            values = tc.values(batch["obs"]).reshape(T, N)
+            nvals = tc.values(batch["next_obs"]).reshape(T, N)
+            obs = tc.cast_obs(batch["obs"]).reshape(T, N, tc.Dx)
+            mask = agent._mask4(batch["mask"])
+        else:
+            values = agent.model.get_value(batch["obs"].reshape(T * N, -1)).reshape(T, N)
+            nvals = agent.model.get_value(batch["next_obs"].reshape(T * N, -1)).reshape(T, N)
+            obs, mask = batch["obs"], batch["mask"]
+        adv, ret = gae(batch["reward"], values, nvals, batch["done"], cfg.gamma, cfg.lamda)
+    n_mb = (t1 - t0) * N
+    adv_mb = agent._normalise_advantages(adv[t0:t1], 1)
+    lr_sum, loss = agent._minibatch_backward(obs[t0:t1].reshape(n_mb, -1), batch["action"][t0:t1].reshape(n_mb, -1),
+                                             mask[t0:t1].reshape(n_mb, agent.V, mask.shape[-1]), batch["logprob"][t0:t1].reshape(-1), adv_mb,
+                                             values[t0:t1].reshape(-1), ret[t0:t1].reshape(-1), n_mb)
+    torch.cuda.synchronize()
+    return agent._flat_grad.clone(), float(lr_sum), float(loss), values
+
+
+def _rollout(agent, vec, T):
+    import torch
+    buf = {k: [] for k in ("obs", "next_obs", "action", "mask", "logprob", "reward", "done")}
+    obs = vec.observe().clone()
+    with torch.no_grad():
+        for _ in range(T):
+            logits = agent.model.actor(obs).contiguous()
+            action, logprob, _, mask = agent._heads(logits, -1.0, want_mask=True)
+            nobs, reward, term, _, _ = vec.step(action, want_valid=False)
+            for k, v in (("obs", obs), ("next_obs", nobs), ("action", action), ("mask", mask), ("logprob", logprob),
+                         ("reward", reward.float()), ("done", vec.terminated_u8)):
+                buf[k].append(v.clone())
+            obs = nobs.clone()
+    return {k: torch.stack(v) for k, v in buf.items()}
+
+
+@pytest.mark.parametrize("shape", ["s10", "s100", "s100_nonull"])
+def test_tensor_core_minibatch_gradients_match_fp32_autograd(shape):
+    import torch
+    from vmgym import Config, VecVmEnv
+    from vmgym.ppo import PPOAgent, PPOConfig
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        if shape == "s10":
+            kw = dict(pms=10, vms=30, arrival_rate=0.4, service_length=30, training_steps=400, eval_steps=1000, reward_function="wr",
+                      allow_null_action=True)
+            N, T, H = 96, 6, 512
+        else:
+            # s100_nonull: without the NULL action every empty slot's row is fully masked (uniform over -1e7 logits): the float32
+            # rounding of the reference's log-sum-exp at that magnitude (log-prob -5.0, not -log 101) must be reproduced
+            kw = dict(pms=100, vms=300, arrival_rate=1.8182, service_length=100, training_steps=10000, eval_steps=100000, reward_function="wr",
+                      allow_null_action=shape == "s100")
+            N, T, H = 160, 4, 512
+        vec = VecVmEnv(Config(**kw), N, rng="philox")
+        vec.agent_step("firstfit", n_steps=150, want_action=False, want_valid=False)
+        torch.manual_seed(11)
+        a32 = PPOAgent(vec, PPOConfig(hidden_size=H, update_math="fp32", env_chunk=4096))
+        if shape == "s10":
+            z = _weights()
+            a32.model.load_state_dict(_state_dict(z, "ppo-wr", torch, vec.device))       # trained weights: peaked, realistic logits
+        atc = PPOAgent(vec, PPOConfig(hidden_size=H, update_math="bf16", env_chunk=200))  # several chunks per minibatch
+        atc._flat.copy_(a32._flat)
+        atc.weights_changed()
+        batch = _rollout(a32, vec, T)
+        g32, lr32, loss32, v32 = _one_minibatch_grads(a32, batch, 0, T // 2)
+        gtc, lrtc, losstc, vtc = _one_minibatch_grads(atc, batch, 0, T // 2)
+        assert atc._tc_network() is not None and a32._tc_network() is None
+        # values through the tensor-core critic: bf16 operands
+        assert torch.allclose(vtc, v32, rtol=2e-2, atol=0.05 * float(v32.abs().max()) + 1e-3)
+        assert lrtc == pytest.approx(lr32, abs=2e-2 * T * N) and losstc == pytest.approx(loss32, rel=5e-2, abs=1e-3)
+        sl = _layer_slices(a32)
+        for name, s_ in sl.items():
+            a, b = g32[s_].double(), gtc[s_].double()
+            rel = float((a - b).norm() / a.norm().clamp_min(1e-30))
+            cos = float((a * b).sum() / (a.norm() * b.norm()).clamp_min(1e-30))
+            assert cos > 0.995 and rel < 0.1, f"{name}: cosine {cos:.5f}, relative L2 error {rel:.3e}"
+        cos_all = float((g32.double() * gtc.double()).sum() / (g32.double().norm() * gtc.double().norm()))
+        assert cos_all > 0.999, f"whole gradient cosine {cos_all}"
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def test_tensor_core_update_tracks_fp32_update_on_reference_batch():
+    """Whole update() on the reference's recorded S10 batch (weights-10/ppo-wr.pt): the tensor-core path takes the same minibatch
+    branch sequence as the fp32 path and its losses / KL estimates stay within bf16 tolerance (loss 3 %, KL 5e-3 absolute)."""
+    import torch
+    from vmgym import Config, VecVmEnv
+    from vmgym.ppo import PPOAgent, PPOConfig
+    fx = _case("upd_default")
+    cfg = json.loads(str(fx["cfg_json"]))
+    vec = VecVmEnv(Config(**cfg), 1, rng="philox")
+    z = _weights()
+    T, V = fx["action"].shape
+    A = vec.action_dim
+    mask = np.unpackbits(fx["mask"], axis=1)[:, :V * A].reshape(T, V, A).astype(bool)
+    dev = vec.device
+    t = lambda x, dt=None: torch.from_numpy(np.ascontiguousarray(x)).to(dev) if dt is None else torch.from_numpy(np.ascontiguousarray(x)).to(dev).to(dt)  # noqa: E731
+    res = {}
+    for mode in ("fp32", "bf16"):
+        agent = PPOAgent(vec, PPOConfig(hidden_size=512, update_math=mode))
+        agent.model.load_state_dict(_state_dict(z, "ppo-wr", torch, dev))
+        agent.weights_changed()
+        pre = agent._flat.clone()
+        st = agent.update(obs=t(fx["obs"])[:, None], next_obs=t(fx["next_obs"])[:, None], action=t(fx["action"], torch.uint8)[:, None],
+                          mask=t(_pack_mask(mask))[:, None], logprob=t(fx["logprob"])[:, None], reward=t(fx["reward"])[:, None],
+                          done=t(fx["done"])[:, None], debug=True)
+        res[mode] = (st, (agent._flat - pre).double())
+    a32, atc = res["fp32"][0]["attempts"], res["bf16"][0]["attempts"]
+    assert [x["stepped"] for x in a32] == [x["stepped"] for x in atc] == [1] * 16
+    assert np.allclose([x["loss"] for x in atc], [x["loss"] for x in a32], rtol=3e-2)
+    assert np.allclose([x["kl"] for x in atc], [x["kl"] for x in a32], atol=5e-3)
+    assert np.allclose([x["grad_norm"] for x in atc], [x["grad_norm"] for x in a32], rtol=5e-2)
+    d32, dtc = res["fp32"][1], res["bf16"][1]
+    # AdamW's first steps are close to lr * sign(gradient): entries with a tiny gradient flip between the two paths, so the
+    # parameter deltas agree less tightly than the gradients do (cosine 0.999 in the gradient test above)
+    cos = float((d32 * dtc).sum() / (d32.norm() * dtc.norm()))
+    assert cos > 0.85, f"parameter update direction: cosine {cos}"
+    # and the reference's own values / advantages within bf16 tolerance
+    assert np.allclose(res["bf16"][0]["values"].flatten().cpu().numpy(), fx["values"], rtol=1e-2, atol=0.3)

@@ -96,6 +96,26 @@ def test_tc_gemm_epilogues():
     assert bool(((db.double() - dz.double().sum(0)).abs() <= 2e-3 * (dz.double().sum(0).abs() + 1.0)).all())
 
 
+def test_tc_gemm_split_k_weight_gradient():
+    """dW += dz^T a with few output tiles and a long sample axis takes the split-K path (atomic partial tiles): same result."""
+    import torch
+    torch.manual_seed(3)
+    M, H, D = 9000, 512, 1100
+    dz = (torch.randn(M, H, device="cuda") * 0.1).to(torch.bfloat16)
+    x = torch.zeros((M, 3 * 1104), dtype=torch.bfloat16, device="cuda")
+    x[:, :D] = torch.randn(M, D, device="cuda")
+    dW = torch.full((H, D), 0.5, dtype=torch.float32, device="cuda")
+    db = torch.full((H,), -1.0, dtype=torch.float32, device="cuda")
+    nv, lib = _lib()
+    nv.check(lib.vmgym_tc_gemm(dz.data_ptr(), 1, dz.stride(0), x.data_ptr(), 1, x.stride(0), H, D, M, None, 0, None, 0, dW.data_ptr(), dW.stride(0), 1,
+                               None, 0, db.data_ptr(), _stream(torch)), "vmgym_tc_gemm")
+    torch.cuda.synchronize()
+    ref = 0.5 + dz.double().t() @ x[:, :D].double()
+    assert bool(((dW.double() - ref).abs() <= 3e-3 * (ref.abs() + 1.0)).all()), f"max |d| {(dW.double() - ref).abs().max().item()}"
+    rs = -1.0 + dz.double().sum(0)
+    assert bool(((db.double() - rs).abs() <= 3e-3 * (rs.abs() + 1.0)).all())
+
+
 def test_small_training_kernels():
     import torch
     nv, lib = _lib()

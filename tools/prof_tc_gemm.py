@@ -1,0 +1,57 @@
+"""ncu / timing target: the three big GEMM shapes of the PPO update on vmgym_tc_gemm and the fused head (forward + gradient mode).
+    python tools/prof_tc_gemm.py [samples]"""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "vm-placement-migration-gym_b200")]
+import torch  # noqa: E402
+
+from vmgym import _native as nv  # noqa: E402
+
+M = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
+V, A, H, T = 300, 102, 512, 128
+lib = nv.lib()
+st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+bf = torch.bfloat16
+g = (torch.randn(M, V * T, device="cuda") * 0.01).to(bf)
+a2 = torch.tanh(torch.randn(M, H, device="cuda")).to(bf)
+w = (torch.randn(V * T, H, device="cuda") * 0.05).to(bf)
+bias = torch.zeros(V * T, device="cuda")
+dW = torch.zeros(V * T, H, device="cuda")
+db = torch.zeros(V * T, device="cuda")
+dz = torch.empty(M, H, device="cuda", dtype=bf)
+mask = torch.zeros(M, V, 4, dtype=torch.int32, device="cuda")
+act = torch.randint(0, A, (M, V), device="cuda").to(torch.uint8)
+lp, en = torch.empty(M, V, device="cuda"), torch.empty(M, V, device="cuda")
+c_lp = torch.randn(M, device="cuda")
+
+
+def gemm(a, a_mn, b, b_mn, Mx, Nx, Kx, c32=None, acc=0, c16=None, mul=None, rows=None):
+    nv.check(lib.vmgym_tc_gemm(a.data_ptr(), a_mn, a.stride(0), b.data_ptr(), b_mn, b.stride(0), Mx, Nx, Kx, None, 0,
+                               mul.data_ptr() if mul is not None else None, mul.stride(0) if mul is not None else 0,
+                               c32.data_ptr() if c32 is not None else None, c32.stride(0) if c32 is not None else 0, acc,
+                               c16.data_ptr() if c16 is not None else None, c16.stride(0) if c16 is not None else 0,
+                               rows.data_ptr() if rows is not None else None, st), "gemm")
+
+
+cases = {
+    "dW3 = g^T a2 (+ row sums)": (lambda: gemm(g, 1, a2, 1, V * T, H, M, c32=dW, acc=1, rows=db), 2.0 * V * T * H * M),
+    "dz2 = (g W3)(1 - a2^2)": (lambda: gemm(g, 0, w, 1, M, H, V * T, c16=dz, mul=a2), 2.0 * V * T * H * M),
+    "fused head forward": (lambda: nv.check(lib.vmgym_policy_fused(a2.data_ptr(), w.data_ptr(), bias.data_ptr(), mask.data_ptr(), act.data_ptr(), M, V, A, H,
+                                                                   0, 0, None, lp.data_ptr(), en.data_ptr(), st), "f"), 2.0 * V * T * H * M),
+    "fused head gradient": (lambda: nv.check(lib.vmgym_policy_fused_grad(a2.data_ptr(), w.data_ptr(), bias.data_ptr(), mask.data_ptr(), act.data_ptr(), M, V, A, H,
+                                                                        c_lp.data_ptr(), -1e-7, g.data_ptr(), g.stride(0), st), "fg"), 2.0 * V * T * H * M),
+}
+for name, (fn, flops) in cases.items():
+    fn(); fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"{name:32s} {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s (padded 128-column tiles)")

@@ -335,13 +335,17 @@ __device__ __forceinline__ void fused_epilogue_row(const FusedOut& fo, const flo
         else fused_chunk<false>(fo, s_bias, r, iw, c0, A, act_given, rnd, st);
     }
     const float ls = __logf(st.ssum);
-    const float H = ls - st.tsum / st.ssum;                          // -sum p log p
+    // The reference normalises in float32: logits - logsumexp with logsumexp = fl(max + log(sum e^(z - max))) (torch Categorical).
+    // For a row whose columns are ALL masked (max = -1e7, float32 spacing 1.0 there) that rounding is visible — log-prob -5.0
+    // instead of -log(101) — so the same rounded log-sum-exp is used here; for ordinary rows it differs by ~1e-6.
+    const float lse = st.m + ls;
+    const float H = (lse - st.m) - st.tsum / st.ssum;                // -sum p log p
     if (e < M) {
         const int act = fo.action_in ? act_given : st.best_a;
         const float za = fo.action_in ? st.z_given : st.best_z;
         const long long o = (long long)e * fo.V + v;
         if (fo.action_out) fo.action_out[o] = (uint8_t)act;
-        if (fo.logprob) fo.logprob[o] = ((unsigned)act < (unsigned)A) ? (za - st.m) - ls : 0.f;
+        if (fo.logprob) fo.logprob[o] = ((unsigned)act < (unsigned)A) ? za - lse : 0.f;
         if (fo.entropy) fo.entropy[o] = H;
     }
     if (fo.g_out) {
@@ -367,7 +371,7 @@ __device__ __forceinline__ void fused_epilogue_row(const FusedOut& fo, const flo
                         const bool dead = ((iw >> (j + t)) & 1u) || a >= A;
                         const float d = x - st.m;
                         const float pa = dead ? 0.f : vmgym::fast_exp(d) * inv_s;
-                        const float lp = d - ls;
+                        const float lp = x - lse;
                         const float gg = dead ? 0.f : clp * ((a == act_given ? 1.f : 0.f) - pa) + (pa > 0.f ? cen * (-pa * (lp + H)) : 0.f);
                         gv[t] = gg;
                     }

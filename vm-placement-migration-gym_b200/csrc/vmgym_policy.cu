@@ -158,7 +158,9 @@ __global__ void __launch_bounds__(256) heads_kernel(const HeadParams p)
         for (int o = 16; o > 0; o >>= 1) { se += __shfl_xor_sync(FULL, se, o); sez += __shfl_xor_sync(FULL, sez, o); }
         const float log_se = logf(se), inv_se = 1.0f / se;
         const float lse = mx + log_se;
-        const float ent = log_se - sez * inv_se;               // Categorical.entropy (0 contribution from masked columns)
+        // Categorical.entropy = -sum p (z - lse) with the float32 log-sum-exp the reference normalises with (0 contribution from
+        // masked columns); (lse - mx) equals log_se except for fully masked rows, where max = -1e7 makes the rounding of lse visible
+        const float ent = (lse - mx) - sez * inv_se;
         // ---- action: given or Gumbel-max sample ----
         int act;
         if (p.action_in) {
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(256) heads_eval_kernel(const HeadParams p)
         if (!live) continue;                           // whole groups only; no shuffles below
         const float log_se = logf(se), inv_se = 1.0f / se;
         const float lse = mx + log_se;
-        const float ent = log_se - sez * inv_se;
+        const float ent = (lse - mx) - sez * inv_se;           // see heads_kernel
         const int act = load_action(arow, p.action_dtype, v);
         float lpa = 0.f;
         if ((unsigned)act < (unsigned)A) {

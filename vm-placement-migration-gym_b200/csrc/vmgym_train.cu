@@ -51,6 +51,9 @@ struct GemmArgs {
     __nv_bfloat16* c_bf16;             // bf16 output [M, ldc_bf16] or nullptr
     long long ldc_bf16;
     float* row_sum;                    // [M]: (+)= sum_k A(m, k), written by the CTAs of the first N tile, or nullptr
+    int tile_n;                        // columns per CTA tile: 256, or 128 when 256-wide tiles would leave SMs idle
+    int k_splits;                      // > 1: split-K (gridDim.z): each CTA contracts a slice of K and adds its partial tile to c_f32 /
+                                       // row_sum atomically (weight-gradient GEMMs with few output tiles and a long sample axis)
 };
 
 // MN-major, 128B-swizzled operand tile: 64-element (128 B) runs along M/N, K rows 128 B apart, 8-row groups 1024 B apart (SBO),
@@ -83,10 +86,14 @@ __global__ void __launch_bounds__(T_THREADS, 1) tc_gemm_kernel(const __grid_cons
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * T_BM, n0 = blockIdx.x * T_BN;
-    const int bn = min(T_BN, (g.N - n0 + 15) & ~15);                 // columns of this tile, rounded up to the MMA's N granularity
-    const int k_blocks = (g.K + T_BK - 1) / T_BK;
+    const int m0 = blockIdx.y * T_BM, n0 = blockIdx.x * g.tile_n;
+    const int bn = min(g.tile_n, (g.N - n0 + 15) & ~15);                 // columns of this tile, rounded up to the MMA's N granularity
+    const int k_blocks_all = (g.K + T_BK - 1) / T_BK;
+    const int kb_per = (k_blocks_all + g.k_splits - 1) / g.k_splits;
+    const int kb0 = blockIdx.z * kb_per;                               // this CTA's K slice: k-blocks [kb0, kb0 + k_blocks)
+    const int k_blocks = max(0, min(kb_per, k_blocks_all - kb0));
     const bool do_rows = g.row_sum != nullptr && blockIdx.x == 0;
+    const bool split = g.k_splits > 1;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -115,23 +122,24 @@ __global__ void __launch_bounds__(T_THREADS, 1) tc_gemm_kernel(const __grid_cons
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
-            const uint32_t a_bytes = T_A_BYTES, b_bytes = (uint32_t)(g.b_mn ? ((bn + 63) / 64) * 8192 : T_B_BYTES);
+            const uint32_t a_bytes = T_A_BYTES, b_bytes = (uint32_t)(g.b_mn ? ((bn + 63) / 64) * 8192 : g.tile_n * T_BK * 2);
             for (int kb = 0; kb < k_blocks; kb++) {
                 const int s = kb % T_STAGES;
                 mbar_wait(&empty_bar[s], (((uint32_t)(kb / T_STAGES)) & 1u) ^ 1u);
                 unsigned char* sa = smem + (size_t)s * T_STAGE_BYTES;
                 unsigned char* sb = sa + T_A_BYTES;
                 mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
+                const int kc = (kb0 + kb) * T_BK;                       // first K index of this block
                 if (g.a_mn) {                                           // two 64 (M) x 64 (K) boxes
-                    tma_load_2d(sa, &map_a, m0, kb * T_BK, &full_bar[s]);
-                    tma_load_2d(sa + 8192, &map_a, m0 + 64, kb * T_BK, &full_bar[s]);
+                    tma_load_2d(sa, &map_a, m0, kc, &full_bar[s]);
+                    tma_load_2d(sa + 8192, &map_a, m0 + 64, kc, &full_bar[s]);
                 } else {
-                    tma_load_2d(sa, &map_a, kb * T_BK, m0, &full_bar[s]);   // one 64 (K) x 128 (M) box
+                    tma_load_2d(sa, &map_a, kc, m0, &full_bar[s]);      // one 64 (K) x 128 (M) box
                 }
                 if (g.b_mn) {
-                    for (int j = 0; j * 64 < bn; j++) tma_load_2d(sb + j * 8192, &map_b, n0 + j * 64, kb * T_BK, &full_bar[s]);
+                    for (int j = 0; j * 64 < bn; j++) tma_load_2d(sb + j * 8192, &map_b, n0 + j * 64, kc, &full_bar[s]);
                 } else {
-                    tma_load_2d(sb, &map_b, kb * T_BK, n0, &full_bar[s]);   // one 64 (K) x 256 (N) box
+                    tma_load_2d(sb, &map_b, kc, n0, &full_bar[s]);      // one 64 (K) x tile_n (N) box
                 }
             }
         }
@@ -157,7 +165,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) tc_gemm_kernel(const __grid_cons
                 }
                 umma_commit(&empty_bar[s]);
             }
-            umma_commit(tmem_full_bar);
+            umma_commit(tmem_full_bar);                                 // (also with an empty K slice: releases the epilogue)
         }
     } else {
         // ===== epilogue: warps 2..5 own TMEM lanes 32 (warp % 4) .. +31 = rows of the tile; thread = row =====
@@ -165,7 +173,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) tc_gemm_kernel(const __grid_cons
         const int row = m0 + q * 32 + lane;
         mbar_wait(tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const bool row_ok = row < g.M;
+        const bool row_ok = row < g.M && k_blocks > 0;                // (an empty K slice of a split launch adds nothing)
 #pragma unroll 1
         for (int c0 = 0; c0 < bn; c0 += 32) {
             uint32_t r[32];
@@ -200,7 +208,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) tc_gemm_kernel(const __grid_cons
                     for (int j = 0; j < nc; j++) { const float f = __bfloat162float(y[j]); v[j] *= 1.0f - f * f; }
                 }
             }
-            if (g.c_f32) {
+            if (g.c_f32 && split) {
+                float* dst = g.c_f32 + (long long)row * g.ldc_f32 + col0;
+#pragma unroll
+                for (int j = 0; j < 32; j++) if (j < nc) atomicAdd(dst + j, v[j]);
+            } else if (g.c_f32) {
                 float* dst = g.c_f32 + (long long)row * g.ldc_f32 + col0;
                 if (nc == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
@@ -232,7 +244,10 @@ __global__ void __launch_bounds__(T_THREADS, 1) tc_gemm_kernel(const __grid_cons
         if (do_rows) {
             uint32_t r[32];
             tmem_ld_row32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)T_BN, r);    // 16 identical columns (+ 16 unused)
-            if (row_ok) g.row_sum[row] = (g.accumulate ? g.row_sum[row] : 0.0f) + __uint_as_float(r[0]);
+            if (row_ok) {
+                if (split) atomicAdd(&g.row_sum[row], __uint_as_float(r[0]));
+                else g.row_sum[row] = (g.accumulate ? g.row_sum[row] : 0.0f) + __uint_as_float(r[0]);
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -274,6 +289,27 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, long long rows, i
             h[t] = __floats2bfloat162_rn(a, b);
         }
         *reinterpret_cast<uint4*>(dst + r * cols_pad + c) = u;
+    }
+}
+
+// fp32 [rows, cols] -> bf16 [rows, 3 * cols_pad]: the value split into hi = bf16(x) and lo = bf16(x - hi) and laid out as
+// [hi | lo | hi] (order 0, activations) or [hi | hi | lo] (order 1, weights), so that ONE bf16 GEMM over the concatenated K
+// computes x_hi w_hi + x_lo w_hi + x_hi w_lo = x w to ~2^-16 relative — used for the first layer, whose inputs are raw
+// observations (PM indices up to P + 1 next to sizes in [0, 1]): plain bf16 operands lose the low bits that matter there.
+__global__ void cast_split_kernel(const float* __restrict__ src, long long rows, int cols, long long lds, __nv_bfloat16* __restrict__ dst, int cols_pad,
+                                  int order)
+{
+    const long long total = rows * cols_pad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cols_pad;
+        const int c = (int)(i - r * cols_pad);
+        const float x = c < cols ? src[r * lds + c] : 0.0f;
+        const __nv_bfloat16 hi = __float2bfloat16(x);
+        const __nv_bfloat16 lo = __float2bfloat16(x - __bfloat162float(hi));
+        __nv_bfloat16* d = dst + r * 3ll * cols_pad + c;
+        d[0] = hi;
+        d[cols_pad] = order == 0 ? lo : hi;
+        d[2 * cols_pad] = order == 0 ? hi : lo;
     }
 }
 
@@ -393,10 +429,19 @@ extern "C" int vmgym_tc_gemm(const void* d_a, int32_t a_mn, int64_t lda, const v
         vmgym_internal_set_error("vmgym_tc_gemm: operand row strides must be multiples of 8 elements and bases 16-byte aligned (TMA)");
         return VMGYM_EINVAL;
     }
+    int n_sm = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
+    const long long m_tiles = (M + T_BM - 1) / T_BM;
+    const int tile_n = (((N + T_BN - 1) / T_BN) * m_tiles < n_sm && N > 128) ? 128 : T_BN;   // narrower tiles when 256-wide ones leave SMs idle
     CUtensorMap map_a, map_b;
     // K-major operand: tensor [rows, K], box = 64 (K) x tile rows.  MN-major operand: tensor [K, rows], box = 64 (rows) x 64 (K).
     const int ra = a_mn ? make_map2(&map_a, d_a, K, M, lda, 64, 64) : make_map2(&map_a, d_a, M, K, lda, T_BK, T_BM);
-    const int rb = b_mn ? make_map2(&map_b, d_b, K, N, ldb, 64, 64) : make_map2(&map_b, d_b, N, K, ldb, T_BK, T_BN);
+    const int rb = b_mn ? make_map2(&map_b, d_b, K, N, ldb, 64, 64) : make_map2(&map_b, d_b, N, K, ldb, T_BK, tile_n);
     if (ra || rb) {
         vmgym_internal_set_error("vmgym_tc_gemm: cuTensorMapEncodeTiled failed");
         return VMGYM_ECUDA;
@@ -411,7 +456,22 @@ extern "C" int vmgym_tc_gemm(const void* d_a, int32_t a_mn, int64_t lda, const v
     g.bias = d_bias; g.act = act; g.mul_y = (const __nv_bfloat16*)d_mul_y; g.ldy = ldy;
     g.c_f32 = d_c_f32; g.ldc_f32 = ldc_f32; g.accumulate = accumulate;
     g.c_bf16 = (__nv_bfloat16*)d_c_bf16; g.ldc_bf16 = ldc_bf16; g.row_sum = d_row_sum;
-    dim3 grid((unsigned)((N + T_BN - 1) / T_BN), (unsigned)((M + T_BM - 1) / T_BM));
+    // split-K for accumulating fp32 outputs with too few tiles to fill the machine (dW = dz^T a over tens of thousands of samples
+    // into a 512 x 512 matrix is 8 tiles): slices of the sample axis on gridDim.z, partial tiles added atomically
+    g.tile_n = tile_n;
+    const long long tiles = ((N + tile_n - 1) / tile_n) * m_tiles;
+    const long long k_blocks = (K + T_BK - 1) / T_BK;
+    g.k_splits = 1;
+    if (accumulate && d_c_f32 && !d_c_bf16 && !d_mul_y && !d_bias && act == 0 && tiles < n_sm && k_blocks >= 16) {
+        long long sp = (2ll * n_sm + tiles - 1) / tiles;
+        if (sp > k_blocks / 8) sp = k_blocks / 8;                       // at least 8 k-blocks per slice
+        if (sp > 1) {
+            const long long per = (k_blocks + sp - 1) / sp;
+            sp = (k_blocks + per - 1) / per;                            // no empty slice
+        }
+        g.k_splits = (int)(sp < 1 ? 1 : sp);
+    }
+    dim3 grid((unsigned)((N + tile_n - 1) / tile_n), (unsigned)m_tiles, (unsigned)g.k_splits);
     tc_gemm_kernel<<<grid, T_THREADS, T_SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_b, g);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { vmgym_internal_set_error(cudaGetErrorString(e)); return VMGYM_ECUDA; }
@@ -429,6 +489,21 @@ extern "C" int vmgym_cast_pad_bf16(const float* d_src, int64_t rows, int64_t col
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     vmgym_train::cast_pad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_src, rows, (int)cols, lds, (__nv_bfloat16*)d_dst_bf16, (int)cols_pad);
+    return cudaGetLastError() == cudaSuccess ? VMGYM_OK : VMGYM_ECUDA;
+}
+
+extern "C" int vmgym_cast_split_bf16(const float* d_src, int64_t rows, int64_t cols, int64_t lds, void* d_dst_bf16, int64_t cols_pad, int32_t order,
+                                     void* stream)
+{
+    if (!d_src || !d_dst_bf16 || rows < 0 || cols < 1 || cols_pad < cols || (cols_pad & 7) || ((uintptr_t)d_dst_bf16 & 15) || (order != 0 && order != 1)) {
+        vmgym_internal_set_error("vmgym_cast_split_bf16: bad arguments (cols_pad must be a multiple of 8 >= cols, order 0 or 1)");
+        return VMGYM_EINVAL;
+    }
+    if (rows == 0) return VMGYM_OK;
+    long long blocks = (rows * cols_pad + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    vmgym_train::cast_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_src, rows, (int)cols, lds, (__nv_bfloat16*)d_dst_bf16,
+                                                                                       (int)cols_pad, order);
     return cudaGetLastError() == cudaSuccess ? VMGYM_OK : VMGYM_ECUDA;
 }
 

@@ -69,7 +69,7 @@ SCALARS_BYTES = 80
 EXPORTS = ["vmgym_last_error", "vmgym_abi_version", "vmgym_get_layout", "vmgym_reset", "vmgym_step",
            "vmgym_agent_step", "vmgym_agent_step_rotation", "vmgym_agent_act", "vmgym_observe", "vmgym_invalid_action_mask", "vmgym_set_tuning",
            "vmgym_policy_heads", "vmgym_policy_heads_backward", "vmgym_gae", "vmgym_drlvmp_choice", "vmgym_drlvmp_iter", "vmgym_linear_bf16", "vmgym_policy_fused", "vmgym_segtree_update",
-           "vmgym_segtree_retrieve", "vmgym_vmstats_finalize", "vmgym_per_sample", "vmgym_c51_project", "vmgym_adamw_step", "vmgym_tc_gemm", "vmgym_cast_pad_bf16",
+           "vmgym_segtree_retrieve", "vmgym_vmstats_finalize", "vmgym_per_sample", "vmgym_c51_project", "vmgym_adamw_step", "vmgym_tc_gemm", "vmgym_cast_pad_bf16", "vmgym_cast_split_bf16",
            "vmgym_value_head", "vmgym_value_head_backward", "vmgym_ppo_loss", "vmgym_policy_fused_grad"]
 
 
@@ -153,6 +153,7 @@ def lib():
     L.vmgym_adamw_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, f32, vp, vp, vp, vp, vp]
     L.vmgym_tc_gemm.argtypes = [vp, i32, i64, vp, i32, i64, i64, i64, i64, vp, i32, vp, i64, vp, i64, i32, vp, i64, vp, vp]
     L.vmgym_cast_pad_bf16.argtypes = [vp, i64, i64, i64, vp, i64, vp]
+    L.vmgym_cast_split_bf16.argtypes = [vp, i64, i64, i64, vp, i64, i32, vp]
     L.vmgym_value_head.argtypes = [vp, i64, i32, vp, vp, vp, vp]
     L.vmgym_value_head_backward.argtypes = [vp, i64, i32, vp, vp, vp, vp, vp, vp]
     L.vmgym_ppo_loss.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, f32, f32, f32, i32, f32, vp, vp, vp, vp]

@@ -52,6 +52,9 @@ class PPOConfig:
     device: str = "cuda"
     env_chunk: int = 2048          # samples (env-steps) per forward/backward chunk inside a minibatch (gradient accumulation)
     fused_rollout: bool = False    # rollouts through the fused tcgen05 actor head (bf16 operands; action_dim <= 128)
+    update_math: str = "auto"      # "bf16": forward + backward of update() and the rollout forward on the hand-written tcgen05 kernels
+                                   # (vmgym/ppo_tc.py; needs action_dim <= 128, hidden % 64 == 0, hidden <= 512); "fp32": torch
+                                   # autograd on fp32 layers — the parity mode against the reference; "auto": bf16 where supported
     vf_broadcast: bool = False     # reference-exact value loss: ppo.py:274-277 subtracts returns [mb] from newvalues [mb, 1], which
                                    # broadcasts to [mb, mb] (every value against every return); False = the elementwise loss it
                                    # evidently means (DESIGN.md §2 "intentional deviations").  O(mb^2) memory: small batches only
@@ -260,6 +263,30 @@ class PPOAgent(AgentBase):
         self._grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.adam = dict(beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01)    # torch.optim.AdamW defaults (ppo.py:143)
 
+    def _tc_network(self):
+        """The tensor-core network (vmgym/ppo_tc.py) when config.update_math selects it and the shape allows it, else None."""
+        mode = self.config.update_math
+        if mode not in ("auto", "bf16", "fp32"):
+            raise ValueError("update_math must be 'auto', 'bf16' or 'fp32'")
+        H = self.config.hidden_size
+        ok = self.A <= 128 and H <= 512 and H % 64 == 0 and not self.config.vf_broadcast and self.vec.place_dtype == torch.uint8
+        if mode == "fp32" or (mode == "auto" and not ok):
+            return None
+        if not ok:
+            raise nv.VmgymError("update_math='bf16' needs action_dim <= 128, hidden % 64 == 0, hidden <= 512 and vf_broadcast off")
+        if getattr(self, "_tc", None) is None:
+            from .ppo_tc import TensorCoreNetwork
+            self._tc = TensorCoreNetwork(self, self.config.env_chunk)
+        return self._tc
+
+    def _mask4(self, mask):
+        """Packed mask rows padded to the 4 words the fused tensor-core head reads per (env, VM)."""
+        if mask is None or mask.shape[-1] == 4:
+            return mask
+        out = torch.zeros(mask.shape[:-1] + (4,), dtype=torch.int32, device=mask.device)
+        out[..., :mask.shape[-1]] = mask
+        return out
+
     def _optim_step(self, grad_scale: float = 1.0):
         """clip_grad_norm_(max_grad_norm) + AdamW step (ppo.py:284-287) unless the device-side skip flag is set."""
         cfg, a = self.config, self.adam
@@ -285,6 +312,14 @@ class PPOAgent(AgentBase):
         sd = {k[len("_orig_mod."):] if k.startswith("_orig_mod.") else k: v for k, v in sd.items()}
         self.model.load_state_dict(sd)
         self.model.eval()
+        self.weights_changed()
+
+    def weights_changed(self):
+        """Call after writing the parameters from outside (load_state_dict, broadcast): re-derives the bf16 operand copies."""
+        if getattr(self, "_tc", None) is not None:
+            self._tc.refresh()
+        elif self._fused is not None:
+            self._fused.refresh()
 
     def _heads(self, logits, migration_ratio: float, want_mask: bool):
         vec = self.vec
@@ -317,14 +352,13 @@ class PPOAgent(AgentBase):
     def fused_sample(self, obs, migration_ratio: float = -1.0):
         """Rollout forward on tensor cores: obs -> hidden (torch) -> fused output layer + heads (tcgen05, bf16 operands).
         Returns (action u8 [N, V], logprob [N], entropy [N], packed mask).  Needs action_dim <= 128."""
+        tc = self._tc_network()
         if self._fused is None:
             self._fused = FusedActorHead(self.model.actor[4], self.V, self.A)
-        hidden = self.model.actor[:4](obs)
-        mask = self._mask_bits(migration_ratio) if self.mask_words == 4 else None
-        if mask is None and self.config.masked:
-            raise nv.VmgymError("fused head expects 4 mask words per row (96 < action_dim <= 128)")
+        hidden = tc.actor_hidden(obs) if tc is not None else self.model.actor[:4](obs)
+        mask = self._mask_bits(migration_ratio)
         self._calls += 1
-        action, lp, ent = self._fused(hidden, mask if self.config.masked else None, self.seed, self._calls)
+        action, lp, ent = self._fused(hidden, self._mask4(mask) if self.config.masked else None, self.seed, self._calls)
         return action, lp, ent, mask
 
     @torch.no_grad()
@@ -450,6 +484,15 @@ class PPOAgent(AgentBase):
         ccfg = self.vec._ccfg()
         n_mb = obs_mb.shape[0]
         self._flat_grad.zero_()
+        tc = self._tc_network()
+        if tc is not None:
+            # hand-written forward + backward (vmgym/ppo_tc.py); obs_mb is the bf16 operand cache built once per update
+            tc.begin_minibatch()
+            for s0 in range(0, n_mb, cfg.env_chunk):
+                s1 = min(n_mb, s0 + cfg.env_chunk)
+                tc.forward_backward(obs_mb[s0:s1], mask_mb[s0:s1] if mask_mb is not None else None, act_mb[s0:s1], lp_mb[s0:s1],
+                                    adv_mb[s0:s1].contiguous(), val_mb[s0:s1], ret_mb[s0:s1], n_total)
+            return tc.end_minibatch()
         logratio_sum = torch.zeros((), dtype=torch.float64, device=self.device)
         loss_sum = torch.zeros((), dtype=torch.float64, device=self.device)
         if cfg.vf_broadcast and n_mb > cfg.env_chunk:
@@ -505,9 +548,16 @@ class PPOAgent(AgentBase):
         T, N = reward.shape
         dist = torch.distributed
         world = dist.get_world_size() if self.data_parallel and dist.is_available() and dist.is_initialized() else 1
+        tc = self._tc_network()
         with torch.no_grad():
-            values = self.model.get_value(obs.reshape(T * N, -1)).reshape(T, N)
-            next_values = self.model.get_value(next_obs.reshape(T * N, -1)).reshape(T, N)
+            if tc is not None:
+                values = tc.values(obs).reshape(T, N)
+                next_values = tc.values(next_obs).reshape(T, N)
+                obs = tc.cast_obs(obs).reshape(T, N, tc.Dx)             # bf16 operand of every minibatch pass, cast once
+                mask = self._mask4(mask)
+            else:
+                values = self.model.get_value(obs.reshape(T * N, -1)).reshape(T, N)
+                next_values = self.model.get_value(next_obs.reshape(T * N, -1)).reshape(T, N)
             advantages, returns = gae(reward, values, next_values, done, cfg.gamma, cfg.lamda)
         stats = {}
         attempts = []
@@ -530,7 +580,7 @@ class PPOAgent(AgentBase):
                 adv_mb = self._normalise_advantages(advantages[t0:t1], world)
                 # the minibatch as one flat list of samples (time-major rollout -> these are views)
                 obs_mb, act_mb = obs[t0:t1].reshape(n_mb, D), action[t0:t1].reshape(n_mb, self.V)
-                mask_mb = mask[t0:t1].reshape(n_mb, self.V, self.mask_words)
+                mask_mb = mask[t0:t1].reshape(n_mb, self.V, mask.shape[-1])
                 lp_mb, val_mb, ret_mb = logprob[t0:t1].reshape(-1), values[t0:t1].reshape(-1), returns[t0:t1].reshape(-1)
                 logratio_sum, loss_sum = self._minibatch_backward(obs_mb, act_mb, mask_mb, lp_mb, adv_mb, val_mb, ret_mb, n_mb * world)
                 # KL early stop on the whole (global) minibatch (ppo.py:263-264): the reference breaks before its backward;
@@ -544,6 +594,8 @@ class PPOAgent(AgentBase):
                 if cfg.kl_max is not None:
                     self._opt_skip.logical_or_(kl_dev > cfg.kl_max)    # sticky until the end of the epoch
                 self._optim_step()
+                if tc is not None:
+                    tc.refresh()
                 if debug:
                     torch.cuda.synchronize(self.device)
                     skipped = int(self._opt_skip.item()) != 0
