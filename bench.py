@@ -251,8 +251,9 @@ def gpu_arm(args):
         hv.act(); hv.step()
         changed += sum(int((g.vec.obs != p_).sum().item()) for g, p_ in zip(hv.groups, prev))
     d2h_obs = changed / 10 * 4
-    # the same loop with the full observation copied device->host every step (copy engine) instead of the changed entries
-    hv1 = HostVecEnv(Config(**cfg), E, groups=8, device=dev, rng="philox", agent="bestfit", delta_obs=False,
+    # the same loop as round 1 ran it: the agent's input re-uploaded from the host observation buffer every step (19 MB H2D per
+    # 4096 envs) — what a caller pays when it hands act() observations of its own instead of the env's buffer
+    hv1 = HostVecEnv(Config(**cfg), E, groups=args.e2e_groups, device=dev, rng="philox", agent="bestfit", resident_obs=False,
                      seeds=cfg["seed"] + 3 * 10**6 + rank * E + np.arange(E, dtype=np.int64))
     hv1.fast_forward(WARM_STEPS)
     hv1.run_pipelined(3)
@@ -426,11 +427,14 @@ def gpu_arm(args):
         "timing_stats": {"replays": R, "steps_per_replay": K, "median_ms": total_ms, "p10_ms": p10_ms, "p90_ms": p90_ms,
                          "mean_ms": mean_ms, "spread": (p90_ms - p10_ms) / total_ms},
         "e2e": {"value": world * E * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": Ke, "groups": args.e2e_groups, "full_obs_copy_value": world * E * Ke / e2e1_s,
-                "path": "HostVecEnv: BestFitAgent.act(host obs) -> host action -> VecVmEnv.step(host action) -> host obs/reward/done in "
-                        "pinned host buffers; envs split into stream groups whose PCIe transfers overlap; the step kernel keeps the host "
-                        "observation buffer current by storing only the entries that changed (d2h_bytes_per_step = actions + measured "
-                        "changed observation entries + reward/done; full_obs_copy_value: the same loop copying all 4(3V+2P) bytes per env)"},
+                "steps": Ke, "groups": args.e2e_groups, "obs_reupload_value": world * E * Ke / e2e1_s,
+                "obs_reupload_h2d_bytes_per_step": E * D * 4 + E * V,
+                "path": "HostVecEnv: action = agent.act(); obs, reward, done = env.step(action) with HOST (pinned) action / observation / "
+                        "reward / done buffers. Per step the actions cross PCIe twice (agent kernel -> host buffer, host buffer -> step "
+                        "kernel) and the step kernel stores reward, done and the CHANGED observation entries to the host buffers "
+                        "(d2h_bytes_per_step = actions + measured changed entries + reward/done). The host observation buffer is a mirror "
+                        "the env keeps current, so act() on it reads the identical device copy instead of re-uploading 4(3V+2P) bytes per "
+                        "env; obs_reupload_value = the round-1 loop that re-uploads it every step (what act(obs) costs for a caller's own array)"},
         "per_launch": {"value": world * E / (per_launch_ms * 1e-3), "unit": UNIT, "ms_per_step": per_launch_ms,
                        "note": "round-1 protocol: the same rotation as K separate launches of the fused step kernel in one CUDA graph "
                                "(programmatic dependent launch), median of 10 replays",

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define VMGYM_ABI_VERSION 6
+#define VMGYM_ABI_VERSION 7
 
 enum vmgym_status {
     VMGYM_OK = 0,
@@ -63,7 +63,11 @@ typedef struct vmgym_layout {
     int32_t place_bytes;        /* 1 (P <= 253) or 2 */
     int32_t off_cpu;            /* f64[P]  PM cpu utilisation accumulators (env.py:190) */
     int32_t off_memory;         /* f64[P]  PM memory utilisation accumulators (env.py:191) */
-    int32_t off_remaining;      /* u16[V]  vm_remaining_runtime (env.py:192) */
+    int32_t off_remaining;      /* u16[V]  vm_remaining_runtime (env.py:192).  WAITING slots hold the steps left; RUNNING slots hold the
+                                   step in which the VM departs, modulo 2^16 (placed in step t with r steps left: t + r - 1), so that
+                                   no counter is decremented per step.  With T = the record's timestep (the next step to run),
+                                   steps left of a running slot = ((value - T) & 0xffff) + 1.  A u32 "earliest departure step"
+                                   follows the scalars at off_scalars + sizeof(vmgym_env_scalars) + 16. */
     int32_t off_placement;      /* u8|u16[V] vm_placement: 0..P-1 running, P waiting, P+1 empty (env.py:187) */
     int32_t off_cpu_code;       /* u8[V]   vm_cpu in hundredths, bit 7 = vm_suspended (env.py:188,204) */
     int32_t off_mem_code;       /* u8[V]   vm_memory in hundredths (env.py:189) */

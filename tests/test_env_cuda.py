@@ -546,8 +546,9 @@ def test_empty_batch_and_bad_arguments():
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("use_graphs,zero_copy,delta_obs", [(True, True, True), (False, True, True), (True, True, False), (True, False, False)])
-def test_host_vec_env_pipelined_equals_fused_device_rollout(use_graphs, zero_copy, delta_obs):
+@pytest.mark.parametrize("use_graphs,zero_copy,delta_obs,resident", [(True, True, True, True), (False, True, True, True), (True, True, False, True),
+                                                                     (True, False, False, True), (True, True, True, False), (False, False, False, False)])
+def test_host_vec_env_pipelined_equals_fused_device_rollout(use_graphs, zero_copy, delta_obs, resident):
     """HostVecEnv (host obs/action buffers, 3 groups on 3 streams, split-phase pipelining) runs the same envs as one
     VecVmEnv stepping the fused best-fit kernel: identical observations, rewards and counters after 60 steps."""
     import torch
@@ -556,7 +557,8 @@ def test_host_vec_env_pipelined_equals_fused_device_rollout(use_graphs, zero_cop
     cfg = Config(pms=100, vms=300, arrival_rate=1.8182, service_length=1000, training_steps=10000, eval_steps=100000,
                  reward_function="wr", allow_null_action=True)
     N = 50
-    hv = HostVecEnv(cfg, N, groups=3, agent="bestfit", use_graphs=use_graphs, zero_copy=zero_copy, delta_obs=delta_obs)
+    hv = HostVecEnv(cfg, N, groups=3, agent="bestfit", use_graphs=use_graphs, zero_copy=zero_copy, delta_obs=delta_obs, resident_obs=resident)
+    assert hv.h2d_bytes_per_step == N * 300 + (0 if resident else N * 1100 * 4)
     obs0 = hv.reset().clone()
     ref = VecVmEnv(cfg, N, rng="philox")
     assert torch.equal(obs0, ref.observe().cpu())
@@ -574,6 +576,14 @@ def test_host_vec_env_pipelined_equals_fused_device_rollout(use_graphs, zero_cop
         if k != "status":                              # the fused kernel's QUIET flag is not part of the env's state
             assert np.array_equal(np.asarray(c[k]), np.asarray(rc[k])), k
     assert c["place_actions"].sum() > 0
+    # act() on a caller's own observation array uploads it and leaves the env's buffers alone
+    mine = hv.obs.clone().numpy()
+    a_env = hv.act().clone()
+    a_mine = hv.act(mine).clone()
+    assert torch.equal(a_env, a_mine)
+    mine[:, 3 * hv.V:] = 1.0                           # every PM full: best-fit proposes nothing, all actions = current placement
+    a_full = hv.act(mine)
+    assert torch.equal(a_full.long(), hv.obs[:, :hv.V].long()) and torch.equal(hv.obs, robs.cpu())
     # explicit host actions: an all-WAIT/NULL-preserving no-op action leaves placements unchanged
     act = hv.obs[:, :hv.V].to(hv.place_dtype).numpy()
     o2, _, _ = hv.step(act)

@@ -69,7 +69,8 @@ static int make_layout(const vmgym_config* c, DevLayout* L, vmgym_layout* pub)
     l.off_memc = l.off_cpuc + l.Vp;
     l.off_cap = l.off_memc + l.Vp;
     l.off_scal = l.off_cap + align_up(2 * l.Pp, 16);
-    l.rec_bytes = align_up(l.off_scal + (int)sizeof(vmgym_env_scalars) + 16, 128);   // + 16 B: parked Philox words (arrival draws)
+    // + 16 B: parked Philox words (arrival draws), + 16 B: next-departure clock (u32) and reserve
+    l.rec_bytes = align_up(l.off_scal + (int)sizeof(vmgym_env_scalars) + 16 + 16, 128);
     layout_scratch(l, pb, false);
     l.svc_cdf_smem = 0;                                    // service table stays in global memory (used on admissions only)
     l.sm_tables = align_up(SIZE_TABLE * 8 + SIZE_TABLE * 4 + ARR_CDF_SMEM * 8 + l.svc_cdf_smem * 8 + (SVC_BRACKETS + 1) * 2, 128);

@@ -74,6 +74,12 @@ struct Env {
     // rcap[p] = kc | km << 8 with kc = max{k : (float)cpu[p] + sz32[k] <= 1.0f} (likewise km for memory)
     __device__ __forceinline__ uint16_t* rcap() const { return reinterpret_cast<uint16_t*>(VMGYM_SMEM(rec) + L->off_cap); }
     __device__ __forceinline__ vmgym_env_scalars* sc() const { return reinterpret_cast<vmgym_env_scalars*>(VMGYM_SMEM(rec) + L->off_scal); }
+    // earliest step at which a running VM departs (absolute; 0xffffffff = no running VM; may be stale-early after a suspension):
+    // lives behind the scalars and the parked Philox words.  While timestep < next_dep the service countdown has nothing to do.
+    __device__ __forceinline__ uint32_t* next_dep() const
+    {
+        return reinterpret_cast<uint32_t*>(VMGYM_SMEM(rec) + L->off_scal + sizeof(vmgym_env_scalars) + 16);
+    }
     // scratch (not part of the record)
     __device__ __forceinline__ float* cpu32() const { return reinterpret_cast<float*>(VMGYM_SMEM(base) + L->sm_cpu32); }  // agents' fp32 view
     __device__ __forceinline__ float* mem32() const { return reinterpret_cast<float*>(VMGYM_SMEM(base) + L->sm_mem32); }
@@ -260,24 +266,28 @@ __device__ __forceinline__ void team_phase(const Env<PT>& e, int cmd, int tid, i
             if ((tid & 31) == 0) cm[v0 >> 5] = m;
         }
     } else if (cmd == TEAM_COUNTDOWN) {
-        // running VMs: remaining -= 1 if > 0 (env.py:245-247); the slots that reach 0 are reported as a bitmap
-        // (and the empty slots as a second bitmap, for the admission of arrivals)
+        // running VMs whose departure step is this step (ctl[1], env.py:245-249) are reported as a bitmap, the empty slots as a
+        // second bitmap (for the admission of arrivals), and the earliest later departure as a distance in ctl[2] (atomicMin)
         const PT* place = e.place();
-        uint16_t* rem = e.rem();
+        const uint16_t* rem = e.rem();
         unsigned* tmk = e.tmask();
         unsigned* emk = e.emask();
+        const uint32_t now16 = (uint32_t)e.ctl()[1] & 0xffffu;
+        unsigned dmin = 0xffffffffu;
         for (int v0 = (tid & ~31); v0 < V; v0 += nth) {
             const int v = v0 + (tid & 31);
             const int pl = v < V ? (int)place[v] : P;
             bool term = false;
             if (pl < P) {
-                int r = (int)rem[v];
-                if (r > 0) { r -= 1; rem[v] = (uint16_t)r; }
-                term = r == 0;
+                const uint32_t d = ((uint32_t)rem[v] - now16) & 0xffffu;       // steps until this VM departs
+                term = d == 0u;
+                if (!term) dmin = min(dmin, d);
             }
             const unsigned m = __ballot_sync(FULL, term), em = __ballot_sync(FULL, pl == P + 1);
             if ((tid & 31) == 0) { tmk[v0 >> 5] = m; emk[v0 >> 5] = em; }
         }
+        dmin = __reduce_min_sync(FULL, dmin);
+        if ((tid & 31) == 0) atomicMin(reinterpret_cast<unsigned*>(const_cast<int*>(e.ctl())) + 2, dmin);
     } else if (cmd == TEAM_FIT) {
         // scatter pass of the fit table (see rebuild_fit_table): fitm[kc] = max(km + 1), plus the two global maxima in
         // ctl[1] / ctl[2] (zeroed by the main warp)
@@ -794,6 +804,11 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                             __syncwarp();
                             if (lane == 0) {                                                                   // :82-85
                                 cpu[a] = nc; mem[a] = nm; place[vv] = (PT)a; cpuc[vv] &= 0x7f;
+                                // a VM placed in step t with r steps left ticks in step t already (:245-247 run after the apply
+                                // loop) and departs in step t + r - 1: running slots hold that step (mod 2^16) instead of a counter
+                                const uint32_t fin = tnow + (uint32_t)rem[vv] - 1u;
+                                rem[vv] = (uint16_t)fin;
+                                if (fin < *e.next_dep()) *e.next_dep() = fin;
                                 e.rcap()[a] = (uint16_t)(max_code(e.sz32, (float)nc) | (max_code(e.sz32, (float)nm) << 8));
                                 if (vmstat) {
                                     uint32_t* s = vs.slots + vv * 4;
@@ -812,6 +827,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
                         __syncwarp();
                         if (lane == 0) {
                             cpu[cv] = nc; mem[cv] = nm; place[vv] = (PT)P; cpuc[vv] |= 0x80;
+                            rem[vv] = (uint16_t)((((uint32_t)rem[vv] - tnow) & 0xffffu) + 1u);     // back to "steps left" (next_dep may go stale-early)
                             e.rcap()[cv] = (uint16_t)(max_code(e.sz32, (float)nc) | (max_code(e.sz32, (float)nm) << 8));
                             if (vmstat) vs.slots[vv * 4 + 3] = tnow;                           // WAIT samples start at this step
                         }
@@ -841,134 +857,8 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
         for (int v = lane; v < V; v += 32) valid_g[v] = 1;
     }
 
-    // ---- 2+3. service countdown and departures in VM-index order (_run_vms, env.py:244-265) ----
-    int served = 0;
-    bool need_full_refresh = false;
-    int freed0 = -1, freed1 = -1, freed2 = -1, freed3 = -1;    // first slots freed by this step's departures (slot order)
-    if (sizeof(PT) == 1) {
-        // 4 slots per lane: placement bytes as one u32, remaining runtimes as 4 x u16 (padding slots are empty)
-        const uint32_t P4 = (uint32_t)P * 0x01010101u;
-        const uint32_t* pl4 = reinterpret_cast<const uint32_t*>(place);
-        uint2* rem4 = reinterpret_cast<uint2*>(rem);
-        const int groups = (V + 3) >> 2;
-        for (int g0 = 0; g0 < groups; g0 += 32) {
-            const int g = g0 + lane;
-            unsigned term4 = 0;
-            if (g < groups) {
-                const uint32_t run = __vcmpltu4(pl4[g], P4);            // 0xff per running slot
-                if (run) {
-                    uint2 r = rem4[g];
-                    const uint32_t dlo = (run & 1u) | ((run & 0x100u) << 8), dhi = ((run >> 16) & 1u) | ((run >> 8) & 0x10000u);
-                    r.x = __vsubus2(r.x, dlo);                           // if remaining > 0: remaining -= 1 (:245-247)
-                    r.y = __vsubus2(r.y, dhi);
-                    rem4[g] = r;
-                    const uint32_t zlo = __vcmpeq2(r.x, 0u), zhi = __vcmpeq2(r.y, 0u);
-                    term4 = ((zlo & 1u) | ((zlo >> 15) & 2u) | ((zhi & 1u) << 2) | ((zhi >> 13) & 8u)) &
-                            ((run & 1u) | ((run >> 7) & 2u) | ((run >> 14) & 4u) | ((run >> 21) & 8u));
-                }
-            }
-            unsigned m = __ballot_sync(FULL, term4 != 0);
-            if (m) {                                                      // some VM finished (:248-265)
-                __syncwarp();
-                while (m) {
-                    const int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    unsigned t4 = __shfl_sync(FULL, term4, b);
-                    for (unsigned tt = t4; tt; tt &= tt - 1) {
-                        const int vf = 4 * (g0 + b) + __ffs(tt) - 1;
-                        if (served == 0) freed0 = vf; else if (served == 1) freed1 = vf; else if (served == 2) freed2 = vf;
-                        else if (served == 3) freed3 = vf;
-                        served++;
-                    }
-                    if (lane == 0) {
-                        while (t4) {
-                            const int j = __ffs(t4) - 1;
-                            t4 &= t4 - 1;
-                            const int vv = 4 * (g0 + b) + j, pm = (int)place[vv];
-                            cpu[pm] -= e.sz64[cpuc[vv] & 0x7f];
-                            mem[pm] -= e.sz64[memc[vv]];
-                            if (cpu[pm] < 1e-7) cpu[pm] = 0.0;           // :267-268 clamp, applied here for this PM
-                            if (mem[pm] < 1e-7) mem[pm] = 0.0;
-                            refresh_cap(e, pm);
-                            place[vv] = (PT)(P + 1); cpuc[vv] = 0; memc[vv] = 0; rem[vv] = 0;
-                            if (vmstat) vmstat_close(vs.slots + vv * 4, tnow - vs.slots[vv * 4], 0u, vs.hist, vs.totals);
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-        }
-    } else if (TM) {
-        // team countdown -> bitmap of the slots that finished; the main warp retires them in slot order exactly like the
-        // byte-placement path above (per-PM subtraction, 1e-7 clamp and capacity-code refresh)
-        team_run(e, TEAM_COUNTDOWN, nth);
-        const unsigned* tmk = e.tmask();
-        const int n_chunks = (V + 31) / 32;
-        for (int cb0 = 0; cb0 < n_chunks; cb0 += 32) {
-            unsigned nz = __ballot_sync(FULL, cb0 + lane < n_chunks && tmk[cb0 + lane] != 0u);
-            while (nz) {
-                const int c = cb0 + __ffs(nz) - 1;
-                nz &= nz - 1;
-                unsigned mm = tmk[c];
-                served += __popc(mm);
-                if (lane == 0) {
-                    while (mm) {
-                        const int vv = 32 * c + __ffs(mm) - 1, pm = (int)place[vv];
-                        mm &= mm - 1;
-                        cpu[pm] -= e.sz64[cpuc[vv] & 0x7f];
-                        mem[pm] -= e.sz64[memc[vv]];
-                        if (cpu[pm] < 1e-7) cpu[pm] = 0.0;           // :267-268 clamp, applied here for this PM
-                        if (mem[pm] < 1e-7) mem[pm] = 0.0;
-                        refresh_cap(e, pm);
-                        place[vv] = (PT)(P + 1); cpuc[vv] = 0; memc[vv] = 0; rem[vv] = 0;
-                        e.emask()[vv >> 5] |= 1u << (vv & 31);         // empty from now on (admissions below)
-                        if (vmstat) vmstat_close(vs.slots + vv * 4, tnow - vs.slots[vv * 4], 0u, vs.hist, vs.totals);
-                    }
-                }
-                __syncwarp();
-            }
-        }
-    } else {
-        for (int c0 = 0; c0 < V; c0 += 32) {
-            const int v = c0 + lane;
-            const int pl = v < V ? (int)place[v] : P + 1;
-            int r = v < V ? (int)rem[v] : 0;
-            const bool running = pl < P;
-            if (running && r > 0) { r -= 1; rem[v] = (uint16_t)r; }
-            const bool term = running && r == 0;
-            unsigned m = __ballot_sync(FULL, term);
-            served += __popc(m);
-            if (m) {
-                if (lane == 0) {
-                    unsigned mm = m;
-                    while (mm) {
-                        const int b = __ffs(mm) - 1;
-                        mm &= mm - 1;
-                        const int vv = c0 + b, pm = (int)place[vv];
-                        cpu[pm] -= e.sz64[cpuc[vv] & 0x7f];
-                        mem[pm] -= e.sz64[memc[vv]];
-                        if (vmstat) vmstat_close(vs.slots + vv * 4, tnow - vs.slots[vv * 4], 0u, vs.hist, vs.totals);
-                    }
-                }
-                __syncwarp();
-                if (term) { place[v] = (PT)(P + 1); cpuc[v] = 0; memc[v] = 0; rem[v] = 0; }
-                need_full_refresh = true;
-            }
-        }
-    }
-    __syncwarp();
-    // ---- 4. clamp (env.py:267-268): values only shrink when something was subtracted this step ----
-    if ((served > 0 && !(TM && sizeof(PT) != 1)) || n_susp > 0) {      // (the team path clamps at each departure)
-        for (int q = lane; q < P; q += 32) {
-            bool ch = need_full_refresh;
-            if (cpu[q] < 1e-7 && cpu[q] != 0.0) { cpu[q] = 0.0; ch = true; }
-            if (mem[q] < 1e-7 && mem[q] != 0.0) { mem[q] = 0.0; ch = true; }
-            if (ch) refresh_cap(e, q);
-        }
-        __syncwarp();
-    }
-
-    // ---- 5. arrivals (_accept_vm_requests, env.py:271-293) ----
+    // ---- 5a. the arrival draw (_accept_vm_requests, env.py:272) does not depend on the state: taken first so that a step in which
+    // nothing departs and nothing arrives skips the scans over the slots altogether ----
     int n_arr = 0;
     const vmgym_trace& tr = p.tr;
     const uint32_t arrival_pos = sc->arrival_pos, admission_pos = sc->admission_pos;
@@ -1005,6 +895,162 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
         }
         n_arr = tr.arrival_kmin + min(lo, tr.arrival_cdf_len - 1);
     }
+
+    // ---- 2+3. service countdown and departures in VM-index order (_run_vms, env.py:244-265) ----
+    // Running slots hold their departure step (see the apply loop), so "remaining -= 1; terminate at 0" is "terminate the VMs whose
+    // departure step is this step" — and the earliest departure step of the env is kept in next_dep: the scan over the slots runs
+    // only in steps in which something (possibly) departs.  The scan also renews next_dep.
+    int served = 0;
+    bool need_full_refresh = false;
+    int freed0 = -1, freed1 = -1, freed2 = -1, freed3 = -1;    // first slots freed by this step's departures (slot order)
+    const uint32_t now16 = tnow & 0xffffu;
+    const bool scan = tnow >= *e.next_dep();
+    // team mode also takes its bitmap of empty slots from the scan: needed when arrivals may be admitted into slots that were
+    // already empty before this step
+    const bool team_scan_needed = TM && sizeof(PT) != 1 && (scan || (n_arr > 0 && sc->n_empty > 0));
+    unsigned dmin = 0xffffffffu;                               // distance to the earliest departure after this step
+    if (sizeof(PT) == 1) {
+        if (scan) {
+        // 4 slots per lane: placement bytes as one u32, departure steps as 4 x u16 (padding slots are empty)
+        const uint32_t P4 = (uint32_t)P * 0x01010101u;
+        const uint32_t now2 = now16 * 0x00010001u;
+        const uint32_t* pl4 = reinterpret_cast<const uint32_t*>(place);
+        const uint2* rem4 = reinterpret_cast<const uint2*>(rem);
+        const int groups = (V + 3) >> 2;
+        for (int g0 = 0; g0 < groups; g0 += 32) {
+            const int g = g0 + lane;
+            unsigned term4 = 0;
+            if (g < groups) {
+                const uint32_t run = __vcmpltu4(pl4[g], P4);            // 0xff per running slot
+                if (run) {
+                    const uint2 r = rem4[g];
+                    const uint32_t dlo = __vsub2(r.x, now2), dhi = __vsub2(r.y, now2);    // steps until departure, per u16 lane
+                    const uint32_t zlo = __vcmpeq2(dlo, 0u), zhi = __vcmpeq2(dhi, 0u);
+                    const unsigned runbits = (run & 1u) | ((run >> 7) & 2u) | ((run >> 14) & 4u) | ((run >> 21) & 8u);
+                    term4 = ((zlo & 1u) | ((zlo >> 15) & 2u) | ((zhi & 1u) << 2) | ((zhi >> 13) & 8u)) & runbits;
+                    const unsigned stay = runbits & ~term4;
+                    if (stay & 1u) dmin = min(dmin, dlo & 0xffffu);
+                    if (stay & 2u) dmin = min(dmin, dlo >> 16);
+                    if (stay & 4u) dmin = min(dmin, dhi & 0xffffu);
+                    if (stay & 8u) dmin = min(dmin, dhi >> 16);
+                }
+            }
+            unsigned m = __ballot_sync(FULL, term4 != 0);
+            if (m) {                                                      // some VM finished (:248-265)
+                __syncwarp();
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    unsigned t4 = __shfl_sync(FULL, term4, b);
+                    for (unsigned tt = t4; tt; tt &= tt - 1) {
+                        const int vf = 4 * (g0 + b) + __ffs(tt) - 1;
+                        if (served == 0) freed0 = vf; else if (served == 1) freed1 = vf; else if (served == 2) freed2 = vf;
+                        else if (served == 3) freed3 = vf;
+                        served++;
+                    }
+                    if (lane == 0) {
+                        while (t4) {
+                            const int j = __ffs(t4) - 1;
+                            t4 &= t4 - 1;
+                            const int vv = 4 * (g0 + b) + j, pm = (int)place[vv];
+                            cpu[pm] -= e.sz64[cpuc[vv] & 0x7f];
+                            mem[pm] -= e.sz64[memc[vv]];
+                            if (cpu[pm] < 1e-7) cpu[pm] = 0.0;           // :267-268 clamp, applied here for this PM
+                            if (mem[pm] < 1e-7) mem[pm] = 0.0;
+                            refresh_cap(e, pm);
+                            place[vv] = (PT)(P + 1); cpuc[vv] = 0; memc[vv] = 0; rem[vv] = 0;
+                            if (vmstat) vmstat_close(vs.slots + vv * 4, tnow - vs.slots[vv * 4], 0u, vs.hist, vs.totals);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        }
+    } else if (TM) {
+        if (team_scan_needed) {
+        // team scan -> bitmap of the slots that finished; the main warp retires them in slot order exactly like the
+        // byte-placement path above (per-PM subtraction, 1e-7 clamp and capacity-code refresh)
+        __syncwarp();
+        if (lane == 0) { e.ctl()[1] = (int)tnow; e.ctl()[2] = (int)0xffffffffu; }
+        team_run(e, TEAM_COUNTDOWN, nth);
+        dmin = (unsigned)e.ctl()[2];
+        const unsigned* tmk = e.tmask();
+        const int n_chunks = (V + 31) / 32;
+        for (int cb0 = 0; cb0 < n_chunks; cb0 += 32) {
+            unsigned nz = __ballot_sync(FULL, cb0 + lane < n_chunks && tmk[cb0 + lane] != 0u);
+            while (nz) {
+                const int c = cb0 + __ffs(nz) - 1;
+                nz &= nz - 1;
+                unsigned mm = tmk[c];
+                served += __popc(mm);
+                if (lane == 0) {
+                    while (mm) {
+                        const int vv = 32 * c + __ffs(mm) - 1, pm = (int)place[vv];
+                        mm &= mm - 1;
+                        cpu[pm] -= e.sz64[cpuc[vv] & 0x7f];
+                        mem[pm] -= e.sz64[memc[vv]];
+                        if (cpu[pm] < 1e-7) cpu[pm] = 0.0;           // :267-268 clamp, applied here for this PM
+                        if (mem[pm] < 1e-7) mem[pm] = 0.0;
+                        refresh_cap(e, pm);
+                        place[vv] = (PT)(P + 1); cpuc[vv] = 0; memc[vv] = 0; rem[vv] = 0;
+                        e.emask()[vv >> 5] |= 1u << (vv & 31);         // empty from now on (admissions below)
+                        if (vmstat) vmstat_close(vs.slots + vv * 4, tnow - vs.slots[vv * 4], 0u, vs.hist, vs.totals);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        }
+    } else {
+        if (scan) {
+        for (int c0 = 0; c0 < V; c0 += 32) {
+            const int v = c0 + lane;
+            const int pl = v < V ? (int)place[v] : P + 1;
+            const bool running = pl < P;
+            const uint32_t d = running ? (((uint32_t)rem[v] - now16) & 0xffffu) : 1u;
+            const bool term = running && d == 0u;
+            if (running && !term) dmin = min(dmin, d);
+            unsigned m = __ballot_sync(FULL, term);
+            served += __popc(m);
+            if (m) {
+                if (lane == 0) {
+                    unsigned mm = m;
+                    while (mm) {
+                        const int b = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        const int vv = c0 + b, pm = (int)place[vv];
+                        cpu[pm] -= e.sz64[cpuc[vv] & 0x7f];
+                        mem[pm] -= e.sz64[memc[vv]];
+                        if (vmstat) vmstat_close(vs.slots + vv * 4, tnow - vs.slots[vv * 4], 0u, vs.hist, vs.totals);
+                    }
+                }
+                __syncwarp();
+                if (term) { place[v] = (PT)(P + 1); cpuc[v] = 0; memc[v] = 0; rem[v] = 0; }
+                need_full_refresh = true;
+            }
+        }
+        }
+    }
+    if (scan) {
+        // the earliest departure among the VMs still running (distance d >= 1 from this step), for the steps to come
+        if (!(TM && sizeof(PT) != 1)) dmin = __reduce_min_sync(FULL, dmin);
+        __syncwarp();
+        if (lane == 0) *e.next_dep() = dmin == 0xffffffffu ? 0xffffffffu : tnow + dmin;
+    }
+    __syncwarp();
+    // ---- 4. clamp (env.py:267-268): values only shrink when something was subtracted this step ----
+    if ((served > 0 && !(TM && sizeof(PT) != 1)) || n_susp > 0) {      // (the team path clamps at each departure)
+        for (int q = lane; q < P; q += 32) {
+            bool ch = need_full_refresh;
+            if (cpu[q] < 1e-7 && cpu[q] != 0.0) { cpu[q] = 0.0; ch = true; }
+            if (mem[q] < 1e-7 && mem[q] != 0.0) { mem[q] = 0.0; ch = true; }
+            if (ch) refresh_cap(e, q);
+        }
+        __syncwarp();
+    }
+
+    // ---- 5b. admissions (_accept_vm_requests, env.py:273-293) ----
     int quota = n_arr;                                         // admissions still allowed this step
     if (trace_mode == VMGYM_TRACE_PRESAMPLED) {
         const long long left = tr.admissions_len - (long long)admission_pos;
@@ -1078,9 +1124,11 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
     const int waiting = (int)sc->n_waiting - n_place + n_susp + admitted;
     const int arrived = V - n_empty;
 
-    // ---- 7. reward (env.py:123-156) ----
+    // ---- 7. reward (env.py:123-156): a function of the state alone, so a step that changed nothing repeats the last one ----
     double reward = 0.0;
-    if (arrived > 0) {
+    if (n_place + n_susp + served + admitted == 0 && tnow > 1u) {
+        reward = sc->last_reward;
+    } else if (arrived > 0) {
         if (reward_fn == VMGYM_REWARD_WR) {
             reward = -((double)waiting / (double)arrived);
         } else if (reward_fn == VMGYM_REWARD_UT) {

@@ -40,7 +40,7 @@ class _Group:
 class HostVecEnv:
     def __init__(self, config: Config, num_envs: int, groups: int = 4, device="cuda", rng: str = "philox", seeds=None,
                  agent: str | None = "bestfit", tiebreak: str | None = None, use_graphs: bool = True, zero_copy: bool = True,
-                 delta_obs: bool = True, **vec_kwargs):
+                 delta_obs: bool = True, resident_obs: bool = True, **vec_kwargs):
         if num_envs < 1 or groups < 1:
             raise ValueError("num_envs and groups must be positive")
         groups = min(groups, num_envs)
@@ -77,7 +77,11 @@ class HostVecEnv:
             g.d_obs_in = torch.empty((n, self.obs_dim), dtype=torch.float32, device=self.device)
             g.d_act_in = torch.empty((n, self.V), dtype=self.place_dtype, device=self.device)
         self.use_graphs, self.zero_copy, self.delta_obs = use_graphs, zero_copy, delta_obs and zero_copy
-        self.h2d_bytes_per_step = N * self.obs_dim * 4 + N * self.V * self.action.element_size()
+        # resident_obs: `act()` on the env's OWN observation buffer reads the device copy instead of uploading the host copy — the
+        # pinned buffer is a mirror the env itself keeps current (callers treat it as read-only), so the two are identical by
+        # construction; an observation array passed in by the caller (`act(obs)`) is always uploaded
+        self.resident_obs = bool(resident_obs)
+        self.h2d_bytes_per_step = (0 if self.resident_obs else N * self.obs_dim * 4) + N * self.V * self.action.element_size()
         self.d2h_bytes_per_step = N * self.V * self.action.element_size() + N * self.obs_dim * 4 + N * 8 + N
         torch.cuda.synchronize(self.device)          # construction-time resets ran on the caller's stream
 
@@ -87,11 +91,15 @@ class HostVecEnv:
     # order across streams, so a 0.3 MB action copy queued behind another group's 4.7 MB observation copy would stall
     # its whole chain (measured: the groups' chains then run back to back instead of overlapping).
     def _act_chain(self, g: _Group):
-        g.d_obs_in.copy_(self.obs[g.lo:g.hi], non_blocking=True)          # host obs -> device (copy engine)
-        if self.zero_copy:
-            g.agent.act(g.d_obs_in, out=self.action[g.lo:g.hi])            # vmgym_agent_act stores actions to host memory
+        if self.resident_obs:
+            d_obs = g.vec.obs                                              # the device copy the host buffer mirrors
         else:
-            self.action[g.lo:g.hi].copy_(g.agent.act(g.d_obs_in), non_blocking=True)
+            g.d_obs_in.copy_(self.obs[g.lo:g.hi], non_blocking=True)      # host obs -> device (copy engine)
+            d_obs = g.d_obs_in
+        if self.zero_copy:
+            g.agent.act(d_obs, out=self.action[g.lo:g.hi])                 # vmgym_agent_act stores actions to host memory
+        else:
+            self.action[g.lo:g.hi].copy_(g.agent.act(d_obs), non_blocking=True)
 
     def _step_chain(self, g: _Group):
         if self.zero_copy and self.delta_obs:
@@ -176,8 +184,19 @@ class HostVecEnv:
             g.ev_step.synchronize()
         return self.obs
 
-    def act(self):
-        """agent.act on the host observations -> host actions (all groups)."""
+    def act(self, obs=None):
+        """agent.act -> host actions (all groups).  `obs` None (or the env's own buffer): the current observations; any other
+        [N, 3V+2P] float32 array is uploaded and acted on as given (the env's buffers are not touched)."""
+        if obs is not None and obs is not self.obs:
+            src = torch.as_tensor(np.asarray(obs), dtype=torch.float32).reshape(self.obs.shape)
+            for g in self.groups:
+                with torch.cuda.device(self.device), torch.cuda.stream(g.stream):
+                    g.d_obs_in.copy_(src[g.lo:g.hi], non_blocking=True)
+                    g.agent.act(g.d_obs_in, out=self.action[g.lo:g.hi])
+                    g.ev_act.record(g.stream)
+            for g in self.groups:
+                g.ev_act.synchronize()
+            return self.action
         for gi in range(len(self.groups)):
             self.act_async(gi)
         for gi in range(len(self.groups)):

@@ -163,8 +163,12 @@ class VecVmEnv:
 
     @property
     def vm_remaining_runtime(self):
-        """int32 [N, V] copy of the remaining runtimes (stored as u16 in the record: values above 32767 stay positive)."""
-        return self._vm_remaining_u16.to(torch.int32) & 0xffff
+        """int32 [N, V]: vm_remaining_runtime of env.py:192.  The record keeps steps-left for waiting slots and the departure
+        step modulo 2^16 for running slots (include/vmgym.h, off_remaining); this converts the latter back."""
+        raw = self._vm_remaining_u16.to(torch.int32) & 0xffff
+        running = (self.vm_placement.to(torch.int32) & 0xffff) < self.P
+        t_next = self._scalars_i32[:, :1]
+        return torch.where(running, ((raw - t_next) & 0xffff) + 1, raw)
 
     def vm_arrival_step(self):
         """int64 [N, V]: the step at which the VM occupying each slot arrived, as the reference logs it
@@ -489,7 +493,9 @@ class VecVmEnv:
         s = dict(vm_placement=placement, vm_cpu=vm_cpu, vm_memory=vm_memory,
                  cpu=rec[L.off_cpu:L.off_cpu + 8 * P].view(np.float64).copy(),
                  memory=rec[L.off_memory:L.off_memory + 8 * P].view(np.float64).copy(),
-                 vm_remaining_runtime=rec[L.off_remaining:L.off_remaining + 2 * V].view(np.uint16).astype(np.int64),
+                 vm_remaining_runtime=np.where(placement < P, ((rec[L.off_remaining:L.off_remaining + 2 * V].view(np.uint16).astype(np.int64)
+                                                               - int(i32[0])) & 0xffff) + 1,
+                                               rec[L.off_remaining:L.off_remaining + 2 * V].view(np.uint16).astype(np.int64)),
                  vm_suspended=(cc >> 7).astype(np.int64))
         for i, k in enumerate(nv.SCALARS_I32):
             s[k] = int(i32[i])
