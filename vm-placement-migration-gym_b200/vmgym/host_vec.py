@@ -96,15 +96,23 @@ class HostVecEnv:
         else:
             g.d_obs_in.copy_(self.obs[g.lo:g.hi], non_blocking=True)      # host obs -> device (copy engine)
             d_obs = g.d_obs_in
-        if self.zero_copy:
+        if self.zero_copy and not self.resident_obs:
             g.agent.act(d_obs, out=self.action[g.lo:g.hi])                 # vmgym_agent_act stores actions to host memory
         else:
-            self.action[g.lo:g.hi].copy_(g.agent.act(d_obs), non_blocking=True)
+            # no observation traffic competes for the copy engines: the action rows leave by DMA (one large transfer instead of
+            # 32-byte PCIe writes from the kernel)
+            g.agent.act(d_obs, out=g.d_act_in)
+            self.action[g.lo:g.hi].copy_(g.d_act_in, non_blocking=True)
 
     def _step_chain(self, g: _Group):
         if self.zero_copy and self.delta_obs:
-            # vmgym_step loads the actions from, and stores reward / done and the CHANGED observation entries to, host memory
-            g.vec.step(self.action[g.lo:g.hi], want_valid=False, obs_mirror=self.obs[g.lo:g.hi],
+            # vmgym_step stores reward / done and the CHANGED observation entries to host memory; the actions come from host memory
+            # directly (32-byte PCIe reads from the kernel) or, with resident observations (idle copy engines), by one DMA transfer
+            act_src = self.action[g.lo:g.hi]
+            if self.resident_obs:
+                g.d_act_in.copy_(act_src, non_blocking=True)
+                act_src = g.d_act_in
+            g.vec.step(act_src, want_valid=False, obs_mirror=self.obs[g.lo:g.hi],
                        host_outputs=(self.reward[g.lo:g.hi], self.terminated[g.lo:g.hi]))
         elif self.zero_copy:
             obs, _, _, _, _ = g.vec.step(self.action[g.lo:g.hi], want_valid=False,          # vmgym_step loads actions from,
