@@ -70,76 +70,90 @@ def main():
     kw2 = dict(pms=10, vms=30, arrival_rate=0.4, service_length=30, training_steps=400, eval_steps=1000,
                reward_function="wr", allow_null_action=True, seed=3)
     Ng, T = 16 * world, 8
-    pc = PPOConfig(hidden_size=64, batch_size=T, minibatch_size=4, k_epochs=2, env_chunk=4096, kl_max=None)
     prev_tf32 = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
-    torch.manual_seed(1234)                                              # identical initial weights on every rank
-    full = VecVmEnv(Config(**kw2), Ng, device=dev, rng="philox", seeds=kw2["seed"] + np.arange(Ng))
-    a_full = PPOAgent(full, pc)
-    a_full.data_parallel = False
-    for p in a_full.model.parameters():
-        dist.broadcast(p.data, 0)
-    w0 = a_full._flat.clone()
-    # the same rollout on every rank: deterministic env + Philox-sampled actions from identical weights
-    full.agent_step("firstfit", n_steps=60, want_action=False, want_valid=False)
-    obs = full.observe().clone()
-    buf = dict(obs=[], next_obs=[], action=[], mask=[], logprob=[], reward=[], done=[])
-    with torch.no_grad():
-        for _ in range(T):
-            logits = a_full.model.actor(obs).contiguous()
-            action, logprob, _, mask = a_full._heads(logits, -1.0, want_mask=True)
-            nobs, reward, term, _, _ = full.step(action, want_valid=False)
-            for k, v in (("obs", obs), ("next_obs", nobs), ("action", action), ("mask", mask), ("logprob", logprob),
-                         ("reward", reward.float()), ("done", full.terminated_u8)):
-                buf[k].append(v.clone())
-            obs = nobs.clone()
-    buf = {k: torch.stack(v) for k, v in buf.items()}
-    chk = buf["obs"].double().sum() + buf["action"].double().sum() + buf["logprob"].double().sum()
-    chks = [torch.zeros_like(chk) for _ in range(world)]
-    dist.all_gather(chks, chk)
-    assert all(float(c) == float(chks[0]) for c in chks), "ranks disagree on the rollout"
-
-    lo, hi = shard_range(Ng, rank, world)
-    shard = {k: v[:, lo:hi].contiguous() for k, v in buf.items()}
-    sh_env = VecVmEnv(Config(**kw2), hi - lo, device=dev, rng="philox", seeds=shard_seeds(kw2["seed"], Ng, rank, world))
-    a_sh = PPOAgent(sh_env, pc)
-    a_sh._flat.copy_(w0)
-
-    def one_minibatch(agent, b, w):
-        Tn, Nn = b["reward"].shape
+    for math in ("fp32", "bf16"):
+        # fp32: torch autograd layers; bf16: the hand-written tensor-core forward / backward (same bf16 roundings per sample on
+        # every rank, so shards and the whole batch differ by summation order only — incl. the split-K atomics)
+        pc = PPOConfig(hidden_size=64, batch_size=T, minibatch_size=4, k_epochs=2, env_chunk=4096, kl_max=None, update_math=math)
+        rtol, atol_rel = (1e-4, 1e-5) if math == "fp32" else (2e-3, 2e-4)
+        torch.manual_seed(1234)                                              # identical initial weights on every rank
+        full = VecVmEnv(Config(**kw2), Ng, device=dev, rng="philox", seeds=kw2["seed"] + np.arange(Ng))
+        a_full = PPOAgent(full, pc)
+        a_full.data_parallel = False
+        for p in a_full.model.parameters():
+            dist.broadcast(p.data, 0)
+        a_full.weights_changed()
+        w0 = a_full._flat.clone()
+        # the same rollout on every rank: deterministic env + Philox-sampled actions from identical weights
+        full.agent_step("firstfit", n_steps=60, want_action=False, want_valid=False)
+        obs = full.observe().clone()
+        buf = dict(obs=[], next_obs=[], action=[], mask=[], logprob=[], reward=[], done=[])
         with torch.no_grad():
+            for _ in range(T):
+                logits = a_full.model.actor(obs).contiguous()
+                action, logprob, _, mask = a_full._heads(logits, -1.0, want_mask=True)
+                nobs, reward, term, _, _ = full.step(action, want_valid=False)
+                for k, v in (("obs", obs), ("next_obs", nobs), ("action", action), ("mask", mask), ("logprob", logprob),
+                             ("reward", reward.float()), ("done", full.terminated_u8)):
+                    buf[k].append(v.clone())
+                obs = nobs.clone()
+        buf = {k: torch.stack(v) for k, v in buf.items()}
+        chk = buf["obs"].double().sum() + buf["action"].double().sum() + buf["logprob"].double().sum()
+        chks = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(chks, chk)
+        assert all(float(c) == float(chks[0]) for c in chks), "ranks disagree on the rollout"
+
+        lo, hi = shard_range(Ng, rank, world)
+        shard = {k: v[:, lo:hi].contiguous() for k, v in buf.items()}
+        sh_env = VecVmEnv(Config(**kw2), hi - lo, device=dev, rng="philox", seeds=shard_seeds(kw2["seed"], Ng, rank, world))
+        a_sh = PPOAgent(sh_env, pc)
+        a_sh._flat.copy_(w0)
+        a_sh.weights_changed()
+
+        def one_minibatch(agent, b, w):
             from vmgym.ppo import gae
-            values = agent.model.get_value(b["obs"].reshape(Tn * Nn, -1)).reshape(Tn, Nn)
-            nvals = agent.model.get_value(b["next_obs"].reshape(Tn * Nn, -1)).reshape(Tn, Nn)
-            adv, ret = gae(b["reward"], values, nvals, b["done"], pc.gamma, pc.lamda)
-        t0, t1 = 0, pc.minibatch_size
-        n_mb = (t1 - t0) * Nn
-        adv_mb = agent._normalise_advantages(adv[t0:t1], w)
-        agent._minibatch_backward(b["obs"][t0:t1].reshape(n_mb, -1), b["action"][t0:t1].reshape(n_mb, -1),
-                                  b["mask"][t0:t1].reshape(n_mb, agent.V, agent.mask_words), b["logprob"][t0:t1].reshape(-1), adv_mb,
-                                  values[t0:t1].reshape(-1), ret[t0:t1].reshape(-1), n_mb * w)
-        if w > 1:
-            dist.all_reduce(agent._flat_grad)
-        return agent._flat_grad.clone()
+            Tn, Nn = b["reward"].shape
+            tc = agent._tc_network()
+            with torch.no_grad():
+                if tc is not None:
+                    values = tc.values(b["obs"]).reshape(Tn, Nn)
+                    nvals = tc.values(b["next_obs"]).reshape(Tn, Nn)
+                    o, m = tc.cast_obs(b["obs"]).reshape(Tn, Nn, tc.Dx), agent._mask4(b["mask"])
+                else:
+                    values = agent.model.get_value(b["obs"].reshape(Tn * Nn, -1)).reshape(Tn, Nn)
+                    nvals = agent.model.get_value(b["next_obs"].reshape(Tn * Nn, -1)).reshape(Tn, Nn)
+                    o, m = b["obs"], b["mask"]
+                adv, ret = gae(b["reward"], values, nvals, b["done"], pc.gamma, pc.lamda)
+            t0, t1 = 0, pc.minibatch_size
+            n_mb = (t1 - t0) * Nn
+            adv_mb = agent._normalise_advantages(adv[t0:t1], w)
+            agent._minibatch_backward(o[t0:t1].reshape(n_mb, -1), b["action"][t0:t1].reshape(n_mb, -1),
+                                      m[t0:t1].reshape(n_mb, agent.V, m.shape[-1]), b["logprob"][t0:t1].reshape(-1), adv_mb,
+                                      values[t0:t1].reshape(-1), ret[t0:t1].reshape(-1), n_mb * w)
+            if w > 1:
+                dist.all_reduce(agent._flat_grad)
+            return agent._flat_grad.clone()
 
-    g_sh = one_minibatch(a_sh, shard, world)
-    g_full = one_minibatch(a_full, buf, 1)
-    d = (g_sh - g_full).abs().max().item()
-    scale = g_full.abs().max().item()
-    assert torch.allclose(g_sh, g_full, rtol=1e-4, atol=1e-5 * scale), f"sharded gradient differs: max |d| {d} at scale {scale}"
-    out["grad_max_abs_diff"], out["grad_scale"] = d, scale
+        g_sh = one_minibatch(a_sh, shard, world)
+        g_full = one_minibatch(a_full, buf, 1)
+        d = (g_sh - g_full).abs().max().item()
+        scale = g_full.abs().max().item()
+        assert torch.allclose(g_sh, g_full, rtol=rtol, atol=atol_rel * scale), f"{math}: sharded gradient differs: max |d| {d} at scale {scale}"
+        out[f"{math}_grad_max_abs_diff"], out[f"{math}_grad_scale"] = d, scale
 
-    # full update: sharded (collectives inside update) vs large batch on one GPU
-    a_sh._flat.copy_(w0); a_full._flat.copy_(w0)
-    a_sh.update(**shard)
-    a_full.update(**buf)
-    dp = (a_sh._flat - a_full._flat).abs().max().item()
-    moved = (a_full._flat - w0).abs().max().item()
-    assert moved > 0 and dp <= 2e-2 * moved + 1e-7, f"parameters after the sharded update differ: {dp} (update size {moved})"
-    ws = [torch.zeros_like(a_sh._flat) for _ in range(world)]
-    dist.all_gather(ws, a_sh._flat)
-    assert all(torch.equal(w, ws[0]) for w in ws), "ranks ended the update with different parameters"
-    out["update_param_max_abs_diff"], out["update_size"] = dp, moved
+        # full update: sharded (collectives inside update) vs large batch on one GPU
+        a_sh._flat.copy_(w0); a_full._flat.copy_(w0)
+        a_sh.weights_changed(); a_full.weights_changed()
+        a_sh.update(**shard)
+        a_full.update(**buf)
+        dp = (a_sh._flat - a_full._flat).abs().max().item()
+        moved = (a_full._flat - w0).abs().max().item()
+        assert moved > 0 and dp <= (2e-2 if math == "fp32" else 1e-1) * moved + 1e-7, f"{math}: parameters after the sharded update differ: {dp} (update size {moved})"
+        ws = [torch.zeros_like(a_sh._flat) for _ in range(world)]
+        dist.all_gather(ws, a_sh._flat)
+        assert all(torch.equal(w, ws[0]) for w in ws), "ranks ended the update with different parameters"
+        out[f"{math}_update_param_max_abs_diff"], out[f"{math}_update_size"] = dp, moved
     torch.backends.cuda.matmul.allow_tf32 = prev_tf32
     if rank == 0:
         print("MULTI_GPU_OK " + json.dumps(out), flush=True)
