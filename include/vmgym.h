@@ -256,13 +256,23 @@ int vmgym_ppo_loss(const float* d_new_logprob, const float* d_old_logprob, const
                    const float* d_old_value, const float* d_return, int64_t n, float eps_clip, float ent_coef, float vf_coef,
                    int32_t vf_loss_clip, float inv_n_total, float* d_c_logprob, float* d_c_value, double* d_sums, void* stream);
 
-/* Backward of the fused actor head (vmgym_policy_fused with stored actions): recomputes the logits of each (128 envs x 1 VM)
- * tile in tensor memory and writes d/dlogits of sum_e c_logprob[e] logprob(e) + c_entropy entropy(e) as bf16
- * d_g_bf16[M, ldg] (column 128 v + a; zeros for masked and padding columns) — the operand of the output layer's two backward
- * GEMMs (vmgym_tc_gemm), and the only [samples, V x 128] tensor of the update that reaches HBM. */
+/* The fused actor head evaluating STORED actions under stored masks (PPOAgent.update, ppo.py:257-258): as vmgym_policy_fused
+ * with d_action_in, plus the softmax statistics of every (env, VM) row — d_stat_max / d_stat_sum [M, V]: row maximum and
+ * sum of e^(z - max) over the valid columns — for vmgym_policy_fused_grad.  The epilogue visits only the columns that are
+ * valid in at least one row of a warp (masked columns contribute exactly 0). */
+int vmgym_policy_fused_eval(const void* d_h_bf16, const void* d_wpad_bf16, const float* d_bias_pad, const uint32_t* d_mask_bits,
+                            const void* d_action_in, int64_t M, int64_t V, int64_t A, int64_t K, float* d_logprob, float* d_entropy,
+                            float* d_stat_max, float* d_stat_sum, void* stream);
+
+/* Backward of the fused actor head: recomputes the logits of each (128 envs x 1 VM) tile in tensor memory and, with the
+ * forward's d_entropy / d_stat_max / d_stat_sum [M, V], writes d/dlogits of sum_e c_logprob[e] logprob(e) + c_entropy entropy(e)
+ * in ONE pass over the accumulator as bf16 d_g_bf16[M, ldg] (column 128 v + a; zeros for masked and padding columns) — the
+ * operand of the output layer's two backward GEMMs (vmgym_tc_gemm), and the only [samples, V x 128] tensor of the update that
+ * reaches HBM. */
 int vmgym_policy_fused_grad(const void* d_h_bf16, const void* d_wpad_bf16, const float* d_bias_pad, const uint32_t* d_mask_bits,
                             const void* d_action_in, int64_t M, int64_t V, int64_t A, int64_t K, const float* d_c_logprob,
-                            float c_entropy, void* d_g_bf16, int64_t ldg, void* stream);
+                            float c_entropy, const float* d_entropy, const float* d_stat_max, const float* d_stat_sum, void* d_g_bf16,
+                            int64_t ldg, void* stream);
 
 /* The optimiser step of PPOAgent.update (ppo.py:143,284-287) on flat fp32 buffers of n elements:
  * nn.utils.clip_grad_norm_(max_grad_norm; <= 0 disables) on d_grad * grad_scale, then torch.optim.AdamW's update

@@ -211,3 +211,37 @@ def test_drlvmp_learn_runs_and_updates():
     assert len(tr.losses) > 50 and all(torch.isfinite(l) for l in tr.losses)
     assert any(not torch.equal(a, b) for a, b in zip(agent.dqn.parameters(), before))
     assert vec.counters()["place_actions"].sum() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["act_s10", "act_s100"])
+@pytest.mark.parametrize("mode", ["eager", "graph", "fused"])
+def test_whole_act_loop_matches_reference_agent(case, mode):
+    """DRLVMPAgent.act (drlvmp.py:504-530) end to end against actions recorded from the UNMODIFIED reference agent
+    (tests/golden/make_golden_drlvmp_act.py: random network, observations from a reference run): the same placement vector for every
+    observation, in every execution mode of the device loop.  The reference's decisions have a q-value margin >= 0.3 (recorded), far
+    above the 1e-4 network tolerance, so the comparison is exact."""
+    import json
+    from vmgym import Config, VecVmEnv
+    from vmgym.drlvmp import DRLVMPAgent, DRLVMPConfig
+    z = np.load(os.path.join(os.path.dirname(GOLD), "drlvmp_act.npz"))
+    fx = {k[len(case) + 1:]: z[k] for k in z.files if k.startswith(case + ".")}
+    cfg = json.loads(str(fx["cfg_json"]))
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        vec = VecVmEnv(Config(**cfg), 1, rng="philox")
+        agent = DRLVMPAgent(vec, DRLVMPConfig(hidden_size=int(fx["hidden"])))
+        agent.dqn.load_state_dict({k[3:]: torch.from_numpy(v).cuda() for k, v in fx.items() if k.startswith("sd.")}, strict=True)
+        agent.eval()
+        obs = torch.from_numpy(fx["obs"]).cuda()
+        n = obs.shape[0]
+        reps = 1 if mode == "eager" else (64 + n - 1) // n               # the graph paths want batches of >= 64 rows
+        batch = obs.repeat(reps, 1)
+        kw = dict(eager=dict(graph=False), graph=dict(graph=True, fused=False), fused=dict(graph=True, fused=True))[mode]
+        act = agent.act(batch, **kw).cpu().numpy()
+        want = np.tile(fx["action"], (reps, 1))
+        assert np.array_equal(act, want), f"{(act != want).sum()} of {want.size} placements differ from the reference agent's"
+        assert float(fx["margin"][fx["choices"] >= 0].min()) > 0.1
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev

@@ -194,8 +194,13 @@ def test_fused_head_gradient_mode_matches_autograd(V, A, M):
     c_lp = torch.randn(M, device="cuda")
     c_ent = -0.37
     g = torch.full((M, V * 128 + 8), float("nan"), dtype=torch.bfloat16, device="cuda")
+    lp_f, en_f = torch.empty((M, V), device="cuda"), torch.empty((M, V), device="cuda")
+    st_m, st_s = torch.empty((M, V), device="cuda"), torch.empty((M, V), device="cuda")
+    nv.check(lib.vmgym_policy_fused_eval(h.data_ptr(), head.w_pad.data_ptr(), head.b_pad.data_ptr(), words.data_ptr(), act.data_ptr(), M, V, A, K,
+                                         lp_f.data_ptr(), en_f.data_ptr(), st_m.data_ptr(), st_s.data_ptr(), _stream(torch)), "fused_eval")
     nv.check(lib.vmgym_policy_fused_grad(h.data_ptr(), head.w_pad.data_ptr(), head.b_pad.data_ptr(), words.data_ptr(), act.data_ptr(), M, V, A, K,
-                                         c_lp.data_ptr(), c_ent, g.data_ptr(), g.stride(0), _stream(torch)), "fused_grad")
+                                         c_lp.data_ptr(), c_ent, en_f.data_ptr(), st_m.data_ptr(), st_s.data_ptr(), g.data_ptr(), g.stride(0),
+                                         _stream(torch)), "fused_grad")
     torch.cuda.synchronize()
     logits = (h.double() @ lin.weight.detach().to(torch.bfloat16).double().t() + lin.bias.detach().double()).requires_grad_(True)
     z = logits.reshape(M, V, A).masked_fill(mask, -1e7)
@@ -203,6 +208,10 @@ def test_fused_head_gradient_mode_matches_autograd(V, A, M):
     lp = logp.gather(-1, act.long().unsqueeze(-1)).squeeze(-1).sum(1)
     ent = -(logp.exp() * logp).sum(-1).sum(1)
     (lp * c_lp.double()).sum().add(c_ent * ent.sum()).backward()
+    # the evaluating forward (valid-column epilogue): per-(env, VM) log-prob and entropy
+    rlp = logp.gather(-1, act.long().unsqueeze(-1)).squeeze(-1).detach()
+    rent = -(logp.exp() * logp).sum(-1).detach()
+    assert torch.allclose(lp_f.double(), rlp, rtol=1e-4, atol=2e-4) and torch.allclose(en_f.double(), rent, rtol=1e-4, atol=2e-4)
     ref = logits.grad.reshape(M, V, A)
     got = g[:, :V * 128].reshape(M, V, 128).double()
     assert bool((got[:, :, A:] == 0).all()), "padding columns must be zero"

@@ -22,10 +22,26 @@ bias = torch.zeros(V * T, device="cuda")
 dW = torch.zeros(V * T, H, device="cuda")
 db = torch.zeros(V * T, device="cuda")
 dz = torch.empty(M, H, device="cuda", dtype=bf)
-mask = torch.zeros(M, V, 4, dtype=torch.int32, device="cuda")
-act = torch.randint(0, A, (M, V), device="cuda").to(torch.uint8)
 lp, en = torch.empty(M, V, device="cuda"), torch.empty(M, V, device="cuda")
+sm_, ss_ = torch.empty(M, V, device="cuda"), torch.empty(M, V, device="cuda")
+# masks as in a saturated config/100.yml env: ~53 % of the slots run (valid: own PM + WAIT), the rest wait with nothing fitting (WAIT only)
+import numpy as np  # noqa: E402
+rng = np.random.default_rng(0)
+valid = np.zeros((M, V, 128), bool)
+valid[:, :, 100] = True
+run = rng.random((M, V)) < 0.53
+pm = rng.integers(0, 100, (M, V))
+ii, jj = np.nonzero(run)
+valid[ii, jj, pm[ii, jj]] = True
+if len(sys.argv) > 2 and sys.argv[2] == "dense":       # far from saturation: a waiting VM fits on most PMs
+    valid[:, :, :100] |= (rng.random((M, V, 100)) < 0.6) & ~run[:, :, None]
+inv = ~valid
+inv[:, :, A:] = False
+words = (inv.reshape(M, V, 4, 32).astype(np.uint64) << np.arange(32, dtype=np.uint64)).sum(-1).astype(np.uint32).view(np.int32)
+mask = torch.from_numpy(words).cuda()
+act = torch.full((M, V), 100, dtype=torch.uint8, device="cuda")
 c_lp = torch.randn(M, device="cuda")
+act2 = torch.empty((M, V), dtype=torch.uint8, device="cuda")
 
 
 def gemm(a, a_mn, b, b_mn, Mx, Nx, Kx, c32=None, acc=0, c16=None, mul=None, rows=None):
@@ -39,10 +55,13 @@ def gemm(a, a_mn, b, b_mn, Mx, Nx, Kx, c32=None, acc=0, c16=None, mul=None, rows
 cases = {
     "dW3 = g^T a2 (+ row sums)": (lambda: gemm(g, 1, a2, 1, V * T, H, M, c32=dW, acc=1, rows=db), 2.0 * V * T * H * M),
     "dz2 = (g W3)(1 - a2^2)": (lambda: gemm(g, 0, w, 1, M, H, V * T, c16=dz, mul=a2), 2.0 * V * T * H * M),
-    "fused head forward": (lambda: nv.check(lib.vmgym_policy_fused(a2.data_ptr(), w.data_ptr(), bias.data_ptr(), mask.data_ptr(), act.data_ptr(), M, V, A, H,
-                                                                   0, 0, None, lp.data_ptr(), en.data_ptr(), st), "f"), 2.0 * V * T * H * M),
+    "fused head eval forward": (lambda: nv.check(lib.vmgym_policy_fused_eval(a2.data_ptr(), w.data_ptr(), bias.data_ptr(), mask.data_ptr(), act.data_ptr(), M, V, A, H,
+                                                                             lp.data_ptr(), en.data_ptr(), sm_.data_ptr(), ss_.data_ptr(), st), "f"), 2.0 * V * T * H * M),
     "fused head gradient": (lambda: nv.check(lib.vmgym_policy_fused_grad(a2.data_ptr(), w.data_ptr(), bias.data_ptr(), mask.data_ptr(), act.data_ptr(), M, V, A, H,
-                                                                        c_lp.data_ptr(), -1e-7, g.data_ptr(), g.stride(0), st), "fg"), 2.0 * V * T * H * M),
+                                                                        c_lp.data_ptr(), -1e-7, en.data_ptr(), sm_.data_ptr(), ss_.data_ptr(), g.data_ptr(), g.stride(0), st), "fg"),
+                            2.0 * V * T * H * M),
+    "fused head sampling (rollout)": (lambda: nv.check(lib.vmgym_policy_fused(a2.data_ptr(), w.data_ptr(), bias.data_ptr(), mask.data_ptr(), None, M, V, A, H,
+                                                                              1, 1, act2.data_ptr(), lp.data_ptr(), en.data_ptr(), st), "fs"), 2.0 * V * T * H * M),
 }
 for name, (fn, flops) in cases.items():
     fn(); fn()

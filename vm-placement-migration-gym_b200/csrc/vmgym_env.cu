@@ -282,6 +282,18 @@ int vmgym_set_tuning(int warps_per_cta, int use_bulk_copy)
     return VMGYM_OK;
 }
 
+#ifdef VMGYM_PROF
+/* development builds only: cycles per section of the step kernel's decision warp (see PROF_ADD), reset after reading */
+int vmgym_debug_prof(unsigned long long* out16)
+{
+    unsigned long long zero[16] = {0};
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, vmgym::g_prof, sizeof(zero));
+    cudaMemcpyToSymbol(vmgym::g_prof, zero, sizeof(zero));
+    return VMGYM_OK;
+}
+#endif
+
 int vmgym_get_layout(const vmgym_config* cfg, vmgym_layout* out)
 {
     if (!out) return fail(VMGYM_EINVAL, "null layout");

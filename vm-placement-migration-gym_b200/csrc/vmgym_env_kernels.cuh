@@ -14,6 +14,22 @@
 
 namespace vmgym {
 
+// Section timing of the step kernel's decision warp (development builds only: -DVMGYM_PROF): cycles per section summed over all envs
+// into g_prof[], read back with vmgym_debug_prof().  Compiles to nothing otherwise.
+#ifdef VMGYM_PROF
+__device__ unsigned long long g_prof[16];
+#define PROF_T0() long long _pt = clock64()
+#define PROF_ADD(i)                                                                                          \
+    do {                                                                                                      \
+        const long long _n = clock64();                                                                       \
+        if ((threadIdx.x & 31) == 0 && threadIdx.x < 32) atomicAdd(&g_prof[i], (unsigned long long)(_n - _pt)); \
+        _pt = _n;                                                                                             \
+    } while (0)
+#else
+#define PROF_T0() do { } while (0)
+#define PROF_ADD(i) do { } while (0)
+#endif
+
 struct StepParams {
     DevLayout L;
     int reward_fn, cap_target, step_limit;
@@ -432,6 +448,7 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
     }
     const bool team_fit = TM && (e.tune & 8) == 0;       // the team builds the fit table (use_bulk bit 3: main warp alone, for A/B runs)
     unsigned kmax = team_fit ? rebuild_fit_table_team(e, nth) : rebuild_fit_table(e);
+    bool dirty = false;                                  // proposals since the table was built (it over-states the free capacity)
 
     // slots are visited in groups: 4 per lane (128 per pass) for byte placements, 1 per lane otherwise
     constexpr int SPL = sizeof(PT) == 1 ? 4 : 1;
@@ -532,10 +549,15 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
                 }
                 if (found >= 0) {
                     n_found++;
-                    placed_any = true;
                     if (lane == 0) { e.act()[vv] = (uint16_t)found; e.prop()[vv >> 5] |= 1u << (vv & 31); }
                     __syncwarp();
-                    kmax = team_fit ? rebuild_fit_table_team(e, nth) : rebuild_fit_table(e);   // capacities shrank: the remaining candidates are re-tested
+                    // capacities shrank, so the fit table now over-states what fits: it stays a valid pre-filter (a superset of the
+                    // candidates — the PM scan itself is exact) and is only rebuilt once a scan comes back empty-handed
+                    dirty = true;
+                } else if (dirty) {
+                    kmax = team_fit ? rebuild_fit_table_team(e, nth) : rebuild_fit_table(e);
+                    dirty = false;
+                    placed_any = true;                 // the not-yet-visited lanes' candidates are re-tested against the fresh table
                     if (bits) {
                         unsigned nb;
                         if (SPL == 4) {
@@ -782,6 +804,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
     uint16_t* rem = e.rem();
     int n_place = 0, n_susp = 0, rejected = 0;
 
+    PROF_T0();
     // ---- 1. apply actions in VM-index order, each seeing earlier updates (env.py:69-87, validate :35-42) ----
     if (have_actions) {
         const uint16_t* act = e.act();
@@ -857,6 +880,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
         for (int v = lane; v < V; v += 32) valid_g[v] = 1;
     }
 
+    PROF_ADD(6);                                               // 6: apply
     // ---- 5a. the arrival draw (_accept_vm_requests, env.py:272) does not depend on the state: taken first so that a step in which
     // nothing departs and nothing arrives skips the scans over the slots altogether ----
     int n_arr = 0;
@@ -896,6 +920,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
         n_arr = tr.arrival_kmin + min(lo, tr.arrival_cdf_len - 1);
     }
 
+    PROF_ADD(7);                                               // 7: arrival draw
     // ---- 2+3. service countdown and departures in VM-index order (_run_vms, env.py:244-265) ----
     // Running slots hold their departure step (see the apply loop), so "remaining -= 1; terminate at 0" is "terminate the VMs whose
     // departure step is this step" — and the earliest departure step of the env is kept in next_dep: the scan over the slots runs
@@ -1039,6 +1064,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
         if (lane == 0) *e.next_dep() = dmin == 0xffffffffu ? 0xffffffffu : tnow + dmin;
     }
     __syncwarp();
+    PROF_ADD(8);                                               // 8: departures
     // ---- 4. clamp (env.py:267-268): values only shrink when something was subtracted this step ----
     if ((served > 0 && !(TM && sizeof(PT) != 1)) || n_susp > 0) {      // (the team path clamps at each departure)
         for (int q = lane; q < P; q += 32) {
@@ -1119,6 +1145,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
         __syncwarp();
     }
 
+    PROF_ADD(9);                                               // 9: clamp + admissions
     // ---- 6. metrics (env.py:112-121) from the incrementally maintained slot counters ----
     const int n_empty = n_empty0 - admitted;
     const int waiting = (int)sc->n_waiting - n_place + n_susp + admitted;
@@ -1159,6 +1186,7 @@ __device__ __forceinline__ StepResult env_step(const Env<PT>& e, const StepParam
         sc->timestep += 1;
     }
     __syncwarp();
+    PROF_ADD(10);                                              // 10: reward + counters
     StepResult res;
     res.reward = reward; res.terminated = terminated; res.rejected = rejected; res.waiting = waiting; res.arrived = arrived;
     res.changed = n_place + n_susp + served + admitted;      // anything that can change which waiting VMs fit
@@ -1387,6 +1415,9 @@ __global__ void __launch_bounds__(TM ? 256 : 896, TM ? 3 : 1) step_kernel(const 
         const long long env = ROT ? (long long)rb * p.rot_envs + idx : idx;
         const bool first_item = idx == env0 && rk == 0;
         unsigned char* grec = p.state + env * (long long)L.rec_bytes;
+#ifdef VMGYM_PROF
+        const long long _pload = clock64();
+#endif
         // ---- stage the record into shared memory ----
         if (DB) {
             unsigned char* other = cur ? base : base + L.sm_stride;
@@ -1413,6 +1444,10 @@ __global__ void __launch_bounds__(TM ? 256 : 896, TM ? 3 : 1) step_kernel(const 
             copy16(base, grec, L.rec_bytes, lane);
         }
 
+#ifdef VMGYM_PROF
+        if (threadIdx.x == 0) atomicAdd(&g_prof[0], (unsigned long long)(clock64() - _pload));      // 0: record load wait
+#endif
+        PROF_T0();
         uint8_t* valid_g = p.out.d_valid ? p.out.d_valid + env * (long long)cV : nullptr;
         StepResult res;
         res.reward = 0.0; res.terminated = 0; res.rejected = 0; res.waiting = 0; res.arrived = 0; res.changed = 0;
@@ -1445,7 +1480,9 @@ __global__ void __launch_bounds__(TM ? 256 : 896, TM ? 3 : 1) step_kernel(const 
                     }
                     AgentView<PT> av;
                     av.place = e.place(); av.cc = e.cpuc(); av.mc = e.memc(); av.c32 = nullptr; av.m32 = nullptr; av.sz32 = sz32;
+                    PROF_ADD(1);                                                                         // 1: setup
                     n_found = agent_act<PT, TM>(e, av, agent_k, tiebreak_k, true, nth);
+                    PROF_ADD(2);                                                                         // 2: agent act
                     evaluated = true;
                     if (p.out.d_action) {        // the action vector: proposals, else the current placement (firstfit.py:29)
                         PT* ao = reinterpret_cast<PT*>(p.out.d_action) + env * (long long)cV;
@@ -1472,6 +1509,7 @@ __global__ void __launch_bounds__(TM ? 256 : 896, TM ? 3 : 1) step_kernel(const 
                 have_actions = any != 0;
             }
             res = env_step<PT, REWARD_CT, MODE_CT, (SPEC < 0), TM>(e, p, env, valid_g, have_actions, nth);
+            PROF_ADD(3);                                                                                 // 3: env step
             if (res.changed) {
                 quiet = false;
                 obs_stale = true;
@@ -1518,6 +1556,7 @@ __global__ void __launch_bounds__(TM ? 256 : 896, TM ? 3 : 1) step_kernel(const 
             }
         }
 
+        PROF_ADD(4);                                                                                     // 4: outputs (obs row)
         if (TM) team_run(e, TEAM_END, nth);       // helpers move on to the next record of this CTA
         // ---- write the record back ----
         if (DB) {
@@ -1542,6 +1581,7 @@ __global__ void __launch_bounds__(TM ? 256 : 896, TM ? 3 : 1) step_kernel(const 
             copy16(grec, base, L.rec_bytes, lane);
             if (BULK) fence_proxy_async();        // generic-proxy reads of smem before the next record's async-proxy write
         }
+        PROF_ADD(5);                                                                                     // 5: write-back
     }
     if (DB && lane == 0) bulk_wait_read0();       // shared memory must outlive the last write-backs
 }

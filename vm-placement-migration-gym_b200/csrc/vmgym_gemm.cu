@@ -197,6 +197,10 @@ struct FusedOut {
     float c_entropy;
     __nv_bfloat16* g_out;        // [M, ldg] or nullptr
     long long ldg;
+    // softmax statistics per (env, VM) row, [M, V] each: row maximum and sum of e^(z - max).  Written by an evaluating forward
+    // call (action_in given) when non-null; READ by the gradient mode, which then needs a single pass over the accumulator.
+    float* stat_m;
+    float* stat_s;
 };
 
 // Per-row running state of the fused epilogue.
@@ -303,6 +307,7 @@ struct RowIn {
     uint4 inv;
     int act_given;
     vmgym::Philox4 rnd;
+    float m, s;                  // gradient mode: the row's softmax statistics from the forward call
 };
 __device__ __forceinline__ RowIn fused_epilogue_prefetch(const FusedOut& fo, int q, int lane, int m0, int v, int M)
 {
@@ -315,6 +320,8 @@ __device__ __forceinline__ RowIn fused_epilogue_prefetch(const FusedOut& fo, int
     // sampling: one Philox call per row, word c = the uniform of chunk c (vmgym_sample.cuh)
     in.rnd = vmgym::Philox4{0u, 0u, 0u, 0u};
     if (!fo.action_in) in.rnd = vmgym::sample_block(v, 0, (uint32_t)e, fo.seed, fo.counter);
+    in.m = 0.f; in.s = 1.f;
+    if (fo.g_out && e < M) { in.m = fo.stat_m[(long long)e * fo.V + v]; in.s = fo.stat_s[(long long)e * fo.V + v]; }
     return in;
 }
 __device__ __forceinline__ void fused_epilogue_row(const FusedOut& fo, const float* s_bias, uint32_t tmem_acc, const RowIn& in, int q,
@@ -347,48 +354,129 @@ __device__ __forceinline__ void fused_epilogue_row(const FusedOut& fo, const flo
         if (fo.action_out) fo.action_out[o] = (uint8_t)act;
         if (fo.logprob) fo.logprob[o] = ((unsigned)act < (unsigned)A) ? za - lse : 0.f;
         if (fo.entropy) fo.entropy[o] = H;
+        if (fo.stat_m) { fo.stat_m[o] = st.m; fo.stat_s[o] = st.ssum; }       // for the gradient mode's single pass
     }
-    if (fo.g_out) {
-        // second pass over the accumulator: the logit gradients of this row, all 128 columns of the tile (zeros above A)
-        const float clp = e < M ? fo.c_logprob[e] : 0.f, cen = fo.c_entropy;
-        const float inv_s = 1.0f / st.ssum;
-        __nv_bfloat16* grow = fo.g_out + (long long)e * fo.ldg + (long long)v * BN;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Evaluate-mode epilogue (PPOAgent.update: stored actions under stored masks; ppo.py:257-258 and its backward).
+// At saturation almost every column of a row is masked (a running VM may only stay or be suspended: 2 valid columns of 102), and a
+// masked column contributes exactly 0 to the softmax sums and gets exactly 0 gradient.  The math therefore visits only the columns
+// that are valid in AT LEAST ONE of the warp's 32 rows (warp-uniform loop over the OR of the rows' valid bits; the accumulator
+// value of column j is picked from the tcgen05.ld registers by a 32-way switch, so no register array is indexed dynamically).
+// A row without any valid column gets no gradient at all (its logits were overwritten by the constant -1e7).  One pass over the
+// accumulator, using the row statistics (max, sum) the evaluating forward call stored.  Chunks in which many columns are in
+// play (an env far from saturation) take straight-line code instead of the loop.
+// (Measured: the forward is bound by its MMA / TMA pipeline, not by its epilogue — a valid-column forward was slower — so the
+// forward keeps the straight-line epilogue of the rollout kernel and only stores the statistics.)
+// ---------------------------------------------------------------------------------------------------
+#define VMGYM_PICK32(r, j, x)                                                                                                            \
+    switch (j) {                                                                                                                         \
+    case 0: x = r[0]; break; case 1: x = r[1]; break; case 2: x = r[2]; break; case 3: x = r[3]; break;                                  \
+    case 4: x = r[4]; break; case 5: x = r[5]; break; case 6: x = r[6]; break; case 7: x = r[7]; break;                                  \
+    case 8: x = r[8]; break; case 9: x = r[9]; break; case 10: x = r[10]; break; case 11: x = r[11]; break;                              \
+    case 12: x = r[12]; break; case 13: x = r[13]; break; case 14: x = r[14]; break; case 15: x = r[15]; break;                          \
+    case 16: x = r[16]; break; case 17: x = r[17]; break; case 18: x = r[18]; break; case 19: x = r[19]; break;                          \
+    case 20: x = r[20]; break; case 21: x = r[21]; break; case 22: x = r[22]; break; case 23: x = r[23]; break;                          \
+    case 24: x = r[24]; break; case 25: x = r[25]; break; case 26: x = r[26]; break; case 27: x = r[27]; break;                          \
+    case 28: x = r[28]; break; case 29: x = r[29]; break; case 30: x = r[30]; break; default: x = r[31]; break;                          \
+    }
+#define VMGYM_PUT16(gb, k, w)                                                                                                            \
+    switch (k) {                                                                                                                         \
+    case 0: gb[0] = w; break; case 1: gb[1] = w; break; case 2: gb[2] = w; break; case 3: gb[3] = w; break;                              \
+    case 4: gb[4] = w; break; case 5: gb[5] = w; break; case 6: gb[6] = w; break; case 7: gb[7] = w; break;                              \
+    case 8: gb[8] = w; break; case 9: gb[9] = w; break; case 10: gb[10] = w; break; case 11: gb[11] = w; break;                          \
+    case 12: gb[12] = w; break; case 13: gb[13] = w; break; case 14: gb[14] = w; break; default: gb[15] = w; break;                      \
+    }
+
+constexpr int EVAL_DENSE = 9;       // columns in play per 32-column chunk above which the straight-line path is cheaper than the loop
+
+__device__ __forceinline__ uint32_t eval_valid_bits(const FusedOut& fo, const uint4& inv, int c0, int A, bool row_live)
+{
+    const uint32_t iw = c0 == 0 ? inv.x : (c0 == 32 ? inv.y : (c0 == 64 ? inv.z : inv.w));
+    const uint32_t real = A - c0 >= 32 ? 0xffffffffu : ((1u << (A - c0)) - 1u);
+    return row_live ? (~iw & real) : 0u;
+}
+
+__device__ __forceinline__ void eval_epilogue_row(const FusedOut& fo, const float* s_bias, uint32_t tmem_acc, const RowIn& in, int q,
+                                                  int lane, int m0, int v, int M)
+{
+    const int e = m0 + q * 32 + lane;
+    const int A = fo.A;
+    const bool live = e < M;
+    const uint4 inv = in.inv;
+    const int act = in.act_given;
+    const uint32_t trow = tmem_acc + ((uint32_t)(q * 32) << 16);
+    const bool any_valid = (eval_valid_bits(fo, inv, 0, A, live) | (A > 32 ? eval_valid_bits(fo, inv, 32, A, live) : 0u) |
+                            (A > 64 ? eval_valid_bits(fo, inv, 64, A, live) : 0u) | (A > 96 ? eval_valid_bits(fo, inv, 96, A, live) : 0u)) != 0u;
+    // ---- gradient: one pass; g_a = c_lp ([a == act] - p_a) - c_ent p_a (log p_a + H) on the valid columns, 0 elsewhere ----
+    const float m = in.m, ssum = in.s;
+    const float ls = __logf(ssum), lse = m + ls, inv_s = 1.0f / ssum;
+    const float clp = live ? fo.c_logprob[e] : 0.f, cen = fo.c_entropy;
+    // H = (lse - m) - tsum / ssum needs tsum: recomputed here from the same pass would need two passes, so the forward's
+    // entropy output is used instead (it is the same number)
+    const float H = (live && fo.entropy) ? fo.entropy[(long long)e * fo.V + v] : 0.f;
+    __nv_bfloat16* grow = fo.g_out + (long long)e * fo.ldg + (long long)v * BN;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t gb[16];
-            if (c0 < A) {
-                uint32_t r[32];
-                tmem_ld_row32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-                const uint32_t iw = c0 == 0 ? inv.x : (c0 == 32 ? inv.y : (c0 == 64 ? inv.z : inv.w));
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t gb[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) gb[k] = 0u;
+        if (c0 < A) {
+            uint32_t r[32];
+            tmem_ld_row32(trow + (uint32_t)c0, r);
+            const uint32_t vb = any_valid ? eval_valid_bits(fo, inv, c0, A, live) : 0u;
+            uint32_t u = __reduce_or_sync(0xffffffffu, vb);
+            if (__popc(u) > EVAL_DENSE) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
                     float gv[2];
 #pragma unroll
                     for (int t = 0; t < 2; t++) {
-                        const int a = c0 + j + t;
-                        float x = __uint_as_float(r[j + t]) + s_bias[min(a, BN - 1)];
-                        // masked columns were overwritten by the constant -1e7 (ppo.py:119): no gradient reaches their logits
-                        const bool dead = ((iw >> (j + t)) & 1u) || a >= A;
-                        const float d = x - st.m;
-                        const float pa = dead ? 0.f : vmgym::fast_exp(d) * inv_s;
-                        const float lp = x - lse;
-                        const float gg = dead ? 0.f : clp * ((a == act_given ? 1.f : 0.f) - pa) + (pa > 0.f ? cen * (-pa * (lp + H)) : 0.f);
+                        const float x = __uint_as_float(r[j + t]) + s_bias[c0 + j + t];
+                        float gg = 0.f;
+                        if ((vb >> (j + t)) & 1u) {
+                            const float pa = vmgym::fast_exp(x - m) * inv_s;
+                            gg = clp * ((c0 + j + t == act ? 1.f : 0.f) - pa) + (pa > 0.f ? cen * (-pa * ((x - lse) + H)) : 0.f);
+                        }
                         gv[t] = gg;
                     }
                     const __nv_bfloat162 h2 = __floats2bfloat162_rn(gv[0], gv[1]);
                     gb[j >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; j++) gb[j] = 0u;
+                u = 0u;
             }
-            if (e < M) {
-                uint4* dst = reinterpret_cast<uint4*>(grow + c0);
-                dst[0] = make_uint4(gb[0], gb[1], gb[2], gb[3]);
-                dst[1] = make_uint4(gb[4], gb[5], gb[6], gb[7]);
-                dst[2] = make_uint4(gb[8], gb[9], gb[10], gb[11]);
-                dst[3] = make_uint4(gb[12], gb[13], gb[14], gb[15]);
+            while (u) {
+                const int j = __ffs(u) - 1;
+                u &= u - 1;
+                uint32_t xr;
+                VMGYM_PICK32(r, j, xr);
+                const float x = __uint_as_float(xr) + s_bias[c0 + j];
+                float gg = 0.f;
+                if ((vb >> j) & 1u) {
+                    const float pa = vmgym::fast_exp(x - m) * inv_s;
+                    gg = clp * ((c0 + j == act ? 1.f : 0.f) - pa) + (pa > 0.f ? cen * (-pa * ((x - lse) + H)) : 0.f);
+                }
+                // the column's bf16 goes into its half of word j / 2 (the other half may already hold its neighbour)
+                const uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(gg));
+                const int k = j >> 1;
+                uint32_t wcur;
+                switch (k) {
+                case 0: wcur = gb[0]; break; case 1: wcur = gb[1]; break; case 2: wcur = gb[2]; break; case 3: wcur = gb[3]; break;
+                case 4: wcur = gb[4]; break; case 5: wcur = gb[5]; break; case 6: wcur = gb[6]; break; case 7: wcur = gb[7]; break;
+                case 8: wcur = gb[8]; break; case 9: wcur = gb[9]; break; case 10: wcur = gb[10]; break; case 11: wcur = gb[11]; break;
+                case 12: wcur = gb[12]; break; case 13: wcur = gb[13]; break; case 14: wcur = gb[14]; break; default: wcur = gb[15]; break;
+                }
+                const uint32_t wnew = (j & 1) ? ((wcur & 0x0000ffffu) | (hb << 16)) : ((wcur & 0xffff0000u) | hb);
+                VMGYM_PUT16(gb, k, wnew);
             }
+        }
+        if (live) {
+            uint4* dst = reinterpret_cast<uint4*>(grow + c0);
+            dst[0] = make_uint4(gb[0], gb[1], gb[2], gb[3]);
+            dst[1] = make_uint4(gb[4], gb[5], gb[6], gb[7]);
+            dst[2] = make_uint4(gb[8], gb[9], gb[10], gb[11]);
+            dst[3] = make_uint4(gb[12], gb[13], gb[14], gb[15]);
         }
     }
 }
@@ -415,7 +503,8 @@ __global__ void __launch_bounds__(THREADS, 1) policy_fused_kernel(const __grid_c
         const RowIn in = fused_epilogue_prefetch(fo, warp & 3, lane, m0, v, M);
         mbar_wait(pipe.tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        fused_epilogue_row(fo, s_bias, tmem_base, in, warp & 3, lane, m0, v, M);
+        if (fo.g_out) eval_epilogue_row(fo, s_bias, tmem_base, in, warp & 3, lane, m0, v, M);
+        else fused_epilogue_row(fo, s_bias, tmem_base, in, warp & 3, lane, m0, v, M);
     }
     pipe_teardown(tmem_base, warp);
 }
@@ -550,7 +639,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) policy_fused_persistent_kernel(c
                 const RowIn in = fused_epilogue_prefetch(fo, q, lane, mt * BM, v, M);
                 mbar_wait(&acc_full[g], (tcount / P_GROUPS) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                fused_epilogue_row(fo, bias_g, tmem_base + g * TMEM_COLS, in, q, lane, mt * BM, v, M);
+                if (fo.g_out) eval_epilogue_row(fo, bias_g, tmem_base + g * TMEM_COLS, in, q, lane, mt * BM, v, M);
+                else fused_epilogue_row(fo, bias_g, tmem_base + g * TMEM_COLS, in, q, lane, mt * BM, v, M);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[g])) : "memory");
             }
@@ -665,23 +755,41 @@ extern "C" int vmgym_policy_fused(const void* d_h_bf16, const void* d_wpad_bf16,
     FusedOut fo;
     fo.mask_bits = d_mask_bits; fo.bias_pad = d_bias_pad; fo.action_in = d_action_in; fo.action_out = d_action_out;
     fo.logprob = d_logprob; fo.entropy = d_entropy; fo.A = (int)A; fo.V = (int)V; fo.seed = seed; fo.counter = (uint32_t)counter;
-    fo.c_logprob = nullptr; fo.c_entropy = 0.f; fo.g_out = nullptr; fo.ldg = 0;
+    fo.c_logprob = nullptr; fo.c_entropy = 0.f; fo.g_out = nullptr; fo.ldg = 0; fo.stat_m = nullptr; fo.stat_s = nullptr;
     return launch_policy_fused("vmgym_policy_fused", d_h_bf16, d_wpad_bf16, fo, M, V, A, K, stream);
+}
+
+extern "C" int vmgym_policy_fused_eval(const void* d_h_bf16, const void* d_wpad_bf16, const float* d_bias_pad, const uint32_t* d_mask_bits,
+                                       const void* d_action_in, int64_t M, int64_t V, int64_t A, int64_t K, float* d_logprob, float* d_entropy,
+                                       float* d_stat_max, float* d_stat_sum, void* stream)
+{
+    using namespace vmgym_gemm;
+    if (!d_h_bf16 || !d_wpad_bf16 || !d_bias_pad || !d_action_in || !d_logprob || !d_entropy || !d_stat_max || !d_stat_sum || M < 0) {
+        vmgym_internal_set_error("vmgym_policy_fused_eval: null operand");
+        return VMGYM_EINVAL;
+    }
+    FusedOut fo;
+    fo.mask_bits = d_mask_bits; fo.bias_pad = d_bias_pad; fo.action_in = d_action_in; fo.action_out = nullptr;
+    fo.logprob = d_logprob; fo.entropy = d_entropy; fo.A = (int)A; fo.V = (int)V; fo.seed = 0; fo.counter = 0;
+    fo.c_logprob = nullptr; fo.c_entropy = 0.f; fo.g_out = nullptr; fo.ldg = 0; fo.stat_m = d_stat_max; fo.stat_s = d_stat_sum;
+    return launch_policy_fused("vmgym_policy_fused_eval", d_h_bf16, d_wpad_bf16, fo, M, V, A, K, stream);
 }
 
 extern "C" int vmgym_policy_fused_grad(const void* d_h_bf16, const void* d_wpad_bf16, const float* d_bias_pad, const uint32_t* d_mask_bits,
                                        const void* d_action_in, int64_t M, int64_t V, int64_t A, int64_t K, const float* d_c_logprob,
-                                       float c_entropy, void* d_g_bf16, int64_t ldg, void* stream)
+                                       float c_entropy, const float* d_entropy, const float* d_stat_max, const float* d_stat_sum,
+                                       void* d_g_bf16, int64_t ldg, void* stream)
 {
     using namespace vmgym_gemm;
-    if (!d_h_bf16 || !d_wpad_bf16 || !d_bias_pad || !d_action_in || !d_c_logprob || !d_g_bf16 || M < 0 || ldg < V * BN || (ldg & 7) ||
-        ((uintptr_t)d_g_bf16 & 15)) {
+    if (!d_h_bf16 || !d_wpad_bf16 || !d_bias_pad || !d_action_in || !d_c_logprob || !d_entropy || !d_stat_max || !d_stat_sum || !d_g_bf16 ||
+        M < 0 || ldg < V * BN || (ldg & 7) || ((uintptr_t)d_g_bf16 & 15)) {
         vmgym_internal_set_error("vmgym_policy_fused_grad: null operand, or ldg < 128 V / not a multiple of 8, or unaligned output");
         return VMGYM_EINVAL;
     }
     FusedOut fo;
     fo.mask_bits = d_mask_bits; fo.bias_pad = d_bias_pad; fo.action_in = d_action_in; fo.action_out = nullptr;
-    fo.logprob = nullptr; fo.entropy = nullptr; fo.A = (int)A; fo.V = (int)V; fo.seed = 0; fo.counter = 0;
+    fo.logprob = nullptr; fo.entropy = const_cast<float*>(d_entropy); fo.A = (int)A; fo.V = (int)V; fo.seed = 0; fo.counter = 0;
     fo.c_logprob = d_c_logprob; fo.c_entropy = c_entropy; fo.g_out = (__nv_bfloat16*)d_g_bf16; fo.ldg = ldg;
+    fo.stat_m = const_cast<float*>(d_stat_max); fo.stat_s = const_cast<float*>(d_stat_sum);
     return launch_policy_fused("vmgym_policy_fused_grad", d_h_bf16, d_wpad_bf16, fo, M, V, A, K, stream);
 }

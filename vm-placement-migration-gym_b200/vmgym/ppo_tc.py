@@ -146,8 +146,10 @@ class TensorCoreNetwork:
         c1, c2 = self.hidden("critic", x)
         lp, ent = self._buf("lp", (M, V), f32), self._buf("ent", (M, V), f32)
         use_mask = mask if cfg.masked else None
-        nv.check(lib.vmgym_policy_fused(a2.data_ptr(), self.head.w_pad.data_ptr(), self.head.b_pad.data_ptr(), _ptr(use_mask),
-                                        action.data_ptr(), M, V, A, H, 0, 0, None, lp.data_ptr(), ent.data_ptr(), st), "vmgym_policy_fused")
+        st_m, st_s = self._buf("st_m", (M, V), f32), self._buf("st_s", (M, V), f32)
+        nv.check(lib.vmgym_policy_fused_eval(a2.data_ptr(), self.head.w_pad.data_ptr(), self.head.b_pad.data_ptr(), _ptr(use_mask),
+                                             action.data_ptr(), M, V, A, H, lp.data_ptr(), ent.data_ptr(), st_m.data_ptr(), st_s.data_ptr(), st),
+                 "vmgym_policy_fused_eval")
         new_lp, ent_sum = lp.sum(1), ent.sum(1)                                       # ppo.py:124-126
         value = self._buf("value", (M,), f32)
         vh = m.critic[4]
@@ -160,8 +162,8 @@ class TensorCoreNetwork:
         # ---- actor backward ----
         g = self._buf("g", (M, V * T), bf)
         nv.check(lib.vmgym_policy_fused_grad(a2.data_ptr(), self.head.w_pad.data_ptr(), self.head.b_pad.data_ptr(), _ptr(use_mask),
-                                             action.data_ptr(), M, V, A, H, c_lp.data_ptr(), -float(cfg.ent_coef) * inv_n, g.data_ptr(),
-                                             g.stride(0), st), "vmgym_policy_fused_grad")
+                                             action.data_ptr(), M, V, A, H, c_lp.data_ptr(), -float(cfg.ent_coef) * inv_n, ent.data_ptr(),
+                                             st_m.data_ptr(), st_s.data_ptr(), g.data_ptr(), g.stride(0), st), "vmgym_policy_fused_grad")
         self._gemm(g, 1, a2, 1, V * T, H, M, c32=self.gpad_w, accumulate=True, row_sum=self.gpad_b)          # dW3, db3 (padded rows)
         dz2 = self._buf("dz2", (M, H), bf)
         self._gemm(g, 0, self.head.w_pad, 1, M, H, V * T, mul_y=a2, c16=dz2)                                  # (g W3) * (1 - a2^2)
