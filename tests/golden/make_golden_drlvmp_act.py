@@ -27,7 +27,7 @@ import yaml  # noqa: E402
 
 CASES = {
     "act_s10": dict(base="10", over=dict(reward_function="wr", arrival_rate=0.4, service_length=40), hidden=64, steps=260, sample=(40, 90, 140, 200, 259)),
-    "act_s100": dict(base="100", over=dict(reward_function="wr", service_length=100), hidden=64, steps=90, sample=(30, 60, 89)),
+    "act_s100": dict(base="100", over=dict(reward_function="wr", service_length=100), hidden=64, steps=420, sample=tuple(range(120, 420, 12))),
 }
 
 
@@ -71,6 +71,26 @@ def run_case(name, spec):
             ch = np.full(V, -1, np.int8); mg = np.zeros(V, np.float32)
             for v, (c, m) in zip(waiting, log):
                 ch[v], mg[v] = c, m
+            # torch.argsort / argmin leave the order of equal keys unspecified (like np.argsort in bestfit.py): keep only the
+            # observations in which no decision hinges on a tie (the PM loads in the working observation never change during act,
+            # drlvmp.py:557-565, so keys and fits are those of the original observation)
+            P = cfg["pms"]
+            cpu, mem = obs[3 * V:3 * V + P], obs[3 * V + P:]
+            tie = False
+            for v in waiting:
+                vc, vm = obs[V + v], obs[2 * V + v]
+                if ch[v] in (0, 3):
+                    fit = (cpu + vc <= 1) & (mem + vm <= 1)
+                    key = (cpu + mem).astype(np.float32)
+                    pm = int(action[v])
+                    if pm < P and np.count_nonzero(fit & (key == key[pm])) > 1:
+                        tie = True
+                else:
+                    key = (cpu * vc + mem * vm) if ch[v] == 1 else np.sqrt((cpu - vc) ** 2 + (mem - vm) ** 2)
+                    if np.count_nonzero(key == key.min()) > 1:
+                        tie = True
+            if tie or len(waiting) == 0:
+                continue
             rows_obs.append(obs.copy()); rows_act.append(np.asarray(action, np.int64)); rows_choice.append(ch); rows_margin.append(mg)
     sd = {k[len("_orig_mod."):] if k.startswith("_orig_mod.") else k: v.detach().numpy() for k, v in agent.dqn.state_dict().items()}
     out = {f"{name}.cfg_json": json.dumps(cfg), f"{name}.hidden": spec["hidden"], f"{name}.obs": np.array(rows_obs, np.float32),
