@@ -326,14 +326,18 @@ def gpu_arm(args):
         torch.set_float32_matmul_precision("high")      # as the reference does (main.py:45)
         ag1 = DRLVMPAgent(v1, DRLVMPConfig(hidden_size=512))
         ag1.eval()
-        o1 = v1.observe()
-        o1, *_ = v1.step(ag1.act(o1), want_valid=False)            # graph capture / allocations
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(2):
-            o1, *_ = v1.step(ag1.act(o1), want_valid=False)
-        barrier()
-        s1000["drlvmp_s_per_step"] = (time.perf_counter() - t0) / 2
+        for mode in ("tc", "torch"):
+            # "tc": every GEMM of the per-VM iteration on the hand-written tcgen05 kernel with split-bf16 operands (fp32-accurate:
+            # the q-value argmax equals the reference's); "torch": the same loop on cuBLAS TF32 GEMMs (library baseline)
+            ag1.gemm = mode
+            o1 = v1.observe()
+            o1, *_ = v1.step(ag1.act(o1), want_valid=False)            # graph capture / allocations
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                o1, *_ = v1.step(ag1.act(o1), want_valid=False)
+            barrier()
+            s1000["drlvmp_s_per_step" + ("" if mode == "tc" else "_cublas")] = (time.perf_counter() - t0) / 2
         del v1, ag1
 
     # ---- extra C: the small shape of BASELINE configs[0] (config/10.yml, first-fit) at 2^20 envs per GPU ----
@@ -472,8 +476,12 @@ def gpu_arm(args):
                         "ms_per_step": s1000["ms_per_step"], "envs_per_gpu": s1000["envs_per_gpu"],
                         "roofline_frac_B_fused": B1 * s1000["envs_per_gpu"] / (s1000["ms_per_step"] * 1e-3) / 1e9 / peak,
                         "drlvmp_rollout": {"value": world * s1000["envs_per_gpu"] / s1000["drlvmp_s_per_step"], "unit": UNIT,
+                                           "cublas_tf32_value": world * s1000["envs_per_gpu"] / s1000["drlvmp_s_per_step_cublas"],
                                            "note": "DRLVMPAgent.act (H=512 dueling C51 net, one network evaluation + heuristic per waiting "
-                                                   "VM) + env.step"},
+                                                   "VM, ~1000 strictly sequential evaluations per step) + env.step; value: head GEMMs on the "
+                                                   "hand-written tcgen05 kernel, split-bf16 operands (fp32-accurate argmax); cublas_tf32_value: "
+                                                   "the same loop on cuBLAS TF32 GEMMs — a ~1 GFLOP GEMM per launch is latency-bound and the "
+                                                   "TMA / TMEM set-up of a tcgen05 kernel (~10 us) costs more than the library's mma.sync kernel"},
                         "config": "synthetic 1000 PMs / 3000 VM slots, highuniform sizes, arrival 1.6 (100 % load), fused best-fit act+step, "
                                   "one launch per step, team-mode kernel"}
         extras["s1000_M"] = round(out["s1000"]["value"] / 1e6, 2)

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define VMGYM_ABI_VERSION 7
+#define VMGYM_ABI_VERSION 8
 
 enum vmgym_status {
     VMGYM_OK = 0,
@@ -227,7 +227,9 @@ int vmgym_policy_heads_backward(const vmgym_config* cfg, const uint32_t* d_mask_
  * Operand X is K-major (x_mn = 0: row-major [rows, K], row stride ldx) or MN-major (x_mn = 1: row-major [K, rows]) — the
  * forward pass (activations x nn.Linear weights) is K-major x K-major, the input-gradient GEMM K-major x MN-major, the
  * weight-gradient GEMM (contracting over samples) MN-major x MN-major; no transposed copies are needed.  Epilogue, fused:
- * + d_bias[N], act (0 none, 1 tanh), * (1 - y^2) with d_mul_y bf16 [M, ldy] (tanh backward), fp32 output d_c_f32 (= or +=
+ * + d_bias[N], act (bits 0-1: 0 none, 1 tanh, 2 relu; bit 2: the fp32 output takes the value BEFORE the activation; bit 3: the bf16
+ * output is written as the split operand [hi | lo | hi] of vmgym_cast_split_bf16, segments N wide, ldc_bf16 >= 3 N),
+ * * (1 - y^2) with d_mul_y bf16 [M, ldy] (tanh backward), fp32 output d_c_f32 (= or +=
  * when `accumulate`) and / or bf16 output d_c_bf16, and d_row_sum[M] (= or +=) sum_k A(m, k) — the bias gradient of the
  * weight-gradient GEMM.  ld* in elements, multiples of 8 for the operands; operand bases 16-byte aligned. */
 int vmgym_tc_gemm(const void* d_a, int32_t a_mn, int64_t lda, const void* d_b, int32_t b_mn, int64_t ldb, int64_t M, int64_t N,
@@ -300,10 +302,13 @@ int vmgym_drlvmp_choice(const vmgym_config* cfg, const float* d_obs, const int32
  * four actions followed by the value atoms (Network.dist, :355-368) -> q-values -> argmax -> heuristic PM choice on the
  * working observation d_obs [n, 3V+2P] (as vmgym_drlvmp_choice) -> placement written into d_obs -> d_pre [n, hidden] (the
  * feature layer's pre-activation) corrected by the changed entry's weight column (d_w_cols [3V+2P, hidden], row j = column j
- * of the layer's weight) and d_feat = relu(d_pre).  d_order [n, V]: waiting slots first, in slot order; d_n_wait [n]. */
+ * of the layer's weight) and d_feat = relu(d_pre); d_feat_split_bf16 (may be NULL) [n, 3 hidden] receives the same activations as
+ * the [hi | lo | hi] bf16 split operand of the tensor-core head GEMMs (vmgym_tc_gemm).  d_order [n, V]: waiting slots first, in
+ * slot order; d_n_wait [n]. */
 int vmgym_drlvmp_iter(const vmgym_config* cfg, int32_t hidden, int32_t n_actions, int32_t atoms, const float* d_heads,
                       int32_t heads_ld, const float* d_support, float* d_obs, const int64_t* d_order, const int64_t* d_n_wait, const int64_t* d_k,
-                      int32_t k_offset, const float* d_w_cols, float* d_pre, float* d_feat, int64_t n_envs, void* stream);
+                      int32_t k_offset, const float* d_w_cols, float* d_pre, float* d_feat, void* d_feat_split_bf16, int64_t n_envs,
+                      void* stream);
 
 /* The actor's output layer (src/agents/ppo.py:103-109, nn.Linear(hidden, V*A)) on tcgen05 tensor cores:
  * d_c[M, N] (fp32, row stride ldc) = d_a[M, K] (bf16) . d_w[N, K]^T (bf16, the nn.Linear weight layout) + d_bias[N].

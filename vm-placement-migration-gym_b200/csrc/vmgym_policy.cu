@@ -4,6 +4,7 @@
 //
 // Reference: src/agents/ppo.py — Network.get_action (:115-126), PPOAgent.act gating (:151-155), update GAE (:237-242);
 // vmenv/envs/env.py:45-53 (get_invalid_action_mask), :35-42 (validate).
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -664,7 +665,7 @@ namespace vmgym {
 __global__ void drlvmp_iter_kernel(int P, int V, int D, int H, int n_actions, int atoms, const float* __restrict__ heads, int heads_ld,
                                    const float* __restrict__ support, float* obs, const long long* __restrict__ order,
                                    const long long* __restrict__ n_wait, const long long* __restrict__ kdev, int k_offset,
-                                   const float* __restrict__ w_cols, float* pre, float* feat, long long n_envs)
+                                   const float* __restrict__ w_cols, float* pre, float* feat, __nv_bfloat16* feat_split, long long n_envs)
 {
     const int lane = threadIdx.x & 31;
     const long long env = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -785,7 +786,14 @@ __global__ void drlvmp_iter_kernel(int P, int V, int D, int H, int n_actions, in
             if (h < H) {
                 const float x = a[i] + w[i] * delta;
                 pr[h] = x;
-                ft[h] = fmaxf(x, 0.f);
+                const float fx = fmaxf(x, 0.f);
+                ft[h] = fx;
+                if (feat_split) {
+                    // the tensor-core head GEMMs' operand: [hi | lo | hi] bf16 split of relu(pre) (vmgym_cast_split_bf16 layout)
+                    __nv_bfloat16* fs = feat_split + env * 3ll * H;
+                    const __nv_bfloat16 hi = __float2bfloat16(fx);
+                    fs[h] = hi; fs[H + h] = __float2bfloat16(fx - __bfloat162float(hi)); fs[2 * H + h] = hi;
+                }
             }
         }
     }
@@ -795,7 +803,8 @@ __global__ void drlvmp_iter_kernel(int P, int V, int D, int H, int n_actions, in
 
 extern "C" int vmgym_drlvmp_iter(const vmgym_config* cfg, int32_t hidden, int32_t n_actions, int32_t atoms, const float* d_heads,
                                  int32_t heads_ld, const float* d_support, float* d_obs, const int64_t* d_order, const int64_t* d_n_wait,
-                                 const int64_t* d_k, int32_t k_offset, const float* d_w_cols, float* d_pre, float* d_feat, int64_t n_envs,
+                                 const int64_t* d_k, int32_t k_offset, const float* d_w_cols, float* d_pre, float* d_feat, void* d_feat_split_bf16,
+                                 int64_t n_envs,
                                  void* stream)
 {
     if (!cfg || !d_heads || !d_support || !d_obs || !d_order || !d_n_wait || !d_k || !d_w_cols || !d_pre || !d_feat || n_envs < 0)
@@ -809,7 +818,7 @@ extern "C" int vmgym_drlvmp_iter(const vmgym_config* cfg, int32_t hidden, int32_
     const long long blocks = (n_envs * 32 + threads - 1) / threads;
     vmgym::drlvmp_iter_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
         P, V, D, hidden, n_actions, atoms, d_heads, heads_ld, d_support, d_obs, (const long long*)d_order, (const long long*)d_n_wait,
-        (const long long*)d_k, k_offset, d_w_cols, d_pre, d_feat, n_envs);
+        (const long long*)d_k, k_offset, d_w_cols, d_pre, d_feat, (__nv_bfloat16*)d_feat_split_bf16, n_envs);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return pfail(VMGYM_ECUDA, cudaGetErrorString(err));
     return VMGYM_OK;

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/vmgym.h"
 #include "vmgym_tc.cuh"
@@ -29,20 +30,22 @@ namespace vmgym_train {
 using namespace vmgym_gemm;
 
 constexpr int T_BM = 128, T_BN = 256, T_BK = 64;
-constexpr int T_STAGES = 4;
+constexpr int T_MAX_STAGES = 6;
 constexpr int T_A_BYTES = T_BM * T_BK * 2;                 // 16 KiB
-constexpr int T_B_BYTES = T_BN * T_BK * 2;                 // 32 KiB
-constexpr int T_STAGE_BYTES = T_A_BYTES + T_B_BYTES;       // 48 KiB
+constexpr int T_B_BYTES = T_BN * T_BK * 2;                 // 32 KiB (256-column tiles; 16 KiB with 128-column tiles)
+constexpr int T_RING_BYTES = 4 * (T_A_BYTES + T_B_BYTES);  // 192 KiB operand ring: 4 stages of 48 KiB or 6 stages of 32 KiB
 constexpr int T_ONES_BYTES = 16 * T_BK * 2;                // 2 KiB: 16 rows x 64 bf16 of 1.0 (any layout: all elements equal)
 constexpr int T_TMEM_COLS = 512;                           // 256 accumulator columns + 16 for the row sums -> next power of two
-constexpr int T_THREADS = 192;
-constexpr size_t T_SMEM_BYTES = (size_t)T_STAGES * T_STAGE_BYTES + T_ONES_BYTES + 1024 /* alignment */ + 256 /* barriers */;
+constexpr int T_THREADS = 320;                            // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr size_t T_SMEM_BYTES = (size_t)T_RING_BYTES + T_ONES_BYTES + 1024 /* alignment */ + 256 /* barriers */;
 
 struct GemmArgs {
     int M, N, K;
     int a_mn, b_mn;                    // 0: K-major operand (row-major [rows, K]); 1: MN-major (row-major [K, rows])
     const float* bias;                 // [N] or nullptr
-    int act;                           // 0 none, 1 tanh
+    int act;                           // 0 none, 1 tanh, 2 relu
+    int f32_pre;                       // the fp32 output takes the value BEFORE the activation (bias included)
+    int bf16_split;                    // the bf16 output is the split operand [hi | lo | hi] of vmgym_cast_split_bf16, segments N wide
     const __nv_bfloat16* mul_y;        // [M, ldy]: result *= 1 - y^2, or nullptr
     long long ldy;
     float* c_f32;                      // fp32 output [M, ldc_f32] or nullptr
@@ -69,9 +72,10 @@ __device__ __forceinline__ uint32_t umma_idesc(int m, int n, int a_mn, int b_mn)
 }
 __device__ __forceinline__ float tanh_fast(float x)
 {
-    // tanh(x) = 1 - 2 / (e^(2x) + 1); exact to float rounding for |x| up to overflow of e^(2x) (-> +-1)
-    const float e = __expf(2.0f * x);
-    return 1.0f - 2.0f / (e + 1.0f);
+    // one MUFU op; |error| ~ 2^-11 relative, far inside the bf16 rounding (2^-9) the result gets anyway
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 __global__ void __launch_bounds__(T_THREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
@@ -79,10 +83,13 @@ __global__ void __launch_bounds__(T_THREADS, 1) tc_gemm_kernel(const __grid_cons
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* s_ones = smem + (size_t)T_STAGES * T_STAGE_BYTES;
+    unsigned char* s_ones = smem + (size_t)T_RING_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_ones + T_ONES_BYTES);
-    uint64_t* empty_bar = full_bar + T_STAGES;
-    uint64_t* tmem_full_bar = empty_bar + T_STAGES;
+    uint64_t* empty_bar = full_bar + T_MAX_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + T_MAX_STAGES;
+    // narrower tiles leave room for a deeper ring: the K loop of a small GEMM is bound by the latency of its operand loads
+    const int T_STAGE_BYTES = T_A_BYTES + g.tile_n * T_BK * 2;
+    const int T_STAGES = g.tile_n <= 128 ? 6 : 4;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -100,7 +107,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) tc_gemm_kernel(const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < T_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < T_MAX_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -111,7 +118,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) tc_gemm_kernel(const __grid_cons
     if (warp >= 2 && do_rows) {
         // the tile of ones, written through the generic proxy and made visible to the tensor core's async proxy
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(s_ones);
-        for (int i = threadIdx.x - 64; i < T_ONES_BYTES / 2; i += 128) o[i] = __float2bfloat16(1.0f);
+        for (int i = threadIdx.x - 64; i < T_ONES_BYTES / 2; i += T_THREADS - 64) o[i] = __float2bfloat16(1.0f);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -168,14 +175,19 @@ __global__ void __launch_bounds__(T_THREADS, 1) tc_gemm_kernel(const __grid_cons
             umma_commit(tmem_full_bar);                                 // (also with an empty K slice: releases the epilogue)
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lanes 32 (warp % 4) .. +31 = rows of the tile; thread = row =====
+        // ===== epilogue: warps 2..9; a warp may touch TMEM lanes 32 (warp % 4) .. +31 = 32 rows of the tile (thread = row); the two
+        // warps of a lane quarter split the tile's columns (the tile's epilogue is not overlapped with a main loop, so its
+        // latency counts in full: measured 2x on the forward layers) =====
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;                                  // 0: first half of the tile's 32-column chunks, 1: second half
         const int row = m0 + q * 32 + lane;
         mbar_wait(tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const bool row_ok = row < g.M && k_blocks > 0;                // (an empty K slice of a split launch adds nothing)
+        const int n_chunks = (bn + 31) >> 5, c_mid = (n_chunks + 1) >> 1;
+        const int c_begin = half ? c_mid * 32 : 0, c_end = half ? bn : min(bn, c_mid * 32);
 #pragma unroll 1
-        for (int c0 = 0; c0 < bn; c0 += 32) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
             uint32_t r[32];
             tmem_ld_row32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
             if (!row_ok) continue;
@@ -187,8 +199,23 @@ __global__ void __launch_bounds__(T_THREADS, 1) tc_gemm_kernel(const __grid_cons
             for (int j = 0; j < 32; j++) {
                 float x = __uint_as_float(r[j]);
                 if (g.bias && j < nc) x += g.bias[col0 + j];
-                if (g.act == 1) x = tanh_fast(x);
                 v[j] = x;
+            }
+            if (g.c_f32 && g.f32_pre) {
+                float* dst = g.c_f32 + (long long)row * g.ldc_f32 + col0;
+                if (nc == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+                    for (int j = 0; j < nc; j++) dst[j] = v[j];
+                }
+            }
+            if (g.act == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = tanh_fast(v[j]);
+            } else if (g.act == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.0f);
             }
             if (g.mul_y) {
                 const __nv_bfloat16* y = g.mul_y + (long long)row * g.ldy + col0;
@@ -208,7 +235,9 @@ __global__ void __launch_bounds__(T_THREADS, 1) tc_gemm_kernel(const __grid_cons
                     for (int j = 0; j < nc; j++) { const float f = __bfloat162float(y[j]); v[j] *= 1.0f - f * f; }
                 }
             }
-            if (g.c_f32 && split) {
+            if (g.c_f32 && g.f32_pre) {
+                // already stored above
+            } else if (g.c_f32 && split) {
                 float* dst = g.c_f32 + (long long)row * g.ldc_f32 + col0;
 #pragma unroll
                 for (int j = 0; j < 32; j++) if (j < nc) atomicAdd(dst + j, v[j]);
@@ -225,7 +254,34 @@ __global__ void __launch_bounds__(T_THREADS, 1) tc_gemm_kernel(const __grid_cons
                     for (int j = 0; j < nc; j++) dst[j] = g.accumulate ? dst[j] + v[j] : v[j];
                 }
             }
-            if (g.c_bf16) {
+            if (g.c_bf16 && g.bf16_split) {
+                __nv_bfloat16* dst = g.c_bf16 + (long long)row * g.ldc_bf16 + col0;
+                if (nc == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (g.N & 7) == 0) {
+                    // 16-byte stores: 8 columns of the hi segment, of the lo segment and of the second hi segment at a time
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 uh, ul;
+                        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&uh);
+                        __nv_bfloat162* hl = reinterpret_cast<__nv_bfloat162*>(&ul);
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            const __nv_bfloat162 hi = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
+                            const float2 hf = __bfloat1622float2(hi);
+                            hh[t] = hi;
+                            hl[t] = __floats2bfloat162_rn(v[j + 2 * t] - hf.x, v[j + 2 * t + 1] - hf.y);
+                        }
+                        *reinterpret_cast<uint4*>(dst + j) = uh;
+                        *reinterpret_cast<uint4*>(dst + g.N + j) = ul;
+                        *reinterpret_cast<uint4*>(dst + 2 * g.N + j) = uh;
+                    }
+                } else {
+                    for (int j = 0; j < nc; j++) {
+                        const __nv_bfloat16 hi = __float2bfloat16(v[j]);
+                        const __nv_bfloat16 lo = __float2bfloat16(v[j] - __bfloat162float(hi));
+                        dst[j] = hi; dst[g.N + j] = lo; dst[2 * g.N + j] = hi;
+                    }
+                }
+            } else if (g.c_bf16) {
                 __nv_bfloat16* dst = g.c_bf16 + (long long)row * g.ldc_bf16 + col0;
                 if (nc == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
@@ -241,7 +297,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) tc_gemm_kernel(const __grid_cons
                 }
             }
         }
-        if (do_rows) {
+        if (do_rows && half == 0) {
             uint32_t r[32];
             tmem_ld_row32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)T_BN, r);    // 16 identical columns (+ 16 unused)
             if (row_ok) {
@@ -425,7 +481,8 @@ extern "C" int vmgym_tc_gemm(const void* d_a, int32_t a_mn, int64_t lda, const v
         return VMGYM_EINVAL;
     }
     if (M == 0 || N == 0) return VMGYM_OK;
-    if ((lda & 7) || (ldb & 7) || ((uintptr_t)d_a & 15) || ((uintptr_t)d_b & 15) || (act != 0 && act != 1)) {
+    const int act_fn = act & 3, f32_pre = (act >> 2) & 1, bf16_split = (act >> 3) & 1;
+    if ((lda & 7) || (ldb & 7) || ((uintptr_t)d_a & 15) || ((uintptr_t)d_b & 15) || act_fn == 3 || (act >> 4)) {
         vmgym_internal_set_error("vmgym_tc_gemm: operand row strides must be multiples of 8 elements and bases 16-byte aligned (TMA)");
         return VMGYM_EINVAL;
     }
@@ -437,7 +494,9 @@ extern "C" int vmgym_tc_gemm(const void* d_a, int32_t a_mn, int64_t lda, const v
         if (n_sm <= 0) n_sm = 148;
     }
     const long long m_tiles = (M + T_BM - 1) / T_BM;
-    const int tile_n = (((N + T_BN - 1) / T_BN) * m_tiles < n_sm && N > 128) ? 128 : T_BN;   // narrower tiles when 256-wide ones leave SMs idle
+    int tile_n = (((N + T_BN - 1) / T_BN) * m_tiles < n_sm && N > 128) ? 128 : T_BN;   // narrower tiles when 256-wide ones leave SMs idle
+    static const int force_tile = getenv("VMGYM_TC_TILE_N") ? atoi(getenv("VMGYM_TC_TILE_N")) : 0;      // A/B experiments
+    if (force_tile == 128 || force_tile == 256) tile_n = force_tile;
     CUtensorMap map_a, map_b;
     // K-major operand: tensor [rows, K], box = 64 (K) x tile rows.  MN-major operand: tensor [K, rows], box = 64 (rows) x 64 (K).
     const int ra = a_mn ? make_map2(&map_a, d_a, K, M, lda, 64, 64) : make_map2(&map_a, d_a, M, K, lda, T_BK, T_BM);
@@ -453,7 +512,7 @@ extern "C" int vmgym_tc_gemm(const void* d_a, int32_t a_mn, int64_t lda, const v
     }
     GemmArgs g;
     g.M = (int)M; g.N = (int)N; g.K = (int)K; g.a_mn = a_mn ? 1 : 0; g.b_mn = b_mn ? 1 : 0;
-    g.bias = d_bias; g.act = act; g.mul_y = (const __nv_bfloat16*)d_mul_y; g.ldy = ldy;
+    g.bias = d_bias; g.act = act_fn; g.f32_pre = f32_pre; g.bf16_split = bf16_split; g.mul_y = (const __nv_bfloat16*)d_mul_y; g.ldy = ldy;
     g.c_f32 = d_c_f32; g.ldc_f32 = ldc_f32; g.accumulate = accumulate;
     g.c_bf16 = (__nv_bfloat16*)d_c_bf16; g.ldc_bf16 = ldc_bf16; g.row_sum = d_row_sum;
     // split-K for accumulating fp32 outputs with too few tiles to fill the machine (dW = dz^T a over tens of thousands of samples
@@ -462,7 +521,7 @@ extern "C" int vmgym_tc_gemm(const void* d_a, int32_t a_mn, int64_t lda, const v
     const long long tiles = ((N + tile_n - 1) / tile_n) * m_tiles;
     const long long k_blocks = (K + T_BK - 1) / T_BK;
     g.k_splits = 1;
-    if (accumulate && d_c_f32 && !d_c_bf16 && !d_mul_y && !d_bias && act == 0 && tiles < n_sm && k_blocks >= 16) {
+    if (accumulate && d_c_f32 && !d_c_bf16 && !d_mul_y && !d_bias && act == 0 && tiles < n_sm && k_blocks >= 16) {   // (act == 0: no flags either)
         long long sp = (2ll * n_sm + tiles - 1) / tiles;
         if (sp > k_blocks / 8) sp = k_blocks / 8;                       // at least 8 k-blocks per slice
         if (sp > 1) {

@@ -145,7 +145,7 @@ def lib():
     L.vmgym_policy_heads_backward.argtypes = [C.POINTER(Config), vp, i32, vp, i64, vp, i32, vp, vp, vp, vp]
     L.vmgym_gae.argtypes = [vp, vp, vp, vp, C.c_int32, i64, f32, f32, vp, vp, vp]
     L.vmgym_drlvmp_choice.argtypes = [C.POINTER(Config), vp, vp, vp, i64, vp, vp]
-    L.vmgym_drlvmp_iter.argtypes = [C.POINTER(Config), i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i64, vp]
+    L.vmgym_drlvmp_iter.argtypes = [C.POINTER(Config), i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i64, vp]
     L.vmgym_linear_bf16.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp]
     L.vmgym_segtree_update.argtypes = [vp, vp, i64, vp, vp, C.c_int32, vp]
     L.vmgym_segtree_retrieve.argtypes = [vp, i64, vp, C.c_int32, vp, vp]

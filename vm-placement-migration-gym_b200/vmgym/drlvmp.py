@@ -260,10 +260,15 @@ class DRLVMPAgent(AgentBase):
         return action[0] if single else action
 
     def _act_fused(self, st, eff, obs, n, n_iter, refresh, lin):
-        """The per-VM iteration of act() as 2 GEMMs + `vmgym_drlvmp_iter`, captured once and replayed per waiting VM."""
+        """The per-VM iteration of act() as 2 GEMMs + `vmgym_drlvmp_iter`, captured once and replayed per waiting VM.
+        The GEMMs (both hidden heads side by side, both output heads block-diagonal, and the D x H feature product of every
+        `refresh`-th VM) run on the hand-written tcgen05 kernel `vmgym_tc_gemm` with split-bf16 operands ([hi | lo | hi] x
+        [hi | hi | lo], ~2^-16 relative: the q-value argmax must not move), unless `self.gemm == "torch"` (cuBLAS, A/B runs)."""
         vec, dev = self.vec, self.device
         (wah, bah), (wa, ba), (wvh, bvh), (wv, bv) = eff
         Hh, H, atoms, A = wah.shape[0], wah.shape[1], self.config.atom_size, self.n_actions
+        tc = getattr(self, "gemm", "tc") == "tc" and H % 8 == 0 and Hh % 4 == 0
+        lib = nv.lib()
         if "WhT" not in st:
             st["WhT"] = torch.empty((H, 2 * Hh), dtype=torch.float32, device=dev)
             st["bh"] = torch.empty(2 * Hh, dtype=torch.float32, device=dev)
@@ -272,6 +277,18 @@ class DRLVMPAgent(AgentBase):
             st["bo"] = torch.zeros(ld, dtype=torch.float32, device=dev)
             st["feat"] = torch.empty((n, H), dtype=torch.float32, device=dev)
             st["graph_fused"] = None
+            # tensor-core operands (bf16 splits): weights [out, 3 in] = [hi | hi | lo], activations [n, 3 in] = [hi | lo | hi]
+            Dp = (vec.obs_dim + 7) // 8 * 8
+            bf = torch.bfloat16
+            st["Dp"] = Dp
+            st["Wf_s"] = torch.zeros((H, 3 * Dp), dtype=bf, device=dev)
+            st["Wh_s"] = torch.zeros((2 * Hh, 3 * H), dtype=bf, device=dev)
+            st["Wo_s"] = torch.zeros((ld, 3 * 2 * Hh), dtype=bf, device=dev)
+            st["obs_s"] = torch.zeros((n, 3 * Dp), dtype=bf, device=dev)
+            st["feat_s"] = torch.zeros((n, 3 * H), dtype=bf, device=dev)
+            st["h_s"] = torch.zeros((n, 3 * 2 * Hh), dtype=bf, device=dev)
+            st["heads"] = torch.zeros((n, ld), dtype=torch.float32, device=dev)
+        ld = st["bo"].shape[0]
         # both hidden heads side by side; both output heads block-diagonal (advantage atoms | value atoms)
         st["WhT"][:, :Hh].copy_(wah.t()); st["WhT"][:, Hh:].copy_(wvh.t())
         st["bh"][:Hh].copy_(bah); st["bh"][Hh:].copy_(bvh)
@@ -280,22 +297,58 @@ class DRLVMPAgent(AgentBase):
         pre, feat, kdev = st["pre"], st["feat"], st["kdev"]
         ccfg = vec._ccfg()
 
+        def stream():
+            return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+        def split(src, dst, cols, cols_pad, order):
+            src = src.contiguous()
+            nv.check(lib.vmgym_cast_split_bf16(src.data_ptr(), src.shape[0], cols, src.stride(0), dst.data_ptr(), cols_pad, order, stream()),
+                     "vmgym_cast_split_bf16")
+
+        def gemm(a, b, M, N, K, bias, act, c32=None, c16=None):
+            nv.check(lib.vmgym_tc_gemm(a.data_ptr(), 0, a.stride(0), b.data_ptr(), 0, b.stride(0), M, N, K, bias.data_ptr(), act, None, 0,
+                                       c32.data_ptr() if c32 is not None else None, c32.stride(0) if c32 is not None else 0, 0,
+                                       c16.data_ptr() if c16 is not None else None, c16.stride(0) if c16 is not None else 0, None, stream()),
+                     "vmgym_tc_gemm")
+
+        if tc:
+            Dp = st["Dp"]
+            split(lin.weight, st["Wf_s"], vec.obs_dim, Dp, 1)
+            split(st["WhT"].t(), st["Wh_s"], H, H, 1)                         # [2 Hh, H] = the two hidden heads' nn.Linear weights
+            split(st["WoT"].t(), st["Wo_s"], 2 * Hh, 2 * Hh, 1)
+
+        def refresh_pre():
+            """pre = obs W_f^T + b_f from scratch, feat = relu(pre) (and its bf16 split)."""
+            if tc:
+                split(obs, st["obs_s"], vec.obs_dim, st["Dp"], 0)
+                # act = relu | fp32 output before the activation | split bf16 output
+                gemm(st["obs_s"], st["Wf_s"], n, H, 3 * st["Dp"], lin.bias, 2 | 4 | 8, c32=pre, c16=st["feat_s"])
+                torch.clamp(pre, min=0.0, out=feat)
+            else:
+                pre.copy_(lin(obs)); torch.clamp(pre, min=0.0, out=feat)
+
         act_mm = getattr(torch, "_addmm_activation", None)                    # addmm with the ReLU in the GEMM epilogue
 
         def iteration(k_offset=0):
-            h = act_mm(st["bh"], feat, st["WhT"]) if act_mm is not None else torch.addmm(st["bh"], feat, st["WhT"]).relu_()
-            heads = torch.addmm(st["bo"], h, st["WoT"])
-            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            nv.check(nv.lib().vmgym_drlvmp_iter(C.byref(ccfg), H, A, atoms, heads.data_ptr(), heads.shape[1], self.support.data_ptr(), obs.data_ptr(),
-                                                st["order"].data_ptr(), st["n_wait"].data_ptr(), kdev.data_ptr(), k_offset,
-                                                st["w_cols"].data_ptr(), pre.data_ptr(), feat.data_ptr(), n, stream), "vmgym_drlvmp_iter")
+            if tc:
+                gemm(st["feat_s"], st["Wh_s"], n, 2 * Hh, 3 * H, st["bh"], 2 | 8, c16=st["h_s"])                 # relu, split out
+                gemm(st["h_s"], st["Wo_s"], n, ld, 3 * 2 * Hh, st["bo"], 0, c32=st["heads"])
+                heads = st["heads"]
+            else:
+                h = act_mm(st["bh"], feat, st["WhT"]) if act_mm is not None else torch.addmm(st["bh"], feat, st["WhT"]).relu_()
+                heads = torch.addmm(st["bo"], h, st["WoT"])
+            nv.check(lib.vmgym_drlvmp_iter(C.byref(ccfg), H, A, atoms, heads.data_ptr(), heads.shape[1], self.support.data_ptr(), obs.data_ptr(),
+                                           st["order"].data_ptr(), st["n_wait"].data_ptr(), kdev.data_ptr(), k_offset,
+                                           st["w_cols"].data_ptr(), pre.data_ptr(), feat.data_ptr(),
+                                           st["feat_s"].data_ptr() if tc else None, n, stream()), "vmgym_drlvmp_iter")
 
         # several iterations per captured graph (fewer replays); iterations past an env's last waiting VM are no-ops
         unroll = next(u for u in (32, 16, 8, 4, 2, 1) if refresh % u == 0)       # 32: ~30 replays per act() at 1000 PMs (host-launch bound otherwise)
         if st["graph_fused"] is None:
             st["graph_fused"] = {}
-        if unroll not in st["graph_fused"] and n_iter > 0:
-            pre.copy_(lin(obs)); torch.clamp(pre, min=0.0, out=feat)
+        key = (unroll, tc)
+        if key not in st["graph_fused"] and n_iter > 0:
+            refresh_pre()
             keep = obs.clone()
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -308,11 +361,11 @@ class DRLVMPAgent(AgentBase):
                 for u in range(unroll):
                     iteration(u)                                               # VM k = device counter + u
                 kdev.add_(unroll)
-            st["graph_fused"][unroll] = g
+            st["graph_fused"][key] = g
         for k in range(0, n_iter, unroll):
             if k % refresh == 0:
-                pre.copy_(lin(obs)); torch.clamp(pre, min=0.0, out=feat)
-            st["graph_fused"][unroll].replay()
+                refresh_pre()
+            st["graph_fused"][key].replay()
 
     def _act_state(self, n: int):
         """Static buffers (and, lazily, the captured graph) of act() for a batch of n observations."""
