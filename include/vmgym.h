@@ -268,7 +268,7 @@ int vmgym_policy_fused_eval(const void* d_h_bf16, const void* d_wpad_bf16, const
 
 /* Backward of the fused actor head: recomputes the logits of each (128 envs x 1 VM) tile in tensor memory and, with the
  * forward's d_entropy / d_stat_max / d_stat_sum [M, V], writes d/dlogits of sum_e c_logprob[e] logprob(e) + c_entropy entropy(e)
- * in ONE pass over the accumulator as bf16 d_g_bf16[M, ldg] (column 128 v + a; zeros for masked and padding columns) — the
+ * in ONE pass over the accumulator as bf16 d_g_bf16[M, ldg] (column R v + a; zeros for masked and padding columns) — the
  * operand of the output layer's two backward GEMMs (vmgym_tc_gemm), and the only [samples, V x 128] tensor of the update that
  * reaches HBM. */
 int vmgym_policy_fused_grad(const void* d_h_bf16, const void* d_wpad_bf16, const float* d_bias_pad, const uint32_t* d_mask_bits,
@@ -319,10 +319,15 @@ int vmgym_linear_bf16(const void* d_a_bf16, const void* d_w_bf16, const float* d
 
 /* Fused actor head (ppo.py:103-109 output layer + :115-126 get_action): logits = h . Wpad^T + bias_pad are produced
  * per (128 envs x 1 VM) tile in tensor memory and consumed there — masked (-1e7), sampled (or d_action_in evaluated),
- * log-prob and entropy per (env, VM) — so the [M, V*A] logits never touch HBM.  d_wpad_bf16[V*128, K] / d_bias_pad[V*128]
- * hold VM v's A rows at [128 v, 128 v + A) (zero above); d_mask_bits[M, V, 4] are the packed invalid bits written by
+ * log-prob and entropy per (env, VM) — so the [M, V*A] logits never touch HBM.  d_wpad_bf16[V*R, K] / d_bias_pad[V*R]
+ * hold VM v's A rows at [R v, R v + A) (zero above; R = vmgym_policy_fused_rows(A, K)); d_mask_bits[M, V, 4] are the packed invalid bits written by
  * vmgym_policy_heads(d_logits = NULL, d_mask_out = ...), or NULL for no mask.  Requires action_dim <= 128 (u8 actions).
  * Sum d_logprob / d_entropy [M, V] over V for the per-env values of ppo.py:126. */
+/* Rows per VM (R) of the padded output-layer operands of the fused head: d_wpad_bf16[V * R, K] / d_bias_pad[V * R] hold VM v's A
+ * rows at [R v, R v + A) (zeros above), and vmgym_policy_fused_grad writes VM v's gradient columns at [R v, R v + R).
+ * R = A rounded up to 16 for the persistent kernel (K <= 512), 128 for the tile-per-CTA fallback. */
+int vmgym_policy_fused_rows(int64_t A, int64_t K);
+
 int vmgym_policy_fused(const void* d_h_bf16, const void* d_wpad_bf16, const float* d_bias_pad, const uint32_t* d_mask_bits,
                        const void* d_action_in, int64_t M, int64_t V, int64_t A, int64_t K, uint64_t seed, uint64_t counter,
                        uint8_t* d_action_out, float* d_logprob, float* d_entropy, void* stream);

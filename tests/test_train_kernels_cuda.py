@@ -193,7 +193,9 @@ def test_fused_head_gradient_mode_matches_autograd(V, A, M):
     words.copy_(torch.from_numpy((pk.reshape(M, V, 4, 32) << np.arange(32, dtype=np.uint64)).sum(-1).astype(np.uint32).view(np.int32)))
     c_lp = torch.randn(M, device="cuda")
     c_ent = -0.37
-    g = torch.full((M, V * 128 + 8), float("nan"), dtype=torch.bfloat16, device="cuda")
+    R = head.TILE                                                        # columns per VM in the gradient tensor: A rounded up to 16
+    assert R == (A + 15) // 16 * 16 == lib.vmgym_policy_fused_rows(A, K)
+    g = torch.full((M, V * R + 8), float("nan"), dtype=torch.bfloat16, device="cuda")
     lp_f, en_f = torch.empty((M, V), device="cuda"), torch.empty((M, V), device="cuda")
     st_m, st_s = torch.empty((M, V), device="cuda"), torch.empty((M, V), device="cuda")
     nv.check(lib.vmgym_policy_fused_eval(h.data_ptr(), head.w_pad.data_ptr(), head.b_pad.data_ptr(), words.data_ptr(), act.data_ptr(), M, V, A, K,
@@ -213,7 +215,7 @@ def test_fused_head_gradient_mode_matches_autograd(V, A, M):
     rent = -(logp.exp() * logp).sum(-1).detach()
     assert torch.allclose(lp_f.double(), rlp, rtol=1e-4, atol=2e-4) and torch.allclose(en_f.double(), rent, rtol=1e-4, atol=2e-4)
     ref = logits.grad.reshape(M, V, A)
-    got = g[:, :V * 128].reshape(M, V, 128).double()
+    got = g[:, :V * R].reshape(M, V, R).double()
     assert bool((got[:, :, A:] == 0).all()), "padding columns must be zero"
     assert bool((got[:, :, :A][mask] == 0).all()), "masked columns must get no gradient"
     err = (got[:, :, :A] - ref).abs()

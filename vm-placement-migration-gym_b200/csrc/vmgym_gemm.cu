@@ -201,6 +201,7 @@ struct FusedOut {
     // call (action_in given) when non-null; READ by the gradient mode, which then needs a single pass over the accumulator.
     float* stat_m;
     float* stat_s;
+    int apad;                    // rows per VM in w_pad / bias_pad and columns per VM in g_out: vmgym_policy_fused_rows(A, K)
 };
 
 // Per-row running state of the fused epilogue.
@@ -416,9 +417,9 @@ __device__ __forceinline__ void eval_epilogue_row(const FusedOut& fo, const floa
     // H = (lse - m) - tsum / ssum needs tsum: recomputed here from the same pass would need two passes, so the forward's
     // entropy output is used instead (it is the same number)
     const float H = (live && fo.entropy) ? fo.entropy[(long long)e * fo.V + v] : 0.f;
-    __nv_bfloat16* grow = fo.g_out + (long long)e * fo.ldg + (long long)v * BN;
+    __nv_bfloat16* grow = fo.g_out + (long long)e * fo.ldg + (long long)v * fo.apad;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = 0; c0 < fo.apad; c0 += 32) {
         uint32_t gb[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) gb[k] = 0u;
@@ -473,10 +474,11 @@ __device__ __forceinline__ void eval_epilogue_row(const FusedOut& fo, const floa
         }
         if (live) {
             uint4* dst = reinterpret_cast<uint4*>(grow + c0);
+            const int n8 = min(4, (fo.apad - c0) >> 3);                  // 16-byte pieces of this chunk inside the VM's apad columns
             dst[0] = make_uint4(gb[0], gb[1], gb[2], gb[3]);
-            dst[1] = make_uint4(gb[4], gb[5], gb[6], gb[7]);
-            dst[2] = make_uint4(gb[8], gb[9], gb[10], gb[11]);
-            dst[3] = make_uint4(gb[12], gb[13], gb[14], gb[15]);
+            if (n8 > 1) dst[1] = make_uint4(gb[4], gb[5], gb[6], gb[7]);
+            if (n8 > 2) dst[2] = make_uint4(gb[8], gb[9], gb[10], gb[11]);
+            if (n8 > 3) dst[3] = make_uint4(gb[12], gb[13], gb[14], gb[15]);
         }
     }
 }
@@ -518,7 +520,7 @@ __global__ void __launch_bounds__(THREADS, 1) policy_fused_kernel(const __grid_c
 // Roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2+4g .. 5+4g epilogue group g
 // (a warp may touch TMEM lanes 32 (warp % 4) .. +31, so both groups cover all 128 lanes).
 // ---------------------------------------------------------------------------------------------------
-constexpr int P_GROUPS = 3;                                    // epilogue warpgroups = TMEM accumulators in flight
+constexpr int P_GROUPS = 4;                                    // epilogue warpgroups = TMEM accumulators in flight
 constexpr int P_THREADS = 64 + 128 * P_GROUPS;
 constexpr int P_TMEM_COLS = P_GROUPS <= 2 ? 256 : 512;         // power of two >= P_GROUPS * 128
 constexpr int P_WSTAGES = 5;
@@ -575,7 +577,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) policy_fused_persistent_kernel(c
         if (lane == 0) {
             uint32_t wcount = 0, ucount = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x, ucount++) {
-                const int mt = u / v_chunks, vc = u % v_chunks;
+                const int vc = u / m_tiles, mt = u % m_tiles;       // CTAs running side by side share the VM chunk's W tiles (L2)
                 const int v0 = vc * P_VCHUNK, v1 = min(fo.V, v0 + P_VCHUNK);
                 mbar_wait(a_empty, (ucount & 1u) ^ 1u);                        // previous unit's MMAs have read A
                 mbar_expect_tx(a_full, (uint32_t)(k_blocks * P_SLICE_BYTES));
@@ -584,8 +586,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) policy_fused_persistent_kernel(c
                     for (int kb = 0; kb < k_blocks; kb++, wcount++) {
                         const int s = wcount % P_WSTAGES;
                         mbar_wait(&w_empty[s], ((wcount / P_WSTAGES) & 1u) ^ 1u);
-                        mbar_expect_tx(&w_full[s], P_SLICE_BYTES);
-                        tma_load_2d(s_w + (size_t)s * P_SLICE_BYTES, &map_w, kb * BK, v * BN, &w_full[s]);
+                        mbar_expect_tx(&w_full[s], (uint32_t)(fo.apad * BK * 2));
+                        tma_load_2d(s_w + (size_t)s * P_SLICE_BYTES, &map_w, kb * BK, v * fo.apad, &w_full[s]);
                     }
                 }
             }
@@ -593,10 +595,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) policy_fused_persistent_kernel(c
     } else if (warp == 1) {
         // ===== MMA issuer (single thread) =====
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+            const uint32_t idesc = umma_idesc_bf16_f32(BM, fo.apad);     // N = the VM's (padded) row count: multiple of 16
             uint32_t wcount = 0, ucount = 0, tcount = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x, ucount++) {
-                const int vc = u % v_chunks;
+                const int vc = u / m_tiles;
                 const int v0 = vc * P_VCHUNK, v1 = min(fo.V, v0 + P_VCHUNK);
                 mbar_wait(a_full, ucount & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -629,12 +631,12 @@ __global__ void __launch_bounds__(P_THREADS, 1) policy_fused_persistent_kernel(c
         float* bias_g = s_bias + g * 128;
         uint32_t tcount = 0;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const int mt = u / v_chunks, vc = u % v_chunks;
+            const int vc = u / m_tiles, mt = u % m_tiles;
             const int v0 = vc * P_VCHUNK, v1 = min(fo.V, v0 + P_VCHUNK);
             for (int v = v0; v < v1; v++, tcount++) {
                 if (tcount % P_GROUPS != (uint32_t)g) continue;
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");    // previous tile's readers of bias_g are done
-                bias_g[tg] = fo.bias_pad[v * BN + tg];
+                bias_g[tg] = tg < fo.apad ? fo.bias_pad[v * fo.apad + tg] : 0.f;
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
                 const RowIn in = fused_epilogue_prefetch(fo, q, lane, mt * BM, v, M);
                 mbar_wait(&acc_full[g], (tcount / P_GROUPS) & 1u);
@@ -693,6 +695,16 @@ extern "C" int vmgym_linear_bf16(const void* d_a_bf16, const void* d_w_bf16, con
     return VMGYM_OK;
 }
 
+// rows per VM of the padded output-layer weights / bias (and columns per VM of the logit gradients): the persistent kernel (K <= 512)
+// issues MMAs of N = align16(A) columns, the tile-per-CTA fallback keeps full 128-column tiles
+extern "C" int vmgym_policy_fused_rows(int64_t A, int64_t K)
+{
+    using namespace vmgym_gemm;
+    static const int persistent = getenv("VMGYM_FUSED_PERSISTENT") ? atoi(getenv("VMGYM_FUSED_PERSISTENT")) : 1;
+    if (A < 1 || A > 128) return 0;
+    return (persistent && K <= P_KSLICES * BK) ? (int)((A + 15) / 16 * 16) : BN;
+}
+
 static int launch_policy_fused(const char* who, const void* d_h_bf16, const void* d_wpad_bf16, vmgym_gemm::FusedOut fo, int64_t M, int64_t V,
                                int64_t A, int64_t K, void* stream)
 {
@@ -704,8 +716,9 @@ static int launch_policy_fused(const char* who, const void* d_h_bf16, const void
         return VMGYM_EUNSUPPORTED;
     }
     if (M == 0 || V == 0) return VMGYM_OK;
+    fo.apad = vmgym_policy_fused_rows(A, K);
     CUtensorMap map_a, map_w;
-    if (make_map(&map_a, d_h_bf16, (int)M, (int)K, BM) || make_map(&map_w, d_wpad_bf16, (int)(V * BN), (int)K, BN)) {
+    if (make_map(&map_a, d_h_bf16, (int)M, (int)K, BM) || make_map(&map_w, d_wpad_bf16, (int)(V * fo.apad), (int)K, fo.apad)) {
         snprintf(msg, sizeof(msg), "%s: cuTensorMapEncodeTiled failed", who);
         vmgym_internal_set_error(msg);
         return VMGYM_ECUDA;
@@ -782,8 +795,8 @@ extern "C" int vmgym_policy_fused_grad(const void* d_h_bf16, const void* d_wpad_
 {
     using namespace vmgym_gemm;
     if (!d_h_bf16 || !d_wpad_bf16 || !d_bias_pad || !d_action_in || !d_c_logprob || !d_entropy || !d_stat_max || !d_stat_sum || !d_g_bf16 ||
-        M < 0 || ldg < V * BN || (ldg & 7) || ((uintptr_t)d_g_bf16 & 15)) {
-        vmgym_internal_set_error("vmgym_policy_fused_grad: null operand, or ldg < 128 V / not a multiple of 8, or unaligned output");
+        M < 0 || ldg < V * vmgym_policy_fused_rows(A, K) || (ldg & 7) || ((uintptr_t)d_g_bf16 & 15)) {
+        vmgym_internal_set_error("vmgym_policy_fused_grad: null operand, or ldg < V * vmgym_policy_fused_rows(A, K) / not a multiple of 8, or unaligned output");
         return VMGYM_EINVAL;
     }
     FusedOut fo;

@@ -163,14 +163,13 @@ def linear_bf16(a: torch.Tensor, weight_bf16: torch.Tensor, bias: torch.Tensor |
 
 class FusedActorHead:
     """The actor's output layer + masked multi-categorical heads as ONE tcgen05 kernel (vmgym_policy_fused): logits live
-    only in tensor memory.  Holds the bf16 re-layout of nn.Linear(hidden, V*A): VM v's A rows at [128 v, 128 v + A)."""
-
-    TILE = 128
+    only in tensor memory.  Holds the bf16 re-layout of nn.Linear(hidden, V*A): VM v's A rows at [R v, R v + A), R = TILE."""
 
     def __init__(self, linear: nn.Linear, n_vms: int, action_dim: int):
-        if action_dim > self.TILE:
+        if action_dim > 128:
             raise nv.VmgymError("the fused actor head needs action_dim <= 128")
         self.V, self.A, self.K = int(n_vms), int(action_dim), linear.in_features
+        self.TILE = int(nv.lib().vmgym_policy_fused_rows(self.A, self.K))     # rows per VM of the padded operands (include/vmgym.h)
         self.linear = linear
         self.refresh()
 

@@ -28,8 +28,6 @@ def _ptr(t):
 
 
 class TensorCoreNetwork:
-    TILE = 128           # rows of the padded output layer per VM (FusedActorHead layout)
-
     def __init__(self, agent, max_chunk: int):
         from .ppo import FusedActorHead
         self.agent = agent
@@ -43,6 +41,7 @@ class TensorCoreNetwork:
         if agent._fused is None:
             agent._fused = FusedActorHead(m.actor[4], self.V, self.A)
         self.head = agent._fused
+        self.TILE = self.head.TILE       # rows of the padded output layer per VM (FusedActorHead layout)
         H, Dp, dev = self.H, self.Dp, self.dev
         bf = torch.bfloat16
         # first layer: split operands [hi | hi | lo] x [hi | lo | hi] over a 3 Dp-wide K (vmgym_cast_split_bf16): raw observations mix
