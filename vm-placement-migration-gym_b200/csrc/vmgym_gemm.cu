@@ -400,7 +400,7 @@ __device__ __forceinline__ uint32_t eval_valid_bits(const FusedOut& fo, const ui
 }
 
 __device__ __forceinline__ void eval_epilogue_row(const FusedOut& fo, const float* s_bias, uint32_t tmem_acc, const RowIn& in, int q,
-                                                  int lane, int m0, int v, int M)
+                                                  int lane, int m0, int v, int M, uint32_t stage_addr)
 {
     const int e = m0 + q * 32 + lane;
     const int A = fo.A;
@@ -472,7 +472,30 @@ __device__ __forceinline__ void eval_epilogue_row(const FusedOut& fo, const floa
                 VMGYM_PUT16(gb, k, wnew);
             }
         }
-        if (live) {
+        if (stage_addr) {
+            // coalesced store: the warp's 32 rows x 64 B go through its 2 KB staging buffer (16-byte pieces XOR-swizzled: no bank
+            // conflicts either way) and leave as 8 rows x 64 contiguous bytes per store instruction — full 32-byte sectors.  One row
+            // per thread (32 rows x 16 B, 67 KB apart) wrote half sectors: 0.7 ms of a 2.0 ms call (profiles/r2_fused_head.md)
+            const uint32_t wr = stage_addr + (uint32_t)lane * 64u, sw = (uint32_t)(lane >> 1) & 3u;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wr + ((0u ^ sw) << 4)), "r"(gb[0]), "r"(gb[1]), "r"(gb[2]), "r"(gb[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wr + ((1u ^ sw) << 4)), "r"(gb[4]), "r"(gb[5]), "r"(gb[6]), "r"(gb[7]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wr + ((2u ^ sw) << 4)), "r"(gb[8]), "r"(gb[9]), "r"(gb[10]), "r"(gb[11]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wr + ((3u ^ sw) << 4)), "r"(gb[12]), "r"(gb[13]), "r"(gb[14]), "r"(gb[15]) : "memory");
+            __syncwarp();
+            const int pc = lane & 3;
+            const bool pc_ok = c0 + pc * 8 < fo.apad;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int row = i * 8 + (lane >> 2);
+                uint4 w;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+                             : "r"(stage_addr + (uint32_t)row * 64u + ((((uint32_t)pc) ^ ((uint32_t)(row >> 1) & 3u)) << 4)));
+                const int er = m0 + q * 32 + row;
+                if (er < M && pc_ok)
+                    *reinterpret_cast<uint4*>(fo.g_out + (long long)er * fo.ldg + (long long)v * fo.apad + c0 + pc * 8) = w;
+            }
+            __syncwarp();
+        } else if (live) {
             uint4* dst = reinterpret_cast<uint4*>(grow + c0);
             const int n8 = min(4, (fo.apad - c0) >> 3);                  // 16-byte pieces of this chunk inside the VM's apad columns
             dst[0] = make_uint4(gb[0], gb[1], gb[2], gb[3]);
@@ -505,7 +528,7 @@ __global__ void __launch_bounds__(THREADS, 1) policy_fused_kernel(const __grid_c
         const RowIn in = fused_epilogue_prefetch(fo, warp & 3, lane, m0, v, M);
         mbar_wait(pipe.tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (fo.g_out) eval_epilogue_row(fo, s_bias, tmem_base, in, warp & 3, lane, m0, v, M);
+        if (fo.g_out) eval_epilogue_row(fo, s_bias, tmem_base, in, warp & 3, lane, m0, v, M, 0u);
         else fused_epilogue_row(fo, s_bias, tmem_base, in, warp & 3, lane, m0, v, M);
     }
     pipe_teardown(tmem_base, warp);
@@ -521,13 +544,16 @@ __global__ void __launch_bounds__(THREADS, 1) policy_fused_kernel(const __grid_c
 // (a warp may touch TMEM lanes 32 (warp % 4) .. +31, so both groups cover all 128 lanes).
 // ---------------------------------------------------------------------------------------------------
 constexpr int P_GROUPS = 4;                                    // epilogue warpgroups = TMEM accumulators in flight
-constexpr int P_THREADS = 64 + 128 * P_GROUPS;
+constexpr int P_THREADS = 64 + 128 * P_GROUPS + 32;           // + the second MMA issuer (last warp)
 constexpr int P_TMEM_COLS = P_GROUPS <= 2 ? 256 : 512;         // power of two >= P_GROUPS * 128
-constexpr int P_WSTAGES = 5;
+static_assert(P_TMEM_COLS == 512, "the MMA warp assumes the whole TMEM (allocation base 0)");
+constexpr int P_WSTAGES = 4;
 constexpr int P_KSLICES = 8;                                   // K <= 512
 constexpr int P_SLICE_BYTES = BM * BK * 2;                     // 16 KiB: one K-slice of a 128-row operand tile
 constexpr int P_VCHUNK = 10;                                   // VM tiles per unit
-constexpr size_t P_SMEM_BYTES = (size_t)(P_KSLICES + P_WSTAGES) * P_SLICE_BYTES + 1024 /* alignment */ + 2048 /* barriers, bias x2 */;
+constexpr int P_STAGE_BYTES = 2048;                            // per epilogue warp: 32 rows x 64 B of logit gradients on their way out
+constexpr size_t P_SMEM_BYTES = (size_t)(P_KSLICES + P_WSTAGES) * P_SLICE_BYTES + (size_t)P_GROUPS * 4 * P_STAGE_BYTES +
+                                1024 /* alignment */ + 2048 /* barriers, bias per group */;
 
 __global__ void __launch_bounds__(P_THREADS, 1) policy_fused_persistent_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                                 const __grid_constant__ CUtensorMap map_w, FusedOut fo,
@@ -537,7 +563,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) policy_fused_persistent_kernel(c
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* s_a = smem;                                              // P_KSLICES slices, resident per unit
     unsigned char* s_w = smem + (size_t)P_KSLICES * P_SLICE_BYTES;          // ring of W K-slices
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + (size_t)P_WSTAGES * P_SLICE_BYTES);
+    unsigned char* s_stage = s_w + (size_t)P_WSTAGES * P_SLICE_BYTES;       // P_STAGE_BYTES per epilogue warp
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + (size_t)P_GROUPS * 4 * P_STAGE_BYTES);
     uint64_t* w_full = bars;                 // [P_WSTAGES]
     uint64_t* w_empty = bars + P_WSTAGES;    // [P_WSTAGES]
     uint64_t* a_full = bars + 2 * P_WSTAGES; // [1]
@@ -558,8 +585,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) policy_fused_persistent_kernel(c
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < P_WSTAGES; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        mbar_init(a_full, 1); mbar_init(a_empty, 1);
+        for (int s = 0; s < P_WSTAGES; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }
+        mbar_init(a_full, 1); mbar_init(a_empty, 2);                  // both MMA issuers release the unit's activation tile
         for (int g = 0; g < P_GROUPS; g++) { mbar_init(&acc_full[g], 1); mbar_init(&acc_empty[g], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -592,36 +619,53 @@ __global__ void __launch_bounds__(P_THREADS, 1) policy_fused_persistent_kernel(c
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer (single thread) =====
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16_f32(BM, fo.apad);     // N = the VM's (padded) row count: multiple of 16
-            uint32_t wcount = 0, ucount = 0, tcount = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ucount++) {
-                const int vc = u / m_tiles;
-                const int v0 = vc * P_VCHUNK, v1 = min(fo.V, v0 + P_VCHUNK);
-                mbar_wait(a_full, ucount & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int v = v0; v < v1; v++, tcount++) {
-                    const uint32_t g = tcount % P_GROUPS;
-                    mbar_wait(&acc_empty[g], ((tcount / P_GROUPS) & 1u) ^ 1u); // epilogue group g has drained its accumulator
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t acc = tmem_base + g * TMEM_COLS;
-                    for (int kb = 0; kb < k_blocks; kb++, wcount++) {
-                        const int s = wcount % P_WSTAGES;
-                        mbar_wait(&w_full[s], (wcount / P_WSTAGES) & 1u);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t sa = smem_u32(s_a + (size_t)kb * P_SLICE_BYTES);
-                        const uint32_t sb = smem_u32(s_w + (size_t)s * P_SLICE_BYTES);
-#pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; k++)
-                            umma_bf16(acc, umma_desc_sw128(sa + k * UMMA_K * 2), umma_desc_sw128(sb + k * UMMA_K * 2), idesc, (kb | k) ? 1u : 0u);
-                        umma_commit(&w_empty[s]);
+    } else if (warp == 1 || warp == P_THREADS / 32 - 1) {
+        // ===== MMA issuers: two warps on different schedulers, issuer i takes the tiles with tile index % 2 == i.  A 128 x apad x 64
+        // K block is ~224 tensor cycles but ~60 dependent SASS instructions to issue (barrier wait, descriptor adds, commit) for a
+        // warp that shares its scheduler with four epilogue warps: one issuer needed ~560 cycles per K block and was the bottleneck
+        // of the kernel (profiles/r2_fused_head.md).  The whole warp walks the loop (uniform control flow keeps the address arithmetic
+        // on the uniform datapath), one elected lane issues.  All 512 TMEM columns are this CTA's, so the allocation starts at
+        // column 0 and the accumulator addresses are plain loop arithmetic (checked once below). =====
+        if (tmem_base != 0u) __trap();
+        const uint32_t me = warp == 1 ? 0u : 1u;
+        const uint32_t idesc = umma_idesc_bf16_f32(BM, fo.apad);         // N = the VM's (padded) row count: multiple of 16
+        const uint32_t a_lo0 = umma_desc_lo(smem_u32(s_a)), w_lo0 = umma_desc_lo(smem_u32(s_w));
+        uint32_t ws = 0, wphase = 0, ucount = 0, tcount = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ucount++) {
+            const int vc = u / m_tiles;
+            const int v0 = vc * P_VCHUNK, v1 = min(fo.V, v0 + P_VCHUNK);
+            mbar_wait(a_full, ucount & 1u);
+            for (int v = v0; v < v1; v++, tcount++) {
+                if ((tcount & 1u) != me) {
+                    // the other issuer's tile.  A parity wait only works for a waiter that sees EVERY phase of its barrier, so this
+                    // warp still observes each ring slot fill and is one of the slot's two releases (w_empty counts 2 arrivals)
+                    for (int kb = 0; kb < k_blocks; kb++) {
+                        mbar_wait(&w_full[ws], wphase);
+                        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&w_empty[ws])) : "memory");
+                        __syncwarp();
+                        if (++ws == P_WSTAGES) { ws = 0; wphase ^= 1u; }
                     }
-                    umma_commit(&acc_full[g]);
+                    continue;
                 }
-                umma_commit(a_empty);                                          // all MMAs reading this unit's A have retired
+                const uint32_t g = tcount % P_GROUPS;
+                mbar_wait(&acc_empty[g], ((tcount / P_GROUPS) & 1u) ^ 1u);     // epilogue group g has drained its accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc = g * TMEM_COLS;
+#pragma unroll 1
+                for (int kb = 0; kb < k_blocks; kb++) {
+                    mbar_wait(&w_full[ws], wphase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        umma_bf16_k64(acc, a_lo0 + (uint32_t)kb * (P_SLICE_BYTES >> 4), w_lo0 + ws * (P_SLICE_BYTES >> 4), idesc, kb ? 1u : 0u);
+                        umma_commit(&w_empty[ws]);
+                        if (kb == k_blocks - 1) umma_commit(&acc_full[g]);
+                    }
+                    __syncwarp();
+                    if (++ws == P_WSTAGES) { ws = 0; wphase ^= 1u; }
+                }
             }
+            if (elect_one()) umma_commit(a_empty);                             // this issuer's MMAs on the unit's A have retired
+            __syncwarp();
         }
     } else {
         // ===== epilogue groups: group g = warps 2+4g .. 5+4g handles the tiles with tile index % P_GROUPS == g =====
@@ -629,6 +673,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) policy_fused_persistent_kernel(c
         const int q = warp & 3;
         const int tg = threadIdx.x - 64 - g * 128;                             // 0..127 inside the group
         float* bias_g = s_bias + g * 128;
+        const uint32_t stage_w = smem_u32(s_stage + (size_t)(warp - 2) * P_STAGE_BYTES);
         uint32_t tcount = 0;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             const int vc = u / m_tiles, mt = u % m_tiles;
@@ -641,7 +686,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) policy_fused_persistent_kernel(c
                 const RowIn in = fused_epilogue_prefetch(fo, q, lane, mt * BM, v, M);
                 mbar_wait(&acc_full[g], (tcount / P_GROUPS) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (fo.g_out) eval_epilogue_row(fo, bias_g, tmem_base + g * TMEM_COLS, in, q, lane, mt * BM, v, M);
+                if (fo.g_out) eval_epilogue_row(fo, bias_g, tmem_base + g * TMEM_COLS, in, q, lane, mt * BM, v, M, stage_w);
                 else fused_epilogue_row(fo, bias_g, tmem_base + g * TMEM_COLS, in, q, lane, mt * BM, v, M);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[g])) : "memory");

@@ -67,6 +67,55 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One 64-wide K block (4 MMAs of K = 16) of K-major SW128 operands as a single instruction group: the descriptors differ only in
+// their low words (start address >> 4, + 2 per 32-byte K step), so the four MMAs need three 32-bit adds and no per-MMA descriptor
+// rebuild.  `a_lo` / `b_lo` = low words of umma_desc_sw128(address of the K block), UMMA_DESC_HI the constant high word.
+// Measured (profiles/r2_fused_head.md): rebuilding 64-bit descriptors per MMA in a lane-0 branch cost ~100 SASS instructions and
+// ~675 cycles per K block — 3x the MMA time — which made the single issuing thread the bottleneck of the fused head.
+constexpr uint32_t UMMA_DESC_HI = 64u | (1u << 14) | (2u << 29);        // SBO = 1024 B, descriptor version 1, 128 B swizzle
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ void umma_bf16_k64(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate_first)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b32 a1, a2, a3, b1, b2, b3;\n\t"
+        ".reg .b64 da0, db0, da1, db1, da2, db2, da3, db3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.b32 q, %5, %5;\n\t"
+        "add.u32 a1, %1, 2;\n\t"
+        "add.u32 b1, %2, 2;\n\t"
+        "add.u32 a2, %1, 4;\n\t"
+        "add.u32 b2, %2, 4;\n\t"
+        "add.u32 a3, %1, 6;\n\t"
+        "add.u32 b3, %2, 6;\n\t"
+        "mov.b64 da0, {%1, %5};\n\t"
+        "mov.b64 db0, {%2, %5};\n\t"
+        "mov.b64 da1, {a1, %5};\n\t"
+        "mov.b64 db1, {b1, %5};\n\t"
+        "mov.b64 da2, {a2, %5};\n\t"
+        "mov.b64 db2, {b2, %5};\n\t"
+        "mov.b64 da3, {a3, %5};\n\t"
+        "mov.b64 db3, {b3, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db0, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da1, db1, %3, q;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da2, db2, %3, q;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da3, db3, %3, q;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate_first), "r"(UMMA_DESC_HI)
+        : "memory");
+}
+// true in exactly one lane of a converged warp (the lane that issues TMA / MMA / commit)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -85,6 +134,12 @@ __device__ __forceinline__ void tmem_ld_row32(uint32_t taddr, uint32_t (&r)[32])
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
 }
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
