@@ -104,6 +104,39 @@ __device__ __forceinline__ void umma_bf16_k64(uint32_t tmem_d, uint32_t a_lo, ui
         "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate_first), "r"(UMMA_DESC_HI)
         : "memory");
 }
+// The same for any operand layout: `a_step` / `b_step` = descriptor low-word increment per K = 16 step (2 for a K-major SW128 tile,
+// 128 for an MN-major one: two 8-row groups of 1024 B), `hi_a` / `hi_b` the operands' constant descriptor high words.
+__device__ __forceinline__ void umma_bf16_k64_ex(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_step, uint32_t b_step,
+                                                 uint32_t hi_a, uint32_t hi_b, uint32_t idesc, uint32_t accumulate_first)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b32 a1, a2, a3, b1, b2, b3;\n\t"
+        ".reg .b64 da0, db0, da1, db1, da2, db2, da3, db3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.b32 q, %5, %5;\n\t"
+        "add.u32 a1, %1, %7;\n\t"
+        "add.u32 b1, %2, %8;\n\t"
+        "add.u32 a2, a1, %7;\n\t"
+        "add.u32 b2, b1, %8;\n\t"
+        "add.u32 a3, a2, %7;\n\t"
+        "add.u32 b3, b2, %8;\n\t"
+        "mov.b64 da0, {%1, %5};\n\t"
+        "mov.b64 db0, {%2, %6};\n\t"
+        "mov.b64 da1, {a1, %5};\n\t"
+        "mov.b64 db1, {b1, %6};\n\t"
+        "mov.b64 da2, {a2, %5};\n\t"
+        "mov.b64 db2, {b2, %6};\n\t"
+        "mov.b64 da3, {a3, %5};\n\t"
+        "mov.b64 db3, {b3, %6};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db0, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da1, db1, %3, q;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da2, db2, %3, q;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da3, db3, %3, q;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate_first), "r"(hi_a), "r"(hi_b), "r"(a_step), "r"(b_step)
+        : "memory");
+}
 // true in exactly one lane of a converged warp (the lane that issues TMA / MMA / commit)
 __device__ __forceinline__ bool elect_one()
 {

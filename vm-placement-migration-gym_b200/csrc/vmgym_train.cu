@@ -151,28 +151,37 @@ __global__ void __launch_bounds__(T_THREADS, 1) tc_gemm_kernel(const __grid_cons
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            const uint32_t idesc = umma_idesc(T_BM, bn, g.a_mn, g.b_mn);
-            const uint32_t idesc_rows = umma_idesc(T_BM, 16, g.a_mn, 0);
-            const uint64_t desc_ones = umma_desc_sw128(smem_u32(s_ones));   // all elements equal: any K-major view of it is "ones"
-            for (int kb = 0; kb < k_blocks; kb++) {
-                const int s = kb % T_STAGES;
-                mbar_wait(&full_bar[s], ((uint32_t)(kb / T_STAGES)) & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem_u32(smem + (size_t)s * T_STAGE_BYTES);
-                const uint32_t sb = sa + T_A_BYTES;
-#pragma unroll
-                for (int k = 0; k < T_BK / UMMA_K; k++) {
-                    // one K = 16 step: 32 B inside the swizzle row of a K-major tile, two 8-row groups (2048 B) of an MN-major tile
-                    const uint64_t da = g.a_mn ? umma_desc_mn_sw128(sa + k * 2048) : umma_desc_sw128(sa + k * UMMA_K * 2);
-                    const uint64_t db = g.b_mn ? umma_desc_mn_sw128(sb + k * 2048) : umma_desc_sw128(sb + k * UMMA_K * 2);
-                    umma_bf16(tmem_base, da, db, idesc, (kb | k) ? 1u : 0u);
-                    if (do_rows) umma_bf16(tmem_base + T_BN, da, desc_ones, idesc_rows, (kb | k) ? 1u : 0u);
-                }
+        // ===== MMA issuer: the whole warp walks the K loop (uniform control flow), one elected lane issues each K block as one
+        // instruction group (vmgym_tc.cuh umma_bf16_k64_ex).  All 512 TMEM columns are this CTA's: the accumulator starts at column 0.
+        if (tmem_base != 0u) __trap();
+        const uint32_t idesc = umma_idesc(T_BM, bn, g.a_mn, g.b_mn);
+        const uint32_t idesc_rows = umma_idesc(T_BM, 16, g.a_mn, 0);
+        const uint32_t ones_lo = umma_desc_lo(smem_u32(s_ones));            // all elements equal: any K-major view of it is "ones"
+        // descriptor words: K-major = umma_desc_sw128 (LBO 16 B, K step 32 B), MN-major = umma_desc_mn_sw128 (LBO 8192 B, K step 2048 B)
+        const uint32_t hi = UMMA_DESC_HI;
+        const uint32_t lbo_a = g.a_mn ? (uint32_t)(8192 >> 4) << 16 : 1u << 16, lbo_b = g.b_mn ? (uint32_t)(8192 >> 4) << 16 : 1u << 16;
+        const uint32_t step_a = g.a_mn ? 2048u >> 4 : (UMMA_K * 2) >> 4, step_b = g.b_mn ? 2048u >> 4 : (UMMA_K * 2) >> 4;
+        const uint32_t ring_lo = (smem_u32(smem) >> 4) & 0x3FFFu;
+        uint32_t s = 0, phase = 0;
+#pragma unroll 1
+        for (int kb = 0; kb < k_blocks; kb++) {
+            mbar_wait(&full_bar[s], phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint32_t a_lo = ring_lo + s * (uint32_t)(T_STAGE_BYTES >> 4);
+                const uint32_t b_lo = a_lo + (T_A_BYTES >> 4);
+                umma_bf16_k64_ex(0u, a_lo | lbo_a, b_lo | lbo_b, step_a, step_b, hi, hi, idesc, kb ? 1u : 0u);
+                // row sums: the same A blocks against the tile of ones (K-major, every K step reads the same 16 x 16 ones)
+                if (do_rows) umma_bf16_k64_ex(T_BN, a_lo | lbo_a, ones_lo, step_a, 0u, hi, hi, idesc_rows, kb ? 1u : 0u);
                 umma_commit(&empty_bar[s]);
+                if (kb == k_blocks - 1) umma_commit(tmem_full_bar);
             }
-            umma_commit(tmem_full_bar);                                 // (also with an empty K slice: releases the epilogue)
+            __syncwarp();
+            if (++s == (uint32_t)T_STAGES) { s = 0; phase ^= 1u; }
+        }
+        if (k_blocks == 0) {                                                // an empty K slice of a split launch: release the epilogue
+            if (elect_one()) umma_commit(tmem_full_bar);
+            __syncwarp();
         }
     } else {
         // ===== epilogue: warps 2..9; a warp may touch TMEM lanes 32 (warp % 4) .. +31 = 32 rows of the tile (thread = row); the two
