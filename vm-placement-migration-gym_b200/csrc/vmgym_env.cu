@@ -278,7 +278,7 @@ int vmgym_set_tuning(int warps_per_cta, int use_bulk_copy)
 {
     if (warps_per_cta < 0 || warps_per_cta > 28) return fail(VMGYM_EINVAL, "warps_per_cta must be 0..28");
     g_warps_per_cta = warps_per_cta;
-    g_use_bulk = use_bulk_copy & 63;
+    g_use_bulk = use_bulk_copy & 127;     // bit 6: no L2 prefetch of the rotation's next record (A/B runs)
     return VMGYM_OK;
 }
 
