@@ -252,15 +252,18 @@ __device__ __forceinline__ void fused_chunk(const FusedOut& fo, const float* s_b
             const float x0 = z[4 * t] - m, x1 = z[4 * t + 1] - m, x2 = z[4 * t + 2] - m, x3 = z[4 * t + 3] - m;
             const float e0 = vmgym::fast_exp(x0), e1 = vmgym::fast_exp(x1), e2 = vmgym::fast_exp(x2), e3 = vmgym::fast_exp(x3);
             g[t] = (e0 + e1) + (e2 + e3);
-            t0 += e0 * x0; t1 += e1 * x1; t2 += e2 * x2; t3 += e3 * x3;
+            t0 = __fmaf_rn(e0, x0, t0); t1 = __fmaf_rn(e1, x1, t1); t2 = __fmaf_rn(e2, x2, t2); t3 = __fmaf_rn(e3, x3, t3);
         }
     }
     const float w = ((g[0] + g[1]) + (g[2] + g[3])) + ((g[4] + g[5]) + (g[6] + g[7]));
     const float ssum_new = ssum + w;
     tsum += (t0 + t1) + (t2 + t3);
     if (fo.action_in) {
+        // one-hot word of the stored action inside this chunk: moved to predicates 7 bits at a time (R2P), the select costs one
+        // instruction per column instead of a compare + select
+        const uint32_t hot = (unsigned)(act_given - c0) < 32u ? 1u << (act_given - c0) : 0u;
 #pragma unroll
-        for (int j = 0; j < 32; j++) if (c0 + j == act_given) st.z_given = z[j];
+        for (int j = 0; j < 32; j++) if ((hot >> j) & 1u) st.z_given = z[j];
     } else {
         // streaming inverse-CDF (vmgym_sample.cuh): this chunk replaces the choice iff u * S < w; the column is where the
         // cumulative sum passes u * S — first over the groups, then inside the group.  Branch-free.
