@@ -29,7 +29,8 @@ for _ in range(steps):
     v.agent_step(agent, 1, want_obs=True, want_action=False, want_valid=False)
 lib.vmgym_debug_prof(buf)
 names = ["record load wait", "setup", "agent act", "env step (total)", "outputs / obs", "write-back", "  apply", "  arrival draw", "  departures",
-         "  clamp + admissions", "  reward + counters"]
+         "  clamp + admissions", "  reward + counters", "  act: team scans", "  act: NUMBER of chunk visits", "  act: fit-table builds", "  act: candidate filter",
+         "  act: chunk visits (incl. scans)"]
 tot = sum(buf[i] for i in (0, 1, 2, 3, 4, 5))
 n_rep = (E * steps) if name == "s1000" else (E * steps) / int(os.environ.get("PROF_WARPS_PER_CTA", "4"))   # thread 0 of each CTA reports
 for i, n in enumerate(names):

@@ -25,9 +25,19 @@ __device__ unsigned long long g_prof[16];
         if ((threadIdx.x & 31) == 0 && threadIdx.x < 32) atomicAdd(&g_prof[i], (unsigned long long)(_n - _pt)); \
         _pt = _n;                                                                                             \
     } while (0)
+#define PROF_SPAN_BEGIN() const long long _ps = clock64()
+#define PROF_SPAN_END(i, cnt)                                                                                 \
+    do {                                                                                                      \
+        if ((threadIdx.x & 31) == 0 && threadIdx.x < 32) {                                                    \
+            atomicAdd(&g_prof[i], (unsigned long long)(clock64() - _ps));                                     \
+            if ((cnt) >= 0) atomicAdd(&g_prof[cnt], 1ull);                                                    \
+        }                                                                                                     \
+    } while (0)
 #else
 #define PROF_T0() do { } while (0)
 #define PROF_ADD(i) do { } while (0)
+#define PROF_SPAN_BEGIN() do { } while (0)
+#define PROF_SPAN_END(i, cnt) do { } while (0)
 #endif
 
 struct StepParams {
@@ -447,7 +457,12 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
         for (int c = lane; c < (V + 31) / 32; c += 32) e.prop()[c] = 0u;
     }
     const bool team_fit = TM && (e.tune & 8) == 0;       // the team builds the fit table (use_bulk bit 3: main warp alone, for A/B runs)
-    unsigned kmax = team_fit ? rebuild_fit_table_team(e, nth) : rebuild_fit_table(e);
+    unsigned kmax;
+    {
+        PROF_SPAN_BEGIN();
+        kmax = team_fit ? rebuild_fit_table_team(e, nth) : rebuild_fit_table(e);
+        PROF_SPAN_END(13, -1);
+    }
     bool dirty = false;                                  // proposals since the table was built (it over-states the free capacity)
 
     // slots are visited in groups: 4 per lane (128 per pass) for byte placements, 1 per lane otherwise
@@ -478,7 +493,11 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
                 int found = -1;
                 if (TM && tiebreak != VMGYM_TIE_NUMPY_INTROSORT) {
                     // team mode: all warps scan (the numpy-introsort tie rule stays on the main warp, below)
-                    found = team_scan(e, agent, c32, m32, nth);
+                    {
+                        PROF_SPAN_BEGIN();
+                        found = team_scan(e, agent, c32, m32, nth);
+                        PROF_SPAN_END(11, -1);
+                    }
                     if (found >= 0 && lane == 0) {
                         const float nc = cpu32[found] + c32;
                         cpu32[found] = nc;                              // firstfit.py:36 / bestfit.py:37-38
@@ -555,7 +574,9 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
                     // candidates — the PM scan itself is exact) and is only rebuilt once a scan comes back empty-handed
                     dirty = true;
                 } else if (dirty) {
+                    PROF_SPAN_BEGIN();
                     kmax = team_fit ? rebuild_fit_table_team(e, nth) : rebuild_fit_table(e);
+                    PROF_SPAN_END(13, -1);
                     dirty = false;
                     placed_any = true;                 // the not-yet-visited lanes' candidates are re-tested against the fresh table
                     if (bits) {
@@ -586,7 +607,11 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
     if constexpr (TM && SPL == 1) {
         // the team marks the 32-slot chunks that hold a candidate; the main warp visits only those, in slot order, and
         // re-tests their slots against the current capacities (visit() evaluates the chunk afresh)
-        team_run(e, TEAM_FILTER, nth);
+        {
+            PROF_SPAN_BEGIN();
+            team_run(e, TEAM_FILTER, nth);
+            PROF_SPAN_END(14, -1);
+        }
         const unsigned* cm = e.cmask();
         const int n_chunks = (V + 31) / 32;
         for (int cb0 = 0; cb0 < n_chunks; cb0 += 32) {
@@ -594,7 +619,9 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
             while (nz) {
                 const int c = cb0 + __ffs(nz) - 1;
                 nz &= nz - 1;
+                PROF_SPAN_BEGIN();
                 visit(32 * c);
+                PROF_SPAN_END(15, 12);
             }
         }
     } else {
