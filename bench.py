@@ -233,11 +233,13 @@ def gpu_arm(args):
     # inside the timed region.  HostVecEnv splits the E envs into groups on separate streams so that one group's
     # device->host copies overlap another group's host->device copies (PCIe is full duplex). ----
     from vmgym.host_vec import HostVecEnv
-    Ke = max(3, min(K, 20))
+    Ke = max(3, min(K, 100))
     hv = HostVecEnv(Config(**cfg), E, groups=args.e2e_groups, device=dev, rng="philox", agent="bestfit",
                     seeds=cfg["seed"] + 3 * 10**6 + rank * E + np.arange(E, dtype=np.int64))
-    hv.fast_forward(WARM_STEPS)
-    hv.run_pipelined(3)
+    # like the batches of the main metric, the groups are warmed to different phases of the service period (departure waves)
+    e2e_warm = [WARM_STEPS + (gi * PERIOD) // len(hv.groups) for gi in range(len(hv.groups))]
+    hv.fast_forward(e2e_warm)
+    hv.run_pipelined(max(3, 10 * W))        # untimed warm-up: graph capture + upload, clocks; the first dozens of steps of a fresh loop run slow
     barrier()
     t0 = time.perf_counter()
     hv.run_pipelined(Ke)
@@ -255,8 +257,8 @@ def gpu_arm(args):
     # 4096 envs) — what a caller pays when it hands act() observations of its own instead of the env's buffer
     hv1 = HostVecEnv(Config(**cfg), E, groups=args.e2e_groups, device=dev, rng="philox", agent="bestfit", resident_obs=False,
                      seeds=cfg["seed"] + 3 * 10**6 + rank * E + np.arange(E, dtype=np.int64))
-    hv1.fast_forward(WARM_STEPS)
-    hv1.run_pipelined(3)
+    hv1.fast_forward(e2e_warm)
+    hv1.run_pipelined(max(3, 10 * W))
     barrier()
     t0 = time.perf_counter()
     hv1.run_pipelined(Ke)
@@ -438,7 +440,9 @@ def gpu_arm(args):
                         "kernel) and the step kernel stores reward, done and the CHANGED observation entries to the host buffers "
                         "(d2h_bytes_per_step = actions + measured changed entries + reward/done). The host observation buffer is a mirror "
                         "the env keeps current, so act() on it reads the identical device copy instead of re-uploading 4(3V+2P) bytes per "
-                        "env; obs_reupload_value = the round-1 loop that re-uploads it every step (what act(obs) costs for a caller's own array)"},
+                        "env; obs_reupload_value = the round-1 loop that re-uploads it every step (what act(obs) costs for a caller's own "
+                        "array). The env groups are warmed to different phases of the service period, like the batches of the main metric; "
+                        "%d untimed steps of the same loop precede the %d timed ones" % (max(3, 10 * W), Ke)},
         "per_launch": {"value": world * E / (per_launch_ms * 1e-3), "unit": UNIT, "ms_per_step": per_launch_ms,
                        "note": "round-1 protocol: the same rotation as K separate launches of the fused step kernel in one CUDA graph "
                                "(programmatic dependent launch), median of 10 replays",

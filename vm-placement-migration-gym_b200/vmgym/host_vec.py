@@ -75,7 +75,12 @@ class HostVecEnv:
             g.g_act = g.g_step = None
             g.x_act = g.x_step = None
             g.stream_h = None
-            g.ev_act, g.ev_step = torch.cuda.Event(), torch.cuda.Event()
+            try:        # external events: a record captured into a graph becomes an event-record node the host can query / wait on
+                g.ev_act, g.ev_step = torch.cuda.Event(external=True), torch.cuda.Event(external=True)
+                self._ev_in_graph = True
+            except TypeError:
+                g.ev_act, g.ev_step = torch.cuda.Event(), torch.cuda.Event()
+                self._ev_in_graph = False
             self.groups.append(g)
         self._cudart = _driver_api()
         v0 = self.groups[0].vec
@@ -140,7 +145,7 @@ class HostVecEnv:
             self.reward[g.lo:g.hi].copy_(rew, non_blocking=True)
             self.terminated[g.lo:g.hi].copy_(g.vec.terminated_u8, non_blocking=True)
 
-    def _graph(self, g: _Group, chain):
+    def _graph(self, g: _Group, chain, ev):
         with torch.cuda.device(self.device):
             with torch.cuda.stream(g.stream):
                 chain(g)                                                   # allocations / plan caches before capture
@@ -148,6 +153,8 @@ class HostVecEnv:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=g.stream):
                 chain(g)
+                if self._ev_in_graph:
+                    ev.record(g.stream)                                    # the phase's completion event is the graph's last node
         return graph
 
     def _run(self, g: _Group, which: str):
@@ -155,7 +162,8 @@ class HostVecEnv:
         x = g.x_act if which == "act" else g.x_step
         if x is not None:
             self._cudart.cudaGraphLaunch(x, g.stream_h)
-            (g.ev_act if which == "act" else g.ev_step).record(g.stream)
+            if not self._ev_in_graph:
+                (g.ev_act if which == "act" else g.ev_step).record(g.stream)
             return
         chain = self._act_chain if which == "act" else self._step_chain
         with torch.cuda.device(self.device), torch.cuda.stream(g.stream):
@@ -164,7 +172,7 @@ class HostVecEnv:
                 if graph is None:
                     # capturing replays nothing: run the chain once for real afterwards
                     state = g.vec.state.clone() if which == "step" else None
-                    graph = self._graph(g, chain)
+                    graph = self._graph(g, chain, g.ev_act if which == "act" else g.ev_step)
                     if state is not None:
                         g.vec.state.copy_(state)                           # undo the warm-up step taken before capture
                     if which == "act":
@@ -253,19 +261,33 @@ class HostVecEnv:
             self.step_wait(gi)
         return self.obs, self.reward, self.terminated
 
-    def run_pipelined(self, n_steps: int):
-        """n_steps of act + step for every env with the groups free-running: whenever a group's current phase has
-        completed (its event is done, i.e. the host has the action / the observation), its next phase is enqueued.
-        Groups drift apart by themselves, so host->device copies of some overlap device->host copies of others.
-        Per env the sequence of calls is exactly the plain loop's; returns (obs, reward, terminated) after the last step."""
+    def run_pipelined(self, n_steps: int, poll: bool = True):
+        """n_steps of act + step for every env with the groups overlapped: as soon as the host has group g's actions it hands them
+        to env.step and moves on to group g + 1, so one group's device->host traffic and kernels run while another group's
+        host->device copy is in flight.  Per env the sequence of calls is exactly the plain loop's; returns (obs, reward, terminated)
+        after the last step.  Default (`poll=True`): the free-running scheduler — every group advances as soon as ITS event has fired,
+        whatever the order (the host polls the events); `poll=False`: groups are served round-robin with a blocking wait on the
+        group's event (no spinning host thread; measured 91-95 vs 85-99 us per 4096-env step with 4 groups)."""
         G = len(self.groups)
         if n_steps <= 0:
+            return self.obs, self.reward, self.terminated
+        if not poll:
+            for gi in range(G):
+                self.act_async(gi)
+            for k in range(n_steps):
+                for gi in range(G):
+                    self.act_wait(gi)              # the host has the action: hand it to env.step
+                    self.step_async(gi)
+                for gi in range(G):
+                    self.step_wait(gi)             # the host has obs / reward / done: next act
+                    if k + 1 < n_steps:
+                        self.act_async(gi)
             return self.obs, self.reward, self.terminated
         phase = [0] * G                                 # completed phases of each group: 2 per step (act, step)
         for gi in range(G):
             self.act_async(gi)
         live = G
-        while live:                                     # polls the groups' events (cudaEventQuery), like a blocking sync would
+        while live:                                     # polls the groups' events (cudaEventQuery)
             for gi, g in enumerate(self.groups):
                 ph = phase[gi]
                 if ph >= 2 * n_steps:
@@ -281,11 +303,15 @@ class HostVecEnv:
                     self.act_async(gi)                 # the host has obs / reward / done: next act
         return self.obs, self.reward, self.terminated
 
-    def fast_forward(self, n_steps: int, agent: str = "bestfit"):
-        """Advance every env n_steps with the fused device-side agent (no host traffic), then refresh the host obs."""
-        for g in self.groups:
+    def fast_forward(self, n_steps, agent: str = "bestfit"):
+        """Advance every env n_steps (an int, or one count per group) with the fused device-side agent (no host traffic), then
+        refresh the host obs."""
+        counts = [int(n_steps)] * len(self.groups) if np.isscalar(n_steps) else [int(n) for n in n_steps]
+        if len(counts) != len(self.groups):
+            raise ValueError("fast_forward: one step count per group")
+        for g, n in zip(self.groups, counts):
             with torch.cuda.device(self.device), torch.cuda.stream(g.stream):
-                obs, _, _ = g.vec.agent_step(agent, n_steps, want_obs=True, want_action=False, want_valid=False)
+                obs, _, _ = g.vec.agent_step(agent, n, want_obs=True, want_action=False, want_valid=False)
                 self.obs[g.lo:g.hi].copy_(obs, non_blocking=True)
                 g.ev_step.record(g.stream)
         for g in self.groups:
