@@ -562,11 +562,12 @@ def test_host_vec_env_pipelined_equals_fused_device_rollout(use_graphs, zero_cop
     obs0 = hv.reset().clone()
     ref = VecVmEnv(cfg, N, rng="philox")
     assert torch.equal(obs0, ref.observe().cpu())
-    # plain loop for 25 steps, pipelined for 35
+    # plain loop for 25 steps, pipelined for 35 (free-running scheduler, then blocking round-robin)
     for _ in range(25):
         hv.act()
         hv.step()
-    obs, rew, term = hv.run_pipelined(35)
+    hv.run_pipelined(20)
+    obs, rew, term = hv.run_pipelined(15, poll=False)
     robs, rrew, rterm = ref.agent_step("bestfit", 60, want_obs=True)
     torch.cuda.synchronize()
     assert torch.equal(obs, robs.cpu())
@@ -589,6 +590,16 @@ def test_host_vec_env_pipelined_equals_fused_device_rollout(use_graphs, zero_cop
     o2, _, _ = hv.step(act)
     ref.step(ref.vm_placement.clone())
     assert torch.equal(o2, ref.observe().cpu())
+    # fast_forward with one step count per group (the benchmark's phase staggering) == the same counts on env slices
+    hv.fast_forward([3, 0, 5])
+    for gi, n in enumerate([3, 0, 5]):
+        g = hv.groups[gi]
+        if n:
+            ref.agent_step("bestfit", n, want_obs=True, envs=(g.lo, g.hi))
+    torch.cuda.synchronize()
+    assert torch.equal(hv.obs, ref.observe().cpu())
+    with pytest.raises(ValueError):
+        hv.fast_forward([1, 2])
 
 
 # ---- the reference's sweep drivers as one batch per agent (vmgym.sweep) --------------------------------------------

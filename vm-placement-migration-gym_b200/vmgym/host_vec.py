@@ -311,6 +311,9 @@ class HostVecEnv:
             raise ValueError("fast_forward: one step count per group")
         for g, n in zip(self.groups, counts):
             with torch.cuda.device(self.device), torch.cuda.stream(g.stream):
+                if n <= 0:                             # nothing to do for this group
+                    g.ev_step.record(g.stream)
+                    continue
                 obs, _, _ = g.vec.agent_step(agent, n, want_obs=True, want_action=False, want_valid=False)
                 self.obs[g.lo:g.hi].copy_(obs, non_blocking=True)
                 g.ev_step.record(g.stream)
