@@ -441,7 +441,9 @@ def gpu_arm(args):
                         "(d2h_bytes_per_step = actions + measured changed entries + reward/done). The host observation buffer is a mirror "
                         "the env keeps current, so act() on it reads the identical device copy instead of re-uploading 4(3V+2P) bytes per "
                         "env; obs_reupload_value = the round-1 loop that re-uploads it every step (what act(obs) costs for a caller's own "
-                        "array). The env groups are warmed to different phases of the service period, like the batches of the main metric; "
+                        "array). The step enqueue ends with the agent's act() on the observation it just produced (eager_act: one graph "
+                        "launch and one host round trip per step; act() then only waits for the actions, which still travel device -> host "
+                        "-> device and may be replaced by the caller before step()). The env groups are warmed to different phases of the service period, like the batches of the main metric; "
                         "%d untimed steps of the same loop precede the %d timed ones" % (max(3, 10 * W), Ke)},
         "per_launch": {"value": world * E / (per_launch_ms * 1e-3), "unit": UNIT, "ms_per_step": per_launch_ms,
                        "note": "round-1 protocol: the same rotation as K separate launches of the fused step kernel in one CUDA graph "

@@ -35,7 +35,7 @@ from .vec_env import VecVmEnv
 
 class _Group:
     __slots__ = ("lo", "hi", "vec", "agent", "stream", "d_obs_in", "d_act_in", "g_act", "g_step", "ev_act", "ev_step", "x_act", "x_step",
-                 "stream_h")
+                 "stream_h", "eager_ready")
 
 
 def _driver_api():
@@ -51,7 +51,7 @@ def _driver_api():
 class HostVecEnv:
     def __init__(self, config: Config, num_envs: int, groups: int = 4, device="cuda", rng: str = "philox", seeds=None,
                  agent: str | None = "bestfit", tiebreak: str | None = None, use_graphs: bool = True, zero_copy: bool = True,
-                 delta_obs: bool = True, resident_obs: bool = True, action_dma: bool = True, **vec_kwargs):
+                 delta_obs: bool = True, resident_obs: bool = True, action_dma: bool = True, eager_act: bool = True, **vec_kwargs):
         if num_envs < 1 or groups < 1:
             raise ValueError("num_envs and groups must be positive")
         groups = min(groups, num_envs)
@@ -75,6 +75,7 @@ class HostVecEnv:
             g.g_act = g.g_step = None
             g.x_act = g.x_step = None
             g.stream_h = None
+            g.eager_ready = False
             try:        # external events: a record captured into a graph becomes an event-record node the host can query / wait on
                 g.ev_act, g.ev_step = torch.cuda.Event(external=True), torch.cuda.Event(external=True)
                 self._ev_in_graph = True
@@ -101,6 +102,12 @@ class HostVecEnv:
         # construction; an observation array passed in by the caller (`act(obs)`) is always uploaded
         self.resident_obs = bool(resident_obs)
         self.action_dma = bool(action_dma)      # resident mode: action rows by copy engine (True) or by the kernels' own PCIe stores / loads
+        # eager_act: the step phase ends with the agent's act() on the observation it has just produced (same stream, same graph), so
+        # the host gets obs / reward / done at `ev_step` and the NEXT actions at `ev_act` from ONE enqueue; act() then only waits.
+        # One host round trip and one graph launch per step instead of two.  What act() returns is unchanged (the agent, the
+        # observation and the kernels are the same), the actions still travel device -> host -> device, and the host may still replace
+        # them before step().  Needs the env's own observations (resident_obs), the built-in agent and events recorded inside graphs.
+        self.eager_act = bool(eager_act) and self.resident_obs and agent is not None and self._ev_in_graph and self.zero_copy and self.delta_obs
         self.h2d_bytes_per_step = (0 if self.resident_obs else N * self.obs_dim * 4) + N * self.V * self.action.element_size()
         self.d2h_bytes_per_step = N * self.V * self.action.element_size() + N * self.obs_dim * 4 + N * 8 + N
         torch.cuda.synchronize(self.device)          # construction-time resets ran on the caller's stream
@@ -145,6 +152,11 @@ class HostVecEnv:
             self.reward[g.lo:g.hi].copy_(rew, non_blocking=True)
             self.terminated[g.lo:g.hi].copy_(g.vec.terminated_u8, non_blocking=True)
 
+    def _step_act_chain(self, g: _Group):
+        self._step_chain(g)
+        g.ev_step.record(g.stream)             # obs / reward / done are on the host (inside a capture: an event-record node)
+        self._act_chain(g)
+
     def _graph(self, g: _Group, chain, ev):
         with torch.cuda.device(self.device):
             with torch.cuda.stream(g.stream):
@@ -165,14 +177,15 @@ class HostVecEnv:
             if not self._ev_in_graph:
                 (g.ev_act if which == "act" else g.ev_step).record(g.stream)
             return
-        chain = self._act_chain if which == "act" else self._step_chain
+        eager = which == "step" and self.eager_act
+        chain = self._act_chain if which == "act" else (self._step_act_chain if eager else self._step_chain)
         with torch.cuda.device(self.device), torch.cuda.stream(g.stream):
             if self.use_graphs:
                 graph = g.g_act if which == "act" else g.g_step
                 if graph is None:
                     # capturing replays nothing: run the chain once for real afterwards
                     state = g.vec.state.clone() if which == "step" else None
-                    graph = self._graph(g, chain, g.ev_act if which == "act" else g.ev_step)
+                    graph = self._graph(g, chain, g.ev_act if (which == "act" or eager) else g.ev_step)
                     if state is not None:
                         g.vec.state.copy_(state)                           # undo the warm-up step taken before capture
                     if which == "act":
@@ -191,15 +204,21 @@ class HostVecEnv:
                         except Exception:       # noqa: BLE001 — keep the torch replay path
                             pass
                 graph.replay()
+                if not self._ev_in_graph:
+                    (g.ev_act if which == "act" else g.ev_step).record(g.stream)
             else:
                 chain(g)
-            (g.ev_act if which == "act" else g.ev_step).record(g.stream)
+                (g.ev_act if (which == "act" or eager) else g.ev_step).record(g.stream)
 
     # ---- split-phase API ------------------------------------------------------------------------------------
     def act_async(self, gi: int):
-        if self.groups[gi].agent is None:
+        g = self.groups[gi]
+        if g.agent is None:
             raise RuntimeError("HostVecEnv was built without an agent")
-        self._run(self.groups[gi], "act")
+        if g.eager_ready:                       # the last step's enqueue already contains this act (eager_act)
+            g.eager_ready = False
+            return
+        self._run(g, "act")
 
     def act_wait(self, gi: int):
         g = self.groups[gi]
@@ -207,7 +226,9 @@ class HostVecEnv:
         return self.action[g.lo:g.hi]
 
     def step_async(self, gi: int):
-        self._run(self.groups[gi], "step")
+        g = self.groups[gi]
+        self._run(g, "step")
+        g.eager_ready = self.eager_act
 
     def step_wait(self, gi: int):
         g = self.groups[gi]
@@ -228,6 +249,7 @@ class HostVecEnv:
                 obs, _ = g.vec.reset(seed=s)
                 self.obs[g.lo:g.hi].copy_(obs, non_blocking=True)
                 g.ev_step.record(g.stream)
+                g.eager_ready = False
         for g in self.groups:
             g.ev_step.synchronize()
         return self.obs
@@ -310,6 +332,7 @@ class HostVecEnv:
         if len(counts) != len(self.groups):
             raise ValueError("fast_forward: one step count per group")
         for g, n in zip(self.groups, counts):
+            g.eager_ready = g.eager_ready and n <= 0
             with torch.cuda.device(self.device), torch.cuda.stream(g.stream):
                 if n <= 0:                             # nothing to do for this group
                     g.ev_step.record(g.stream)
