@@ -16,8 +16,8 @@ def timed(fn):
     return (time.perf_counter() - t0) / S * 1e6
 
 
-for resident, dma in ((True, True), (False, True)):
-    for groups in (1, 2, 4, 8):
+for resident, dma in ((True, True), (True, "d2h"), (True, "h2d"), (False, True)):
+    for groups in (2, 4):
         hv = HostVecEnv(Config(**cfg), E, groups=groups, rng="philox", agent="bestfit", resident_obs=resident, action_dma=dma)
         hv.fast_forward(WARM_STEPS); hv.run_pipelined(300); hv.run_pipelined(300, poll=True)
 
@@ -28,6 +28,6 @@ for resident, dma in ((True, True), (False, True)):
         for _ in range(2):
             r.append((timed(lambda: hv.run_pipelined(S)), timed(lambda: hv.run_pipelined(S, poll=True)), timed(plain)))
         best = [min(x[i] for x in r) for i in range(3)]
-        print(f"resident={resident} groups={groups}: blocking round-robin {r[0][0]:6.1f} / {r[1][0]:6.1f}  polling {r[0][1]:6.1f} / {r[1][1]:6.1f}  "
+        print(f"resident={resident} dma={dma} groups={groups}: blocking round-robin {r[0][0]:6.1f} / {r[1][0]:6.1f}  polling {r[0][1]:6.1f} / {r[1][1]:6.1f}  "
               f"plain loop {r[0][2]:6.1f} / {r[1][2]:6.1f} us per step -> best {E / min(best):.2f} M env-steps/s")
         hv.close(); del hv

@@ -101,7 +101,11 @@ class HostVecEnv:
         # pinned buffer is a mirror the env itself keeps current (callers treat it as read-only), so the two are identical by
         # construction; an observation array passed in by the caller (`act(obs)`) is always uploaded
         self.resident_obs = bool(resident_obs)
-        self.action_dma = bool(action_dma)      # resident mode: action rows by copy engine (True) or by the kernels' own PCIe stores / loads
+        # resident mode: action rows by copy engine (True), by the kernels' own PCIe stores / loads (False), or one direction each
+        # ("d2h": agent -> host by DMA, host -> step kernel by the kernel's loads; "h2d": the reverse)
+        self.action_dma = action_dma if action_dma in ("d2h", "h2d") else bool(action_dma)
+        self._dma_out = self.action_dma in (True, "d2h")
+        self._dma_in = self.action_dma in (True, "h2d")
         # eager_act: the step phase ends with the agent's act() on the observation it has just produced (same stream, same graph), so
         # the host gets obs / reward / done at `ev_step` and the NEXT actions at `ev_act` from ONE enqueue; act() then only waits.
         # One host round trip and one graph launch per step instead of two.  What act() returns is unchanged (the agent, the
@@ -123,7 +127,7 @@ class HostVecEnv:
         else:
             g.d_obs_in.copy_(self.obs[g.lo:g.hi], non_blocking=True)      # host obs -> device (copy engine)
             d_obs = g.d_obs_in
-        if self.zero_copy and not (self.resident_obs and self.action_dma):
+        if self.zero_copy and not (self.resident_obs and self._dma_out):
             g.agent.act(d_obs, out=self.action[g.lo:g.hi])                 # vmgym_agent_act stores actions to host memory
         else:
             # no observation traffic competes for the copy engines: the action rows leave by DMA (one large transfer instead of
@@ -136,7 +140,7 @@ class HostVecEnv:
             # vmgym_step stores reward / done and the CHANGED observation entries to host memory; the actions come from host memory
             # directly (32-byte PCIe reads from the kernel) or, with resident observations (idle copy engines), by one DMA transfer
             act_src = self.action[g.lo:g.hi]
-            if self.resident_obs and self.action_dma:
+            if self.resident_obs and self._dma_in:
                 g.d_act_in.copy_(act_src, non_blocking=True)
                 act_src = g.d_act_in
             g.vec.step(act_src, want_valid=False, obs_mirror=self.obs[g.lo:g.hi],
