@@ -443,7 +443,8 @@ def gpu_arm(args):
                         "env; obs_reupload_value = the round-1 loop that re-uploads it every step (what act(obs) costs for a caller's own "
                         "array). The step enqueue ends with the agent's act() on the observation it just produced (eager_act: one graph "
                         "launch and one host round trip per step; act() then only waits for the actions, which still travel device -> host "
-                        "-> device and may be replaced by the caller before step()). The env groups are warmed to different phases of the service period, like the batches of the main metric; "
+                        "-> device and may be replaced by the caller before step(); the host observation mirror is brought up to date by a kernel "
+                        "on a side stream, vmgym_obs_mirror_update, off the path to the next actions). The env groups are warmed to different phases of the service period, like the batches of the main metric; "
                         "%d untimed steps of the same loop precede the %d timed ones" % (max(3, 10 * W), Ke)},
         "per_launch": {"value": world * E / (per_launch_ms * 1e-3), "unit": UNIT, "ms_per_step": per_launch_ms,
                        "note": "round-1 protocol: the same rotation as K separate launches of the fused step kernel in one CUDA graph "

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define VMGYM_ABI_VERSION 8
+#define VMGYM_ABI_VERSION 9
 
 enum vmgym_status {
     VMGYM_OK = 0,
@@ -199,6 +199,14 @@ int vmgym_agent_act(const vmgym_config* cfg, int agent, int tiebreak, const floa
 
 /* VmEnv._get_obs (env.py:295-296). */
 int vmgym_observe(const vmgym_config* cfg, const void* d_state, int64_t n_envs, float* d_obs, void* stream);
+
+/* Host-resident observations (the caller of env.step of the reference holds numpy arrays, src/agents/base.py:71-86): keeps a mapped
+ * pinned HOST copy `h_obs` of the device observation buffer `d_obs` current by storing only the entries whose bits differ from the
+ * device-side shadow `d_shadow` (which is updated alongside); also forwards the step's reward [n_envs] f64 and done flags [n_envs] u8
+ * to host buffers when those are given.  `n_floats` = n_envs * obs_dim, a multiple of 4; all three observation buffers 16-byte
+ * aligned.  Runs on `stream`: HostVecEnv puts it on a side stream so that it is off the path to the next actions. */
+int vmgym_obs_mirror_update(const float* d_obs, float* d_shadow, float* h_obs, int64_t n_floats, const double* d_reward, double* h_reward,
+                            const uint8_t* d_terminated, uint8_t* h_terminated, int64_t n_envs, void* stream);
 
 /* VmEnv.get_invalid_action_mask (env.py:45-53): d_mask[n_envs, V, A], 1 = invalid. */
 int vmgym_invalid_action_mask(const vmgym_config* cfg, const void* d_state, int64_t n_envs, uint8_t* d_mask,

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/vmgym.h but not exported"
     assert sorted(nv.EXPORTS) == names
-    assert lib.vmgym_abi_version() == 8
+    assert lib.vmgym_abi_version() == 9
 
 
 @pytest.mark.parametrize("P,V,place_bytes", [(10, 30, 1), (100, 300, 1), (253, 64, 1), (254, 64, 2), (1000, 3000, 2), (3, 5, 1)])

@@ -419,6 +419,50 @@ int vmgym_observe(const vmgym_config* cfg, const void* d_state, int64_t n_envs, 
     return check_cuda(cudaGetLastError(), "observe_kernel launch");
 }
 
+// Host mirror of the observation buffer (HostVecEnv): entries whose bits differ from the shadow copy are stored to the mapped host
+// buffer and to the shadow; reward / done rows follow.  Element-wise, grid-stride, 128-bit loads.
+__global__ void obs_mirror_kernel(const float4* __restrict__ obs, float4* __restrict__ prev, float* __restrict__ host, long long n4,
+                                  const double* __restrict__ d_reward, double* __restrict__ h_reward,
+                                  const uint8_t* __restrict__ d_term, uint8_t* __restrict__ h_term, long long n_envs)
+{
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = t0; i < n4; i += stride) {
+        const float4 a = obs[i], b = prev[i];
+        const bool cx = __float_as_uint(a.x) != __float_as_uint(b.x), cy = __float_as_uint(a.y) != __float_as_uint(b.y);
+        const bool cz = __float_as_uint(a.z) != __float_as_uint(b.z), cw = __float_as_uint(a.w) != __float_as_uint(b.w);
+        if (cx | cy | cz | cw) {
+            prev[i] = a;
+            float* h = host + 4 * i;
+            if (cx) h[0] = a.x;
+            if (cy) h[1] = a.y;
+            if (cz) h[2] = a.z;
+            if (cw) h[3] = a.w;
+        }
+    }
+    for (long long e = t0; e < n_envs; e += stride) {
+        if (h_reward) h_reward[e] = d_reward[e];
+        if (h_term) h_term[e] = d_term[e];
+    }
+}
+
+int vmgym_obs_mirror_update(const float* d_obs, float* d_shadow, float* h_obs, int64_t n_floats, const double* d_reward, double* h_reward,
+                            const uint8_t* d_terminated, uint8_t* h_terminated, int64_t n_envs, void* stream)
+{
+    if (!d_obs || !d_shadow || !h_obs || n_floats < 0 || n_envs < 0 || (h_reward && !d_reward) || (h_terminated && !d_terminated))
+        return fail(VMGYM_EINVAL, "vmgym_obs_mirror_update: null operand");
+    if ((n_floats & 3) || ((uintptr_t)d_obs & 15) || ((uintptr_t)d_shadow & 15) || ((uintptr_t)h_obs & 15))
+        return fail(VMGYM_EINVAL, "vmgym_obs_mirror_update: buffers must be 16-byte aligned and a multiple of 4 floats long");
+    if (n_floats == 0 && n_envs == 0) return VMGYM_OK;
+    const int threads = 256;
+    long long blocks = (n_floats / 4 + threads - 1) / threads;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    obs_mirror_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(d_obs), reinterpret_cast<float4*>(d_shadow),
+                                                                                  h_obs, n_floats / 4, d_reward, h_reward, d_terminated, h_terminated, n_envs);
+    return check_cuda(cudaGetLastError(), "obs_mirror_kernel launch");
+}
+
 int vmgym_invalid_action_mask(const vmgym_config* cfg, const void* d_state, int64_t n_envs, uint8_t* d_mask, void* stream)
 {
     DevLayout L;

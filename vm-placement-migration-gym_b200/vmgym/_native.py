@@ -70,7 +70,7 @@ EXPORTS = ["vmgym_last_error", "vmgym_abi_version", "vmgym_get_layout", "vmgym_r
            "vmgym_agent_step", "vmgym_agent_step_rotation", "vmgym_agent_act", "vmgym_observe", "vmgym_invalid_action_mask", "vmgym_set_tuning",
            "vmgym_policy_heads", "vmgym_policy_heads_backward", "vmgym_gae", "vmgym_drlvmp_choice", "vmgym_drlvmp_iter", "vmgym_linear_bf16", "vmgym_policy_fused", "vmgym_segtree_update",
            "vmgym_segtree_retrieve", "vmgym_vmstats_finalize", "vmgym_per_sample", "vmgym_c51_project", "vmgym_adamw_step", "vmgym_tc_gemm", "vmgym_cast_pad_bf16", "vmgym_cast_split_bf16",
-           "vmgym_value_head", "vmgym_value_head_backward", "vmgym_ppo_loss", "vmgym_policy_fused_grad", "vmgym_policy_fused_eval", "vmgym_policy_fused_rows"]
+           "vmgym_value_head", "vmgym_value_head_backward", "vmgym_ppo_loss", "vmgym_policy_fused_grad", "vmgym_policy_fused_eval", "vmgym_policy_fused_rows", "vmgym_obs_mirror_update"]
 
 
 class VmgymError(RuntimeError):
@@ -132,6 +132,7 @@ def lib():
                                             C.POINTER(Outputs), vp]
     L.vmgym_agent_act.argtypes = [C.POINTER(Config), i32, i32, vp, i64, vp, i32, vp]
     L.vmgym_observe.argtypes = [C.POINTER(Config), vp, i64, vp, vp]
+    L.vmgym_obs_mirror_update.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, i64, vp]
     L.vmgym_invalid_action_mask.argtypes = [C.POINTER(Config), vp, i64, vp, vp]
     L.vmgym_per_sample.restype = i32
     L.vmgym_per_sample.argtypes = [vp, vp, i64, i64, i32, vp, C.c_double, vp, vp, vp]

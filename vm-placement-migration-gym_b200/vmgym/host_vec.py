@@ -35,7 +35,7 @@ from .vec_env import VecVmEnv
 
 class _Group:
     __slots__ = ("lo", "hi", "vec", "agent", "stream", "d_obs_in", "d_act_in", "g_act", "g_step", "ev_act", "ev_step", "x_act", "x_step",
-                 "stream_h", "eager_ready")
+                 "stream_h", "eager_ready", "side", "shadow")
 
 
 def _driver_api():
@@ -76,6 +76,8 @@ class HostVecEnv:
             g.x_act = g.x_step = None
             g.stream_h = None
             g.eager_ready = False
+            g.side = torch.cuda.Stream(device=self.device)
+            g.shadow = None
             try:        # external events: a record captured into a graph becomes an event-record node the host can query / wait on
                 g.ev_act, g.ev_step = torch.cuda.Event(external=True), torch.cuda.Event(external=True)
                 self._ev_in_graph = True
@@ -112,6 +114,14 @@ class HostVecEnv:
         # observation and the kernels are the same), the actions still travel device -> host -> device, and the host may still replace
         # them before step().  Needs the env's own observations (resident_obs), the built-in agent and events recorded inside graphs.
         self.eager_act = bool(eager_act) and self.resident_obs and agent is not None and self._ev_in_graph and self.zero_copy and self.delta_obs
+        # with eager_act the host mirror of the observations is kept current by a separate kernel on a side stream (vmgym_obs_mirror_update:
+        # compares the device observations with a device-side shadow of the host copy and stores the differences), so the scattered
+        # PCIe stores are off the path H2D actions -> step -> act -> D2H actions that decides how long a step takes
+        self.side_mirror = self.eager_act and self.obs_dim % 4 == 0           # (16-byte aligned row ranges for the 128-bit compare)
+        if self.side_mirror:
+            for g in self.groups:
+                g.shadow = g.vec.observe().clone()
+                self.obs[g.lo:g.hi].copy_(g.shadow)                    # host copy == shadow from the start
         self.h2d_bytes_per_step = (0 if self.resident_obs else N * self.obs_dim * 4) + N * self.V * self.action.element_size()
         self.d2h_bytes_per_step = N * self.V * self.action.element_size() + N * self.obs_dim * 4 + N * 8 + N
         torch.cuda.synchronize(self.device)          # construction-time resets ran on the caller's stream
@@ -157,9 +167,27 @@ class HostVecEnv:
             self.terminated[g.lo:g.hi].copy_(g.vec.terminated_u8, non_blocking=True)
 
     def _step_act_chain(self, g: _Group):
-        self._step_chain(g)
-        g.ev_step.record(g.stream)             # obs / reward / done are on the host (inside a capture: an event-record node)
-        self._act_chain(g)
+        if not self.side_mirror:
+            self._step_chain(g)
+            g.ev_step.record(g.stream)         # obs / reward / done are on the host (inside a capture: an event-record node)
+            self._act_chain(g)
+            return
+        import ctypes as C
+        from . import _native as nv
+        g.d_act_in.copy_(self.action[g.lo:g.hi], non_blocking=True)            # host actions -> device (copy engine)
+        obs, rew, term, _, _ = g.vec.step(g.d_act_in, want_valid=False)        # device outputs only
+        term_u8 = g.vec.terminated_u8
+        g.side.wait_stream(g.stream)
+        with torch.cuda.stream(g.side):
+            n = g.hi - g.lo
+            nv.check(nv.lib().vmgym_obs_mirror_update(obs.data_ptr(), g.shadow.data_ptr(), self.obs[g.lo:g.hi].data_ptr(), n * self.obs_dim,
+                                                      rew.data_ptr(), self.reward[g.lo:g.hi].data_ptr(), term_u8.data_ptr(),
+                                                      self.terminated[g.lo:g.hi].data_ptr(), n, C.c_void_p(g.side.cuda_stream)),
+                     "vmgym_obs_mirror_update")
+            g.ev_step.record(g.side)           # obs / reward / done are on the host
+        self._act_chain(g)                     # meanwhile: the agent's act on the new device observations, actions -> host
+        g.ev_act.record(g.stream)
+        g.stream.wait_stream(g.side)           # the next step must not overwrite the observations under the mirror kernel
 
     def _graph(self, g: _Group, chain, ev):
         with torch.cuda.device(self.device):
@@ -169,7 +197,7 @@ class HostVecEnv:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=g.stream):
                 chain(g)
-                if self._ev_in_graph:
+                if self._ev_in_graph and ev is not None:
                     ev.record(g.stream)                                    # the phase's completion event is the graph's last node
         return graph
 
@@ -189,7 +217,8 @@ class HostVecEnv:
                 if graph is None:
                     # capturing replays nothing: run the chain once for real afterwards
                     state = g.vec.state.clone() if which == "step" else None
-                    graph = self._graph(g, chain, g.ev_act if (which == "act" or eager) else g.ev_step)
+                    own_events = eager and self.side_mirror                # that chain records ev_step / ev_act itself
+                    graph = self._graph(g, chain, None if own_events else (g.ev_act if (which == "act" or eager) else g.ev_step))
                     if state is not None:
                         g.vec.state.copy_(state)                           # undo the warm-up step taken before capture
                     if which == "act":
@@ -212,7 +241,8 @@ class HostVecEnv:
                     (g.ev_act if which == "act" else g.ev_step).record(g.stream)
             else:
                 chain(g)
-                (g.ev_act if (which == "act" or eager) else g.ev_step).record(g.stream)
+                if not (eager and self.side_mirror):
+                    (g.ev_act if (which == "act" or eager) else g.ev_step).record(g.stream)
 
     # ---- split-phase API ------------------------------------------------------------------------------------
     def act_async(self, gi: int):
@@ -252,6 +282,8 @@ class HostVecEnv:
                 s = self._seeds0[g.lo:g.hi] if seed is None else int(seed) + np.arange(g.lo, g.hi, dtype=np.int64)
                 obs, _ = g.vec.reset(seed=s)
                 self.obs[g.lo:g.hi].copy_(obs, non_blocking=True)
+                if g.shadow is not None:
+                    g.shadow.copy_(obs)
                 g.ev_step.record(g.stream)
                 g.eager_ready = False
         for g in self.groups:
@@ -343,6 +375,8 @@ class HostVecEnv:
                     continue
                 obs, _, _ = g.vec.agent_step(agent, n, want_obs=True, want_action=False, want_valid=False)
                 self.obs[g.lo:g.hi].copy_(obs, non_blocking=True)
+                if g.shadow is not None:
+                    g.shadow.copy_(obs)
                 g.ev_step.record(g.stream)
         for g in self.groups:
             g.ev_step.synchronize()
