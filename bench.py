@@ -442,7 +442,8 @@ def gpu_arm(args):
                         "the env keeps current, so act() on it reads the identical device copy instead of re-uploading 4(3V+2P) bytes per "
                         "env; obs_reupload_value = the round-1 loop that re-uploads it every step (what act(obs) costs for a caller's own "
                         "array). The step enqueue ends with the agent's act() on the observation it just produced (eager_act: one graph "
-                        "launch and one host round trip per step; act() then only waits for the actions, which still travel device -> host "
+                        "launch and one host round trip per step, the act itself computed by the step kernel on the record it still holds, "
+                        "vmgym_outputs.d_next_action; act() then only waits for the actions, which still travel device -> host "
                         "-> device and may be replaced by the caller before step(); the host observation mirror is brought up to date by a kernel "
                         "on a side stream, vmgym_obs_mirror_update, off the path to the next actions). The env groups are warmed to different phases of the service period, like the batches of the main metric; "
                         "%d untimed steps of the same loop precede the %d timed ones" % (max(3, 10 * W), Ke)},

@@ -143,6 +143,13 @@ typedef struct vmgym_outputs {
      * carry the "changed since last stored" bit; vmgym_reset with a d_obs counts as a store.  0: every call stores. */
     int32_t obs_persistent;
     int32_t reserved0;
+    /* vmgym_step only: after the step, the heuristic agent's act() on the NEW state (= on the float32 observation just produced:
+     * firstfit.py:21-38 / bestfit.py:21-40), as [n_envs, V] actions of the placement type — what the caller's next
+     * `agent.act(obs)` returns, computed while the record is still in shared memory (HostVecEnv's eager act).  NULL: off.
+     * May alias the d_action argument of vmgym_step when that is of the placement type (an env reads its row before it writes it). */
+    void* d_next_action;
+    int32_t next_agent;      /* VMGYM_AGENT_FIRSTFIT / VMGYM_AGENT_BESTFIT */
+    int32_t next_tiebreak;   /* VMGYM_TIE_* */
 } vmgym_outputs;
 #define VMGYM_STATS 16
 #define VMGYM_VMSTAT_BINS 1024   /* rates are rounded to 3 decimals (record.py:61,79): bins 0..1000 are used */

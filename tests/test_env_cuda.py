@@ -546,6 +546,32 @@ def test_empty_batch_and_bad_arguments():
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("shape", ["s10wr", "s100", "odd", "p254", "wide"])
+@pytest.mark.parametrize("agent,tiebreak", [("firstfit", None), ("bestfit", "stable"), ("bestfit", "numpy_introsort")])
+def test_step_next_action_equals_agent_act_on_the_new_observation(shape, agent, tiebreak):
+    """vmgym_outputs.d_next_action: after a step on external actions the kernel also leaves the heuristic agent's act() on the NEW
+    state; it must equal the stand-alone agent.act(obs) on the returned observation (firstfit.py:21-38 / bestfit.py:21-40), also
+    when the output tensor is the action tensor itself."""
+    import torch
+    from vmgym import VecVmEnv
+    from vmgym.agents import BestFitAgent, FirstFitAgent
+    N = 6 if shape == "wide" else 40
+    vec = VecVmEnv(_cfg(**SHAPES[shape]), N, rng="philox", tiebreak=tiebreak or "stable")
+    ag = (FirstFitAgent if agent == "firstfit" else BestFitAgent)(vec, tiebreak=tiebreak)
+    obs = vec.observe()
+    act = ag.act(obs).clone().to(vec.place_dtype)
+    nxt = torch.empty_like(act)
+    for k in range(60):
+        in_place = k % 2 == 1
+        out = act if in_place else nxt
+        obs, *_ = vec.step(act, want_valid=False, next_action=(agent, out, tiebreak))
+        want = ag.act(obs).to(vec.place_dtype)
+        torch.cuda.synchronize()
+        assert torch.equal(out, want), f"step {k}: next_action differs from agent.act(obs)"
+        act = want.clone()
+    assert int(vec.counters()["place_actions"].sum()) > 0
+
+
 @pytest.mark.parametrize("use_graphs,zero_copy,delta_obs,resident", [(True, True, True, True), (False, True, True, True), (True, True, False, True),
                                                                      (True, False, False, True), (True, True, True, False), (False, False, False, False)])
 def test_host_vec_env_pipelined_equals_fused_device_rollout(use_graphs, zero_copy, delta_obs, resident):

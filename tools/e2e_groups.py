@@ -16,9 +16,9 @@ def timed(fn):
     return (time.perf_counter() - t0) / S * 1e6
 
 
-for resident, dma in ((True, True), (True, "d2h"), (True, "h2d"), (False, True)):
-    for groups in (2, 4):
-        hv = HostVecEnv(Config(**cfg), E, groups=groups, rng="philox", agent="bestfit", resident_obs=resident, action_dma=dma)
+for resident, dma in ((True, True), (True, "nofuse")):
+    for groups in (2, 4, 8):
+        hv = HostVecEnv(Config(**cfg), E, groups=groups, rng="philox", agent="bestfit", resident_obs=resident, action_dma=True, fused_next=(dma is True))
         hv.fast_forward(WARM_STEPS); hv.run_pipelined(300); hv.run_pipelined(300, poll=True)
 
         def plain():

@@ -147,7 +147,8 @@ static int launch_step(StepParams& sp, cudaStream_t st)
     const bool team = team_ok && sizeof(PT) == 2;
     if (team) {
         // launches that never sort (stable ties / first-fit / external actions) do without the sort scratch
-        const bool sorts = sp.agent == VMGYM_AGENT_BESTFIT && sp.tiebreak == VMGYM_TIE_NUMPY_INTROSORT;
+        const bool sorts = (sp.agent == VMGYM_AGENT_BESTFIT && sp.tiebreak == VMGYM_TIE_NUMPY_INTROSORT) ||
+                           (sp.out.d_next_action && sp.out.next_agent == VMGYM_AGENT_BESTFIT && sp.out.next_tiebreak == VMGYM_TIE_NUMPY_INTROSORT);
         const bool kl_fits = 2 * align_up(sp.L.V, 16) <= sp.L.sm_act - sp.L.sm_cpu32;
         static const bool small_ok = getenv("VMGYM_TEAM_FULL_SCRATCH") == nullptr;          // A/B switch for experiments
         if (small_ok && !sorts && kl_fits) layout_scratch(sp.L, 2, true);
@@ -189,7 +190,7 @@ static int launch_step(StepParams& sp, cudaStream_t st)
     if (specialise && L.P == 100 && L.V == 300) {                                           // config/100.yml
         kern = pick_db<PT, 100, 300, -1>(db);
         // the benchmark configurations of this shape: fused heuristic agents / external actions, reward wr, stable ties
-        if (sp.reward_fn == VMGYM_REWARD_WR && sp.tiebreak == VMGYM_TIE_STABLE && !sp.out.d_vm_slots) {   // per-VM stats: generic kernel
+        if (sp.reward_fn == VMGYM_REWARD_WR && sp.tiebreak == VMGYM_TIE_STABLE && !sp.out.d_vm_slots && !sp.out.d_next_action) {   // per-VM stats, next-action output: generic kernel
             const int mode = sp.tr.mode;
             if (sp.agent == VMGYM_AGENT_BESTFIT && mode == VMGYM_TRACE_PHILOX)
                 kern = pick_db<PT, 100, 300, make_spec(VMGYM_AGENT_BESTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>(db);
@@ -200,7 +201,7 @@ static int launch_step(StepParams& sp, cudaStream_t st)
         }
     } else if (specialise && L.P == 10 && L.V == 30) {
         kern = pick_db<PT, 10, 30, -1>(db);                                                // config/10.yml
-        if (sp.reward_fn == VMGYM_REWARD_WR && sp.tiebreak == VMGYM_TIE_STABLE && !sp.out.d_vm_slots && sp.tr.mode == VMGYM_TRACE_PHILOX) {
+        if (sp.reward_fn == VMGYM_REWARD_WR && sp.tiebreak == VMGYM_TIE_STABLE && !sp.out.d_vm_slots && !sp.out.d_next_action && sp.tr.mode == VMGYM_TRACE_PHILOX) {
             if (sp.agent == VMGYM_AGENT_FIRSTFIT)                                          // BASELINE configs[0]: first-fit evaluation
                 kern = pick_db<PT, 10, 30, make_spec(VMGYM_AGENT_FIRSTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>(db);
             else if (sp.agent == VMGYM_AGENT_BESTFIT)
@@ -325,6 +326,12 @@ int vmgym_step(const vmgym_config* cfg, void* d_state, int64_t n_envs, const vmg
     if (rc) return rc;
     if (n_envs == 0) return VMGYM_OK;
     if (!d_action) return fail(VMGYM_EINVAL, "null action");
+    if (sp.out.d_next_action) {
+        if (sp.out.next_agent != VMGYM_AGENT_FIRSTFIT && sp.out.next_agent != VMGYM_AGENT_BESTFIT)
+            return fail(VMGYM_EUNSUPPORTED, "d_next_action: next_agent must be firstfit or bestfit");
+        if (sp.out.next_tiebreak != VMGYM_TIE_STABLE && sp.out.next_tiebreak != VMGYM_TIE_NUMPY_INTROSORT)
+            return fail(VMGYM_EINVAL, "d_next_action: unknown tiebreak");
+    }
     sp.action = d_action;
     sp.action_dtype = action_dtype;
     cudaStream_t st = (cudaStream_t)stream;
@@ -346,6 +353,7 @@ int vmgym_agent_step(const vmgym_config* cfg, void* d_state, int64_t n_envs, con
     if (tiebreak != VMGYM_TIE_STABLE && tiebreak != VMGYM_TIE_NUMPY_INTROSORT) return fail(VMGYM_EINVAL, "unknown tiebreak");
     if (n_steps < 1) return fail(VMGYM_EINVAL, "n_steps must be >= 1");
     if (n_envs == 0) return VMGYM_OK;
+    sp.out.d_next_action = nullptr;            // (vmgym_step only)
     sp.agent = agent; sp.tiebreak = tiebreak; sp.n_steps = n_steps;
     cudaStream_t st = (cudaStream_t)stream;
     return sp.L.P <= 253 ? launch_step<uint8_t>(sp, st) : launch_step<uint16_t>(sp, st);
@@ -365,6 +373,7 @@ int vmgym_agent_step_rotation(const vmgym_config* cfg, void* d_state, int64_t en
     if (tiebreak != VMGYM_TIE_STABLE && tiebreak != VMGYM_TIE_NUMPY_INTROSORT) return fail(VMGYM_EINVAL, "unknown tiebreak");
     if (n_steps < 1) return fail(VMGYM_EINVAL, "n_steps must be >= 1");
     if (envs_per_batch == 0 || n_batch_steps == 0) return VMGYM_OK;
+    sp.out.d_next_action = nullptr;            // (vmgym_step only)
     sp.agent = agent; sp.tiebreak = tiebreak; sp.n_steps = n_steps;
     sp.rot_batches = n_batches; sp.rot_steps = n_batch_steps; sp.rot_first = first_batch; sp.rot_envs = envs_per_batch;
     cudaStream_t st = (cudaStream_t)stream;

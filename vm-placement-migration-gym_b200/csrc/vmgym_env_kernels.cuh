@@ -1559,6 +1559,25 @@ __global__ void __launch_bounds__(TM ? 256 : 896, TM ? 3 : 1) step_kernel(const 
             if (res.terminated) break;
         }
 
+        // ---- the agent's act() on the state just produced (vmgym_outputs.d_next_action; generic kernels only) ----
+        if constexpr (SPEC < 0) {
+            if (p.out.d_next_action) {
+                if (!TM) {
+                    const double* cpu = e.cpu();
+                    const double* mem = e.mem();
+                    for (int q = lane; q < cP; q += 32) { e.cpu32()[q] = (float)cpu[q]; e.mem32()[q] = (float)mem[q]; }
+                    __syncwarp();
+                }
+                AgentView<PT> av;
+                av.place = e.place(); av.cc = e.cpuc(); av.mc = e.memc(); av.c32 = nullptr; av.m32 = nullptr; av.sz32 = sz32;
+                agent_act<PT, TM>(e, av, p.out.next_agent, p.out.next_tiebreak, true, nth);
+                PT* ao = reinterpret_cast<PT*>(p.out.d_next_action) + env * (long long)cV;
+                for (int v = lane; v < cV; v += 32)
+                    ao[v] = ((e.prop()[v >> 5] >> (v & 31)) & 1u) ? (PT)e.act()[v] : e.place()[v];
+                __syncwarp();
+            }
+        }
+
         // ---- outputs ----
         if (p.out.d_obs) {
             // a persistent observation buffer keeps the rows of envs whose state did not change (a quiet step changes

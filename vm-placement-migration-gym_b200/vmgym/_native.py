@@ -54,7 +54,8 @@ class Outputs(C.Structure):
     _fields_ = [("d_obs", C.c_void_p), ("d_reward", C.c_void_p), ("d_terminated", C.c_void_p),
                 ("d_valid", C.c_void_p), ("d_action", C.c_void_p), ("d_stats", C.c_void_p),
                 ("d_vm_slots", C.c_void_p), ("d_vm_hist", C.c_void_p), ("d_vm_totals", C.c_void_p), ("d_obs_mirror", C.c_void_p),
-                ("obs_persistent", C.c_int32), ("reserved0", C.c_int32)]
+                ("obs_persistent", C.c_int32), ("reserved0", C.c_int32),
+                ("d_next_action", C.c_void_p), ("next_agent", C.c_int32), ("next_tiebreak", C.c_int32)]
 
 
 VMSTAT_BINS = 1024

@@ -51,7 +51,8 @@ def _driver_api():
 class HostVecEnv:
     def __init__(self, config: Config, num_envs: int, groups: int = 4, device="cuda", rng: str = "philox", seeds=None,
                  agent: str | None = "bestfit", tiebreak: str | None = None, use_graphs: bool = True, zero_copy: bool = True,
-                 delta_obs: bool = True, resident_obs: bool = True, action_dma: bool = True, eager_act: bool = True, **vec_kwargs):
+                 delta_obs: bool = True, resident_obs: bool = True, action_dma: bool = True, eager_act: bool = True, fused_next: bool = True,
+                 **vec_kwargs):
         if num_envs < 1 or groups < 1:
             raise ValueError("num_envs and groups must be positive")
         groups = min(groups, num_envs)
@@ -118,6 +119,8 @@ class HostVecEnv:
         # compares the device observations with a device-side shadow of the host copy and stores the differences), so the scattered
         # PCIe stores are off the path H2D actions -> step -> act -> D2H actions that decides how long a step takes
         self.side_mirror = self.eager_act and self.obs_dim % 4 == 0           # (16-byte aligned row ranges for the 128-bit compare)
+        self._agent_name, self._tiebreak = agent, tiebreak
+        self.fused_next = self.side_mirror and bool(fused_next) and self.action_dma is True
         if self.side_mirror:
             for g in self.groups:
                 g.shadow = g.vec.observe().clone()
@@ -175,7 +178,11 @@ class HostVecEnv:
         import ctypes as C
         from . import _native as nv
         g.d_act_in.copy_(self.action[g.lo:g.hi], non_blocking=True)            # host actions -> device (copy engine)
-        obs, rew, term, _, _ = g.vec.step(g.d_act_in, want_valid=False)        # device outputs only
+        # device outputs only; with fused_next the same kernel also leaves the agent's act() on the new state in d_act_in (each env
+        # reads its action row before it writes its next one): no separate act kernel, no second pass over the observations
+        fused = self.fused_next
+        obs, rew, term, _, _ = g.vec.step(g.d_act_in, want_valid=False,
+                                          next_action=(self._agent_name, g.d_act_in, self._tiebreak) if fused else None)
         term_u8 = g.vec.terminated_u8
         g.side.wait_stream(g.stream)
         with torch.cuda.stream(g.side):
@@ -185,7 +192,10 @@ class HostVecEnv:
                                                       self.terminated[g.lo:g.hi].data_ptr(), n, C.c_void_p(g.side.cuda_stream)),
                      "vmgym_obs_mirror_update")
             g.ev_step.record(g.side)           # obs / reward / done are on the host
-        self._act_chain(g)                     # meanwhile: the agent's act on the new device observations, actions -> host
+        if fused:
+            self.action[g.lo:g.hi].copy_(g.d_act_in, non_blocking=True)       # next actions -> host (copy engine)
+        else:
+            self._act_chain(g)                 # meanwhile: the agent's act on the new device observations, actions -> host
         g.ev_act.record(g.stream)
         g.stream.wait_stream(g.side)           # the next step must not overwrite the observations under the mirror kernel
 

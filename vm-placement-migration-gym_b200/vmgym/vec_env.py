@@ -60,6 +60,10 @@ def vm_stats_from_histograms(hist, totals):
     return out
 
 
+def ctypes_addr(obj) -> int:
+    return C.addressof(obj)
+
+
 class VecVmEnv:
     def __init__(self, config: Config, num_envs: int, device="cuda", rng: str = "numpy", seeds=None,
                  trace_steps: int | None = None, max_admissions: int | None = None, tiebreak: str = "stable",
@@ -282,13 +286,16 @@ class VecVmEnv:
         return t
 
     def step(self, action, want_obs: bool = True, want_valid: bool = True, host_outputs=None, want_stats: bool = False,
-             obs_mirror=None):
+             obs_mirror=None, next_action=None):
         """env.py:66-103 for all envs.  `action`: [N, V] device tensor (uint8 / int16 / int64), numpy int array, or a
         PINNED host tensor (device-mapped under UVA: the kernel reads it over PCIe, no copy-engine transfer).
         `host_outputs`: optional (reward f64 [N], terminated u8 [N]) pinned host tensors the kernel writes directly,
         instead of the env's device buffers.  `want_stats`: accumulate the episode sums behind summary().
         `obs_mirror`: optional pinned host tensor [N, 3V+2P] kept equal to self.obs by storing only the entries that changed
-        (it must already equal self.obs, e.g. copied once after reset)."""
+        (it must already equal self.obs, e.g. copied once after reset).
+        `next_action`: optional (agent name, [N, V] device tensor of the placement dtype, tiebreak or None): the kernel also
+        writes that heuristic agent's act() on the NEW state into the tensor (what `agent.act(obs)` of the returned observation
+        gives; the tensor may be `action` itself when the dtypes agree)."""
         if not isinstance(action, torch.Tensor):
             action = torch.from_numpy(np.ascontiguousarray(action, dtype=np.int64)).to(self.device, non_blocking=True)
         elif not action.is_cuda and not action.is_pinned():
@@ -317,6 +324,19 @@ class VecVmEnv:
                                   obs_persistent=1)
                 self._out_cache[key] = hout
             out = hout
+        if next_action is not None:
+            na_agent, na_out, na_tie = next_action
+            if not (na_out.is_cuda and na_out.dtype == self.place_dtype and na_out.shape == (self.num_envs, self.V) and na_out.is_contiguous()):
+                raise ValueError("next_action: need a contiguous device tensor [N, V] of the placement dtype")
+            key = ("next", ctypes_addr(out), na_out.data_ptr(), na_agent, na_tie)
+            nout = self._out_cache.get(key)
+            if nout is None:
+                nout = nv.Outputs.from_buffer_copy(out)
+                nout.d_next_action = na_out.data_ptr()
+                nout.next_agent = {"firstfit": nv.AGENT_FIRSTFIT, "bestfit": nv.AGENT_BESTFIT}[na_agent]
+                nout.next_tiebreak = nv.TIE_IDS[na_tie or self.tiebreak]
+                self._out_cache[key] = nout
+            out = nout
         with self._on_device():
             nv.check(self._lib.vmgym_step(C.byref(self._ccfg()), self.state.data_ptr(), self.num_envs,
                                           C.byref(self._trace), action.data_ptr(), _TORCH_ACTION_DTYPES[action.dtype],
