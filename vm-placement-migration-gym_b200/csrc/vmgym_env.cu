@@ -190,7 +190,11 @@ static int launch_step(StepParams& sp, cudaStream_t st)
     if (specialise && L.P == 100 && L.V == 300) {                                           // config/100.yml
         kern = pick_db<PT, 100, 300, -1>(db);
         // the benchmark configurations of this shape: fused heuristic agents / external actions, reward wr, stable ties
-        if (sp.reward_fn == VMGYM_REWARD_WR && sp.tiebreak == VMGYM_TIE_STABLE && !sp.out.d_vm_slots && !sp.out.d_next_action) {   // per-VM stats, next-action output: generic kernel
+        if (sp.reward_fn == VMGYM_REWARD_WR && sp.agent == VMGYM_AGENT_NONE && sp.tr.mode == VMGYM_TRACE_PHILOX && !sp.out.d_vm_slots &&
+            sp.out.d_next_action && sp.out.next_agent == VMGYM_AGENT_BESTFIT && sp.out.next_tiebreak == VMGYM_TIE_STABLE) {
+            // HostVecEnv's step: external actions, then best-fit's act on the new state
+            kern = pick_db<PT, 100, 300, make_spec(VMGYM_AGENT_NONE, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX, VMGYM_AGENT_BESTFIT)>(db);
+        } else if (sp.reward_fn == VMGYM_REWARD_WR && sp.tiebreak == VMGYM_TIE_STABLE && !sp.out.d_vm_slots && !sp.out.d_next_action) {   // per-VM stats, other next-action outputs: generic kernel
             const int mode = sp.tr.mode;
             if (sp.agent == VMGYM_AGENT_BESTFIT && mode == VMGYM_TRACE_PHILOX)
                 kern = pick_db<PT, 100, 300, make_spec(VMGYM_AGENT_BESTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>(db);

@@ -1337,7 +1337,11 @@ __host__ __device__ __forceinline__ int dtype_bytes(int dtype) { return dtype ==
 // PC / VC: compile-time pms / vms of the instantiation (0 = take them from the layout at run time); the named
 // configs of the reference (config/10.yml, config/100.yml) get fully unrolled loops.
 // SPEC >= 0 additionally fixes (agent, tiebreak, reward, trace mode) = spec_* fields at compile time (SPEC < 0: run time).
-constexpr int make_spec(int agent, int tiebreak, int reward, int mode) { return agent | (tiebreak << 4) | (reward << 8) | (mode << 12); }
+// `post_agent` != 0: the kernel also computes that agent's act() on the new state (vmgym_outputs.d_next_action, stable ties)
+constexpr int make_spec(int agent, int tiebreak, int reward, int mode, int post_agent = 0)
+{
+    return agent | (tiebreak << 4) | (reward << 8) | (mode << 12) | (post_agent << 16);
+}
 
 // TM: team mode (one env per CTA, warp 0 + helper warps; see "Team mode" above) — instantiated for u16 placements.
 // DB: double-buffered records for launches in which a warp steps several envs one after the other (grid capped at the
@@ -1559,9 +1563,12 @@ __global__ void __launch_bounds__(TM ? 256 : 896, TM ? 3 : 1) step_kernel(const 
             if (res.terminated) break;
         }
 
-        // ---- the agent's act() on the state just produced (vmgym_outputs.d_next_action; generic kernels only) ----
-        if constexpr (SPEC < 0) {
+        // ---- the agent's act() on the state just produced (vmgym_outputs.d_next_action; generic kernels and the specs with a post agent) ----
+        constexpr int POST_CT = SPEC >= 0 ? ((SPEC >> 16) & 0xf) : -1;
+        if constexpr (POST_CT != 0) {
             if (p.out.d_next_action) {
+                const int post_agent = SPEC >= 0 ? POST_CT : p.out.next_agent;
+                const int post_tie = SPEC >= 0 ? VMGYM_TIE_STABLE : p.out.next_tiebreak;
                 if (!TM) {
                     const double* cpu = e.cpu();
                     const double* mem = e.mem();
@@ -1570,7 +1577,7 @@ __global__ void __launch_bounds__(TM ? 256 : 896, TM ? 3 : 1) step_kernel(const 
                 }
                 AgentView<PT> av;
                 av.place = e.place(); av.cc = e.cpuc(); av.mc = e.memc(); av.c32 = nullptr; av.m32 = nullptr; av.sz32 = sz32;
-                agent_act<PT, TM>(e, av, p.out.next_agent, p.out.next_tiebreak, true, nth);
+                agent_act<PT, TM>(e, av, post_agent, post_tie, true, nth);
                 PT* ao = reinterpret_cast<PT*>(p.out.d_next_action) + env * (long long)cV;
                 for (int v = lane; v < cV; v += 32)
                     ao[v] = ((e.prop()[v >> 5] >> (v & 31)) & 1u) ? (PT)e.act()[v] : e.place()[v];
