@@ -572,6 +572,44 @@ def test_step_next_action_equals_agent_act_on_the_new_observation(shape, agent, 
     assert int(vec.counters()["place_actions"].sum()) > 0
 
 
+def test_obs_mirror_update_stores_exactly_the_changed_entries():
+    """vmgym_obs_mirror_update: host copy and device shadow follow the device observations; untouched entries are not written
+    (a poisoned host value under an unchanged entry survives), -0.0 vs 0.0 counts as a change (bit compare); reward / done forwarded."""
+    import ctypes as C
+    import torch
+    from vmgym import _native as nv
+    N, D = 37, 1100
+    lib = nv.lib()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    obs = torch.rand((N, D), device="cuda", generator=g)
+    shadow = obs.clone()
+    host = obs.cpu().pin_memory()
+    rew_d = torch.rand(N, device="cuda", dtype=torch.float64, generator=g)
+    term_d = (torch.rand(N, device="cuda", generator=g) < 0.3).to(torch.uint8)
+    rew_h = torch.zeros(N, dtype=torch.float64).pin_memory()
+    term_h = torch.zeros(N, dtype=torch.uint8).pin_memory()
+    idx = torch.randint(0, N * D, (500,), device="cuda", generator=g).unique()
+    flat = obs.view(-1)
+    flat[idx] = flat[idx] + 1.0
+    flat[7] = -0.0 if float(flat[7]) == 0.0 else flat[7]
+    shadow.view(-1)[11] = 0.0
+    flat[11] = -0.0                                     # same value, different bits
+    host.view(-1)[5] = 123.0 if 5 not in idx.tolist() and 5 not in (7, 11) else host.view(-1)[5]
+    poisoned = float(host.view(-1)[5]) == 123.0
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    nv.check(lib.vmgym_obs_mirror_update(obs.data_ptr(), shadow.data_ptr(), host.data_ptr(), N * D, rew_d.data_ptr(), rew_h.data_ptr(),
+                                         term_d.data_ptr(), term_h.data_ptr(), N, st), "mirror")
+    torch.cuda.synchronize()
+    assert torch.equal(shadow.view(torch.int32), obs.view(torch.int32))
+    want = obs.cpu()
+    if poisoned:
+        want.view(-1)[5] = 123.0                       # never rewritten: the entry did not change
+    assert torch.equal(host.view(torch.int32), want.view(torch.int32))
+    assert torch.equal(rew_h, rew_d.cpu()) and torch.equal(term_h, term_d.cpu())
+    rc = lib.vmgym_obs_mirror_update(obs.data_ptr(), shadow.data_ptr(), host.data_ptr(), N * D + 2, None, None, None, None, 0, st)
+    assert rc == nv.EINVAL
+
+
 @pytest.mark.parametrize("use_graphs,zero_copy,delta_obs,resident", [(True, True, True, True), (False, True, True, True), (True, True, False, True),
                                                                      (True, False, False, True), (True, True, True, False), (False, False, False, False)])
 def test_host_vec_env_pipelined_equals_fused_device_rollout(use_graphs, zero_copy, delta_obs, resident):
