@@ -352,7 +352,9 @@ __global__ void __launch_bounds__(256) heads_eval_kernel(const HeadParams p)
 // admissible cpu / memory code is found once per env (binary search with the same fp64 expression) and every waiting
 // row then reduces to byte-SIMD compares of its two codes against 4 PMs per instruction.  Bit-identical to
 // row_invalid_bits; ~7x fewer instructions and no per-row global latency (placement / codes staged in SMEM).
-template <typename PT>
+// NW = mask words per row the kernel is compiled for (A <= 32 NW): the per-row loops are fully unrolled over NW words, so a 102-action
+// row costs 4 words of work, not 8 (178 -> 131 us at 8192 envs of config/100.yml; ncu: the 8-word code ran 12.2 k warp-instructions per env with 3.4 no_instruction stalls per issue)
+template <typename PT, int NW>
 __global__ void __launch_bounds__(128) mask_bits_kernel(const HeadParams p)
 {
     extern __shared__ __align__(16) unsigned char ms[];
@@ -388,15 +390,15 @@ __global__ void __launch_bounds__(128) mask_bits_kernel(const HeadParams p)
     const PT* place = reinterpret_cast<const PT*>(rec + L.off_place);
     for (int v = threadIdx.x; v < V; v += blockDim.x) {
         const int cur = (int)place[v];
-        uint32_t bits[8];
+        uint32_t bits[NW];
         #pragma unroll
-        for (int w = 0; w < 8; w++) bits[w] = 0xffffffffu;
+        for (int w = 0; w < NW; w++) bits[w] = 0xffffffffu;
         if (p.masked) {
             if (cur == P) {
                 const uint32_t c4 = (uint32_t)(rec[L.off_cpuc + v] & 0x7f) * 0x01010101u;
                 const uint32_t m4 = (uint32_t)rec[L.off_memc + v] * 0x01010101u;
                 #pragma unroll
-                for (int w = 0; w < 8; w++) {
+                for (int w = 0; w < NW; w++) {
                     uint32_t word = 0;
                     #pragma unroll
                     for (int j = 0; j < 8; j++) {
@@ -412,7 +414,7 @@ __global__ void __launch_bounds__(128) mask_bits_kernel(const HeadParams p)
             }
             // columns >= P are invalid unless named below; a == cur is always valid; a placed VM may also go back to P
             #pragma unroll
-            for (int w = 0; w < 8; w++) {
+            for (int w = 0; w < NW; w++) {
                 const int base = w * 32;
                 if (P - base < 32) bits[w] |= (P - base <= 0) ? 0xffffffffu : (0xffffffffu << (P - base));
                 if (A - base < 32) bits[w] &= (A - base <= 0) ? 0u : ~(0xffffffffu << (A - base));
@@ -421,26 +423,26 @@ __global__ void __launch_bounds__(128) mask_bits_kernel(const HeadParams p)
             }
         } else {
             #pragma unroll
-            for (int w = 0; w < 8; w++) bits[w] = 0u;
+            for (int w = 0; w < NW; w++) bits[w] = 0u;
         }
         if (p.migration_ratio >= 0.f) {
             // ppo.py:153-155: if count_nonzero(invalid_row) > 1 and not invalid_row[P] and rand() > migration_ratio
             int cnt = 0;
             #pragma unroll
-            for (int w = 0; w < 8; w++) cnt += (w < W) ? __popc(bits[w]) : 0;
+            for (int w = 0; w < NW; w++) cnt += (w < W) ? __popc(bits[w]) : 0;
             uint32_t wait_inv = 0;
             #pragma unroll
-            for (int w = 0; w < 8; w++) if ((P >> 5) == w) wait_inv = (bits[w] >> (P & 31)) & 1u;
+            for (int w = 0; w < NW; w++) if ((P >> 5) == w) wait_inv = (bits[w] >> (P & 31)) & 1u;
             if (cnt > 1 && !wait_inv) {
                 const float u = gate_uniform(v, (uint32_t)env, p.seed, (uint32_t)p.counter);
                 if (u > p.migration_ratio) {
                     #pragma unroll
-                    for (int w = 0; w < 8; w++) if ((P >> 5) == w) bits[w] |= 1u << (P & 31);
+                    for (int w = 0; w < NW; w++) if ((P >> 5) == w) bits[w] |= 1u << (P & 31);
                 }
             }
         }
         #pragma unroll
-        for (int w = 0; w < 8; w++) if (w < W) s_out[v * W + w] = bits[w];
+        for (int w = 0; w < NW; w++) if (w < W) s_out[v * W + w] = bits[w];
     }
     __syncthreads();
     uint32_t* mo = p.mask_out + env * (long long)V * W;
@@ -510,13 +512,16 @@ static int heads_launch(HeadParams& hp, const vmgym_config* cfg, bool backward, 
         // mask-only call: thread-per-row kernel
         const size_t msmem = 128 * sizeof(double) + 128 * sizeof(uint32_t) + (size_t)L.V * ((L.A + 31) / 32) * sizeof(uint32_t);
         if (msmem > 200 * 1024) return pfail(VMGYM_EUNSUPPORTED, "vms too large for the mask kernel");
-        if (small) {
-            if (msmem > 48 * 1024) cudaFuncSetAttribute(mask_bits_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
-            mask_bits_kernel<uint8_t><<<(unsigned)hp.n_envs, 128, msmem, st>>>(hp);
-        } else {
-            if (msmem > 48 * 1024) cudaFuncSetAttribute(mask_bits_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
-            mask_bits_kernel<uint16_t><<<(unsigned)hp.n_envs, 128, msmem, st>>>(hp);
-        }
+        const int words = (L.A + 31) / 32;
+        if (words > 8) return pfail(VMGYM_EUNSUPPORTED, "the mask kernel supports action_dim <= 256");
+#define VMGYM_MASK_LAUNCH(PT_, NW_) do {                                                                                              \
+            if (msmem > 48 * 1024) cudaFuncSetAttribute(mask_bits_kernel<PT_, NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem); \
+            mask_bits_kernel<PT_, NW_><<<(unsigned)hp.n_envs, 128, msmem, st>>>(hp); } while (0)
+#define VMGYM_MASK_WORDS(PT_) do { if (words <= 1) VMGYM_MASK_LAUNCH(PT_, 1); else if (words <= 2) VMGYM_MASK_LAUNCH(PT_, 2);            \
+                                   else if (words <= 4) VMGYM_MASK_LAUNCH(PT_, 4); else VMGYM_MASK_LAUNCH(PT_, 8); } while (0)
+        if (small) VMGYM_MASK_WORDS(uint8_t); else VMGYM_MASK_WORDS(uint16_t);
+#undef VMGYM_MASK_WORDS
+#undef VMGYM_MASK_LAUNCH
         cudaError_t merr = cudaGetLastError();
         if (merr != cudaSuccess) return pfail(VMGYM_ECUDA, cudaGetErrorString(merr));
         return VMGYM_OK;
