@@ -789,11 +789,16 @@ def test_performance_rows_through_sweep(shape, agent, load, reward, seeds, want)
 
 @pytest.mark.parametrize("shape,E,NB,K,n_steps,agent,bulk", [("s100", 300, 3, 8, 1, "bestfit", 7), ("s100", 4200, 2, 5, 1, "bestfit", 7),
                                                             ("s10", 700, 4, 9, 2, "firstfit", 7 | 32), ("wide", 5, 3, 7, 1, "firstfit", 7),
-                                                            ("s100", 64, 5, 12, 3, "firstfit", 0)])
+                                                            ("s100", 64, 5, 12, 3, "firstfit", 0),
+                                                            # team mode with more envs per batch than resident CTAs: records are shared out
+                                                            # as (batch * E + index) mod grid (balanced team rotation)
+                                                            ("p254", 5000, 2, 5, 1, "firstfit", 7), ("big", 1300, 3, 7, 2, "bestfit", 7),
+                                                            ("s1000", 700, 2, 4, 1, "bestfit", 7)])
 def test_rotation_launch_equals_per_batch_launches(shape, E, NB, K, n_steps, agent, bulk):
     """vmgym_agent_step_rotation: ONE persistent launch over NB sub-batches x K batch steps == K calls of the fused agent step on
     the sub-batches in rotation (byte-identical records, observations, rewards, done flags), for record staging by bulk copies,
-    double-buffered records, plain loads, the team-mode kernel (wide) and more env indexes than resident warps (4200)."""
+    double-buffered records, plain loads, the team-mode kernel (wide; p254 / big / s1000 with more envs per batch than resident
+    CTAs) and more env indexes than resident warps (4200)."""
     torch = _torch()
     from vmgym import VecVmEnv
     from vmgym import _native as nv

@@ -1376,8 +1376,19 @@ __global__ void __launch_bounds__(TM ? 256 : 896, TM ? 3 : 1) step_kernel(const 
     const bool ROT = p.rot_batches > 0;
     const long long n_idx = ROT ? p.rot_envs : p.n_envs;
     const int per_idx = ROT ? p.rot_steps : 1;
-    const bool any_item = env0 < n_idx && per_idx > 0;
-    const long long first_env = env0 + (ROT ? (long long)p.rot_first * p.rot_envs : 0ll);
+    // Team-mode rotation ("balanced", BAL): a CTA steps ONE env at a time and a batch rarely holds a multiple of the resident
+    // CTAs (1024 envs on 592 CTA slots at 1000 PMs: two rounds, the second 73 % full).  So the CTAs do not own env indexes but
+    // RECORDS: record r = batch * rot_envs + idx belongs to CTA r mod gridDim.x — still one fixed CTA per record, hence every
+    // record's steps stay in one CTA's program order — and the loop nest is batch step outside, the CTA's records of that batch
+    // inside.  The remainder of each batch then lands on different CTAs from batch to batch and the load evens out.
+    const bool BAL = TM && ROT;                       // compile-time false outside team mode
+    const long long bal_g = (long long)gridDim.x;     // (grid <= rot_envs: every CTA owns >= 1 record of every batch)
+    auto bal_idx0 = [&](int rb) -> int {              // lowest env index of batch rb owned by this CTA
+        return (int)(((long long)blockIdx.x - ((long long)rb * p.rot_envs) % bal_g + bal_g) % bal_g);
+    };
+    const bool any_item = BAL ? per_idx > 0 : (env0 < n_idx && per_idx > 0);
+    const long long first_env = BAL ? (long long)p.rot_first * p.rot_envs + bal_idx0(p.rot_first)
+                                    : env0 + (ROT ? (long long)p.rot_first * p.rot_envs : 0ll);
     // Programmatic dependent launch (use_bulk bit 2): let the NEXT kernel of the stream start launching right away (its CTAs
     // take the slots this grid frees as its fast CTAs finish) ...
     const bool PDL = (p.use_bulk & 4) != 0;
@@ -1432,19 +1443,27 @@ __global__ void __launch_bounds__(TM ? 256 : 896, TM ? 3 : 1) step_kernel(const 
     uint32_t phase = 0;
     if (helper) {
         // helper warps: wait for each record of this CTA, then serve the main warp's phases until it closes the env
-        for (long long idx = env0; idx < n_idx; idx += stride)
-            for (int rk = 0; rk < per_idx; rk++) {
+        for (long long o = BAL ? 0ll : env0; o < (BAL ? (long long)per_idx : n_idx); o += BAL ? 1ll : stride) {
+            const int i0 = BAL ? bal_idx0((int)((p.rot_first + o) % p.rot_batches)) : 0;
+            for (int i = i0; i < (BAL ? (int)n_idx : per_idx); i += BAL ? (int)stride : 1) {
                 if (BULK) { mbar_wait(bar, phase); phase ^= 1; }
                 team_serve(e, (int)threadIdx.x, nth);
             }
+        }
         return;
     }
     uint32_t phase1 = 0;
     int cur = 0;                             // DB: which record buffer holds the current env
-    for (long long idx = env0; idx < n_idx; idx += stride)
-    for (int rk = 0, rb = ROT ? p.rot_first : 0; rk < per_idx; rk++, rb = (rb + 1 == p.rot_batches) ? 0 : rb + 1) {
+    // loop nest: env index outside, its rotation steps inside — or, balanced team rotation, batch step outside, records inside
+    for (long long o = BAL ? 0ll : env0; o < (BAL ? (long long)per_idx : n_idx); o += BAL ? 1ll : stride) {
+    const int rb_o = BAL ? (int)((p.rot_first + o) % p.rot_batches) : 0;
+    const int i0 = BAL ? bal_idx0(rb_o) : 0;
+    for (int i = i0, rbi = ROT ? p.rot_first : 0; i < (BAL ? (int)n_idx : per_idx); i += BAL ? (int)stride : 1, rbi = (rbi + 1 == p.rot_batches) ? 0 : rbi + 1) {
+        const long long idx = BAL ? (long long)i : o;
+        const int rk = BAL ? (int)o : i;
+        const int rb = BAL ? rb_o : rbi;
         const long long env = ROT ? (long long)rb * p.rot_envs + idx : idx;
-        const bool first_item = idx == env0 && rk == 0;
+        const bool first_item = BAL ? (o == 0 && i == i0) : (idx == env0 && rk == 0);
         unsigned char* grec = p.state + env * (long long)L.rec_bytes;
 #ifdef VMGYM_PROF
         const long long _pload = clock64();
@@ -1454,9 +1473,20 @@ __global__ void __launch_bounds__(TM ? 256 : 896, TM ? 3 : 1) step_kernel(const 
         // batch steps, i.e. a DRAM round trip on the warp's serial chain.  Ask L2 for it now; the load one step later then hits
         // L2.  (The bytes still cross HBM once per step; a second shared-memory buffer per warp — DB — would cost resident
         // warps at this record size.)  Measured: 6.54 -> 6.46 us per 4096-env step.
-        if (!DB && ROT && lane == 0 && rk + 1 < per_idx && (p.use_bulk & 64) == 0) {
+        if (!DB && ROT && !BAL && lane == 0 && rk + 1 < per_idx && (p.use_bulk & 64) == 0) {
             const long long nxt = (long long)((rb + 1 == p.rot_batches) ? 0 : rb + 1) * p.rot_envs + idx;
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.state + nxt * (long long)L.rec_bytes), "r"((uint32_t)L.rec_bytes) : "memory");
+        }
+        if (BAL && lane == 0 && (p.use_bulk & 64) == 0) {
+            // balanced team rotation: the CTA's next record = its next one in this batch, else its first one in the next batch
+            long long nxt = -1;
+            if (idx + stride < n_idx) nxt = (long long)rb * p.rot_envs + idx + stride;
+            else if (rk + 1 < per_idx) {
+                const int nb = (rb + 1 == p.rot_batches) ? 0 : rb + 1;
+                nxt = (long long)nb * p.rot_envs + bal_idx0(nb);
+            }
+            if (nxt >= 0)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.state + nxt * (long long)L.rec_bytes), "r"((uint32_t)L.rec_bytes) : "memory");
         }
         if (DB) {
             unsigned char* other = cur ? base : base + L.sm_stride;
@@ -1643,6 +1673,7 @@ __global__ void __launch_bounds__(TM ? 256 : 896, TM ? 3 : 1) step_kernel(const 
             if (BULK) fence_proxy_async();        // generic-proxy reads of smem before the next record's async-proxy write
         }
         PROF_ADD(5);                                                                                     // 5: write-back
+    }
     }
     if (DB && lane == 0) bulk_wait_read0();       // shared memory must outlive the last write-backs
 }
