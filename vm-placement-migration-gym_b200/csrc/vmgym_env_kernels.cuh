@@ -285,11 +285,37 @@ __device__ __forceinline__ void team_phase(const Env<PT>& e, int cmd, int tid, i
         const uint8_t* mc = e.memc();
         const unsigned* fitm = e.fitm();
         unsigned* cm = e.cmask();
-        for (int v0 = (tid & ~31); v0 < V; v0 += nth) {
-            const int v = v0 + (tid & 31);
-            const bool cand = v < V && (int)place[v] == P && (unsigned)mc[v] + 1u <= fitm[cc[v] & 0x7f];
-            const unsigned m = __ballot_sync(FULL, cand);
-            if ((tid & 31) == 0) cm[v0 >> 5] = m;
+        if constexpr (sizeof(PT) == 2) {
+            // four slots per thread (the arrays are padded to 16 slots with empty ones); a 32-slot chunk = 8 neighbouring threads
+            const uint2* pl4 = reinterpret_cast<const uint2*>(place);
+            const uint32_t* cc4 = reinterpret_cast<const uint32_t*>(cc);
+            const uint32_t* mc4 = reinterpret_cast<const uint32_t*>(mc);
+            const int nq = e.L->Vp >> 2;
+            for (int q0 = (tid & ~31); q0 < nq; q0 += nth) {
+                const int q = q0 + (tid & 31);
+                unsigned w = 0;
+                if (q < nq) {
+                    const uint2 a = pl4[q];
+                    const uint32_t c4 = cc4[q] & 0x7f7f7f7fu, m4 = mc4[q];
+                    const unsigned pl[4] = {a.x & 0xffffu, a.x >> 16, a.y & 0xffffu, a.y >> 16};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const bool wait = pl[j] == (unsigned)P;
+                        const unsigned f = fitm[wait ? ((c4 >> (8 * j)) & 0xffu) : 0u];
+                        w |= (wait && ((m4 >> (8 * j)) & 0xffu) + 1u <= f) ? (1u << j) : 0u;
+                    }
+                    w <<= 4 * (q & 7);
+                }
+                w |= __shfl_xor_sync(FULL, w, 1); w |= __shfl_xor_sync(FULL, w, 2); w |= __shfl_xor_sync(FULL, w, 4);
+                if ((q & 7) == 0 && q < nq) cm[q >> 3] = w;
+            }
+        } else {
+            for (int v0 = (tid & ~31); v0 < V; v0 += nth) {
+                const int v = v0 + (tid & 31);
+                const bool cand = v < V && (int)place[v] == P && (unsigned)mc[v] + 1u <= fitm[cc[v] & 0x7f];
+                const unsigned m = __ballot_sync(FULL, cand);
+                if ((tid & 31) == 0) cm[v0 >> 5] = m;
+            }
         }
     } else if (cmd == TEAM_COUNTDOWN) {
         // running VMs whose departure step is this step (ctl[1], env.py:245-249) are reported as a bitmap, the empty slots as a
@@ -300,17 +326,47 @@ __device__ __forceinline__ void team_phase(const Env<PT>& e, int cmd, int tid, i
         unsigned* emk = e.emask();
         const uint32_t now16 = (uint32_t)e.ctl()[1] & 0xffffu;
         unsigned dmin = 0xffffffffu;
-        for (int v0 = (tid & ~31); v0 < V; v0 += nth) {
-            const int v = v0 + (tid & 31);
-            const int pl = v < V ? (int)place[v] : P;
-            bool term = false;
-            if (pl < P) {
-                const uint32_t d = ((uint32_t)rem[v] - now16) & 0xffffu;       // steps until this VM departs
-                term = d == 0u;
-                if (!term) dmin = min(dmin, d);
+        if constexpr (sizeof(PT) == 2) {
+            // four slots per thread, a 32-slot chunk = 8 neighbouring threads (see TEAM_FILTER); padding slots read as waiting here:
+            // neither running nor empty (they must not receive admissions)
+            const uint2* pl4 = reinterpret_cast<const uint2*>(place);
+            const uint2* rm4 = reinterpret_cast<const uint2*>(rem);
+            const int nq = e.L->Vp >> 2;
+            for (int q0 = (tid & ~31); q0 < nq; q0 += nth) {
+                const int q = q0 + (tid & 31);
+                unsigned wt = 0, we = 0;
+                if (q < nq) {
+                    const uint2 a = pl4[q], r = rm4[q];
+                    const unsigned pl[4] = {a.x & 0xffffu, a.x >> 16, a.y & 0xffffu, a.y >> 16};
+                    const unsigned rr[4] = {r.x & 0xffffu, r.x >> 16, r.y & 0xffffu, r.y >> 16};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const bool running = pl[j] < (unsigned)P;
+                        const uint32_t d = (rr[j] - now16) & 0xffffu;              // steps until this VM departs
+                        const bool term = running && d == 0u;
+                        if (running && !term) dmin = min(dmin, d);
+                        wt |= term ? (1u << j) : 0u;
+                        we |= (pl[j] == (unsigned)(P + 1) && 4 * q + j < V) ? (1u << j) : 0u;
+                    }
+                    wt <<= 4 * (q & 7); we <<= 4 * (q & 7);
+                }
+                wt |= __shfl_xor_sync(FULL, wt, 1); wt |= __shfl_xor_sync(FULL, wt, 2); wt |= __shfl_xor_sync(FULL, wt, 4);
+                we |= __shfl_xor_sync(FULL, we, 1); we |= __shfl_xor_sync(FULL, we, 2); we |= __shfl_xor_sync(FULL, we, 4);
+                if ((q & 7) == 0 && q < nq) { tmk[q >> 3] = wt; emk[q >> 3] = we; }
             }
-            const unsigned m = __ballot_sync(FULL, term), em = __ballot_sync(FULL, pl == P + 1);
-            if ((tid & 31) == 0) { tmk[v0 >> 5] = m; emk[v0 >> 5] = em; }
+        } else {
+            for (int v0 = (tid & ~31); v0 < V; v0 += nth) {
+                const int v = v0 + (tid & 31);
+                const int pl = v < V ? (int)place[v] : P;
+                bool term = false;
+                if (pl < P) {
+                    const uint32_t d = ((uint32_t)rem[v] - now16) & 0xffffu;       // steps until this VM departs
+                    term = d == 0u;
+                    if (!term) dmin = min(dmin, d);
+                }
+                const unsigned m = __ballot_sync(FULL, term), em = __ballot_sync(FULL, pl == P + 1);
+                if ((tid & 31) == 0) { tmk[v0 >> 5] = m; emk[v0 >> 5] = em; }
+            }
         }
         dmin = __reduce_min_sync(FULL, dmin);
         if ((tid & 31) == 0) atomicMin(reinterpret_cast<unsigned*>(const_cast<int*>(e.ctl())) + 2, dmin);
