@@ -326,7 +326,9 @@ def test_invalid_action_mask_matches_oracle():
 
 @pytest.mark.parametrize("shape,n_envs,steps,agent", [("s100", 6, 900, "firstfit"), ("s10", 12, 390, "firstfit"),
                                                        ("wide", 3, 300, "firstfit"), ("s100", 4, 4200, "bestfit"),
-                                                       ("s10wr", 12, 390, "firstfit"), ("s10wr", 12, 390, "bestfit")])
+                                                       ("s10wr", 12, 390, "firstfit"), ("s10wr", 12, 390, "bestfit"),
+                                                       # reward wr + Philox + stable ties on u16 placements: the specialised team-mode kernels
+                                                       ("big", 3, 300, "bestfit"), ("big", 3, 300, "firstfit"), ("s1000", 2, 1100, "bestfit")])
 def test_philox_mode_matches_oracle_on_same_draws(shape, n_envs, steps, agent):
     """rng='philox': the kernel's in-flight Philox/inverse-CDF draws == the host restatement of the same
     counters fed to the oracle env as a pre-sampled trace (arrivals, sizes, service lengths, cursors)."""

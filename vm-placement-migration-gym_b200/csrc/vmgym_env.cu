@@ -163,6 +163,7 @@ static int launch_step(StepParams& sp, cudaStream_t st)
         const long long need = (n_sched + sm_count() - 1) / sm_count();
         if (per_sm > need) per_sm = need;
         if (per_sm < 1) per_sm = 1;
+        // (the specialised team kernels below are compiled under the same launch bounds: at most the generic kernel's registers)
         static int team_regs = 0;
         if (team_regs == 0) {
             cudaFuncAttributes fa;
@@ -184,7 +185,21 @@ static int launch_step(StepParams& sp, cudaStream_t st)
     const size_t smem = (size_t)L.sm_tables + (size_t)(team ? 1 : w) * (db ? wstride_db : L.sm_stride);
     if (smem > 227 * 1024) return fail(VMGYM_EUNSUPPORTED, "env record does not fit in shared memory (pms/vms too large)");
     void (*kern)(const StepParams) = pick_db<PT, 0, 0, -1>(db);
-    if (team) kern = step_kernel<PT, 0, 0, -1, (sizeof(PT) == 2)>;
+    if (team) {
+        kern = step_kernel<PT, 0, 0, -1, (sizeof(PT) == 2)>;
+        // the benchmark configurations of the large shapes: fused heuristic agent, reward wr, stable ties, Philox arrivals, no per-VM
+        // statistics — a third of the generic kernel's code (agent / reward / trace mode compiled in)
+        static const bool specialise_team = getenv("VMGYM_NO_SPECIALIZE") == nullptr;
+        if constexpr (sizeof(PT) == 2) {
+            if (specialise_team && sp.reward_fn == VMGYM_REWARD_WR && sp.tiebreak == VMGYM_TIE_STABLE && !sp.out.d_vm_slots && !sp.out.d_next_action &&
+                sp.tr.mode == VMGYM_TRACE_PHILOX) {
+                if (sp.agent == VMGYM_AGENT_BESTFIT)
+                    kern = step_kernel<PT, 0, 0, make_spec(VMGYM_AGENT_BESTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX), true>;
+                else if (sp.agent == VMGYM_AGENT_FIRSTFIT)
+                    kern = step_kernel<PT, 0, 0, make_spec(VMGYM_AGENT_FIRSTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX), true>;
+            }
+        }
+    }
     static const bool specialise = getenv("VMGYM_NO_SPECIALIZE") == nullptr;               // A/B switch for experiments
     if constexpr (sizeof(PT) == 1) {
     if (specialise && L.P == 100 && L.V == 300) {                                           // config/100.yml
