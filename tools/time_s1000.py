@@ -1,6 +1,6 @@
 """Fused best-fit step at the 1000-PM shape: us per step by CUDA events, one launch per step and as a rotation launch
 (NB phase-staggered batches of E envs, K batch steps per launch).
-    python tools/time_s1000.py [envs] [steps] [batches] [K]"""
+    python tools/time_s1000.py [envs] [steps] [batches] [K] [team warps]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "vm-placement-migration-gym_b200"), ROOT]
@@ -11,6 +11,9 @@ E = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 NB = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 K = int(sys.argv[4]) if len(sys.argv) > 4 else 20
+if len(sys.argv) > 5:
+    from vmgym import _native as nv
+    nv.lib().vmgym_set_tuning(int(sys.argv[5]), 7)
 cfg = dict(load_env_cfg(), pms=1000, vms=3000, sequence="highuniform", arrival_rate=1.6)
 quiet = dict(want_obs=False, want_action=False, want_valid=False)
 v = VecVmEnv(Config(**cfg), E, rng="philox")

@@ -193,7 +193,9 @@ static int launch_step(StepParams& sp, cudaStream_t st)
         if constexpr (sizeof(PT) == 2) {
             if (specialise_team && sp.reward_fn == VMGYM_REWARD_WR && sp.tiebreak == VMGYM_TIE_STABLE && !sp.out.d_vm_slots && !sp.out.d_next_action &&
                 sp.tr.mode == VMGYM_TRACE_PHILOX) {
-                if (sp.agent == VMGYM_AGENT_BESTFIT)
+                if (sp.agent == VMGYM_AGENT_BESTFIT && L.P == 1000 && L.V == 3000)         // BASELINE config 5's shape
+                    kern = step_kernel<PT, 1000, 3000, make_spec(VMGYM_AGENT_BESTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX), true>;
+                else if (sp.agent == VMGYM_AGENT_BESTFIT)
                     kern = step_kernel<PT, 0, 0, make_spec(VMGYM_AGENT_BESTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX), true>;
                 else if (sp.agent == VMGYM_AGENT_FIRSTFIT)
                     kern = step_kernel<PT, 0, 0, make_spec(VMGYM_AGENT_FIRSTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX), true>;
