@@ -311,7 +311,7 @@ def gpu_arm(args):
     s1000 = None
     if "s1000" in extras_on:
         kw1000 = dict(cfg, pms=1000, vms=3000, sequence="highuniform", arrival_rate=1000 / 0.625 / cfg["service_length"])
-        E1, NB1, K1 = 1024, 4, 20
+        E1, NB1, K1 = 1024, 4, 50
         # the headline's protocol at this shape: NB1 phase-staggered batches of E1 envs (4 x 37 MB of records > 126 MB L2), K1 batch
         # steps per rotation launch (team-mode kernel, records shared out over the CTAs), median of 7 replays
         v1 = VecVmEnv(Config(**kw1000), NB1 * E1, device=dev, rng="philox",

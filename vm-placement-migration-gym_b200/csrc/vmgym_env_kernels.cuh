@@ -520,6 +520,7 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
         PROF_SPAN_END(13, -1);
     }
     bool dirty = false;                                  // proposals since the table was built (it over-states the free capacity)
+    bool refiltered = false;                             // team mode: the chunk marks were refreshed inside visit()
 
     // slots are visited in groups: 4 per lane (128 per pass) for byte placements, 1 per lane otherwise
     constexpr int SPL = sizeof(PT) == 1 ? 4 : 1;
@@ -635,6 +636,14 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
                     PROF_SPAN_END(13, -1);
                     dirty = false;
                     placed_any = true;                 // the not-yet-visited lanes' candidates are re-tested against the fresh table
+                    if constexpr (TM && SPL == 1) {
+                        // The chunk marks date from the start of act(): every marked chunk would still get a (fruitless) visit although
+                        // the capacity that made its VMs candidates is gone (at saturation ~20 visits per step for the one or two PMs a
+                        // departure freed).  The fresh table is exact, so the team marks the chunks again (four slots per thread: cheaper
+                        // than the visits it saves).
+                        team_run(e, TEAM_FILTER, nth);
+                        refiltered = true;
+                    }
                     if (bits) {
                         unsigned nb;
                         if (SPL == 4) {
@@ -678,6 +687,11 @@ __device__ __forceinline__ int agent_act(const Env<PT>& e, const AgentView<PT>& 
                 PROF_SPAN_BEGIN();
                 visit(32 * c);
                 PROF_SPAN_END(15, 12);
+                if (refiltered) {
+                    // marks only ever lose bits (capacities shrink during act()); later groups of 32 chunks read the fresh marks anyway
+                    nz &= __ballot_sync(FULL, cb0 + lane < n_chunks && cm[cb0 + lane] != 0u);
+                    refiltered = false;
+                }
             }
         }
     } else {
