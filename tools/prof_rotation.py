@@ -1,5 +1,5 @@
 """ncu target: the benchmark's rotation launch (vmgym_agent_step_rotation) in isolation.
-    python tools/prof_rotation.py [envs_per_batch] [batches] [K] [replays]
+    python tools/prof_rotation.py [envs_per_batch] [batches] [K] [replays] [s100|s1000]
 Launch order of step_kernel: `batches` warm-up launches, one full untimed rotation, then `replays` launches of K batch steps
 (ncu: -k regex:step_kernel -s <batches + 1> -c <replays>)."""
 import os
@@ -18,6 +18,8 @@ NB = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 K = int(sys.argv[3]) if len(sys.argv) > 3 else 20
 R = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 cfg = load_env_cfg()
+if len(sys.argv) > 5 and sys.argv[5] == "s1000":      # BASELINE config 5's shape: team-mode kernel
+    cfg = dict(cfg, pms=1000, vms=3000, sequence="highuniform", arrival_rate=1.6)
 seeds = np.concatenate([cfg["seed"] + b * E + np.arange(E, dtype=np.int64) for b in range(NB)])
 vec = VecVmEnv(Config(**cfg), NB * E, rng="philox", seeds=seeds)
 for b in range(NB):
