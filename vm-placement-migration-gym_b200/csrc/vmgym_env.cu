@@ -174,6 +174,7 @@ static int launch_step(StepParams& sp, cudaStream_t st)
         w = w < 1 ? 1 : (w > 8 ? 8 : w);                                                    // compiled for <= 256 threads
     } else {
         w = pick_warps(n_sched, L.sm_stride, L.sm_tables);
+        if (L.P == 10 && L.V == 30 && w > 8) w = 8;        // the 10-PM kernels are compiled for <= 256 threads: 64 registers, 32 resident warps per SM (72: 28 warps; 1.59 -> 1.68 G env-steps/s; 56 registers: 1.60)
     }
     // double-buffered records once a warp steps several envs per launch (more envs than ~1.4 x the resident warps) — for
     // small records only: measured +7.5 % at the 10-PM shape (2^20 envs), but -6 % at 100 PMs, where the second 3.4 KB

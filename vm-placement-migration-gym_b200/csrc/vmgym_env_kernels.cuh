@@ -1418,7 +1418,7 @@ constexpr int make_spec(int agent, int tiebreak, int reward, int mode, int post_
 // resident CTAs): the next env's record is fetched (bulk-async, second buffer + second mbarrier) while the current one is
 // stepped, and the write-back of the previous one drains in the background.  Needs bulk loads and stores (use_bulk bits 0, 1).
 template <typename PT, int PC, int VC, int SPEC, bool TM = false, bool DB = false>
-__global__ void __launch_bounds__(TM ? 256 : 896, TM ? 3 : 1) step_kernel(const __grid_constant__ StepParams p)
+__global__ void __launch_bounds__(TM ? 256 : (PC == 10 ? 256 : 896), TM ? 3 : (PC == 10 ? 4 : 1)) step_kernel(const __grid_constant__ StepParams p)
 {
     constexpr int REWARD_CT = SPEC >= 0 ? ((SPEC >> 8) & 0xf) : 0;
     constexpr int MODE_CT = SPEC >= 0 ? ((SPEC >> 12) & 0xf) : -1;
