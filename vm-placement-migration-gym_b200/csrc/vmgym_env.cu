@@ -131,11 +131,33 @@ static int pick_warps(long long n_envs, int smem_per_warp, int smem_fixed)
     return w;
 }
 
+// warp-per-env kernel by record buffering (db) and launch kind (rot); the specialised fused-agent kernels have the launch kind
+// compiled in (external-action kernels are never rotation launches; generic kernels test rot_batches)
 template <typename PT, int PC, int VC, int SPEC>
-static void (*pick_db(bool db))(const StepParams)
+static void (*pick_db(bool db, bool rot))(const StepParams)
 {
-    if (db) return step_kernel<PT, PC, VC, SPEC, false, true>;
-    return step_kernel<PT, PC, VC, SPEC, false, false>;
+    if constexpr (SPEC >= 0 && (SPEC & 0xf) != VMGYM_AGENT_NONE) {
+        if (rot) {
+            if (db) return step_kernel<PT, PC, VC, SPEC, false, true, 1>;
+            return step_kernel<PT, PC, VC, SPEC, false, false, 1>;
+        }
+        if (db) return step_kernel<PT, PC, VC, SPEC, false, true, 0>;
+        return step_kernel<PT, PC, VC, SPEC, false, false, 0>;
+    } else if constexpr (SPEC >= 0) {
+        if (db) return step_kernel<PT, PC, VC, SPEC, false, true, 0>;
+        return step_kernel<PT, PC, VC, SPEC, false, false, 0>;
+    } else {
+        if (db) return step_kernel<PT, PC, VC, SPEC, false, true>;
+        return step_kernel<PT, PC, VC, SPEC, false, false>;
+    }
+}
+
+// specialised team-mode kernel by launch kind
+template <typename PT, int PC, int VC, int SPEC>
+static void (*pick_team(bool rot))(const StepParams)
+{
+    if (rot) return step_kernel<PT, PC, VC, SPEC, true, false, 1>;
+    return step_kernel<PT, PC, VC, SPEC, true, false, 0>;
 }
 
 template <typename PT>
@@ -185,49 +207,53 @@ static int launch_step(StepParams& sp, cudaStream_t st)
                     n_sched * (sp.rot_batches > 0 ? sp.rot_steps : 1) * 10 > (long long)sm_count() * 7 * w * 14 && (size_t)L.sm_tables + (size_t)w * wstride_db <= 227 * 1024;
     const size_t smem = (size_t)L.sm_tables + (size_t)(team ? 1 : w) * (db ? wstride_db : L.sm_stride);
     if (smem > 227 * 1024) return fail(VMGYM_EUNSUPPORTED, "env record does not fit in shared memory (pms/vms too large)");
-    void (*kern)(const StepParams) = pick_db<PT, 0, 0, -1>(db);
+    const bool rot = sp.rot_batches > 0;
+    void (*kern)(const StepParams) = pick_db<PT, 0, 0, -1>(db, rot);
     if (team) {
         kern = step_kernel<PT, 0, 0, -1, (sizeof(PT) == 2)>;
         // the benchmark configurations of the large shapes: fused heuristic agent, reward wr, stable ties, Philox arrivals, no per-VM
         // statistics — a third of the generic kernel's code (agent / reward / trace mode compiled in)
-        static const bool specialise_team = getenv("VMGYM_NO_SPECIALIZE") == nullptr;
+        static const bool specialise_team_ok = getenv("VMGYM_NO_SPECIALIZE") == nullptr;
+        // (the specialised kernels take the small arrival table and the service brackets for granted)
+        const bool specialise_team = specialise_team_ok && sp.tr.arrival_cdf_len <= ARR_CDF_SMEM && sp.tr.d_service_bracket != nullptr;
         if constexpr (sizeof(PT) == 2) {
             if (specialise_team && sp.reward_fn == VMGYM_REWARD_WR && sp.tiebreak == VMGYM_TIE_STABLE && !sp.out.d_vm_slots && !sp.out.d_next_action &&
                 sp.tr.mode == VMGYM_TRACE_PHILOX) {
                 if (sp.agent == VMGYM_AGENT_BESTFIT && L.P == 1000 && L.V == 3000)         // BASELINE config 5's shape
-                    kern = step_kernel<PT, 1000, 3000, make_spec(VMGYM_AGENT_BESTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX), true>;
+                    kern = pick_team<PT, 1000, 3000, make_spec(VMGYM_AGENT_BESTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>(rot);
                 else if (sp.agent == VMGYM_AGENT_BESTFIT)
-                    kern = step_kernel<PT, 0, 0, make_spec(VMGYM_AGENT_BESTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX), true>;
+                    kern = pick_team<PT, 0, 0, make_spec(VMGYM_AGENT_BESTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>(rot);
                 else if (sp.agent == VMGYM_AGENT_FIRSTFIT)
-                    kern = step_kernel<PT, 0, 0, make_spec(VMGYM_AGENT_FIRSTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX), true>;
+                    kern = pick_team<PT, 0, 0, make_spec(VMGYM_AGENT_FIRSTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>(rot);
             }
         }
     }
+    // (the specialised kernels are all Philox kernels and take the small arrival table and the service brackets for granted: philox_fast)
     static const bool specialise = getenv("VMGYM_NO_SPECIALIZE") == nullptr;               // A/B switch for experiments
+    const bool philox_fast = sp.tr.mode == VMGYM_TRACE_PHILOX && sp.tr.arrival_cdf_len <= ARR_CDF_SMEM && sp.tr.d_service_bracket != nullptr;
     if constexpr (sizeof(PT) == 1) {
     if (specialise && L.P == 100 && L.V == 300) {                                           // config/100.yml
-        kern = pick_db<PT, 100, 300, -1>(db);
+        kern = pick_db<PT, 100, 300, -1>(db, rot);
         // the benchmark configurations of this shape: fused heuristic agents / external actions, reward wr, stable ties
-        if (sp.reward_fn == VMGYM_REWARD_WR && sp.agent == VMGYM_AGENT_NONE && sp.tr.mode == VMGYM_TRACE_PHILOX && !sp.out.d_vm_slots &&
+        if (sp.reward_fn == VMGYM_REWARD_WR && sp.agent == VMGYM_AGENT_NONE && philox_fast && !sp.out.d_vm_slots &&
             sp.out.d_next_action && sp.out.next_agent == VMGYM_AGENT_BESTFIT && sp.out.next_tiebreak == VMGYM_TIE_STABLE) {
             // HostVecEnv's step: external actions, then best-fit's act on the new state
-            kern = pick_db<PT, 100, 300, make_spec(VMGYM_AGENT_NONE, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX, VMGYM_AGENT_BESTFIT)>(db);
+            kern = pick_db<PT, 100, 300, make_spec(VMGYM_AGENT_NONE, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX, VMGYM_AGENT_BESTFIT)>(db, rot);
         } else if (sp.reward_fn == VMGYM_REWARD_WR && sp.tiebreak == VMGYM_TIE_STABLE && !sp.out.d_vm_slots && !sp.out.d_next_action) {   // per-VM stats, other next-action outputs: generic kernel
-            const int mode = sp.tr.mode;
-            if (sp.agent == VMGYM_AGENT_BESTFIT && mode == VMGYM_TRACE_PHILOX)
-                kern = pick_db<PT, 100, 300, make_spec(VMGYM_AGENT_BESTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>(db);
-            else if (sp.agent == VMGYM_AGENT_FIRSTFIT && mode == VMGYM_TRACE_PHILOX)
-                kern = pick_db<PT, 100, 300, make_spec(VMGYM_AGENT_FIRSTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>(db);
-            else if (sp.agent == VMGYM_AGENT_NONE && mode == VMGYM_TRACE_PHILOX)
-                kern = pick_db<PT, 100, 300, make_spec(VMGYM_AGENT_NONE, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>(db);
+            if (sp.agent == VMGYM_AGENT_BESTFIT && philox_fast)
+                kern = pick_db<PT, 100, 300, make_spec(VMGYM_AGENT_BESTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>(db, rot);
+            else if (sp.agent == VMGYM_AGENT_FIRSTFIT && philox_fast)
+                kern = pick_db<PT, 100, 300, make_spec(VMGYM_AGENT_FIRSTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>(db, rot);
+            else if (sp.agent == VMGYM_AGENT_NONE && philox_fast)
+                kern = pick_db<PT, 100, 300, make_spec(VMGYM_AGENT_NONE, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>(db, rot);
         }
     } else if (specialise && L.P == 10 && L.V == 30) {
-        kern = pick_db<PT, 10, 30, -1>(db);                                                // config/10.yml
-        if (sp.reward_fn == VMGYM_REWARD_WR && sp.tiebreak == VMGYM_TIE_STABLE && !sp.out.d_vm_slots && !sp.out.d_next_action && sp.tr.mode == VMGYM_TRACE_PHILOX) {
+        kern = pick_db<PT, 10, 30, -1>(db, rot);                                                // config/10.yml
+        if (sp.reward_fn == VMGYM_REWARD_WR && sp.tiebreak == VMGYM_TIE_STABLE && !sp.out.d_vm_slots && !sp.out.d_next_action && philox_fast) {
             if (sp.agent == VMGYM_AGENT_FIRSTFIT)                                          // BASELINE configs[0]: first-fit evaluation
-                kern = pick_db<PT, 10, 30, make_spec(VMGYM_AGENT_FIRSTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>(db);
+                kern = pick_db<PT, 10, 30, make_spec(VMGYM_AGENT_FIRSTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>(db, rot);
             else if (sp.agent == VMGYM_AGENT_BESTFIT)
-                kern = pick_db<PT, 10, 30, make_spec(VMGYM_AGENT_BESTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>(db);
+                kern = pick_db<PT, 10, 30, make_spec(VMGYM_AGENT_BESTFIT, 0, VMGYM_REWARD_WR, VMGYM_TRACE_PHILOX)>(db, rot);
         }
     }
     }
@@ -271,6 +297,7 @@ static int fill_params(StepParams* sp, const vmgym_config* cfg, void* d_state, i
     if (rc) return rc;
     if (n_envs == 0) return VMGYM_OK;     // callers test n_envs == 0 again before launching
     if (!d_state || n_envs < 0) return fail(VMGYM_EINVAL, "null state / negative n_envs");
+    if (n_envs > 0x7fffffffLL) return fail(VMGYM_EINVAL, "more than 2^31 - 1 envs in one launch");   // the step kernel's record addresses are 32 x 32-bit products
     if (!trace) return fail(VMGYM_EINVAL, "null trace");
     if (trace->mode == VMGYM_TRACE_PRESAMPLED) {
         if (!trace->d_arrivals || !trace->d_admissions) return fail(VMGYM_EINVAL, "pre-sampled trace arrays missing");

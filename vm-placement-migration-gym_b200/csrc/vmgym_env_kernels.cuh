@@ -1417,7 +1417,9 @@ constexpr int make_spec(int agent, int tiebreak, int reward, int mode, int post_
 // DB: double-buffered records for launches in which a warp steps several envs one after the other (grid capped at the
 // resident CTAs): the next env's record is fetched (bulk-async, second buffer + second mbarrier) while the current one is
 // stepped, and the write-back of the previous one drains in the background.  Needs bulk loads and stores (use_bulk bits 0, 1).
-template <typename PT, int PC, int VC, int SPEC, bool TM = false, bool DB = false>
+// ROT_CT: rotation launch known at compile time (1 yes, 0 no, -1 = look at rot_batches): the specialised kernels drop the other
+// loop nest's index arithmetic from the per-record scaffolding.
+template <typename PT, int PC, int VC, int SPEC, bool TM = false, bool DB = false, int ROT_CT = -1>
 __global__ void __launch_bounds__(TM ? 256 : (PC == 10 ? 256 : 896), TM ? 3 : (PC == 10 ? 4 : 1)) step_kernel(const __grid_constant__ StepParams p)
 {
     constexpr int REWARD_CT = SPEC >= 0 ? ((SPEC >> 8) & 0xf) : 0;
@@ -1443,7 +1445,7 @@ __global__ void __launch_bounds__(TM ? 256 : (PC == 10 ? 256 : 896), TM ? 3 : (P
     const long long env0 = (long long)blockIdx.x * wpc + warp;
     // the warp's work list.  Plain launches walk env0, env0 + stride, ...; a rotation launch takes the rot_steps batch steps of
     // each env index it owns (batch rot_first, rot_first + 1, ... modulo rot_batches) before moving on to the next index
-    const bool ROT = p.rot_batches > 0;
+    const bool ROT = ROT_CT >= 0 ? (ROT_CT != 0) : (p.rot_batches > 0);
     const long long n_idx = ROT ? p.rot_envs : p.n_envs;
     const int per_idx = ROT ? p.rot_steps : 1;
     // Team-mode rotation ("balanced", BAL): a CTA steps ONE env at a time and a batch rarely holds a multiple of the resident
@@ -1476,8 +1478,10 @@ __global__ void __launch_bounds__(TM ? 256 : (PC == 10 ? 256 : 896), TM ? 3 : (P
         }
     }
     const bool philox = (MODE_CT >= 0 ? MODE_CT : p.tr.mode) == VMGYM_TRACE_PHILOX;
-    const bool arr_in_smem = philox && p.tr.arrival_cdf_len <= ARR_CDF_SMEM;
-    const bool have_bracket = philox && p.tr.d_service_bracket != nullptr;
+    // the specialised Philox kernels are only launched with a small arrival table and service brackets (launch_step checks)
+    constexpr bool TABLES_CT = SPEC >= 0 && MODE_CT == VMGYM_TRACE_PHILOX;
+    const bool arr_in_smem = TABLES_CT || (philox && p.tr.arrival_cdf_len <= ARR_CDF_SMEM);
+    const bool have_bracket = TABLES_CT || (philox && p.tr.d_service_bracket != nullptr);
     {
         // CTA-wide tables: every global load is issued before the first shared-memory store so that the round trips
         // overlap each other (and the record's bulk copy) instead of queueing behind one another
@@ -1534,7 +1538,10 @@ __global__ void __launch_bounds__(TM ? 256 : (PC == 10 ? 256 : 896), TM ? 3 : (P
         const int rb = BAL ? rb_o : rbi;
         const long long env = ROT ? (long long)rb * p.rot_envs + idx : idx;
         const bool first_item = BAL ? (o == 0 && i == i0) : (idx == env0 && rk == 0);
-        unsigned char* grec = p.state + env * (long long)L.rec_bytes;
+        // 32 x 32 -> 64-bit products for the per-record addresses (launches hold < 2^31 envs, fill_params): one IMAD.WIDE each
+        // instead of a 64 x 64 multiply chain per output pointer
+        const unsigned env_u = (unsigned)env;
+        unsigned char* grec = p.state + (unsigned long long)env_u * (unsigned)L.rec_bytes;
 #ifdef VMGYM_PROF
         const long long _pload = clock64();
 #endif
@@ -1545,7 +1552,7 @@ __global__ void __launch_bounds__(TM ? 256 : (PC == 10 ? 256 : 896), TM ? 3 : (P
         // warps at this record size.)  Measured: 6.54 -> 6.46 us per 4096-env step.
         if (!DB && ROT && !BAL && lane == 0 && rk + 1 < per_idx && (p.use_bulk & 64) == 0) {
             const long long nxt = (long long)((rb + 1 == p.rot_batches) ? 0 : rb + 1) * p.rot_envs + idx;
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.state + nxt * (long long)L.rec_bytes), "r"((uint32_t)L.rec_bytes) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.state + (unsigned long long)(unsigned)nxt * (unsigned)L.rec_bytes), "r"((uint32_t)L.rec_bytes) : "memory");
         }
         if (BAL && lane == 0 && (p.use_bulk & 64) == 0) {
             // balanced team rotation: the CTA's next record = its next one in this batch, else its first one in the next batch
@@ -1556,7 +1563,7 @@ __global__ void __launch_bounds__(TM ? 256 : (PC == 10 ? 256 : 896), TM ? 3 : (P
                 nxt = (long long)nb * p.rot_envs + bal_idx0(nb);
             }
             if (nxt >= 0)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.state + nxt * (long long)L.rec_bytes), "r"((uint32_t)L.rec_bytes) : "memory");
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.state + (unsigned long long)(unsigned)nxt * (unsigned)L.rec_bytes), "r"((uint32_t)L.rec_bytes) : "memory");
         }
         if (DB) {
             unsigned char* other = cur ? base : base + L.sm_stride;
@@ -1568,7 +1575,7 @@ __global__ void __launch_bounds__(TM ? 256 : (PC == 10 ? 256 : 896), TM ? 3 : (P
             if (lane == 0 && (more_rot || idx + stride < n_idx)) {
                 bulk_wait_read0();            // the other buffer's write-back (previous env) has left shared memory
                 mbar_arrive_expect_tx(bar + (cur ^ 1), (uint32_t)L.rec_bytes);
-                bulk_g2s(other, p.state + nxt * (long long)L.rec_bytes, (uint32_t)L.rec_bytes, bar + (cur ^ 1));
+                bulk_g2s(other, p.state + (unsigned long long)(unsigned)nxt * (unsigned)L.rec_bytes, (uint32_t)L.rec_bytes, bar + (cur ^ 1));
             }
             if (cur) { mbar_wait(bar + 1, phase1); phase1 ^= 1; }
             else { mbar_wait(bar, phase); phase ^= 1; }
@@ -1587,7 +1594,7 @@ __global__ void __launch_bounds__(TM ? 256 : (PC == 10 ? 256 : 896), TM ? 3 : (P
         if (threadIdx.x == 0) atomicAdd(&g_prof[0], (unsigned long long)(clock64() - _pload));      // 0: record load wait
 #endif
         PROF_T0();
-        uint8_t* valid_g = p.out.d_valid ? p.out.d_valid + env * (long long)cV : nullptr;
+        uint8_t* valid_g = p.out.d_valid ? p.out.d_valid + (unsigned long long)env_u * (unsigned)cV : nullptr;
         StepResult res;
         res.reward = 0.0; res.terminated = 0; res.rejected = 0; res.waiting = 0; res.arrived = 0; res.changed = 0;
         double* st_acc = reinterpret_cast<double*>(base + L.sm_stats);     // per-launch stats sums (lane 0)
@@ -1624,7 +1631,7 @@ __global__ void __launch_bounds__(TM ? 256 : (PC == 10 ? 256 : 896), TM ? 3 : (P
                     PROF_ADD(2);                                                                         // 2: agent act
                     evaluated = true;
                     if (p.out.d_action) {        // the action vector: proposals, else the current placement (firstfit.py:29)
-                        PT* ao = reinterpret_cast<PT*>(p.out.d_action) + env * (long long)cV;
+                        PT* ao = reinterpret_cast<PT*>(p.out.d_action) + (unsigned long long)env_u * (unsigned)cV;
                         for (int v = lane; v < cV; v += 32)
                             ao[v] = ((e.prop()[v >> 5] >> (v & 31)) & 1u) ? (PT)e.act()[v] : e.place()[v];
                     }
@@ -1633,7 +1640,7 @@ __global__ void __launch_bounds__(TM ? 256 : (PC == 10 ? 256 : 896), TM ? 3 : (P
             } else {
                 // external actions: stage the row and mark the slots whose action differs from their placement
                 const int adt = p.action_dtype;
-                const unsigned char* arow = reinterpret_cast<const unsigned char*>(p.action) + env * (long long)cV * dtype_bytes(adt);
+                const unsigned char* arow = reinterpret_cast<const unsigned char*>(p.action) + (unsigned long long)env_u * (unsigned)(cV * dtype_bytes(adt));
                 unsigned any = 0;
                 for (int c0 = 0; c0 < cV; c0 += 32) {
                     const int v = c0 + lane;
@@ -1678,7 +1685,7 @@ __global__ void __launch_bounds__(TM ? 256 : (PC == 10 ? 256 : 896), TM ? 3 : (P
                 AgentView<PT> av;
                 av.place = e.place(); av.cc = e.cpuc(); av.mc = e.memc(); av.c32 = nullptr; av.m32 = nullptr; av.sz32 = sz32;
                 agent_act<PT, TM>(e, av, post_agent, post_tie, true, nth);
-                PT* ao = reinterpret_cast<PT*>(p.out.d_next_action) + env * (long long)cV;
+                PT* ao = reinterpret_cast<PT*>(p.out.d_next_action) + (unsigned long long)env_u * (unsigned)cV;
                 for (int v = lane; v < cV; v += 32)
                     ao[v] = ((e.prop()[v >> 5] >> (v & 31)) & 1u) ? (PT)e.act()[v] : e.place()[v];
                 __syncwarp();
@@ -1694,8 +1701,8 @@ __global__ void __launch_bounds__(TM ? 256 : (PC == 10 ? 256 : 896), TM ? 3 : (P
             const bool mirrored = MIRROR_OK && p.out.d_obs_mirror != nullptr;
             const bool persistent = p.out.obs_persistent != 0 || mirrored;
             if (!persistent || obs_stale) {
-                float* orow = p.out.d_obs + env * (long long)cD;
-                if (mirrored) write_obs_mirrored(e, orow, p.out.d_obs_mirror + env * (long long)cD);
+                float* orow = p.out.d_obs + (unsigned long long)env_u * (unsigned)cD;
+                if (mirrored) write_obs_mirrored(e, orow, p.out.d_obs_mirror + (unsigned long long)env_u * (unsigned)cD);
                 else if (TM) {
                     if (lane == 0) {
                         e.ctl()[2] = (int)(unsigned)((unsigned long long)orow & 0xffffffffull);
@@ -1709,10 +1716,10 @@ __global__ void __launch_bounds__(TM ? 256 : (PC == 10 ? 256 : 896), TM ? 3 : (P
         if (lane == 0) {
             e.sc()->status = (e.sc()->status & STATUS_EXHAUSTED) | (obs_stale ? STATUS_OBS_STALE : 0u) |
                              (quiet ? (STATUS_QUIET | (quiet_key << STATUS_KEY_SHIFT) | ((uint32_t)quiet_rejected << 16)) : 0u);
-            if (p.out.d_reward) p.out.d_reward[env] = res.reward;
-            if (p.out.d_terminated) p.out.d_terminated[env] = (uint8_t)res.terminated;
+            if (p.out.d_reward) p.out.d_reward[env_u] = res.reward;
+            if (p.out.d_terminated) p.out.d_terminated[env_u] = (uint8_t)res.terminated;
             if (p.out.d_stats) {
-                double* st = p.out.d_stats + env * VMGYM_STATS;
+                double* st = p.out.d_stats + (unsigned long long)env_u * (unsigned)VMGYM_STATS;
                 for (int k = 0; k < VMGYM_STATS; k++) st[k] += st_acc[k];
             }
         }
