@@ -193,8 +193,10 @@ int vmgym_agent_step(const vmgym_config* cfg, void* d_state, int64_t n_envs, con
  * n_batches x envs_per_batch records (batch b = records [b * envs_per_batch, (b + 1) * envs_per_batch)), outputs are sized for
  * all of them, and the launch executes n_batch_steps consecutive "batch steps" — batch step k advances every env of batch
  * (first_batch + k) % n_batches by n_steps steps of the Base.test loop (base.py:71-86).  Equivalent to n_batch_steps calls of
- * vmgym_agent_step on the batches in rotation; a warp owns env index i of every batch, so the grid stays resident and no launch
- * boundary separates the steps.  Results are identical to the per-batch calls (tested). */
+ * vmgym_agent_step on the batches in rotation; a warp owns env index i of every batch (large shapes, pms > 253: a CTA owns the records
+ * r = batch * envs_per_batch + i with r mod grid == its index), so every record is always stepped by the same warp / CTA in program
+ * order, the grid stays resident and no launch boundary separates the steps.  Results are identical to the per-batch calls (tested).
+ * n_batches * envs_per_batch must be < 2^31. */
 int vmgym_agent_step_rotation(const vmgym_config* cfg, void* d_state, int64_t envs_per_batch, int32_t n_batches, int32_t first_batch,
                               int32_t n_batch_steps, const vmgym_trace* trace, int agent, int tiebreak, int n_steps,
                               const vmgym_outputs* out, void* stream);
