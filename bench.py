@@ -172,15 +172,16 @@ def gpu_arm(args):
     if sampler:
         sampler.start()
         time.sleep(0.3)
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(R)]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(R)]
+    # R + 1 boundary events: replay r is timed from boundary r to boundary r + 1 (nothing between two replays is left out of the
+    # timed spans, and only one event record sits between consecutive launches)
+    evb = [torch.cuda.Event(enable_timing=True) for _ in range(R + 1)]
     barrier()
+    evb[0].record()
     for r in range(R):
-        ev0[r].record()
         nxt = vec.agent_step_rotation("bestfit", E, K, first_batch=nxt)
-        ev1[r].record()
+        evb[r + 1].record()
     barrier()
-    replay_ms = np.array([a_.elapsed_time(b_) for a_, b_ in zip(ev0, ev1)], dtype=np.float64)
+    replay_ms = np.array([evb[r].elapsed_time(evb[r + 1]) for r in range(R)], dtype=np.float64)
     total_ms = float(np.median(replay_ms))
 
     # observation rows the step kernel actually stores: a row is re-stored only when its env's state changed since the row was
@@ -446,7 +447,7 @@ def gpu_arm(args):
                          f"({NB} x {2 * 3456 * E / 1e6:.0f} MB of records touched between two visits of a batch, L2 = 126 MB)",
                    "phase_sampling": f"batch b warmed up to phase b*{PERIOD}/{NB} of the service period (departure waves)",
                    "timing": f"one step = one fused act+step pass over one {E}-env batch; K consecutive steps = ONE persistent launch "
-                             f"(vmgym_agent_step_rotation); {R} replays of the K-step launch, one CUDA-event pair each; "
+                             f"(vmgym_agent_step_rotation); {R} replays of the K-step launch back to back, replay r timed between boundary events r and r + 1; "
                              "ms_per_step = median replay / K",
                    "rng": "philox", "tiebreak": "stable",
                    "obs_written": "into the env's persistent observation buffer; rows of envs whose state did not change are kept, not re-stored",
